@@ -1,0 +1,88 @@
+"""ctypes binding of libdeepbedmap_b200.so (the C ABI declared in include/deepbedmap_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or fails to load, every product entry
+point raises immediately.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdeepbedmap_b200.so")
+
+_P, _L, _I, _F = ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_float
+
+# name -> argument ctypes, in the order of include/deepbedmap_b200.h
+SIGNATURES = {
+    "dbm_version": [],
+    "dbm_debug_set": [_I, _I],
+    "dbm_conv2d_fwd_f32": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dbm_conv2d_bwd_data_f32": [_P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dbm_conv2d_bwd_weight_f32": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dbm_bias_grad_f32": [_P, _L, _P, _I, _I, _I, _P],
+    "dbm_gemm_f32": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dbm_axpby_f32": [_P, _L, _P, _L, _P, _L, _F, _F, _I, _L, _P],
+    "dbm_lrelu_fwd_f32": [_P, _P, _L, _P],
+    "dbm_lrelu_bwd_f32": [_P, _L, _P, _L, _P, _L, _I, _L, _I, _P],
+    "dbm_upsample2_fwd_f32": [_P, _P, _L, _I, _I, _P],
+    "dbm_upsample2_bwd_f32": [_P, _P, _L, _I, _I, _P],
+    "dbm_fill_f32": [_P, _F, _L, _P],
+    "dbm_nchw_to_slab8": [_P, _L, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dbm_slab8_to_nchw": [_P, _I, _I, _P, _L, _I, _I, _I, _I, _P],
+    "dbm_nchw_to_slab4": [_P, _L, _P, _I, _I, _I, _I, _P],
+    "dbm_slab4_to_nchw": [_P, _P, _L, _I, _I, _I, _I, _I, _P],
+    "dbm_pack_conv3x3_weights": [_P, _P, _I, _I, _I, _P],
+    "dbm_conv3x3_umma": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P, _P],
+    "dbm_deform_sample_f32": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "dbm_deform_bwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dbm_bn_lrelu_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
+    "dbm_bn_lrelu_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dbm_ragan_loss_f32": [_P, _P, _I, _F, _F, _F, _P, _P, _P, _P],
+    "dbm_gen_image_loss_f32": [_P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P],
+    "dbm_adam_step_f32": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
+    "dbm_crop_clip_f32": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dbm_place_tile_f32": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+}
+
+_lib: Optional[ctypes.CDLL] = None
+launch_count = 0  # number of library calls that enqueue kernels (bench.py reports it)
+
+
+class DeepBedMapError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library; raises loudly when it is missing (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DeepBedMapError(
+            f"{LIB_PATH} is missing: build it with `python -m deepbedmap_b200.build` "
+            "(nvcc, sm_100a). deepbedmap_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.dbm_last_error.restype = ctypes.c_char_p
+    lib.dbm_last_error.argtypes = []
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    """Invoke a C-ABI entry point; non-zero status -> ValueError (bad arguments, mirroring the
+    reference's shape/type errors) or DeepBedMapError (CUDA failure)."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    launch_count += 1
+    if rc != 0:
+        msg = lib.dbm_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{name}: {msg}")
+        raise DeepBedMapError(f"{name}: {msg}")

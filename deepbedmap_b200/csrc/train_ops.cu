@@ -1,0 +1,358 @@
+// Training-step kernels: batch normalisation, RaGAN / content / topographic / SSIM losses with
+// their gradients, PSNR partial sums and the Chainer-variant Adam update.
+// Reference semantics: srgan_train.py:636-689 (BN + LeakyReLU), :841-1009 (losses),
+// :1043-1048 (Adam); third-party details restated in SURVEY App. B.7, B.9, B.10.
+#include "common.cuh"
+
+namespace dbm {
+
+__device__ __forceinline__ float block_sum(float s, float* red) {
+  for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += red[i];
+  return r;
+}
+
+// ---- BatchNormalization(axis=(0,2,3), eps=1e-5, decay=0.9) -------------------------------------
+// One block per channel. train: batch mean / biased variance (two-pass), running stats updated
+// with the unbiased variance; eval: running stats. Writes mean[c], invstd[c] for apply/backward.
+__global__ void bn_stats_kernel(const float* __restrict__ x, int N, int C, int HW, float eps, float decay, int train,
+                                float* __restrict__ avg_mean, float* __restrict__ avg_var,
+                                float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  if (!train) {
+    if (threadIdx.x == 0) {
+      mean_out[c] = avg_mean[c];
+      invstd_out[c] = rsqrtf(avg_var[c] + eps);
+    }
+    return;
+  }
+  const long m = (long)N * HW;
+  float s = 0.f;
+  for (long i = threadIdx.x; i < m; i += blockDim.x) {
+    const long n = i / HW, r = i - n * HW;
+    s += x[(n * C + c) * HW + r];
+  }
+  const float mean = block_sum(s, red) / (float)m;
+  float q = 0.f;
+  for (long i = threadIdx.x; i < m; i += blockDim.x) {
+    const long n = i / HW, r = i - n * HW;
+    const float d = x[(n * C + c) * HW + r] - mean;
+    q += d * d;
+  }
+  const float var = block_sum(q, red) / (float)m;
+  if (threadIdx.x == 0) {
+    mean_out[c] = mean;
+    invstd_out[c] = 1.0f / sqrtf(var + eps);
+    const float adjust = (float)m / fmaxf((float)m - 1.f, 1.f);
+    avg_mean[c] = decay * avg_mean[c] + (1.f - decay) * mean;
+    avg_var[c] = decay * avg_var[c] + (1.f - decay) * var * adjust;
+  }
+}
+// y = lrelu(gamma * (x - mean) * invstd + beta)
+__global__ void bn_apply_lrelu_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ mean, const float* __restrict__ invstd, int C, int HW,
+                                      long total) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (i / HW) % C;
+    y[i] = lrelu(gamma[c] * (x[i] - mean[c]) * invstd[c] + beta[c]);
+  }
+}
+// Backward of y = lrelu(BN_train(x)): per-channel reductions (dgamma += , dbeta +=) ...
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                     const float* __restrict__ dy, int N, int C, int HW,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const long m = (long)N * HW;
+  const float mu = mean[c], is = invstd[c];
+  float s1 = 0.f, s2 = 0.f;
+  for (long i = threadIdx.x; i < m; i += blockDim.x) {
+    const long n = i / HW, r = i - n * HW;
+    const long idx = (n * C + c) * HW + r;
+    float dz = dy[idx];
+    if (y[idx] < 0.f) dz *= kLreluSlope;
+    s1 += dz;
+    s2 += dz * (x[idx] - mu) * is;
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (threadIdx.x == 0) {
+    sum_dz[c] = s1;
+    sum_dz_xhat[c] = s2;
+    dbeta[c] += s1;
+    dgamma[c] += s2;
+  }
+}
+// ... then dx = gamma * invstd * (dz - sum_dz/m - xhat * sum_dz_xhat/m)
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                    const float* __restrict__ dy, float* __restrict__ dx,
+                                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ sum_dz,
+                                    const float* __restrict__ sum_dz_xhat, int C, int HW, long total, float inv_m) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (i / HW) % C;
+    float dz = dy[i];
+    if (y[i] < 0.f) dz *= kLreluSlope;
+    const float xhat = (x[i] - mean[c]) * invstd[c];
+    dx[i] = gamma[c] * invstd[c] * (dz - sum_dz[c] * inv_m - xhat * sum_dz_xhat[c] * inv_m);
+  }
+}
+
+// ---- RaGAN sigmoid cross-entropy (srgan_train.py:960-1009) ---------------------------------------
+// out[0] = loss, out[1] = binary accuracy of [real; fake] vs [1; 0] (srgan_train.py:1156-1158).
+// Optional gradients d_real, d_fake (N each), scaled by `gscale`.
+__device__ __forceinline__ float sce(float x, float t) {
+  return -(x * (t - (x >= 0.f ? 1.f : 0.f)) - log1pf(expf(-fabsf(x))));
+}
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void ragan_loss_kernel(const float* __restrict__ real, const float* __restrict__ fake, int n, float t_rmf,
+                                  float t_fmr, float gscale, float* __restrict__ out, float* __restrict__ d_real,
+                                  float* __restrict__ d_fake) {
+  __shared__ float red[32];
+  float sr = 0.f, sf = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    sr += real[i];
+    sf += fake[i];
+  }
+  const float rbar = block_sum(sr, red) / n;
+  const float fbar = block_sum(sf, red) / n;
+  float l = 0.f, acc = 0.f, g1 = 0.f, g2 = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = real[i] - fbar, b = fake[i] - rbar;
+    l += sce(a, t_rmf) + sce(b, t_fmr);
+    acc += (real[i] >= 0.f ? 1.f : 0.f) + (fake[i] >= 0.f ? 0.f : 1.f);
+    g1 += sigmoidf(a) - t_rmf;
+    g2 += sigmoidf(b) - t_fmr;
+  }
+  l = block_sum(l, red);
+  acc = block_sum(acc, red);
+  g1 = block_sum(g1, red);
+  g2 = block_sum(g2, red);
+  if (threadIdx.x == 0) {
+    out[0] = l / n;
+    out[1] = acc / (2.f * n);
+  }
+  if (d_real && d_fake) {
+    const float inv = 1.f / n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float a = real[i] - fbar, b = fake[i] - rbar;
+      d_real[i] = gscale * inv * ((sigmoidf(a) - t_rmf) - inv * g2);
+      d_fake[i] = gscale * inv * ((sigmoidf(b) - t_fmr) - inv * g1);
+    }
+  }
+}
+
+// ---- generator image losses: content L1, topographic L1 (4x4 avg-pool), SSIM 9x9 valid ----------
+// (srgan_train.py:871, 882-887, 932-956). One block per image (1 channel, H x W, H,W <= 48).
+// sums[0..3] += sum|yp-yt|, sum|pool(yp)-xt|, sum ssim_map, sum (yp-yt)^2.
+// dy (optional) = w_content*dL1 + w_topo*dTopo + w_struct*d(1-ssim), all with mean normalisers.
+constexpr int kMaxImg = 48;
+constexpr int kWin = 9;
+__constant__ float c_gauss[kWin];  // normalised 1-D Gaussian, sigma 1.5
+
+__global__ void gen_image_loss_kernel(const float* __restrict__ yp, const float* __restrict__ yt,
+                                      const float* __restrict__ xt, int N, int H, int W, float w_content,
+                                      float w_topo, float w_struct, float* __restrict__ sums,
+                                      float* __restrict__ dy) {
+  __shared__ float sp[kMaxImg * kMaxImg], st[kMaxImg * kMaxImg];
+  __shared__ float gP[(kMaxImg - 8) * (kMaxImg - 8)], gQ[(kMaxImg - 8) * (kMaxImg - 8)],
+      gR[(kMaxImg - 8) * (kMaxImg - 8)];
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  const int HW = H * W;
+  const int MH = H - kWin + 1, MW = W - kWin + 1;
+  const int PH = H / 4, PW = W / 4;
+  const float* p = yp + (long)n * HW;
+  const float* q = yt + (long)n * HW;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    sp[i] = p[i];
+    st[i] = q[i];
+  }
+  __syncthreads();
+  const float C1 = 1e-4f, C2 = 9e-4f;
+  const float ssim_scale = -w_struct / ((float)N * MH * MW);  // d(1 - mean ssim)
+  float s_ssim = 0.f;
+  for (int wi = threadIdx.x; wi < MH * MW; wi += blockDim.x) {
+    const int wy = wi / MW, wx = wi - wy * MW;
+    float P = 0.f, M2 = 0.f, Q = 0.f, S2 = 0.f, R = 0.f;
+    for (int a = 0; a < kWin; ++a) {
+      float rp = 0.f, rt = 0.f, rq = 0.f, rs = 0.f, rr = 0.f;
+      for (int b = 0; b < kWin; ++b) {
+        const float g = c_gauss[b];
+        const float u = sp[(wy + a) * W + wx + b], v = st[(wy + a) * W + wx + b];
+        rp += g * u; rt += g * v; rq += g * u * u; rs += g * v * v; rr += g * u * v;
+      }
+      const float g = c_gauss[a];
+      P += g * rp; M2 += g * rt; Q += g * rq; S2 += g * rs; R += g * rr;
+    }
+    const float s1 = Q - P * P, s2 = S2 - M2 * M2, s12 = R - P * M2;
+    const float A = 2.f * P * M2 + C1, B = 2.f * s12 + C2, Cc = P * P + M2 * M2 + C1, D = s1 + s2 + C2;
+    const float inv = 1.f / (Cc * D);
+    s_ssim += A * B * inv;
+    // partial derivatives wrt P = G*yp, Q = G*yp^2, R = G*(yp*yt)
+    const float dP = (2.f * M2 * B - 2.f * M2 * A) * inv - A * B * inv * inv * (2.f * P * D - 2.f * P * Cc);
+    const float dQ = -A * B * inv / D;
+    const float dR = 2.f * A * inv;
+    gP[wi] = ssim_scale * dP;
+    gQ[wi] = ssim_scale * dQ;
+    gR[wi] = ssim_scale * dR;
+  }
+  __syncthreads();
+  float s_l1 = 0.f, s_sq = 0.f;
+  const float l1_scale = w_content / ((float)N * HW);
+  const float topo_scale = w_topo / ((float)N * PH * PW) / 16.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const int y = i / W, x = i - y * W;
+    const float u = sp[i], v = st[i];
+    const float d = u - v;
+    s_l1 += fabsf(d);
+    s_sq += d * d;
+    if (dy) {
+      float g = l1_scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+      // topographic term: pooled cell (y/4, x/4)
+      if (y / 4 < PH && x / 4 < PW) {
+        float pool = 0.f;
+        const int by = (y / 4) * 4, bx = (x / 4) * 4;
+        for (int a = 0; a < 4; ++a)
+          for (int b = 0; b < 4; ++b) pool += sp[(by + a) * W + bx + b];
+        const float dd = pool * (1.f / 16.f) - xt[((long)n * PH + y / 4) * PW + x / 4];
+        g += topo_scale * (dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f));
+      }
+      // SSIM term: adjoint of the valid Gaussian filtering
+      float gp = 0.f, gq = 0.f, gr = 0.f;
+      for (int a = 0; a < kWin; ++a) {
+        const int wy = y - a;
+        if (wy < 0 || wy >= MH) continue;
+        for (int b = 0; b < kWin; ++b) {
+          const int wx = x - b;
+          if (wx < 0 || wx >= MW) continue;
+          const float gg = c_gauss[a] * c_gauss[b];
+          gp += gg * gP[wy * MW + wx];
+          gq += gg * gQ[wy * MW + wx];
+          gr += gg * gR[wy * MW + wx];
+        }
+      }
+      g += gp + 2.f * u * gq + v * gr;
+      dy[(long)n * HW + i] = g;
+    }
+  }
+  float s_topo = 0.f;
+  for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
+    const int cy = i / PW, cx = i - cy * PW;
+    float pool = 0.f;
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b) pool += sp[(cy * 4 + a) * W + cx * 4 + b];
+    s_topo += fabsf(pool * (1.f / 16.f) - xt[(long)n * PH * PW + i]);
+  }
+  s_l1 = block_sum(s_l1, red);
+  s_topo = block_sum(s_topo, red);
+  s_ssim = block_sum(s_ssim, red);
+  s_sq = block_sum(s_sq, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums + 0, s_l1);
+    atomicAdd(sums + 1, s_topo);
+    atomicAdd(sums + 2, s_ssim);
+    atomicAdd(sums + 3, s_sq);
+  }
+}
+
+// ---- chainer.optimizers.Adam: eps added to the UNcorrected sqrt(v) -------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long n, float lr_t, float beta1, float beta2, float eps,
+                            float grad_scale) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = m[i] + (1.f - beta1) * (gi - m[i]);
+    const float vi = v[i] + (1.f - beta2) * (gi * gi - v[i]);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+}  // namespace dbm
+
+using namespace dbm;
+
+static inline int grid_for(long total) {
+  long b = (total + 255) / 256;
+  long cap = (long)num_sms() * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+extern "C" int dbm_bn_lrelu_fwd_f32(const float* x, float* y, const float* gamma, const float* beta, float* avg_mean,
+                                    float* avg_var, float* save_mean, float* save_invstd, int n, int c, int hw,
+                                    float eps, float decay, int train, cudaStream_t st) {
+  DBM_REQUIRE(n > 0 && c > 0 && hw > 0, "bn: empty input");
+  bn_stats_kernel<<<c, 256, 0, st>>>(x, n, c, hw, eps, decay, train, avg_mean, avg_var, save_mean, save_invstd);
+  int rc = check_launch("bn_stats");
+  if (rc) return rc;
+  const long total = (long)n * c * hw;
+  bn_apply_lrelu_kernel<<<grid_for(total), 256, 0, st>>>(x, y, gamma, beta, save_mean, save_invstd, c, hw, total);
+  return check_launch("bn_apply_lrelu");
+}
+
+extern "C" int dbm_bn_lrelu_bwd_f32(const float* x, const float* y, const float* dy, float* dx, const float* gamma,
+                                    const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
+                                    float* scratch2c, int n, int c, int hw, cudaStream_t st) {
+  DBM_REQUIRE(n > 0 && c > 0 && hw > 0, "bn_bwd: empty input");
+  bn_bwd_reduce_kernel<<<c, 256, 0, st>>>(x, y, dy, n, c, hw, save_mean, save_invstd, dgamma, dbeta, scratch2c,
+                                          scratch2c + c);
+  int rc = check_launch("bn_bwd_reduce");
+  if (rc) return rc;
+  const long total = (long)n * c * hw;
+  bn_bwd_apply_kernel<<<grid_for(total), 256, 0, st>>>(x, y, dy, dx, gamma, save_mean, save_invstd, scratch2c,
+                                                       scratch2c + c, c, hw, total, 1.f / ((float)n * hw));
+  return check_launch("bn_bwd_apply");
+}
+
+extern "C" int dbm_ragan_loss_f32(const float* real_pred, const float* fake_pred, int n, float t_real_minus_fake,
+                                  float t_fake_minus_real, float grad_scale, float* out2, float* d_real,
+                                  float* d_fake, cudaStream_t st) {
+  DBM_REQUIRE(n > 0, "ragan_loss: empty batch");
+  ragan_loss_kernel<<<1, 256, 0, st>>>(real_pred, fake_pred, n, t_real_minus_fake, t_fake_minus_real, grad_scale,
+                                       out2, d_real, d_fake);
+  return check_launch("ragan_loss");
+}
+
+extern "C" int dbm_gen_image_loss_f32(const float* y_pred, const float* y_true, const float* x_topo, int n, int h,
+                                      int w, float w_content, float w_topo, float w_struct, float* sums4,
+                                      float* dy, cudaStream_t st) {
+  DBM_REQUIRE(n > 0, "gen_image_loss: empty batch");
+  DBM_REQUIRE(h >= kWin && w >= kWin && h <= kMaxImg && w <= kMaxImg && h % 4 == 0 && w % 4 == 0,
+              "gen_image_loss: image %dx%d unsupported (need 9..48, multiple of 4)", h, w);
+  static bool init = false;
+  if (!init) {
+    float g[kWin];
+    double s = 0;
+    for (int i = 0; i < kWin; ++i) {
+      double d = i - kWin / 2;
+      g[i] = (float)exp(-(d * d) / (2.0 * 1.5 * 1.5));
+      s += g[i];
+    }
+    for (int i = 0; i < kWin; ++i) g[i] = (float)(g[i] / s);
+    DBM_CUDA(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
+    init = true;
+  }
+  DBM_CUDA(cudaMemsetAsync(sums4, 0, 4 * sizeof(float), st));
+  gen_image_loss_kernel<<<n, 256, 0, st>>>(y_pred, y_true, x_topo, n, h, w, w_content, w_topo, w_struct, sums4, dy);
+  return check_launch("gen_image_loss");
+}
+
+extern "C" int dbm_adam_step_f32(float* params, const float* grads, float* m, float* v, long n, float alpha,
+                                 float beta1, float beta2, float eps, int t, float grad_scale, cudaStream_t st) {
+  DBM_REQUIRE(n > 0 && t >= 1, "adam: bad arguments (n=%ld, t=%d)", n, t);
+  const double fix1 = 1.0 - pow((double)beta1, t), fix2 = 1.0 - pow((double)beta2, t);
+  const float lr_t = (float)(alpha * sqrt(fix2) / fix1);
+  adam_kernel<<<grid_for(n), 256, 0, st>>>(params, grads, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+  return check_launch("adam");
+}

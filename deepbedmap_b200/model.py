@@ -1,0 +1,583 @@
+"""GeneratorModel / DiscriminatorModel with the reference's call surface
+(srgan_train.py:421-576, 591-699), executed by the CUDA kernels of libdeepbedmap_b200.so.
+
+Two arithmetic modes, both on the GPU (there is no CPU path):
+  precision="bf16"  inference: trunk / upsample / offset convolutions on the tcgen05 tensor cores
+                    (bf16 operands, fp32 TMEM accumulators, fp32 residual stream);
+  precision="fp32"  exact float32 CUDA-core path, also the path that keeps activations for
+                    backward (the training step).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import layout, ops
+from . import npz as npz_io
+
+
+class Variable:
+    """Minimal stand-in for chainer.Variable: callers only use ``.array`` / ``.shape``
+    (srgan_train.py:1137, 1229, 1450; deepbedmap.py:421, 733)."""
+
+    def __init__(self, array: torch.Tensor):
+        self.array = array
+        self.data = array
+
+    @property
+    def shape(self):
+        return tuple(self.array.shape)
+
+    def numpy(self) -> np.ndarray:
+        return self.array.detach().cpu().numpy()
+
+
+class _DeviceArrayModule:
+    """``model.xp`` shim: ``model.xp.asarray(a, dtype="float32")`` moves a host crop to the GPU
+    (deepbedmap.py:715-722)."""
+
+    @staticmethod
+    def asarray(a, dtype="float32"):
+        return as_device(a)
+
+
+def as_device(a) -> torch.Tensor:
+    if isinstance(a, Variable):
+        a = a.array
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return t.to(device="cuda", dtype=torch.float32, non_blocking=True).contiguous()
+
+
+class _Link:
+    """Flat fp32 parameter / gradient buffers on the device with named views."""
+
+    def __init__(self, shapes: "OrderedDict[str, tuple]", values: Dict[str, np.ndarray]):
+        if not torch.cuda.is_available():
+            raise RuntimeError("deepbedmap_b200 needs a CUDA device (B200); there is no CPU fallback")
+        from . import _lib
+        _lib.load()  # fail loudly if the CUDA library is missing
+        self._shapes = shapes
+        total = sum(int(np.prod(s)) for s in shapes.values())
+        host = np.empty(total, np.float32)
+        self._slices = OrderedDict()
+        off = 0
+        for k, shp in shapes.items():
+            n = int(np.prod(shp))
+            host[off:off + n] = np.asarray(values[k], np.float32).reshape(-1)
+            self._slices[k] = (off, n)
+            off += n
+        self.flat = torch.from_numpy(host).cuda()
+        self.flat_grad = ops.zeros(total)
+        self.p = OrderedDict((k, self.flat[o:o + n].view(shapes[k])) for k, (o, n) in self._slices.items())
+        self.g = OrderedDict((k, self.flat_grad[o:o + n].view(shapes[k])) for k, (o, n) in self._slices.items())
+        self.version = 0
+        self.xp = _DeviceArrayModule()
+
+    # -- chainer.Link surface used by the reference --
+    def to_gpu(self, device=None):
+        return self
+
+    def params(self):
+        return iter(self.p.values())
+
+    def namedparams(self):
+        return iter(self.p.items())
+
+    def count_params(self) -> int:
+        return int(self.flat.numel())
+
+    def cleargrads(self):
+        ops.fill(self.flat_grad, 0.0)
+
+    def set_param(self, key: str, value):
+        if key not in self.p:
+            raise KeyError(key)
+        v = np.asarray(value, np.float32)
+        if tuple(v.shape) != tuple(self._shapes[key]):
+            raise ValueError(f"{key}: shape {v.shape} != {self._shapes[key]}")
+        self.p[key].copy_(torch.from_numpy(np.ascontiguousarray(v)))
+        self.version += 1
+
+    def get_param(self, key: str) -> np.ndarray:
+        return self.p[key].detach().cpu().numpy()
+
+    def state_dict(self) -> "OrderedDict[str, np.ndarray]":
+        return OrderedDict((k, self.get_param(k)) for k in self.p)
+
+    def mark_updated(self):
+        self.version += 1
+
+
+# ================================================================================================
+# Generator
+# ================================================================================================
+class GeneratorModel(_Link):
+    """Drop-in for srgan_train.GeneratorModel (srgan_train.py:421-576).
+
+    >>> model = GeneratorModel()                                      # doctest: +SKIP
+    >>> model.forward(x=X, w1=W1, w2=W2, w3=W3).shape               # doctest: +SKIP
+    (1, 1, 36, 36)
+    >>> model.count_params()                                          # doctest: +SKIP
+    8907749
+    """
+
+    def __init__(self, inblock_class=None, resblock_class=None, num_residual_blocks: int = 12,
+                 residual_scaling: float = 0.1, out_channels: int = 1, *, inter_channels: int = 32,
+                 precision: str = "bf16", seed: int = 0, init_scale: float = 0.1):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if inter_channels not in (32, 64):
+            raise ValueError("inter_channels must be 32 or 64 (reference search space, srgan_train.py:283-284)")
+        self.num_residual_blocks = int(num_residual_blocks)
+        self.residual_scaling = float(residual_scaling)
+        self.out_channels = int(out_channels)
+        self.inter_channels = int(inter_channels)
+        self.precision = precision
+        shapes = layout.generator_shapes(self.num_residual_blocks, self.inter_channels, self.out_channels)
+        super().__init__(shapes, layout.init_values(shapes, seed, init_scale))
+        self._packed_version = -1
+        self._packed = {}
+        self._ctx = None
+
+    # ---- serialisation (chainer.serializers.load_npz / save_npz, App. C layout) ----
+    def load_npz(self, file, strict: bool = True):
+        npz_io.load_npz(file, self, strict=strict)
+        return self
+
+    def save_npz(self, file, compression: bool = True):
+        npz_io.save_npz(file, self, compression=compression)
+
+    # ---- forward ----
+    def __call__(self, x, w1, w2, w3):
+        return self.forward(x, w1, w2, w3)
+
+    def forward(self, x, w1, w2, w3) -> Variable:
+        """Inference forward: inputs (N,1,h,w), (N,1,10h,10w), (N,2,2h,2w), (N,1,h,w) float32
+        (NumPy or torch, host or device) -> Variable with .array (N,1,4(h-2),4(w-2)) on the GPU."""
+        x, w1, w2, w3 = (as_device(a) for a in (x, w1, w2, w3))
+        self._check_shapes(x, w1, w2, w3)
+        if self.precision == "bf16":
+            y = self._forward_bf16(x, w1, w2, w3)
+        else:
+            y = self._forward_fp32(x, w1, w2, w3, save=False)
+        return Variable(y)
+
+    def forward_train(self, x, w1, w2, w3) -> Variable:
+        """fp32 forward that keeps the activations needed by ``backward`` (the reference's
+        graph-building forward, srgan_train.py:1222-1227)."""
+        x, w1, w2, w3 = (as_device(a) for a in (x, w1, w2, w3))
+        self._check_shapes(x, w1, w2, w3)
+        return Variable(self._forward_fp32(x, w1, w2, w3, save=True))
+
+    @staticmethod
+    def _check_shapes(x, w1, w2, w3):
+        if x.dim() != 4 or w1.dim() != 4 or w2.dim() != 4 or w3.dim() != 4:
+            raise ValueError("inputs must be 4-D (N, C, H, W) arrays")
+        n, c, h, w = x.shape
+        ok = (c == 1 and tuple(w1.shape) == (n, 1, 10 * h, 10 * w) and tuple(w2.shape) == (n, 2, 2 * h, 2 * w)
+              and tuple(w3.shape) == (n, 1, h, w) and h >= 3 and w >= 3)
+        if not ok:
+            # Chainer raises InvalidType from F.concat for inconsistent input sizes (srgan_train.py:265)
+            raise ValueError(f"inconsistent input shapes: x{tuple(x.shape)} w1{tuple(w1.shape)} "
+                             f"w2{tuple(w2.shape)} w3{tuple(w3.shape)}; need w1 = 10x, w2 = 2x (2 ch), w3 = 1x of x")
+
+    def _rdb_prefix(self, i, r):
+        return f"residual_network/{i}/residual_dense_block{r}"
+
+    # ---------------- fp32 path ----------------
+    def _stem_fp32(self, x, w1, w2, w3, out, c0=0):
+        P = self.p
+        ops.conv2d_fwd(x, 0, 1, P["input_block/conv_on_X/W"], P["input_block/conv_on_X/b"], out, c0 + 0, 3, 1, 0)
+        ops.conv2d_fwd(w1, 0, 1, P["input_block/conv_on_W1/W"], P["input_block/conv_on_W1/b"], out, c0 + 32, 30, 10, 0)
+        ops.conv2d_fwd(w2, 0, 2, P["input_block/conv_on_W2/W"], P["input_block/conv_on_W2/b"], out, c0 + 64, 6, 2, 0)
+        ops.conv2d_fwd(w3, 0, 1, P["input_block/conv_on_W3/W"], P["input_block/conv_on_W3/b"], out, c0 + 96, 3, 1, 0)
+
+    def _forward_fp32(self, x, w1, w2, w3, save: bool):
+        P = self.p
+        g = self.inter_channels
+        cc = 64 + 4 * g
+        beta = self.residual_scaling
+        n, _, h, w = x.shape
+        H, W = h - 2, w - 2
+        a0 = ops.empty(n, 128, H, W)
+        self._stem_fp32(x, w1, w2, w3, a0)
+        nrdb = 3 * self.num_residual_blocks
+        cats = [ops.empty(n, cc, H, W) for _ in range(nrdb + 1)]  # cats[j][:, :64] = input of RDB j
+        ops.conv2d_fwd(a0, 0, 128, P["pre_residual_conv_layer/W"], P["pre_residual_conv_layer/b"], cats[0], 0, 3, 1, 1,
+                       act=True)
+        t5s = []
+        j = 0
+        for i in range(self.num_residual_blocks):
+            rrdb_in = cats[j]
+            for r in (1, 2, 3):
+                cat = cats[j]
+                pre = self._rdb_prefix(i, r)
+                for k in (1, 2, 3, 4):
+                    cin = 64 + (k - 1) * g
+                    ops.conv2d_fwd(cat, 0, cin, P[f"{pre}/conv_layer{k}/W"], P[f"{pre}/conv_layer{k}/b"], cat, cin, 3, 1,
+                                   1, act=True)
+                t5 = ops.empty(n, 64, H, W)
+                ops.conv2d_fwd(cat, 0, cc, P[f"{pre}/conv_layer5/W"], P[f"{pre}/conv_layer5/b"], t5, 0, 3, 1, 1)
+                nxt = cats[j + 1]
+                # a6 = a5 * beta + a0 (srgan_train.py:358)
+                ops.axpby(t5, 0, cat, 0, nxt, 0, 64, beta, 1.0)
+                if r == 3:  # a4 = a3 * beta + x (srgan_train.py:402)
+                    ops.axpby(nxt, 0, rrdb_in, 0, nxt, 0, 64, beta, 1.0)
+                j += 1
+        last = cats[nrdb]
+        t = ops.empty(n, 64, H, W)
+        ops.conv2d_fwd(last, 0, 64, P["post_residual_conv_layer/W"], P["post_residual_conv_layer/b"], t, 0, 3, 1, 1)
+        a3 = ops.empty(n, 64, H, W)
+        ops.axpby(t, 0, cats[0], 0, a3, 0, 64, 1.0, 1.0)  # a3 = a1 + conv (srgan_train.py:551)
+        u1 = ops.upsample2_fwd(a3)
+        c1 = ops.empty(n, 64, 2 * H, 2 * W)
+        ops.conv2d_fwd(u1, 0, 64, P["post_upsample_conv_layer_1/W"], P["post_upsample_conv_layer_1/b"], c1, 0, 3, 1, 1,
+                       act=True)
+        u2 = ops.upsample2_fwd(c1)
+        c2 = ops.empty(n, 64, 4 * H, 4 * W)
+        ops.conv2d_fwd(u2, 0, 64, P["post_upsample_conv_layer_2/W"], P["post_upsample_conv_layer_2/b"], c2, 0, 3, 1, 1,
+                       act=True)
+        off1 = ops.empty(n, 18, 4 * H, 4 * W)
+        ops.conv2d_fwd(c2, 0, 64, P["final_conv_layer1/offset_conv/W"], P["final_conv_layer1/offset_conv/b"], off1, 0, 3,
+                       1, 1)
+        d1, cols1 = ops.deform_conv_fwd(c2, off1, P["final_conv_layer1/deform_conv/W"],
+                                        P["final_conv_layer1/deform_conv/b"], act=True)
+        off2 = ops.empty(n, 18, 4 * H, 4 * W)
+        ops.conv2d_fwd(d1, 0, 64, P["final_conv_layer2/offset_conv/W"], P["final_conv_layer2/offset_conv/b"], off2, 0, 3,
+                       1, 1)
+        y, cols2 = ops.deform_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"],
+                                       P["final_conv_layer2/deform_conv/b"], act=False)
+        if save:
+            self._ctx = dict(x=x, w1=w1, w2=w2, w3=w3, a0=a0, cats=cats, u1=u1, c1=c1, u2=u2, c2=c2, off1=off1, d1=d1,
+                             cols1=cols1, off2=off2, cols2=cols2, H=H, W=W, n=n)
+        return y
+
+    def backward(self, dy: torch.Tensor):
+        """Accumulates d(loss)/d(params) into ``flat_grad`` given d(loss)/d(output) (N,1,4H,4W);
+        replaces g_loss.backward() for the generator (srgan_train.py:1256). No gradient wrt the
+        inputs is produced (no caller needs it)."""
+        if self._ctx is None:
+            raise RuntimeError("backward() needs a preceding forward_train()")
+        c = self._ctx
+        P, G = self.p, self.g
+        g = self.inter_channels
+        cc = 64 + 4 * g
+        beta = self.residual_scaling
+        n, H, W = c["n"], c["H"], c["W"]
+        dy = dy.contiguous()
+        # ---- final_conv_layer2 (deformable, no activation) ----
+        dd1 = ops.zeros(n, 64, 4 * H, 4 * W)
+        doff2 = ops.deform_conv_bwd(c["d1"], c["off2"], P["final_conv_layer2/deform_conv/W"], c["cols2"], dy,
+                                    G["final_conv_layer2/deform_conv/W"], G["final_conv_layer2/deform_conv/b"], dd1)
+        ops.conv2d_bwd_weight(c["d1"], 0, 64, doff2, 0, G["final_conv_layer2/offset_conv/W"], 3, 1, 1,
+                              db=G["final_conv_layer2/offset_conv/b"])
+        ops.conv2d_bwd_data(doff2, 0, P["final_conv_layer2/offset_conv/W"], dd1, 0, 64, 3, 1, 1, accumulate=True)
+        ops.lrelu_bwd(dd1, 0, c["d1"], 0, dd1, 0, 64)
+        # ---- final_conv_layer1 ----
+        dc2 = ops.zeros(n, 64, 4 * H, 4 * W)
+        doff1 = ops.deform_conv_bwd(c["c2"], c["off1"], P["final_conv_layer1/deform_conv/W"], c["cols1"], dd1,
+                                    G["final_conv_layer1/deform_conv/W"], G["final_conv_layer1/deform_conv/b"], dc2)
+        ops.conv2d_bwd_weight(c["c2"], 0, 64, doff1, 0, G["final_conv_layer1/offset_conv/W"], 3, 1, 1,
+                              db=G["final_conv_layer1/offset_conv/b"])
+        ops.conv2d_bwd_data(doff1, 0, P["final_conv_layer1/offset_conv/W"], dc2, 0, 64, 3, 1, 1, accumulate=True)
+        del dd1, doff1, doff2
+        # ---- upsample convs ----
+        ops.lrelu_bwd(dc2, 0, c["c2"], 0, dc2, 0, 64)
+        ops.conv2d_bwd_weight(c["u2"], 0, 64, dc2, 0, G["post_upsample_conv_layer_2/W"], 3, 1, 1,
+                              db=G["post_upsample_conv_layer_2/b"])
+        du2 = ops.empty(n, 64, 4 * H, 4 * W)
+        ops.conv2d_bwd_data(dc2, 0, P["post_upsample_conv_layer_2/W"], du2, 0, 64, 3, 1, 1)
+        dc1 = ops.upsample2_bwd(du2)
+        del du2, dc2
+        ops.lrelu_bwd(dc1, 0, c["c1"], 0, dc1, 0, 64)
+        ops.conv2d_bwd_weight(c["u1"], 0, 64, dc1, 0, G["post_upsample_conv_layer_1/W"], 3, 1, 1,
+                              db=G["post_upsample_conv_layer_1/b"])
+        du1 = ops.empty(n, 64, 2 * H, 2 * W)
+        ops.conv2d_bwd_data(dc1, 0, P["post_upsample_conv_layer_1/W"], du1, 0, 64, 3, 1, 1)
+        da3 = ops.upsample2_bwd(du1)  # = d a1 (skip) = d (post-res conv output)
+        del du1, dc1
+        # ---- post-residual conv ----
+        cats = c["cats"]
+        nrdb = 3 * self.num_residual_blocks
+        ops.conv2d_bwd_weight(cats[nrdb], 0, 64, da3, 0, G["post_residual_conv_layer/W"], 3, 1, 1,
+                              db=G["post_residual_conv_layer/b"])
+        dcur = ops.empty(n, 64, H, W)  # gradient wrt the trunk output
+        ops.conv2d_bwd_data(da3, 0, P["post_residual_conv_layer/W"], dcur, 0, 64, 3, 1, 1)
+        # ---- trunk, reversed ----
+        j = nrdb
+        for i in reversed(range(self.num_residual_blocks)):
+            d_rrdb_out = dcur  # out = x + beta * a3
+            d_rdb_out = ops.empty(n, 64, H, W)
+            ops.axpby(d_rrdb_out, 0, None, 0, d_rdb_out, 0, 64, beta, 0.0)
+            for r in (3, 2, 1):
+                j -= 1
+                cat = cats[j]
+                pre = self._rdb_prefix(i, r)
+                # a6 = a0 + beta * a5
+                d5 = ops.empty(n, 64, H, W)
+                ops.axpby(d_rdb_out, 0, None, 0, d5, 0, 64, beta, 0.0)
+                ops.conv2d_bwd_weight(cat, 0, cc, d5, 0, G[f"{pre}/conv_layer5/W"], 3, 1, 1, db=G[f"{pre}/conv_layer5/b"])
+                dcat = ops.empty(n, cc, H, W)
+                ops.conv2d_bwd_data(d5, 0, P[f"{pre}/conv_layer5/W"], dcat, 0, cc, 3, 1, 1)
+                ops.axpby(dcat, 0, d_rdb_out, 0, dcat, 0, 64, 1.0, 1.0)  # + d a0 (skip)
+                for k in (4, 3, 2, 1):
+                    cin = 64 + (k - 1) * g
+                    ops.lrelu_bwd(dcat, cin, cat, cin, dcat, cin, g)
+                    ops.conv2d_bwd_weight(cat, 0, cin, dcat, cin, G[f"{pre}/conv_layer{k}/W"], 3, 1, 1,
+                                          db=G[f"{pre}/conv_layer{k}/b"])
+                    ops.conv2d_bwd_data(dcat, cin, P[f"{pre}/conv_layer{k}/W"], dcat, 0, cin, 3, 1, 1, accumulate=True)
+                d_rdb_out = ops.empty(n, 64, H, W)
+                ops.axpby(dcat, 0, None, 0, d_rdb_out, 0, 64, 1.0, 0.0)
+            # RRDB skip: d x += d out
+            dcur = ops.empty(n, 64, H, W)
+            ops.axpby(d_rdb_out, 0, d_rrdb_out, 0, dcur, 0, 64, 1.0, 1.0)
+        # ---- a1 = lrelu(pre_res(a0)); total gradient = trunk input + skip to a3 ----
+        da1 = ops.empty(n, 64, H, W)
+        ops.axpby(dcur, 0, da3, 0, da1, 0, 64, 1.0, 1.0)
+        ops.lrelu_bwd(da1, 0, cats[0], 0, da1, 0, 64)
+        ops.conv2d_bwd_weight(c["a0"], 0, 128, da1, 0, G["pre_residual_conv_layer/W"], 3, 1, 1,
+                              db=G["pre_residual_conv_layer/b"])
+        da0 = ops.empty(n, 128, H, W)
+        ops.conv2d_bwd_data(da1, 0, P["pre_residual_conv_layer/W"], da0, 0, 128, 3, 1, 1)
+        # ---- stem weights ----
+        ops.conv2d_bwd_weight(c["x"], 0, 1, da0, 0, G["input_block/conv_on_X/W"], 3, 1, 0, db=G["input_block/conv_on_X/b"])
+        ops.conv2d_bwd_weight(c["w1"], 0, 1, da0, 32, G["input_block/conv_on_W1/W"], 30, 10, 0,
+                              db=G["input_block/conv_on_W1/b"])
+        ops.conv2d_bwd_weight(c["w2"], 0, 2, da0, 64, G["input_block/conv_on_W2/W"], 6, 2, 0,
+                              db=G["input_block/conv_on_W2/b"])
+        ops.conv2d_bwd_weight(c["w3"], 0, 1, da0, 96, G["input_block/conv_on_W3/W"], 3, 1, 0,
+                              db=G["input_block/conv_on_W3/b"])
+        self._ctx = None
+
+    # ---------------- bf16 tensor-core path (inference) ----------------
+    def _pack(self):
+        if self._packed_version == self.version:
+            return self._packed
+        P = self.p
+        pk = {}
+
+        def add(key, cout_padded):
+            w = P[f"{key}/W"]
+            b = P[f"{key}/b"]
+            if b.numel() < cout_padded:
+                bp = ops.zeros(cout_padded)
+                bp[: b.numel()].copy_(b)
+            else:
+                bp = b
+            pk[key] = (ops.pack_conv3x3(w, cout_padded), bp)
+
+        add("pre_residual_conv_layer", 64)
+        for i in range(self.num_residual_blocks):
+            for r in (1, 2, 3):
+                pre = self._rdb_prefix(i, r)
+                for k in (1, 2, 3, 4):
+                    add(f"{pre}/conv_layer{k}", self.inter_channels)
+                add(f"{pre}/conv_layer5", 64)
+        for key in ("post_residual_conv_layer", "post_upsample_conv_layer_1", "post_upsample_conv_layer_2"):
+            add(key, 64)
+        add("final_conv_layer1/offset_conv", 32)
+        add("final_conv_layer2/offset_conv", 32)
+        self._packed = pk
+        self._packed_version = self.version
+        return pk
+
+    def _forward_bf16(self, x, w1, w2, w3):
+        P = self.p
+        pk = self._pack()
+        g = self.inter_channels
+        cc = 64 + 4 * g
+        ccs = cc // 8
+        beta = self.residual_scaling
+        n, _, h, w = x.shape
+        H, W = h - 2, w - 2
+        bf = torch.bfloat16
+        a0 = ops.empty(n, 128, H, W)
+        self._stem_fp32(x, w1, w2, w3, a0)
+        s0 = ops.empty(n, 16, H, W, 8, dtype=bf)
+        ops.nchw_to_slab8(a0, s0)
+        del a0
+        cat = [ops.empty(n, ccs, H, W, 8, dtype=bf) for _ in range(2)]
+        a1_f32 = ops.empty(n, 16, H, W, 4)
+        f32 = [ops.empty(n, 16, H, W, 4) for _ in range(3)]
+        wq, bq = pk["pre_residual_conv_layer"]
+        ops.conv3x3_umma(s0, 128, wq, bq, 64, act=True, out=cat[0], out_f32=a1_f32)
+        cur, cur_f32 = 0, a1_f32
+        fi = 0
+        for i in range(self.num_residual_blocks):
+            rrdb_in = cur_f32
+            for r in (1, 2, 3):
+                pre = self._rdb_prefix(i, r)
+                for k in (1, 2, 3, 4):
+                    cin = 64 + (k - 1) * g
+                    wq, bq = pk[f"{pre}/conv_layer{k}"]
+                    ops.conv3x3_umma(cat[cur], cin, wq, bq, g, act=True, out=cat[cur], out_cs0=cin // 8)
+                wq, bq = pk[f"{pre}/conv_layer5"]
+                # pick an fp32 buffer that is neither the RDB input nor the RRDB input
+                while f32[fi] is cur_f32 or f32[fi] is rrdb_in:
+                    fi = (fi + 1) % 3
+                nxt_f32 = f32[fi]
+                ops.conv3x3_umma(cat[cur], cc, wq, bq, 64, beta=beta, out=cat[1 - cur], out_f32=nxt_f32, res1=cur_f32,
+                                 res2=rrdb_in if r == 3 else None)
+                cur, cur_f32 = 1 - cur, nxt_f32
+        u1 = ops.empty(n, 8, 2 * H, 2 * W, 8, dtype=bf)
+        wq, bq = pk["post_residual_conv_layer"]
+        ops.conv3x3_umma(cat[cur], 64, wq, bq, 64, beta=1.0, up2=True, out=u1, res1=a1_f32)
+        del cat, f32
+        u2 = ops.empty(n, 8, 4 * H, 4 * W, 8, dtype=bf)
+        wq, bq = pk["post_upsample_conv_layer_1"]
+        ops.conv3x3_umma(u1, 64, wq, bq, 64, act=True, up2=True, out=u2)
+        del u1
+        f1 = ops.empty(n, 8, 4 * H, 4 * W, 8, dtype=bf)
+        wq, bq = pk["post_upsample_conv_layer_2"]
+        ops.conv3x3_umma(u2, 64, wq, bq, 64, act=True, out=f1)
+        del u2
+        # deformable layers: offset convs on the tensor cores, sampling + contraction in fp32
+        off1_s = ops.empty(n, 8, 4 * H, 4 * W, 4)
+        wq, bq = pk["final_conv_layer1/offset_conv"]
+        ops.conv3x3_umma(f1, 64, wq, bq, 32, out_f32=off1_s)
+        c2 = ops.slab8_to_nchw(f1, 64)
+        off1 = ops.slab4_to_nchw(off1_s, 18)
+        del f1, off1_s
+        d1, _ = ops.deform_conv_fwd(c2, off1, P["final_conv_layer1/deform_conv/W"], P["final_conv_layer1/deform_conv/b"],
+                                    act=True)
+        del c2, off1, _
+        d1_s = ops.empty(n, 8, 4 * H, 4 * W, 8, dtype=bf)
+        ops.nchw_to_slab8(d1, d1_s)
+        off2_s = ops.empty(n, 8, 4 * H, 4 * W, 4)
+        wq, bq = pk["final_conv_layer2/offset_conv"]
+        ops.conv3x3_umma(d1_s, 64, wq, bq, 32, out_f32=off2_s)
+        off2 = ops.slab4_to_nchw(off2_s, 18)
+        del d1_s, off2_s
+        y, _ = ops.deform_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"], P["final_conv_layer2/deform_conv/b"])
+        return y
+
+
+# ================================================================================================
+# Discriminator
+# ================================================================================================
+class DiscriminatorModel(_Link):
+    """Drop-in for srgan_train.DiscriminatorModel (srgan_train.py:591-699): logits (N,1), no sigmoid.
+
+    ``train`` replaces chainer.global_config.train (srgan_train.py:1125, 1228): True = batch
+    statistics + running-stat update, False = running statistics.
+    """
+
+    BN_EPS = 1e-5
+    BN_DECAY = 0.9
+
+    def __init__(self, *, seed: int = 1, init_scale: float = 0.1):
+        shapes = layout.discriminator_shapes()
+        super().__init__(shapes, layout.init_values(shapes, seed, init_scale))
+        self.persistent = OrderedDict()
+        for k, shp in layout.discriminator_persistents().items():
+            self.persistent[k] = ops.zeros(*shp)
+            if k.endswith("avg_var"):
+                ops.fill(self.persistent[k], 1.0)
+        self.bn_N = {i: 0 for i in range(1, 10)}
+        self.train = True
+        self._ctx = None
+
+    def load_npz(self, file, strict: bool = True):
+        npz_io.load_npz(file, self, strict=strict)
+        return self
+
+    def save_npz(self, file, compression: bool = True):
+        npz_io.save_npz(file, self, compression=compression)
+
+    def __call__(self, x, train: Optional[bool] = None):
+        return self.forward(x, train=train)
+
+    def forward(self, x, train: Optional[bool] = None, save: bool = False) -> Variable:
+        train = self.train if train is None else bool(train)
+        x = as_device(x)
+        if x.dim() != 4 or tuple(x.shape[1:]) != (1, 36, 36):
+            # linear_1 is initialised for 512 inputs, i.e. 36x36 images (srgan_train.py:646, 693)
+            raise ValueError(f"DiscriminatorModel expects (N,1,36,36) input, got {tuple(x.shape)}")
+        P = self.p
+        n = x.shape[0]
+        acts = [x]
+        pres = []
+        a = ops.empty(n, 64, 36, 36)
+        ops.conv2d_fwd(x, 0, 1, P["conv_layer0/W"], P["conv_layer0/b"], a, 0, 3, 1, 1, act=True)
+        acts.append(a)
+        stats = []
+        hcur = 36
+        cin = 64
+        for i in range(1, 10):
+            cout, k, s = layout.DISC_CONVS[i]
+            ho, _ = ops.conv_out_hw(hcur, hcur, k, s, 1)
+            z = ops.empty(n, cout, ho, ho)
+            ops.conv2d_fwd(acts[-1], 0, cin, P[f"conv_layer{i}/W"], None, z, 0, k, s, 1)
+            y = ops.empty(n, cout, ho, ho)
+            mean, invstd = ops.empty(cout), ops.empty(cout)
+            ops.call("dbm_bn_lrelu_fwd_f32", z.data_ptr(), y.data_ptr(), P[f"batch_norm{i}/gamma"].data_ptr(),
+                     P[f"batch_norm{i}/beta"].data_ptr(), self.persistent[f"batch_norm{i}/avg_mean"].data_ptr(),
+                     self.persistent[f"batch_norm{i}/avg_var"].data_ptr(), mean.data_ptr(), invstd.data_ptr(), n, cout,
+                     ho * ho, self.BN_EPS, self.BN_DECAY, int(train), ops.stream())
+            if train:
+                self.bn_N[i] += 1
+            pres.append(z)
+            stats.append((mean, invstd))
+            acts.append(y)
+            hcur, cin = ho, cout
+        flat = acts[-1].view(n, 512)
+        l1 = ops.empty(n, 100)
+        ops.gemm(flat, 512, 1, 0, P["linear_1/W"], 1, 512, 0, l1, 100, 1, 0, P["linear_1/b"], n, 100, 512, act=True)
+        out = ops.empty(n, 1)
+        ops.gemm(l1, 100, 1, 0, P["linear_2/W"], 1, 100, 0, out, 1, 1, 0, P["linear_2/b"], n, 1, 100)
+        if save:
+            if not train:
+                raise ValueError("backward through eval-mode BatchNormalization is not needed by the reference")
+            self._ctx = dict(acts=acts, pres=pres, stats=stats, l1=l1, n=n)
+        return Variable(out)
+
+    def backward(self, dlogit: torch.Tensor):
+        """Accumulates parameter gradients for the most recent ``forward(save=True)`` given
+        d(loss)/d(logits) (N,1); replaces d_loss.backward() (srgan_train.py:1163)."""
+        if self._ctx is None:
+            raise RuntimeError("backward() needs a preceding forward(save=True)")
+        c = self._ctx
+        P, G = self.p, self.g
+        n = c["n"]
+        acts, pres, stats, l1 = c["acts"], c["pres"], c["stats"], c["l1"]
+        dlogit = dlogit.contiguous()
+        # linear_2
+        ops.gemm(dlogit, 1, 1, 0, l1, 100, 1, 0, G["linear_2/W"], 100, 1, 0, None, 1, 100, n, accumulate=1)
+        ops.call("dbm_bias_grad_f32", dlogit.data_ptr(), 1, G["linear_2/b"].data_ptr(), n, 1, 1, ops.stream())
+        dl1 = ops.empty(n, 100)
+        ops.gemm(dlogit, 1, 1, 0, P["linear_2/W"], 100, 1, 0, dl1, 100, 1, 0, None, n, 100, 1)
+        ops.lrelu_bwd(dl1, 0, l1, 0, dl1, 0, 100)
+        # linear_1: dW[o, i] += sum_n dl1[n, o] * flat[n, i]
+        flat = acts[-1].view(n, 512)
+        ops.gemm(dl1, 1, 100, 0, flat, 512, 1, 0, G["linear_1/W"], 512, 1, 0, None, 100, 512, n, accumulate=1)
+        ops.call("dbm_bias_grad_f32", dl1.data_ptr(), 100, G["linear_1/b"].data_ptr(), n, 100, 1, ops.stream())
+        dflat = ops.empty(n, 512, 1, 1)
+        ops.gemm(dl1, 100, 1, 0, P["linear_1/W"], 512, 1, 0, dflat, 512, 1, 0, None, n, 512, 100)
+        dy = dflat
+        for i in range(9, 0, -1):
+            cout, k, s = layout.DISC_CONVS[i]
+            z, y = pres[i - 1], acts[i + 1]
+            mean, invstd = stats[i - 1]
+            hw = z.shape[2] * z.shape[3]
+            dz = ops.empty(*z.shape)
+            scratch = ops.empty(2 * cout)
+            ops.call("dbm_bn_lrelu_bwd_f32", z.data_ptr(), y.data_ptr(), dy.data_ptr(), dz.data_ptr(),
+                     P[f"batch_norm{i}/gamma"].data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                     G[f"batch_norm{i}/gamma"].data_ptr(), G[f"batch_norm{i}/beta"].data_ptr(), scratch.data_ptr(), n,
+                     cout, hw, ops.stream())
+            xin = acts[i]
+            cin = xin.shape[1]
+            ops.conv2d_bwd_weight(xin, 0, cin, dz, 0, G[f"conv_layer{i}/W"], k, s, 1)
+            dx = ops.empty(*xin.shape)
+            ops.conv2d_bwd_data(dz, 0, P[f"conv_layer{i}/W"], dx, 0, cin, k, s, 1)
+            dy = dx
+        # conv_layer0 + LeakyReLU
+        ops.lrelu_bwd(dy, 0, acts[1], 0, dy, 0, 64)
+        ops.conv2d_bwd_weight(acts[0], 0, 1, dy, 0, G["conv_layer0/W"], 3, 1, 1, db=G["conv_layer0/b"])
+        self._ctx = None

@@ -1,0 +1,192 @@
+"""Thin Python wrappers over the C ABI: they only compute pointers/strides from torch tensors
+(torch is the allocator and stream host) and enqueue the CUDA kernels."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+call = _lib.call
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t, elem_offset: int = 0) -> int:
+    return t.data_ptr() + elem_offset * t.element_size()
+
+
+def _chk(t, dtype=torch.float32):
+    if not (t.is_cuda and t.is_contiguous() and t.dtype == dtype):
+        raise ValueError(f"expected contiguous CUDA {dtype} tensor, got {t.dtype} {t.device} contiguous={t.is_contiguous()}")
+
+
+def empty(*shape, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device="cuda")
+
+
+def zeros(*shape, dtype=torch.float32):
+    t = torch.empty(shape, dtype=dtype, device="cuda")
+    if dtype == torch.float32:
+        fill(t, 0.0)
+    else:
+        # raw memset through the same kernel on the fp32 view (sizes are multiples of 4 bytes)
+        n32 = t.numel() * t.element_size() // 4
+        call("dbm_fill_f32", t.data_ptr(), 0.0, n32, stream())
+    return t
+
+
+def fill(t, v: float):
+    _chk(t)
+    call("dbm_fill_f32", t.data_ptr(), float(v), t.numel(), stream())
+
+
+# ---- fp32 conv family (NCHW, channel-slice views via batch strides) ----------------------------
+def conv_out_hw(h, w, k, s, p):
+    return (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+
+
+def conv2d_fwd(x, x_c0, cin, w, b, y, y_c0, k, s, p, act=False):
+    """y[:, y_c0:y_c0+O] = conv(x[:, x_c0:x_c0+cin], w) + b, optional LeakyReLU(0.2)."""
+    n, cx, h, wd = x.shape
+    o = w.shape[0]
+    ho, wo = conv_out_hw(h, wd, k, s, p)
+    assert y.shape[0] == n and y.shape[2] == ho and y.shape[3] == wo, (x.shape, y.shape)
+    assert w.shape[1] == cin and x_c0 + cin <= cx and y_c0 + o <= y.shape[1]
+    call("dbm_conv2d_fwd_f32", _ptr(x, x_c0 * h * wd), cx * h * wd, w.data_ptr(), b.data_ptr() if b is not None else None,
+         _ptr(y, y_c0 * ho * wo), y.shape[1] * ho * wo, n, cin, h, wd, o, k, s, p, int(act), stream())
+
+
+def conv2d_bwd_data(dy, dy_c0, w, dx, dx_c0, cin, k, s, p, accumulate=False):
+    n, cdx, h, wd = dx.shape
+    o = w.shape[0]
+    ho, wo = dy.shape[2], dy.shape[3]
+    call("dbm_conv2d_bwd_data_f32", _ptr(dy, dy_c0 * ho * wo), dy.shape[1] * ho * wo, w.data_ptr(),
+         _ptr(dx, dx_c0 * h * wd), cdx * h * wd, n, cin, h, wd, o, k, s, p, int(accumulate), stream())
+
+
+def conv2d_bwd_weight(x, x_c0, cin, dy, dy_c0, dw, k, s, p, db=None):
+    """dw += x (*) dy ; db += sum dy."""
+    n, cx, h, wd = x.shape
+    o = dw.shape[0]
+    ho, wo = dy.shape[2], dy.shape[3]
+    call("dbm_conv2d_bwd_weight_f32", _ptr(x, x_c0 * h * wd), cx * h * wd, _ptr(dy, dy_c0 * ho * wo),
+         dy.shape[1] * ho * wo, dw.data_ptr(), n, cin, h, wd, o, k, s, p, stream())
+    if db is not None:
+        call("dbm_bias_grad_f32", _ptr(dy, dy_c0 * ho * wo), dy.shape[1] * ho * wo, db.data_ptr(), n, o, ho * wo, stream())
+
+
+def gemm(a, lda_m, lda_k, a_bs, b, ldb_k, ldb_n, b_bs, c, ldc_m, ldc_n, c_bs, bias, m, n, k, batch=1, act=False,
+         accumulate=0):
+    call("dbm_gemm_f32", a.data_ptr(), lda_m, lda_k, a_bs, b.data_ptr(), ldb_k, ldb_n, b_bs, c.data_ptr(), ldc_m,
+         ldc_n, c_bs, bias.data_ptr() if bias is not None else None, m, n, k, batch, int(act), accumulate, stream())
+
+
+def axpby(x, x_c0, y, y_c0, out, out_c0, channels, a, b):
+    """out[:, out_c0:+channels] = a * x[:, x_c0:+channels] + b * y[:, y_c0:+channels] (y may be None)."""
+    n = x.shape[0]
+    hw = x.shape[2] * x.shape[3]
+    call("dbm_axpby_f32", _ptr(x, x_c0 * hw), x.shape[1] * hw, _ptr(y, y_c0 * hw) if y is not None else None,
+         (y.shape[1] * hw) if y is not None else 0, _ptr(out, out_c0 * hw), out.shape[1] * hw, float(a), float(b), n,
+         channels * hw, stream())
+
+
+def lrelu_bwd(dy, dy_c0, y, y_c0, dx, dx_c0, channels, accumulate=False):
+    n = dy.shape[0]
+    hw = dy.shape[2] * dy.shape[3] if dy.dim() == 4 else 1
+    call("dbm_lrelu_bwd_f32", _ptr(dy, dy_c0 * hw), dy.shape[1] * hw, _ptr(y, y_c0 * hw), y.shape[1] * hw,
+         _ptr(dx, dx_c0 * hw), dx.shape[1] * hw, n, channels * hw, int(accumulate), stream())
+
+
+def upsample2_fwd(x):
+    n, c, h, w = x.shape
+    y = empty(n, c, 2 * h, 2 * w)
+    call("dbm_upsample2_fwd_f32", x.data_ptr(), y.data_ptr(), n * c, h, w, stream())
+    return y
+
+
+def upsample2_bwd(dy):
+    n, c, h2, w2 = dy.shape
+    dx = empty(n, c, h2 // 2, w2 // 2)
+    call("dbm_upsample2_bwd_f32", dy.data_ptr(), dx.data_ptr(), n * c, h2 // 2, w2 // 2, stream())
+    return dx
+
+
+# ---- layouts for the tensor-core path ---------------------------------------------------------
+def nchw_to_slab8(src, dst, dst_cs0=0):
+    n, c, h, w = src.shape
+    call("dbm_nchw_to_slab8", src.data_ptr(), 0, dst.data_ptr(), n, c, h, w, dst.shape[1], dst_cs0, stream())
+
+
+def slab8_to_nchw(src, c, src_cs0=0):
+    n, cs, h, w, _ = src.shape
+    dst = empty(n, c, h, w)
+    call("dbm_slab8_to_nchw", src.data_ptr(), cs, src_cs0, dst.data_ptr(), 0, n, c, h, w, stream())
+    return dst
+
+
+def nchw_to_slab4(src):
+    n, c, h, w = src.shape
+    dst = empty(n, c // 4, h, w, 4)
+    call("dbm_nchw_to_slab4", src.data_ptr(), 0, dst.data_ptr(), n, c, h, w, stream())
+    return dst
+
+
+def slab4_to_nchw(src, c_keep):
+    n, cs, h, w, _ = src.shape
+    dst = empty(n, c_keep, h, w)
+    call("dbm_slab4_to_nchw", src.data_ptr(), dst.data_ptr(), 0, n, cs * 4, c_keep, h, w, stream())
+    return dst
+
+
+def pack_conv3x3(w, cout_padded):
+    o, cin = w.shape[0], w.shape[1]
+    packed = empty(9 * cin * cout_padded, dtype=torch.bfloat16)
+    call("dbm_pack_conv3x3_weights", w.data_ptr(), packed.data_ptr(), o, cin, cout_padded, stream())
+    return packed
+
+
+def conv3x3_umma(inp, cin, wpacked, bias, cout_padded, *, beta=0.0, act=False, up2=False, out=None, out_cs0=0,
+                 out_f32=None, out_f32_cs0=0, res1=None, res2=None):
+    """tcgen05 implicit-GEMM 3x3 conv on slab8 bf16 input (N, CS, H, W, 8)."""
+    n, cs, h, w, _ = inp.shape
+    call("dbm_conv3x3_umma", inp.data_ptr(), cs, cin, wpacked.data_ptr(), bias.data_ptr(), cout_padded, n, h, w,
+         float(beta), int(act), int(up2),
+         out.data_ptr() if out is not None else None, out.shape[1] if out is not None else 0, out_cs0,
+         out_f32.data_ptr() if out_f32 is not None else None, out_f32.shape[1] if out_f32 is not None else 0,
+         out_f32_cs0, res1.data_ptr() if res1 is not None else None, res2.data_ptr() if res2 is not None else None,
+         stream())
+
+
+# ---- deformable conv (fp32 path) -----------------------------------------------------------------
+def deform_conv_fwd(x, offset, w, b, act=False):
+    """x (N,C,H,W), offset (N,18,H,W), w (O,C,3,3) -> y (N,O,H,W), cols (N, C*9, H*W) kept for backward."""
+    n, c, h, wd = x.shape
+    o = w.shape[0]
+    hw = h * wd
+    cols = empty(n, c * 9, hw)
+    call("dbm_deform_sample_f32", x.data_ptr(), offset.data_ptr(), cols.data_ptr(), n, c, h, wd, stream())
+    y = empty(n, o, h, wd)
+    k = c * 9
+    # per image: y[o, p] = sum_k cols[k, p] * w[o, k]   (M = pixels, N = O)
+    gemm(cols, 1, hw, k * hw, w, 1, k, 0, y, 1, hw, o * hw, b, hw, o, k, batch=n, act=act)
+    return y, cols
+
+
+def deform_conv_bwd(x, offset, w, cols, dy, dw, db, dx):
+    """Accumulates dw, db; dx += d/dx; returns doffset (N,18,H,W)."""
+    n, c, h, wd = x.shape
+    o = w.shape[0]
+    hw = h * wd
+    k = c * 9
+    # dw[o, kk] += sum_{n,p} dy[n,o,p] * cols[n,kk,p]   (atomic across the batch)
+    gemm(dy, hw, 1, o * hw, cols, 1, hw, k * hw, dw, k, 1, 0, None, o, k, hw, batch=n, accumulate=2)
+    call("dbm_bias_grad_f32", dy.data_ptr(), o * hw, db.data_ptr(), n, o, hw, stream())
+    # dcols[n, kk, p] = sum_o w[o, kk] * dy[n, o, p]
+    dcols = empty(n, k, hw)
+    gemm(dy, 1, hw, o * hw, w, k, 1, 0, dcols, 1, hw, k * hw, None, hw, k, o, batch=n)
+    doff = empty(n, 18, h, wd)
+    call("dbm_deform_bwd_f32", x.data_ptr(), offset.data_ptr(), dcols.data_ptr(),
+         dx.data_ptr() if dx is not None else None, doff.data_ptr(), n, c, h, wd, stream())
+    return doff

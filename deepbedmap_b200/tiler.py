@@ -1,0 +1,135 @@
+"""Tiled whole-continent predictor (deepbedmap.py:681-740), tiles sharded over GPUs.
+
+Tile geometry is reproduced exactly (it is semantics: the crop borders decide where the trunk's
+zero padding falls): 18 x 22 output tiles of 1000 x 1000 px, each predicted from a lowres crop
+with an 18+1 px halo, the outer 72 px of every prediction cropped, the canvas pre-filled with NaN.
+
+B200 design: the four continent grids (10.9 GB) are uploaded ONCE and stay resident in HBM
+(the reference re-uploads 14.4 GB of overlapping crops); crop + clip>=0 (deepbedmap.py:663-665,
+715-722) is one small kernel per input, same-shape tiles are batched through the generator, and
+predictions are placed on a device-resident canvas that is read back once.  With
+torch.distributed initialised, tiles are dealt round-robin to ranks and gathered on rank 0 (the
+only collective).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .model import GeneratorModel, as_device
+
+
+def tile_plan(final_shape=(18000, 22000), ary_shape=(1000, 1000), stride=(1000, 1000), xtrapad=(18, 18)):
+    """(y0, y1, x0, x1, ys, ye, xs, xe) per tile, in the reference's order (deepbedmap.py:700-732)."""
+    plan = []
+    for sy in range(0, final_shape[0], stride[0]):
+        for sx in range(0, final_shape[1], stride[1]):
+            y0 = max(0, (sy // 4) - xtrapad[0] - 1)
+            y1 = min(final_shape[0] // 4, ((sy + ary_shape[0]) // 4) + xtrapad[0] + 1)
+            x0 = max(0, (sx // 4) - xtrapad[1] - 1)
+            x1 = min(final_shape[1] // 4, ((sx + ary_shape[1]) // 4) + xtrapad[1] + 1)
+            plan.append((y0, y1, x0, x1, (y0 + xtrapad[0] + 1) * 4, (y1 - xtrapad[0] - 1) * 4,
+                         (x0 + xtrapad[1] + 1) * 4, (x1 - xtrapad[1] - 1) * 4))
+    return plan
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+class ContinentGrids:
+    """The four input rasters resident on the device: X (1,1,H,W), W1 (1,1,10H,10W), W2 (1,2,2H,2W),
+    W3 (1,1,H,W); the reference's shapes are 4502x5502 etc. (deepbedmap.ipynb:1519)."""
+
+    def __init__(self, X, W1, W2, W3):
+        self.X, self.W1, self.W2, self.W3 = (as_device(a) for a in (X, W1, W2, W3))
+        for a, c in ((self.X, 1), (self.W1, 1), (self.W2, 2), (self.W3, 1)):
+            if a.dim() != 4 or a.shape[0] != 1 or a.shape[1] != c:
+                raise ValueError(f"continent grids must be (1,C,H,W); got {tuple(a.shape)}")
+
+
+def predict_continent(model: GeneratorModel, X, W1, W2, W3, final_shape=(18000, 22000), ary_shape=(1000, 1000),
+                      stride=(1000, 1000), xtrapad=(18, 18), batch_tiles: int = 2, to_host: bool = True,
+                      grids: Optional[ContinentGrids] = None):
+    """Returns Y_hat (1, final_y, final_x) float32 (NumPy if ``to_host`` else a CUDA tensor), NaN
+    where the reference leaves NaN. On ranks != 0 of a distributed run returns None."""
+    dist, rank, world = _dist()
+    g = grids if grids is not None else ContinentGrids(X, W1, W2, W3)
+    Hs, Ws = g.X.shape[2], g.X.shape[3]
+    if tuple(g.W1.shape[2:]) != (10 * Hs, 10 * Ws) or tuple(g.W2.shape[2:]) != (2 * Hs, 2 * Ws) or \
+            tuple(g.W3.shape[2:]) != (Hs, Ws):
+        raise ValueError("W1/W2/W3 must be 10x/2x/1x the BEDMAP2 grid")
+    plan = tile_plan(final_shape, ary_shape, stride, xtrapad)
+    for (y0, y1, x0, x1, *_r) in plan:
+        if y1 > Hs or x1 > Ws:
+            raise ValueError("final_shape exceeds the input grids")
+    mine = [(i, t) for i, t in enumerate(plan) if i % world == rank]
+    groups: "OrderedDict[Tuple[int, int], List]" = OrderedDict()
+    for i, t in mine:
+        groups.setdefault((t[1] - t[0], t[3] - t[2]), []).append((i, t))
+    py, px = xtrapad[0] * 4, xtrapad[1] * 4
+    single = world == 1
+    if single:
+        canvas = ops.empty(final_shape[0], final_shape[1])
+        ops.fill(canvas, float("nan"))
+        results = None
+    else:
+        # per-rank result stack, gathered on rank 0 at the end
+        per_rank = (len(plan) + world - 1) // world
+        results = ops.empty(per_rank, ary_shape[0], ary_shape[1])
+        ops.fill(results, float("nan"))
+    st = ops.stream
+    for (h, w), tiles in groups.items():
+        for b0 in range(0, len(tiles), batch_tiles):
+            chunk = tiles[b0:b0 + batch_tiles]
+            nb = len(chunk)
+            xb = ops.empty(nb, 1, h, w)
+            w1b = ops.empty(nb, 1, 10 * h, 10 * w)
+            w2b = ops.empty(nb, 2, 2 * h, 2 * w)
+            w3b = ops.empty(nb, 1, h, w)
+            for j, (_, (y0, y1, x0, x1, *_r)) in enumerate(chunk):
+                ops.call("dbm_crop_clip_f32", g.X.data_ptr(), Hs, Ws, xb[j].data_ptr(), 1, y0, x0, h, w, 0, st())
+                ops.call("dbm_crop_clip_f32", g.W1.data_ptr(), 10 * Hs, 10 * Ws, w1b[j].data_ptr(), 1, 10 * y0, 10 * x0,
+                         10 * h, 10 * w, 1, st())
+                ops.call("dbm_crop_clip_f32", g.W2.data_ptr(), 2 * Hs, 2 * Ws, w2b[j].data_ptr(), 2, 2 * y0, 2 * x0,
+                         2 * h, 2 * w, 1, st())
+                ops.call("dbm_crop_clip_f32", g.W3.data_ptr(), Hs, Ws, w3b[j].data_ptr(), 1, y0, x0, h, w, 1, st())
+            y = model.forward(xb, w1b, w2b, w3b).array  # (nb, 1, 4(h-2), 4(w-2))
+            th, tw = y.shape[2], y.shape[3]
+            for j, (i, (y0, y1, x0, x1, ys, ye, xs, xe)) in enumerate(chunk):
+                hh, ww = ye - ys, xe - xs
+                # the reference assigns Y_pred[72:-72, 72:-72] into Y_hat[ys:ye, xs:xe] and raises
+                # ValueError on a shape mismatch (deepbedmap.py:734-738)
+                if (th - 2 * py, tw - 2 * px) != (hh, ww):
+                    raise ValueError(f"could not broadcast tile {(th - 2 * py, tw - 2 * px)} into {(hh, ww)}")
+                if single:
+                    ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, canvas.data_ptr(), final_shape[0],
+                             final_shape[1], ys, xs, hh, ww, st())
+                else:
+                    slot = i // world
+                    ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, results[slot].data_ptr(),
+                             ary_shape[0], ary_shape[1], 0, 0, hh, ww, st())
+            del y, xb, w1b, w2b, w3b
+    if single:
+        out = canvas.view(1, final_shape[0], final_shape[1])
+        return out.cpu().numpy() if to_host else out
+    # ---- the only collective: gather result stacks on rank 0 ----
+    gathered = [torch.empty_like(results) for _ in range(world)] if rank == 0 else None
+    dist.gather(results, gathered, dst=0)
+    if rank != 0:
+        return None
+    canvas = ops.empty(final_shape[0], final_shape[1])
+    ops.fill(canvas, float("nan"))
+    for i, (y0, y1, x0, x1, ys, ye, xs, xe) in enumerate(plan):
+        src = gathered[i % world][i // world]
+        ops.call("dbm_place_tile_f32", src.data_ptr(), ary_shape[0], ary_shape[1], 0, 0, canvas.data_ptr(),
+                 final_shape[0], final_shape[1], ys, xs, ye - ys, xe - xs, st())
+    out = canvas.view(1, final_shape[0], final_shape[1])
+    return out.cpu().numpy() if to_host else out

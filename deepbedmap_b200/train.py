@@ -1,0 +1,205 @@
+"""Training step with the reference's function surface (srgan_train.py:1014-1329):
+compile_srgan_model, train_eval_discriminator, train_eval_generator, trainer.
+
+Data parallelism (new; the reference is single-GPU): when torch.distributed is initialised the
+flat gradient buffer of the model being trained is all-reduced (NCCL over NVLink, averaged over
+ranks) between backward and the Adam update. BatchNorm statistics and the RaGAN batch means stay
+local to each rank, so world_size == 1 reproduces the reference exactly.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .model import DiscriminatorModel, GeneratorModel, Variable, as_device
+
+
+class Adam:
+    """chainer.optimizers.Adam(alpha, beta1=0.9, beta2=0.999, eps=1e-8).setup(link)
+    (srgan_train.py:1043-1048); one fused kernel over the link's flat parameter buffer."""
+
+    def __init__(self, alpha: float = 1.6e-4, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8):
+        self.alpha, self.beta1, self.beta2, self.eps = alpha, beta1, beta2, eps
+        self.t = 0
+        self.target = None
+
+    def setup(self, link):
+        self.target = link
+        self.m = ops.zeros(link.flat.numel())
+        self.v = ops.zeros(link.flat.numel())
+        return self
+
+    def update(self, grad_scale: float = 1.0):
+        link = self.target
+        self.t += 1
+        ops.call("dbm_adam_step_f32", link.flat.data_ptr(), link.flat_grad.data_ptr(), self.m.data_ptr(),
+                 self.v.data_ptr(), link.flat.numel(), self.alpha, self.beta1, self.beta2, self.eps, self.t,
+                 float(grad_scale), ops.stream())
+        link.mark_updated()
+
+
+def allreduce_grads(link) -> float:
+    """Sum the flat gradient over ranks (async NCCL op on the current stream); returns the
+    scale (1/world_size) the optimizer applies."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(link.flat_grad, op=dist.ReduceOp.SUM)
+        return 1.0 / dist.get_world_size()
+    return 1.0
+
+
+def compile_srgan_model(num_residual_blocks: int = 12, residual_scaling: float = 0.1,
+                        learning_rate: float = 1.6e-4, seed: int = 0):
+    """srgan_train.py:1014-1055: returns (g_model, g_optimizer, d_model, d_optimizer)."""
+    g = GeneratorModel(num_residual_blocks=num_residual_blocks, residual_scaling=residual_scaling, seed=seed)
+    d = DiscriminatorModel(seed=seed + 1)
+    g_opt = Adam(alpha=learning_rate, eps=1e-8).setup(g)
+    d_opt = Adam(alpha=learning_rate, eps=1e-8).setup(d)
+    return g, g_opt, d, d_opt
+
+
+def _ragan(real_pred, fake_pred, t_rmf, t_fmr, want_grads, grad_scale=1.0):
+    n = real_pred.shape[0]
+    out = ops.empty(2)
+    d_real = ops.empty(n, 1) if want_grads else None
+    d_fake = ops.empty(n, 1) if want_grads else None
+    ops.call("dbm_ragan_loss_f32", real_pred.data_ptr(), fake_pred.data_ptr(), n, float(t_rmf), float(t_fmr),
+             float(grad_scale), out.data_ptr(), d_real.data_ptr() if want_grads else None,
+             d_fake.data_ptr() if want_grads else None, ops.stream())
+    return out, d_real, d_fake
+
+
+def train_eval_discriminator(input_arrays: Dict[str, object], g_model: GeneratorModel, d_model: DiscriminatorModel,
+                             d_optimizer: Optional[Adam] = None, train: bool = True):
+    """srgan_train.py:1084-1166 -> (d_loss, d_accu)."""
+    if train:
+        assert d_optimizer is not None  # :1127
+    fake = g_model.forward(x=input_arrays["X"], w1=input_arrays["W1"], w2=input_arrays["W2"],
+                           w3=input_arrays["W3"]).array                         # :1131-1137 (no graph)
+    real = as_device(input_arrays["Y"])
+    if train:
+        d_model.cleargrads()                                                       # :1162
+    # two separate passes with their own batch statistics, real first (:1145-1146)
+    real_pred = d_model.forward(real, train=train, save=train).array
+    ctx_real = d_model._ctx
+    fake_pred = d_model.forward(fake, train=train, save=train).array
+    ctx_fake = d_model._ctx
+    out, d_real, d_fake = _ragan(real_pred, fake_pred, 1.0, 0.0, want_grads=train)  # :1149-1158
+    if train:
+        d_model._ctx = ctx_fake
+        d_model.backward(d_fake)                                                   # :1163
+        d_model._ctx = ctx_real
+        d_model.backward(d_real)
+        scale = allreduce_grads(d_model)
+        d_optimizer.update(grad_scale=scale)                                       # :1164
+    d_model._ctx = None
+    res = out.cpu()                                                                # :1166 (host sync)
+    return float(res[0]), float(res[1])
+
+
+def train_eval_generator(input_arrays: Dict[str, object], g_model: GeneratorModel, d_model: DiscriminatorModel,
+                         g_optimizer: Optional[Adam] = None, train: bool = True,
+                         content_loss_weighting: float = 1e-2, adversarial_loss_weighting: float = 2e-2,
+                         topographic_loss_weighting: float = 2e-3, structural_loss_weighting: float = 5.25):
+    """srgan_train.py:1170-1263 -> (g_loss, g_psnr, g_ssim)."""
+    if train:
+        assert g_optimizer is not None  # :1218
+    X = as_device(input_arrays["X"])
+    if train:
+        fake = g_model.forward_train(X, input_arrays["W1"], input_arrays["W2"], input_arrays["W3"]).array
+    else:
+        fake = g_model.forward(X, input_arrays["W1"], input_arrays["W2"], input_arrays["W3"]).array
+    # eval-mode BatchNorm and `.array`: the adversarial term carries no gradient (:1228-1229)
+    fake_labels = d_model.forward(fake, train=False).array
+    real = as_device(input_arrays["Y"])
+    if tuple(real.shape) != tuple(fake.shape):
+        raise ValueError("Input images must have the same dimensions.")            # :950-951
+    n, _, H, W = fake.shape
+    real_labels = ops.empty(n, 1)
+    ops.fill(real_labels, 1.0)                                                     # :1233
+    # adversarial: calculate_discriminator_loss(real=real_labels, fake=fake_labels, rmf=0, fmr=1) (:874-879)
+    adv, _, _ = _ragan(real_labels, fake_labels, 0.0, 1.0, want_grads=False)
+    # x_topo = X[:, :, 1:-1, 1:-1] (:1248)
+    h, w = X.shape[2], X.shape[3]
+    x_topo = ops.empty(n, 1, h - 2, w - 2)
+    ops.call("dbm_crop_clip_f32", X.data_ptr(), h, w, x_topo.data_ptr(), n, 1, 1, h - 2, w - 2, 0, ops.stream())
+    if (h - 2) * 4 != H or (w - 2) * 4 != W:
+        raise ValueError("x_topo does not match the 4x4 average-pooled prediction")
+    sums = ops.empty(4)
+    dy = ops.empty(n, 1, H, W) if train else None
+    ops.call("dbm_gen_image_loss_f32", fake.data_ptr(), real.data_ptr(), x_topo.data_ptr(), n, H, W,
+             content_loss_weighting, topographic_loss_weighting, structural_loss_weighting, sums.data_ptr(),
+             dy.data_ptr() if train else None, ops.stream())
+    if train:
+        g_model.cleargrads()                                                       # :1255
+        g_model.backward(dy)                                                       # :1256
+        scale = allreduce_grads(g_model)
+        g_optimizer.update(grad_scale=scale)                                       # :1257
+    s = sums.cpu().double().numpy()                                                # host sync (:1259-1263)
+    adv_v = float(adv.cpu()[0])
+    npx = n * H * W
+    content = s[0] / npx
+    topo = s[1] / (n * (H // 4) * (W // 4))
+    ssim = s[2] / (n * (H - 8) * (W - 8))
+    mse = s[3] / npx
+    g_loss = (content_loss_weighting * content + adversarial_loss_weighting * adv_v
+              + topographic_loss_weighting * topo + structural_loss_weighting * (1.0 - ssim))
+    with np.errstate(divide="ignore"):
+        g_psnr = float(20.0 * np.log10(2.0 ** 32 / np.sqrt(mse)))                  # :906-928
+    return float(g_loss), g_psnr, float(ssim)
+
+
+def trainer(i: int, columns: list, train_iter, dev_iter, g_model, g_optimizer, d_model, d_optimizer):
+    """srgan_train.py:1267-1329. ``train_iter`` / ``dev_iter`` are objects with ``.epoch`` and
+    ``.next()`` returning a dict of batched arrays {X, W1, W2, W3, Y}."""
+    metrics = {mn: [] for mn in columns}
+    while i == train_iter.epoch:
+        arrays = train_iter.next()
+        dl, da = train_eval_discriminator(arrays, g_model, d_model, d_optimizer)
+        metrics["discriminator_loss"].append(dl)
+        metrics["discriminator_accu"].append(da)
+        gl, gp, gs = train_eval_generator(arrays, g_model, d_model, g_optimizer)
+        metrics["generator_loss"].append(gl)
+        metrics["generator_psnr"].append(gp)
+        metrics["generator_ssim"].append(gs)
+    while i == dev_iter.epoch:
+        arrays = dev_iter.next()
+        dl, da = train_eval_discriminator(arrays, g_model, d_model, train=False)
+        metrics["val_discriminator_loss"].append(dl)
+        metrics["val_discriminator_accu"].append(da)
+        gl, gp, gs = train_eval_generator(arrays, g_model, d_model, train=False)
+        metrics["val_generator_loss"].append(gl)
+        metrics["val_generator_psnr"].append(gp)
+        metrics["val_generator_ssim"].append(gs)
+    return metrics
+
+
+class ArrayIterator:
+    """Minimal SerialIterator stand-in (chainer.iterators.SerialIterator as used at
+    srgan_train.py:132-166): batches a dict of equally long arrays, counts epochs."""
+
+    def __init__(self, arrays: Dict[str, np.ndarray], batch_size: int, shuffle: bool = True, seed: int = 42):
+        self.arrays = arrays
+        self.n = len(next(iter(arrays.values())))
+        self.batch_size = batch_size
+        self.rng = np.random.RandomState(seed)
+        self.shuffle = shuffle
+        self.epoch = 0
+        self._order = self._new_order()
+        self._pos = 0
+
+    def _new_order(self):
+        return self.rng.permutation(self.n) if self.shuffle else np.arange(self.n)
+
+    def next(self):
+        idx = self._order[self._pos:self._pos + self.batch_size]
+        self._pos += self.batch_size
+        if self._pos >= self.n:
+            self.epoch += 1
+            self._pos = 0
+            self._order = self._new_order()
+        return {k: v[idx] for k, v in self.arrays.items()}

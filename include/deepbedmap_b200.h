@@ -1,0 +1,147 @@
+/*
+ * deepbedmap_b200 -- C ABI of the B200-native ESRGAN hot path of weiji14/deepbedmap.
+ *
+ * The reference has no FFI: its hot path is a Python/Chainer class surface
+ * (GeneratorModel / DiscriminatorModel / loss + step functions in srgan_train.py, the tiler in
+ * deepbedmap.py) whose arithmetic is executed by Chainer function nodes. Each entry point
+ * below is the drop-in for one group of those nodes; the Python shim in deepbedmap_b200/
+ * (model.py, train.py, tiler.py) composes them with the reference's own call surface.
+ * See INTEGRATION.md for the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 (DBM_OK) or a negative status; dbm_last_error() gives the text;
+ *     no exceptions cross the ABI;
+ *   - all pointers are DEVICE pointers owned by the caller unless named host_*; no allocation
+ *     happens inside the library; all work is enqueued on the caller's `stream`;
+ *   - tensors at the boundary are float32, NCHW, C-contiguous (Chainer layout). A
+ *     `*_batch_stride` argument (elements; 0 = dense) lets a call read or write a channel slice
+ *     of a wider NCHW buffer, which is how F.concat (srgan_train.py:341-353) is realised
+ *     without copies;
+ *   - "slab8" = bf16 [N][C/8][H][W][8], "slab4" = fp32 [N][C/4][H][W][4]: the tensor-core
+ *     path's internal HBM layouts (one 16-byte vector per pixel per slab).
+ */
+#ifndef DEEPBEDMAP_B200_H_
+#define DEEPBEDMAP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define DBM_OK 0
+#define DBM_ERR_INVALID (-1)
+#define DBM_ERR_CUDA (-2)
+
+int dbm_version(void);
+const char* dbm_last_error(void);
+int dbm_debug_set(int key, int value);
+
+/* ---- fp32 convolution family -------------------------------------------------------------
+ * L.Convolution2D forward (+ optional fused F.leaky_relu(slope=0.2)):
+ *   srgan_train.py:223-254 (stem: k3s1p0, k30s10p0, k6s2p0), :292-331, :467-503 (k3s1p1),
+ *   :617-634 (discriminator: k3s1p1, k4s2p1). Supported (ksize, stride): (3,1) (4,2) (6,2) (30,10).
+ * The two gradient entry points replace Chainer's autograd of the same link
+ * (d_loss.backward() / g_loss.backward(), srgan_train.py:1163, 1256). */
+int dbm_conv2d_fwd_f32(const float* x, long x_batch_stride, const float* w, const float* bias, float* y,
+                       long y_batch_stride, int n, int c, int h, int wd, int o, int ksize, int stride, int pad,
+                       int act, cudaStream_t stream);
+int dbm_conv2d_bwd_data_f32(const float* dy, long y_batch_stride, const float* w, float* dx, long x_batch_stride,
+                            int n, int c, int h, int wd, int o, int ksize, int stride, int pad, int accumulate,
+                            cudaStream_t stream);
+/* dw += ...  (caller zeroes the gradient buffer once per step: Link.cleargrads(), :1162, 1255) */
+int dbm_conv2d_bwd_weight_f32(const float* x, long x_batch_stride, const float* dy, long y_batch_stride, float* dw,
+                              int n, int c, int h, int wd, int o, int ksize, int stride, int pad,
+                              cudaStream_t stream);
+int dbm_bias_grad_f32(const float* dy, long dy_batch_stride, float* db, int n, int o, int hw, cudaStream_t stream);
+
+/* Batched strided GEMM: L.Linear (srgan_train.py:646-647, 694-696), the filter contraction of the
+ * deformable convolution, and their gradients. accumulate: 0 overwrite, 1 +=, 2 atomicAdd. */
+int dbm_gemm_f32(const float* a, long lda_m, long lda_k, long a_batch_stride, const float* b, long ldb_k, long ldb_n,
+                 long b_batch_stride, float* c, long ldc_m, long ldc_n, long c_batch_stride, const float* bias, int m,
+                 int n, int k, int batch, int act, int accumulate, cudaStream_t stream);
+
+/* ---- element-wise / layout ------------------------------------------------------------------ */
+/* out = a*x + b*y on (batch, inner) views: F.add(a5 * residual_scaling, a0), srgan_train.py:358, 402, 551 */
+int dbm_axpby_f32(const float* x, long x_bs, const float* y, long y_bs, float* out, long out_bs, float a, float b,
+                  int nbatch, long inner, cudaStream_t stream);
+int dbm_lrelu_fwd_f32(const float* x, float* y, long total, cudaStream_t stream);
+/* backward of F.leaky_relu given its output y: dx (+)= dy * (y >= 0 ? 1 : 0.2) */
+int dbm_lrelu_bwd_f32(const float* dy, long dy_bs, const float* y, long y_bs, float* dx, long dx_bs, int nbatch,
+                      long inner, int accumulate, cudaStream_t stream);
+/* F.resize_images(mode="nearest") to 2x (srgan_train.py:556-566) and its adjoint */
+int dbm_upsample2_fwd_f32(const float* x, float* y, long planes, int h, int w, cudaStream_t stream);
+int dbm_upsample2_bwd_f32(const float* dy, float* dx, long planes, int h, int w, cudaStream_t stream);
+int dbm_fill_f32(float* p, float v, long n, cudaStream_t stream);
+int dbm_nchw_to_slab8(const float* src, long src_batch_stride, void* dst_slab8, int n, int c, int h, int w,
+                      int dst_cs_total, int dst_cs0, cudaStream_t stream);
+int dbm_slab8_to_nchw(const void* src_slab8, int src_cs_total, int src_cs0, float* dst, long dst_batch_stride, int n,
+                      int c, int h, int w, cudaStream_t stream);
+int dbm_nchw_to_slab4(const float* src, long src_batch_stride, float* dst_slab4, int n, int c, int h, int w,
+                      cudaStream_t stream);
+int dbm_slab4_to_nchw(const float* src_slab4, float* dst, long dst_batch_stride, int n, int c_slab, int c_keep, int h,
+                      int w, cudaStream_t stream);
+
+/* ---- tensor-core trunk: 3x3 'same' conv, tcgen05 implicit GEMM ---------------------------------
+ * Replaces L.Convolution2D(k3,s1,p1) + F.leaky_relu + F.concat + (x*beta, F.add) +
+ * F.resize_images(nearest) chains of srgan_train.py:339-358, 397-402, 541-568 and the
+ * offset_conv of L.DeformableConvolution2D (:506-523).
+ *   v = conv(in[:, :cin]) + bias;  if res1: v = res1 + beta*v;  if res2: v = res2 + beta*v;
+ *   if act: v = lrelu(v);  out_f32_slab4[.., cs0..] = v;  out_slab8[.., cs0..] = bf16(v)
+ *   (up2: every output pixel is written to its 2x2 nearest-neighbour block of a 2H x 2W map).
+ * cout_padded in {32, 64}; cin multiple of 32. Weights come from dbm_pack_conv3x3_weights. */
+int dbm_pack_conv3x3_weights(const float* w_oihw, void* packed_bf16, int cout, int cin, int cout_padded,
+                             cudaStream_t stream);
+int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void* wpacked, const float* bias,
+                     int cout_padded, int n, int h, int w, float beta, int act, int up2, void* out_slab8,
+                     int out_cs_total, int out_cs0, float* out_f32_slab4, int out_f32_cs_total, int out_f32_cs0,
+                     const float* res1_slab4, const float* res2_slab4, cudaStream_t stream);
+
+/* ---- deformable convolution, fp32 path (L.DeformableConvolution2D, srgan_train.py:506-523) -----
+ * cols[n][c*9+t][pixel] = bilinear sample; contraction with W (O, C*9) is a dbm_gemm_f32 call.
+ * offset: (N,18,H,W), channels [0:9] = dx, [9:18] = dy of tap t = ky*3+kx. */
+int dbm_deform_sample_f32(const float* x, const float* offset, float* cols, int n, int c, int h, int w,
+                          cudaStream_t stream);
+/* dx += scatter(dcols) (may be NULL), doffset = d/d(offset) */
+int dbm_deform_bwd_f32(const float* x, const float* offset, const float* dcols, float* dx, float* doffset, int n,
+                       int c, int h, int w, cudaStream_t stream);
+
+/* ---- discriminator normalisation (L.BatchNormalization + F.leaky_relu, srgan_train.py:636-689) - */
+int dbm_bn_lrelu_fwd_f32(const float* x, float* y, const float* gamma, const float* beta, float* avg_mean,
+                         float* avg_var, float* save_mean, float* save_invstd, int n, int c, int hw, float eps,
+                         float decay, int train, cudaStream_t stream);
+int dbm_bn_lrelu_bwd_f32(const float* x, const float* y, const float* dy, float* dx, const float* gamma,
+                         const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
+                         float* scratch2c, int n, int c, int hw, cudaStream_t stream);
+
+/* ---- losses (srgan_train.py:841-1009) -------------------------------------------------------- */
+/* out2[0] = RaGAN loss (calculate_discriminator_loss), out2[1] = F.binary_accuracy of
+ * [real; fake] against [1; 0]; d_real/d_fake (nullable) = grad_scale * dLoss/dlogit. */
+int dbm_ragan_loss_f32(const float* real_pred, const float* fake_pred, int n, float t_real_minus_fake,
+                       float t_fake_minus_real, float grad_scale, float* out2, float* d_real, float* d_fake,
+                       cudaStream_t stream);
+/* sums4 = {sum|yp-yt|, sum|avgpool4(yp)-x_topo|, sum ssim_map, sum (yp-yt)^2};
+ * dy (nullable) = d/dyp of w_content*L1 + w_topo*Topo + w_struct*(1 - SSIM). */
+int dbm_gen_image_loss_f32(const float* y_pred, const float* y_true, const float* x_topo, int n, int h, int w,
+                           float w_content, float w_topo, float w_struct, float* sums4, float* dy,
+                           cudaStream_t stream);
+
+/* ---- chainer.optimizers.Adam(alpha, beta1, beta2, eps) over a flat parameter buffer (:1043-1048) */
+int dbm_adam_step_f32(float* params, const float* grads, float* m, float* v, long n, float alpha, float beta1,
+                      float beta2, float eps, int t, float grad_scale, cudaStream_t stream);
+
+/* ---- continent tiler staging (deepbedmap.py:663-665, 715-722, 731-736) ------------------------- */
+int dbm_crop_clip_f32(const float* src, int hs, int ws, float* dst, int c, int y0, int x0, int h, int w, int clip0,
+                      cudaStream_t stream);
+int dbm_place_tile_f32(const float* tile, int th, int tw, int cy, int cx, float* canvas, int ch, int cw, int ys,
+                       int xs, int hh, int ww, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPBEDMAP_B200_H_ */

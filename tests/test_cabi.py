@@ -1,0 +1,78 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds/loads and exports every
+symbol include/deepbedmap_b200.h declares; host-side inventories agree with the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "deepbedmap_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dbm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from deepbedmap_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    # every declared entry point has a ctypes signature (and vice versa)
+    assert set(names) - {"dbm_last_error"} == set(_lib.SIGNATURES)
+    assert lib.dbm_version() >= 100
+
+
+def test_signature_arity_matches_header():
+    from deepbedmap_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "deepbedmap_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name, args in _lib.SIGNATURES.items():
+        m = re.search(r"\b%s\s*\((.*?)\)\s*;" % name, text, flags=re.S)
+        assert m, name
+        decl = m.group(1).strip()
+        n = 0 if decl in ("", "void") else decl.count(",") + 1
+        assert n == len(args), f"{name}: header has {n} args, ctypes table {len(args)}"
+
+
+def test_layout_matches_oracle_inventory():
+    from deepbedmap_b200 import layout
+    from oracle import deepbedmap_oracle as O
+    for nb in (1, 12):
+        assert list(layout.generator_shapes(nb).items()) == list(O.generator_param_shapes(nb).items())
+    assert list(layout.discriminator_shapes().items()) == list(O.discriminator_param_shapes().items())
+    assert sum(int(np.prod(s)) for s in layout.generator_shapes().values()) == 8907749
+    assert sum(int(np.prod(s)) for s in layout.discriminator_shapes().values()) == 10370761
+    assert layout.infer_num_residual_blocks(layout.generator_shapes(7)) == 7
+
+
+def test_tile_plan_matches_oracle():
+    from deepbedmap_b200.tiler import tile_plan
+    from oracle import deepbedmap_oracle as O
+    a = tile_plan()
+    b = O.tile_plan()
+    assert len(a) == len(b) == 396
+    for t, r in zip(a, b):
+        assert t[:4] == r[:4] and (t[4], t[5]) == (r[4].start, r[4].stop) and (t[6], t[7]) == (r[5].start, r[5].stop)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "deepbedmap_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "oracle" not in src, f"{f} references the oracle"
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from deepbedmap_b200 import GeneratorModel
+    with pytest.raises(RuntimeError):
+        GeneratorModel()

@@ -1,0 +1,199 @@
+"""Model-level GPU parity against the CPU oracle (fp64) on seeded synthetic inputs and weights.
+
+Tolerances (stated, per BASELINE.json north_star):
+  precision="fp32" (CUDA-core path)  : relative L2 <= 2e-5, i.e. float32 accumulation noise;
+  precision="bf16" (tcgen05 path)    : bf16 operands, fp32 accumulation, fp32 residual stream:
+                                        relative L2 <= 2e-2 and max-abs error <= 3e-2 * max|y|
+                                        (max-abs "bed elevation error" scales with the output range).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import deepbedmap_oracle as O  # noqa: E402  (test infrastructure)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+
+
+def make_generator(nb, precision, scale=1.0, bias_std=0.1, seed=0):
+    from deepbedmap_b200 import GeneratorModel
+    params = O.init_generator_params(nb, seed=seed, bias_std=bias_std, scale=scale)
+    m = GeneratorModel(num_residual_blocks=nb, residual_scaling=0.1, precision=precision)
+    for k, v in params.items():
+        m.set_param(k, v)
+    return m, params
+
+
+def test_counts_and_shapes():
+    from deepbedmap_b200 import DiscriminatorModel, GeneratorModel
+    g = GeneratorModel()
+    assert g.count_params() == 8907749                      # srgan_train.py:446-447
+    x, w1, w2, w3 = O.synthetic_inputs(1)
+    y = g.forward(x=x, w1=w1, w2=w2, w3=w3)
+    assert y.shape == (1, 1, 36, 36)                        # srgan_train.py:444-445
+    d = DiscriminatorModel()
+    assert d.count_params() == 10370761                     # srgan_train.py:607-608
+    assert d.forward(np.random.rand(2, 1, 36, 36).astype("float32")).shape == (2, 1)
+    with pytest.raises(ValueError):
+        g.forward(x, w1[:, :, :100], w2, w3)
+    with pytest.raises(ValueError):
+        d.forward(np.zeros((2, 1, 32, 32), np.float32))
+
+
+@pytest.mark.parametrize("regime", ["unit", "physical"])
+@pytest.mark.parametrize("nb,n,h,w", [(1, 2, 11, 11), (2, 1, 14, 9)])
+def test_generator_fp32_matches_oracle(regime, nb, n, h, w):
+    m, params = make_generator(nb, "fp32")
+    ins = O.synthetic_inputs(n, h, w, regime=regime)
+    ref = O.generator_forward_numpy(params, *ins, num_residual_blocks=nb)
+    got = m.forward(*ins).numpy()
+    assert got.shape == ref.shape == (n, 1, 4 * (h - 2), 4 * (w - 2))
+    assert rel_l2(got, ref) < 2e-5
+
+
+@pytest.mark.parametrize("regime", ["unit", "physical"])
+@pytest.mark.parametrize("nb,n,h,w", [(1, 2, 11, 11), (3, 1, 23, 30), (12, 2, 11, 11)])
+def test_generator_bf16_matches_oracle(regime, nb, n, h, w):
+    m, params = make_generator(nb, "bf16")
+    ins = O.synthetic_inputs(n, h, w, regime=regime)
+    ref = O.generator_forward_numpy(params, *ins, num_residual_blocks=nb)
+    got = m.forward(*ins).numpy()
+    err = rel_l2(got, ref)
+    maxabs = float(np.abs(got - ref).max())
+    print(f"bf16 nb={nb} {regime}: rel_l2={err:.3e} max_abs={maxabs:.3e} (output max {np.abs(ref).max():.3e})")
+    assert err < 2e-2
+    assert maxabs < 3e-2 * float(np.abs(ref).max())
+
+
+def test_generator_reference_init_scale():
+    """Reference initialisation (HeNormal scale 0.1, zero biases): outputs are tiny but must
+    still agree relatively."""
+    m, params = make_generator(12, "bf16", scale=0.1, bias_std=0.0)
+    ins = O.synthetic_inputs(1)
+    ref = O.generator_forward_numpy(params, *ins)
+    assert rel_l2(m.forward(*ins).numpy(), ref) < 2e-2
+
+
+def _load_disc(seed=1):
+    from deepbedmap_b200 import DiscriminatorModel
+    params = O.init_discriminator_params(seed=seed, bias_std=0.1, scale=1.0)
+    d = DiscriminatorModel()
+    for k in d.p:
+        d.set_param(k, params[k])
+    return d, params
+
+
+def test_discriminator_matches_oracle():
+    d, params = _load_disc()
+    x = np.random.RandomState(0).rand(6, 1, 36, 36).astype(np.float32)
+    p = O.to_torch(params)
+    stats = {}
+    ref = O.discriminator_forward(p, torch.as_tensor(x, dtype=torch.float64), train=True, stats_out=stats).numpy()
+    got = d.forward(x, train=True).numpy()
+    assert rel_l2(got, ref) < 5e-5
+    for k, v in stats.items():
+        assert rel_l2(d.persistent[k].cpu().numpy(), v.numpy()) < 1e-5
+    # eval mode uses the (just updated) running statistics
+    p.update(stats)
+    ref_eval = O.discriminator_forward(p, torch.as_tensor(x, dtype=torch.float64), train=False).numpy()
+    assert rel_l2(d.forward(x, train=False).numpy(), ref_eval) < 5e-5
+
+
+def test_training_step_matches_oracle():
+    """One D-step then one G-step (srgan_train.py:1286-1308) on a batch of 3, 1 RRDB: losses,
+    metrics, gradients and post-Adam weights against autograd on the fp64 oracle."""
+    from deepbedmap_b200 import train as T
+    nb = 1
+    g, gparams = make_generator(nb, "fp32", scale=1.0, bias_std=0.05)
+    d, dparams = _load_disc()
+    rng = np.random.RandomState(42)
+    n = 3
+    arrays = {"X": rng.rand(n, 1, 11, 11), "W1": rng.rand(n, 1, 110, 110), "W2": rng.rand(n, 2, 22, 22),
+              "W3": rng.rand(n, 1, 11, 11), "Y": rng.rand(n, 1, 36, 36)}
+    arrays = {k: v.astype(np.float32) for k, v in arrays.items()}
+    ta = {k: torch.as_tensor(v, dtype=torch.float64) for k, v in arrays.items()}
+    gp, dp = O.to_torch(gparams), O.to_torch(dparams)
+    g_opt_ref, d_opt_ref = O.ChainerAdam(1.6e-4), O.ChainerAdam(1.6e-4)
+    g_opt = T.Adam(1.6e-4).setup(g)
+    d_opt = T.Adam(1.6e-4).setup(d)
+
+    dl_ref, da_ref, dgrads = O.train_eval_discriminator(ta, gp, dp, d_opt_ref, num_residual_blocks=nb, return_grads=True)
+    d0 = d.flat.clone()
+    dl, da = T.train_eval_discriminator(arrays, g, d, d_opt)
+    assert abs(dl - dl_ref) < 1e-4 * max(1, abs(dl_ref)) and abs(da - da_ref) < 1e-6
+    for k in ("conv_layer0/W", "conv_layer5/W", "batch_norm3/gamma", "batch_norm9/beta", "linear_1/W", "linear_2/b"):
+        assert rel_l2(d.g[k].cpu().numpy(), dgrads[k].numpy()) < 2e-3, k
+    for k in ("conv_layer0/W", "conv_layer9/W", "linear_2/W"):
+        assert rel_l2((d.p[k] - d0[d._slices[k][0]:d._slices[k][0] + d._slices[k][1]].view_as(d.p[k])).cpu().numpy(),
+                      dp[k].numpy() - dparams[k]) < 5e-2, k
+    assert not torch.equal(d0, d.flat)                                         # srgan_train.py:1121-1122
+
+    gl_ref, gp_ref, gs_ref, ggrads = O.train_eval_generator(ta, gp, dp, g_opt_ref, num_residual_blocks=nb,
+                                                            return_grads=True)
+    g0 = g.flat.clone()
+    gl, gpsnr, gssim = T.train_eval_generator(arrays, g, d, g_opt)
+    assert abs(gl - gl_ref) < 1e-4 * max(1, abs(gl_ref))
+    assert abs(gpsnr - gp_ref) < 1e-3 and abs(gssim - gs_ref) < 1e-4
+    for k in ("final_conv_layer2/deform_conv/W", "final_conv_layer2/offset_conv/W", "final_conv_layer1/deform_conv/b",
+              "final_conv_layer1/offset_conv/W", "post_upsample_conv_layer_1/W", "post_residual_conv_layer/W",
+              "residual_network/0/residual_dense_block3/conv_layer5/W",
+              "residual_network/0/residual_dense_block1/conv_layer2/W", "pre_residual_conv_layer/W",
+              "input_block/conv_on_W1/W", "input_block/conv_on_W2/b"):
+        assert rel_l2(g.g[k].cpu().numpy(), ggrads[k].numpy()) < 2e-3, k
+    assert not torch.equal(g0, g.flat)                                         # srgan_train.py:1211-1212
+    # eval mode returns finite metrics and leaves the weights alone
+    g1 = g.flat.clone()
+    vals = T.train_eval_discriminator(arrays, g, d, train=False) + T.train_eval_generator(arrays, g, d, train=False)
+    assert all(np.isfinite(v) for v in vals) and torch.equal(g1, g.flat)
+
+
+def test_npz_roundtrip(tmp_path):
+    from deepbedmap_b200 import DiscriminatorModel, GeneratorModel
+    from deepbedmap_b200.npz import peek_num_residual_blocks
+    m, params = make_generator(2, "fp32")
+    f = tmp_path / "g.npz"
+    np.savez_compressed(f, **params)                        # file written in the Chainer key layout
+    assert peek_num_residual_blocks(f) == 2
+    m2 = GeneratorModel(num_residual_blocks=2, precision="fp32").load_npz(f)
+    assert torch.equal(m.flat, m2.flat)
+    with pytest.raises(KeyError):
+        GeneratorModel(num_residual_blocks=3, precision="fp32").load_npz(f)
+    m2.save_npz(tmp_path / "g2.npz")
+    with np.load(tmp_path / "g2.npz") as z:
+        assert set(z.files) == set(params) and all(np.array_equal(z[k], params[k]) for k in params)
+    d, dparams = _load_disc()
+    d.forward(np.random.rand(4, 1, 36, 36).astype(np.float32), train=True)
+    d.save_npz(tmp_path / "d.npz")
+    with np.load(tmp_path / "d.npz") as z:
+        assert len(z.files) == 60 and int(z["batch_norm1/N"]) == 1
+    d2 = DiscriminatorModel().load_npz(tmp_path / "d.npz")
+    assert torch.equal(d.flat, d2.flat) and torch.equal(d.persistent["batch_norm4/avg_var"],
+                                                        d2.persistent["batch_norm4/avg_var"])
+
+
+def test_tiled_predictor_matches_oracle_tiler():
+    """Reference tile geometry at reduced size: 3x3 tiles of 40x40 output px, halo 3+1."""
+    from deepbedmap_b200 import predict_continent
+    nb = 1
+    m, params = make_generator(nb, "fp32")
+    final, ary, pad = (120, 120), (40, 40), (3, 3)
+    H = W = 32
+    rng = np.random.RandomState(5)
+    X = rng.rand(1, 1, H, W).astype(np.float32)
+    W1 = (rng.rand(1, 1, 10 * H, 10 * W) - 0.3).astype(np.float32)     # negatives exercise the clip
+    W2 = (rng.rand(1, 2, 2 * H, 2 * W) - 0.3).astype(np.float32)
+    W3 = (rng.rand(1, 1, H, W) - 0.3).astype(np.float32)
+    got = predict_continent(m, X, W1, W2, W3, final_shape=final, ary_shape=ary, stride=ary, xtrapad=pad, batch_tiles=2)
+    fwd = lambda a, b, c, d: O.generator_forward_numpy(params, a, b, c, d, num_residual_blocks=nb)
+    ref = O.predict_continent(fwd, X, np.clip(W1, 0, None), np.clip(W2, 0, None), np.clip(W3, 0, None),
+                              final_shape=final, ary_shape=ary, stride=ary, xtrapad=pad)
+    assert got.shape == ref.shape == (1, 120, 120)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.isnan(ref).any()
+    ok = ~np.isnan(ref)
+    assert rel_l2(got[ok], ref[ok]) < 2e-5
