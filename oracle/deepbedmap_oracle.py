@@ -268,8 +268,59 @@ def deformable_layer(p: Params, name: str, x):
     return deformable_conv2d(x, off, p[f"{name}/deform_conv/W"], p[f"{name}/deform_conv/b"])
 
 
+def _q(t):
+    """Round to bfloat16 and back (emulates the tensor-core path's operand / storage rounding)."""
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
 def generator_forward(p: Params, x, w1, w2, w3, num_residual_blocks=12,
-                      residual_scaling=0.1, return_intermediates=False):
+                      residual_scaling=0.1, return_intermediates=False, emulate_bf16=False):
+    """GeneratorModel.forward, srgan_train.py:525-576.
+
+    ``emulate_bf16=True`` restates the SAME graph with the operand rounding of the product's
+    tcgen05 path (documented in DESIGN.md): 3x3-conv inputs and weights rounded to bf16, fp32
+    (here: wider) accumulation, fp32 bias / residual stream, dense-block features a1..a4 and the
+    upsample-conv outputs stored as bf16; stem and deformable sampling/contraction in fp32.
+    It exists so that the CUDA kernels can be checked tightly (accumulation order is then the only
+    difference) independently of how strongly a given weight set amplifies rounding noise.
+    """
+    if not emulate_bf16:
+        return _generator_forward_exact(p, x, w1, w2, w3, num_residual_blocks, residual_scaling,
+                                        return_intermediates)
+    beta = residual_scaling
+    q = _q
+
+    def conv(inp_q, name):  # inp_q already bf16-representable
+        return F.conv2d(inp_q, q(p[f"{name}/W"]), p[f"{name}/b"], padding=1)
+
+    a0 = input_block(p, x, w1, w2, w3)
+    a1 = _lrelu(conv(q(a0), "pre_residual_conv_layer"))          # fp32 master
+    cur = a1
+    for i in range(num_residual_blocks):
+        rrdb_in = cur
+        for r in (1, 2, 3):
+            pre = f"residual_network/{i}/residual_dense_block{r}"
+            feats = [q(cur)]
+            for k in (1, 2, 3, 4):
+                feats.append(q(_lrelu(conv(torch.cat(feats, dim=1), f"{pre}/conv_layer{k}"))))
+            a5 = conv(torch.cat(feats, dim=1), f"{pre}/conv_layer5")
+            cur = cur + beta * a5
+            if r == 3:
+                cur = rrdb_in + beta * cur
+    a3 = a1 + conv(q(cur), "post_residual_conv_layer")
+    u1 = upsample_nearest2(q(a3))
+    c1 = q(_lrelu(conv(u1, "post_upsample_conv_layer_1")))
+    c2 = q(_lrelu(conv(upsample_nearest2(c1), "post_upsample_conv_layer_2")))
+    off1 = conv(c2, "final_conv_layer1/offset_conv")
+    d1 = _lrelu(deformable_conv2d(c2, off1, p["final_conv_layer1/deform_conv/W"],
+                                  p["final_conv_layer1/deform_conv/b"]))
+    off2 = conv(q(d1), "final_conv_layer2/offset_conv")
+    return deformable_conv2d(d1, off2, p["final_conv_layer2/deform_conv/W"],
+                             p["final_conv_layer2/deform_conv/b"])
+
+
+def _generator_forward_exact(p: Params, x, w1, w2, w3, num_residual_blocks=12,
+                             residual_scaling=0.1, return_intermediates=False):
     """GeneratorModel.forward, srgan_train.py:525-576."""
     inter = {}
     a0 = input_block(p, x, w1, w2, w3)                                      # :537
@@ -565,12 +616,12 @@ def predict_continent(forward: Callable, X, W1, W2, W3, final_shape=(18000, 2200
 # Convenience wrappers used by tests / bench
 # --------------------------------------------------------------------------------------
 def generator_forward_numpy(params_np, x, w1, w2, w3, num_residual_blocks=12,
-                            residual_scaling=0.1, dtype=torch.float64) -> np.ndarray:
+                            residual_scaling=0.1, dtype=torch.float64, emulate_bf16=False) -> np.ndarray:
     p = to_torch(params_np, dtype)
     with torch.no_grad():
         y = generator_forward(p, *(torch.as_tensor(np.asarray(a)).to(dtype) for a in (x, w1, w2, w3)),
                               num_residual_blocks=num_residual_blocks,
-                              residual_scaling=residual_scaling)
+                              residual_scaling=residual_scaling, emulate_bf16=emulate_bf16)
     return y.numpy()
 
 
