@@ -1,0 +1,335 @@
+// Deformable 3x3 convolution for the tensor-core inference path
+// (L.DeformableConvolution2D, srgan_train.py:506-523, 572-574; semantics SURVEY App. B.6).
+//
+//   deform_umma_kernel  (64 -> 64): gather warps bilinearly sample the bf16 slab8 input at the
+//       offset-displaced tap positions straight into shared memory in the UMMA K-major
+//       core-matrix layout (no im2col buffer in HBM: Chainer materialises 3 GB per continent
+//       tile here); one thread issues tcgen05.mma against the SMEM-resident 576x64 filter;
+//       epilogue warps add bias, LeakyReLU and store bf16 slab8.
+//   deform_out1_kernel  (64 -> 1): the final layer is a 576-long dot product per pixel: CUDA
+//       cores, fp32 accumulation, fp32 NCHW output.
+#include "common.cuh"
+
+namespace dbm {
+
+constexpr int kDTileW = 16, kDTileH = 8;   // 128 output pixels per work item
+constexpr int kDStages = 4;
+constexpr int kDGatherThreads = 256;
+constexpr int kDThreads = kDGatherThreads + 32 + 128;  // + MMA warp + 4 epilogue warps
+constexpr int kDABytes = 128 * 64 * 2;                 // one tap: 128 px x 64 ch bf16
+constexpr int kDBBytes = 9 * 64 * 64 * 2;
+constexpr int kDSmem = kDBBytes + kDStages * kDABytes + 256 + 1024;
+
+struct DeformParams {
+  int N, H, W;
+  int tiles_x, tiles_y, num_items;
+  const __nv_bfloat16* x;       // slab8 [N][8][H][W][8]
+  const float* off;             // slab4 [N][off_cs][H][W][4], channels 0..17 used
+  int off_cs;
+  const __nv_bfloat16* wpacked; // [9][8][8][8][8]
+  const float* bias;
+  int act;
+  __nv_bfloat16* out;           // slab8 [N][out_cs_total][H][W][8] at slab offset out_cs0
+  int out_cs_total, out_cs0;
+};
+
+struct TapPos {
+  int x0, y0;
+  float w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ TapPos tap_pos(float dx, float dy, int x, int y, int tap, int H, int W) {
+  float px = (float)(x + (tap % 3) - 1) + dx;
+  float py = (float)(y + (tap / 3) - 1) + dy;
+  px = fminf(fmaxf(px, -2.f), (float)W + 1.f);
+  py = fminf(fmaxf(py, -2.f), (float)H + 1.f);
+  const float fx0 = floorf(px), fy0 = floorf(py);
+  const float fx = px - fx0, fy = py - fy0;
+  TapPos t;
+  t.x0 = (int)fx0; t.y0 = (int)fy0;
+  t.w00 = (1.f - fy) * (1.f - fx); t.w01 = (1.f - fy) * fx;
+  t.w10 = fy * (1.f - fx);         t.w11 = fy * fx;
+  return t;
+}
+
+__device__ __forceinline__ void fma8(float (&acc)[8], const uint4& v, float w) {
+  acc[0] = fmaf(w, __uint_as_float(v.x << 16), acc[0]);
+  acc[1] = fmaf(w, __uint_as_float(v.x & 0xffff0000u), acc[1]);
+  acc[2] = fmaf(w, __uint_as_float(v.y << 16), acc[2]);
+  acc[3] = fmaf(w, __uint_as_float(v.y & 0xffff0000u), acc[3]);
+  acc[4] = fmaf(w, __uint_as_float(v.z << 16), acc[4]);
+  acc[5] = fmaf(w, __uint_as_float(v.z & 0xffff0000u), acc[5]);
+  acc[6] = fmaf(w, __uint_as_float(v.w << 16), acc[6]);
+  acc[7] = fmaf(w, __uint_as_float(v.w & 0xffff0000u), acc[7]);
+}
+
+// bilinear sample of 8 channels (one slab) -> acc
+__device__ __forceinline__ void sample8(const __nv_bfloat16* __restrict__ plane, const TapPos& t, int H, int W,
+                                        float (&acc)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const bool y0ok = t.y0 >= 0 && t.y0 < H, y1ok = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+  const bool x0ok = t.x0 >= 0 && t.x0 < W, x1ok = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+  const uint4* p = reinterpret_cast<const uint4*>(plane);
+  if (y0ok && x0ok) fma8(acc, __ldg(p + (size_t)t.y0 * W + t.x0), t.w00);
+  if (y0ok && x1ok) fma8(acc, __ldg(p + (size_t)t.y0 * W + t.x0 + 1), t.w01);
+  if (y1ok && x0ok) fma8(acc, __ldg(p + (size_t)(t.y0 + 1) * W + t.x0), t.w10);
+  if (y1ok && x1ok) fma8(acc, __ldg(p + (size_t)(t.y0 + 1) * W + t.x0 + 1), t.w11);
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 o;
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 t1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]);
+  __nv_bfloat162 t3 = __floats2bfloat162_rn(v[6], v[7]);
+  o.x = *reinterpret_cast<uint32_t*>(&t0);
+  o.y = *reinterpret_cast<uint32_t*>(&t1);
+  o.z = *reinterpret_cast<uint32_t*>(&t2);
+  o.w = *reinterpret_cast<uint32_t*>(&t3);
+  return o;
+}
+
+__global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smB = smem;
+  uint8_t* smA = smem + kDBBytes;
+  uint64_t* bars = (uint64_t*)(smem + kDBBytes + kDStages * kDABytes);
+  uint64_t* full = bars;                  // gather -> MMA   (count 256)
+  uint64_t* empty = bars + kDStages;      // MMA -> gather   (tcgen05.commit)
+  uint64_t* tfull = bars + 2 * kDStages;  // MMA -> epilogue
+  uint64_t* tempty = bars + 2 * kDStages + 2;
+  uint64_t* wbar = bars + 2 * kDStages + 4;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kDStages + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kMmaWarp = kDGatherThreads / 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDStages; ++s) {
+      mbar_init(&full[s], kDGatherThreads);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);
+    }
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int items_per_img = p.tiles_x * p.tiles_y;
+  const size_t plane = (size_t)p.H * p.W * 8;  // elements per (n, slab) plane of x
+
+  if (warp < kMmaWarp) {
+    // ======================= gather warps =======================
+    const int t = threadIdx.x;
+    const int pix = t & 127, sg = t >> 7;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int n = item / items_per_img;
+      const int r = item - n * items_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int y = ty * kDTileH + (pix >> 4), x = tx * kDTileW + (pix & 15);
+      const bool valid = y < p.H && x < p.W;
+      float off[20];
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const float4 o4 = __ldg(reinterpret_cast<const float4*>(
+              p.off + ((((size_t)n * p.off_cs + q) * p.H + y) * p.W + x) * 4));
+          off[4 * q] = o4.x; off[4 * q + 1] = o4.y; off[4 * q + 2] = o4.z; off[4 * q + 3] = o4.w;
+        }
+      }
+      const __nv_bfloat16* xin = p.x + (size_t)n * 8 * plane;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* a = smA + s * kDABytes;
+        if (valid) {
+          const TapPos tp = tap_pos(off[tap], off[9 + tap], x, y, tap, p.H, p.W);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int slab = sg * 4 + k;
+            float v[8];
+            sample8(xin + slab * plane, tp, p.H, p.W, v);
+            *reinterpret_cast<uint4*>(a + ((size_t)slab * 128 + pix) * 16) = pack8(v);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(a + ((size_t)(sg * 4 + k) * 128 + pix) * 16) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&full[s]);
+        if (++s == kDStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, kDBBytes);
+      for (int c = 0; c < 9; ++c)
+        bulk_load(smB + c * (kDBBytes / 9), reinterpret_cast<const uint8_t*>(p.wpacked) + c * (kDBBytes / 9),
+                  kDBBytes / 9, wbar);
+      mbar_wait(wbar, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      const uint32_t b0 = smem_u32(smB);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * 64);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smA + s * kDABytes);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma_bf16(d, umma_desc_kmajor_noswz(a0 + (uint32_t)(2 * ks) * 2048u, 2048u, 128u),
+                      umma_desc_kmajor_noswz(b0 + (uint32_t)((tap * 8 + 2 * ks) * 8) * 128u, 1024u, 128u), idesc,
+                      (tap | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+          if (++s == kDStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    // ======================= epilogue =======================
+    const int q = warp & 3;
+    const int m = 32 * q + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      const int n = item / items_per_img;
+      const int r = item - n * items_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int y = ty * kDTileH + (m >> 4), x = tx * kDTileW + (m & 15);
+      const bool valid = y < p.H && x < p.W;
+      const int buf = it & 1;
+      mbar_wait(&tfull[buf], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 64 + c0), acc);
+        tmem_wait_ld();
+        if (valid) {
+#pragma unroll
+          for (int s8 = 0; s8 < 4; ++s8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[i] = __uint_as_float(acc[8 * s8 + i]) + __ldg(p.bias + c0 + 8 * s8 + i);
+              if (p.act) v[i] = lrelu(v[i]);
+            }
+            const size_t cs = (size_t)n * p.out_cs_total + (p.out_cs0 + c0 / 8 + s8);
+            *reinterpret_cast<uint4*>(p.out + ((cs * p.H + y) * p.W + x) * 8) = pack8(v);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+// ---- final layer: 64 -> 1, one thread per output pixel ------------------------------------------
+__global__ void __launch_bounds__(256) deform_out1_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          const float* __restrict__ off, int off_cs,
+                                                          const float* __restrict__ w,  // (1, 64, 3, 3) fp32
+                                                          const float* __restrict__ bias, float* __restrict__ y,
+                                                          int N, int H, int W) {
+  __shared__ float sw[9][64];  // [tap][c]
+  for (int i = threadIdx.x; i < 576; i += blockDim.x) sw[i % 9][i / 9] = w[i];
+  __syncthreads();
+  const size_t plane = (size_t)H * W * 8;
+  const long total = (long)N * H * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int xx = i % W;
+    const long r = i / W;
+    const int yy = r % H;
+    const int n = r / H;
+    float offv[20];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const float4 o4 =
+          __ldg(reinterpret_cast<const float4*>(off + ((((size_t)n * off_cs + q) * H + yy) * W + xx) * 4));
+      offv[4 * q] = o4.x; offv[4 * q + 1] = o4.y; offv[4 * q + 2] = o4.z; offv[4 * q + 3] = o4.w;
+    }
+    const __nv_bfloat16* xin = x + (size_t)n * 8 * plane;
+    float acc = bias[0];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const TapPos tp = tap_pos(offv[tap], offv[9 + tap], xx, yy, tap, H, W);
+#pragma unroll 2
+      for (int slab = 0; slab < 8; ++slab) {
+        float v[8];
+        sample8(xin + slab * plane, tp, H, W, v);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc = fmaf(v[c], sw[tap][slab * 8 + c], acc);
+      }
+    }
+    y[i] = acc;
+  }
+}
+
+}  // namespace dbm
+
+using namespace dbm;
+
+extern "C" int dbm_deform_conv_umma(const void* x_slab8, const float* offset_slab4, int offset_cs_total,
+                                    const void* wpacked_ck64, const float* bias, int n, int h, int w, int act,
+                                    void* out_slab8, int out_cs_total, int out_cs0, cudaStream_t stream) {
+  DBM_REQUIRE(n > 0 && h > 0 && w > 0, "deform_conv_umma: empty input");
+  DBM_REQUIRE(offset_cs_total >= 5, "deform_conv_umma: offset tensor needs >= 18 channels (5 slabs)");
+  DBM_REQUIRE(((uintptr_t)x_slab8 & 15) == 0 && ((uintptr_t)wpacked_ck64 & 15) == 0 &&
+                  ((uintptr_t)offset_slab4 & 15) == 0 && ((uintptr_t)out_slab8 & 15) == 0,
+              "deform_conv_umma: unaligned pointer");
+  static bool attr_done = false;
+  if (!attr_done) {
+    DBM_CUDA(cudaFuncSetAttribute(deform_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
+    attr_done = true;
+  }
+  DeformParams p;
+  p.N = n; p.H = h; p.W = w;
+  p.tiles_x = ceil_div(w, kDTileW); p.tiles_y = ceil_div(h, kDTileH);
+  p.num_items = n * p.tiles_x * p.tiles_y;
+  p.x = (const __nv_bfloat16*)x_slab8; p.off = offset_slab4; p.off_cs = offset_cs_total;
+  p.wpacked = (const __nv_bfloat16*)wpacked_ck64; p.bias = bias; p.act = act;
+  p.out = (__nv_bfloat16*)out_slab8; p.out_cs_total = out_cs_total; p.out_cs0 = out_cs0;
+  const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
+  deform_umma_kernel<<<grid, kDThreads, kDSmem, stream>>>(p);
+  return check_launch("deform_umma_kernel");
+}
+
+extern "C" int dbm_deform_conv_out1(const void* x_slab8, const float* offset_slab4, int offset_cs_total,
+                                    const float* w_f32, const float* bias, float* y, int n, int h, int w,
+                                    cudaStream_t stream) {
+  DBM_REQUIRE(n > 0 && h > 0 && w > 0, "deform_conv_out1: empty input");
+  DBM_REQUIRE(offset_cs_total >= 5, "deform_conv_out1: offset tensor needs >= 18 channels (5 slabs)");
+  const long total = (long)n * h * w;
+  long blocks = (total + 255) / 256;
+  const long cap = (long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  deform_out1_kernel<<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)x_slab8, offset_slab4, offset_cs_total,
+                                                      w_f32, bias, y, n, h, w);
+  return check_launch("deform_out1_kernel");
+}

@@ -383,6 +383,8 @@ class GeneratorModel(_Link):
             add(key, 64)
         add("final_conv_layer1/offset_conv", 32)
         add("final_conv_layer2/offset_conv", 32)
+        pk["final_conv_layer1/deform_conv"] = (ops.pack_conv3x3(P["final_conv_layer1/deform_conv/W"], 64, ck=64),
+                                               P["final_conv_layer1/deform_conv/b"])
         self._packed = pk
         self._packed_version = self.version
         return pk
@@ -437,25 +439,20 @@ class GeneratorModel(_Link):
         wq, bq = pk["post_upsample_conv_layer_2"]
         ops.conv3x3_umma(u2, 64, wq, bq, 64, act=True, out=f1)
         del u2
-        # deformable layers: offset convs on the tensor cores, sampling + contraction in fp32
-        off1_s = ops.empty(n, 8, 4 * H, 4 * W, 4)
+        # deformable layers: offset conv (tcgen05) -> gather + tcgen05 contraction / output dot product
+        off_s = ops.empty(n, 8, 4 * H, 4 * W, 4)
         wq, bq = pk["final_conv_layer1/offset_conv"]
-        ops.conv3x3_umma(f1, 64, wq, bq, 32, out_f32=off1_s)
-        c2 = ops.slab8_to_nchw(f1, 64)
-        off1 = ops.slab4_to_nchw(off1_s, 18)
-        del f1, off1_s
-        d1, _ = ops.deform_conv_fwd(c2, off1, P["final_conv_layer1/deform_conv/W"], P["final_conv_layer1/deform_conv/b"],
-                                    act=True)
-        del c2, off1, _
-        d1_s = ops.empty(n, 8, 4 * H, 4 * W, 8, dtype=bf)
-        ops.nchw_to_slab8(d1, d1_s)
-        off2_s = ops.empty(n, 8, 4 * H, 4 * W, 4)
+        ops.conv3x3_umma(f1, 64, wq, bq, 32, out_f32=off_s)
+        d1 = ops.empty(n, 8, 4 * H, 4 * W, 8, dtype=bf)
+        wq, bq = pk["final_conv_layer1/deform_conv"]
+        ops.deform_conv_umma(f1, off_s, wq, bq, d1, act=True)
+        del f1
         wq, bq = pk["final_conv_layer2/offset_conv"]
-        ops.conv3x3_umma(d1_s, 64, wq, bq, 32, out_f32=off2_s)
-        off2 = ops.slab4_to_nchw(off2_s, 18)
-        del d1_s, off2_s
-        y, _ = ops.deform_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"], P["final_conv_layer2/deform_conv/b"])
-        return y
+        ops.conv3x3_umma(d1, 64, wq, bq, 32, out_f32=off_s)
+        if self.out_channels != 1:
+            raise ValueError("the tensor-core path implements out_channels == 1 (the reference's only use)")
+        return ops.deform_conv_out1(d1, off_s, P["final_conv_layer2/deform_conv/W"],
+                                    P["final_conv_layer2/deform_conv/b"])
 
 
 # ================================================================================================

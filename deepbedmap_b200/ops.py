@@ -140,11 +140,29 @@ def slab4_to_nchw(src, c_keep):
     return dst
 
 
-def pack_conv3x3(w, cout_padded):
+def pack_conv3x3(w, cout_padded, ck=32):
     o, cin = w.shape[0], w.shape[1]
     packed = empty(9 * cin * cout_padded, dtype=torch.bfloat16)
-    call("dbm_pack_conv3x3_weights", w.data_ptr(), packed.data_ptr(), o, cin, cout_padded, stream())
+    call("dbm_pack_conv3x3_weights", w.data_ptr(), packed.data_ptr(), o, cin, cout_padded, ck, stream())
     return packed
+
+
+def deform_conv_umma(x_s8, off_s4, wpacked, bias, out_s8, act=False, out_cs0=0):
+    """Deformable 3x3 conv 64->64 on the tensor cores: x (N,8,H,W,8) bf16, offsets (N,>=5,H,W,4) fp32."""
+    n, cs, h, w, _ = x_s8.shape
+    assert cs == 8, "deform_conv_umma needs 64 input channels"
+    call("dbm_deform_conv_umma", x_s8.data_ptr(), off_s4.data_ptr(), off_s4.shape[1], wpacked.data_ptr(),
+         bias.data_ptr(), n, h, w, int(act), out_s8.data_ptr(), out_s8.shape[1], out_cs0, stream())
+
+
+def deform_conv_out1(x_s8, off_s4, w, bias):
+    """Final deformable conv 64->1: fp32 NCHW output (N,1,H,W)."""
+    n, cs, h, wd, _ = x_s8.shape
+    assert cs == 8 and tuple(w.shape) == (1, 64, 3, 3)
+    y = empty(n, 1, h, wd)
+    call("dbm_deform_conv_out1", x_s8.data_ptr(), off_s4.data_ptr(), off_s4.shape[1], w.data_ptr(), bias.data_ptr(),
+         y.data_ptr(), n, h, wd, stream())
+    return y
 
 
 def conv3x3_umma(inp, cin, wpacked, bias, cout_padded, *, beta=0.0, act=False, up2=False, out=None, out_cs0=0,

@@ -95,12 +95,23 @@ int dbm_slab4_to_nchw(const float* src_slab4, float* dst, long dst_batch_stride,
  *   if act: v = lrelu(v);  out_f32_slab4[.., cs0..] = v;  out_slab8[.., cs0..] = bf16(v)
  *   (up2: every output pixel is written to its 2x2 nearest-neighbour block of a 2H x 2W map).
  * cout_padded in {32, 64}; cin multiple of 32. Weights come from dbm_pack_conv3x3_weights. */
-int dbm_pack_conv3x3_weights(const float* w_oihw, void* packed_bf16, int cout, int cin, int cout_padded,
+int dbm_pack_conv3x3_weights(const float* w_oihw, void* packed_bf16, int cout, int cin, int cout_padded, int ck,
                              cudaStream_t stream);
 int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void* wpacked, const float* bias,
                      int cout_padded, int n, int h, int w, float beta, int act, int up2, void* out_slab8,
                      int out_cs_total, int out_cs0, float* out_f32_slab4, int out_f32_cs_total, int out_f32_cs0,
                      const float* res1_slab4, const float* res2_slab4, cudaStream_t stream);
+
+/* ---- deformable convolution, tensor-core inference path (L.DeformableConvolution2D 64->64 and 64->1,
+ * srgan_train.py:506-523, 572-574): bilinear gather straight into the UMMA operand layout in SMEM,
+ * tcgen05 contraction with the SMEM-resident filter (weights packed with ck = 64), bias + LeakyReLU
+ * epilogue; the 64->1 output layer is a CUDA-core dot product with fp32 NCHW output.
+ * offset_slab4: fp32 slab4 with >= 18 channels ([0:9] = dx, [9:18] = dy). */
+int dbm_deform_conv_umma(const void* x_slab8, const float* offset_slab4, int offset_cs_total,
+                         const void* wpacked_ck64, const float* bias, int n, int h, int w, int act, void* out_slab8,
+                         int out_cs_total, int out_cs0, cudaStream_t stream);
+int dbm_deform_conv_out1(const void* x_slab8, const float* offset_slab4, int offset_cs_total, const float* w_f32,
+                         const float* bias, float* y, int n, int h, int w, cudaStream_t stream);
 
 /* ---- deformable convolution, fp32 path (L.DeformableConvolution2D, srgan_train.py:506-523) -----
  * cols[n][c*9+t][pixel] = bilinear sample; contraction with W (O, C*9) is a dbm_gemm_f32 call.

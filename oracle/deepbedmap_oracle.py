@@ -218,7 +218,7 @@ def upsample_nearest2(x):
     return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
 
 
-def deformable_conv2d(x, offset, W, b):
+def deformable_conv2d(x, offset, W, b, quantize=None):
     """chainer.functions.deformable_convolution_2d_sampler with ksize 3, stride 1, pad 1
     (call sites srgan_train.py:506-523, 572-574; semantics SURVEY App. B.6).
 
@@ -258,6 +258,8 @@ def deformable_conv2d(x, offset, W, b):
                + corner(y0, x0 + 1) * ((1 - fy) * fx).unsqueeze(1)
                + corner(y0 + 1, x0) * (fy * (1 - fx)).unsqueeze(1)
                + corner(y0 + 1, x0 + 1) * (fy * fx).unsqueeze(1))  # (N,C,9,H,W)
+    if quantize is not None:  # tensor-core path: sampled operand and filter rounded to bf16
+        sampled, W = quantize(sampled), quantize(W)
     y = torch.einsum("nckhw,ock->nohw", sampled, W.reshape(O, C, 9))
     return y + b.view(1, O, 1, 1)
 
@@ -280,7 +282,8 @@ def generator_forward(p: Params, x, w1, w2, w3, num_residual_blocks=12,
     ``emulate_bf16=True`` restates the SAME graph with the operand rounding of the product's
     tcgen05 path (documented in DESIGN.md): 3x3-conv inputs and weights rounded to bf16, fp32
     (here: wider) accumulation, fp32 bias / residual stream, dense-block features a1..a4 and the
-    upsample-conv outputs stored as bf16; stem and deformable sampling/contraction in fp32.
+    upsample-conv outputs stored as bf16; first deformable layer: bilinear samples and filter
+    rounded to bf16, output stored as bf16; stem and the 64->1 output layer in fp32.
     It exists so that the CUDA kernels can be checked tightly (accumulation order is then the only
     difference) independently of how strongly a given weight set amplifies rounding noise.
     """
@@ -312,9 +315,10 @@ def generator_forward(p: Params, x, w1, w2, w3, num_residual_blocks=12,
     c1 = q(_lrelu(conv(u1, "post_upsample_conv_layer_1")))
     c2 = q(_lrelu(conv(upsample_nearest2(c1), "post_upsample_conv_layer_2")))
     off1 = conv(c2, "final_conv_layer1/offset_conv")
-    d1 = _lrelu(deformable_conv2d(c2, off1, p["final_conv_layer1/deform_conv/W"],
-                                  p["final_conv_layer1/deform_conv/b"]))
-    off2 = conv(q(d1), "final_conv_layer2/offset_conv")
+    d1 = q(_lrelu(deformable_conv2d(c2, off1, p["final_conv_layer1/deform_conv/W"],
+                                    p["final_conv_layer1/deform_conv/b"], quantize=q)))
+    off2 = conv(d1, "final_conv_layer2/offset_conv")
+    # output layer: CUDA-core dot product, fp32 filter, no operand rounding
     return deformable_conv2d(d1, off2, p["final_conv_layer2/deform_conv/W"],
                              p["final_conv_layer2/deform_conv/b"])
 

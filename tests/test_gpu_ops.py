@@ -173,6 +173,35 @@ def test_conv3x3_umma_fused_epilogues(ops):
     assert rel_l2(ops.slab8_to_nchw(up, 64), ref) < 4e-3
 
 
+@pytest.mark.parametrize("n,h,w", [(1, 8, 16), (2, 37, 45), (3, 36, 36)])
+def test_deform_conv_tensor_core_path(ops, n, h, w):
+    """dbm_deform_conv_umma (64->64) and dbm_deform_conv_out1 (64->1) vs the oracle's deformable
+    convolution on the same bf16-representable input."""
+    from oracle import deepbedmap_oracle as O
+    x = rnd(n, 64, h, w, seed=1).bfloat16().float()
+    off = rnd(n, 18, h, w, seed=2, scale=1.5)
+    off[0, :, 0, 0] = 50.0
+    off[0, :9, 1, 1] = -30.0
+    offp = torch.zeros(n, 32, h, w, device="cuda")
+    offp[:, :18] = off
+    x8 = ops.empty(n, 8, h, w, 8, dtype=torch.bfloat16)
+    ops.nchw_to_slab8(x, x8)
+    off4 = ops.nchw_to_slab4(offp)
+    wt = rnd(64, 64, 3, 3, seed=3, scale=0.1)
+    b = rnd(64, seed=4)
+    out = ops.empty(n, 8, h, w, 8, dtype=torch.bfloat16)
+    ops.deform_conv_umma(x8, off4, ops.pack_conv3x3(wt, 64, ck=64), b, out, act=True)
+    torch.cuda.synchronize()
+    ref = F.leaky_relu(O.deformable_conv2d(x.double().cpu(), off.double().cpu(), wt.double().cpu(), b.double().cpu(),
+                                           quantize=O._q), 0.2)
+    assert rel_l2(ops.slab8_to_nchw(out, 64), ref) < 4e-3
+    w1 = rnd(1, 64, 3, 3, seed=5, scale=0.1)
+    b1 = rnd(1, seed=6)
+    y = ops.deform_conv_out1(x8, off4, w1, b1)
+    ref1 = O.deformable_conv2d(x.double().cpu(), off.double().cpu(), w1.double().cpu(), b1.double().cpu())
+    assert rel_l2(y, ref1) < 1e-5
+
+
 def test_deform_conv_fwd_bwd(ops):
     from oracle import deepbedmap_oracle as O
     n, c, h, w, o = 2, 6, 9, 11, 5
