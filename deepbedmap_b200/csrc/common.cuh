@@ -135,6 +135,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the descriptors formed inside the asm block from per-stage base words plus
+// compile-time start-address offsets (16-byte units): keeps the live uniform-register set small
+// (2 adds + 2 moves + UTCHMMA per instruction instead of hoisted/spilled descriptor tables).
+template <uint32_t kAOff, uint32_t kBOff>
+__device__ __forceinline__ void umma_bf16_off(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 alo, blo;\n\t.reg .b64 ad, bd;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "add.u32 alo, %1, %7;\n\t"
+      "add.u32 blo, %3, %8;\n\t"
+      "mov.b64 ad, {alo, %2};\n\t"
+      "mov.b64 bd, {blo, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "n"(kAOff), "n"(kBOff)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -156,6 +173,29 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Exactly one lane of a converged warp gets true (keeps the surrounding code warp-uniform so
+// descriptors stay in uniform registers; a plain `lane == 0` branch makes ptxas emit
+// R2UR + ELECT loops in front of every tcgen05.mma).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+      "@P1 mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
+  return ((uint64_t)hi << 32) | (uint64_t)lo;
+}
+// lo/hi words of the K-major no-swizzle descriptor for a 16-byte-aligned smem address
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);  // version 1 at bit 46
 }
 
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave") canonical layout

@@ -15,6 +15,8 @@
 // UMMA shared-memory descriptors into that same tile (K-major, no-swizzle core matrices:
 // 8 consecutive pixels x 8 channels = 128 contiguous bytes), so activations cross L2->SMEM
 // 1.27x instead of 9x.
+#include <utility>
+
 #include "common.cuh"
 
 namespace dbm {
@@ -47,6 +49,30 @@ struct UmmaCfg {
   static constexpr int TMEM_COLS = 4 * COUT;  // 2 sub-tiles x 2 accumulator buffers
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
 };
+
+// All MMAs of one pipeline stage: 2 sub-tiles x 9 taps x CK/16 k-steps, offsets are template
+// constants (start-address field advances in 16-byte units; no carry into the LBO field).
+template <int COUT, int CK, int IDX>
+__device__ __forceinline__ void issue_one(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t acc0) {
+  constexpr int KS = CK / 16;
+  constexpr int j = IDX / (9 * KS), tap = (IDX / KS) % 9, ks = IDX % KS;
+  constexpr int ky = tap / 3, kx = tap % 3;
+  constexpr uint32_t a_off = (uint32_t)(((2 * ks) * kHalo + ky) * kHalo + kx + 8 * j);
+  constexpr uint32_t b_off = (uint32_t)((tap * (CK / 8) + 2 * ks) * (COUT / 8) * 8);
+  umma_bf16_off<a_off, b_off>(d0 + (uint32_t)(j * COUT), a_lo, a_hi, b_lo, b_hi, idesc,
+                              (tap | ks) != 0 ? 1u : acc0);
+}
+template <int COUT, int CK, int... IDX>
+__device__ __forceinline__ void issue_all(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t acc0, std::integer_sequence<int, IDX...>) {
+  (issue_one<COUT, CK, IDX>(d0, a_lo, a_hi, b_lo, b_hi, idesc, acc0), ...);
+}
+template <int COUT, int CK>
+__device__ __forceinline__ void issue_stage_mmas(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                 uint32_t b_hi, uint32_t idesc, uint32_t acc0) {
+  issue_all<COUT, CK>(d0, a_lo, a_hi, b_lo, b_hi, idesc, acc0, std::make_integer_sequence<int, 2 * 9 * (CK / 16)>{});
+}
 
 template <int COUT, int CK, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -108,47 +134,37 @@ umma_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const UmmaConvP
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, COUT);
-      uint32_t a_lbo = kHalo * kHalo * 16, a_sbo = kHalo * 16;
-      uint32_t b_lbo = (COUT / 8) * 128, b_sbo = 128;
-      if (p.swap) {
-        uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t;
-        t = b_lbo; b_lbo = b_sbo; b_sbo = t;
-      }
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+    // ================= MMA issuer: converged warp, one elected lane issues =================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, COUT);
+    uint32_t a_lbo = kHalo * kHalo * 16, a_sbo = kHalo * 16;
+    uint32_t b_lbo = (COUT / 8) * 128, b_sbo = 128;
+    if (p.swap) {
+      uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t;
+      t = b_lbo; b_lbo = b_sbo; b_sbo = t;
+    }
+    const uint32_t a_hi = desc_hi(a_sbo), b_hi = desc_hi(b_sbo);
+    const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * 2 * COUT);
+      for (int kc = 0; kc < num_kc; ++kc) {
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        for (int kc = 0; kc < num_kc; ++kc) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(smA + s * Cfg::A_BYTES);
-          const uint32_t b0 = smem_u32(smB + s * Cfg::B_BYTES);
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t d = tmem_base + (uint32_t)(buf * 2 * COUT + j * COUT);
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int ky = tap / 3, kx = tap % 3;
-#pragma unroll
-              for (int ks = 0; ks < CK / 16; ++ks) {
-                const uint32_t a_addr = a0 + (uint32_t)((((2 * ks) * kHalo + ky) * kHalo + kx + 8 * j) * 16);
-                const uint32_t b_addr = b0 + (uint32_t)((tap * (CK / 8) + 2 * ks) * (COUT / 8) * 128);
-                umma_bf16(d, umma_desc_kmajor_noswz(a_addr, a_lbo, a_sbo),
-                          umma_desc_kmajor_noswz(b_addr, b_lbo, b_sbo), idesc,
-                          (kc | tap | ks) != 0 ? 1u : 0u);
-              }
-            }
-          }
+        const uint32_t a_lo = desc_lo(smA_u + s * Cfg::A_BYTES, a_lbo);
+        const uint32_t b_lo = desc_lo(smB_u + s * Cfg::B_BYTES, b_lbo);
+        const uint32_t acc0 = kc != 0 ? 1u : 0u;
+        if (elect_one_sync()) {
+          issue_stage_mmas<COUT, CK>(d0, a_lo, a_hi, b_lo, b_hi, idesc, acc0);
           umma_commit(&empty[s]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (kc == num_kc - 1) umma_commit(&tfull[buf]);
         }
-        umma_commit(&tfull[buf]);
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else {

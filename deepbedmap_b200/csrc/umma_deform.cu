@@ -172,37 +172,43 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
       }
     }
   } else if (warp == kMmaWarp) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
+    // ======================= MMA issuer (converged warp, one elected lane issues) =======================
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(wbar, kDBBytes);
       for (int c = 0; c < 9; ++c)
         bulk_load(smB + c * (kDBBytes / 9), reinterpret_cast<const uint8_t*>(p.wpacked) + c * (kDBBytes / 9),
                   kDBBytes / 9, wbar);
-      mbar_wait(wbar, 0);
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-      const uint32_t b0 = smem_u32(smB);
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    mbar_wait(wbar, 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+    constexpr uint32_t a_hi = desc_hi(128u), b_hi = desc_hi(128u);
+    const uint32_t smA_u = smem_u32(smA);
+    const uint32_t b_lo = desc_lo(smem_u32(smB), 1024u);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(buf * 64);
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(buf * 64);
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(smA + s * kDABytes);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            umma_bf16(d, umma_desc_kmajor_noswz(a0 + (uint32_t)(2 * ks) * 2048u, 2048u, 128u),
-                      umma_desc_kmajor_noswz(b0 + (uint32_t)((tap * 8 + 2 * ks) * 8) * 128u, 1024u, 128u), idesc,
-                      (tap | ks) != 0 ? 1u : 0u);
-          }
+        const uint32_t a_lo = desc_lo(smA_u + s * kDABytes, 2048u);
+        const uint32_t bt_lo = b_lo + (uint32_t)(tap * 8 * 8 * 8);  // tap stride = 8 slabs x 8 groups x 128 B
+        if (elect_one_sync()) {
+          umma_bf16_off<0u, 0u>(d, a_lo, a_hi, bt_lo, b_hi, idesc, tap != 0 ? 1u : 0u);
+          umma_bf16_off<256u, 128u>(d, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
+          umma_bf16_off<512u, 256u>(d, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
+          umma_bf16_off<768u, 384u>(d, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
           umma_commit(&empty[s]);
-          if (++s == kDStages) { s = 0; ph ^= 1; }
+          if (tap == 8) umma_commit(&tfull[buf]);
         }
-        umma_commit(&tfull[buf]);
+        __syncwarp();
+        if (++s == kDStages) { s = 0; ph ^= 1; }
       }
     }
   } else {
