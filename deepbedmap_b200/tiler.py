@@ -4,23 +4,21 @@ Tile geometry is reproduced exactly (it is semantics: the crop borders decide wh
 zero padding falls): 18 x 22 output tiles of 1000 x 1000 px, each predicted from a lowres crop
 with an 18+1 px halo, the outer 72 px of every prediction cropped, the canvas pre-filled with NaN.
 
-B200 design: the four continent grids (10.9 GB) are uploaded ONCE and stay resident in HBM
-(the reference re-uploads 14.4 GB of overlapping crops); crop + clip>=0 (deepbedmap.py:663-665,
+B200 design: the continent grids (10.9 GB) are uploaded ONCE and stay resident in HBM (the
+reference re-uploads 14.4 GB of overlapping crops); crop + clip>=0 (deepbedmap.py:663-665,
 715-722) is one small kernel per input, same-shape tiles are batched through the generator, and
 predictions are placed on a device-resident canvas that is read back once.  With
-torch.distributed initialised, tiles are dealt round-robin to ranks and gathered on rank 0 (the
-only collective).
+torch.distributed initialised, each rank takes a contiguous run of tiles (so it only needs - and
+only uploads - the band of grid rows under its tiles) and rank 0 gathers the per-rank result
+stacks: the only collective.
 """
 from __future__ import annotations
 
 from collections import OrderedDict
-from typing import List, Optional, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
-
-from . import ops
-from .model import GeneratorModel, as_device
 
 
 def tile_plan(final_shape=(18000, 22000), ary_shape=(1000, 1000), stride=(1000, 1000), xtrapad=(18, 18)):
@@ -37,6 +35,33 @@ def tile_plan(final_shape=(18000, 22000), ary_shape=(1000, 1000), stride=(1000, 
     return plan
 
 
+# ---- host-side sharding logic (device independent; covered by gloo tests on CPU) -----------------
+def rank_tile_range(n_tiles: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced run of tile indices owned by ``rank``."""
+    base, rem = divmod(n_tiles, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def max_tiles_per_rank(n_tiles: int, world: int) -> int:
+    return (n_tiles + world - 1) // world
+
+
+def rank_row_band(plan, rank: int, world: int) -> Tuple[int, int]:
+    """Lowres row range [r0, r1) of the input grids that the rank's tiles read."""
+    a, b = rank_tile_range(len(plan), rank, world)
+    if a == b:
+        return 0, 0
+    return min(t[0] for t in plan[a:b]), max(t[1] for t in plan[a:b])
+
+
+def group_by_shape(indexed_tiles):
+    groups: "OrderedDict[Tuple[int, int], List]" = OrderedDict()
+    for i, t in indexed_tiles:
+        groups.setdefault((t[1] - t[0], t[3] - t[2]), []).append((i, t))
+    return groups
+
+
 def _dist():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
@@ -44,48 +69,82 @@ def _dist():
     return None, 0, 1
 
 
+def gather_and_assemble(results: torch.Tensor, plan, final_shape, ary_shape, rank: int, world: int,
+                        new_canvas: Callable[[], torch.Tensor], place: Callable) -> Optional[torch.Tensor]:
+    """Final gather: every rank contributes its (max_tiles_per_rank, ary_y, ary_x) result stack;
+    rank 0 places slot ``i - start(rank_of_i)`` of each stack at the tile's canvas window.
+    ``place(src_tile, canvas, ys, xs, hh, ww)`` copies src[:hh, :ww] into canvas[ys:, xs:]."""
+    import torch.distributed as dist
+    gathered = [torch.empty_like(results) for _ in range(world)] if rank == 0 else None
+    dist.gather(results, gathered, dst=0)
+    if rank != 0:
+        return None
+    canvas = new_canvas()
+    for r in range(world):
+        a, b = rank_tile_range(len(plan), r, world)
+        for i in range(a, b):
+            _, _, _, _, ys, ye, xs, xe = plan[i]
+            place(gathered[r][i - a], canvas, ys, xs, ye - ys, xe - xs)
+    return canvas
+
+
+# ---- device side -----------------------------------------------------------------------------------
 class ContinentGrids:
     """The four input rasters resident on the device: X (1,1,H,W), W1 (1,1,10H,10W), W2 (1,2,2H,2W),
-    W3 (1,1,H,W); the reference's shapes are 4502x5502 etc. (deepbedmap.ipynb:1519)."""
+    W3 (1,1,H,W); the reference's shapes are 4502x5502 etc. (deepbedmap.ipynb:1519). ``row0`` is the
+    lowres row of the full grid that row 0 of these (possibly band-cropped) arrays corresponds to."""
 
-    def __init__(self, X, W1, W2, W3):
-        self.X, self.W1, self.W2, self.W3 = (as_device(a) for a in (X, W1, W2, W3))
-        for a, c in ((self.X, 1), (self.W1, 1), (self.W2, 2), (self.W3, 1)):
-            if a.dim() != 4 or a.shape[0] != 1 or a.shape[1] != c:
+    def __init__(self, X, W1, W2, W3, rows: Optional[Tuple[int, int]] = None):
+        from .model import as_device
+        for a, c in ((X, 1), (W1, 1), (W2, 2), (W3, 1)):
+            if a.ndim != 4 or a.shape[0] != 1 or a.shape[1] != c:
                 raise ValueError(f"continent grids must be (1,C,H,W); got {tuple(a.shape)}")
+        Hs, Ws = X.shape[2], X.shape[3]
+        if tuple(W1.shape[2:]) != (10 * Hs, 10 * Ws) or tuple(W2.shape[2:]) != (2 * Hs, 2 * Ws) or \
+                tuple(W3.shape[2:]) != (Hs, Ws):
+            raise ValueError("W1/W2/W3 must be 10x/2x/1x the BEDMAP2 grid")
+        self.full_rows = Hs
+        r0, r1 = rows if rows is not None else (0, Hs)
+        self.row0 = r0
+        self.X = as_device(X[:, :, r0:r1])
+        self.W1 = as_device(W1[:, :, 10 * r0:10 * r1])
+        self.W2 = as_device(W2[:, :, 2 * r0:2 * r1])
+        self.W3 = as_device(W3[:, :, r0:r1])
+
+    @property
+    def rows(self):
+        return self.row0, self.row0 + self.X.shape[2]
 
 
-def predict_continent(model: GeneratorModel, X, W1, W2, W3, final_shape=(18000, 22000), ary_shape=(1000, 1000),
-                      stride=(1000, 1000), xtrapad=(18, 18), batch_tiles: int = 2, to_host: bool = True,
+def predict_continent(model, X, W1, W2, W3, final_shape=(18000, 22000), ary_shape=(1000, 1000),
+                      stride=(1000, 1000), xtrapad=(18, 18), batch_tiles: int = 4, to_host: bool = True,
                       grids: Optional[ContinentGrids] = None):
     """Returns Y_hat (1, final_y, final_x) float32 (NumPy if ``to_host`` else a CUDA tensor), NaN
     where the reference leaves NaN. On ranks != 0 of a distributed run returns None."""
+    from . import ops
     dist, rank, world = _dist()
-    g = grids if grids is not None else ContinentGrids(X, W1, W2, W3)
-    Hs, Ws = g.X.shape[2], g.X.shape[3]
-    if tuple(g.W1.shape[2:]) != (10 * Hs, 10 * Ws) or tuple(g.W2.shape[2:]) != (2 * Hs, 2 * Ws) or \
-            tuple(g.W3.shape[2:]) != (Hs, Ws):
-        raise ValueError("W1/W2/W3 must be 10x/2x/1x the BEDMAP2 grid")
     plan = tile_plan(final_shape, ary_shape, stride, xtrapad)
-    for (y0, y1, x0, x1, *_r) in plan:
-        if y1 > Hs or x1 > Ws:
+    a, b = rank_tile_range(len(plan), rank, world)
+    if grids is None:
+        band = rank_row_band(plan, rank, world) if world > 1 else None
+        grids = ContinentGrids(X, W1, W2, W3, rows=band)
+    g = grids
+    Hs, Ws = g.X.shape[2], g.X.shape[3]
+    r0, r1 = g.rows
+    for (y0, y1, x0, x1, *_r) in plan[a:b]:
+        if y0 < r0 or y1 > r1 or x1 > Ws:
             raise ValueError("final_shape exceeds the input grids")
-    mine = [(i, t) for i, t in enumerate(plan) if i % world == rank]
-    groups: "OrderedDict[Tuple[int, int], List]" = OrderedDict()
-    for i, t in mine:
-        groups.setdefault((t[1] - t[0], t[3] - t[2]), []).append((i, t))
+    groups = group_by_shape([(i, plan[i]) for i in range(a, b)])
     py, px = xtrapad[0] * 4, xtrapad[1] * 4
     single = world == 1
+    st = ops.stream
     if single:
         canvas = ops.empty(final_shape[0], final_shape[1])
         ops.fill(canvas, float("nan"))
         results = None
     else:
-        # per-rank result stack, gathered on rank 0 at the end
-        per_rank = (len(plan) + world - 1) // world
-        results = ops.empty(per_rank, ary_shape[0], ary_shape[1])
+        results = ops.empty(max_tiles_per_rank(len(plan), world), ary_shape[0], ary_shape[1])
         ops.fill(results, float("nan"))
-    st = ops.stream
     for (h, w), tiles in groups.items():
         for b0 in range(0, len(tiles), batch_tiles):
             chunk = tiles[b0:b0 + batch_tiles]
@@ -95,12 +154,13 @@ def predict_continent(model: GeneratorModel, X, W1, W2, W3, final_shape=(18000, 
             w2b = ops.empty(nb, 2, 2 * h, 2 * w)
             w3b = ops.empty(nb, 1, h, w)
             for j, (_, (y0, y1, x0, x1, *_r)) in enumerate(chunk):
-                ops.call("dbm_crop_clip_f32", g.X.data_ptr(), Hs, Ws, xb[j].data_ptr(), 1, y0, x0, h, w, 0, st())
-                ops.call("dbm_crop_clip_f32", g.W1.data_ptr(), 10 * Hs, 10 * Ws, w1b[j].data_ptr(), 1, 10 * y0, 10 * x0,
+                yy = y0 - r0
+                ops.call("dbm_crop_clip_f32", g.X.data_ptr(), Hs, Ws, xb[j].data_ptr(), 1, yy, x0, h, w, 0, st())
+                ops.call("dbm_crop_clip_f32", g.W1.data_ptr(), 10 * Hs, 10 * Ws, w1b[j].data_ptr(), 1, 10 * yy, 10 * x0,
                          10 * h, 10 * w, 1, st())
-                ops.call("dbm_crop_clip_f32", g.W2.data_ptr(), 2 * Hs, 2 * Ws, w2b[j].data_ptr(), 2, 2 * y0, 2 * x0,
+                ops.call("dbm_crop_clip_f32", g.W2.data_ptr(), 2 * Hs, 2 * Ws, w2b[j].data_ptr(), 2, 2 * yy, 2 * x0,
                          2 * h, 2 * w, 1, st())
-                ops.call("dbm_crop_clip_f32", g.W3.data_ptr(), Hs, Ws, w3b[j].data_ptr(), 1, y0, x0, h, w, 1, st())
+                ops.call("dbm_crop_clip_f32", g.W3.data_ptr(), Hs, Ws, w3b[j].data_ptr(), 1, yy, x0, h, w, 1, st())
             y = model.forward(xb, w1b, w2b, w3b).array  # (nb, 1, 4(h-2), 4(w-2))
             th, tw = y.shape[2], y.shape[3]
             for j, (i, (y0, y1, x0, x1, ys, ye, xs, xe)) in enumerate(chunk):
@@ -113,23 +173,21 @@ def predict_continent(model: GeneratorModel, X, W1, W2, W3, final_shape=(18000, 
                     ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, canvas.data_ptr(), final_shape[0],
                              final_shape[1], ys, xs, hh, ww, st())
                 else:
-                    slot = i // world
-                    ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, results[slot].data_ptr(),
+                    ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, results[i - a].data_ptr(),
                              ary_shape[0], ary_shape[1], 0, 0, hh, ww, st())
             del y, xb, w1b, w2b, w3b
-    if single:
-        out = canvas.view(1, final_shape[0], final_shape[1])
-        return out.cpu().numpy() if to_host else out
-    # ---- the only collective: gather result stacks on rank 0 ----
-    gathered = [torch.empty_like(results) for _ in range(world)] if rank == 0 else None
-    dist.gather(results, gathered, dst=0)
-    if rank != 0:
-        return None
-    canvas = ops.empty(final_shape[0], final_shape[1])
-    ops.fill(canvas, float("nan"))
-    for i, (y0, y1, x0, x1, ys, ye, xs, xe) in enumerate(plan):
-        src = gathered[i % world][i // world]
-        ops.call("dbm_place_tile_f32", src.data_ptr(), ary_shape[0], ary_shape[1], 0, 0, canvas.data_ptr(),
-                 final_shape[0], final_shape[1], ys, xs, ye - ys, xe - xs, st())
+    if not single:
+        def new_canvas():
+            c = ops.empty(final_shape[0], final_shape[1])
+            ops.fill(c, float("nan"))
+            return c
+
+        def place(src, canvas_, ys, xs, hh, ww):
+            ops.call("dbm_place_tile_f32", src.data_ptr(), ary_shape[0], ary_shape[1], 0, 0, canvas_.data_ptr(),
+                     final_shape[0], final_shape[1], ys, xs, hh, ww, st())
+
+        canvas = gather_and_assemble(results, plan, final_shape, ary_shape, rank, world, new_canvas, place)
+        if canvas is None:
+            return None
     out = canvas.view(1, final_shape[0], final_shape[1])
     return out.cpu().numpy() if to_host else out
