@@ -33,8 +33,11 @@ struct DeformParams {
   int out_cs_total, out_cs0;
 };
 
+// Sampling position of one tap: the four corner addresses are CLAMPED into the image and the
+// bilinear weight of an out-of-image corner is zeroed, so all corner loads are unconditional and
+// can be issued back to back (16 independent 16-byte loads in flight per thread).
 struct TapPos {
-  int x0, y0;
+  int o00, o01, o10, o11;   // pixel offsets (y * W + x) of the clamped corners
   float w00, w01, w10, w11;
 };
 
@@ -45,10 +48,17 @@ __device__ __forceinline__ TapPos tap_pos(float dx, float dy, int x, int y, int 
   py = fminf(fmaxf(py, -2.f), (float)H + 1.f);
   const float fx0 = floorf(px), fy0 = floorf(py);
   const float fx = px - fx0, fy = py - fy0;
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const bool y0ok = y0 >= 0 && y0 < H, y1ok = y0 + 1 >= 0 && y0 + 1 < H;
+  const bool x0ok = x0 >= 0 && x0 < W, x1ok = x0 + 1 >= 0 && x0 + 1 < W;
+  const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
+  const int ya = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
   TapPos t;
-  t.x0 = (int)fx0; t.y0 = (int)fy0;
-  t.w00 = (1.f - fy) * (1.f - fx); t.w01 = (1.f - fy) * fx;
-  t.w10 = fy * (1.f - fx);         t.w11 = fy * fx;
+  t.o00 = ya * W + xa; t.o01 = ya * W + xb; t.o10 = yb * W + xa; t.o11 = yb * W + xb;
+  t.w00 = (y0ok && x0ok) ? (1.f - fy) * (1.f - fx) : 0.f;
+  t.w01 = (y0ok && x1ok) ? (1.f - fy) * fx : 0.f;
+  t.w10 = (y1ok && x0ok) ? fy * (1.f - fx) : 0.f;
+  t.w11 = (y1ok && x1ok) ? fy * fx : 0.f;
   return t;
 }
 
@@ -63,18 +73,25 @@ __device__ __forceinline__ void fma8(float (&acc)[8], const uint4& v, float w) {
   acc[7] = fmaf(w, __uint_as_float(v.w & 0xffff0000u), acc[7]);
 }
 
-// bilinear sample of 8 channels (one slab) -> acc
-__device__ __forceinline__ void sample8(const __nv_bfloat16* __restrict__ plane, const TapPos& t, int H, int W,
-                                        float (&acc)[8]) {
+struct Corners {
+  uint4 c00, c01, c10, c11;
+};
+__device__ __forceinline__ Corners load_corners(const __nv_bfloat16* __restrict__ plane, const TapPos& t) {
+  const uint4* p = reinterpret_cast<const uint4*>(plane);
+  Corners c;
+  c.c00 = __ldg(p + t.o00);
+  c.c01 = __ldg(p + t.o01);
+  c.c10 = __ldg(p + t.o10);
+  c.c11 = __ldg(p + t.o11);
+  return c;
+}
+__device__ __forceinline__ void blend8(const Corners& c, const TapPos& t, float (&acc)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  const bool y0ok = t.y0 >= 0 && t.y0 < H, y1ok = t.y0 + 1 >= 0 && t.y0 + 1 < H;
-  const bool x0ok = t.x0 >= 0 && t.x0 < W, x1ok = t.x0 + 1 >= 0 && t.x0 + 1 < W;
-  const uint4* p = reinterpret_cast<const uint4*>(plane);
-  if (y0ok && x0ok) fma8(acc, __ldg(p + (size_t)t.y0 * W + t.x0), t.w00);
-  if (y0ok && x1ok) fma8(acc, __ldg(p + (size_t)t.y0 * W + t.x0 + 1), t.w01);
-  if (y1ok && x0ok) fma8(acc, __ldg(p + (size_t)(t.y0 + 1) * W + t.x0), t.w10);
-  if (y1ok && x1ok) fma8(acc, __ldg(p + (size_t)(t.y0 + 1) * W + t.x0 + 1), t.w11);
+  fma8(acc, c.c00, t.w00);
+  fma8(acc, c.c01, t.w01);
+  fma8(acc, c.c10, t.w10);
+  fma8(acc, c.c11, t.w11);
 }
 
 __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
@@ -154,12 +171,14 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
         uint8_t* a = smA + s * kDABytes;
         if (valid) {
           const TapPos tp = tap_pos(off[tap], off[9 + tap], x, y, tap, p.H, p.W);
+          Corners cr[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) cr[k] = load_corners(xin + (sg * 4 + k) * plane, tp);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int slab = sg * 4 + k;
             float v[8];
-            sample8(xin + slab * plane, tp, p.H, p.W, v);
-            *reinterpret_cast<uint4*>(a + ((size_t)slab * 128 + pix) * 16) = pack8(v);
+            blend8(cr[k], tp, v);
+            *reinterpret_cast<uint4*>(a + ((size_t)(sg * 4 + k) * 128 + pix) * 16) = pack8(v);
           }
         } else {
 #pragma unroll
@@ -285,12 +304,18 @@ __global__ void __launch_bounds__(256) deform_out1_kernel(const __nv_bfloat16* _
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const TapPos tp = tap_pos(offv[tap], offv[9 + tap], xx, yy, tap, H, W);
-#pragma unroll 2
-      for (int slab = 0; slab < 8; ++slab) {
-        float v[8];
-        sample8(xin + slab * plane, tp, H, W, v);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc = fmaf(v[c], sw[tap][slab * 8 + c], acc);
+      for (int s0 = 0; s0 < 8; s0 += 4) {
+        Corners cr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cr[k] = load_corners(xin + (s0 + k) * plane, tp);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float v[8];
+          blend8(cr[k], tp, v);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc = fmaf(v[c], sw[tap][(s0 + k) * 8 + c], acc);
+        }
       }
     }
     y[i] = acc;
