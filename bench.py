@@ -242,7 +242,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch-tiles", type=int, default=2)
+    ap.add_argument("--batch-tiles", type=int, default=4)
     ap.add_argument("--cpu-crop", type=int, default=96)
     ap.add_argument("--scale", type=float, default=1.0, help="debug only: shrink the continent (invalid as a result)")
     ap.add_argument("--no-train", action="store_true")

@@ -50,28 +50,35 @@ struct UmmaCfg {
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
 };
 
-// All MMAs of one pipeline stage: 2 sub-tiles x 9 taps x CK/16 k-steps, offsets are template
-// constants (start-address field advances in 16-byte units; no carry into the LBO field).
+// All MMAs of one pipeline stage: 9 taps x (2 sub-tiles x CK/16 k-steps). The tap loop is kept
+// rolled: fully unrolling it makes ptxas hoist all 72 descriptor words, overflow the uniform
+// register file and pay R2UR.FILL / MOV.SPILL around every UTCHMMA.
 template <int COUT, int CK, int IDX>
 __device__ __forceinline__ void issue_one(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                          uint32_t idesc, uint32_t acc0) {
+                                          uint32_t idesc, uint32_t acc) {
   constexpr int KS = CK / 16;
-  constexpr int j = IDX / (9 * KS), tap = (IDX / KS) % 9, ks = IDX % KS;
-  constexpr int ky = tap / 3, kx = tap % 3;
-  constexpr uint32_t a_off = (uint32_t)(((2 * ks) * kHalo + ky) * kHalo + kx + 8 * j);
-  constexpr uint32_t b_off = (uint32_t)((tap * (CK / 8) + 2 * ks) * (COUT / 8) * 8);
-  umma_bf16_off<a_off, b_off>(d0 + (uint32_t)(j * COUT), a_lo, a_hi, b_lo, b_hi, idesc,
-                              (tap | ks) != 0 ? 1u : acc0);
+  constexpr int j = IDX / KS, ks = IDX % KS;
+  // start-address field advances in 16-byte units: no carry into the LBO field
+  constexpr uint32_t a_off = (uint32_t)((2 * ks) * kHalo * kHalo + 8 * j);
+  constexpr uint32_t b_off = (uint32_t)((2 * ks) * (COUT / 8) * 8);
+  umma_bf16_off<a_off, b_off>(d0 + (uint32_t)(j * COUT), a_lo, a_hi, b_lo, b_hi, idesc, ks != 0 ? 1u : acc);
 }
 template <int COUT, int CK, int... IDX>
-__device__ __forceinline__ void issue_all(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                          uint32_t idesc, uint32_t acc0, std::integer_sequence<int, IDX...>) {
-  (issue_one<COUT, CK, IDX>(d0, a_lo, a_hi, b_lo, b_hi, idesc, acc0), ...);
+__device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t acc, std::integer_sequence<int, IDX...>) {
+  (issue_one<COUT, CK, IDX>(d0, a_lo, a_hi, b_lo, b_hi, idesc, acc), ...);
 }
 template <int COUT, int CK>
 __device__ __forceinline__ void issue_stage_mmas(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
                                                  uint32_t b_hi, uint32_t idesc, uint32_t acc0) {
-  issue_all<COUT, CK>(d0, a_lo, a_hi, b_lo, b_hi, idesc, acc0, std::make_integer_sequence<int, 2 * 9 * (CK / 16)>{});
+  constexpr uint32_t kBTap = (uint32_t)((CK / 8) * (COUT / 8) * 8);  // per-tap stride of the packed weights
+#pragma unroll 1
+  for (uint32_t tap = 0; tap < 9; ++tap) {
+    const uint32_t a_tap = a_lo + tap + (tap / 3) * (kHalo - 3);     // ky * 18 + kx
+    const uint32_t b_tap = b_lo + tap * kBTap;
+    issue_tap<COUT, CK>(d0, a_tap, a_hi, b_tap, b_hi, idesc, tap != 0 ? 1u : acc0,
+                        std::make_integer_sequence<int, 2 * (CK / 16)>{});
+  }
 }
 
 template <int COUT, int CK, int STAGES>
