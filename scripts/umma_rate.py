@@ -8,13 +8,13 @@ lib.dbm_debug_umma_rate.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes
 lib.dbm_debug_umma_rate.restype = ctypes.c_int
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
 for grid in (1, 148):
-    for n in (32, 64, 128):
+    for n in (32, 64, 128, 256):
         for mode, name in ((0, "noswz-halo"), (1, "noswz-dense"), (2, "sw128")):
-            for per_commit in (36, 144):
-                iters = 200
-                rc = lib.dbm_debug_umma_rate(mode, n, iters, per_commit, out.data_ptr(), grid, None)
-                torch.cuda.synchronize()
-                assert rc == 0, lib.dbm_last_error()
-                cyc = out[:grid].double().mean().item() / (iters * per_commit)
-                print(f"grid={grid:3d} N={n:3d} {name:12s} per_commit={per_commit:3d}: {cyc:7.1f} cyc/MMA "
-                      f"(ideal {n/2:.0f}) -> {n/2/cyc*100:5.1f}% of tensor peak")
+            iters = 400
+            rc = lib.dbm_debug_umma_rate(mode, n, iters, 36, out.data_ptr(), grid, None)
+            torch.cuda.synchronize()
+            assert rc == 0, lib.dbm_last_error()
+            cyc = out[:grid].double().mean().item() / (iters * 36)
+            smem_b = 128 * 32 + n * 32
+            print(f"grid={grid:3d} N={n:3d} {name:12s}: {cyc:7.1f} cyc/MMA (tensor floor {n/2:.0f}) -> "
+                  f"{n/2/cyc*100:5.1f}% of tensor peak, operand bytes/cyc {smem_b/cyc:6.1f}")
