@@ -1,0 +1,208 @@
+// Fused generator input block for the tensor-core path
+// (DeepbedmapInputBlock.forward, srgan_train.py:256-266): the four valid-padded strided convs
+//   conv_on_X  1->32 k3 s1 | conv_on_W1 1->32 k30 s10 | conv_on_W2 2->32 k6 s2 | conv_on_W3 1->32 k3 s1
+// and F.concat, computed in fp32 on the CUDA cores (raw-metre inputs stay fp32) and written once
+// as the 128-channel bf16 slab8 operand of the pre-residual conv. Small-channel direct conv:
+// the 100x180 REMA window of an 8x16-pixel output tile and the whole 900x32 filter are staged in
+// shared memory; each thread owns 2 pixels x 8 channels (2 scalar + 2 vector LDS per 16 FMA).
+#include "common.cuh"
+
+namespace dbm {
+
+constexpr int kSTH = 8, kSTW = 16;                 // output tile
+constexpr int kW1Rows = (kSTH - 1) * 10 + 30;      // 100
+constexpr int kW1Cols = (kSTW - 1) * 10 + 30;      // 180
+constexpr int kXRows = kSTH + 2, kXCols = kSTW + 2;                    // 10 x 18
+constexpr int kW2Rows = (kSTH - 1) * 2 + 6, kW2Cols = (kSTW - 1) * 2 + 6;  // 20 x 36
+constexpr int kStemSmemFloats = kW1Rows * kW1Cols + 900 * 32 + 2 * kXRows * kXCols + 2 * kW2Rows * kW2Cols + 90 * 32;
+constexpr int kStemSmem = kStemSmemFloats * 4;
+
+struct StemParams {
+  const float *x, *w1, *w2, *w3;   // (N,1,h,w) (N,1,10h,10w) (N,2,2h,2w) (N,1,h,w)
+  const float* wt1;                // [900][32]   conv_on_W1 filter, tap-major
+  const float* wts;                // [90][32]    conv_on_X (9) | conv_on_W2 (72) | conv_on_W3 (9), tap-major
+  const float* bias;               // [128]       X | W1 | W2 | W3
+  __nv_bfloat16* out;              // slab8 [N][out_cs_total][H][W][8], channels written at slab out_cs0..+16
+  int out_cs_total, out_cs0;
+  int N, h, w, H, W, tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ void store_pair(const StemParams& p, int n, int slab, int y, int x, const float (&a)[2][8],
+                                           const float* __restrict__ bias8) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    if (y < p.H && x + i < p.W) {
+      __nv_bfloat162 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        v[k] = __floats2bfloat162_rn(a[i][2 * k] + bias8[2 * k], a[i][2 * k + 1] + bias8[2 * k + 1]);
+      *reinterpret_cast<uint4*>(p.out + ((((size_t)n * p.out_cs_total + p.out_cs0 + slab) * p.H + y) * p.W + x + i) * 8) =
+          *reinterpret_cast<uint4*>(v);
+    }
+  }
+}
+
+__device__ __forceinline__ void fma_pair(float (&a)[2][8], float i0, float i1, const float* __restrict__ w8) {
+  const float4 wa = *reinterpret_cast<const float4*>(w8);
+  const float4 wb = *reinterpret_cast<const float4*>(w8 + 4);
+  const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    a[0][k] = fmaf(i0, ww[k], a[0][k]);
+    a[1][k] = fmaf(i1, ww[k], a[1][k]);
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) stem_kernel(const StemParams p) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_w1in = sm;                                   // [100][180]
+  float* s_w1w = s_w1in + kW1Rows * kW1Cols;            // [900][32]
+  float* s_x = s_w1w + 900 * 32;                        // [10][18]
+  float* s_w3 = s_x + kXRows * kXCols;                  // [10][18]
+  float* s_w2 = s_w3 + kXRows * kXCols;                 // [2][20][36]
+  float* s_ws = s_w2 + 2 * kW2Rows * kW2Cols;           // [90][32]
+
+  const int t = threadIdx.x;
+  int b = blockIdx.x;
+  const int tx = b % p.tiles_x; b /= p.tiles_x;
+  const int ty = b % p.tiles_y;
+  const int n = b / p.tiles_y;
+  const int oy0 = ty * kSTH, ox0 = tx * kSTW;
+
+  // ---- stage filters and input windows (zero fill beyond the image; never read for valid outputs)
+  for (int i = t; i < 900 * 32 / 4; i += 256)
+    reinterpret_cast<float4*>(s_w1w)[i] = __ldg(reinterpret_cast<const float4*>(p.wt1) + i);
+  for (int i = t; i < 90 * 32 / 4; i += 256)
+    reinterpret_cast<float4*>(s_ws)[i] = __ldg(reinterpret_cast<const float4*>(p.wts) + i);
+  {
+    const int H1 = 10 * p.h, W1 = 10 * p.w;
+    const float* src = p.w1 + (size_t)n * H1 * W1;
+    const int r0 = oy0 * 10, c0 = ox0 * 10;
+    for (int i = t; i < kW1Rows * kW1Cols; i += 256) {
+      const int r = i / kW1Cols, c = i - r * kW1Cols;
+      const int gr = r0 + r, gc = c0 + c;
+      s_w1in[i] = (gr < H1 && gc < W1) ? __ldg(src + (size_t)gr * W1 + gc) : 0.f;
+    }
+  }
+  for (int i = t; i < kXRows * kXCols; i += 256) {
+    const int r = i / kXCols, c = i - r * kXCols;
+    const int gr = oy0 + r, gc = ox0 + c;
+    const bool ok = gr < p.h && gc < p.w;
+    s_x[i] = ok ? __ldg(p.x + ((size_t)n * p.h + gr) * p.w + gc) : 0.f;
+    s_w3[i] = ok ? __ldg(p.w3 + ((size_t)n * p.h + gr) * p.w + gc) : 0.f;
+  }
+  {
+    const int H2 = 2 * p.h, W2 = 2 * p.w;
+    for (int i = t; i < 2 * kW2Rows * kW2Cols; i += 256) {
+      const int ch = i / (kW2Rows * kW2Cols), rem = i - ch * (kW2Rows * kW2Cols);
+      const int r = rem / kW2Cols, c = rem - r * kW2Cols;
+      const int gr = 2 * oy0 + r, gc = 2 * ox0 + c;
+      s_w2[i] = (gr < H2 && gc < W2) ? __ldg(p.w2 + (((size_t)n * 2 + ch) * H2 + gr) * W2 + gc) : 0.f;
+    }
+  }
+  __syncthreads();
+
+  const int cg = t & 3;        // 8-channel group of the 32 outputs of each conv
+  const int pp = t >> 2;       // pixel pair 0..63
+  const int r = pp >> 3, c = (pp & 7) * 2;
+  const int y = oy0 + r, x = ox0 + c;
+  float a[2][8];
+
+  // ---- conv_on_W1: k30 s10 ----
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[i][k] = 0.f;
+  {
+    const float* in = s_w1in + (r * 10) * kW1Cols + c * 10;
+    const float* wq = s_w1w + cg * 8;
+    for (int ky = 0; ky < 30; ++ky) {
+#pragma unroll 10
+      for (int kx = 0; kx < 30; ++kx)
+        fma_pair(a, in[ky * kW1Cols + kx], in[ky * kW1Cols + kx + 10], wq + (ky * 30 + kx) * 32);
+    }
+  }
+  store_pair(p, n, 4 + cg, y, x, a, p.bias + 32 + cg * 8);
+
+  // ---- conv_on_X: k3 s1 ----
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[i][k] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+      fma_pair(a, s_x[(r + ky) * kXCols + c + kx], s_x[(r + ky) * kXCols + c + kx + 1],
+               s_ws + (ky * 3 + kx) * 32 + cg * 8);
+  store_pair(p, n, 0 + cg, y, x, a, p.bias + 0 + cg * 8);
+
+  // ---- conv_on_W2: 2 channels, k6 s2 ----
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[i][k] = 0.f;
+  for (int ch = 0; ch < 2; ++ch)
+    for (int ky = 0; ky < 6; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 6; ++kx) {
+        const float* in = s_w2 + (ch * kW2Rows + 2 * r + ky) * kW2Cols + 2 * c + kx;
+        fma_pair(a, in[0], in[2], s_ws + (9 + ch * 36 + ky * 6 + kx) * 32 + cg * 8);
+      }
+  store_pair(p, n, 8 + cg, y, x, a, p.bias + 64 + cg * 8);
+
+  // ---- conv_on_W3: k3 s1 ----
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[i][k] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+      fma_pair(a, s_w3[(r + ky) * kXCols + c + kx], s_w3[(r + ky) * kXCols + c + kx + 1],
+               s_ws + (81 + ky * 3 + kx) * 32 + cg * 8);
+  store_pair(p, n, 12 + cg, y, x, a, p.bias + 96 + cg * 8);
+}
+
+// dst[c][r] = src[r][c]  (filter (32, taps) -> tap-major (taps, 32)); tiny, run once per weight update
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  const int total = rows * cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / cols, c = i - r * cols;
+    dst[(size_t)c * rows + r] = src[i];
+  }
+}
+
+}  // namespace dbm
+
+using namespace dbm;
+
+extern "C" int dbm_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t stream) {
+  DBM_REQUIRE(rows > 0 && cols > 0, "transpose: empty matrix");
+  transpose_kernel<<<ceil_div((long)rows * cols, 256), 256, 0, stream>>>(src, dst, rows, cols);
+  return check_launch("transpose");
+}
+
+extern "C" int dbm_stem_fwd_slab8(const float* x, const float* w1, const float* w2, const float* w3,
+                                  const float* w1_filter_tapmajor, const float* small_filters_tapmajor,
+                                  const float* bias128, void* out_slab8, int out_cs_total, int out_cs0, int n, int h,
+                                  int w, cudaStream_t stream) {
+  DBM_REQUIRE(n > 0 && h >= 3 && w >= 3, "stem: input %dx%d too small (need >= 3x3)", h, w);
+  DBM_REQUIRE(out_cs_total >= out_cs0 + 16, "stem: output needs 16 slabs");
+  static bool attr_done = false;
+  if (!attr_done) {
+    DBM_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
+    attr_done = true;
+  }
+  StemParams p;
+  p.x = x; p.w1 = w1; p.w2 = w2; p.w3 = w3;
+  p.wt1 = w1_filter_tapmajor; p.wts = small_filters_tapmajor; p.bias = bias128;
+  p.out = (__nv_bfloat16*)out_slab8; p.out_cs_total = out_cs_total; p.out_cs0 = out_cs0;
+  p.N = n; p.h = h; p.w = w; p.H = h - 2; p.W = w - 2;
+  p.tiles_x = ceil_div(p.W, kSTW); p.tiles_y = ceil_div(p.H, kSTH);
+  const long blocks = (long)n * p.tiles_x * p.tiles_y;
+  DBM_REQUIRE(blocks < (1L << 31), "stem: too many tiles");
+  stem_kernel<<<(int)blocks, 256, kStemSmem, stream>>>(p);
+  return check_launch("stem_kernel");
+}

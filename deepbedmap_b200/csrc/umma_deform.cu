@@ -14,7 +14,7 @@ namespace dbm {
 
 constexpr int kDTileW = 16, kDTileH = 8;   // 128 output pixels per work item
 constexpr int kDStages = 4;
-constexpr int kDGatherThreads = 256;
+constexpr int kDGatherThreads = 512;      // 16 warps: 128 px x 4 slab pairs
 constexpr int kDThreads = kDGatherThreads + 32 + 128;  // + MMA warp + 4 epilogue warps
 constexpr int kDABytes = 128 * 64 * 2;                 // one tap: 128 px x 64 ch bf16
 constexpr int kDBBytes = 9 * 64 * 64 * 2;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
   uint8_t* smB = smem;
   uint8_t* smA = smem + kDBBytes;
   uint64_t* bars = (uint64_t*)(smem + kDBBytes + kDStages * kDABytes);
-  uint64_t* full = bars;                  // gather -> MMA   (count 256)
+  uint64_t* full = bars;                  // gather -> MMA   (one arrive per gather warp)
   uint64_t* empty = bars + kDStages;      // MMA -> gather   (tcgen05.commit)
   uint64_t* tfull = bars + 2 * kDStages;  // MMA -> epilogue
   uint64_t* tempty = bars + 2 * kDStages + 2;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDStages; ++s) {
-      mbar_init(&full[s], kDGatherThreads);
+      mbar_init(&full[s], kDGatherThreads / 32);  // one arrive per gather warp
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -171,22 +171,23 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
         uint8_t* a = smA + s * kDABytes;
         if (valid) {
           const TapPos tp = tap_pos(off[tap], off[9 + tap], x, y, tap, p.H, p.W);
-          Corners cr[4];
+          Corners cr[2];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) cr[k] = load_corners(xin + (sg * 4 + k) * plane, tp);
+          for (int k = 0; k < 2; ++k) cr[k] = load_corners(xin + (sg * 2 + k) * plane, tp);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < 2; ++k) {
             float v[8];
             blend8(cr[k], tp, v);
-            *reinterpret_cast<uint4*>(a + ((size_t)(sg * 4 + k) * 128 + pix) * 16) = pack8(v);
+            *reinterpret_cast<uint4*>(a + ((size_t)(sg * 2 + k) * 128 + pix) * 16) = pack8(v);
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<uint4*>(a + ((size_t)(sg * 4 + k) * 128 + pix) * 16) = make_uint4(0, 0, 0, 0);
+          for (int k = 0; k < 2; ++k)
+            *reinterpret_cast<uint4*>(a + ((size_t)(sg * 2 + k) * 128 + pix) * 16) = make_uint4(0, 0, 0, 0);
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(&full[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
         if (++s == kDStages) { s = 0; ph ^= 1; }
       }
     }
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
   }
 }
 
-// ---- final layer: 64 -> 1, one thread per output pixel ------------------------------------------
+// ---- final layer: 64 -> 1: four threads per output pixel (two slabs each), shuffle-reduced -----
 __global__ void __launch_bounds__(256) deform_out1_kernel(const __nv_bfloat16* __restrict__ x,
                                                           const float* __restrict__ off, int off_cs,
                                                           const float* __restrict__ w,  // (1, 64, 3, 3) fp32
@@ -287,38 +288,42 @@ __global__ void __launch_bounds__(256) deform_out1_kernel(const __nv_bfloat16* _
   __syncthreads();
   const size_t plane = (size_t)H * W * 8;
   const long total = (long)N * H * W;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  const int q = threadIdx.x & 3;
+  const long px_per_iter = ((long)gridDim.x * blockDim.x) >> 2;
+  for (long base = ((long)blockIdx.x * blockDim.x) >> 2; base < total; base += px_per_iter) {
+    const long i0 = base + (threadIdx.x >> 2);
+    const bool live = i0 < total;
+    const long i = live ? i0 : total - 1;
     const int xx = i % W;
     const long r = i / W;
     const int yy = r % H;
     const int n = r / H;
     float offv[20];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
+    for (int k = 0; k < 5; ++k) {
       const float4 o4 =
-          __ldg(reinterpret_cast<const float4*>(off + ((((size_t)n * off_cs + q) * H + yy) * W + xx) * 4));
-      offv[4 * q] = o4.x; offv[4 * q + 1] = o4.y; offv[4 * q + 2] = o4.z; offv[4 * q + 3] = o4.w;
+          __ldg(reinterpret_cast<const float4*>(off + ((((size_t)n * off_cs + k) * H + yy) * W + xx) * 4));
+      offv[4 * k] = o4.x; offv[4 * k + 1] = o4.y; offv[4 * k + 2] = o4.z; offv[4 * k + 3] = o4.w;
     }
-    const __nv_bfloat16* xin = x + (size_t)n * 8 * plane;
-    float acc = bias[0];
+    const __nv_bfloat16* xin = x + ((size_t)n * 8 + 2 * q) * plane;
+    float acc = 0.f;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const TapPos tp = tap_pos(offv[tap], offv[9 + tap], xx, yy, tap, H, W);
+      Corners cr[2];
+      cr[0] = load_corners(xin, tp);
+      cr[1] = load_corners(xin + plane, tp);
 #pragma unroll
-      for (int s0 = 0; s0 < 8; s0 += 4) {
-        Corners cr[4];
+      for (int k = 0; k < 2; ++k) {
+        float v[8];
+        blend8(cr[k], tp, v);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cr[k] = load_corners(xin + (s0 + k) * plane, tp);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float v[8];
-          blend8(cr[k], tp, v);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc = fmaf(v[c], sw[tap][(s0 + k) * 8 + c], acc);
-        }
+        for (int c = 0; c < 8; ++c) acc = fmaf(v[c], sw[tap][(2 * q + k) * 8 + c], acc);
       }
     }
-    y[i] = acc;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (live && q == 0) y[i] = acc + bias[0];
   }
 }
 
@@ -357,8 +362,8 @@ extern "C" int dbm_deform_conv_out1(const void* x_slab8, const float* offset_sla
   DBM_REQUIRE(n > 0 && h > 0 && w > 0, "deform_conv_out1: empty input");
   DBM_REQUIRE(offset_cs_total >= 5, "deform_conv_out1: offset tensor needs >= 18 channels (5 slabs)");
   const long total = (long)n * h * w;
-  long blocks = (total + 255) / 256;
-  const long cap = (long)num_sms() * 8;
+  long blocks = (total * 4 + 255) / 256;
+  const long cap = (long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   deform_out1_kernel<<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)x_slab8, offset_slab4, offset_cs_total,
                                                       w_f32, bias, y, n, h, w);

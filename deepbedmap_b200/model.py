@@ -372,6 +372,21 @@ class GeneratorModel(_Link):
                 bp = b
             pk[key] = (ops.pack_conv3x3(w, cout_padded), bp)
 
+        # stem filters, tap-major, and the concatenated stem bias
+        def tapmajor(keys):
+            taps = [int(P[f"input_block/conv_on_{k}/W"][0].numel()) for k in keys]
+            buf = ops.empty(sum(taps), 32)
+            r0 = 0
+            for k, nt in zip(keys, taps):
+                ops.call("dbm_transpose_f32", P[f"input_block/conv_on_{k}/W"].data_ptr(), buf[r0:].data_ptr(), 32, nt,
+                         ops.stream())
+                r0 += nt
+            return buf
+        bias128 = ops.empty(128)
+        for j, k in enumerate(("X", "W1", "W2", "W3")):
+            ops.axpby(P[f"input_block/conv_on_{k}/b"].view(1, 32, 1, 1), 0, None, 0,
+                      bias128.view(1, 128, 1, 1), 32 * j, 32, 1.0, 0.0)
+        pk["stem"] = (tapmajor(("W1",)), tapmajor(("X", "W2", "W3")), bias128)
         add("pre_residual_conv_layer", 64)
         for i in range(self.num_residual_blocks):
             for r in (1, 2, 3):
@@ -399,11 +414,10 @@ class GeneratorModel(_Link):
         n, _, h, w = x.shape
         H, W = h - 2, w - 2
         bf = torch.bfloat16
-        a0 = ops.empty(n, 128, H, W)
-        self._stem_fp32(x, w1, w2, w3, a0)
         s0 = ops.empty(n, 16, H, W, 8, dtype=bf)
-        ops.nchw_to_slab8(a0, s0)
-        del a0
+        wt1, wts, bias128 = pk["stem"]
+        ops.call("dbm_stem_fwd_slab8", x.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), wt1.data_ptr(),
+                 wts.data_ptr(), bias128.data_ptr(), s0.data_ptr(), 16, 0, n, h, w, ops.stream())
         cat = [ops.empty(n, ccs, H, W, 8, dtype=bf) for _ in range(2)]
         a1_f32 = ops.empty(n, 16, H, W, 4)
         f32 = [ops.empty(n, 16, H, W, 4) for _ in range(3)]

@@ -102,6 +102,16 @@ int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void*
                      int out_cs_total, int out_cs0, float* out_f32_slab4, int out_f32_cs_total, int out_f32_cs0,
                      const float* res1_slab4, const float* res2_slab4, cudaStream_t stream);
 
+/* ---- fused generator input block for the tensor-core path (DeepbedmapInputBlock.forward,
+ * srgan_train.py:256-266): four valid strided convs + F.concat, fp32 math, 128-channel bf16 slab8 out.
+ * Filters are passed tap-major (dbm_transpose_f32 of the (32, taps) Chainer filters):
+ * w1_filter_tapmajor [900][32]; small_filters_tapmajor [9 | 72 | 9][32] = conv_on_X | conv_on_W2 | conv_on_W3;
+ * bias128 = biases of X | W1 | W2 | W3. */
+int dbm_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t stream);
+int dbm_stem_fwd_slab8(const float* x, const float* w1, const float* w2, const float* w3,
+                       const float* w1_filter_tapmajor, const float* small_filters_tapmajor, const float* bias128,
+                       void* out_slab8, int out_cs_total, int out_cs0, int n, int h, int w, cudaStream_t stream);
+
 /* ---- deformable convolution, tensor-core inference path (L.DeformableConvolution2D 64->64 and 64->1,
  * srgan_train.py:506-523, 572-574): bilinear gather straight into the UMMA operand layout in SMEM,
  * tcgen05 contraction with the SMEM-resident filter (weights packed with ck = 64), bias + LeakyReLU

@@ -107,6 +107,34 @@ def test_elementwise_and_layouts(ops):
     assert torch.equal(ops.slab4_to_nchw(s4, 14), x[:, :14])
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 11, 11), (1, 21, 37), (3, 10, 19)])
+def test_fused_stem_kernel(ops, n, h, w):
+    """dbm_stem_fwd_slab8 vs the four valid strided convs + concat (srgan_train.py:256-266)."""
+    x = rnd(n, 1, h, w, seed=1)
+    w1 = rnd(n, 1, 10 * h, 10 * w, seed=2)
+    w2 = rnd(n, 2, 2 * h, 2 * w, seed=3)
+    w3 = rnd(n, 1, h, w, seed=4)
+    fx, f1, f2, f3 = (rnd(32, 1, 3, 3, seed=5), rnd(32, 1, 30, 30, seed=6, scale=0.05),
+                      rnd(32, 2, 6, 6, seed=7, scale=0.2), rnd(32, 1, 3, 3, seed=8))
+    bias = rnd(128, seed=9)
+    wt1 = ops.empty(900, 32)
+    ops.call("dbm_transpose_f32", f1.data_ptr(), wt1.data_ptr(), 32, 900, ops.stream())
+    assert torch.equal(wt1, f1.view(32, 900).t())
+    wts = torch.cat([f.reshape(32, -1).t() for f in (fx, f2, f3)]).contiguous()
+    out = ops.empty(n, 16, h - 2, w - 2, 8, dtype=torch.bfloat16)
+    ops.call("dbm_stem_fwd_slab8", x.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), wt1.data_ptr(),
+             wts.data_ptr(), bias.data_ptr(), out.data_ptr(), 16, 0, n, h, w, ops.stream())
+    torch.cuda.synchronize()
+    d = torch.double
+    ref = torch.cat([F.conv2d(x.to(d), fx.to(d), bias[:32].to(d)), F.conv2d(w1.to(d), f1.to(d), bias[32:64].to(d), stride=10),
+                     F.conv2d(w2.to(d), f2.to(d), bias[64:96].to(d), stride=2), F.conv2d(w3.to(d), f3.to(d), bias[96:].to(d))],
+                    dim=1)
+    got = ops.slab8_to_nchw(out, 128)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < 4e-3
+    assert rel_l2(got, ref.float().bfloat16().float()) < 2e-4   # only the final bf16 rounding separates them
+
+
 UMMA_CASES = [  # n, cin(read), in_cs_total, h, w, cout_real, cout_pad
     (2, 64, 8, 20, 23, 32, 32), (1, 192, 24, 37, 41, 64, 64), (3, 128, 16, 9, 9, 64, 64),
     (2, 96, 24, 16, 16, 32, 32), (1, 64, 8, 33, 18, 18, 32), (5, 160, 24, 9, 9, 32, 32),
