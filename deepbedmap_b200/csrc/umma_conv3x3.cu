@@ -15,16 +15,12 @@
 // UMMA shared-memory descriptors into that same tile (K-major, no-swizzle core matrices:
 // 8 consecutive pixels x 8 channels = 128 contiguous bytes), so activations cross L2->SMEM
 // 1.27x instead of 9x.
-#include <utility>
-
-#include "common.cuh"
+#include "umma_common.cuh"
 
 namespace dbm {
 
 static int g_debug_swap_lbo_sbo = 0;
 
-constexpr int kTile = 16;              // output unit is kTile x kTile pixels
-constexpr int kHalo = kTile + 2;       // 18
 constexpr int kThreads = 192;          // warp0 TMA, warp1 MMA, warps2-5 epilogue
 
 struct UmmaConvParams {
@@ -49,37 +45,6 @@ struct UmmaCfg {
   static constexpr int TMEM_COLS = 4 * COUT;  // 2 sub-tiles x 2 accumulator buffers
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
 };
-
-// All MMAs of one pipeline stage: 9 taps x (2 sub-tiles x CK/16 k-steps). The tap loop is kept
-// rolled: fully unrolling it makes ptxas hoist all 72 descriptor words, overflow the uniform
-// register file and pay R2UR.FILL / MOV.SPILL around every UTCHMMA.
-template <int COUT, int CK, int IDX>
-__device__ __forceinline__ void issue_one(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                          uint32_t idesc, uint32_t acc) {
-  constexpr int KS = CK / 16;
-  constexpr int j = IDX / KS, ks = IDX % KS;
-  // start-address field advances in 16-byte units: no carry into the LBO field
-  constexpr uint32_t a_off = (uint32_t)((2 * ks) * kHalo * kHalo + 8 * j);
-  constexpr uint32_t b_off = (uint32_t)((2 * ks) * (COUT / 8) * 8);
-  umma_bf16_off<a_off, b_off>(d0 + (uint32_t)(j * COUT), a_lo, a_hi, b_lo, b_hi, idesc, ks != 0 ? 1u : acc);
-}
-template <int COUT, int CK, int... IDX>
-__device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                          uint32_t idesc, uint32_t acc, std::integer_sequence<int, IDX...>) {
-  (issue_one<COUT, CK, IDX>(d0, a_lo, a_hi, b_lo, b_hi, idesc, acc), ...);
-}
-template <int COUT, int CK>
-__device__ __forceinline__ void issue_stage_mmas(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                                 uint32_t b_hi, uint32_t idesc, uint32_t acc0) {
-  constexpr uint32_t kBTap = (uint32_t)((CK / 8) * (COUT / 8) * 8);  // per-tap stride of the packed weights
-#pragma unroll 1
-  for (uint32_t tap = 0; tap < 9; ++tap) {
-    const uint32_t a_tap = a_lo + tap + (tap / 3) * (kHalo - 3);     // ky * 18 + kx
-    const uint32_t b_tap = b_lo + tap * kBTap;
-    issue_tap<COUT, CK>(d0, a_tap, a_hi, b_tap, b_hi, idesc, tap != 0 ? 1u : acc0,
-                        std::make_integer_sequence<int, 2 * (CK / 16)>{});
-  }
-}
 
 template <int COUT, int CK, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -299,7 +264,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // slab8 bf16 tensor [N][CS][H][W][8] viewed as 4-D (W*8, H, CS, N); box = 18 px x 18 rows x CK/8 slabs.
-static int make_slab8_tmap(CUtensorMap* tm, const void* base, int N, int CS, int H, int W, int ck) {
+int make_slab8_tmap(CUtensorMap* tm, const void* base, int N, int CS, int H, int W, int ck) {
   PFN_encodeTiled enc = get_encode();
   DBM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)CS, (cuuint64_t)N};

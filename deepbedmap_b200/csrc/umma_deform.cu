@@ -12,7 +12,7 @@
 
 namespace dbm {
 
-constexpr int kDTileW = 16, kDTileH = 8;   // 128 output pixels per work item
+constexpr int kDTileW = 32, kDTileH = 4;   // 128 output pixels per work item; a warp = one 32-px row
 constexpr int kDStages = 4;
 constexpr int kDGatherThreads = 512;      // 16 warps: 128 px x 4 slab pairs
 constexpr int kDThreads = kDGatherThreads + 32 + 128;  // + MMA warp + 4 epilogue warps
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
       const int n = item / items_per_img;
       const int r = item - n * items_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      const int y = ty * kDTileH + (pix >> 4), x = tx * kDTileW + (pix & 15);
+      const int y = ty * kDTileH + (pix >> 5), x = tx * kDTileW + (pix & 31);
       const bool valid = y < p.H && x < p.W;
       float off[20];
       if (valid) {
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
       const int n = item / items_per_img;
       const int r = item - n * items_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      const int y = ty * kDTileH + (m >> 4), x = tx * kDTileW + (m & 15);
+      const int y = ty * kDTileH + (m >> 5), x = tx * kDTileW + (m & 31);
       const bool valid = y < p.H && x < p.W;
       const int buf = it & 1;
       mbar_wait(&tfull[buf], (it >> 1) & 1);
@@ -277,23 +277,19 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
   }
 }
 
-// ---- final layer: 64 -> 1: four threads per output pixel (two slabs each), shuffle-reduced -----
-__global__ void __launch_bounds__(256) deform_out1_kernel(const __nv_bfloat16* __restrict__ x,
-                                                          const float* __restrict__ off, int off_cs,
-                                                          const float* __restrict__ w,  // (1, 64, 3, 3) fp32
-                                                          const float* __restrict__ bias, float* __restrict__ y,
-                                                          int N, int H, int W) {
+// ---- final layer: 64 -> 1, one thread per output pixel (a warp = 32 consecutive pixels, so every
+// corner load of a warp is one 512-byte run: the kernel is L1-wavefront bound) --------------------
+__global__ void __launch_bounds__(256, 2) deform_out1_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             const float* __restrict__ off, int off_cs,
+                                                             const float* __restrict__ w,  // (1, 64, 3, 3) fp32
+                                                             const float* __restrict__ bias, float* __restrict__ y,
+                                                             int N, int H, int W) {
   __shared__ float sw[9][64];  // [tap][c]
   for (int i = threadIdx.x; i < 576; i += blockDim.x) sw[i % 9][i / 9] = w[i];
   __syncthreads();
   const size_t plane = (size_t)H * W * 8;
   const long total = (long)N * H * W;
-  const int q = threadIdx.x & 3;
-  const long px_per_iter = ((long)gridDim.x * blockDim.x) >> 2;
-  for (long base = ((long)blockIdx.x * blockDim.x) >> 2; base < total; base += px_per_iter) {
-    const long i0 = base + (threadIdx.x >> 2);
-    const bool live = i0 < total;
-    const long i = live ? i0 : total - 1;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int xx = i % W;
     const long r = i / W;
     const int yy = r % H;
@@ -305,25 +301,26 @@ __global__ void __launch_bounds__(256) deform_out1_kernel(const __nv_bfloat16* _
           __ldg(reinterpret_cast<const float4*>(off + ((((size_t)n * off_cs + k) * H + yy) * W + xx) * 4));
       offv[4 * k] = o4.x; offv[4 * k + 1] = o4.y; offv[4 * k + 2] = o4.z; offv[4 * k + 3] = o4.w;
     }
-    const __nv_bfloat16* xin = x + ((size_t)n * 8 + 2 * q) * plane;
-    float acc = 0.f;
+    const __nv_bfloat16* xin = x + (size_t)n * 8 * plane;
+    float acc = bias[0];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const TapPos tp = tap_pos(offv[tap], offv[9 + tap], xx, yy, tap, H, W);
-      Corners cr[2];
-      cr[0] = load_corners(xin, tp);
-      cr[1] = load_corners(xin + plane, tp);
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        float v[8];
-        blend8(cr[k], tp, v);
+      for (int s0 = 0; s0 < 8; s0 += 2) {
+        Corners cr[2];
+        cr[0] = load_corners(xin + s0 * plane, tp);
+        cr[1] = load_corners(xin + (s0 + 1) * plane, tp);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc = fmaf(v[c], sw[tap][(2 * q + k) * 8 + c], acc);
+        for (int k = 0; k < 2; ++k) {
+          float v[8];
+          blend8(cr[k], tp, v);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc = fmaf(v[c], sw[tap][(s0 + k) * 8 + c], acc);
+        }
       }
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (live && q == 0) y[i] = acc + bias[0];
+    y[i] = acc;
   }
 }
 
@@ -362,7 +359,7 @@ extern "C" int dbm_deform_conv_out1(const void* x_slab8, const float* offset_sla
   DBM_REQUIRE(n > 0 && h > 0 && w > 0, "deform_conv_out1: empty input");
   DBM_REQUIRE(offset_cs_total >= 5, "deform_conv_out1: offset tensor needs >= 18 channels (5 slabs)");
   const long total = (long)n * h * w;
-  long blocks = (total * 4 + 255) / 256;
+  long blocks = (total + 255) / 256;
   const long cap = (long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   deform_out1_kernel<<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)x_slab8, offset_slab4, offset_cs_total,

@@ -1,0 +1,327 @@
+// Persistent whole-trunk kernel: pre-residual conv -> 36 residual dense blocks (5 convs each) ->
+// post-residual conv (GeneratorModel.forward, srgan_train.py:541-551, RDB :339-358, RRDB :397-402)
+// as ONE launch instead of 182.
+//
+// Every layer is the same tcgen05 implicit-GEMM 3x3 conv as umma_conv3x3_kernel (TMA halo tile,
+// nine shifted descriptors, fused epilogue); what changes is the scheduling. All (layer, 16x16
+// pixel unit) work items are numbered layer-major and dealt round-robin to one resident CTA per
+// SM. An item of layer L may start once the <= 9 neighbouring units of layer L-1 (its 1-pixel
+// halo) are complete, which each finished item publishes through a global flag
+// (st.global -> fence -> atomicAdd / ld.acquire -> fence.proxy.async -> TMA). That removes the
+// per-layer launch + pipeline fill/drain (~8 us x 182 at continent-tile size) and the tail wave
+// of every layer: CTAs flow into the next layer while the last units of the previous one finish.
+#include "umma_common.cuh"
+
+namespace dbm {
+
+constexpr int kTrunkThreads = 192;  // warp0 TMA + dependency wait, warp1 MMA, warps2-5 epilogue
+constexpr int kTStages = 3;
+constexpr int kTCK = 32;
+constexpr int kTABytes = kHalo * kHalo * kTCK * 2;   // 20736
+constexpr int kTBBytesMax = 9 * kTCK * 64 * 2;       // 36864
+constexpr int kTrunkSmem = kTStages * (kTABytes + kTBBytesMax) + 256 + 1024;
+
+struct TrunkLayer {  // 96 bytes, mirrored by deepbedmap_b200/model.py (TRUNK_LAYER_DTYPE)
+  const __nv_bfloat16* wpacked;
+  const float* bias;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;      // slab4, 16 slabs
+  const float* res1;   // slab4, 16 slabs
+  const float* res2;
+  int cin, cout;       // cout in {32, 64}
+  int in_map, act;     // in_map: 0 = stem output (16 slabs), 1 / 2 = dense-block buffers
+  int up2, out_cs_total;
+  int out_cs0, pad0;
+  float beta;
+  int pad1, pad2, pad3;
+};
+static_assert(sizeof(TrunkLayer) == 96, "TrunkLayer layout is part of the C ABI");
+
+struct TrunkParams {
+  const TrunkLayer* layers;
+  int num_layers;
+  int N, H, W, tiles_x, tiles_y, items_per_layer;
+  unsigned int* done;  // [num_layers][items_per_layer], zeroed before the launch; complete == 4
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {  // L2-coherent load (data written by other SMs)
+  return __ldcg(reinterpret_cast<const float4*>(p));
+}
+
+__global__ void __launch_bounds__(kTrunkThreads, 1)
+umma_trunk_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+                  const __grid_constant__ CUtensorMap tmap2, const TrunkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + kTStages * kTABytes;
+  uint64_t* bars = (uint64_t*)(smem + kTStages * (kTABytes + kTBBytesMax));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kTStages;
+  uint64_t* tfull = bars + 2 * kTStages;
+  uint64_t* tempty = bars + 2 * kTStages + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kTStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap0);
+    tma_prefetch_desc(&tmap1);
+    tma_prefetch_desc(&tmap2);
+    for (int s = 0; s < kTStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int I = p.items_per_layer;
+  const int per_img = p.tiles_x * p.tiles_y;
+  const long total_items = (long)p.num_layers * I;
+
+  if (warp == 0) {
+    // ================= dependency wait + TMA producer (converged warp) =================
+    int s = 0;
+    uint32_t ph = 0;
+    for (long g = blockIdx.x; g < total_items; g += gridDim.x) {
+      const int L = (int)(g / I);
+      const int item = (int)(g - (long)L * I);
+      const int n = item / per_img;
+      const int r = item - n * per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const TrunkLayer* ly = p.layers + L;
+      const int cin = ly->cin, cout = ly->cout, in_map = ly->in_map;
+      const __nv_bfloat16* wp = ly->wpacked;
+      if (L > 0) {
+        // lanes 0..8 each watch one neighbouring unit of the previous layer
+        bool ok = true;
+        if (lane < 9) {
+          const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
+          if (ny >= 0 && ny < p.tiles_y && nx >= 0 && nx < p.tiles_x) {
+            const unsigned int* f = p.done + (size_t)(L - 1) * I + (size_t)n * per_img + ny * p.tiles_x + nx;
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(f) < 4u) {
+              if (++spins > (1u << 24)) {
+                printf("dbm: trunk dependency timeout layer %d item %d\n", L, item);
+                __trap();
+              }
+              __nanosleep(64);
+            }
+          }
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        (void)ok;
+      }
+      const CUtensorMap* tm = in_map == 0 ? &tmap0 : (in_map == 1 ? &tmap1 : &tmap2);
+      const uint32_t b_bytes = (uint32_t)(9 * kTCK * cout * 2);
+      const int num_kc = cin / kTCK;
+      for (int kc = 0; kc < num_kc; ++kc) {
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one_sync()) {
+          // order the acquired flags (generic proxy) before the TMA reads (async proxy)
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          mbar_arrive_expect_tx(&full[s], kTABytes + b_bytes);
+          tma_load_4d(smA + s * kTABytes, tm, &full[s], (tx * kTile - 1) * 8, ty * kTile - 1, kc * (kTCK / 8), n);
+          bulk_load(smB + s * kTBBytesMax, wp + (size_t)kc * (b_bytes / 2), b_bytes, &full[s]);
+        }
+        __syncwarp();
+        if (++s == kTStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: converged warp, one elected lane issues =================
+    const uint32_t a_hi = desc_hi(kHalo * 16);
+    const uint32_t b_hi = desc_hi(128);
+    const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (long g = blockIdx.x; g < total_items; g += gridDim.x, ++it) {
+      const int L = (int)(g / I);
+      const TrunkLayer* ly = p.layers + L;
+      const int cin = ly->cin, cout = ly->cout;
+      const int num_kc = cin / kTCK;
+      const int buf = it & 1;
+      mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * 128);
+      for (int kc = 0; kc < num_kc; ++kc) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_lo = desc_lo(smA_u + s * kTABytes, kHalo * kHalo * 16);
+        const uint32_t acc0 = kc != 0 ? 1u : 0u;
+        if (cout == 32) {
+          const uint32_t b_lo = desc_lo(smB_u + s * kTBBytesMax, 4 * 128);
+          if (elect_one_sync()) {
+            issue_stage_mmas<32, kTCK, 64>(d0, a_lo, a_hi, b_lo, b_hi, umma_idesc_bf16(128, 32), acc0);
+            umma_commit(&empty[s]);
+            if (kc == num_kc - 1) umma_commit(&tfull[buf]);
+          }
+        } else {
+          const uint32_t b_lo = desc_lo(smB_u + s * kTBBytesMax, 8 * 128);
+          if (elect_one_sync()) {
+            issue_stage_mmas<64, kTCK, 64>(d0, a_lo, a_hi, b_lo, b_hi, umma_idesc_bf16(128, 64), acc0);
+            umma_commit(&empty[s]);
+            if (kc == num_kc - 1) umma_commit(&tfull[buf]);
+          }
+        }
+        __syncwarp();
+        if (++s == kTStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue: TMEM -> registers -> HBM, then publish the unit =================
+    const int q = warp & 3;
+    const int m = 32 * q + lane;
+    const int gy = m >> 3, xr = m & 7;
+    int it = 0;
+    for (long g = blockIdx.x; g < total_items; g += gridDim.x, ++it) {
+      const int L = (int)(g / I);
+      const int item = (int)(g - (long)L * I);
+      const int n = item / per_img;
+      const int r = item - n * per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const TrunkLayer ly = p.layers[L];
+      const int buf = it & 1;
+      mbar_wait(&tfull[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const int y = ty * kTile + gy;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int x = tx * kTile + 8 * j + xr;
+        const bool valid = (y < p.H) && (x < p.W);
+        for (int c0 = 0; c0 < ly.cout; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 128 + j * 64 + c0), acc);
+          tmem_wait_ld();
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + __ldg(ly.bias + c0 + i);
+            if (ly.res1) {
+#pragma unroll
+              for (int s4 = 0; s4 < 8; ++s4) {
+                const float4 rr = ld_cg_f4(ly.res1 + ((((size_t)n * 16 + (c0 / 4 + s4)) * p.H + y) * p.W + x) * 4);
+                v[4 * s4 + 0] = rr.x + ly.beta * v[4 * s4 + 0];
+                v[4 * s4 + 1] = rr.y + ly.beta * v[4 * s4 + 1];
+                v[4 * s4 + 2] = rr.z + ly.beta * v[4 * s4 + 2];
+                v[4 * s4 + 3] = rr.w + ly.beta * v[4 * s4 + 3];
+              }
+            }
+            if (ly.res2) {
+#pragma unroll
+              for (int s4 = 0; s4 < 8; ++s4) {
+                const float4 rr = ld_cg_f4(ly.res2 + ((((size_t)n * 16 + (c0 / 4 + s4)) * p.H + y) * p.W + x) * 4);
+                v[4 * s4 + 0] = rr.x + ly.beta * v[4 * s4 + 0];
+                v[4 * s4 + 1] = rr.y + ly.beta * v[4 * s4 + 1];
+                v[4 * s4 + 2] = rr.z + ly.beta * v[4 * s4 + 2];
+                v[4 * s4 + 3] = rr.w + ly.beta * v[4 * s4 + 3];
+              }
+            }
+            if (ly.act) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
+            }
+            if (ly.out_f32) {
+#pragma unroll
+              for (int s4 = 0; s4 < 8; ++s4)
+                *reinterpret_cast<float4*>(ly.out_f32 + ((((size_t)n * 16 + (c0 / 4 + s4)) * p.H + y) * p.W + x) * 4) =
+                    make_float4(v[4 * s4], v[4 * s4 + 1], v[4 * s4 + 2], v[4 * s4 + 3]);
+            }
+            if (ly.out_bf16) {
+#pragma unroll
+              for (int s8 = 0; s8 < 4; ++s8) {
+                uint4 o;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * s8 + 0], v[8 * s8 + 1]);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * s8 + 2], v[8 * s8 + 3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * s8 + 4], v[8 * s8 + 5]);
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * s8 + 6], v[8 * s8 + 7]);
+                o.x = *reinterpret_cast<uint32_t*>(&t0);
+                o.y = *reinterpret_cast<uint32_t*>(&t1);
+                o.z = *reinterpret_cast<uint32_t*>(&t2);
+                o.w = *reinterpret_cast<uint32_t*>(&t3);
+                const size_t cs = (size_t)n * ly.out_cs_total + (ly.out_cs0 + c0 / 8 + s8);
+                if (!ly.up2) {
+                  *reinterpret_cast<uint4*>(ly.out_bf16 + ((cs * p.H + y) * p.W + x) * 8) = o;
+                } else {
+                  const int Ho = 2 * p.H, Wo = 2 * p.W;
+                  __nv_bfloat16* base = ly.out_bf16 + ((cs * Ho + 2 * y) * Wo + 2 * x) * 8;
+                  *reinterpret_cast<uint4*>(base) = o;
+                  *reinterpret_cast<uint4*>(base + 8) = o;
+                  *reinterpret_cast<uint4*>(base + (size_t)Wo * 8) = o;
+                  *reinterpret_cast<uint4*>(base + (size_t)Wo * 8 + 8) = o;
+                }
+              }
+            }
+          }
+        }
+      }
+      // release TMEM to the MMA warp, then publish the finished unit (device-scope release)
+      tc_fence_before();
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tempty[buf]);
+        atomicAdd(p.done + (size_t)L * I + item, 1u);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+}  // namespace dbm
+
+using namespace dbm;
+
+extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
+                              int stem_cs_total, const void* cat_a_slab8, const void* cat_b_slab8, int cat_cs_total,
+                              unsigned int* flags_dev, cudaStream_t stream) {
+  DBM_REQUIRE(num_layers > 0 && n > 0 && h > 0 && w > 0, "trunk: empty problem");
+  DBM_REQUIRE(((uintptr_t)layers_dev & 7) == 0, "trunk: layer table must be 8-byte aligned");
+  CUtensorMap tm0, tm1, tm2;
+  int rc = make_slab8_tmap(&tm0, stem_slab8, n, stem_cs_total, h, w, kTCK);
+  if (rc) return rc;
+  rc = make_slab8_tmap(&tm1, cat_a_slab8, n, cat_cs_total, h, w, kTCK);
+  if (rc) return rc;
+  rc = make_slab8_tmap(&tm2, cat_b_slab8, n, cat_cs_total, h, w, kTCK);
+  if (rc) return rc;
+  TrunkParams p;
+  p.layers = (const TrunkLayer*)layers_dev;
+  p.num_layers = num_layers;
+  p.N = n; p.H = h; p.W = w;
+  p.tiles_x = ceil_div(w, kTile); p.tiles_y = ceil_div(h, kTile);
+  p.items_per_layer = n * p.tiles_x * p.tiles_y;
+  p.done = flags_dev;
+  DBM_CUDA(cudaMemsetAsync(flags_dev, 0, (size_t)num_layers * p.items_per_layer * sizeof(unsigned int), stream));
+  static bool attr_done = false;
+  if (!attr_done) {
+    DBM_CUDA(cudaFuncSetAttribute(umma_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmem));
+    attr_done = true;
+  }
+  const long total = (long)num_layers * p.items_per_layer;
+  // every CTA must be co-resident (items spin on flags set by other CTAs): one CTA per SM
+  const int grid = total < num_sms() ? (int)total : num_sms();
+  umma_trunk_kernel<<<grid, kTrunkThreads, kTrunkSmem, stream>>>(tm0, tm1, tm2, p);
+  return check_launch("umma_trunk_kernel");
+}

@@ -19,6 +19,14 @@ from . import layout, ops
 from . import npz as npz_io
 
 
+# mirror of struct TrunkLayer in csrc/umma_trunk.cu (96 bytes)
+TRUNK_LAYER_DTYPE = np.dtype([("wpacked", "<u8"), ("bias", "<u8"), ("out_bf16", "<u8"), ("out_f32", "<u8"),
+                              ("res1", "<u8"), ("res2", "<u8"), ("cin", "<i4"), ("cout", "<i4"), ("in_map", "<i4"),
+                              ("act", "<i4"), ("up2", "<i4"), ("out_cs_total", "<i4"), ("out_cs0", "<i4"),
+                              ("pad0", "<i4"), ("beta", "<f4"), ("pad1", "<i4"), ("pad2", "<i4"), ("pad3", "<i4")])
+assert TRUNK_LAYER_DTYPE.itemsize == 96
+
+
 class Variable:
     """Minimal stand-in for chainer.Variable: callers only use ``.array`` / ``.shape``
     (srgan_train.py:1137, 1229, 1450; deepbedmap.py:421, 733)."""
@@ -143,6 +151,8 @@ class GeneratorModel(_Link):
         super().__init__(shapes, layout.init_values(shapes, seed, init_scale))
         self._packed_version = -1
         self._packed = {}
+        self._ws = {}
+        self.persistent_trunk = True
         self._ctx = None
 
     # ---- serialisation (chainer.serializers.load_npz / save_npz, App. C layout) ----
@@ -404,51 +414,90 @@ class GeneratorModel(_Link):
         self._packed_version = self.version
         return pk
 
-    def _forward_bf16(self, x, w1, w2, w3):
-        P = self.p
+    def _trunk_workspace(self, n, H, W):
+        """Per-shape persistent buffers of the trunk + the device layer table of the persistent
+        trunk kernel (pointers are baked into the table, so the buffers are cached)."""
+        key = (n, H, W)
+        ws = self._ws.get(key)
         pk = self._pack()
+        if ws is not None and ws["version"] == self._packed_version:
+            return ws
+        bf = torch.bfloat16
         g = self.inter_channels
         cc = 64 + 4 * g
         ccs = cc // 8
         beta = self.residual_scaling
-        n, _, h, w = x.shape
-        H, W = h - 2, w - 2
-        bf = torch.bfloat16
-        s0 = ops.empty(n, 16, H, W, 8, dtype=bf)
-        wt1, wts, bias128 = pk["stem"]
-        ops.call("dbm_stem_fwd_slab8", x.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), wt1.data_ptr(),
-                 wts.data_ptr(), bias128.data_ptr(), s0.data_ptr(), 16, 0, n, h, w, ops.stream())
-        cat = [ops.empty(n, ccs, H, W, 8, dtype=bf) for _ in range(2)]
-        a1_f32 = ops.empty(n, 16, H, W, 4)
-        f32 = [ops.empty(n, 16, H, W, 4) for _ in range(3)]
-        wq, bq = pk["pre_residual_conv_layer"]
-        ops.conv3x3_umma(s0, 128, wq, bq, 64, act=True, out=cat[0], out_f32=a1_f32)
-        cur, cur_f32 = 0, a1_f32
-        fi = 0
+        if ws is None:
+            ws = dict(s0=ops.empty(n, 16, H, W, 8, dtype=bf), cat=[ops.empty(n, ccs, H, W, 8, dtype=bf) for _ in range(2)],
+                      a1_f32=ops.empty(n, 16, H, W, 4), f32=[ops.empty(n, 16, H, W, 4) for _ in range(3)],
+                      u1=ops.empty(n, 8, 2 * H, 2 * W, 8, dtype=bf))
+        cat, f32, a1_f32 = ws["cat"], ws["f32"], ws["a1_f32"]
+        layers = []
+
+        def layer(key, cin, cout, in_map, act=0, beta_=0.0, out=None, out_cs0=0, out_f32=None, res1=None, res2=None,
+                  up2=0):
+            wq, bq = pk[key]
+            layers.append((wq.data_ptr(), bq.data_ptr(), out.data_ptr() if out is not None else 0,
+                           out_f32.data_ptr() if out_f32 is not None else 0,
+                           res1.data_ptr() if res1 is not None else 0, res2.data_ptr() if res2 is not None else 0,
+                           cin, cout, in_map, act, up2, out.shape[1] if out is not None else 0, out_cs0, 0,
+                           beta_, 0, 0, 0))
+
+        layer("pre_residual_conv_layer", 128, 64, 0, act=1, out=cat[0], out_f32=a1_f32)
+        cur, cur_f32, fi = 0, a1_f32, 0
         for i in range(self.num_residual_blocks):
             rrdb_in = cur_f32
             for r in (1, 2, 3):
                 pre = self._rdb_prefix(i, r)
                 for k in (1, 2, 3, 4):
                     cin = 64 + (k - 1) * g
-                    wq, bq = pk[f"{pre}/conv_layer{k}"]
-                    ops.conv3x3_umma(cat[cur], cin, wq, bq, g, act=True, out=cat[cur], out_cs0=cin // 8)
-                wq, bq = pk[f"{pre}/conv_layer5"]
-                # pick an fp32 buffer that is neither the RDB input nor the RRDB input
+                    layer(f"{pre}/conv_layer{k}", cin, g, 1 + cur, act=1, out=cat[cur], out_cs0=cin // 8)
+                # fp32 residual buffer that is neither the RDB input nor the RRDB input
                 while f32[fi] is cur_f32 or f32[fi] is rrdb_in:
                     fi = (fi + 1) % 3
                 nxt_f32 = f32[fi]
-                ops.conv3x3_umma(cat[cur], cc, wq, bq, 64, beta=beta, out=cat[1 - cur], out_f32=nxt_f32, res1=cur_f32,
-                                 res2=rrdb_in if r == 3 else None)
+                layer(f"{pre}/conv_layer5", cc, 64, 1 + cur, beta_=beta, out=cat[1 - cur], out_f32=nxt_f32, res1=cur_f32,
+                      res2=rrdb_in if r == 3 else None)
                 cur, cur_f32 = 1 - cur, nxt_f32
-        u1 = ops.empty(n, 8, 2 * H, 2 * W, 8, dtype=bf)
-        wq, bq = pk["post_residual_conv_layer"]
-        ops.conv3x3_umma(cat[cur], 64, wq, bq, 64, beta=1.0, up2=True, out=u1, res1=a1_f32)
-        del cat, f32
+        layer("post_residual_conv_layer", 64, 64, 1 + cur, beta_=1.0, out=ws["u1"], res1=a1_f32, up2=1)
+        table = np.array(layers, dtype=TRUNK_LAYER_DTYPE)
+        ws["layers"] = layers
+        ws["table"] = torch.from_numpy(table.view(np.uint8).copy()).cuda()
+        tiles = ((H + 15) // 16) * ((W + 15) // 16)
+        ws["flags"] = ops.empty(len(layers) * n * tiles, dtype=torch.int32)
+        ws["version"] = self._packed_version
+        self._ws[key] = ws
+        return ws
+
+    def _run_trunk(self, ws, n, H, W):
+        if self.persistent_trunk:
+            ops.call("dbm_trunk_umma", ws["table"].data_ptr(), len(ws["layers"]), n, H, W, ws["s0"].data_ptr(), 16,
+                     ws["cat"][0].data_ptr(), ws["cat"][1].data_ptr(), ws["cat"][0].shape[1], ws["flags"].data_ptr(),
+                     ops.stream())
+            return
+        # one launch per layer (kept for A/B measurements of the persistent kernel)
+        srcs = (ws["s0"], ws["cat"][0], ws["cat"][1])
+        for (wq, bq, out, out_f32, res1, res2, cin, cout, in_map, act, up2, out_cs_total, out_cs0, _p0, beta_, *_r) in \
+                ws["layers"]:
+            inp = srcs[in_map]
+            ops.call("dbm_conv3x3_umma", inp.data_ptr(), inp.shape[1], cin, wq, bq, cout, n, H, W, float(beta_), act, up2,
+                     out or None, out_cs_total, out_cs0, out_f32 or None, 16, 0, res1 or None, res2 or None, ops.stream())
+
+    def _forward_bf16(self, x, w1, w2, w3):
+        P = self.p
+        pk = self._pack()
+        n, _, h, w = x.shape
+        H, W = h - 2, w - 2
+        bf = torch.bfloat16
+        ws = self._trunk_workspace(n, H, W)
+        wt1, wts, bias128 = pk["stem"]
+        ops.call("dbm_stem_fwd_slab8", x.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), wt1.data_ptr(),
+                 wts.data_ptr(), bias128.data_ptr(), ws["s0"].data_ptr(), 16, 0, n, h, w, ops.stream())
+        self._run_trunk(ws, n, H, W)
+        u1 = ws["u1"]
         u2 = ops.empty(n, 8, 4 * H, 4 * W, 8, dtype=bf)
         wq, bq = pk["post_upsample_conv_layer_1"]
         ops.conv3x3_umma(u1, 64, wq, bq, 64, act=True, up2=True, out=u2)
-        del u1
         f1 = ops.empty(n, 8, 4 * H, 4 * W, 8, dtype=bf)
         wq, bq = pk["post_upsample_conv_layer_2"]
         ops.conv3x3_umma(u2, 64, wq, bq, 64, act=True, out=f1)

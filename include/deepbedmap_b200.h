@@ -102,6 +102,15 @@ int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void*
                      int out_cs_total, int out_cs0, float* out_f32_slab4, int out_f32_cs_total, int out_f32_cs0,
                      const float* res1_slab4, const float* res2_slab4, cudaStream_t stream);
 
+/* Persistent whole-trunk kernel: pre-residual conv + 3*nb residual dense blocks + post-residual conv
+ * (srgan_train.py:541-551) in ONE launch; `layers_dev` is a device array of `num_layers` 96-byte records
+ * (struct TrunkLayer in csrc/umma_trunk.cu: weight/bias/output/residual pointers, cin, cout, input
+ * buffer id {0 = stem_slab8, 1 = cat_a, 2 = cat_b}, epilogue flags), flags_dev holds
+ * num_layers * n * ceil(h/16) * ceil(w/16) uint32 (zeroed by the call). */
+int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
+                   int stem_cs_total, const void* cat_a_slab8, const void* cat_b_slab8, int cat_cs_total,
+                   unsigned int* flags_dev, cudaStream_t stream);
+
 /* ---- fused generator input block for the tensor-core path (DeepbedmapInputBlock.forward,
  * srgan_train.py:256-266): four valid strided convs + F.concat, fp32 math, 128-channel bf16 slab8 out.
  * Filters are passed tap-major (dbm_transpose_f32 of the (32, taps) Chainer filters):
