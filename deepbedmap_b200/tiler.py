@@ -89,6 +89,17 @@ def gather_and_assemble(results: torch.Tensor, plan, final_shape, ary_shape, ran
 
 
 # ---- device side -----------------------------------------------------------------------------------
+def _check_grids(X, W1, W2, W3):
+    for a, c in ((X, 1), (W1, 1), (W2, 2), (W3, 1)):
+        if a.ndim != 4 or a.shape[0] != 1 or a.shape[1] != c:
+            raise ValueError(f"continent grids must be (1,C,H,W); got {tuple(a.shape)}")
+    Hs, Ws = X.shape[2], X.shape[3]
+    if tuple(W1.shape[2:]) != (10 * Hs, 10 * Ws) or tuple(W2.shape[2:]) != (2 * Hs, 2 * Ws) or \
+            tuple(W3.shape[2:]) != (Hs, Ws):
+        raise ValueError("W1/W2/W3 must be 10x/2x/1x the BEDMAP2 grid")
+    return Hs, Ws
+
+
 class ContinentGrids:
     """The four input rasters resident on the device: X (1,1,H,W), W1 (1,1,10H,10W), W2 (1,2,2H,2W),
     W3 (1,1,H,W); the reference's shapes are 4502x5502 etc. (deepbedmap.ipynb:1519). ``row0`` is the
@@ -96,45 +107,98 @@ class ContinentGrids:
 
     def __init__(self, X, W1, W2, W3, rows: Optional[Tuple[int, int]] = None):
         from .model import as_device
-        for a, c in ((X, 1), (W1, 1), (W2, 2), (W3, 1)):
-            if a.ndim != 4 or a.shape[0] != 1 or a.shape[1] != c:
-                raise ValueError(f"continent grids must be (1,C,H,W); got {tuple(a.shape)}")
-        Hs, Ws = X.shape[2], X.shape[3]
-        if tuple(W1.shape[2:]) != (10 * Hs, 10 * Ws) or tuple(W2.shape[2:]) != (2 * Hs, 2 * Ws) or \
-                tuple(W3.shape[2:]) != (Hs, Ws):
-            raise ValueError("W1/W2/W3 must be 10x/2x/1x the BEDMAP2 grid")
-        self.full_rows = Hs
+        Hs, _ = _check_grids(X, W1, W2, W3)
         r0, r1 = rows if rows is not None else (0, Hs)
         self.row0 = r0
         self.X = as_device(X[:, :, r0:r1])
         self.W1 = as_device(W1[:, :, 10 * r0:10 * r1])
         self.W2 = as_device(W2[:, :, 2 * r0:2 * r1])
         self.W3 = as_device(W3[:, :, r0:r1])
+        self._uploaded = None  # fully resident
 
     @property
     def rows(self):
         return self.row0, self.row0 + self.X.shape[2]
 
+    def ensure_rows(self, upto: int, prefetch_upto: Optional[int] = None):
+        """Resident grids: nothing to do."""
+
+
+class StreamedGrids(ContinentGrids):
+    """Host grids uploaded band by band on a side stream while earlier tile rows are computing
+    (the host->device copy of the 10.9 GB continent overlaps the generator)."""
+
+    def __init__(self, X, W1, W2, W3, rows: Optional[Tuple[int, int]] = None):
+        from . import ops
+        Hs, Ws = _check_grids(X, W1, W2, W3)
+        r0, r1 = rows if rows is not None else (0, Hs)
+        self.row0 = r0
+        nr = r1 - r0
+        to_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a, dtype=np.float32))
+        self._host = [to_t(a) for a in (X, W1, W2, W3)]
+        if any(t.dtype != torch.float32 for t in self._host):
+            self._host = [t.float() for t in self._host]
+        self.X = ops.empty(1, 1, nr, Ws)
+        self.W1 = ops.empty(1, 1, 10 * nr, 10 * Ws)
+        self.W2 = ops.empty(1, 2, 2 * nr, 2 * Ws)
+        self.W3 = ops.empty(1, 1, nr, Ws)
+        self._dev = [self.X, self.W1, self.W2, self.W3]
+        self._scale = [1, 10, 2, 1]
+        self._done = 0  # lowres rows (relative to row0) already enqueued
+        self._events = []
+        self._stream = torch.cuda.Stream()
+        self._stream.wait_stream(torch.cuda.current_stream())
+
+    def _enqueue(self, upto: int):
+        upto = min(upto - self.row0, self.X.shape[2])
+        if upto > self._done:
+            with torch.cuda.stream(self._stream):
+                for host, dev, sc in zip(self._host, self._dev, self._scale):
+                    a, b = sc * self._done, sc * upto
+                    ha = sc * self.row0
+                    for c in range(dev.shape[1]):
+                        dev[0, c, a:b].copy_(host[0, c, ha + a:ha + b], non_blocking=True)
+                self._events.append((upto, self._stream.record_event()))
+            self._done = upto
+
+    def ensure_rows(self, upto: int, prefetch_upto: Optional[int] = None):
+        """Enqueue the upload of lowres rows up to ``prefetch_upto`` (one tile row ahead) on the copy
+        stream and make the compute stream wait only for the rows < ``upto`` it is about to read."""
+        self._enqueue(upto)
+        need = min(upto - self.row0, self.X.shape[2])
+        for rows_done, ev in self._events:
+            if rows_done >= need:
+                torch.cuda.current_stream().wait_event(ev)
+                break
+        if prefetch_upto is not None:
+            self._enqueue(prefetch_upto)
+
 
 def predict_continent(model, X, W1, W2, W3, final_shape=(18000, 22000), ary_shape=(1000, 1000),
                       stride=(1000, 1000), xtrapad=(18, 18), batch_tiles: int = 4, to_host: bool = True,
-                      grids: Optional[ContinentGrids] = None):
+                      grids: Optional[ContinentGrids] = None, out: Optional[torch.Tensor] = None):
     """Returns Y_hat (1, final_y, final_x) float32 (NumPy if ``to_host`` else a CUDA tensor), NaN
-    where the reference leaves NaN. On ranks != 0 of a distributed run returns None."""
+    where the reference leaves NaN. On ranks != 0 of a distributed run returns None.
+    ``out``: optional pinned host tensor (1, final_y, final_x) to receive the result without a
+    pageable staging copy."""
     from . import ops
     dist, rank, world = _dist()
     plan = tile_plan(final_shape, ary_shape, stride, xtrapad)
     a, b = rank_tile_range(len(plan), rank, world)
     if grids is None:
         band = rank_row_band(plan, rank, world) if world > 1 else None
-        grids = ContinentGrids(X, W1, W2, W3, rows=band)
+        on_device = all(isinstance(t, torch.Tensor) and t.is_cuda for t in (X, W1, W2, W3))
+        grids = (ContinentGrids if on_device else StreamedGrids)(X, W1, W2, W3, rows=band)
     g = grids
     Hs, Ws = g.X.shape[2], g.X.shape[3]
     r0, r1 = g.rows
     for (y0, y1, x0, x1, *_r) in plan[a:b]:
         if y0 < r0 or y1 > r1 or x1 > Ws:
             raise ValueError("final_shape exceeds the input grids")
-    groups = group_by_shape([(i, plan[i]) for i in range(a, b)])
+    # tile rows in order (so a streamed upload can stay just ahead), same-shape tiles batched
+    rows_of_tiles: "OrderedDict[int, List]" = OrderedDict()
+    for i in range(a, b):
+        rows_of_tiles.setdefault(plan[i][0], []).append((i, plan[i]))
     py, px = xtrapad[0] * 4, xtrapad[1] * 4
     single = world == 1
     st = ops.stream
@@ -145,37 +209,41 @@ def predict_continent(model, X, W1, W2, W3, final_shape=(18000, 22000), ary_shap
     else:
         results = ops.empty(max_tiles_per_rank(len(plan), world), ary_shape[0], ary_shape[1])
         ops.fill(results, float("nan"))
-    for (h, w), tiles in groups.items():
-        for b0 in range(0, len(tiles), batch_tiles):
-            chunk = tiles[b0:b0 + batch_tiles]
-            nb = len(chunk)
-            xb = ops.empty(nb, 1, h, w)
-            w1b = ops.empty(nb, 1, 10 * h, 10 * w)
-            w2b = ops.empty(nb, 2, 2 * h, 2 * w)
-            w3b = ops.empty(nb, 1, h, w)
-            for j, (_, (y0, y1, x0, x1, *_r)) in enumerate(chunk):
-                yy = y0 - r0
-                ops.call("dbm_crop_clip_f32", g.X.data_ptr(), Hs, Ws, xb[j].data_ptr(), 1, yy, x0, h, w, 0, st())
-                ops.call("dbm_crop_clip_f32", g.W1.data_ptr(), 10 * Hs, 10 * Ws, w1b[j].data_ptr(), 1, 10 * yy, 10 * x0,
-                         10 * h, 10 * w, 1, st())
-                ops.call("dbm_crop_clip_f32", g.W2.data_ptr(), 2 * Hs, 2 * Ws, w2b[j].data_ptr(), 2, 2 * yy, 2 * x0,
-                         2 * h, 2 * w, 1, st())
-                ops.call("dbm_crop_clip_f32", g.W3.data_ptr(), Hs, Ws, w3b[j].data_ptr(), 1, yy, x0, h, w, 1, st())
-            y = model.forward(xb, w1b, w2b, w3b).array  # (nb, 1, 4(h-2), 4(w-2))
-            th, tw = y.shape[2], y.shape[3]
-            for j, (i, (y0, y1, x0, x1, ys, ye, xs, xe)) in enumerate(chunk):
-                hh, ww = ye - ys, xe - xs
-                # the reference assigns Y_pred[72:-72, 72:-72] into Y_hat[ys:ye, xs:xe] and raises
-                # ValueError on a shape mismatch (deepbedmap.py:734-738)
-                if (th - 2 * py, tw - 2 * px) != (hh, ww):
-                    raise ValueError(f"could not broadcast tile {(th - 2 * py, tw - 2 * px)} into {(hh, ww)}")
-                if single:
-                    ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, canvas.data_ptr(), final_shape[0],
-                             final_shape[1], ys, xs, hh, ww, st())
-                else:
-                    ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, results[i - a].data_ptr(),
-                             ary_shape[0], ary_shape[1], 0, 0, hh, ww, st())
-            del y, xb, w1b, w2b, w3b
+    row_list = list(rows_of_tiles.values())
+    for k, row_tiles in enumerate(row_list):
+        nxt = max(t[1] for _, t in row_list[k + 1]) if k + 1 < len(row_list) else None
+        g.ensure_rows(max(t[1] for _, t in row_tiles), prefetch_upto=nxt)
+        for (h, w), tiles in group_by_shape(row_tiles).items():
+            for b0 in range(0, len(tiles), batch_tiles):
+                chunk = tiles[b0:b0 + batch_tiles]
+                nb = len(chunk)
+                xb = ops.empty(nb, 1, h, w)
+                w1b = ops.empty(nb, 1, 10 * h, 10 * w)
+                w2b = ops.empty(nb, 2, 2 * h, 2 * w)
+                w3b = ops.empty(nb, 1, h, w)
+                for j, (_, (y0, y1, x0, x1, *_r)) in enumerate(chunk):
+                    yy = y0 - r0
+                    ops.call("dbm_crop_clip_f32", g.X.data_ptr(), Hs, Ws, xb[j].data_ptr(), 1, yy, x0, h, w, 0, st())
+                    ops.call("dbm_crop_clip_f32", g.W1.data_ptr(), 10 * Hs, 10 * Ws, w1b[j].data_ptr(), 1, 10 * yy,
+                             10 * x0, 10 * h, 10 * w, 1, st())
+                    ops.call("dbm_crop_clip_f32", g.W2.data_ptr(), 2 * Hs, 2 * Ws, w2b[j].data_ptr(), 2, 2 * yy, 2 * x0,
+                             2 * h, 2 * w, 1, st())
+                    ops.call("dbm_crop_clip_f32", g.W3.data_ptr(), Hs, Ws, w3b[j].data_ptr(), 1, yy, x0, h, w, 1, st())
+                y = model.forward(xb, w1b, w2b, w3b).array  # (nb, 1, 4(h-2), 4(w-2))
+                th, tw = y.shape[2], y.shape[3]
+                for j, (i, (y0, y1, x0, x1, ys, ye, xs, xe)) in enumerate(chunk):
+                    hh, ww = ye - ys, xe - xs
+                    # the reference assigns Y_pred[72:-72, 72:-72] into Y_hat[ys:ye, xs:xe] and raises
+                    # ValueError on a shape mismatch (deepbedmap.py:734-738)
+                    if (th - 2 * py, tw - 2 * px) != (hh, ww):
+                        raise ValueError(f"could not broadcast tile {(th - 2 * py, tw - 2 * px)} into {(hh, ww)}")
+                    if single:
+                        ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, canvas.data_ptr(),
+                                 final_shape[0], final_shape[1], ys, xs, hh, ww, st())
+                    else:
+                        ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, results[i - a].data_ptr(),
+                                 ary_shape[0], ary_shape[1], 0, 0, hh, ww, st())
+                del y, xb, w1b, w2b, w3b
     if not single:
         def new_canvas():
             c = ops.empty(final_shape[0], final_shape[1])
@@ -189,5 +257,13 @@ def predict_continent(model, X, W1, W2, W3, final_shape=(18000, 22000), ary_shap
         canvas = gather_and_assemble(results, plan, final_shape, ary_shape, rank, world, new_canvas, place)
         if canvas is None:
             return None
-    out = canvas.view(1, final_shape[0], final_shape[1])
-    return out.cpu().numpy() if to_host else out
+    res = canvas.view(1, final_shape[0], final_shape[1])
+    if not to_host:
+        return res
+    if out is not None:
+        if tuple(out.shape) != tuple(res.shape) or out.dtype != torch.float32 or out.is_cuda:
+            raise ValueError("out must be a host float32 tensor of shape (1, final_y, final_x)")
+        out.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out.numpy()
+    return res.cpu().numpy()
