@@ -13,8 +13,8 @@
 namespace dbm {
 
 constexpr int kDTileW = 32, kDTileH = 4;   // 128 output pixels per work item; a warp = one 32-px row
-constexpr int kDStages = 4;
-constexpr int kDGatherThreads = 512;      // 16 warps: 128 px x 4 slab pairs
+constexpr int kDStages = 3;                // stage s holds taps s, s+3, s+6 (filled by tap-slot s)
+constexpr int kDGatherThreads = 384;       // 12 warps: 128 px x 3 tap slots (each thread: all 64 channels of one tap)
 constexpr int kDThreads = kDGatherThreads + 32 + 128;  // + MMA warp + 4 epilogue warps
 constexpr int kDABytes = 128 * 64 * 2;                 // one tap: 128 px x 64 ch bf16
 constexpr int kDBBytes = 9 * 64 * 64 * 2;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDStages; ++s) {
-      mbar_init(&full[s], kDGatherThreads / 32);  // one arrive per gather warp
+      mbar_init(&full[s], 4);   // one arrive per gather warp of the slot (128 threads)
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -145,50 +145,54 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
 
   if (warp < kMmaWarp) {
     // ======================= gather warps =======================
+    // thread = (pixel, tap slot): the sampling position of a tap is computed once per pixel and
+    // all 8 slabs (64 channels) of that tap are gathered by the same thread.
     const int t = threadIdx.x;
-    const int pix = t & 127, sg = t >> 7;
-    int s = 0;
-    uint32_t ph = 0;
+    const int pix = t & 127, slot = t >> 7;
+    uint32_t fills = 0;
+    uint8_t* a = smA + slot * kDABytes;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int n = item / items_per_img;
       const int r = item - n * items_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const int y = ty * kDTileH + (pix >> 5), x = tx * kDTileW + (pix & 31);
       const bool valid = y < p.H && x < p.W;
-      float off[20];
+      float odx[3], ody[3];
       if (valid) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-          const float4 o4 = __ldg(reinterpret_cast<const float4*>(
-              p.off + ((((size_t)n * p.off_cs + q) * p.H + y) * p.W + x) * 4));
-          off[4 * q] = o4.x; off[4 * q + 1] = o4.y; off[4 * q + 2] = o4.z; off[4 * q + 3] = o4.w;
+        for (int k = 0; k < 3; ++k) {
+          const int tap = slot + 3 * k;
+          odx[k] = __ldg(p.off + ((((size_t)n * p.off_cs + (tap >> 2)) * p.H + y) * p.W + x) * 4 + (tap & 3));
+          ody[k] = __ldg(p.off + ((((size_t)n * p.off_cs + ((9 + tap) >> 2)) * p.H + y) * p.W + x) * 4 + ((9 + tap) & 3));
         }
       }
       const __nv_bfloat16* xin = p.x + (size_t)n * 8 * plane;
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* a = smA + s * kDABytes;
+      for (int k = 0; k < 3; ++k, ++fills) {
+        const int tap = slot + 3 * k;
+        mbar_wait(&empty[slot], (fills & 1) ^ 1);
         if (valid) {
-          const TapPos tp = tap_pos(off[tap], off[9 + tap], x, y, tap, p.H, p.W);
-          Corners cr[2];
+          const TapPos tp = tap_pos(odx[k], ody[k], x, y, tap, p.H, p.W);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) cr[k] = load_corners(xin + (sg * 2 + k) * plane, tp);
+          for (int s0 = 0; s0 < 8; s0 += 4) {
+            Corners cr[4];
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            float v[8];
-            blend8(cr[k], tp, v);
-            *reinterpret_cast<uint4*>(a + ((size_t)(sg * 2 + k) * 128 + pix) * 16) = pack8(v);
+            for (int q = 0; q < 4; ++q) cr[q] = load_corners(xin + (s0 + q) * plane, tp);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float v[8];
+              blend8(cr[q], tp, v);
+              *reinterpret_cast<uint4*>(a + ((size_t)(s0 + q) * 128 + pix) * 16) = pack8(v);
+            }
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            *reinterpret_cast<uint4*>(a + ((size_t)(sg * 2 + k) * 128 + pix) * 16) = make_uint4(0, 0, 0, 0);
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(a + ((size_t)q * 128 + pix) * 16) = make_uint4(0, 0, 0, 0);
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
-        if (++s == kDStages) { s = 0; ph ^= 1; }
+        if (lane == 0) mbar_arrive(&full[slot]);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -205,8 +209,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
     constexpr uint32_t a_hi = desc_hi(128u), b_hi = desc_hi(128u);
     const uint32_t smA_u = smem_u32(smA);
     const uint32_t b_lo = desc_lo(smem_u32(smB), 1024u);
-    int s = 0;
-    uint32_t ph = 0;
+    uint32_t phbits = 0;  // bit s = parity the MMA warp waits for on full[s]
     int it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -215,7 +218,8 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
       const uint32_t d = tmem_base + (uint32_t)(buf * 64);
 #pragma unroll 1
       for (int tap = 0; tap < 9; ++tap) {
-        mbar_wait(&full[s], ph);
+        const int s = tap % 3;
+        mbar_wait(&full[s], (phbits >> s) & 1u);
         tc_fence_after();
         const uint32_t a_lo = desc_lo(smA_u + s * kDABytes, 2048u);
         const uint32_t bt_lo = b_lo + (uint32_t)(tap * 8 * 8 * 8);  // tap stride = 8 slabs x 8 groups x 128 B
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
           if (tap == 8) umma_commit(&tfull[buf]);
         }
         __syncwarp();
-        if (++s == kDStages) { s = 0; ph ^= 1; }
+        phbits ^= 1u << s;
       }
     }
   } else {
@@ -277,23 +281,53 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
   }
 }
 
-// ---- final layer: 64 -> 1, one thread per output pixel (a warp = 32 consecutive pixels, so every
-// corner load of a warp is one 512-byte run: the kernel is L1-wavefront bound) --------------------
-__global__ void __launch_bounds__(256, 2) deform_out1_kernel(const __nv_bfloat16* __restrict__ x,
-                                                             const float* __restrict__ off, int off_cs,
-                                                             const float* __restrict__ w,  // (1, 64, 3, 3) fp32
-                                                             const float* __restrict__ bias, float* __restrict__ y,
-                                                             int N, int H, int W) {
-  __shared__ float sw[9][64];  // [tap][c]
+// ---- final layer: 64 -> 1 -------------------------------------------------------------------------
+// Bilinear sampling is linear, so  y = b + sum_tap sample( sum_c w[c,tap] * x[c] , pos_tap ):
+// project the 64 channels onto the 9 taps FIRST (a 1x1 conv 64 -> 9 at integer pixels, 576 MAC per
+// pixel, fully coalesced), then sample the nine scalar fields. The gather shrinks from
+// 9 taps x 4 corners x 64 channels to 9 x 4 scalars per pixel (the direct form is L1-wavefront and
+// issue bound: 288 16-byte gathers + ~5k instructions per pixel).
+__global__ void __launch_bounds__(256) deform_out1_project_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                  const float* __restrict__ w,  // (1,64,3,3)
+                                                                  float* __restrict__ proj,     // [N][9][H*W]
+                                                                  int N, int HW) {
+  __shared__ float sw[9][64];
   for (int i = threadIdx.x; i < 576; i += blockDim.x) sw[i % 9][i / 9] = w[i];
   __syncthreads();
-  const size_t plane = (size_t)H * W * 8;
-  const long total = (long)N * H * W;
+  const long total = (long)N * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / HW, px = i - n * HW;
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+#pragma unroll
+    for (int slab = 0; slab < 8; ++slab) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((n * 8 + slab) * HW + px) * 8));
+      const float f[8] = {__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
+                          __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u),
+                          __uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u),
+                          __uint_as_float(v.w << 16), __uint_as_float(v.w & 0xffff0000u)};
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[t] = fmaf(f[c], sw[t][slab * 8 + c], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) proj[(n * 9 + t) * HW + px] = acc[t];
+  }
+}
+
+__global__ void __launch_bounds__(256) deform_out1_sample_kernel(const float* __restrict__ proj,
+                                                                 const float* __restrict__ off, int off_cs,
+                                                                 const float* __restrict__ bias,
+                                                                 float* __restrict__ y, int N, int H, int W) {
+  const int HW = H * W;
+  const long total = (long)N * HW;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int xx = i % W;
     const long r = i / W;
     const int yy = r % H;
-    const int n = r / H;
+    const long n = r / H;
     float offv[20];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -301,24 +335,15 @@ __global__ void __launch_bounds__(256, 2) deform_out1_kernel(const __nv_bfloat16
           __ldg(reinterpret_cast<const float4*>(off + ((((size_t)n * off_cs + k) * H + yy) * W + xx) * 4));
       offv[4 * k] = o4.x; offv[4 * k + 1] = o4.y; offv[4 * k + 2] = o4.z; offv[4 * k + 3] = o4.w;
     }
-    const __nv_bfloat16* xin = x + (size_t)n * 8 * plane;
     float acc = bias[0];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const TapPos tp = tap_pos(offv[tap], offv[9 + tap], xx, yy, tap, H, W);
-#pragma unroll
-      for (int s0 = 0; s0 < 8; s0 += 2) {
-        Corners cr[2];
-        cr[0] = load_corners(xin + s0 * plane, tp);
-        cr[1] = load_corners(xin + (s0 + 1) * plane, tp);
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          float v[8];
-          blend8(cr[k], tp, v);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc = fmaf(v[c], sw[tap][(s0 + k) * 8 + c], acc);
-        }
-      }
+      const float* pl = proj + (n * 9 + tap) * HW;
+      acc = fmaf(tp.w00, __ldg(pl + tp.o00), acc);
+      acc = fmaf(tp.w01, __ldg(pl + tp.o01), acc);
+      acc = fmaf(tp.w10, __ldg(pl + tp.o10), acc);
+      acc = fmaf(tp.w11, __ldg(pl + tp.o11), acc);
     }
     y[i] = acc;
   }
@@ -354,15 +379,20 @@ extern "C" int dbm_deform_conv_umma(const void* x_slab8, const float* offset_sla
 }
 
 extern "C" int dbm_deform_conv_out1(const void* x_slab8, const float* offset_slab4, int offset_cs_total,
-                                    const float* w_f32, const float* bias, float* y, int n, int h, int w,
-                                    cudaStream_t stream) {
+                                    const float* w_f32, const float* bias, float* y, float* proj_scratch, int n,
+                                    int h, int w, cudaStream_t stream) {
   DBM_REQUIRE(n > 0 && h > 0 && w > 0, "deform_conv_out1: empty input");
   DBM_REQUIRE(offset_cs_total >= 5, "deform_conv_out1: offset tensor needs >= 18 channels (5 slabs)");
+  DBM_REQUIRE(proj_scratch != nullptr, "deform_conv_out1: needs a scratch buffer of n*9*h*w floats");
   const long total = (long)n * h * w;
   long blocks = (total + 255) / 256;
   const long cap = (long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  deform_out1_kernel<<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)x_slab8, offset_slab4, offset_cs_total,
-                                                      w_f32, bias, y, n, h, w);
-  return check_launch("deform_out1_kernel");
+  deform_out1_project_kernel<<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)x_slab8, w_f32, proj_scratch, n,
+                                                              h * w);
+  int rc = check_launch("deform_out1_project_kernel");
+  if (rc) return rc;
+  deform_out1_sample_kernel<<<(int)blocks, 256, 0, stream>>>(proj_scratch, offset_slab4, offset_cs_total, bias, y, n,
+                                                             h, w);
+  return check_launch("deform_out1_sample_kernel");
 }

@@ -160,8 +160,9 @@ def deform_conv_out1(x_s8, off_s4, w, bias):
     n, cs, h, wd, _ = x_s8.shape
     assert cs == 8 and tuple(w.shape) == (1, 64, 3, 3)
     y = empty(n, 1, h, wd)
+    proj = empty(n, 9, h, wd)
     call("dbm_deform_conv_out1", x_s8.data_ptr(), off_s4.data_ptr(), off_s4.shape[1], w.data_ptr(), bias.data_ptr(),
-         y.data_ptr(), n, h, wd, stream())
+         y.data_ptr(), proj.data_ptr(), n, h, wd, stream())
     return y
 
 

@@ -129,8 +129,9 @@ int dbm_stem_fwd_slab8(const float* x, const float* w1, const float* w2, const f
 int dbm_deform_conv_umma(const void* x_slab8, const float* offset_slab4, int offset_cs_total,
                          const void* wpacked_ck64, const float* bias, int n, int h, int w, int act, void* out_slab8,
                          int out_cs_total, int out_cs0, cudaStream_t stream);
+/* proj_scratch: n*9*h*w floats (the 64 channels projected onto the 9 taps before sampling) */
 int dbm_deform_conv_out1(const void* x_slab8, const float* offset_slab4, int offset_cs_total, const float* w_f32,
-                         const float* bias, float* y, int n, int h, int w, cudaStream_t stream);
+                         const float* bias, float* y, float* proj_scratch, int n, int h, int w, cudaStream_t stream);
 
 /* ---- deformable convolution, fp32 path (L.DeformableConvolution2D, srgan_train.py:506-523) -----
  * cols[n][c*9+t][pixel] = bilinear sample; contraction with W (O, C*9) is a dbm_gemm_f32 call.
