@@ -324,7 +324,8 @@ extern "C" int dbm_debug_set(int key, int value) {
 
 extern "C" int dbm_pack_conv3x3_weights(const float* w_oihw, void* packed_bf16, int cout, int cin, int cout_padded,
                                         int ck, cudaStream_t stream) {
-  DBM_REQUIRE(ck == 32 || ck == 64, "pack: K-chunk %d must be 32 (conv3x3_umma) or 64 (deform_conv_umma)", ck);
+  DBM_REQUIRE(ck == 16 || ck == 32 || ck == 64,
+              "pack: K-chunk %d must be 16 / 32 (conv3x3_umma, trunk) or 64 (deform_conv_umma)", ck);
   DBM_REQUIRE(cin % ck == 0, "pack: Cin=%d must be a multiple of %d", cin, ck);
   DBM_REQUIRE(cout_padded == 32 || cout_padded == 64, "pack: padded Cout=%d must be 32 or 64", cout_padded);
   DBM_REQUIRE(cout <= cout_padded, "pack: Cout=%d > padded %d", cout, cout_padded);

@@ -15,11 +15,17 @@
 namespace dbm {
 
 constexpr int kTrunkThreads = 192;  // warp0 TMA + dependency wait, warp1 MMA, warps2-5 epilogue
-constexpr int kTStages = 3;
-constexpr int kTCK = 32;
-constexpr int kTABytes = kHalo * kHalo * kTCK * 2;   // 20736
-constexpr int kTBBytesMax = 9 * kTCK * 64 * 2;       // 36864
+// K-chunk per pipeline stage: 32 channels for 32-wide layers, 16 for 64-wide layers, so that both
+// kinds of layer use the same 18432-byte weight stage and the ring has 5 stages (4 x 1650 MMA
+// cycles of cover for a ~3000-cycle TMA round trip; with 3 x 57.6 KB stages the issuer starved).
+constexpr int kTStages = 5;
+constexpr int kTABytes = kHalo * kHalo * 32 * 2;     // 20736 (half used when the chunk is 16 channels)
+constexpr int kTBBytesMax = 9 * 32 * 32 * 2;         // 18432 = 9*32*32*2 = 9*16*64*2
 constexpr int kTrunkSmem = kTStages * (kTABytes + kTBBytesMax) + 256 + 1024;
+
+struct TrunkMaps {  // [input buffer][0: 32-channel box, 1: 16-channel box]
+  CUtensorMap m[3][2];
+};
 
 struct TrunkLayer {  // 96 bytes, mirrored by deepbedmap_b200/model.py (TRUNK_LAYER_DTYPE)
   const __nv_bfloat16* wpacked;
@@ -54,8 +60,7 @@ __device__ __forceinline__ float4 ld_cg_f4(const float* p) {  // L2-coherent loa
 }
 
 __global__ void __launch_bounds__(kTrunkThreads, 1)
-umma_trunk_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
-                  const __grid_constant__ CUtensorMap tmap2, const TrunkParams p) {
+umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = smem;
@@ -71,9 +76,10 @@ umma_trunk_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_consta
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap0);
-    tma_prefetch_desc(&tmap1);
-    tma_prefetch_desc(&tmap2);
+    for (int i = 0; i < 3; ++i) {
+      tma_prefetch_desc(&maps.m[i][0]);
+      tma_prefetch_desc(&maps.m[i][1]);
+    }
     for (int s = 0; s < kTStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -127,17 +133,18 @@ umma_trunk_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_consta
         ok = __all_sync(0xffffffffu, ok);
         (void)ok;
       }
-      const CUtensorMap* tm = in_map == 0 ? &tmap0 : (in_map == 1 ? &tmap1 : &tmap2);
-      const uint32_t b_bytes = (uint32_t)(9 * kTCK * cout * 2);
-      const int num_kc = cin / kTCK;
+      const int ck = cout == 32 ? 32 : 16;
+      const CUtensorMap* tm = &maps.m[in_map][cout == 32 ? 0 : 1];
+      const uint32_t a_bytes = (uint32_t)(kHalo * kHalo * ck * 2);
+      const int num_kc = cin / ck;
       for (int kc = 0; kc < num_kc; ++kc) {
         mbar_wait(&empty[s], ph ^ 1);
         if (elect_one_sync()) {
           // order the acquired flags (generic proxy) before the TMA reads (async proxy)
           asm volatile("fence.proxy.async.global;" ::: "memory");
-          mbar_arrive_expect_tx(&full[s], kTABytes + b_bytes);
-          tma_load_4d(smA + s * kTABytes, tm, &full[s], (tx * kTile - 1) * 8, ty * kTile - 1, kc * (kTCK / 8), n);
-          bulk_load(smB + s * kTBBytesMax, wp + (size_t)kc * (b_bytes / 2), b_bytes, &full[s]);
+          mbar_arrive_expect_tx(&full[s], a_bytes + kTBBytesMax);
+          tma_load_4d(smA + s * kTABytes, tm, &full[s], (tx * kTile - 1) * 8, ty * kTile - 1, kc * (ck / 8), n);
+          bulk_load(smB + s * kTBBytesMax, wp + (size_t)kc * (kTBBytesMax / 2), kTBBytesMax, &full[s]);
         }
         __syncwarp();
         if (++s == kTStages) { s = 0; ph ^= 1; }
@@ -155,7 +162,7 @@ umma_trunk_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_consta
       const int L = (int)(g / I);
       const TrunkLayer* ly = p.layers + L;
       const int cin = ly->cin, cout = ly->cout;
-      const int num_kc = cin / kTCK;
+      const int num_kc = cin / (cout == 32 ? 32 : 16);
       const int buf = it & 1;
       mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -168,14 +175,14 @@ umma_trunk_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_consta
         if (cout == 32) {
           const uint32_t b_lo = desc_lo(smB_u + s * kTBBytesMax, 4 * 128);
           if (elect_one_sync()) {
-            issue_stage_mmas<32, kTCK, 64>(d0, a_lo, a_hi, b_lo, b_hi, umma_idesc_bf16(128, 32), acc0);
+            issue_stage_mmas<32, 32, 64>(d0, a_lo, a_hi, b_lo, b_hi, umma_idesc_bf16(128, 32), acc0);
             umma_commit(&empty[s]);
             if (kc == num_kc - 1) umma_commit(&tfull[buf]);
           }
         } else {
           const uint32_t b_lo = desc_lo(smB_u + s * kTBBytesMax, 8 * 128);
           if (elect_one_sync()) {
-            issue_stage_mmas<64, kTCK, 64>(d0, a_lo, a_hi, b_lo, b_hi, umma_idesc_bf16(128, 64), acc0);
+            issue_stage_mmas<64, 16, 64>(d0, a_lo, a_hi, b_lo, b_hi, umma_idesc_bf16(128, 64), acc0);
             umma_commit(&empty[s]);
             if (kc == num_kc - 1) umma_commit(&tfull[buf]);
           }
@@ -299,13 +306,14 @@ extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int
                               unsigned int* flags_dev, cudaStream_t stream) {
   DBM_REQUIRE(num_layers > 0 && n > 0 && h > 0 && w > 0, "trunk: empty problem");
   DBM_REQUIRE(((uintptr_t)layers_dev & 7) == 0, "trunk: layer table must be 8-byte aligned");
-  CUtensorMap tm0, tm1, tm2;
-  int rc = make_slab8_tmap(&tm0, stem_slab8, n, stem_cs_total, h, w, kTCK);
-  if (rc) return rc;
-  rc = make_slab8_tmap(&tm1, cat_a_slab8, n, cat_cs_total, h, w, kTCK);
-  if (rc) return rc;
-  rc = make_slab8_tmap(&tm2, cat_b_slab8, n, cat_cs_total, h, w, kTCK);
-  if (rc) return rc;
+  TrunkMaps maps;
+  const void* bases[3] = {stem_slab8, cat_a_slab8, cat_b_slab8};
+  const int cs_tot[3] = {stem_cs_total, cat_cs_total, cat_cs_total};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 2; ++j) {
+      int rc = make_slab8_tmap(&maps.m[i][j], bases[i], n, cs_tot[i], h, w, j == 0 ? 32 : 16);
+      if (rc) return rc;
+    }
   TrunkParams p;
   p.layers = (const TrunkLayer*)layers_dev;
   p.num_layers = num_layers;
@@ -322,6 +330,6 @@ extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int
   const long total = (long)num_layers * p.items_per_layer;
   // every CTA must be co-resident (items spin on flags set by other CTAs): one CTA per SM
   const int grid = total < num_sms() ? (int)total : num_sms();
-  umma_trunk_kernel<<<grid, kTrunkThreads, kTrunkSmem, stream>>>(tm0, tm1, tm2, p);
+  umma_trunk_kernel<<<grid, kTrunkThreads, kTrunkSmem, stream>>>(maps, p);
   return check_launch("umma_trunk_kernel");
 }

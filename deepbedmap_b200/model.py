@@ -372,7 +372,7 @@ class GeneratorModel(_Link):
         P = self.p
         pk = {}
 
-        def add(key, cout_padded):
+        def add(key, cout_padded, trunk=False):
             w = P[f"{key}/W"]
             b = P[f"{key}/b"]
             if b.numel() < cout_padded:
@@ -381,6 +381,11 @@ class GeneratorModel(_Link):
             else:
                 bp = b
             pk[key] = (ops.pack_conv3x3(w, cout_padded), bp)
+            if trunk and cout_padded == 64:
+                # the persistent trunk kernel streams 64-wide layers in 16-channel chunks
+                pk[key + "@trunk"] = (ops.pack_conv3x3(w, cout_padded, ck=16), bp)
+            elif trunk:
+                pk[key + "@trunk"] = pk[key]
 
         # stem filters, tap-major, and the concatenated stem bias
         def tapmajor(keys):
@@ -397,14 +402,15 @@ class GeneratorModel(_Link):
             ops.axpby(P[f"input_block/conv_on_{k}/b"].view(1, 32, 1, 1), 0, None, 0,
                       bias128.view(1, 128, 1, 1), 32 * j, 32, 1.0, 0.0)
         pk["stem"] = (tapmajor(("W1",)), tapmajor(("X", "W2", "W3")), bias128)
-        add("pre_residual_conv_layer", 64)
+        add("pre_residual_conv_layer", 64, trunk=True)
         for i in range(self.num_residual_blocks):
             for r in (1, 2, 3):
                 pre = self._rdb_prefix(i, r)
                 for k in (1, 2, 3, 4):
-                    add(f"{pre}/conv_layer{k}", self.inter_channels)
-                add(f"{pre}/conv_layer5", 64)
-        for key in ("post_residual_conv_layer", "post_upsample_conv_layer_1", "post_upsample_conv_layer_2"):
+                    add(f"{pre}/conv_layer{k}", self.inter_channels, trunk=True)
+                add(f"{pre}/conv_layer5", 64, trunk=True)
+        add("post_residual_conv_layer", 64, trunk=True)
+        for key in ("post_upsample_conv_layer_1", "post_upsample_conv_layer_2"):
             add(key, 64)
         add("final_conv_layer1/offset_conv", 32)
         add("final_conv_layer2/offset_conv", 32)
@@ -420,7 +426,7 @@ class GeneratorModel(_Link):
         key = (n, H, W)
         ws = self._ws.get(key)
         pk = self._pack()
-        if ws is not None and ws["version"] == self._packed_version:
+        if ws is not None and ws["version"] == (self._packed_version, self.persistent_trunk):
             return ws
         bf = torch.bfloat16
         g = self.inter_channels
@@ -436,7 +442,7 @@ class GeneratorModel(_Link):
 
         def layer(key, cin, cout, in_map, act=0, beta_=0.0, out=None, out_cs0=0, out_f32=None, res1=None, res2=None,
                   up2=0):
-            wq, bq = pk[key]
+            wq, bq = pk[key + "@trunk"] if self.persistent_trunk else pk[key]
             layers.append((wq.data_ptr(), bq.data_ptr(), out.data_ptr() if out is not None else 0,
                            out_f32.data_ptr() if out_f32 is not None else 0,
                            res1.data_ptr() if res1 is not None else 0, res2.data_ptr() if res2 is not None else 0,
@@ -465,7 +471,7 @@ class GeneratorModel(_Link):
         ws["table"] = torch.from_numpy(table.view(np.uint8).copy()).cuda()
         tiles = ((H + 15) // 16) * ((W + 15) // 16)
         ws["flags"] = ops.empty(len(layers) * n * tiles, dtype=torch.int32)
-        ws["version"] = self._packed_version
+        ws["version"] = (self._packed_version, self.persistent_trunk)
         self._ws[key] = ws
         return ws
 
