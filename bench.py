@@ -195,7 +195,7 @@ def instrumented_roofline(model, grids, kw, peak_tf):
         if name == "dbm_trunk_umma":
             n, h, w = a[2], a[3], a[4]
             ws = model._ws[(n, h, w)]
-            fl = sum(2.0 * 9 * ly[6] * ly[7] * n * h * w for ly in ws["layers"])
+            fl = ws["flops"]
             recs["umma_trunk_kernel"].append((e0, e1, fl))
         else:
             cin, coutp, n, h, w = a[2], a[5], a[6], a[7], a[8]

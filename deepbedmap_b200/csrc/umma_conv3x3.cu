@@ -20,6 +20,8 @@
 namespace dbm {
 
 static int g_debug_swap_lbo_sbo = 0;
+static int g_debug_ck16 = 0;   // 64-wide layers in 16-channel chunks (the trunk kernel's summation order)
+extern int g_trunk_debug;
 
 constexpr int kThreads = 192;          // warp0 TMA, warp1 MMA, warps2-5 epilogue
 
@@ -294,6 +296,26 @@ static int launch_umma(const CUtensorMap& tm, const UmmaConvParams& p, cudaStrea
 }
 
 // fp32 OIHW 3x3 weights -> bf16 UMMA operand image [Cin/CK][9][CK/8][COUTP/8][8][8]
+// Same operand image, filled from a channel slice of a wider filter: rows [o0, o0 + O) of the
+// image take w[o][c0 + c][tap] (o < O, c < Cin) of an (O, CinTotal, 3, 3) filter; other rows are
+// left untouched, so several filters can be stacked along Cout (dense-block layer pairing).
+__global__ void pack_w3x3_slice_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int o0,
+                                       int Cin, int CinTotal, int c0, int COUTP, int CK) {
+  const long total = (long)9 * Cin * COUTP;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int c8 = t % 8; t /= 8;
+    const int o8 = t % 8; t /= 8;
+    const int cg = t % (COUTP / 8); t /= (COUTP / 8);
+    const int ksl = t % (CK / 8); t /= (CK / 8);
+    const int tap = t % 9; t /= 9;
+    const int kc = (int)t;
+    const int o = cg * 8 + o8 - o0;
+    const int c = kc * CK + ksl * 8 + c8;
+    if (o >= 0 && o < O) out[i] = __float2bfloat16_rn(w[((long)o * CinTotal + c0 + c) * 9 + tap]);
+  }
+}
+
 __global__ void pack_w3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int Cin,
                                  int COUTP, int CK) {
   const long total = (long)9 * Cin * COUTP;
@@ -319,6 +341,8 @@ using namespace dbm;
 
 extern "C" int dbm_debug_set(int key, int value) {
   if (key == 1) g_debug_swap_lbo_sbo = value;
+  if (key == 2) g_debug_ck16 = value;
+  if (key == 3) g_trunk_debug = value;
   return DBM_OK;
 }
 
@@ -333,6 +357,20 @@ extern "C" int dbm_pack_conv3x3_weights(const float* w_oihw, void* packed_bf16, 
   pack_w3x3_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w_oihw, (__nv_bfloat16*)packed_bf16, cout, cin,
                                                              cout_padded, ck);
   return check_launch("pack_w3x3_kernel");
+}
+
+extern "C" int dbm_pack_conv3x3_weights_slice(const float* w_oihw, int w_cin_total, int w_c0, void* packed_bf16,
+                                              int cout, int cout0, int cin, int cout_padded, int ck,
+                                              cudaStream_t stream) {
+  DBM_REQUIRE(ck == 16 || ck == 32 || ck == 64, "pack: K-chunk %d must be 16, 32 or 64", ck);
+  DBM_REQUIRE(cin % ck == 0 && w_c0 >= 0 && w_c0 + cin <= w_cin_total, "pack: bad channel slice [%d, %d) of %d",
+              w_c0, w_c0 + cin, w_cin_total);
+  DBM_REQUIRE(cout_padded % 8 == 0 && cout0 >= 0 && cout0 + cout <= cout_padded, "pack: bad Cout rows [%d, %d) of %d",
+              cout0, cout0 + cout, cout_padded);
+  const long total = (long)9 * cin * cout_padded;
+  pack_w3x3_slice_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w_oihw, (__nv_bfloat16*)packed_bf16, cout, cout0,
+                                                                   cin, w_cin_total, w_c0, cout_padded, ck);
+  return check_launch("pack_w3x3_slice_kernel");
 }
 
 extern "C" int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void* wpacked,
@@ -358,5 +396,10 @@ extern "C" int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, 
   p.out_f32 = out_f32_slab4; p.out_f32_cs_total = out_f32_cs_total; p.out_f32_cs0 = out_f32_cs0;
   p.res1 = res1_slab4; p.res2 = res2_slab4;
   if (cout_padded == 32) return launch_umma<32, 32, 5>(tm, p, stream);
+  if (g_debug_ck16) {
+    rc = make_slab8_tmap(&tm, in_slab8, n, in_cs_total, h, w, 16);
+    if (rc) return rc;
+    return launch_umma<64, 16, 5>(tm, p, stream);
+  }
   return launch_umma<64, 32, 3>(tm, p, stream);
 }

@@ -14,40 +14,52 @@
 
 namespace dbm {
 
-constexpr int kTrunkThreads = 192;  // warp0 TMA + dependency wait, warp1 MMA, warps2-5 epilogue
+constexpr int kTrunkThreads = 320;  // warp0 TMA + dependency wait, warp1 MMA, warps2-9 epilogue
+constexpr int kEpiWarps = 8;        // two warps per TMEM lane quadrant, one per 8x16-pixel sub-tile
 // K-chunk per pipeline stage: 32 channels for 32-wide layers, 16 for 64-wide layers, so that both
 // kinds of layer use the same 18432-byte weight stage and the ring has 5 stages (4 x 1650 MMA
 // cycles of cover for a ~3000-cycle TMA round trip; with 3 x 57.6 KB stages the issuer starved).
 constexpr int kTStages = 5;
 constexpr int kTABytes = kHalo * kHalo * 32 * 2;     // 20736 (half used when the chunk is 16 channels)
 constexpr int kTBBytesMax = 9 * 32 * 32 * 2;         // 18432 = 9*32*32*2 = 9*16*64*2
-constexpr int kTrunkSmem = kTStages * (kTABytes + kTBBytesMax) + 256 + 1024;
+constexpr int kMaxTrunkLayers = 512;                 // 23 RRDB (config 5's deepest) = 347 passes
+constexpr int kTrunkSmem = kTStages * (kTABytes + kTBBytesMax) + 256 + kMaxTrunkLayers * 24 + 1024;
 
 struct TrunkMaps {  // [input buffer][0: 32-channel box, 1: 16-channel box]
   CUtensorMap m[3][2];
 };
 
-struct TrunkLayer {  // 96 bytes, mirrored by deepbedmap_b200/model.py (TRUNK_LAYER_DTYPE)
+// One MMA pass: out[:, 0:cout] = conv3x3(in[:, 8*in_cs0 : 8*in_cs0 + cin]) with the packed filter.
+// Columns [0, cout_main) take the fused epilogue (bias, residuals, LeakyReLU, bf16 / fp32 stores);
+// columns [cout_main, cout) are a *partial* pre-activation of a later layer that shares this
+// layer's input (dense-block pairing, see model.py) and are stashed raw as fp32 slab4.
+struct TrunkLayer {  // 128 bytes, mirrored by deepbedmap_b200/model.py (TRUNK_LAYER_DTYPE)
   const __nv_bfloat16* wpacked;
   const float* bias;
   __nv_bfloat16* out_bf16;
   float* out_f32;      // slab4, 16 slabs
-  const float* res1;   // slab4, 16 slabs
-  const float* res2;
-  int cin, cout;       // cout in {32, 64}
-  int in_map, act;     // in_map: 0 = stem output (16 slabs), 1 / 2 = dense-block buffers
-  int up2, out_cs_total;
-  int out_cs0, pad0;
+  const float* res1;   // slab4, res1_cs_total slabs
+  const float* res2;   // slab4, 16 slabs
+  float* stash_out;    // slab4, (cout - cout_main) / 4 slabs
+  int cin, cout;       // cout (MMA N) in {32, 64}
+  int in_map, in_cs0;  // in_map: 0 = stem output (16 slabs), 1 / 2 = dense-block buffers
+  int act, up2;
+  int out_cs_total, out_cs0;
+  int cout_main, res1_cs_total;
   float beta;
-  int pad1, pad2, pad3;
+  int pad[7];
 };
-static_assert(sizeof(TrunkLayer) == 96, "TrunkLayer layout is part of the C ABI");
+static_assert(sizeof(TrunkLayer) == 128, "TrunkLayer layout is part of the C ABI");
+
+extern int g_trunk_debug;
 
 struct TrunkParams {
   const TrunkLayer* layers;
   int num_layers;
   int N, H, W, tiles_x, tiles_y, items_per_layer;
-  unsigned int* done;  // [num_layers][items_per_layer], zeroed before the launch; complete == 4
+  unsigned int* done;  // [num_layers][items_per_layer], zeroed before the launch; complete == kEpiWarps
+  int debug;           // ablation mask for tuning runs (results invalid): 1 no dependency wait, 2 no epilogue
+                       // memory traffic, 4 no TMA loads
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -71,10 +83,19 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
   uint64_t* tfull = bars + 2 * kTStages;
   uint64_t* tempty = bars + 2 * kTStages + 2;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kTStages + 4);
+  // per-layer scalars the producer / MMA warps need for every item, staged once in shared memory
+  // (the epilogue's gpu-scope fences keep invalidating L1, a global read per item costs an L2 trip)
+  int4* linfo = (int4*)(smem + kTStages * (kTABytes + kTBBytesMax) + 256);         // {cin, cout, in_map, in_cs0}
+  const __nv_bfloat16** lw = (const __nv_bfloat16**)(linfo + kMaxTrunkLayers);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  for (int L = threadIdx.x; L < p.num_layers; L += kTrunkThreads) {
+    const TrunkLayer* ly = p.layers + L;
+    linfo[L] = make_int4(ly->cin, ly->cout, ly->in_map, ly->in_cs0);
+    lw[L] = ly->wpacked;
+  }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 3; ++i) {
       tma_prefetch_desc(&maps.m[i][0]);
@@ -86,7 +107,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);
+      mbar_init(&tempty[b], kEpiWarps / 2);
     }
     fence_mbar_init();
   }
@@ -110,18 +131,17 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       const int n = item / per_img;
       const int r = item - n * per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      const TrunkLayer* ly = p.layers + L;
-      const int cin = ly->cin, cout = ly->cout, in_map = ly->in_map;
-      const __nv_bfloat16* wp = ly->wpacked;
-      if (L > 0) {
+      const int4 li = linfo[L];
+      const int cin = li.x, cout = li.y, in_map = li.z, in_cs0 = li.w;
+      const __nv_bfloat16* wp = lw[L];
+      if (L > 0 && !(p.debug & 1)) {
         // lanes 0..8 each watch one neighbouring unit of the previous layer
-        bool ok = true;
         if (lane < 9) {
           const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
           if (ny >= 0 && ny < p.tiles_y && nx >= 0 && nx < p.tiles_x) {
             const unsigned int* f = p.done + (size_t)(L - 1) * I + (size_t)n * per_img + ny * p.tiles_x + nx;
             uint32_t spins = 0;
-            while (ld_acquire_gpu(f) < 4u) {
+            while (ld_acquire_gpu(f) < (unsigned)(kEpiWarps / 2)) {
               if (++spins > (1u << 24)) {
                 printf("dbm: trunk dependency timeout layer %d item %d\n", L, item);
                 __trap();
@@ -130,8 +150,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
             }
           }
         }
-        ok = __all_sync(0xffffffffu, ok);
-        (void)ok;
+        __syncwarp();
       }
       const int ck = cout == 32 ? 32 : 16;
       const CUtensorMap* tm = &maps.m[in_map][cout == 32 ? 0 : 1];
@@ -140,11 +159,16 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       for (int kc = 0; kc < num_kc; ++kc) {
         mbar_wait(&empty[s], ph ^ 1);
         if (elect_one_sync()) {
-          // order the acquired flags (generic proxy) before the TMA reads (async proxy)
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          mbar_arrive_expect_tx(&full[s], a_bytes + kTBBytesMax);
-          tma_load_4d(smA + s * kTABytes, tm, &full[s], (tx * kTile - 1) * 8, ty * kTile - 1, kc * (ck / 8), n);
-          bulk_load(smB + s * kTBBytesMax, wp + (size_t)kc * (kTBBytesMax / 2), kTBBytesMax, &full[s]);
+          if (p.debug & 4) {
+            mbar_arrive(&full[s]);
+          } else {
+            // order the acquired flags (generic proxy) before the TMA reads (async proxy)
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            mbar_arrive_expect_tx(&full[s], a_bytes + kTBBytesMax);
+            tma_load_4d(smA + s * kTABytes, tm, &full[s], (tx * kTile - 1) * 8, ty * kTile - 1,
+                        in_cs0 + kc * (ck / 8), n);
+            bulk_load(smB + s * kTBBytesMax, wp + (size_t)kc * (kTBBytesMax / 2), kTBBytesMax, &full[s]);
+          }
         }
         __syncwarp();
         if (++s == kTStages) { s = 0; ph ^= 1; }
@@ -160,8 +184,8 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
     int it = 0;
     for (long g = blockIdx.x; g < total_items; g += gridDim.x, ++it) {
       const int L = (int)(g / I);
-      const TrunkLayer* ly = p.layers + L;
-      const int cin = ly->cin, cout = ly->cout;
+      const int4 li = linfo[L];
+      const int cin = li.x, cout = li.y;
       const int num_kc = cin / (cout == 32 ? 32 : 16);
       const int buf = it & 1;
       mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
@@ -193,97 +217,164 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
     }
   } else {
     // ================= epilogue: TMEM -> registers -> HBM, then publish the unit =================
+    // Two groups of four warps (warp w may touch TMEM lanes 32*(w%4)..+31). Group e handles the
+    // CTA's items with (it & 1) == e, i.e. always TMEM accumulator buffer e, so consecutive items'
+    // epilogues (residual loads, stores, the release fence) overlap each other. The accumulator is
+    // handed back to the MMA warp as soon as its last column block is in registers.
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int m = 32 * q + lane;
     const int gy = m >> 3, xr = m & 7;
-    int it = 0;
-    for (long g = blockIdx.x; g < total_items; g += gridDim.x, ++it) {
+    const bool mem = !(p.debug & 2);
+    const size_t plane = (size_t)p.H * p.W;
+    int it = grp;
+    for (long g = blockIdx.x + (long)grp * gridDim.x; g < total_items; g += 2L * gridDim.x, it += 2) {
       const int L = (int)(g / I);
       const int item = (int)(g - (long)L * I);
       const int n = item / per_img;
       const int r = item - n * per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const TrunkLayer ly = p.layers[L];
-      const int buf = it & 1;
-      mbar_wait(&tfull[buf], (it >> 1) & 1);
-      tc_fence_after();
       const int y = ty * kTile + gy;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int x = tx * kTile + 8 * j + xr;
-        const bool valid = (y < p.H) && (x < p.W);
-        for (int c0 = 0; c0 < ly.cout; c0 += 32) {
-          uint32_t acc[32];
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 128 + j * 64 + c0), acc);
-          tmem_wait_ld();
-          if (valid) {
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + __ldg(ly.bias + c0 + i);
-            if (ly.res1) {
-#pragma unroll
-              for (int s4 = 0; s4 < 8; ++s4) {
-                const float4 rr = ld_cg_f4(ly.res1 + ((((size_t)n * 16 + (c0 / 4 + s4)) * p.H + y) * p.W + x) * 4);
-                v[4 * s4 + 0] = rr.x + ly.beta * v[4 * s4 + 0];
-                v[4 * s4 + 1] = rr.y + ly.beta * v[4 * s4 + 1];
-                v[4 * s4 + 2] = rr.z + ly.beta * v[4 * s4 + 2];
-                v[4 * s4 + 3] = rr.w + ly.beta * v[4 * s4 + 3];
-              }
+      const int x0 = tx * kTile + xr;
+      const int nbc = ly.cout >> 5;            // 32-column blocks per sub-tile
+      const int nblk = 2 * nbc;                // sub-tile-major
+      float4 r1[8], r2[8];
+      const bool pre = mem && (y < p.H) && (x0 < p.W) && ly.cout_main > 0;
+      // Addends of the first block are fetched before the accumulator is even complete. They were
+      // written by the same unit of earlier passes; (L-1, item) complete implies all of those are
+      // (dependencies are transitive), and this warp must acquire that flag itself: the producer
+      // warp's acquire is only inherited through tfull, which has not been waited on yet.
+      if (L > 0 && (ly.res1 || ly.res2) && !(p.debug & 1)) {
+        if (lane == 0) {
+          const unsigned int* f = p.done + (size_t)(L - 1) * I + item;
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(f) < (unsigned)(kEpiWarps / 2)) {
+            if (++spins > (1u << 24)) {
+              printf("dbm: trunk epilogue dependency timeout layer %d item %d\n", L, item);
+              __trap();
             }
-            if (ly.res2) {
+            __nanosleep(32);
+          }
+        }
+        __syncwarp();
+      }
+      if (pre && ly.res1) {
+        const float* rp = ly.res1 + (((size_t)n * ly.res1_cs_total) * plane + (size_t)y * p.W + x0) * 4;
 #pragma unroll
-              for (int s4 = 0; s4 < 8; ++s4) {
-                const float4 rr = ld_cg_f4(ly.res2 + ((((size_t)n * 16 + (c0 / 4 + s4)) * p.H + y) * p.W + x) * 4);
-                v[4 * s4 + 0] = rr.x + ly.beta * v[4 * s4 + 0];
-                v[4 * s4 + 1] = rr.y + ly.beta * v[4 * s4 + 1];
-                v[4 * s4 + 2] = rr.z + ly.beta * v[4 * s4 + 2];
-                v[4 * s4 + 3] = rr.w + ly.beta * v[4 * s4 + 3];
-              }
-            }
-            if (ly.act) {
+        for (int s4 = 0; s4 < 8; ++s4) r1[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
+      }
+      if (pre && ly.res2) {
+        const float* rp = ly.res2 + (((size_t)n * 16) * plane + (size_t)y * p.W + x0) * 4;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
-            }
-            if (ly.out_f32) {
+        for (int s4 = 0; s4 < 8; ++s4) r2[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
+      }
+      mbar_wait(&tfull[grp], (it >> 1) & 1);
+      tc_fence_after();
+      for (int b = 0; b < nblk; ++b) {
+        const int j = b >= nbc ? 1 : 0;
+        const int c0 = (b - j * nbc) << 5;
+        const int x = x0 + 8 * j;
+        const bool valid = mem && (y < p.H) && (x < p.W);
+        const size_t pix = (size_t)y * p.W + x;
+        const bool main_blk = c0 < ly.cout_main;
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(grp * 128 + j * 64 + c0), acc);
+        const bool has1 = main_blk && ly.res1 != nullptr && valid, has2 = main_blk && ly.res2 != nullptr && valid;
+        if (b > 0) {
+          if (has1) {
+            const float* rp = ly.res1 + (((size_t)n * ly.res1_cs_total + (c0 >> 2)) * plane + pix) * 4;
 #pragma unroll
-              for (int s4 = 0; s4 < 8; ++s4)
-                *reinterpret_cast<float4*>(ly.out_f32 + ((((size_t)n * 16 + (c0 / 4 + s4)) * p.H + y) * p.W + x) * 4) =
-                    make_float4(v[4 * s4], v[4 * s4 + 1], v[4 * s4 + 2], v[4 * s4 + 3]);
-            }
-            if (ly.out_bf16) {
+            for (int s4 = 0; s4 < 8; ++s4) r1[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
+          }
+          if (has2) {
+            const float* rp = ly.res2 + (((size_t)n * 16 + (c0 >> 2)) * plane + pix) * 4;
 #pragma unroll
-              for (int s8 = 0; s8 < 4; ++s8) {
-                uint4 o;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * s8 + 0], v[8 * s8 + 1]);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * s8 + 2], v[8 * s8 + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * s8 + 4], v[8 * s8 + 5]);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * s8 + 6], v[8 * s8 + 7]);
-                o.x = *reinterpret_cast<uint32_t*>(&t0);
-                o.y = *reinterpret_cast<uint32_t*>(&t1);
-                o.z = *reinterpret_cast<uint32_t*>(&t2);
-                o.w = *reinterpret_cast<uint32_t*>(&t3);
-                const size_t cs = (size_t)n * ly.out_cs_total + (ly.out_cs0 + c0 / 8 + s8);
-                if (!ly.up2) {
-                  *reinterpret_cast<uint4*>(ly.out_bf16 + ((cs * p.H + y) * p.W + x) * 8) = o;
-                } else {
-                  const int Ho = 2 * p.H, Wo = 2 * p.W;
-                  __nv_bfloat16* base = ly.out_bf16 + ((cs * Ho + 2 * y) * Wo + 2 * x) * 8;
-                  *reinterpret_cast<uint4*>(base) = o;
-                  *reinterpret_cast<uint4*>(base + 8) = o;
-                  *reinterpret_cast<uint4*>(base + (size_t)Wo * 8) = o;
-                  *reinterpret_cast<uint4*>(base + (size_t)Wo * 8 + 8) = o;
-                }
-              }
+            for (int s4 = 0; s4 < 8; ++s4) r2[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
+          }
+        }
+        tmem_wait_ld();
+        if (b == nblk - 1) {  // accumulator fully in registers: release it to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[grp]);
+        }
+        if (!valid) continue;
+        if (!main_blk) {
+          // raw partial sums of the paired layer -> fp32 stash
+          const int scs = (ly.cout - ly.cout_main) >> 2;
+          float* sp = ly.stash_out + (((size_t)n * scs + ((c0 - ly.cout_main) >> 2)) * plane + pix) * 4;
+#pragma unroll
+          for (int s4 = 0; s4 < 8; ++s4)
+            *reinterpret_cast<float4*>(sp + (size_t)s4 * plane * 4) =
+                make_float4(__uint_as_float(acc[4 * s4]), __uint_as_float(acc[4 * s4 + 1]),
+                            __uint_as_float(acc[4 * s4 + 2]), __uint_as_float(acc[4 * s4 + 3]));
+          continue;
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + __ldg(ly.bias + c0 + i);
+        if (has1) {
+#pragma unroll
+          for (int s4 = 0; s4 < 8; ++s4) {
+            v[4 * s4 + 0] = r1[s4].x + ly.beta * v[4 * s4 + 0];
+            v[4 * s4 + 1] = r1[s4].y + ly.beta * v[4 * s4 + 1];
+            v[4 * s4 + 2] = r1[s4].z + ly.beta * v[4 * s4 + 2];
+            v[4 * s4 + 3] = r1[s4].w + ly.beta * v[4 * s4 + 3];
+          }
+        }
+        if (has2) {
+#pragma unroll
+          for (int s4 = 0; s4 < 8; ++s4) {
+            v[4 * s4 + 0] = r2[s4].x + ly.beta * v[4 * s4 + 0];
+            v[4 * s4 + 1] = r2[s4].y + ly.beta * v[4 * s4 + 1];
+            v[4 * s4 + 2] = r2[s4].z + ly.beta * v[4 * s4 + 2];
+            v[4 * s4 + 3] = r2[s4].w + ly.beta * v[4 * s4 + 3];
+          }
+        }
+        if (ly.act) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
+        }
+        if (ly.out_f32) {
+          float* op = ly.out_f32 + (((size_t)n * 16 + (c0 >> 2)) * plane + pix) * 4;
+#pragma unroll
+          for (int s4 = 0; s4 < 8; ++s4)
+            *reinterpret_cast<float4*>(op + (size_t)s4 * plane * 4) =
+                make_float4(v[4 * s4], v[4 * s4 + 1], v[4 * s4 + 2], v[4 * s4 + 3]);
+        }
+        if (ly.out_bf16) {
+#pragma unroll
+          for (int s8 = 0; s8 < 4; ++s8) {
+            uint4 o;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * s8 + 0], v[8 * s8 + 1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * s8 + 2], v[8 * s8 + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * s8 + 4], v[8 * s8 + 5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * s8 + 6], v[8 * s8 + 7]);
+            o.x = *reinterpret_cast<uint32_t*>(&t0);
+            o.y = *reinterpret_cast<uint32_t*>(&t1);
+            o.z = *reinterpret_cast<uint32_t*>(&t2);
+            o.w = *reinterpret_cast<uint32_t*>(&t3);
+            const size_t cs = (size_t)n * ly.out_cs_total + (ly.out_cs0 + c0 / 8 + s8);
+            if (!ly.up2) {
+              *reinterpret_cast<uint4*>(ly.out_bf16 + (cs * plane + pix) * 8) = o;
+            } else {
+              const int Ho = 2 * p.H, Wo = 2 * p.W;
+              __nv_bfloat16* base = ly.out_bf16 + ((cs * Ho + 2 * y) * Wo + 2 * x) * 8;
+              *reinterpret_cast<uint4*>(base) = o;
+              *reinterpret_cast<uint4*>(base + 8) = o;
+              *reinterpret_cast<uint4*>(base + (size_t)Wo * 8) = o;
+              *reinterpret_cast<uint4*>(base + (size_t)Wo * 8 + 8) = o;
             }
           }
         }
       }
-      // release TMEM to the MMA warp, then publish the finished unit (device-scope release)
-      tc_fence_before();
-      __threadfence();
+      // publish the finished unit: the warp's stores are ordered before lane 0's gpu-scope fence by
+      // __syncwarp, the fence is cumulative, the flag increment follows it (release pattern)
+      if (p.debug & 8) __threadfence();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&tempty[buf]);
+        __threadfence();
         atomicAdd(p.done + (size_t)L * I + item, 1u);
       }
     }
@@ -301,10 +392,16 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
 
 using namespace dbm;
 
+namespace dbm {
+int g_trunk_debug = 0;  // set through dbm_debug_set(3, mask)
+}
+
 extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
                               int stem_cs_total, const void* cat_a_slab8, const void* cat_b_slab8, int cat_cs_total,
                               unsigned int* flags_dev, cudaStream_t stream) {
   DBM_REQUIRE(num_layers > 0 && n > 0 && h > 0 && w > 0, "trunk: empty problem");
+  DBM_REQUIRE(num_layers <= kMaxTrunkLayers, "trunk: %d passes exceed the kernel's table of %d", num_layers,
+              kMaxTrunkLayers);
   DBM_REQUIRE(((uintptr_t)layers_dev & 7) == 0, "trunk: layer table must be 8-byte aligned");
   TrunkMaps maps;
   const void* bases[3] = {stem_slab8, cat_a_slab8, cat_b_slab8};
@@ -321,6 +418,7 @@ extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int
   p.tiles_x = ceil_div(w, kTile); p.tiles_y = ceil_div(h, kTile);
   p.items_per_layer = n * p.tiles_x * p.tiles_y;
   p.done = flags_dev;
+  p.debug = g_trunk_debug;
   DBM_CUDA(cudaMemsetAsync(flags_dev, 0, (size_t)num_layers * p.items_per_layer * sizeof(unsigned int), stream));
   static bool attr_done = false;
   if (!attr_done) {

@@ -19,12 +19,13 @@ from . import layout, ops
 from . import npz as npz_io
 
 
-# mirror of struct TrunkLayer in csrc/umma_trunk.cu (96 bytes)
+# mirror of struct TrunkLayer in csrc/umma_trunk.cu (128 bytes)
 TRUNK_LAYER_DTYPE = np.dtype([("wpacked", "<u8"), ("bias", "<u8"), ("out_bf16", "<u8"), ("out_f32", "<u8"),
-                              ("res1", "<u8"), ("res2", "<u8"), ("cin", "<i4"), ("cout", "<i4"), ("in_map", "<i4"),
-                              ("act", "<i4"), ("up2", "<i4"), ("out_cs_total", "<i4"), ("out_cs0", "<i4"),
-                              ("pad0", "<i4"), ("beta", "<f4"), ("pad1", "<i4"), ("pad2", "<i4"), ("pad3", "<i4")])
-assert TRUNK_LAYER_DTYPE.itemsize == 96
+                              ("res1", "<u8"), ("res2", "<u8"), ("stash_out", "<u8"), ("cin", "<i4"), ("cout", "<i4"),
+                              ("in_map", "<i4"), ("in_cs0", "<i4"), ("act", "<i4"), ("up2", "<i4"),
+                              ("out_cs_total", "<i4"), ("out_cs0", "<i4"), ("cout_main", "<i4"),
+                              ("res1_cs_total", "<i4"), ("beta", "<f4"), ("pad", "<i4", (7,))])
+assert TRUNK_LAYER_DTYPE.itemsize == 128
 
 
 class Variable:
@@ -152,7 +153,9 @@ class GeneratorModel(_Link):
         self._packed_version = -1
         self._packed = {}
         self._ws = {}
-        self.persistent_trunk = True
+        self.persistent_trunk = True   # one-launch trunk kernel (False: one launch per layer, for A/B tests)
+        self.paired_trunk = True       # dense-block layer pairing inside the persistent kernel
+        self.per_layer_ck16 = False    # per-layer launches in the trunk kernel's 16-channel chunks (bit-exact A/B)
         self._ctx = None
 
     # ---- serialisation (chainer.serializers.load_npz / save_npz, App. C layout) ----
@@ -410,6 +413,25 @@ class GeneratorModel(_Link):
                     add(f"{pre}/conv_layer{k}", self.inter_channels, trunk=True)
                 add(f"{pre}/conv_layer5", 64, trunk=True)
         add("post_residual_conv_layer", 64, trunk=True)
+        if self.inter_channels == 32:
+            # dense-block pairing (see _trunk_workspace): conv_k and the partial sums of conv_{k+1}
+            # over their shared inputs are one 64-wide MMA pass; conv_{k+1} then only contracts a_k
+            for i in range(self.num_residual_blocks):
+                for r in (1, 2, 3):
+                    pre = self._rdb_prefix(i, r)
+                    for k in (1, 3):
+                        cin = 64 + (k - 1) * 32
+                        wa, wb = P[f"{pre}/conv_layer{k}/W"], P[f"{pre}/conv_layer{k + 1}/W"]
+                        both = ops.empty(9 * cin * 64, dtype=torch.bfloat16)
+                        ops.call("dbm_pack_conv3x3_weights_slice", wa.data_ptr(), cin, 0, both.data_ptr(), 32, 0, cin,
+                                 64, 16, ops.stream())
+                        ops.call("dbm_pack_conv3x3_weights_slice", wb.data_ptr(), cin + 32, 0, both.data_ptr(), 32, 32,
+                                 cin, 64, 16, ops.stream())
+                        pk[f"{pre}/pair{k}"] = (both, P[f"{pre}/conv_layer{k}/b"])
+                        tail = ops.empty(9 * 32 * 32, dtype=torch.bfloat16)
+                        ops.call("dbm_pack_conv3x3_weights_slice", wb.data_ptr(), cin + 32, cin, tail.data_ptr(), 32, 0,
+                                 32, 32, 32, ops.stream())
+                        pk[f"{pre}/tail{k + 1}"] = (tail, P[f"{pre}/conv_layer{k + 1}/b"])
         for key in ("post_upsample_conv_layer_1", "post_upsample_conv_layer_2"):
             add(key, 64)
         add("final_conv_layer1/offset_conv", 32)
@@ -426,28 +448,32 @@ class GeneratorModel(_Link):
         key = (n, H, W)
         ws = self._ws.get(key)
         pk = self._pack()
-        if ws is not None and ws["version"] == (self._packed_version, self.persistent_trunk):
+        if ws is not None and ws["version"] == (self._packed_version, self.persistent_trunk, self.paired_trunk,
+                                                self.per_layer_ck16):
             return ws
         bf = torch.bfloat16
         g = self.inter_channels
         cc = 64 + 4 * g
         ccs = cc // 8
         beta = self.residual_scaling
+        paired = self.persistent_trunk and self.paired_trunk and g == 32
         if ws is None:
             ws = dict(s0=ops.empty(n, 16, H, W, 8, dtype=bf), cat=[ops.empty(n, ccs, H, W, 8, dtype=bf) for _ in range(2)],
                       a1_f32=ops.empty(n, 16, H, W, 4), f32=[ops.empty(n, 16, H, W, 4) for _ in range(3)],
-                      u1=ops.empty(n, 8, 2 * H, 2 * W, 8, dtype=bf))
-        cat, f32, a1_f32 = ws["cat"], ws["f32"], ws["a1_f32"]
+                      u1=ops.empty(n, 8, 2 * H, 2 * W, 8, dtype=bf), stash=ops.empty(n, 8, H, W, 4))
+        cat, f32, a1_f32, stash = ws["cat"], ws["f32"], ws["a1_f32"], ws["stash"]
         layers = []
+        flops = []
 
-        def layer(key, cin, cout, in_map, act=0, beta_=0.0, out=None, out_cs0=0, out_f32=None, res1=None, res2=None,
-                  up2=0):
-            wq, bq = pk[key + "@trunk"] if self.persistent_trunk else pk[key]
-            layers.append((wq.data_ptr(), bq.data_ptr(), out.data_ptr() if out is not None else 0,
-                           out_f32.data_ptr() if out_f32 is not None else 0,
-                           res1.data_ptr() if res1 is not None else 0, res2.data_ptr() if res2 is not None else 0,
-                           cin, cout, in_map, act, up2, out.shape[1] if out is not None else 0, out_cs0, 0,
-                           beta_, 0, 0, 0))
+        def layer(wkey, cin, cout, in_map, act=0, beta_=0.0, out=None, out_cs0=0, out_f32=None, res1=None, res2=None,
+                  up2=0, in_cs0=0, cout_main=None, res1_cs=16, stash_out=None, raw=False):
+            trunk_pack = self.persistent_trunk or self.per_layer_ck16
+            wq, bq = pk[wkey] if raw else (pk[wkey + "@trunk"] if trunk_pack else pk[wkey])
+            ptr = lambda t: t.data_ptr() if t is not None else 0
+            layers.append((wq.data_ptr(), bq.data_ptr(), ptr(out), ptr(out_f32), ptr(res1), ptr(res2), ptr(stash_out),
+                           cin, cout, in_map, in_cs0, act, up2, out.shape[1] if out is not None else 0, out_cs0,
+                           cout if cout_main is None else cout_main, res1_cs, beta_, (0,) * 7))
+            flops.append(2.0 * 9 * cin * cout * n * H * W)
 
         layer("pre_residual_conv_layer", 128, 64, 0, act=1, out=cat[0], out_f32=a1_f32)
         cur, cur_f32, fi = 0, a1_f32, 0
@@ -455,9 +481,23 @@ class GeneratorModel(_Link):
             rrdb_in = cur_f32
             for r in (1, 2, 3):
                 pre = self._rdb_prefix(i, r)
-                for k in (1, 2, 3, 4):
-                    cin = 64 + (k - 1) * g
-                    layer(f"{pre}/conv_layer{k}", cin, g, 1 + cur, act=1, out=cat[cur], out_cs0=cin // 8)
+                if paired:
+                    # a_k = lrelu(conv_k([a0..a_{k-1}])) for k = 1..4 (srgan_train.py:339-352) in four passes:
+                    #   k odd : N = 64 over [a0..a_{k-1}] -> a_k (32 cols, fused epilogue) and the partial sums of
+                    #           conv_{k+1} over the same inputs (32 cols, raw fp32 stash)
+                    #   k even: N = 32 over a_{k-1} only, stash added in the epilogue -> a_k
+                    # Same FLOPs; 252 N=32 MMAs per 128-pixel tile become 108 N=64 + 36 N=32 MMAs (each MMA
+                    # re-reads its 4 KB A operand from shared memory whatever N is).
+                    for k in (1, 3):
+                        cin = 64 + (k - 1) * g
+                        layer(f"{pre}/pair{k}", cin, 64, 1 + cur, act=1, out=cat[cur], out_cs0=cin // 8, cout_main=32,
+                              stash_out=stash, raw=True)
+                        layer(f"{pre}/tail{k + 1}", 32, 32, 1 + cur, in_cs0=cin // 8, act=1, beta_=1.0, out=cat[cur],
+                              out_cs0=cin // 8 + 4, res1=stash, res1_cs=8, raw=True)
+                else:
+                    for k in (1, 2, 3, 4):
+                        cin = 64 + (k - 1) * g
+                        layer(f"{pre}/conv_layer{k}", cin, g, 1 + cur, act=1, out=cat[cur], out_cs0=cin // 8)
                 # fp32 residual buffer that is neither the RDB input nor the RRDB input
                 while f32[fi] is cur_f32 or f32[fi] is rrdb_in:
                     fi = (fi + 1) % 3
@@ -468,10 +508,11 @@ class GeneratorModel(_Link):
         layer("post_residual_conv_layer", 64, 64, 1 + cur, beta_=1.0, out=ws["u1"], res1=a1_f32, up2=1)
         table = np.array(layers, dtype=TRUNK_LAYER_DTYPE)
         ws["layers"] = layers
+        ws["flops"] = float(sum(flops))  # executed MMA FLOPs (= algorithmic: pairing moves work, it adds none)
         ws["table"] = torch.from_numpy(table.view(np.uint8).copy()).cuda()
         tiles = ((H + 15) // 16) * ((W + 15) // 16)
         ws["flags"] = ops.empty(len(layers) * n * tiles, dtype=torch.int32)
-        ws["version"] = (self._packed_version, self.persistent_trunk)
+        ws["version"] = (self._packed_version, self.persistent_trunk, self.paired_trunk, self.per_layer_ck16)
         self._ws[key] = ws
         return ws
 
@@ -483,11 +524,13 @@ class GeneratorModel(_Link):
             return
         # one launch per layer (kept for A/B measurements of the persistent kernel)
         srcs = (ws["s0"], ws["cat"][0], ws["cat"][1])
-        for (wq, bq, out, out_f32, res1, res2, cin, cout, in_map, act, up2, out_cs_total, out_cs0, _p0, beta_, *_r) in \
-                ws["layers"]:
+        ops.call("dbm_debug_set", 2, int(self.per_layer_ck16))
+        for (wq, bq, out, out_f32, res1, res2, _stash, cin, cout, in_map, _cs0, act, up2, out_cs_total, out_cs0, _cm,
+             _r1cs, beta_, _pad) in ws["layers"]:
             inp = srcs[in_map]
             ops.call("dbm_conv3x3_umma", inp.data_ptr(), inp.shape[1], cin, wq, bq, cout, n, H, W, float(beta_), act, up2,
                      out or None, out_cs_total, out_cs0, out_f32 or None, 16, 0, res1 or None, res2 or None, ops.stream())
+        ops.call("dbm_debug_set", 2, 0)
 
     def _forward_bf16(self, x, w1, w2, w3):
         P = self.p

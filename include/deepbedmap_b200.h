@@ -97,15 +97,21 @@ int dbm_slab4_to_nchw(const float* src_slab4, float* dst, long dst_batch_stride,
  * cout_padded in {32, 64}; cin multiple of 32. Weights come from dbm_pack_conv3x3_weights. */
 int dbm_pack_conv3x3_weights(const float* w_oihw, void* packed_bf16, int cout, int cin, int cout_padded, int ck,
                              cudaStream_t stream);
+/* Rows [cout0, cout0+cout) of the packed image <- w[o][w_c0 + c][tap] of an (cout, w_cin_total, 3, 3) filter
+ * (c < cin); other rows untouched. Stacks several filters that share an input along Cout. */
+int dbm_pack_conv3x3_weights_slice(const float* w_oihw, int w_cin_total, int w_c0, void* packed_bf16, int cout,
+                                   int cout0, int cin, int cout_padded, int ck, cudaStream_t stream);
 int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void* wpacked, const float* bias,
                      int cout_padded, int n, int h, int w, float beta, int act, int up2, void* out_slab8,
                      int out_cs_total, int out_cs0, float* out_f32_slab4, int out_f32_cs_total, int out_f32_cs0,
                      const float* res1_slab4, const float* res2_slab4, cudaStream_t stream);
 
 /* Persistent whole-trunk kernel: pre-residual conv + 3*nb residual dense blocks + post-residual conv
- * (srgan_train.py:541-551) in ONE launch; `layers_dev` is a device array of `num_layers` 96-byte records
- * (struct TrunkLayer in csrc/umma_trunk.cu: weight/bias/output/residual pointers, cin, cout, input
- * buffer id {0 = stem_slab8, 1 = cat_a, 2 = cat_b}, epilogue flags), flags_dev holds
+ * (srgan_train.py:541-551) in ONE launch; `layers_dev` is a device array of `num_layers` 128-byte records
+ * (struct TrunkLayer in csrc/umma_trunk.cu: weight/bias/output/residual/stash pointers, cin, cout, input
+ * buffer id {0 = stem_slab8, 1 = cat_a, 2 = cat_b} and first input slab, epilogue flags). A record is one
+ * MMA pass; with dense-block pairing (model.py) a pass computes one layer plus the partial sums of the
+ * next layer over their shared inputs. flags_dev holds
  * num_layers * n * ceil(h/16) * ceil(w/16) uint32 (zeroed by the call). */
 int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
                    int stem_cs_total, const void* cat_a_slab8, const void* cat_b_slab8, int cat_cs_total,
