@@ -10,7 +10,9 @@ constexpr int kTile = 16;         // a work item is a kTile x kTile pixel output
 constexpr int kHalo = kTile + 2;  // 18: halo tile edge
 
 // slab8 bf16 tensor [N][CS][H][W][8] viewed as 4-D (W*8, H, CS, N); box = 18 px x 18 rows x ck/8 slabs
-int make_slab8_tmap(CUtensorMap* tm, const void* base, int N, int CS, int H, int W, int ck);
+// (default box: the 18 x 18 halo tile of a 16 x 16 unit)
+int make_slab8_tmap(CUtensorMap* tm, const void* base, int N, int CS, int H, int W, int ck, int box_w = kHalo,
+                    int box_h = kHalo);
 
 // All MMAs of one pipeline stage: 9 taps x (2 sub-tiles x CK/16 k-steps). The tap loop is kept
 // rolled: fully unrolling it makes ptxas hoist all 72 descriptor words, overflow the uniform

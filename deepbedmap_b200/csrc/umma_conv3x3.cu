@@ -266,12 +266,12 @@ static PFN_encodeTiled get_encode() {
 }
 
 // slab8 bf16 tensor [N][CS][H][W][8] viewed as 4-D (W*8, H, CS, N); box = 18 px x 18 rows x CK/8 slabs.
-int make_slab8_tmap(CUtensorMap* tm, const void* base, int N, int CS, int H, int W, int ck) {
+int make_slab8_tmap(CUtensorMap* tm, const void* base, int N, int CS, int H, int W, int ck, int box_w, int box_h) {
   PFN_encodeTiled enc = get_encode();
   DBM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)CS, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)CS * H * W * 16};
-  cuuint32_t box[4] = {(cuuint32_t)kHalo * 8, (cuuint32_t)kHalo, (cuuint32_t)(ck / 8), 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_h, (cuuint32_t)(ck / 8), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -395,11 +395,12 @@ extern "C" int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, 
   p.out_bf16 = (__nv_bfloat16*)out_slab8; p.out_cs_total = out_cs_total; p.out_cs0 = out_cs0;
   p.out_f32 = out_f32_slab4; p.out_f32_cs_total = out_f32_cs_total; p.out_f32_cs0 = out_f32_cs0;
   p.res1 = res1_slab4; p.res2 = res2_slab4;
-  if (cout_padded == 32) return launch_umma<32, 32, 5>(tm, p, stream);
   if (g_debug_ck16) {
     rc = make_slab8_tmap(&tm, in_slab8, n, in_cs_total, h, w, 16);
     if (rc) return rc;
+    if (cout_padded == 32) return launch_umma<32, 16, 5>(tm, p, stream);
     return launch_umma<64, 16, 5>(tm, p, stream);
   }
+  if (cout_padded == 32) return launch_umma<32, 32, 5>(tm, p, stream);
   return launch_umma<64, 32, 3>(tm, p, stream);
 }

@@ -3,7 +3,7 @@
 // as ONE launch instead of 182.
 //
 // Every layer is the same tcgen05 implicit-GEMM 3x3 conv as umma_conv3x3_kernel (TMA halo tile,
-// nine shifted descriptors, fused epilogue); what changes is the scheduling. All (layer, 16x16
+// nine shifted descriptors, fused epilogue); what changes is the scheduling. All (layer, 32-row x 16-column
 // pixel unit) work items are numbered layer-major and dealt round-robin to one resident CTA per
 // SM. An item of layer L may start once the <= 9 neighbouring units of layer L-1 (its 1-pixel
 // halo) are complete, which each finished item publishes through a global flag
@@ -15,19 +15,43 @@
 namespace dbm {
 
 constexpr int kTrunkThreads = 320;  // warp0 TMA + dependency wait, warp1 MMA, warps2-9 epilogue
-constexpr int kEpiWarps = 8;        // two warps per TMEM lane quadrant, one per 8x16-pixel sub-tile
-// K-chunk per pipeline stage: 32 channels for 32-wide layers, 16 for 64-wide layers, so that both
-// kinds of layer use the same 18432-byte weight stage and the ring has 5 stages (4 x 1650 MMA
-// cycles of cover for a ~3000-cycle TMA round trip; with 3 x 57.6 KB stages the issuer starved).
+constexpr int kEpiWarps = 8;        // two groups of four warps, one group per TMEM accumulator buffer
+// A work item is a 32-row x 16-column pixel unit = four M=128 sub-tiles (8 columns x 16 rows each)
+// that share every weight stage: halves the weight traffic (L2 -> SMEM) and the per-item / per-stage
+// hand-offs of the 16x16 unit the per-layer kernel uses, and gives the epilogue of the short K=32
+// "tail" passes twice the time to drain.
+constexpr int kTW = 16, kTH = 32;                    // (a TMA box is at most 256 elements = 32 pixels wide)
+constexpr int kHW = kTW + 2, kHH = kTH + 2;          // 18-px x 34-row halo tile
+// Every pass streams K in 16-channel chunks: one stage = halo tile (19584 B) + 9 taps x 16 x Cout
+// filter slice (<= 18432 B); five stages cover the ~3000-cycle TMA round trip.
 constexpr int kTStages = 5;
-constexpr int kTABytes = kHalo * kHalo * 32 * 2;     // 20736 (half used when the chunk is 16 channels)
-constexpr int kTBBytesMax = 9 * 32 * 32 * 2;         // 18432 = 9*32*32*2 = 9*16*64*2
+constexpr int kTABytes = kHW * kHH * 16 * 2;         // 19584
+constexpr int kTBBytesMax = 9 * 16 * 64 * 2;         // 18432
 constexpr int kMaxTrunkLayers = 512;                 // 23 RRDB (config 5's deepest) = 347 passes
 constexpr int kTrunkSmem = kTStages * (kTABytes + kTBBytesMax) + 256 + kMaxTrunkLayers * 24 + 1024;
 
-struct TrunkMaps {  // [input buffer][0: 32-channel box, 1: 16-channel box]
-  CUtensorMap m[3][2];
+struct TrunkMaps {  // one 18 px x 34 rows x 16-channel box map per input buffer
+  CUtensorMap m[3];
 };
+
+// All MMAs of one stage: 9 taps x 4 sub-tiles, K = 16 (one instruction each). Tap loop rolled for
+// the same uniform-register reason as issue_stage_mmas.
+template <int COUT>
+__device__ __forceinline__ void issue_stage_wide(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                 uint32_t b_hi, uint32_t acc0) {
+  constexpr uint32_t idesc = umma_idesc_bf16(128, COUT);
+  constexpr uint32_t kBTap = (uint32_t)(2 * (COUT / 8) * 8);  // per-tap stride of the packed filter, 16-B units
+#pragma unroll 1
+  for (uint32_t tap = 0; tap < 9; ++tap) {
+    const uint32_t a_tap = a_lo + tap + (tap / 3) * (kHW - 3);  // ky * 18 + kx
+    const uint32_t b_tap = b_lo + tap * kBTap;
+    const uint32_t acc = tap != 0 ? 1u : acc0;
+    umma_bf16_off<0, 0>(d0, a_tap, a_hi, b_tap, b_hi, idesc, acc);
+    umma_bf16_off<8, 0>(d0 + 64, a_tap, a_hi, b_tap, b_hi, idesc, acc);
+    umma_bf16_off<16 * kHW, 0>(d0 + 128, a_tap, a_hi, b_tap, b_hi, idesc, acc);
+    umma_bf16_off<16 * kHW + 8, 0>(d0 + 192, a_tap, a_hi, b_tap, b_hi, idesc, acc);
+  }
+}
 
 // One MMA pass: out[:, 0:cout] = conv3x3(in[:, 8*in_cs0 : 8*in_cs0 + cin]) with the packed filter.
 // Columns [0, cout_main) take the fused epilogue (bias, residuals, LeakyReLU, bf16 / fp32 stores);
@@ -97,10 +121,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
     lw[L] = ly->wpacked;
   }
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 3; ++i) {
-      tma_prefetch_desc(&maps.m[i][0]);
-      tma_prefetch_desc(&maps.m[i][1]);
-    }
+    for (int i = 0; i < 3; ++i) tma_prefetch_desc(&maps.m[i]);
     for (int s = 0; s < kTStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -111,7 +132,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -152,10 +173,9 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         }
         __syncwarp();
       }
-      const int ck = cout == 32 ? 32 : 16;
-      const CUtensorMap* tm = &maps.m[in_map][cout == 32 ? 0 : 1];
-      const uint32_t a_bytes = (uint32_t)(kHalo * kHalo * ck * 2);
-      const int num_kc = cin / ck;
+      const CUtensorMap* tm = &maps.m[in_map];
+      const uint32_t b_bytes = (uint32_t)(9 * 16 * 2) * (uint32_t)cout;
+      const int num_kc = cin >> 4;
       for (int kc = 0; kc < num_kc; ++kc) {
         mbar_wait(&empty[s], ph ^ 1);
         if (elect_one_sync()) {
@@ -164,10 +184,9 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
           } else {
             // order the acquired flags (generic proxy) before the TMA reads (async proxy)
             asm volatile("fence.proxy.async.global;" ::: "memory");
-            mbar_arrive_expect_tx(&full[s], a_bytes + kTBBytesMax);
-            tma_load_4d(smA + s * kTABytes, tm, &full[s], (tx * kTile - 1) * 8, ty * kTile - 1,
-                        in_cs0 + kc * (ck / 8), n);
-            bulk_load(smB + s * kTBBytesMax, wp + (size_t)kc * (kTBBytesMax / 2), kTBBytesMax, &full[s]);
+            mbar_arrive_expect_tx(&full[s], (uint32_t)kTABytes + b_bytes);
+            tma_load_4d(smA + s * kTABytes, tm, &full[s], (tx * kTW - 1) * 8, ty * kTH - 1, in_cs0 + kc * 2, n);
+            bulk_load(smB + s * kTBBytesMax, wp + (size_t)kc * (b_bytes / 2), b_bytes, &full[s]);
           }
         }
         __syncwarp();
@@ -176,7 +195,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
     }
   } else if (warp == 1) {
     // ================= MMA issuer: converged warp, one elected lane issues =================
-    const uint32_t a_hi = desc_hi(kHalo * 16);
+    const uint32_t a_hi = desc_hi(kHW * 16);
     const uint32_t b_hi = desc_hi(128);
     const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
     int s = 0;
@@ -186,27 +205,27 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       const int L = (int)(g / I);
       const int4 li = linfo[L];
       const int cin = li.x, cout = li.y;
-      const int num_kc = cin / (cout == 32 ? 32 : 16);
+      const int num_kc = cin >> 4;
       const int buf = it & 1;
       mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + (uint32_t)(buf * 128);
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
       for (int kc = 0; kc < num_kc; ++kc) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t a_lo = desc_lo(smA_u + s * kTABytes, kHalo * kHalo * 16);
+        const uint32_t a_lo = desc_lo(smA_u + s * kTABytes, kHW * kHH * 16);
         const uint32_t acc0 = kc != 0 ? 1u : 0u;
         if (cout == 32) {
           const uint32_t b_lo = desc_lo(smB_u + s * kTBBytesMax, 4 * 128);
           if (elect_one_sync()) {
-            issue_stage_mmas<32, 32, 64>(d0, a_lo, a_hi, b_lo, b_hi, umma_idesc_bf16(128, 32), acc0);
+            issue_stage_wide<32>(d0, a_lo, a_hi, b_lo, b_hi, acc0);
             umma_commit(&empty[s]);
             if (kc == num_kc - 1) umma_commit(&tfull[buf]);
           }
         } else {
           const uint32_t b_lo = desc_lo(smB_u + s * kTBBytesMax, 8 * 128);
           if (elect_one_sync()) {
-            issue_stage_mmas<64, 16, 64>(d0, a_lo, a_hi, b_lo, b_hi, umma_idesc_bf16(128, 64), acc0);
+            issue_stage_wide<64>(d0, a_lo, a_hi, b_lo, b_hi, acc0);
             umma_commit(&empty[s]);
             if (kc == num_kc - 1) umma_commit(&tfull[buf]);
           }
@@ -235,12 +254,12 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       const int r = item - n * per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const TrunkLayer ly = p.layers[L];
-      const int y = ty * kTile + gy;
-      const int x0 = tx * kTile + xr;
+      const int y0 = ty * kTH + gy;
+      const int x0 = tx * kTW + xr;
       const int nbc = ly.cout >> 5;            // 32-column blocks per sub-tile
-      const int nblk = 2 * nbc;                // sub-tile-major
+      const int nblk = 4 * nbc;                // sub-tile-major
       float4 r1[8], r2[8];
-      const bool pre = mem && (y < p.H) && (x0 < p.W) && ly.cout_main > 0;
+      const bool pre = mem && (y0 < p.H) && (x0 < p.W) && ly.cout_main > 0;
       // Addends of the first block are fetched before the accumulator is even complete. They were
       // written by the same unit of earlier passes; (L-1, item) complete implies all of those are
       // (dependencies are transitive), and this warp must acquire that flag itself: the producer
@@ -260,26 +279,27 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         __syncwarp();
       }
       if (pre && ly.res1) {
-        const float* rp = ly.res1 + (((size_t)n * ly.res1_cs_total) * plane + (size_t)y * p.W + x0) * 4;
+        const float* rp = ly.res1 + (((size_t)n * ly.res1_cs_total) * plane + (size_t)y0 * p.W + x0) * 4;
 #pragma unroll
         for (int s4 = 0; s4 < 8; ++s4) r1[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
       }
       if (pre && ly.res2) {
-        const float* rp = ly.res2 + (((size_t)n * 16) * plane + (size_t)y * p.W + x0) * 4;
+        const float* rp = ly.res2 + (((size_t)n * 16) * plane + (size_t)y0 * p.W + x0) * 4;
 #pragma unroll
         for (int s4 = 0; s4 < 8; ++s4) r2[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
       }
       mbar_wait(&tfull[grp], (it >> 1) & 1);
       tc_fence_after();
       for (int b = 0; b < nblk; ++b) {
-        const int j = b >= nbc ? 1 : 0;
+        const int j = nbc == 2 ? (b >> 1) : b;
         const int c0 = (b - j * nbc) << 5;
-        const int x = x0 + 8 * j;
+        const int x = x0 + 8 * (j & 1);
+        const int y = y0 + 16 * (j >> 1);
         const bool valid = mem && (y < p.H) && (x < p.W);
         const size_t pix = (size_t)y * p.W + x;
         const bool main_blk = c0 < ly.cout_main;
         uint32_t acc[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(grp * 128 + j * 64 + c0), acc);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(grp * 256 + j * 64 + c0), acc);
         const bool has1 = main_blk && ly.res1 != nullptr && valid, has2 = main_blk && ly.res2 != nullptr && valid;
         if (b > 0) {
           if (has1) {
@@ -384,7 +404,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -406,16 +426,15 @@ extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int
   TrunkMaps maps;
   const void* bases[3] = {stem_slab8, cat_a_slab8, cat_b_slab8};
   const int cs_tot[3] = {stem_cs_total, cat_cs_total, cat_cs_total};
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 2; ++j) {
-      int rc = make_slab8_tmap(&maps.m[i][j], bases[i], n, cs_tot[i], h, w, j == 0 ? 32 : 16);
-      if (rc) return rc;
-    }
+  for (int i = 0; i < 3; ++i) {
+    int rc = make_slab8_tmap(&maps.m[i], bases[i], n, cs_tot[i], h, w, 16, kHW, kHH);
+    if (rc) return rc;
+  }
   TrunkParams p;
   p.layers = (const TrunkLayer*)layers_dev;
   p.num_layers = num_layers;
   p.N = n; p.H = h; p.W = w;
-  p.tiles_x = ceil_div(w, kTile); p.tiles_y = ceil_div(h, kTile);
+  p.tiles_x = ceil_div(w, kTW); p.tiles_y = ceil_div(h, kTH);
   p.items_per_layer = n * p.tiles_x * p.tiles_y;
   p.done = flags_dev;
   p.debug = g_trunk_debug;

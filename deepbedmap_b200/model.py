@@ -384,11 +384,9 @@ class GeneratorModel(_Link):
             else:
                 bp = b
             pk[key] = (ops.pack_conv3x3(w, cout_padded), bp)
-            if trunk and cout_padded == 64:
-                # the persistent trunk kernel streams 64-wide layers in 16-channel chunks
+            if trunk:
+                # the persistent trunk kernel streams every layer in 16-channel chunks
                 pk[key + "@trunk"] = (ops.pack_conv3x3(w, cout_padded, ck=16), bp)
-            elif trunk:
-                pk[key + "@trunk"] = pk[key]
 
         # stem filters, tap-major, and the concatenated stem bias
         def tapmajor(keys):
@@ -430,7 +428,7 @@ class GeneratorModel(_Link):
                         pk[f"{pre}/pair{k}"] = (both, P[f"{pre}/conv_layer{k}/b"])
                         tail = ops.empty(9 * 32 * 32, dtype=torch.bfloat16)
                         ops.call("dbm_pack_conv3x3_weights_slice", wb.data_ptr(), cin + 32, cin, tail.data_ptr(), 32, 0,
-                                 32, 32, 32, ops.stream())
+                                 32, 32, 16, ops.stream())
                         pk[f"{pre}/tail{k + 1}"] = (tail, P[f"{pre}/conv_layer{k + 1}/b"])
         for key in ("post_upsample_conv_layer_1", "post_upsample_conv_layer_2"):
             add(key, 64)
@@ -510,7 +508,7 @@ class GeneratorModel(_Link):
         ws["layers"] = layers
         ws["flops"] = float(sum(flops))  # executed MMA FLOPs (= algorithmic: pairing moves work, it adds none)
         ws["table"] = torch.from_numpy(table.view(np.uint8).copy()).cuda()
-        tiles = ((H + 15) // 16) * ((W + 15) // 16)
+        tiles = ((H + 31) // 32) * ((W + 15) // 16)   # 32-row x 16-column units (kTH x kTW in umma_trunk.cu)
         ws["flags"] = ops.empty(len(layers) * n * tiles, dtype=torch.int32)
         ws["version"] = (self._packed_version, self.persistent_trunk, self.paired_trunk, self.per_layer_ck16)
         self._ws[key] = ws

@@ -112,7 +112,7 @@ int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void*
  * buffer id {0 = stem_slab8, 1 = cat_a, 2 = cat_b} and first input slab, epilogue flags). A record is one
  * MMA pass; with dense-block pairing (model.py) a pass computes one layer plus the partial sums of the
  * next layer over their shared inputs. flags_dev holds
- * num_layers * n * ceil(h/16) * ceil(w/16) uint32 (zeroed by the call). */
+ * num_layers * n * ceil(h/32) * ceil(w/16) uint32 (zeroed by the call). */
 int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
                    int stem_cs_total, const void* cat_a_slab8, const void* cat_b_slab8, int cat_cs_total,
                    unsigned int* flags_dev, cudaStream_t stream);
