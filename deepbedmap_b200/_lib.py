@@ -18,6 +18,7 @@ _P, _L, _I, _F = ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_float
 SIGNATURES = {
     "dbm_version": [],
     "dbm_debug_set": [_I, _I],
+    "dbm_debug_set_ptr": [_I, _P],
     "dbm_conv2d_fwd_f32": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dbm_conv2d_bwd_data_f32": [_P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dbm_conv2d_bwd_weight_f32": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -28,7 +28,7 @@ constexpr int kTStages = 5;
 constexpr int kTABytes = kHW * kHH * 16 * 2;         // 19584
 constexpr int kTBBytesMax = 9 * 16 * 64 * 2;         // 18432
 constexpr int kMaxTrunkLayers = 512;                 // 23 RRDB (config 5's deepest) = 347 passes
-constexpr int kTrunkSmem = kTStages * (kTABytes + kTBBytesMax) + 256 + kMaxTrunkLayers * 24 + 1024;
+constexpr int kTrunkSmem = kTStages * (kTABytes + kTBBytesMax) + 256 + kMaxTrunkLayers * 24 + kEpiWarps * 256 + 1024;
 
 struct TrunkMaps {  // one 18 px x 34 rows x 16-channel box map per input buffer
   CUtensorMap m[3];
@@ -76,12 +76,14 @@ struct TrunkLayer {  // 128 bytes, mirrored by deepbedmap_b200/model.py (TRUNK_L
 static_assert(sizeof(TrunkLayer) == 128, "TrunkLayer layout is part of the C ABI");
 
 extern int g_trunk_debug;
+extern unsigned long long* g_trunk_prof;
 
 struct TrunkParams {
   const TrunkLayer* layers;
   int num_layers;
   int N, H, W, tiles_x, tiles_y, items_per_layer;
   unsigned int* done;  // [num_layers][items_per_layer], zeroed before the launch; complete == kEpiWarps
+  unsigned long long* prof;  // tuning only (NULL = off): [num_layers][8] cycle counters, see scripts/trunk_ablate.py
   int debug;           // ablation mask for tuning runs (results invalid): 1 no dependency wait, 2 no epilogue
                        // memory traffic, 4 no TMA loads
 };
@@ -111,6 +113,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
   // (the epilogue's gpu-scope fences keep invalidating L1, a global read per item costs an L2 trip)
   int4* linfo = (int4*)(smem + kTStages * (kTABytes + kTBBytesMax) + 256);         // {cin, cout, in_map, in_cs0}
   const __nv_bfloat16** lw = (const __nv_bfloat16**)(linfo + kMaxTrunkLayers);
+  float* sbias_all = (float*)(lw + kMaxTrunkLayers);  // [kEpiWarps][64]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -207,12 +210,17 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       const int cin = li.x, cout = li.y;
       const int num_kc = cin >> 4;
       const int buf = it & 1;
+      const long long t0 = p.prof ? clock64() : 0;
       mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
+      const long long t1 = p.prof ? clock64() : 0;
+      long long tw = 0;
       const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
       for (int kc = 0; kc < num_kc; ++kc) {
+        const long long tw0 = p.prof ? clock64() : 0;
         mbar_wait(&full[s], ph);
         tc_fence_after();
+        if (p.prof) tw += clock64() - tw0;
         const uint32_t a_lo = desc_lo(smA_u + s * kTABytes, kHW * kHH * 16);
         const uint32_t acc0 = kc != 0 ? 1u : 0u;
         if (cout == 32) {
@@ -233,6 +241,12 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         __syncwarp();
         if (++s == kTStages) { s = 0; ph ^= 1; }
       }
+      if (p.prof && lane == 0) {
+        atomicAdd(p.prof + L * 8 + 0, (unsigned long long)(t1 - t0));       // waiting for a free accumulator
+        atomicAdd(p.prof + L * 8 + 1, (unsigned long long)tw);              // waiting for operands
+        atomicAdd(p.prof + L * 8 + 2, (unsigned long long)(clock64() - t0)); // whole item at the issuer
+        atomicAdd(p.prof + L * 8 + 3, 1ull);
+      }
     }
   } else {
     // ================= epilogue: TMEM -> registers -> HBM, then publish the unit =================
@@ -246,6 +260,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
     const int gy = m >> 3, xr = m & 7;
     const bool mem = !(p.debug & 2);
     const size_t plane = (size_t)p.H * p.W;
+    float* sbias = sbias_all + (warp - 2) * 64;
     int it = grp;
     for (long g = blockIdx.x + (long)grp * gridDim.x; g < total_items; g += 2L * gridDim.x, it += 2) {
       const int L = (int)(g / I);
@@ -258,12 +273,15 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       const int x0 = tx * kTW + xr;
       const int nbc = ly.cout >> 5;            // 32-column blocks per sub-tile
       const int nblk = 4 * nbc;                // sub-tile-major
-      float4 r1[8], r2[8];
-      const bool pre = mem && (y0 < p.H) && (x0 < p.W) && ly.cout_main > 0;
-      // Addends of the first block are fetched before the accumulator is even complete. They were
-      // written by the same unit of earlier passes; (L-1, item) complete implies all of those are
-      // (dependencies are transitive), and this warp must acquire that flag itself: the producer
-      // warp's acquire is only inherited through tfull, which has not been waited on yet.
+      float4 r1[8], r1n[8];
+      // this pass's bias, staged per warp in shared memory (a global read per block would cost an
+      // L2 round trip each: the gpu-scope fences keep invalidating L1)
+      if (lane < ly.cout_main) sbias[lane] = __ldg(ly.bias + lane);
+      if (lane + 32 < ly.cout_main) sbias[lane + 32] = __ldg(ly.bias + lane + 32);
+      // Addends (residual stream / stash) were written by the same unit of earlier passes;
+      // (L-1, item) complete implies all of those are (dependencies are transitive), and this warp
+      // must acquire that flag itself: the producer warp's acquire is only inherited through tfull,
+      // which has not been waited on yet.
       if (L > 0 && (ly.res1 || ly.res2) && !(p.debug & 1)) {
         if (lane == 0) {
           const unsigned int* f = p.done + (size_t)(L - 1) * I + item;
@@ -276,20 +294,25 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
             __nanosleep(32);
           }
         }
-        __syncwarp();
       }
-      if (pre && ly.res1) {
-        const float* rp = ly.res1 + (((size_t)n * ly.res1_cs_total) * plane + (size_t)y0 * p.W + x0) * 4;
+      __syncwarp();
+      // res1 of block b is requested one block ahead (block 0: before the accumulator is complete)
+      auto load_r1 = [&](int b, float4 (&dst)[8]) {
+        const int j = nbc == 2 ? (b >> 1) : b;
+        const int c0 = (b - j * nbc) << 5;
+        const int x = x0 + 8 * (j & 1), y = y0 + 16 * (j >> 1);
+        if (ly.res1 != nullptr && c0 < ly.cout_main && mem && y < p.H && x < p.W) {
+          const float* rp = ly.res1 + (((size_t)n * ly.res1_cs_total + (c0 >> 2)) * plane + (size_t)y * p.W + x) * 4;
 #pragma unroll
-        for (int s4 = 0; s4 < 8; ++s4) r1[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
-      }
-      if (pre && ly.res2) {
-        const float* rp = ly.res2 + (((size_t)n * 16) * plane + (size_t)y0 * p.W + x0) * 4;
-#pragma unroll
-        for (int s4 = 0; s4 < 8; ++s4) r2[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
-      }
+          for (int s4 = 0; s4 < 8; ++s4) dst[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
+        }
+      };
+      load_r1(0, r1);
+      const long long e0 = p.prof ? clock64() : 0;
       mbar_wait(&tfull[grp], (it >> 1) & 1);
       tc_fence_after();
+      const long long e1 = p.prof ? clock64() : 0;
+      long long e2 = 0;
       for (int b = 0; b < nblk; ++b) {
         const int j = nbc == 2 ? (b >> 1) : b;
         const int c0 = (b - j * nbc) << 5;
@@ -301,26 +324,15 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(grp * 256 + j * 64 + c0), acc);
         const bool has1 = main_blk && ly.res1 != nullptr && valid, has2 = main_blk && ly.res2 != nullptr && valid;
-        if (b > 0) {
-          if (has1) {
-            const float* rp = ly.res1 + (((size_t)n * ly.res1_cs_total + (c0 >> 2)) * plane + pix) * 4;
-#pragma unroll
-            for (int s4 = 0; s4 < 8; ++s4) r1[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
-          }
-          if (has2) {
-            const float* rp = ly.res2 + (((size_t)n * 16 + (c0 >> 2)) * plane + pix) * 4;
-#pragma unroll
-            for (int s4 = 0; s4 < 8; ++s4) r2[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
-          }
-        }
+        if (b + 1 < nblk) load_r1(b + 1, r1n);
         tmem_wait_ld();
         if (b == nblk - 1) {  // accumulator fully in registers: release it to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[grp]);
+          if (p.prof) e2 = clock64();
         }
-        if (!valid) continue;
-        if (!main_blk) {
+        if (valid && !main_blk) {
           // raw partial sums of the paired layer -> fp32 stash
           const int scs = (ly.cout - ly.cout_main) >> 2;
           float* sp = ly.stash_out + (((size_t)n * scs + ((c0 - ly.cout_main) >> 2)) * plane + pix) * 4;
@@ -329,11 +341,16 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
             *reinterpret_cast<float4*>(sp + (size_t)s4 * plane * 4) =
                 make_float4(__uint_as_float(acc[4 * s4]), __uint_as_float(acc[4 * s4 + 1]),
                             __uint_as_float(acc[4 * s4 + 2]), __uint_as_float(acc[4 * s4 + 3]));
-          continue;
-        }
+        } else if (valid) {
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + __ldg(ly.bias + c0 + i);
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 bb = *reinterpret_cast<const float4*>(sbias + c0 + 4 * i4);
+          v[4 * i4 + 0] = __uint_as_float(acc[4 * i4 + 0]) + bb.x;
+          v[4 * i4 + 1] = __uint_as_float(acc[4 * i4 + 1]) + bb.y;
+          v[4 * i4 + 2] = __uint_as_float(acc[4 * i4 + 2]) + bb.z;
+          v[4 * i4 + 3] = __uint_as_float(acc[4 * i4 + 3]) + bb.w;
+        }
         if (has1) {
 #pragma unroll
           for (int s4 = 0; s4 < 8; ++s4) {
@@ -343,13 +360,15 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
             v[4 * s4 + 3] = r1[s4].w + ly.beta * v[4 * s4 + 3];
           }
         }
-        if (has2) {
+        if (has2) {  // RRDB skip (every third dense block): fetched in place, the item is a long one
+          const float* rp = ly.res2 + (((size_t)n * 16 + (c0 >> 2)) * plane + pix) * 4;
 #pragma unroll
           for (int s4 = 0; s4 < 8; ++s4) {
-            v[4 * s4 + 0] = r2[s4].x + ly.beta * v[4 * s4 + 0];
-            v[4 * s4 + 1] = r2[s4].y + ly.beta * v[4 * s4 + 1];
-            v[4 * s4 + 2] = r2[s4].z + ly.beta * v[4 * s4 + 2];
-            v[4 * s4 + 3] = r2[s4].w + ly.beta * v[4 * s4 + 3];
+            const float4 rr = ld_cg_f4(rp + (size_t)s4 * plane * 4);
+            v[4 * s4 + 0] = rr.x + ly.beta * v[4 * s4 + 0];
+            v[4 * s4 + 1] = rr.y + ly.beta * v[4 * s4 + 1];
+            v[4 * s4 + 2] = rr.z + ly.beta * v[4 * s4 + 2];
+            v[4 * s4 + 3] = rr.w + ly.beta * v[4 * s4 + 3];
           }
         }
         if (ly.act) {
@@ -388,14 +407,22 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
             }
           }
         }
+        }
+#pragma unroll
+        for (int s4 = 0; s4 < 8; ++s4) r1[s4] = r1n[s4];
       }
       // publish the finished unit: the warp's stores are ordered before lane 0's gpu-scope fence by
       // __syncwarp, the fence is cumulative, the flag increment follows it (release pattern)
       if (p.debug & 8) __threadfence();
       __syncwarp();
       if (lane == 0) {
-        __threadfence();
+        if (!(p.debug & 16)) __threadfence();
         atomicAdd(p.done + (size_t)L * I + item, 1u);
+        if (p.prof && q == 0) {
+          atomicAdd(p.prof + L * 8 + 4, (unsigned long long)(e1 - e0));        // waiting for the accumulator
+          atomicAdd(p.prof + L * 8 + 5, (unsigned long long)(e2 - e1));        // read-out until TMEM release
+          atomicAdd(p.prof + L * 8 + 6, (unsigned long long)(clock64() - e2)); // rest: stores, fence, flag
+        }
       }
     }
   }
@@ -414,6 +441,12 @@ using namespace dbm;
 
 namespace dbm {
 int g_trunk_debug = 0;  // set through dbm_debug_set(3, mask)
+unsigned long long* g_trunk_prof = nullptr;
+}
+
+extern "C" int dbm_debug_set_ptr(int key, void* ptr) {
+  if (key == 1) g_trunk_prof = (unsigned long long*)ptr;
+  return DBM_OK;
 }
 
 extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
@@ -438,6 +471,7 @@ extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int
   p.items_per_layer = n * p.tiles_x * p.tiles_y;
   p.done = flags_dev;
   p.debug = g_trunk_debug;
+  p.prof = g_trunk_prof;
   DBM_CUDA(cudaMemsetAsync(flags_dev, 0, (size_t)num_layers * p.items_per_layer * sizeof(unsigned int), stream));
   static bool attr_done = false;
   if (!attr_done) {

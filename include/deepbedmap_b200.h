@@ -41,6 +41,7 @@ typedef struct CUstream_st* cudaStream_t;
 int dbm_version(void);
 const char* dbm_last_error(void);
 int dbm_debug_set(int key, int value);
+int dbm_debug_set_ptr(int key, void* device_ptr); /* tuning only: 1 = trunk-kernel cycle counters */
 
 /* ---- fp32 convolution family -------------------------------------------------------------
  * L.Convolution2D forward (+ optional fused F.leaky_relu(slope=0.2)):
