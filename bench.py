@@ -101,7 +101,9 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # short watchdog: a mismatched collective must fail in minutes, not burn the GPU box for ten
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     else:
         torch.cuda.set_device(0)
     return rank, world, local
@@ -305,7 +307,9 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     value = mpx * args.steps / (ms * 1e-3)
 
-    roof = instrumented_roofline(model, grids, kw, peak_tf) if rank == 0 else None
+    # every rank runs the instrumented strip (predict_continent ends in a collective gather); rank 0's
+    # CUDA-event timings are the ones reported
+    roof = instrumented_roofline(model, grids, kw, peak_tf)
     barrier(world)
 
     # ---- end to end: pinned host grids -> host DEM ----

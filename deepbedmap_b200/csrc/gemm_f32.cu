@@ -82,7 +82,12 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int kt = kbeg; kt < kend; kt += BK) {
+  // Global -> register fetch of the next K tile is issued before the math of the current one
+  // (register double buffering): these layers are small (M ~ 10^4), so latency, not FLOPs, bounds them.
+  float ra[4], rb[4];
+  const bool a_kmajor = (MODE == kFwd || MODE == kDgrad || (MODE == kPlain && p.lda_m == 1));
+  const bool b_kmajor = (MODE == kPlain && p.ldb_n == 1);
+  auto fetch = [&](int kt) {
     // ---------------- load A tile -> As[k][m] ----------------
     if (MODE == kFwd) {
 #pragma unroll
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
           if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W)
             v = __ldg(p.A + a_n * p.x_bs + (long)c * HW + hi * p.W + wi);
         }
-        As[kl][t & 63] = v;
+        ra[i] = v;
       }
     } else if (MODE == kDgrad) {
 #pragma unroll
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
             if (ho < p.HO && wo < p.WO) v = __ldg(p.A + a_n * p.y_bs + (long)o * HOWO + ho * p.WO + wo);
           }
         }
-        As[kl][t & 63] = v;
+        ra[i] = v;
       }
     } else if (MODE == kWgrad) {
       const int kl = t & 15, k = kt + kl;
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
         const int ml = (t >> 4) + 16 * i, m = m0 + ml;
         float v = 0.f;
         if (kok && m < p.M) v = __ldg(p.A + n_img * p.y_bs + (long)m * HOWO + rem);
-        As[kl][ml] = v;
+        ra[i] = v;
       }
     } else if (p.lda_m == 1) {  // plain, A unit-stride along m
 #pragma unroll
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
         const int kl = (t >> 6) + 4 * i, k = kt + kl, m = m0 + (t & 63);
         float v = 0.f;
         if (k < kend && m < p.M) v = __ldg(Ap + m + k * p.lda_k);
-        As[kl][t & 63] = v;
+        ra[i] = v;
       }
     } else {  // plain, A unit-stride along k
       const int kl = t & 15, k = kt + kl;
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
         const int ml = (t >> 4) + 16 * i, m = m0 + ml;
         float v = 0.f;
         if (k < kend && m < p.M) v = __ldg(Ap + m * p.lda_m + k * p.lda_k);
-        As[kl][ml] = v;
+        ra[i] = v;
       }
     }
     // ---------------- load B tile -> Bs[k][n] ----------------
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
         const int nl = (t >> 4) + 16 * i, n = n0 + nl;
         float v = 0.f;
         if (k < kend && n < p.N) v = __ldg(p.B + (long)n * p.K + k);
-        Bs[kl][nl] = v;
+        rb[i] = v;
       }
     } else if (MODE == kDgrad) {
       const int kl = t & 15, k = kt + kl;
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
         const int nl = (t >> 4) + 16 * i, n = n0 + nl;
         float v = 0.f;
         if (k < kend && n < p.N) v = __ldg(p.B + ((long)o * p.C + n) * KK + r);
-        Bs[kl][nl] = v;
+        rb[i] = v;
       }
     } else if (MODE == kWgrad) {
       const int kl = t & 15, k = kt + kl;
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
           if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W)
             v = __ldg(p.B + n_img * p.x_bs + (long)bw_c[i] * HW + hi * p.W + wi);
         }
-        Bs[kl][nl] = v;
+        rb[i] = v;
       }
     } else {  // plain: pick the mapping along B's unit-stride dim
       if (p.ldb_n == 1) {
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
           const int kl = (t >> 6) + 4 * i, k = kt + kl, n = n0 + (t & 63);
           float v = 0.f;
           if (k < kend && n < p.N) v = __ldg(Bp + k * p.ldb_k + n);
-          Bs[kl][t & 63] = v;
+          rb[i] = v;
         }
       } else {
         const int kl = t & 15, k = kt + kl;
@@ -198,11 +203,25 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
           const int nl = (t >> 4) + 16 * i, n = n0 + nl;
           float v = 0.f;
           if (k < kend && n < p.N) v = __ldg(Bp + k * p.ldb_k + n * p.ldb_n);
-          Bs[kl][nl] = v;
+          rb[i] = v;
         }
       }
     }
+  };
+  auto commit = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (a_kmajor) As[(t >> 6) + 4 * i][t & 63] = ra[i];
+      else As[t & 15][(t >> 4) + 16 * i] = ra[i];
+      if (b_kmajor) Bs[(t >> 6) + 4 * i][t & 63] = rb[i];
+      else Bs[t & 15][(t >> 4) + 16 * i] = rb[i];
+    }
+  };
+  if (kbeg < kend) fetch(kbeg);
+  for (int kt = kbeg; kt < kend; kt += BK) {
+    commit();
     __syncthreads();
+    if (kt + BK < kend) fetch(kt + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[4], b[4];

@@ -161,11 +161,14 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, float* __rest
 
 // db[o] += sum_{n,pixels} dy[n, o, :]  (bias gradient of L.Convolution2D)
 __global__ void bias_grad_kernel(const float* __restrict__ dy, long dy_bs, float* __restrict__ db, int N, int HW) {
+  // grid = (channels, image chunks): each block reduces its images' planes, one atomicAdd per block
   const int o = blockIdx.x;
+  const int per = (N + gridDim.y - 1) / gridDim.y;
+  const int n0 = blockIdx.y * per, n1 = min(N, n0 + per);
   float s = 0.f;
-  for (long i = threadIdx.x; i < (long)N * HW; i += blockDim.x) {
-    const long n = i / HW, r = i - n * HW;
-    s += dy[n * dy_bs + (long)o * HW + r];
+  for (int n = n0; n < n1; ++n) {
+    const float* __restrict__ src = dy + (long)n * dy_bs + (long)o * HW;
+    for (int r = threadIdx.x; r < HW; r += blockDim.x) s += src[r];
   }
   __shared__ float red[32];
   for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -174,7 +177,7 @@ __global__ void bias_grad_kernel(const float* __restrict__ dy, long dy_bs, float
   if (threadIdx.x < 32) {
     s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (threadIdx.x == 0) db[o] += s;
+    if (threadIdx.x == 0 && n0 < n1) atomicAdd(db + o, s);
   }
 }
 
@@ -271,7 +274,12 @@ extern "C" int dbm_upsample2_bwd_f32(const float* dy, float* dx, long planes, in
   return check_launch("upsample2_bwd");
 }
 extern "C" int dbm_bias_grad_f32(const float* dy, long dy_bs, float* db, int n, int o, int hw, cudaStream_t st) {
-  bias_grad_kernel<<<o, 256, 0, st>>>(dy, dy_bs ? dy_bs : (long)o * hw, db, n, hw);
+  // small planes (9x9 training tiles): fewer threads per block, more image chunks
+  const int threads = hw >= 1024 ? 256 : (hw >= 256 ? 128 : 64);
+  int chunks = (8 * num_sms() + o - 1) / o;
+  if (chunks > n) chunks = n;
+  if (chunks < 1) chunks = 1;
+  bias_grad_kernel<<<dim3(o, chunks), threads, 0, st>>>(dy, dy_bs ? dy_bs : (long)o * hw, db, n, hw);
   return check_launch("bias_grad");
 }
 extern "C" int dbm_crop_clip_f32(const float* src, int hs, int ws, float* dst, int c, int y0, int x0, int h, int w,

@@ -122,6 +122,14 @@ class _Link:
     def mark_updated(self):
         self.version += 1
 
+    def grad_range(self, prefixes):
+        """[lo, hi) element range of ``flat_grad`` covering every parameter whose key starts with one of
+        ``prefixes`` (parameters of one stage are contiguous in the flat buffer)."""
+        rng = [(o, o + n) for k, (o, n) in self._slices.items() if any(k.startswith(p) for p in prefixes)]
+        if not rng:
+            raise KeyError(prefixes)
+        return min(a for a, _ in rng), max(b for _, b in rng)
+
 
 # ================================================================================================
 # Generator
@@ -271,12 +279,15 @@ class GeneratorModel(_Link):
                              cols1=cols1, off2=off2, cols2=cols2, H=H, W=W, n=n)
         return y
 
-    def backward(self, dy: torch.Tensor):
+    def backward(self, dy: torch.Tensor, on_ready=None):
         """Accumulates d(loss)/d(params) into ``flat_grad`` given d(loss)/d(output) (N,1,4H,4W);
         replaces g_loss.backward() for the generator (srgan_train.py:1256). No gradient wrt the
-        inputs is produced (no caller needs it)."""
+        inputs is produced (no caller needs it). ``on_ready(lo, hi)`` is called as soon as the
+        gradients of flat_grad[lo:hi] are final (head, then each RRDB from last to first, then the
+        stem), so a data-parallel caller can all-reduce that bucket while the rest of backward runs."""
         if self._ctx is None:
             raise RuntimeError("backward() needs a preceding forward_train()")
+        ready = (lambda *pre: on_ready(*self.grad_range(pre))) if on_ready is not None else (lambda *pre: None)
         c = self._ctx
         P, G = self.p, self.g
         g = self.inter_channels
@@ -322,6 +333,7 @@ class GeneratorModel(_Link):
                               db=G["post_residual_conv_layer/b"])
         dcur = ops.empty(n, 64, H, W)  # gradient wrt the trunk output
         ops.conv2d_bwd_data(da3, 0, P["post_residual_conv_layer/W"], dcur, 0, 64, 3, 1, 1)
+        ready("post_residual_conv_layer", "post_upsample_conv_layer", "final_conv_layer")
         # ---- trunk, reversed ----
         j = nrdb
         for i in reversed(range(self.num_residual_blocks)):
@@ -350,6 +362,7 @@ class GeneratorModel(_Link):
             # RRDB skip: d x += d out
             dcur = ops.empty(n, 64, H, W)
             ops.axpby(d_rdb_out, 0, d_rrdb_out, 0, dcur, 0, 64, 1.0, 1.0)
+            ready(f"residual_network/{i}/")
         # ---- a1 = lrelu(pre_res(a0)); total gradient = trunk input + skip to a3 ----
         da1 = ops.empty(n, 64, H, W)
         ops.axpby(dcur, 0, da3, 0, da1, 0, 64, 1.0, 1.0)
@@ -366,6 +379,7 @@ class GeneratorModel(_Link):
                               db=G["input_block/conv_on_W2/b"])
         ops.conv2d_bwd_weight(c["w3"], 0, 1, da0, 96, G["input_block/conv_on_W3/W"], 3, 1, 0,
                               db=G["input_block/conv_on_W3/b"])
+        ready("input_block/", "pre_residual_conv_layer")
         self._ctx = None
 
     # ---------------- bf16 tensor-core path (inference) ----------------
@@ -644,11 +658,14 @@ class DiscriminatorModel(_Link):
             self._ctx = dict(acts=acts, pres=pres, stats=stats, l1=l1, n=n)
         return Variable(out)
 
-    def backward(self, dlogit: torch.Tensor):
+    def backward(self, dlogit: torch.Tensor, on_ready=None):
         """Accumulates parameter gradients for the most recent ``forward(save=True)`` given
-        d(loss)/d(logits) (N,1); replaces d_loss.backward() (srgan_train.py:1163)."""
+        d(loss)/d(logits) (N,1); replaces d_loss.backward() (srgan_train.py:1163). ``on_ready(lo, hi)``:
+        see GeneratorModel.backward (pass it only on the LAST backward of a step: the real and fake
+        passes accumulate into the same buffer)."""
         if self._ctx is None:
             raise RuntimeError("backward() needs a preceding forward(save=True)")
+        ready = (lambda *pre: on_ready(*self.grad_range(pre))) if on_ready is not None else (lambda *pre: None)
         c = self._ctx
         P, G = self.p, self.g
         n = c["n"]
@@ -684,7 +701,14 @@ class DiscriminatorModel(_Link):
             dx = ops.empty(*xin.shape)
             ops.conv2d_bwd_data(dz, 0, P[f"conv_layer{i}/W"], dx, 0, cin, k, s, 1)
             dy = dx
+            if i == 9:
+                ready("linear_", "conv_layer9/", "batch_norm9/")
+            elif i == 5:
+                ready("conv_layer5/", "batch_norm5/", "conv_layer6/", "batch_norm6/", "conv_layer7/", "batch_norm7/",
+                      "conv_layer8/", "batch_norm8/")
         # conv_layer0 + LeakyReLU
         ops.lrelu_bwd(dy, 0, acts[1], 0, dy, 0, 64)
         ops.conv2d_bwd_weight(acts[0], 0, 1, dy, 0, G["conv_layer0/W"], 3, 1, 1, db=G["conv_layer0/b"])
+        ready("conv_layer0/", "conv_layer1/", "batch_norm1/", "conv_layer2/", "batch_norm2/", "conv_layer3/",
+              "batch_norm3/", "conv_layer4/", "batch_norm4/")
         self._ctx = None

@@ -3,8 +3,10 @@ compile_srgan_model, train_eval_discriminator, train_eval_generator, trainer.
 
 Data parallelism (new; the reference is single-GPU): when torch.distributed is initialised the
 flat gradient buffer of the model being trained is all-reduced (NCCL over NVLink, averaged over
-ranks) between backward and the Adam update. BatchNorm statistics and the RaGAN batch means stay
-local to each rank, so world_size == 1 reproduces the reference exactly.
+ranks) in buckets that are launched from inside backward as their layers finish (last layers first),
+so the exchange overlaps the remaining backward kernels; Adam runs after the last bucket. BatchNorm
+statistics and the RaGAN batch means stay local to each rank, so world_size == 1 reproduces the
+reference exactly.
 """
 from __future__ import annotations
 
@@ -42,14 +44,69 @@ class Adam:
         link.mark_updated()
 
 
+_COMM_STREAM = None
+
+
+def _comm_stream():
+    global _COMM_STREAM
+    if _COMM_STREAM is None:
+        _COMM_STREAM = torch.cuda.Stream()
+    return _COMM_STREAM
+
+
+class GradBucketReducer:
+    """Data-parallel gradient all-reduce overlapped with backward: ``bucket(lo, hi)`` (the models'
+    ``on_ready`` hook) enqueues an NCCL all-reduce(SUM) of flat_grad[lo:hi] on a side stream as soon as
+    backward has finished that range, so the exchange of the last layers' gradients over NVLink runs
+    under the wgrad/dgrad kernels of the earlier ones. ``finish()`` makes the compute stream wait for
+    all buckets and returns the 1/world_size scale the optimizer applies. With world_size == 1 (the
+    reference's case) it does nothing."""
+
+    def __init__(self, link):
+        import torch.distributed as dist
+        self.link = link
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.works = []
+        self.covered = []
+        if self.dist is not None:
+            # gloo (CPU tests) has no streams; NCCL buckets go on one side stream per reducer
+            self.stream = _comm_stream() if link.flat_grad.is_cuda else None
+
+    def bucket(self, lo: int, hi: int):
+        self.covered.append((lo, hi))
+        if self.dist is None:
+            return
+        view = self.link.flat_grad[lo:hi]
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream())   # bucket's kernels are enqueued before this point
+            with torch.cuda.stream(self.stream):
+                self.works.append(self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, async_op=True))
+        else:
+            self.works.append(self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self) -> float:
+        total = self.link.flat_grad.numel()
+        pos = 0
+        for lo, hi in sorted(self.covered):
+            if lo != pos:
+                raise RuntimeError(f"gradient buckets do not tile the parameter buffer (gap at {pos}:{lo})")
+            pos = hi
+        if pos != total:
+            raise RuntimeError(f"gradient buckets stop at {pos} of {total}")
+        if self.dist is None:
+            return 1.0
+        for w in self.works:
+            w.wait()                                               # current stream waits for the NCCL work
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        return 1.0 / self.dist.get_world_size()
+
+
 def allreduce_grads(link) -> float:
-    """Sum the flat gradient over ranks (async NCCL op on the current stream); returns the
-    scale (1/world_size) the optimizer applies."""
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(link.flat_grad, op=dist.ReduceOp.SUM)
-        return 1.0 / dist.get_world_size()
-    return 1.0
+    """Un-bucketed variant: one all-reduce of the whole flat gradient after backward."""
+    r = GradBucketReducer(link)
+    r.bucket(0, link.flat_grad.numel())
+    return r.finish()
 
 
 def compile_srgan_model(num_residual_blocks: int = 12, residual_scaling: float = 0.1,
@@ -90,12 +147,12 @@ def train_eval_discriminator(input_arrays: Dict[str, object], g_model: Generator
     ctx_fake = d_model._ctx
     out, d_real, d_fake = _ragan(real_pred, fake_pred, 1.0, 0.0, want_grads=train)  # :1149-1158
     if train:
+        reducer = GradBucketReducer(d_model)
         d_model._ctx = ctx_fake
         d_model.backward(d_fake)                                                   # :1163
         d_model._ctx = ctx_real
-        d_model.backward(d_real)
-        scale = allreduce_grads(d_model)
-        d_optimizer.update(grad_scale=scale)                                       # :1164
+        d_model.backward(d_real, on_ready=reducer.bucket)   # gradients are final after the second pass
+        d_optimizer.update(grad_scale=reducer.finish())                            # :1164
     d_model._ctx = None
     res = out.cpu()                                                                # :1166 (host sync)
     return float(res[0]), float(res[1])
@@ -136,9 +193,9 @@ def train_eval_generator(input_arrays: Dict[str, object], g_model: GeneratorMode
              dy.data_ptr() if train else None, ops.stream())
     if train:
         g_model.cleargrads()                                                       # :1255
-        g_model.backward(dy)                                                       # :1256
-        scale = allreduce_grads(g_model)
-        g_optimizer.update(grad_scale=scale)                                       # :1257
+        reducer = GradBucketReducer(g_model)
+        g_model.backward(dy, on_ready=reducer.bucket)                              # :1256
+        g_optimizer.update(grad_scale=reducer.finish())                            # :1257
     s = sums.cpu().double().numpy()                                                # host sync (:1259-1263)
     adv_v = float(adv.cpu()[0])
     npx = n * H * W

@@ -70,6 +70,21 @@ def _worker(rank, world, port, q):
         scale = train.allreduce_grads(Link)
         expect = torch.arange(10, dtype=torch.float32) * 3  # (1 + 2)
         ok = bool(torch.equal(Link.flat_grad, expect)) and scale == 0.5
+        # bucketed variant: buckets arrive in backward order (tail of the buffer first)
+        class Link2:
+            flat_grad = torch.arange(12, dtype=torch.float32) * (rank + 1)
+
+        red = train.GradBucketReducer(Link2)
+        for lo, hi in ((9, 12), (4, 9), (0, 4)):
+            red.bucket(lo, hi)
+        ok = ok and red.finish() == 0.5 and bool(torch.equal(Link2.flat_grad, torch.arange(12, dtype=torch.float32) * 3))
+        bad = train.GradBucketReducer(Link2)
+        bad.bucket(0, 4)
+        try:
+            bad.finish()
+            ok = False
+        except RuntimeError:
+            pass
         if rank == 0:
             q.put(("allreduce", ok))
     finally:
