@@ -31,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MPX = 396.0  # 18000 x 22000 output pixels
+TRUNK_DRAM_BYTES_PER_FLOP = 25.05e9 / 5.717e12  # measured, see instrumented_roofline()
 FULL = dict(final_shape=(18000, 22000), ary_shape=(1000, 1000), grid=(4502, 5502))
 
 
@@ -222,8 +223,13 @@ def instrumented_roofline(model, grids, kw, peak_tf):
                   "flops_per_launch_avg": fl / len(v), "ms_total": ms}
     dom = max(out, key=lambda k: out[k]["ms_total"])
     ach = out[dom]["tflops"]
+    # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one
+    # `ncu --set full` capture (profiles/r1c_trunk_kernel_ncu_full_raw.csv: 14.17 + 10.88 GB for a launch of
+    # 4 interior tiles = 5.72 TFLOP), scaled to this run's average launch by its algorithmic FLOPs
+    traffic = TRUNK_DRAM_BYTES_PER_FLOP * out[dom]["flops_per_launch_avg"] if dom == "umma_trunk_kernel" else None
     return {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-            "traffic": None, "kernel": dom, "launches_timed": out[dom]["launches_timed"],
+            "traffic": traffic, "traffic_source": "ncu --set full, profiles/r1c_trunk_kernel_ncu_full_raw.csv",
+            "kernel": dom, "launches_timed": out[dom]["launches_timed"],
             "avg_launch_us": out[dom]["avg_launch_us"], "flops_per_launch_avg": out[dom]["flops_per_launch_avg"],
             "all_tcgen05_conv_kernels": {k: {kk: vv for kk, vv in v.items() if kk != "ms_total"} | {
                 "frac": v["tflops"] / peak_tf} for k, v in out.items()}}
@@ -250,7 +256,8 @@ def train_bench(rank, world, steps=3, warmup=2, batch=128):
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     return {"metric": "train steps/s (D-step + G-step, batch 128 per GPU)", "value": steps / (ms * 1e-3),
             "unit": "steps/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "scaling": "weak",
-            "global_batch": batch * world, "dtype": "f32 backward / f32 forward (bf16 tcgen05 generator in the D-step)"}
+            "global_batch": batch * world, "dtype": "f32 backward / f32 forward (bf16 tcgen05 generator in the D-step)",
+            "allreduce": "bucketed, launched from inside backward (NCCL, overlapped)" if world > 1 else "none (1 GPU)"}
 
 
 def main():
