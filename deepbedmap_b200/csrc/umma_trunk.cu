@@ -61,10 +61,10 @@ struct TrunkLayer {  // 128 bytes, mirrored by deepbedmap_b200/model.py (TRUNK_L
   const __nv_bfloat16* wpacked;
   const float* bias;
   __nv_bfloat16* out_bf16;
-  float* out_f32;      // slab4, 16 slabs
-  const float* res1;   // slab4, res1_cs_total slabs
-  const float* res2;   // slab4, 16 slabs
-  float* stash_out;    // slab4, (cout - cout_main) / 4 slabs
+  float* out_f32;      // slab8f (fp32 [N][8][H][W][8]), 64 channels
+  const float* res1;   // slab8f, 4 * res1_cs_total channels
+  const float* res2;   // slab8f, 64 channels
+  float* stash_out;    // slab8f, cout - cout_main channels
   int cin, cout;       // cout (MMA N) in {32, 64}
   int in_map, in_cs0;  // in_map: 0 = stem output (16 slabs), 1 / 2 = dense-block buffers
   int act, up2;
@@ -93,8 +93,26 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ float4 ld_cg_f4(const float* p) {  // L2-coherent load (data written by other SMs)
-  return __ldcg(reinterpret_cast<const float4*>(p));
+// The trunk's fp32 side buffers (residual stream, stash) are "slab8f": fp32 [N][C/8][H][W][8], one
+// 32-byte vector per pixel per slab, moved with 256-bit loads / stores (half the LSU instructions of
+// the 16-byte slab4 form; the epilogue shares the L1 data path with the UMMA operand fetch).
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ld_cg_f8(const float* p) {  // L2-coherent (data written by other SMs)
+  F8 r;
+  asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
+                 "=f"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_f8(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6,
+                                      float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3),
+               "f"(a4), "f"(a5), "f"(a6), "f"(a7)
+               : "memory");
 }
 
 __global__ void __launch_bounds__(kTrunkThreads, 1)
@@ -273,7 +291,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       const int x0 = tx * kTW + xr;
       const int nbc = ly.cout >> 5;            // 32-column blocks per sub-tile
       const int nblk = 4 * nbc;                // sub-tile-major
-      float4 r1[8], r1n[8];
+      F8 r1[4], r1n[4];
       // this pass's bias, staged per warp in shared memory (a global read per block would cost an
       // L2 round trip each: the gpu-scope fences keep invalidating L1)
       if (lane < ly.cout_main) sbias[lane] = __ldg(ly.bias + lane);
@@ -297,14 +315,15 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       }
       __syncwarp();
       // res1 of block b is requested one block ahead (block 0: before the accumulator is complete)
-      auto load_r1 = [&](int b, float4 (&dst)[8]) {
+      auto load_r1 = [&](int b, F8 (&dst)[4]) {
         const int j = nbc == 2 ? (b >> 1) : b;
         const int c0 = (b - j * nbc) << 5;
         const int x = x0 + 8 * (j & 1), y = y0 + 16 * (j >> 1);
         if (ly.res1 != nullptr && c0 < ly.cout_main && mem && y < p.H && x < p.W) {
-          const float* rp = ly.res1 + (((size_t)n * ly.res1_cs_total + (c0 >> 2)) * plane + (size_t)y * p.W + x) * 4;
+          const float* rp =
+              ly.res1 + (((size_t)n * (ly.res1_cs_total >> 1) + (c0 >> 3)) * plane + (size_t)y * p.W + x) * 8;
 #pragma unroll
-          for (int s4 = 0; s4 < 8; ++s4) dst[s4] = ld_cg_f4(rp + (size_t)s4 * plane * 4);
+          for (int s8 = 0; s8 < 4; ++s8) dst[s8] = ld_cg_f8(rp + (size_t)s8 * plane * 8);
         }
       };
       load_r1(0, r1);
@@ -334,13 +353,13 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         }
         if (valid && !main_blk) {
           // raw partial sums of the paired layer -> fp32 stash
-          const int scs = (ly.cout - ly.cout_main) >> 2;
-          float* sp = ly.stash_out + (((size_t)n * scs + ((c0 - ly.cout_main) >> 2)) * plane + pix) * 4;
+          const int scs = (ly.cout - ly.cout_main) >> 3;
+          float* sp = ly.stash_out + (((size_t)n * scs + ((c0 - ly.cout_main) >> 3)) * plane + pix) * 8;
 #pragma unroll
-          for (int s4 = 0; s4 < 8; ++s4)
-            *reinterpret_cast<float4*>(sp + (size_t)s4 * plane * 4) =
-                make_float4(__uint_as_float(acc[4 * s4]), __uint_as_float(acc[4 * s4 + 1]),
-                            __uint_as_float(acc[4 * s4 + 2]), __uint_as_float(acc[4 * s4 + 3]));
+          for (int s8 = 0; s8 < 4; ++s8)
+            st_f8(sp + (size_t)s8 * plane * 8, __uint_as_float(acc[8 * s8]), __uint_as_float(acc[8 * s8 + 1]),
+                  __uint_as_float(acc[8 * s8 + 2]), __uint_as_float(acc[8 * s8 + 3]), __uint_as_float(acc[8 * s8 + 4]),
+                  __uint_as_float(acc[8 * s8 + 5]), __uint_as_float(acc[8 * s8 + 6]), __uint_as_float(acc[8 * s8 + 7]));
         } else if (valid) {
         float v[32];
 #pragma unroll
@@ -353,22 +372,15 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         }
         if (has1) {
 #pragma unroll
-          for (int s4 = 0; s4 < 8; ++s4) {
-            v[4 * s4 + 0] = r1[s4].x + ly.beta * v[4 * s4 + 0];
-            v[4 * s4 + 1] = r1[s4].y + ly.beta * v[4 * s4 + 1];
-            v[4 * s4 + 2] = r1[s4].z + ly.beta * v[4 * s4 + 2];
-            v[4 * s4 + 3] = r1[s4].w + ly.beta * v[4 * s4 + 3];
-          }
+          for (int i = 0; i < 32; ++i) v[i] = r1[i >> 3].v[i & 7] + ly.beta * v[i];
         }
         if (has2) {  // RRDB skip (every third dense block): fetched in place, the item is a long one
-          const float* rp = ly.res2 + (((size_t)n * 16 + (c0 >> 2)) * plane + pix) * 4;
+          const float* rp = ly.res2 + (((size_t)n * 8 + (c0 >> 3)) * plane + pix) * 8;
 #pragma unroll
-          for (int s4 = 0; s4 < 8; ++s4) {
-            const float4 rr = ld_cg_f4(rp + (size_t)s4 * plane * 4);
-            v[4 * s4 + 0] = rr.x + ly.beta * v[4 * s4 + 0];
-            v[4 * s4 + 1] = rr.y + ly.beta * v[4 * s4 + 1];
-            v[4 * s4 + 2] = rr.z + ly.beta * v[4 * s4 + 2];
-            v[4 * s4 + 3] = rr.w + ly.beta * v[4 * s4 + 3];
+          for (int s8 = 0; s8 < 4; ++s8) {
+            const F8 rr = ld_cg_f8(rp + (size_t)s8 * plane * 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * s8 + i] = rr.v[i] + ly.beta * v[8 * s8 + i];
           }
         }
         if (ly.act) {
@@ -376,11 +388,11 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
           for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
         }
         if (ly.out_f32) {
-          float* op = ly.out_f32 + (((size_t)n * 16 + (c0 >> 2)) * plane + pix) * 4;
+          float* op = ly.out_f32 + (((size_t)n * 8 + (c0 >> 3)) * plane + pix) * 8;
 #pragma unroll
-          for (int s4 = 0; s4 < 8; ++s4)
-            *reinterpret_cast<float4*>(op + (size_t)s4 * plane * 4) =
-                make_float4(v[4 * s4], v[4 * s4 + 1], v[4 * s4 + 2], v[4 * s4 + 3]);
+          for (int s8 = 0; s8 < 4; ++s8)
+            st_f8(op + (size_t)s8 * plane * 8, v[8 * s8], v[8 * s8 + 1], v[8 * s8 + 2], v[8 * s8 + 3], v[8 * s8 + 4],
+                  v[8 * s8 + 5], v[8 * s8 + 6], v[8 * s8 + 7]);
         }
         if (ly.out_bf16) {
 #pragma unroll
@@ -409,7 +421,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         }
         }
 #pragma unroll
-        for (int s4 = 0; s4 < 8; ++s4) r1[s4] = r1n[s4];
+        for (int s8 = 0; s8 < 4; ++s8) r1[s8] = r1n[s8];
       }
       // publish the finished unit: the warp's stores are ordered before lane 0's gpu-scope fence by
       // __syncwarp, the fence is cumulative, the flag increment follows it (release pattern)
