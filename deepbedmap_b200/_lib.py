@@ -36,6 +36,7 @@ SIGNATURES = {
     "dbm_slab4_to_nchw": [_P, _P, _L, _I, _I, _I, _I, _I, _P],
     "dbm_pack_conv3x3_weights": [_P, _P, _I, _I, _I, _I, _P],
     "dbm_pack_conv3x3_weights_slice": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _P],
+    "dbm_pack_conv3x3_table": [_P, _I, _L, _P],
     "dbm_trunk_umma": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P],
     "dbm_transpose_f32": [_P, _P, _I, _I, _P],
     "dbm_stem_fwd_slab8": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

@@ -27,11 +27,17 @@ struct GemmP {
   int atomic;                                     // plain GEMM: atomicAdd epilogue (batch-reduced C)
 };
 
-constexpr int BM = 64, BN = 64, BK = 16, LDS = 68;
+constexpr int BK = 16, LDS = 68;
 
-template <int MODE, int KH, int S>
+// TM x TN = outputs per thread (tile = 16 TM x 16 TN): the narrow variants serve the generator's
+// 32-channel dense-block convs (forward / dgrad with N = 32: TN = 2; wgrad with M = 32: TM = 2)
+// without computing a half-empty 64-wide tile.
+template <int MODE, int KH, int S, int TM = 4, int TN = 4>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
   constexpr int KK = KH * KH;
+  constexpr int BM = 16 * TM, BN = 16 * TN;
+  static_assert(TM == 4 || MODE == kWgrad, "narrow M tiles: wgrad only");
+  static_assert(TN == 4 || MODE == kFwd || MODE == kDgrad, "narrow N tiles: forward / dgrad only");
   __shared__ __align__(16) float As[BK][LDS];
   __shared__ __align__(16) float Bs[BK][LDS];
   const int t = threadIdx.x;
@@ -76,11 +82,11 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
     }
   }
 
-  float acc[4][4];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   // Global -> register fetch of the next K tile is issued before the math of the current one
   // (register double buffering): these layers are small (M ~ 10^4), so latency, not FLOPs, bounds them.
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
       const bool kok = k < kend;
       if (kok) { n_img = k / HOWO; rem = k - n_img * HOWO; }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < TM; ++i) {
         const int ml = (t >> 4) + 16 * i, m = m0 + ml;
         float v = 0.f;
         if (kok && m < p.M) v = __ldg(p.A + n_img * p.y_bs + (long)m * HOWO + rem);
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
     if (MODE == kFwd) {
       const int kl = t & 15, k = kt + kl;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < TN; ++i) {
         const int nl = (t >> 4) + 16 * i, n = n0 + nl;
         float v = 0.f;
         if (k < kend && n < p.N) v = __ldg(p.B + (long)n * p.K + k);
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
       const int kl = t & 15, k = kt + kl;
       const int o = k / KK, r = k - o * KK;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < TN; ++i) {
         const int nl = (t >> 4) + 16 * i, n = n0 + nl;
         float v = 0.f;
         if (k < kend && n < p.N) v = __ldg(p.B + ((long)o * p.C + n) * KK + r);
@@ -212,9 +218,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (a_kmajor) As[(t >> 6) + 4 * i][t & 63] = ra[i];
-      else As[t & 15][(t >> 4) + 16 * i] = ra[i];
+      else if (i < TM) As[t & 15][(t >> 4) + 16 * i] = ra[i];
       if (b_kmajor) Bs[(t >> 6) + 4 * i][t & 63] = rb[i];
-      else Bs[t & 15][(t >> 4) + 16 * i] = rb[i];
+      else if (i < TN) Bs[t & 15][(t >> 4) + 16 * i] = rb[i];
     }
   };
   if (kbeg < kend) fetch(kbeg);
@@ -224,22 +230,22 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
     if (kt + BK < kend) fetch(kt + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      float a[4], b[4];
+      float a[TM], b[TN];
       if (C_MFAST) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
-        const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][ty * 4]);
-        b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
-      } else {
-        const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-        a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+        for (int i = 0; i < TM; ++i) a[i] = As[kk][tx + 16 * i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+        for (int j = 0; j < TN; ++j) b[j] = Bs[kk][ty * TN + j];
+      } else {
+#pragma unroll
+        for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx + 16 * j];
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -247,8 +253,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
   // ---------------- epilogue ----------------
   const bool atomic = (MODE == kPlain) ? (p.atomic != 0) : (gridDim.z > 1);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + (C_MFAST ? tx + 16 * i : ty * 4 + i);
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + (C_MFAST ? tx + 16 * i : ty * TM + i);
     if (m >= p.M) continue;
     long mbase = 0;
     if (MODE == kFwd) {
@@ -259,8 +265,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
       mbase = n_img * p.x_bs + r;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + (C_MFAST ? ty * 4 + j : tx + 16 * j);
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + (C_MFAST ? ty * TN + j : tx + 16 * j);
       if (n >= p.N) continue;
       float v = acc[i][j];
       long idx;
@@ -282,11 +288,24 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmP p) {
 
 template <int MODE>
 static int dispatch(const GemmP& p, int kh, int s, int splits, cudaStream_t st) {
+  constexpr int BM = 64, BN = 64;
   dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, BN), splits);
   if (MODE == kPlain) {
     if (p.ldc_m == 1 && p.ldc_n != 1) gemm_f32_kernel<kPlain, 2, 1><<<grid, 256, 0, st>>>(p);
     else gemm_f32_kernel<kPlain, 1, 1><<<grid, 256, 0, st>>>(p);
   } else if (kh == 3 && s == 1) {
+    if constexpr (MODE == kFwd || MODE == kDgrad) {
+      if (p.N <= 32) {
+        gemm_f32_kernel<MODE, 3, 1, 4, 2><<<dim3(grid.x, 1, splits), 256, 0, st>>>(p);
+        return check_launch("gemm_f32_kernel");
+      }
+    }
+    if constexpr (MODE == kWgrad) {
+      if (p.M <= 32) {
+        gemm_f32_kernel<MODE, 3, 1, 2, 4><<<dim3(1, grid.y, splits), 256, 0, st>>>(p);
+        return check_launch("gemm_f32_kernel");
+      }
+    }
     gemm_f32_kernel<MODE, 3, 1><<<grid, 256, 0, st>>>(p);
   } else if (kh == 4 && s == 2) {
     gemm_f32_kernel<MODE, 4, 2><<<grid, 256, 0, st>>>(p);
@@ -348,6 +367,7 @@ extern "C" int dbm_conv2d_bwd_weight_f32(const float* x, long x_batch_stride, co
   if (rc) return rc;
   p.M = o; p.N = c * ksize * ksize; p.K = n * p.HO * p.WO;
   p.A = dy; p.B = x; p.Cc = dw;
+  const int BM = p.M <= 32 ? 32 : 64, BN = 64;
   const int tiles = ceil_div(p.M, BM) * ceil_div(p.N, BN);
   int splits = (4 * num_sms() + tiles - 1) / tiles;
   int max_splits = ceil_div(p.K, 4 * BK);

@@ -316,6 +316,33 @@ __global__ void pack_w3x3_slice_kernel(const float* __restrict__ w, __nv_bfloat1
   }
 }
 
+// Table-driven form: one launch re-packs every filter of a model (blockIdx.y = table entry). The
+// training step re-packs the generator's ~600 operand images after every Adam update; one launch
+// instead of ~1200 keeps that off the critical path.
+struct PackEntry {  // 48 bytes, mirrored by deepbedmap_b200/model.py (PACK_ENTRY_DTYPE)
+  const float* w;
+  __nv_bfloat16* out;
+  int O, o0, Cin, CinTotal, c0, COUTP, CK, pad;
+};
+static_assert(sizeof(PackEntry) == 48, "PackEntry layout is part of the C ABI");
+
+__global__ void pack_w3x3_table_kernel(const PackEntry* __restrict__ table) {
+  const PackEntry e = table[blockIdx.y];
+  const long total = (long)9 * e.Cin * e.COUTP;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int c8 = t % 8; t /= 8;
+    const int o8 = t % 8; t /= 8;
+    const int cg = t % (e.COUTP / 8); t /= (e.COUTP / 8);
+    const int ksl = t % (e.CK / 8); t /= (e.CK / 8);
+    const int tap = t % 9; t /= 9;
+    const int kc = (int)t;
+    const int o = cg * 8 + o8 - e.o0;
+    const int c = kc * e.CK + ksl * 8 + c8;
+    if (o >= 0 && o < e.O) e.out[i] = __float2bfloat16_rn(e.w[((long)o * e.CinTotal + e.c0 + c) * 9 + tap]);
+  }
+}
+
 __global__ void pack_w3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int Cin,
                                  int COUTP, int CK) {
   const long total = (long)9 * Cin * COUTP;
@@ -371,6 +398,17 @@ extern "C" int dbm_pack_conv3x3_weights_slice(const float* w_oihw, int w_cin_tot
   pack_w3x3_slice_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w_oihw, (__nv_bfloat16*)packed_bf16, cout, cout0,
                                                                    cin, w_cin_total, w_c0, cout_padded, ck);
   return check_launch("pack_w3x3_slice_kernel");
+}
+
+extern "C" int dbm_pack_conv3x3_table(const void* table_dev, int num_entries, long max_elements,
+                                      cudaStream_t stream) {
+  DBM_REQUIRE(num_entries > 0 && num_entries <= 65535 && max_elements > 0, "pack table: bad size (%d entries)",
+              num_entries);
+  DBM_REQUIRE(((uintptr_t)table_dev & 7) == 0, "pack table: unaligned");
+  int gx = ceil_div(max_elements, 256 * 4);
+  if (gx > 64) gx = 64;
+  pack_w3x3_table_kernel<<<dim3(gx, num_entries), 256, 0, stream>>>((const PackEntry*)table_dev);
+  return check_launch("pack_w3x3_table_kernel");
 }
 
 extern "C" int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void* wpacked,

@@ -26,6 +26,10 @@ TRUNK_LAYER_DTYPE = np.dtype([("wpacked", "<u8"), ("bias", "<u8"), ("out_bf16", 
                               ("out_cs_total", "<i4"), ("out_cs0", "<i4"), ("cout_main", "<i4"),
                               ("res1_cs_total", "<i4"), ("beta", "<f4"), ("pad", "<i4", (7,))])
 assert TRUNK_LAYER_DTYPE.itemsize == 128
+# mirror of struct PackEntry in csrc/umma_conv3x3.cu (48 bytes)
+PACK_ENTRY_DTYPE = np.dtype([("w", "<u8"), ("out", "<u8"), ("O", "<i4"), ("o0", "<i4"), ("Cin", "<i4"),
+                             ("CinTotal", "<i4"), ("c0", "<i4"), ("COUTP", "<i4"), ("CK", "<i4"), ("pad", "<i4")])
+assert PACK_ENTRY_DTYPE.itemsize == 48
 
 
 class Variable:
@@ -160,6 +164,8 @@ class GeneratorModel(_Link):
         super().__init__(shapes, layout.init_values(shapes, seed, init_scale))
         self._packed_version = -1
         self._packed = {}
+        self._pack_plan = None
+        self._pack_gen = 0   # bumps when the packed buffers are (re)allocated: cached pointer tables key on it
         self._ws = {}
         self.persistent_trunk = True   # one-launch trunk kernel (False: one launch per layer, for A/B tests)
         self.paired_trunk = True       # dense-block layer pairing inside the persistent kernel
@@ -384,73 +390,94 @@ class GeneratorModel(_Link):
 
     # ---------------- bf16 tensor-core path (inference) ----------------
     def _pack(self):
+        """bf16 UMMA operand images of every 3x3 filter (+ the stem's tap-major fp32 filters). The
+        buffers and a device table describing them are created once; after a weight update (training)
+        the whole set is refreshed by ONE table-driven launch (dbm_pack_conv3x3_table)."""
         if self._packed_version == self.version:
             return self._packed
         P = self.p
-        pk = {}
+        if self._pack_plan is None:
+            pk = {}
+            entries = []      # (w, out, O, o0, Cin, CinTotal, c0, COUTP, CK)
+            pad_biases = []   # (padded bias buffer, source bias)
 
-        def add(key, cout_padded, trunk=False):
-            w = P[f"{key}/W"]
-            b = P[f"{key}/b"]
-            if b.numel() < cout_padded:
-                bp = ops.zeros(cout_padded)
-                bp[: b.numel()].copy_(b)
-            else:
-                bp = b
-            pk[key] = (ops.pack_conv3x3(w, cout_padded), bp)
-            if trunk:
-                # the persistent trunk kernel streams every layer in 16-channel chunks
-                pk[key + "@trunk"] = (ops.pack_conv3x3(w, cout_padded, ck=16), bp)
+            def image(cin, cout_padded):
+                return ops.zeros(9 * cin * cout_padded, dtype=torch.bfloat16)
 
-        # stem filters, tap-major, and the concatenated stem bias
-        def tapmajor(keys):
-            taps = [int(P[f"input_block/conv_on_{k}/W"][0].numel()) for k in keys]
-            buf = ops.empty(sum(taps), 32)
-            r0 = 0
-            for k, nt in zip(keys, taps):
-                ops.call("dbm_transpose_f32", P[f"input_block/conv_on_{k}/W"].data_ptr(), buf[r0:].data_ptr(), 32, nt,
-                         ops.stream())
-                r0 += nt
-            return buf
-        bias128 = ops.empty(128)
-        for j, k in enumerate(("X", "W1", "W2", "W3")):
-            ops.axpby(P[f"input_block/conv_on_{k}/b"].view(1, 32, 1, 1), 0, None, 0,
-                      bias128.view(1, 128, 1, 1), 32 * j, 32, 1.0, 0.0)
-        pk["stem"] = (tapmajor(("W1",)), tapmajor(("X", "W2", "W3")), bias128)
-        add("pre_residual_conv_layer", 64, trunk=True)
-        for i in range(self.num_residual_blocks):
-            for r in (1, 2, 3):
-                pre = self._rdb_prefix(i, r)
-                for k in (1, 2, 3, 4):
-                    add(f"{pre}/conv_layer{k}", self.inter_channels, trunk=True)
-                add(f"{pre}/conv_layer5", 64, trunk=True)
-        add("post_residual_conv_layer", 64, trunk=True)
-        if self.inter_channels == 32:
-            # dense-block pairing (see _trunk_workspace): conv_k and the partial sums of conv_{k+1}
-            # over their shared inputs are one 64-wide MMA pass; conv_{k+1} then only contracts a_k
+            def entry(w, out, o, o0, cin, cin_total, c0, coutp, ck):
+                entries.append((w.data_ptr(), out.data_ptr(), o, o0, cin, cin_total, c0, coutp, ck, 0))
+
+            def add(key, cout_padded, trunk=False, ck=32):
+                w, b = P[f"{key}/W"], P[f"{key}/b"]
+                o, cin = w.shape[0], w.shape[1]
+                if b.numel() < cout_padded:
+                    bp = ops.zeros(cout_padded)
+                    pad_biases.append((bp, b))
+                else:
+                    bp = b
+                img = image(cin, cout_padded)
+                entry(w, img, o, 0, cin, cin, 0, cout_padded, ck)
+                pk[key] = (img, bp)
+                if trunk:
+                    # the persistent trunk kernel streams every layer in 16-channel chunks
+                    img16 = image(cin, cout_padded)
+                    entry(w, img16, o, 0, cin, cin, 0, cout_padded, 16)
+                    pk[key + "@trunk"] = (img16, bp)
+
+            add("pre_residual_conv_layer", 64, trunk=True)
             for i in range(self.num_residual_blocks):
                 for r in (1, 2, 3):
                     pre = self._rdb_prefix(i, r)
-                    for k in (1, 3):
-                        cin = 64 + (k - 1) * 32
-                        wa, wb = P[f"{pre}/conv_layer{k}/W"], P[f"{pre}/conv_layer{k + 1}/W"]
-                        both = ops.empty(9 * cin * 64, dtype=torch.bfloat16)
-                        ops.call("dbm_pack_conv3x3_weights_slice", wa.data_ptr(), cin, 0, both.data_ptr(), 32, 0, cin,
-                                 64, 16, ops.stream())
-                        ops.call("dbm_pack_conv3x3_weights_slice", wb.data_ptr(), cin + 32, 0, both.data_ptr(), 32, 32,
-                                 cin, 64, 16, ops.stream())
-                        pk[f"{pre}/pair{k}"] = (both, P[f"{pre}/conv_layer{k}/b"])
-                        tail = ops.empty(9 * 32 * 32, dtype=torch.bfloat16)
-                        ops.call("dbm_pack_conv3x3_weights_slice", wb.data_ptr(), cin + 32, cin, tail.data_ptr(), 32, 0,
-                                 32, 32, 16, ops.stream())
-                        pk[f"{pre}/tail{k + 1}"] = (tail, P[f"{pre}/conv_layer{k + 1}/b"])
-        for key in ("post_upsample_conv_layer_1", "post_upsample_conv_layer_2"):
-            add(key, 64)
-        add("final_conv_layer1/offset_conv", 32)
-        add("final_conv_layer2/offset_conv", 32)
-        pk["final_conv_layer1/deform_conv"] = (ops.pack_conv3x3(P["final_conv_layer1/deform_conv/W"], 64, ck=64),
-                                               P["final_conv_layer1/deform_conv/b"])
-        self._packed = pk
+                    for k in (1, 2, 3, 4):
+                        add(f"{pre}/conv_layer{k}", self.inter_channels, trunk=True)
+                    add(f"{pre}/conv_layer5", 64, trunk=True)
+            add("post_residual_conv_layer", 64, trunk=True)
+            if self.inter_channels == 32:
+                # dense-block pairing (see _trunk_workspace): conv_k and the partial sums of conv_{k+1}
+                # over their shared inputs are one 64-wide MMA pass; conv_{k+1} then only contracts a_k
+                for i in range(self.num_residual_blocks):
+                    for r in (1, 2, 3):
+                        pre = self._rdb_prefix(i, r)
+                        for k in (1, 3):
+                            cin = 64 + (k - 1) * 32
+                            wa, wb = P[f"{pre}/conv_layer{k}/W"], P[f"{pre}/conv_layer{k + 1}/W"]
+                            both = image(cin, 64)
+                            entry(wa, both, 32, 0, cin, cin, 0, 64, 16)
+                            entry(wb, both, 32, 32, cin, cin + 32, 0, 64, 16)
+                            pk[f"{pre}/pair{k}"] = (both, P[f"{pre}/conv_layer{k}/b"])
+                            tail = image(32, 32)
+                            entry(wb, tail, 32, 0, 32, cin + 32, cin, 32, 16)
+                            pk[f"{pre}/tail{k + 1}"] = (tail, P[f"{pre}/conv_layer{k + 1}/b"])
+            for key in ("post_upsample_conv_layer_1", "post_upsample_conv_layer_2"):
+                add(key, 64)
+            add("final_conv_layer1/offset_conv", 32)
+            add("final_conv_layer2/offset_conv", 32)
+            add("final_conv_layer1/deform_conv", 64, ck=64)
+            # stem filters, tap-major, and the concatenated stem bias
+            taps = {k: int(P[f"input_block/conv_on_{k}/W"][0].numel()) for k in ("X", "W1", "W2", "W3")}
+            pk["stem"] = (ops.empty(taps["W1"], 32), ops.empty(taps["X"] + taps["W2"] + taps["W3"], 32), ops.empty(128))
+            table = np.array(entries, dtype=PACK_ENTRY_DTYPE)
+            self._pack_plan = dict(table=torch.from_numpy(table.view(np.uint8).copy()).cuda(), n=len(entries),
+                                   max_elements=max(9 * e[4] * e[7] for e in entries), pad_biases=pad_biases,
+                                   taps=taps)
+            self._packed = pk
+            self._pack_gen += 1
+        plan, pk = self._pack_plan, self._packed
+        ops.call("dbm_pack_conv3x3_table", plan["table"].data_ptr(), plan["n"], plan["max_elements"], ops.stream())
+        for bp, b in plan["pad_biases"]:
+            ops.axpby(b.view(1, b.numel(), 1, 1), 0, None, 0, bp.view(1, bp.numel(), 1, 1), 0, b.numel(), 1.0, 0.0)
+        wt1, wts, bias128 = pk["stem"]
+        r0 = 0
+        for k, dst in (("W1", wt1), ("X", wts), ("W2", wts), ("W3", wts)):
+            nt = plan["taps"][k]
+            row = 0 if k == "W1" else r0
+            ops.call("dbm_transpose_f32", P[f"input_block/conv_on_{k}/W"].data_ptr(), dst[row:].data_ptr(), 32, nt,
+                     ops.stream())
+            if k != "W1":
+                r0 += nt
+        for j, k in enumerate(("X", "W1", "W2", "W3")):
+            ops.axpby(P[f"input_block/conv_on_{k}/b"].view(1, 32, 1, 1), 0, None, 0,
+                      bias128.view(1, 128, 1, 1), 32 * j, 32, 1.0, 0.0)
         self._packed_version = self.version
         return pk
 
@@ -460,7 +487,7 @@ class GeneratorModel(_Link):
         key = (n, H, W)
         ws = self._ws.get(key)
         pk = self._pack()
-        if ws is not None and ws["version"] == (self._packed_version, self.persistent_trunk, self.paired_trunk,
+        if ws is not None and ws["version"] == (self._pack_gen, self.persistent_trunk, self.paired_trunk,
                                                 self.per_layer_ck16):
             return ws
         bf = torch.bfloat16
@@ -524,7 +551,7 @@ class GeneratorModel(_Link):
         ws["table"] = torch.from_numpy(table.view(np.uint8).copy()).cuda()
         tiles = ((H + 31) // 32) * ((W + 15) // 16)   # 32-row x 16-column units (kTH x kTW in umma_trunk.cu)
         ws["flags"] = ops.empty(len(layers) * n * tiles, dtype=torch.int32)
-        ws["version"] = (self._packed_version, self.persistent_trunk, self.paired_trunk, self.per_layer_ck16)
+        ws["version"] = (self._pack_gen, self.persistent_trunk, self.paired_trunk, self.per_layer_ck16)
         self._ws[key] = ws
         return ws
 

@@ -102,6 +102,10 @@ int dbm_pack_conv3x3_weights(const float* w_oihw, void* packed_bf16, int cout, i
  * (c < cin); other rows untouched. Stacks several filters that share an input along Cout. */
 int dbm_pack_conv3x3_weights_slice(const float* w_oihw, int w_cin_total, int w_c0, void* packed_bf16, int cout,
                                    int cout0, int cin, int cout_padded, int ck, cudaStream_t stream);
+/* The same for a whole model in ONE launch: table_dev = num_entries 48-byte records
+ * {const float* w; bf16* out; int cout, cout0, cin, w_cin_total, w_c0, cout_padded, ck, pad}
+ * (struct PackEntry, csrc/umma_conv3x3.cu); max_elements = the largest 9*cin*cout_padded. */
+int dbm_pack_conv3x3_table(const void* table_dev, int num_entries, long max_elements, cudaStream_t stream);
 int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void* wpacked, const float* bias,
                      int cout_padded, int n, int h, int w, float beta, int act, int up2, void* out_slab8,
                      int out_cs_total, int out_cs0, float* out_f32_slab4, int out_f32_cs_total, int out_f32_cs0,
