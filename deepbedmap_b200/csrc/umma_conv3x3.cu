@@ -322,7 +322,7 @@ __global__ void pack_w3x3_slice_kernel(const float* __restrict__ w, __nv_bfloat1
 struct PackEntry {  // 48 bytes, mirrored by deepbedmap_b200/model.py (PACK_ENTRY_DTYPE)
   const float* w;
   __nv_bfloat16* out;
-  int O, o0, Cin, CinTotal, c0, COUTP, CK, pad;
+  int O, o0, Cin, CinTotal, c0, COUTP, CK, mode;  // mode 1: transposed + flipped (dgrad operand)
 };
 static_assert(sizeof(PackEntry) == 48, "PackEntry layout is part of the C ABI");
 
@@ -339,6 +339,12 @@ __global__ void pack_w3x3_table_kernel(const PackEntry* __restrict__ table) {
     const int kc = (int)t;
     const int o = cg * 8 + o8 - e.o0;
     const int c = kc * e.CK + ksl * 8 + c8;
+    if (e.mode == 1) {
+      // data-gradient operand: the GEMM's N index o runs over the filter's INPUT channels, its K index c over
+      // the filter's OUTPUT channels, taps flipped: image[c][o][tap] = w[c][o][8 - tap], w of shape (Cin, CinTotal, 3, 3)
+      if (o >= 0 && o < e.O) e.out[i] = __float2bfloat16_rn(e.w[((long)c * e.CinTotal + e.c0 + o) * 9 + (8 - tap)]);
+      continue;
+    }
     if (o >= 0 && o < e.O) e.out[i] = __float2bfloat16_rn(e.w[((long)o * e.CinTotal + e.c0 + c) * 9 + tap]);
   }
 }

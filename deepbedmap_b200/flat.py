@@ -1,0 +1,347 @@
+"""Host side of the tensor-core TRAINING trunk (csrc/umma_flat.cu): buffers in the flat-padded slab
+layout and the launch / unit tables of the forward chain, the data-gradient chain and the batched
+weight-gradient of the generator trunk (pre-residual conv, 3*nb residual dense blocks, post-residual
+conv: srgan_train.py:292-358, 393-404, 467-486, 541-551, and their autograd in g_loss.backward(), :1256).
+
+Arithmetic: bf16 operands (activations, gradients wrt activations, filters), fp32 TMEM accumulation,
+fp32 residual stream and fp32 accumulation of the dense-block gradients; fp32 master weights/gradients.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import ops
+
+# mirrors of the structs in csrc/umma_flat.cu
+EPI_DTYPE = np.dtype([("bias", "<u8"), ("add1", "<u8"), ("add2", "<u8"), ("mask", "<u8"), ("out_f32", "<u8"),
+                      ("out_bf16", "<u8"), ("s1", "<f4"), ("beta", "<f4"), ("beta2", "<f4"), ("out_scale", "<f4"),
+                      ("act", "<i4"), ("pad", "<i4")])
+assert EPI_DTYPE.itemsize == 72
+LAUNCH_DTYPE = np.dtype([("in", "<u8"), ("wpacked", "<u8"), ("cin", "<i4"), ("nout", "<i4"), ("blk", EPI_DTYPE, (6,))])
+assert LAUNCH_DTYPE.itemsize == 456
+WGRAD_UNIT_DTYPE = np.dtype([("act", "<u8"), ("gout", "<u8"), ("partial", "<u8"), ("blk0", "<i4"), ("nblk", "<i4"),
+                             ("nslab", "<i4"), ("pad", "<i4", (3,))])
+assert WGRAD_UNIT_DTYPE.itemsize == 48
+WGRAD_REDUCE_DTYPE = np.dtype([("partial", "<u8"), ("dw", "<u8"), ("split_stride", "<i8"), ("nsplit", "<i4"),
+                               ("cin_total", "<i4"), ("c0", "<i4"), ("o0", "<i4"), ("nch", "<i4"), ("pad", "<i4")])
+assert WGRAD_REDUCE_DTYPE.itemsize == 48
+BIAS_GRAD_DTYPE = np.dtype([("gout", "<u8"), ("db", "<u8")])
+PARTIAL_FLOATS = 9 * 32 * 128
+
+
+def geometry(n: int, h: int, w: int) -> dict:
+    """{P, tiles, G0, Pg, R} of the flat-padded layout for n images of h x w pixels (from the library,
+    so host tables and kernels cannot disagree)."""
+    out = (ctypes.c_int * 5)()
+    ops.call("dbm_flat_geometry", n, h, w, ctypes.cast(out, ctypes.c_void_p))
+    return dict(P=out[0], tiles=out[1], G0=out[2], Pg=out[3], R=out[4])
+
+
+def geometry_host(n: int, h: int, w: int) -> dict:
+    """The same formula in Python (checked against the library by tests/test_cabi.py)."""
+    wp = w + 2
+    P = n * (h + 2) * wp
+    tiles = (P + 127) // 128
+    halo = wp + 1
+    g0 = (halo + 7) & ~7
+    return dict(P=P, tiles=tiles, G0=g0, Pg=g0 + tiles * 128 + g0, R=128 + 2 * halo)
+
+
+def split_blocks(tiles: int, nsplit: int):
+    """[(blk0, nblk)] covering range(tiles) in nsplit near-equal contiguous ranges (empty ranges dropped)."""
+    nsplit = max(1, min(nsplit, tiles))
+    base, rem = divmod(tiles, nsplit)
+    out, b = [], 0
+    for s in range(nsplit):
+        k = base + (1 if s < rem else 0)
+        out.append((b, k))
+        b += k
+    return out
+
+
+def chunk_channels(cin: int, chunk: int = 128):
+    """[(c0, nch)] input-channel chunks of a weight-gradient GEMM (M = 128 channels per UMMA tile)."""
+    return [(c0, min(chunk, cin - c0)) for c0 in range(0, cin, chunk)]
+
+
+def rdb_plan(nrdb: int, beta: float):
+    """Per residual dense block j (0-based, r = j % 3 + 1 within its RRDB): sigma_j = d(rdb_out)/d(x_{j+1})
+    scale (beta for the third block of an RRDB, whose output is scaled again by the RRDB: :402), and the scale
+    of the bf16 conv5 output gradient g5_j = beta * sigma_j * dX_{j+1} (:358)."""
+    plan = []
+    for j in range(nrdb):
+        r = j % 3 + 1
+        sigma = beta if r == 3 else 1.0
+        plan.append(dict(j=j, r=r, sigma=sigma, g5_scale=beta * sigma))
+    return plan
+
+
+class FlatTrunk:
+    """Buffers + tables of the tensor-core training trunk for one (batch, H, W)."""
+
+    NSPLIT = 3
+
+    def __init__(self, model, n: int, H: int, W: int):
+        if model.inter_channels != 32:
+            raise ValueError("the tensor-core training trunk implements inter_channels == 32")
+        self.model = model
+        self.n, self.H, self.W = n, H, W
+        self.geom = geometry(n, H, W)
+        Pg = self.geom["Pg"]
+        self.Pg = Pg
+        nrdb = 3 * model.num_residual_blocks
+        self.nrdb = nrdb
+        bf = torch.bfloat16
+        zb = lambda c: torch.zeros(c // 8, Pg, 8, dtype=bf, device="cuda")
+        zf = lambda c: torch.zeros(c // 4, Pg, 4, dtype=torch.float32, device="cuda")
+        self.s0 = zb(128)
+        self.cat = [zb(192) for _ in range(nrdb + 1)]       # cat[j][:64] = bf16 input of RDB j, slots a1..a4 follow
+        self.gcat = [zb(192) for _ in range(nrdb)]          # [g1 | g2 | g3 | g4 | g5 (64)] gradients wrt conv outputs
+        self.x0 = zf(64)
+        self.xring = [zf(64) for _ in range(4)]
+        self.a3f = zf(64)
+        self.gpost, self.gpre = zb(64), zb(64)
+        self.da3f = zf(64)
+        self.dX = [zf(64) for _ in range(4)]
+        self.dcat = zf(192)
+        self.da0f = zf(128)
+        self._pack_gen = -1
+        self._built_beta = None
+
+    # ---- pointer helpers (block = 32 channels starting at channel c) ----
+    def _pb(self, t, c=0):
+        return t.data_ptr() + 2 * c * self.Pg
+
+    def _pf(self, t, c=0):
+        return t.data_ptr() + 4 * c * self.Pg
+
+    def _x(self, j):
+        return self.x0 if j == 0 else self.xring[j % 4]
+
+    @staticmethod
+    def _epi(**kw):
+        e = np.zeros((), dtype=EPI_DTYPE)
+        e["s1"] = 1.0
+        e["beta"] = 1.0
+        e["beta2"] = 1.0
+        e["out_scale"] = 1.0
+        for k, v in kw.items():
+            e[k] = v
+        return e
+
+    def _launch(self, inp_ptr, wq, cin, nout, blocks):
+        L = np.zeros((), dtype=LAUNCH_DTYPE)
+        L["in"] = inp_ptr
+        L["wpacked"] = wq.data_ptr()
+        L["cin"] = cin
+        L["nout"] = nout
+        assert len(blocks) == nout // 32
+        for b, e in enumerate(blocks):
+            L["blk"][b] = e
+        return L
+
+    def build(self, pk):
+        """(Re)build every table against the model's packed-operand buffers ``pk`` (model._pack())."""
+        m = self.model
+        beta = m.residual_scaling
+        if self._pack_gen == m._pack_gen and self._built_beta == beta:
+            return
+        P, G = m.p, m.g
+        nrdb = self.nrdb
+        pb, pf, epi = self._pb, self._pf, self._epi
+        plan = rdb_plan(nrdb, beta)
+        fwd, bwd = [], []
+        convs = []  # (key, act tensor, cin, g tensor, g channel0, cout) for the weight / bias gradients
+
+        # ---------------- forward chain ----------------
+        wq, bq = pk["pre_residual_conv_layer@trunk"]
+        fwd.append(self._launch(pb(self.s0), wq, 128, 64, [
+            epi(bias=bq.data_ptr() + 128 * b, act=1, out_f32=pf(self.x0, 32 * b), out_bf16=pb(self.cat[0], 32 * b))
+            for b in range(2)]))
+        for d in plan:
+            j, r = d["j"], d["r"]
+            pre = m._rdb_prefix(j // 3, r)
+            cat = self.cat[j]
+            for k in (1, 2, 3, 4):
+                cin = 64 + 32 * (k - 1)
+                wq, bq = pk[f"{pre}/conv_layer{k}@trunk"]
+                fwd.append(self._launch(pb(cat), wq, cin, 32, [epi(bias=bq.data_ptr(), act=1, out_bf16=pb(cat, cin))]))
+            wq, bq = pk[f"{pre}/conv_layer5@trunk"]
+            blocks = []
+            for b in range(2):
+                kw = dict(bias=bq.data_ptr() + 128 * b, add1=pf(self._x(j), 32 * b), s1=1.0, beta=beta,
+                          out_f32=pf(self._x(j + 1), 32 * b), out_bf16=pb(self.cat[j + 1], 32 * b))
+                if r == 3:
+                    kw.update(add2=pf(self._x(j - 2), 32 * b), beta2=beta)
+                blocks.append(epi(**kw))
+            fwd.append(self._launch(pb(cat), wq, 192, 64, blocks))
+        wq, bq = pk["post_residual_conv_layer@trunk"]
+        fwd.append(self._launch(pb(self.cat[nrdb]), wq, 64, 64, [
+            epi(bias=bq.data_ptr() + 128 * b, add1=pf(self.x0, 32 * b), s1=1.0, beta=1.0, out_f32=pf(self.a3f, 32 * b))
+            for b in range(2)]))
+
+        # ---------------- data-gradient chain ----------------
+        dX = lambda j: self.dX[j % 4]
+        wq = pk["post_residual_conv_layer@dgrad"]
+        bwd.append(self._launch(pb(self.gpost), wq, 64, 64, [
+            epi(out_f32=pf(dX(nrdb), 32 * b), out_bf16=pb(self.gcat[nrdb - 1], 128 + 32 * b),
+                out_scale=plan[nrdb - 1]["g5_scale"]) for b in range(2)]))
+        convs.append(("post_residual_conv_layer", self.cat[nrdb], 64, self.gpost, 0, 64))
+        for d in reversed(plan):
+            j, r, sigma = d["j"], d["r"], d["sigma"]
+            pre = m._rdb_prefix(j // 3, r)
+            cat, gcat = self.cat[j], self.gcat[j]
+            # conv5: g5 (64) -> d[a0..a4] (192); + skip sigma * dX_{j+1} on a0; slot a4 finalised -> g4
+            blocks = []
+            for b in range(6):
+                kw = {}
+                if b < 2:
+                    kw.update(add1=pf(dX(j + 1), 32 * b), s1=sigma, beta=1.0)
+                    if j == 0:  # the skip a3 = a1 + post_res(...) (:551) reaches a1 = input of RDB 0
+                        kw.update(add2=pf(self.da3f, 32 * b), beta2=1.0)
+                if b < 5:
+                    kw.update(out_f32=pf(self.dcat, 32 * b))
+                else:
+                    kw.update(mask=pb(cat, 32 * b), out_bf16=pb(gcat, 96))
+                blocks.append(epi(**kw))
+            bwd.append(self._launch(pb(gcat, 128), pk[f"{pre}/conv_layer5@dgrad"], 64, 192, blocks))
+            convs.append((f"{pre}/conv_layer5", cat, 192, gcat, 128, 64))
+            for k in (4, 3, 2):
+                nout = 64 + 32 * (k - 1)
+                blocks = []
+                for b in range(nout // 32):
+                    kw = dict(add1=pf(self.dcat, 32 * b), s1=1.0, beta=1.0)
+                    if b < nout // 32 - 1:
+                        kw.update(out_f32=pf(self.dcat, 32 * b))
+                    else:  # slot a_{k-1} is final: apply lrelu' and emit the bf16 operand of the next dgrad
+                        kw.update(mask=pb(cat, 32 * b), out_bf16=pb(gcat, 32 * (k - 2)))
+                    blocks.append(epi(**kw))
+                bwd.append(self._launch(pb(gcat, 32 * (k - 1)), pk[f"{pre}/conv_layer{k}@dgrad"], 32, nout, blocks))
+                convs.append((f"{pre}/conv_layer{k}", cat, nout, gcat, 32 * (k - 1), 32))
+            blocks = []
+            for b in range(2):
+                kw = dict(add1=pf(self.dcat, 32 * b), s1=1.0, beta=1.0)
+                if r == 1:  # RRDB skip: d x_{3i} += d x_{3i+3} (:402)
+                    kw.update(add2=pf(dX(j + 3), 32 * b), beta2=1.0)
+                if j > 0:
+                    kw.update(out_f32=pf(dX(j), 32 * b), out_bf16=pb(self.gcat[j - 1], 128 + 32 * b),
+                              out_scale=plan[j - 1]["g5_scale"])
+                else:   # a1 = lrelu(pre_res(a0)) (:541-544)
+                    kw.update(mask=pb(self.cat[0], 32 * b), out_bf16=pb(self.gpre, 32 * b))
+                blocks.append(epi(**kw))
+            bwd.append(self._launch(pb(gcat, 0), pk[f"{pre}/conv_layer1@dgrad"], 32, 64, blocks))
+            convs.append((f"{pre}/conv_layer1", cat, 64, gcat, 0, 32))
+        bwd.append(self._launch(pb(self.gpre), pk["pre_residual_conv_layer@dgrad"], 64, 128,
+                                [epi(out_f32=pf(self.da0f, 32 * b)) for b in range(4)]))
+        convs.append(("pre_residual_conv_layer", self.s0, 128, self.gpre, 0, 64))
+
+        # ---------------- weight / bias gradient tables ----------------
+        splits = split_blocks(self.geom["tiles"], self.NSPLIT)
+        units, reduces, biases = [], [], []
+        for key, act, cin, gt, g0, cout in convs:
+            for half in range(cout // 32):
+                biases.append((pb(gt, g0 + 32 * half), G[f"{key}/b"].data_ptr() + 128 * half))
+                for c0, nch in chunk_channels(cin):
+                    first = len(units)
+                    for blk0, nblk in splits:
+                        units.append((pb(act, c0), pb(gt, g0 + 32 * half), len(units), blk0, nblk, nch // 8, (0, 0, 0)))
+                    reduces.append((first, G[f"{key}/W"].data_ptr(), PARTIAL_FLOATS, len(splits), cin, c0, 32 * half,
+                                    nch, 0))
+        need = len(units) * PARTIAL_FLOATS
+        if getattr(self, "partial", None) is None or self.partial.numel() < need:
+            self.partial = torch.empty(need, dtype=torch.float32, device="cuda")
+        base = self.partial.data_ptr()
+        u = np.array(units, dtype=WGRAD_UNIT_DTYPE)
+        u["partial"] = base + u["partial"] * np.uint64(PARTIAL_FLOATS * 4)
+        rd = np.array(reduces, dtype=WGRAD_REDUCE_DTYPE)
+        rd["partial"] = base + rd["partial"] * np.uint64(PARTIAL_FLOATS * 4)
+        bg = np.array(biases, dtype=BIAS_GRAD_DTYPE)
+        dev = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).cuda()
+        self.units_dev, self.n_units = dev(u), len(u)
+        self.reduce_dev, self.n_reduce = dev(rd), len(rd)
+        self.bias_dev, self.n_bias = dev(bg), len(bg)
+        self.fwd = np.ascontiguousarray(np.stack(fwd))
+        self.bwd = np.ascontiguousarray(np.stack(bwd))
+        self.flops_fwd = float(sum(2.0 * 9 * int(L["cin"]) * int(L["nout"]) for L in fwd)) * self.n * self.H * self.W
+        self._pack_gen = m._pack_gen
+        self._built_beta = beta
+
+    # ---- execution ----
+    def forward(self, a0_nchw: torch.Tensor) -> torch.Tensor:
+        """a0 = stem output (n,128,H,W) fp32 -> a3 = a1 + post_res(trunk(a1)) (n,64,H,W) fp32 (:541-551);
+        keeps the bf16 activations of every dense block for backward()."""
+        n, H, W = self.n, self.H, self.W
+        st = ops.stream()
+        ops.call("dbm_flat_from_nchw", a0_nchw.data_ptr(), 128, self.s0.data_ptr(), None, 1.0, n, H, W, st)
+        ops.call("dbm_flat_conv3x3_seq", self.fwd.ctypes.data, len(self.fwd), n, H, W, st)
+        a3 = ops.empty(n, 64, H, W)
+        ops.call("dbm_flat_to_nchw", self.a3f.data_ptr(), None, a3.data_ptr(), 64, n, H, W, st)
+        return a3
+
+    def backward(self, da3_nchw: torch.Tensor) -> torch.Tensor:
+        """da3 (n,64,H,W) -> accumulates the trunk's weight/bias gradients into the model's flat_grad and
+        returns d(loss)/d(a0) (n,128,H,W)."""
+        n, H, W = self.n, self.H, self.W
+        st = ops.stream()
+        ops.call("dbm_flat_from_nchw", da3_nchw.data_ptr(), 64, self.gpost.data_ptr(), self.da3f.data_ptr(), 1.0, n, H, W,
+                 st)
+        ops.call("dbm_flat_conv3x3_seq", self.bwd.ctypes.data, len(self.bwd), n, H, W, st)
+        ops.call("dbm_flat_wgrad", self.units_dev.data_ptr(), self.n_units, n, H, W, st)
+        ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, st)
+        ops.call("dbm_flat_bias_grad", self.bias_dev.data_ptr(), self.n_bias, n, H, W, st)
+        da0 = ops.empty(n, 128, H, W)
+        ops.call("dbm_flat_to_nchw", self.da0f.data_ptr(), None, da0.data_ptr(), 128, n, H, W, st)
+        return da0
+
+
+# ---- single-layer helpers (tests, diagnostics) -----------------------------------------------------
+def pack_dgrad(w: torch.Tensor) -> torch.Tensor:
+    """Data-gradient operand image of an fp32 (O, Cin, 3, 3) filter: GEMM N = Cin, K = O, taps flipped."""
+    from .model import PACK_ENTRY_DTYPE
+    o, cin = int(w.shape[0]), int(w.shape[1])
+    out = ops.empty(9 * cin * o, dtype=torch.bfloat16)
+    table = np.array([(w.data_ptr(), out.data_ptr(), cin, 0, o, cin, 0, cin, 16, 1)], dtype=PACK_ENTRY_DTYPE)
+    tdev = torch.from_numpy(table.view(np.uint8).copy()).cuda()
+    ops.call("dbm_pack_conv3x3_table", tdev.data_ptr(), 1, 9 * cin * o, ops.stream())
+    torch.cuda.current_stream().synchronize()   # tdev must outlive the launch
+    return out
+
+
+def alloc_bf16(c: int, geom: dict) -> torch.Tensor:
+    return torch.zeros(c // 8, geom["Pg"], 8, dtype=torch.bfloat16, device="cuda")
+
+
+def alloc_f32(c: int, geom: dict) -> torch.Tensor:
+    return torch.zeros(c // 4, geom["Pg"], 4, dtype=torch.float32, device="cuda")
+
+
+def from_nchw(src: torch.Tensor, dst8=None, dst4=None, scale: float = 1.0):
+    n, c, h, w = src.shape
+    ops.call("dbm_flat_from_nchw", src.data_ptr(), c, dst8.data_ptr() if dst8 is not None else None,
+             dst4.data_ptr() if dst4 is not None else None, float(scale), n, h, w, ops.stream())
+
+
+def to_nchw(src: torch.Tensor, c: int, n: int, h: int, w: int, c0: int = 0) -> torch.Tensor:
+    """Channels [c0, c0 + c) of a flat slab4 (fp32) or slab8 (bf16) buffer -> (n, c, h, w) fp32."""
+    dst = ops.empty(n, c, h, w)
+    pg = src.shape[1]
+    if src.dtype == torch.float32:
+        ops.call("dbm_flat_to_nchw", src.data_ptr() + 4 * c0 * pg, None, dst.data_ptr(), c, n, h, w, ops.stream())
+    else:
+        ops.call("dbm_flat_to_nchw", None, src.data_ptr() + 2 * c0 * pg, dst.data_ptr(), c, n, h, w, ops.stream())
+    return dst
+
+
+def conv3x3(inp: torch.Tensor, cin: int, wpacked: torch.Tensor, nout: int, blocks, n: int, h: int, w: int, c0: int = 0):
+    """One flat 3x3 conv launch; ``blocks`` = list of dicts of FlatEpiBlock fields (device addresses)."""
+    L = np.zeros(1, dtype=LAUNCH_DTYPE)
+    L[0]["in"] = inp.data_ptr() + 2 * c0 * inp.shape[1]
+    L[0]["wpacked"] = wpacked.data_ptr()
+    L[0]["cin"] = cin
+    L[0]["nout"] = nout
+    for b, kw in enumerate(blocks):
+        L[0]["blk"][b] = FlatTrunk._epi(**kw)
+    ops.call("dbm_flat_conv3x3_seq", L.ctypes.data, 1, n, h, w, ops.stream())

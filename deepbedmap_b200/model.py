@@ -28,7 +28,7 @@ TRUNK_LAYER_DTYPE = np.dtype([("wpacked", "<u8"), ("bias", "<u8"), ("out_bf16", 
 assert TRUNK_LAYER_DTYPE.itemsize == 128
 # mirror of struct PackEntry in csrc/umma_conv3x3.cu (48 bytes)
 PACK_ENTRY_DTYPE = np.dtype([("w", "<u8"), ("out", "<u8"), ("O", "<i4"), ("o0", "<i4"), ("Cin", "<i4"),
-                             ("CinTotal", "<i4"), ("c0", "<i4"), ("COUTP", "<i4"), ("CK", "<i4"), ("pad", "<i4")])
+                             ("CinTotal", "<i4"), ("c0", "<i4"), ("COUTP", "<i4"), ("CK", "<i4"), ("mode", "<i4")])
 assert PACK_ENTRY_DTYPE.itemsize == 48
 
 
@@ -150,9 +150,17 @@ class GeneratorModel(_Link):
 
     def __init__(self, inblock_class=None, resblock_class=None, num_residual_blocks: int = 12,
                  residual_scaling: float = 0.1, out_channels: int = 1, *, inter_channels: int = 32,
-                 precision: str = "bf16", seed: int = 0, init_scale: float = 0.1):
+                 precision: str = "bf16", train_precision: Optional[str] = None, seed: int = 0,
+                 init_scale: float = 0.1):
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
+        if train_precision is None:
+            # the tensor-core training trunk (flat.py) covers the reference's inter_channels = 32
+            train_precision = "bf16" if (precision == "bf16" and inter_channels == 32) else "fp32"
+        if train_precision not in ("bf16", "fp32"):
+            raise ValueError("train_precision must be 'bf16' or 'fp32'")
+        if train_precision == "bf16" and inter_channels != 32:
+            raise ValueError("train_precision='bf16' implements inter_channels == 32 only")
         if inter_channels not in (32, 64):
             raise ValueError("inter_channels must be 32 or 64 (reference search space, srgan_train.py:283-284)")
         self.num_residual_blocks = int(num_residual_blocks)
@@ -160,6 +168,8 @@ class GeneratorModel(_Link):
         self.out_channels = int(out_channels)
         self.inter_channels = int(inter_channels)
         self.precision = precision
+        self.train_precision = train_precision
+        self._flat = {}
         shapes = layout.generator_shapes(self.num_residual_blocks, self.inter_channels, self.out_channels)
         super().__init__(shapes, layout.init_values(shapes, seed, init_scale))
         self._packed_version = -1
@@ -196,8 +206,10 @@ class GeneratorModel(_Link):
         return Variable(y)
 
     def forward_train(self, x, w1, w2, w3) -> Variable:
-        """fp32 forward that keeps the activations needed by ``backward`` (the reference's
-        graph-building forward, srgan_train.py:1222-1227)."""
+        """Forward that keeps the activations needed by ``backward`` (the reference's graph-building
+        forward, srgan_train.py:1222-1227). Stem, upsample and deformable layers run in fp32; the trunk
+        (98 % of the trunk+stem FLOPs) runs on the tensor cores when ``train_precision == "bf16"``
+        (flat.py / csrc/umma_flat.cu) and in fp32 otherwise."""
         x, w1, w2, w3 = (as_device(a) for a in (x, w1, w2, w3))
         self._check_shapes(x, w1, w2, w3)
         return Variable(self._forward_fp32(x, w1, w2, w3, save=True))
@@ -235,6 +247,10 @@ class GeneratorModel(_Link):
         a0 = ops.empty(n, 128, H, W)
         self._stem_fp32(x, w1, w2, w3, a0)
         nrdb = 3 * self.num_residual_blocks
+        if save and self.train_precision == "bf16":
+            ft = self._flat_trunk(n, H, W)
+            a3 = ft.forward(a0)
+            return self._head_fp32(a3, dict(x=x, w1=w1, w2=w2, w3=w3, a0=a0, flat=ft, H=H, W=W, n=n), save)
         cats = [ops.empty(n, cc, H, W) for _ in range(nrdb + 1)]  # cats[j][:, :64] = input of RDB j
         ops.conv2d_fwd(a0, 0, 128, P["pre_residual_conv_layer/W"], P["pre_residual_conv_layer/b"], cats[0], 0, 3, 1, 1,
                        act=True)
@@ -262,6 +278,21 @@ class GeneratorModel(_Link):
         ops.conv2d_fwd(last, 0, 64, P["post_residual_conv_layer/W"], P["post_residual_conv_layer/b"], t, 0, 3, 1, 1)
         a3 = ops.empty(n, 64, H, W)
         ops.axpby(t, 0, cats[0], 0, a3, 0, 64, 1.0, 1.0)  # a3 = a1 + conv (srgan_train.py:551)
+        return self._head_fp32(a3, dict(x=x, w1=w1, w2=w2, w3=w3, a0=a0, cats=cats, H=H, W=W, n=n), save)
+
+    def _flat_trunk(self, n, H, W):
+        from . import flat
+        pk = self._pack()
+        ft = self._flat.get((n, H, W))
+        if ft is None:
+            ft = self._flat[(n, H, W)] = flat.FlatTrunk(self, n, H, W)
+        ft.build(pk)
+        return ft
+
+    def _head_fp32(self, a3, ctx, save: bool):
+        """Upsample convs + the two deformable layers (srgan_train.py:553-574), fp32."""
+        P = self.p
+        n, H, W = ctx["n"], ctx["H"], ctx["W"]
         u1 = ops.upsample2_fwd(a3)
         c1 = ops.empty(n, 64, 2 * H, 2 * W)
         ops.conv2d_fwd(u1, 0, 64, P["post_upsample_conv_layer_1/W"], P["post_upsample_conv_layer_1/b"], c1, 0, 3, 1, 1,
@@ -281,8 +312,8 @@ class GeneratorModel(_Link):
         y, cols2 = ops.deform_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"],
                                        P["final_conv_layer2/deform_conv/b"], act=False)
         if save:
-            self._ctx = dict(x=x, w1=w1, w2=w2, w3=w3, a0=a0, cats=cats, u1=u1, c1=c1, u2=u2, c2=c2, off1=off1, d1=d1,
-                             cols1=cols1, off2=off2, cols2=cols2, H=H, W=W, n=n)
+            ctx.update(u1=u1, c1=c1, u2=u2, c2=c2, off1=off1, d1=d1, cols1=cols1, off2=off2, cols2=cols2)
+            self._ctx = ctx
         return y
 
     def backward(self, dy: torch.Tensor, on_ready=None):
@@ -332,6 +363,14 @@ class GeneratorModel(_Link):
         ops.conv2d_bwd_data(dc1, 0, P["post_upsample_conv_layer_1/W"], du1, 0, 64, 3, 1, 1)
         da3 = ops.upsample2_bwd(du1)  # = d a1 (skip) = d (post-res conv output)
         del du1, dc1
+        if "flat" in c:
+            # tensor-core trunk: data-gradient chain, batched weight/bias gradients (flat.py)
+            da0 = c["flat"].backward(da3)
+            ready("post_residual_conv_layer", "post_upsample_conv_layer", "final_conv_layer")
+            for i in reversed(range(self.num_residual_blocks)):
+                ready(f"residual_network/{i}/")
+            self._stem_bwd(c, da0, ready)
+            return
         # ---- post-residual conv ----
         cats = c["cats"]
         nrdb = 3 * self.num_residual_blocks
@@ -377,6 +416,10 @@ class GeneratorModel(_Link):
                               db=G["pre_residual_conv_layer/b"])
         da0 = ops.empty(n, 128, H, W)
         ops.conv2d_bwd_data(da1, 0, P["pre_residual_conv_layer/W"], da0, 0, 128, 3, 1, 1)
+        self._stem_bwd(c, da0, ready)
+
+    def _stem_bwd(self, c, da0, ready):
+        G = self.g
         # ---- stem weights ----
         ops.conv2d_bwd_weight(c["x"], 0, 1, da0, 0, G["input_block/conv_on_X/W"], 3, 1, 0, db=G["input_block/conv_on_X/b"])
         ops.conv2d_bwd_weight(c["w1"], 0, 1, da0, 32, G["input_block/conv_on_W1/W"], 30, 10, 0,
@@ -404,8 +447,8 @@ class GeneratorModel(_Link):
             def image(cin, cout_padded):
                 return ops.zeros(9 * cin * cout_padded, dtype=torch.bfloat16)
 
-            def entry(w, out, o, o0, cin, cin_total, c0, coutp, ck):
-                entries.append((w.data_ptr(), out.data_ptr(), o, o0, cin, cin_total, c0, coutp, ck, 0))
+            def entry(w, out, o, o0, cin, cin_total, c0, coutp, ck, mode=0):
+                entries.append((w.data_ptr(), out.data_ptr(), o, o0, cin, cin_total, c0, coutp, ck, mode))
 
             def add(key, cout_padded, trunk=False, ck=32):
                 w, b = P[f"{key}/W"], P[f"{key}/b"]
@@ -423,6 +466,11 @@ class GeneratorModel(_Link):
                     img16 = image(cin, cout_padded)
                     entry(w, img16, o, 0, cin, cin, 0, cout_padded, 16)
                     pk[key + "@trunk"] = (img16, bp)
+                    if self.train_precision == "bf16":
+                        # data-gradient operand (transposed + flipped filter): GEMM N = cin, K = cout
+                        imgd = image(cin, o)
+                        entry(w, imgd, cin, 0, o, cin, 0, cin, 16, mode=1)
+                        pk[key + "@dgrad"] = imgd
 
             add("pre_residual_conv_layer", 64, trunk=True)
             for i in range(self.num_residual_blocks):

@@ -103,7 +103,7 @@ int dbm_pack_conv3x3_weights(const float* w_oihw, void* packed_bf16, int cout, i
 int dbm_pack_conv3x3_weights_slice(const float* w_oihw, int w_cin_total, int w_c0, void* packed_bf16, int cout,
                                    int cout0, int cin, int cout_padded, int ck, cudaStream_t stream);
 /* The same for a whole model in ONE launch: table_dev = num_entries 48-byte records
- * {const float* w; bf16* out; int cout, cout0, cin, w_cin_total, w_c0, cout_padded, ck, pad}
+ * {const float* w; bf16* out; int cout, cout0, cin, w_cin_total, w_c0, cout_padded, ck, mode}
  * (struct PackEntry, csrc/umma_conv3x3.cu); max_elements = the largest 9*cin*cout_padded. */
 int dbm_pack_conv3x3_table(const void* table_dev, int num_entries, long max_elements, cudaStream_t stream);
 int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void* wpacked, const float* bias,
@@ -121,6 +121,40 @@ int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void*
 int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
                    int stem_cs_total, const void* cat_a_slab8, const void* cat_b_slab8, int cat_cs_total,
                    unsigned int* flags_dev, cudaStream_t stream);
+
+/* ---- tensor-core TRAINING trunk ("flat-padded" layout, csrc/umma_flat.cu) --------------------------
+ * Forward, data gradient and weight gradient of the trunk's L.Convolution2D(k3,s1,p1) links
+ * (srgan_train.py:292-358, 467-486) and of their autograd in g_loss.backward() (:1256) as tcgen05
+ * implicit GEMMs. Activations / gradients live in flat slabs: every image keeps its one-pixel zero
+ * border and the padded images are flattened, p = (img*(h+2) + y)*(w+2) + x;
+ *   bf16 slab8 [C/8][Pg][8], fp32 slab4 [C/4][Pg][4]; dbm_flat_geometry -> {P, tiles, G0, Pg, R}:
+ *   Pg = slab stride in positions, G0 = leading zero guard. Buffers must be zero-initialised once;
+ *   the kernels only ever write interior positions.
+ * dbm_flat_conv3x3_seq runs `count` launches described by 456-byte HOST records (struct FlatLaunch:
+ *   {const bf16* in; const bf16* wpacked; int cin, nout; FlatEpiBlock blk[6]}), each a 3x3 'same' conv
+ *   with N = nout in {32..192} output columns whose epilogue is given per 32 columns by a 72-byte
+ *   FlatEpiBlock {bias, add1, add2, mask, out_f32, out_bf16 (pointers to the block's first slab),
+ *   s1, beta, beta2, out_scale, act}:
+ *     v = acc + bias; v = s1*add1 + beta*v; v = add2 + beta2*v; act: v = lrelu(v);
+ *     mask: v *= (mask >= 0 ? 1 : 0.2); out_f32 = v; out_bf16 = bf16(out_scale*v).
+ *   Forward filters are packed by dbm_pack_conv3x3_table with ck = 16; data-gradient filters with
+ *   PackEntry.mode = 1 (transposed + flipped).
+ * dbm_flat_wgrad: dW[o][c][tap] partial sums; units_dev = 48-byte records {const bf16* act; const bf16*
+ *   gout; float* partial[9][32][128]; int blk0, nblk, nslab; pad} (struct WgradUnit);
+ * dbm_flat_wgrad_reduce: 48-byte records {const float* partial; float* dw; long split_stride; int nsplit,
+ *   cin_total, c0, o0, nch; pad}: dw[(o0+o)*cin_total + c0 + c][tap] += sum_s partial[s][tap][o][c];
+ * dbm_flat_bias_grad: 16-byte records {const bf16* gout; float* db}: db[0:32] += sum_p gout[.][p]. */
+int dbm_flat_debug_set(int key, int value);
+int dbm_flat_geometry(int n, int h, int w, int* out5_host);
+int dbm_flat_conv3x3_seq(const void* launches_host, int count, int n, int h, int w, cudaStream_t stream);
+int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h, int w, cudaStream_t stream);
+int dbm_flat_wgrad_reduce(const void* entries_dev, int count, cudaStream_t stream);
+int dbm_flat_bias_grad(const void* entries_dev, int count, int n, int h, int w, cudaStream_t stream);
+/* NCHW fp32 (n, c, h, w) -> scale * x into a flat slab8 and/or slab4 (either may be NULL), and back */
+int dbm_flat_from_nchw(const float* src, int c, void* dst_slab8, float* dst_slab4, float scale, int n, int h, int w,
+                       cudaStream_t stream);
+int dbm_flat_to_nchw(const float* src_slab4, const void* src_slab8, float* dst, int c, int n, int h, int w,
+                     cudaStream_t stream);
 
 /* ---- fused generator input block for the tensor-core path (DeepbedmapInputBlock.forward,
  * srgan_train.py:256-266): four valid strided convs + F.concat, fp32 math, 128-channel bf16 slab8 out.

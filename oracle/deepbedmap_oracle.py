@@ -323,18 +323,58 @@ def generator_forward(p: Params, x, w1, w2, w3, num_residual_blocks=12,
                              p["final_conv_layer2/deform_conv/b"])
 
 
+def trunk_forward(p: Params, a0, num_residual_blocks=12, residual_scaling=0.1, emulate_bf16=False,
+                  return_a1=False):
+    """a3 = a1 + post_res(RRDB^nb(a1)), a1 = lrelu(pre_res(a0)): srgan_train.py:541-551.
+
+    ``emulate_bf16=True`` restates the SAME graph with the operand rounding of the product's tensor-core
+    TRAINING trunk (deepbedmap_b200/flat.py): every 3x3-conv input and filter rounded to bf16 (dense-block
+    features a1..a4 are stored as bf16), fp32 (here: wider) accumulation, bias and residual stream.
+    ``_q`` is a dtype round trip, so autograd treats the rounding as straight-through -- exactly what the
+    product's backward does -- and LeakyReLU derivatives are taken at the ROUNDED forward's values. This
+    matters: a forward perturbation of relative size e flips the sign of a fraction ~e of the
+    pre-activations, each flip changes that element's gradient by a factor 5, so gradients of a
+    bf16-operand forward (e ~ 3e-3) differ from the exact graph's by ~sqrt(e) * 0.8 ~ 4e-2 in relative L2
+    whatever the implementation; against this emulation only accumulation order and the bf16 rounding
+    of the gradient operands remain."""
+    q = _q if emulate_bf16 else (lambda t: t)
+    beta = residual_scaling
+
+    def conv(inp, name):
+        return F.conv2d(inp, q(p[f"{name}/W"]), p[f"{name}/b"], padding=1)
+
+    a1 = _lrelu(conv(q(a0), "pre_residual_conv_layer"))                      # :541-542
+    cur = a1
+    for i in range(num_residual_blocks):                                     # :546
+        rrdb_in = cur
+        for r in (1, 2, 3):
+            pre = f"residual_network/{i}/residual_dense_block{r}"
+            feats = [q(cur)]
+            for k in (1, 2, 3, 4):                                           # :339-352
+                feats.append(q(_lrelu(conv(torch.cat(feats, dim=1), f"{pre}/conv_layer{k}"))))
+            cur = conv(torch.cat(feats, dim=1), f"{pre}/conv_layer5") * beta + cur   # :354-358
+        cur = cur * beta + rrdb_in                                           # :402
+    a3 = a1 + conv(q(cur), "post_residual_conv_layer")                       # :550-551
+    return (a3, a1) if return_a1 else a3
+
+
 def _generator_forward_exact(p: Params, x, w1, w2, w3, num_residual_blocks=12,
-                             residual_scaling=0.1, return_intermediates=False):
-    """GeneratorModel.forward, srgan_train.py:525-576."""
+                             residual_scaling=0.1, return_intermediates=False, trunk_bf16=False):
+    """GeneratorModel.forward, srgan_train.py:525-576. ``trunk_bf16``: the trunk with the operand rounding
+    of the product's tensor-core training path (see trunk_forward), everything else exact."""
     inter = {}
     a0 = input_block(p, x, w1, w2, w3)                                      # :537
-    a1 = _lrelu(F.conv2d(a0, p["pre_residual_conv_layer/W"],
-                         p["pre_residual_conv_layer/b"], padding=1))        # :541-542
-    a2 = a1
-    for i in range(num_residual_blocks):                                     # :546
-        a2 = rrdb(p, f"residual_network/{i}", a2, residual_scaling)
-    a3 = a1 + F.conv2d(a2, p["post_residual_conv_layer/W"],
-                       p["post_residual_conv_layer/b"], padding=1)          # :550-551
+    if trunk_bf16:
+        a3, a1 = trunk_forward(p, a0, num_residual_blocks, residual_scaling, emulate_bf16=True, return_a1=True)
+        a2 = None
+    else:
+        a1 = _lrelu(F.conv2d(a0, p["pre_residual_conv_layer/W"],
+                             p["pre_residual_conv_layer/b"], padding=1))        # :541-542
+        a2 = a1
+        for i in range(num_residual_blocks):                                     # :546
+            a2 = rrdb(p, f"residual_network/{i}", a2, residual_scaling)
+        a3 = a1 + F.conv2d(a2, p["post_residual_conv_layer/W"],
+                           p["post_residual_conv_layer/b"], padding=1)          # :550-551
     a4_1 = _lrelu(F.conv2d(upsample_nearest2(a3), p["post_upsample_conv_layer_1/W"],
                            p["post_upsample_conv_layer_1/b"], padding=1))   # :556-560
     a4_2 = _lrelu(F.conv2d(upsample_nearest2(a4_1), p["post_upsample_conv_layer_2/W"],

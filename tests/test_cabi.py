@@ -76,3 +76,19 @@ def test_no_gpu_fails_loudly():
     from deepbedmap_b200 import GeneratorModel
     with pytest.raises(RuntimeError):
         GeneratorModel()
+
+
+def test_flat_layout_geometry_host_formula_matches_library():
+    """The flat-padded layout of the tensor-core training trunk: host tables (flat.py) and kernels
+    (umma_flat.cu) must agree on {P, tiles, G0, Pg, R}; dbm_flat_geometry is host-only arithmetic."""
+    from deepbedmap_b200 import flat
+    for n, h, w in [(1, 1, 1), (128, 9, 9), (3, 9, 9), (5, 7, 12), (1, 20, 33), (2, 150, 170)]:
+        g = flat.geometry(n, h, w)
+        assert g == flat.geometry_host(n, h, w)
+        assert g["G0"] >= w + 3 and g["G0"] % 8 == 0 and g["Pg"] == 2 * g["G0"] + 128 * g["tiles"]
+        assert 128 * g["tiles"] >= g["P"] == n * (h + 2) * (w + 2)
+    assert flat.split_blocks(121, 3) == [(0, 41), (41, 40), (81, 40)]
+    assert sum(k for _, k in flat.split_blocks(7, 16)) == 7
+    assert flat.chunk_channels(160) == [(0, 128), (128, 32)]
+    # d(x_{j+1}) -> conv5 output gradient scale: beta, beta, beta^2 within every RRDB (srgan_train.py:358, 402)
+    assert [round(d["g5_scale"], 6) for d in flat.rdb_plan(6, 0.1)] == [0.1, 0.1, 0.01, 0.1, 0.1, 0.01]
