@@ -40,12 +40,14 @@ SIGNATURES = {
     "dbm_trunk_umma": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P],
     "dbm_flat_debug_set": [_I, _I],
     "dbm_flat_geometry": [_I, _I, _I, _P],
-    "dbm_flat_conv3x3_seq": [_P, _I, _I, _I, _I, _P],
+    "dbm_flat_conv3x3_seq": [_P, _I, _I, _I, _I, _I, _I, _P],
     "dbm_flat_wgrad": [_P, _I, _I, _I, _I, _P],
     "dbm_flat_wgrad_reduce": [_P, _I, _P],
     "dbm_flat_bias_grad": [_P, _I, _I, _I, _I, _P],
     "dbm_flat_from_nchw": [_P, _I, _P, _P, _F, _I, _I, _I, _P],
     "dbm_flat_to_nchw": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "dbm_flat_from_nchw_ex": [_P, _I, _I, _I, _I, _P, _P, _F, _I, _I, _I, _P],
+    "dbm_flat_to_nchw_ex": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dbm_transpose_f32": [_P, _P, _I, _I, _P],
     "dbm_stem_fwd_slab8": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dbm_deform_conv_umma": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P],

@@ -322,7 +322,7 @@ __global__ void pack_w3x3_slice_kernel(const float* __restrict__ w, __nv_bfloat1
 struct PackEntry {  // 48 bytes, mirrored by deepbedmap_b200/model.py (PACK_ENTRY_DTYPE)
   const float* w;
   __nv_bfloat16* out;
-  int O, o0, Cin, CinTotal, c0, COUTP, CK, mode;  // mode 1: transposed + flipped (dgrad operand)
+  int O, o0, Cin, CinTotal, c0, COUTP, CK, mode;  // mode: see pack_w3x3_table_kernel
 };
 static_assert(sizeof(PackEntry) == 48, "PackEntry layout is part of the C ABI");
 
@@ -337,15 +337,38 @@ __global__ void pack_w3x3_table_kernel(const PackEntry* __restrict__ table) {
     const int ksl = t % (e.CK / 8); t /= (e.CK / 8);
     const int tap = t % 9; t /= 9;
     const int kc = (int)t;
-    const int o = cg * 8 + o8 - e.o0;
-    const int c = kc * e.CK + ksl * 8 + c8;
-    if (e.mode == 1) {
-      // data-gradient operand: the GEMM's N index o runs over the filter's INPUT channels, its K index c over
-      // the filter's OUTPUT channels, taps flipped: image[c][o][tap] = w[c][o][8 - tap], w of shape (Cin, CinTotal, 3, 3)
-      if (o >= 0 && o < e.O) e.out[i] = __float2bfloat16_rn(e.w[((long)c * e.CinTotal + e.c0 + o) * 9 + (8 - tap)]);
+    const int on = cg * 8 + o8;                 // GEMM N index (row of the operand image)
+    const int c = kc * e.CK + ksl * 8 + c8;     // GEMM K index
+    if (e.mode == 0) {
+      // forward operand; rows [o0, o0 + O) <- w[o][c0 + c][tap], other rows untouched (stacked filters)
+      const int o = on - e.o0;
+      if (o >= 0 && o < e.O) e.out[i] = __float2bfloat16_rn(e.w[((long)o * e.CinTotal + e.c0 + c) * 9 + tap]);
       continue;
     }
-    if (o >= 0 && o < e.O) e.out[i] = __float2bfloat16_rn(e.w[((long)o * e.CinTotal + e.c0 + c) * 9 + tap]);
+    // modes 1-3 write the whole image. o0 = number of REAL filter output channels along the padded
+    // output-channel axis (0 = all): the remaining rows / K-lines are zero.
+    float v = 0.f;
+    if (e.mode == 1) {
+      // data-gradient operand of a 3x3 filter w (Oreal, CinTotal, 3, 3): N index = input channel c0 + on,
+      // K index c = output channel, taps flipped
+      const int kvalid = e.o0 > 0 ? e.o0 : e.Cin;
+      if (on < e.O && c < kvalid) v = e.w[((long)c * e.CinTotal + e.c0 + on) * 9 + (8 - tap)];
+    } else {
+      // 4x4 stride-2 pad-1 filter w4 (Oreal, C, 4, 4), C = CinTotal, embedded as a 3x3 stride-1 filter over the four
+      // space-to-depth phases (channel = phase * C + cc): tap (ty, tx) of phase (py, px) is
+      // w4[.., 2(ty-1)+py+1, 2(tx-1)+px+1] when that index exists, else 0.
+      // mode 2: forward operand (N = output channel on, K = phase channel c; the w pointer is pre-offset per
+      // output chunk); mode 3: data-gradient operand (N = phase channel c0 + on, K = output channel c, taps flipped).
+      const int oc = e.mode == 2 ? on : c;             // filter output channel
+      const int pc = e.mode == 2 ? c : e.c0 + on;      // phase channel
+      const int ovalid = e.o0 > 0 ? e.o0 : (e.mode == 2 ? e.O : e.Cin);
+      const int t3 = e.mode == 2 ? tap : 8 - tap;
+      const int ph = pc / e.CinTotal, cc = pc - ph * e.CinTotal;
+      const int ky = 2 * (t3 / 3 - 1) + (ph >> 1) + 1, kx = 2 * (t3 % 3 - 1) + (ph & 1) + 1;
+      if (on < e.O && oc < ovalid && ph < 4 && ky >= 0 && ky <= 3 && kx >= 0 && kx <= 3)
+        v = e.w[(((long)oc * e.CinTotal + cc) * 4 + ky) * 4 + kx];
+    }
+    e.out[i] = __float2bfloat16_rn(v);
   }
 }
 

@@ -25,6 +25,7 @@ static int g_flat_swap_wgrad = 0;  // debug: swap LBO/SBO of the MN-major descri
 
 struct FlatGeom {
   int n, H, W, Hp, Wp, img, P, tiles, G0, Pg, halo, R;
+  int oh, ow;  // output window written by the conv epilogue: rows 1..oh, columns 1..ow (<= H, W)
 };
 
 static FlatGeom flat_geom(int n, int h, int w) {
@@ -36,6 +37,7 @@ static FlatGeom flat_geom(int n, int h, int w) {
   g.G0 = (g.halo + 7) & ~7;
   g.Pg = g.G0 + g.tiles * 128 + g.G0;
   g.R = 128 + 2 * g.halo;
+  g.oh = h; g.ow = w;
   return g;
 }
 
@@ -51,13 +53,15 @@ struct FlatEpiBlock {  // 72 bytes; mirrored by deepbedmap_b200/flat.py (EPI_DTY
 };
 static_assert(sizeof(FlatEpiBlock) == 72, "FlatEpiBlock layout is part of the C ABI");
 
-struct FlatLaunch {  // 456 bytes
+struct FlatLaunch {  // 472 bytes
   const __nv_bfloat16* in;       // first input slab
-  const __nv_bfloat16* wpacked;  // [Cin/16][9][2][N/8][8][8]
-  int cin, nout;
+  const __nv_bfloat16* wpacked;  // [ny][Cin/16][9][2][N/8][8][8]
+  int cin, nout;                 // nout = N = output columns of ONE chunk
+  int ny, pad;                   // output-channel chunks (grid.y): chunk y uses filter image y and every epilogue
+  long w_chunk_stride;           // pointer advanced by y * N channels; w_chunk_stride = elements per filter image
   FlatEpiBlock blk[6];
 };
-static_assert(sizeof(FlatLaunch) == 456, "FlatLaunch layout is part of the C ABI");
+static_assert(sizeof(FlatLaunch) == 472, "FlatLaunch layout is part of the C ABI");
 
 constexpr int kFlatThreads = 192;  // warp0 bulk-copy producer, warp1 MMA issuer, warps2-5 epilogue
 constexpr int kFlatSmem = 208 * 1024;
@@ -108,7 +112,8 @@ flat_conv_kernel(const __grid_constant__ FlatLaunch L, const FlatGeom g) {
           uint8_t* st = stages + (size_t)s * stage_bytes;
           bulk_load(st, L.in + ((long)(2 * kc) * g.Pg + pos0) * 8, slab_bytes, &full[s]);
           bulk_load(st + slab_bytes, L.in + ((long)(2 * kc + 1) * g.Pg + pos0) * 8, slab_bytes, &full[s]);
-          bulk_load(st + a_bytes, L.wpacked + (size_t)kc * (b_bytes / 2), b_bytes, &full[s]);
+          bulk_load(st + a_bytes, L.wpacked + (size_t)blockIdx.y * L.w_chunk_stride + (size_t)kc * (b_bytes / 2),
+                    b_bytes, &full[s]);
           if (++s == nst) { s = 0; ph ^= 1; }
         }
       }
@@ -155,9 +160,11 @@ flat_conv_kernel(const __grid_constant__ FlatLaunch L, const FlatGeom g) {
       const int p = tile * 128 + m;
       const int r = p % g.img;
       const int y = r / g.Wp, x = r - y * g.Wp;
-      const bool interior = (p < g.P) && y >= 1 && y <= g.H && x >= 1 && x <= g.W;
+      const bool interior = (p < g.P) && y >= 1 && y <= g.oh && x >= 1 && x <= g.ow;
       const long pos = (long)g.G0 + p;
       const int nblk = N / 32;
+      const long ych = (long)blockIdx.y * N;        // first output channel of this chunk
+      const long yf = ych * g.Pg;                   // slab-pointer advance in elements (fp32: x1 floats, bf16: x1 halves)
 #pragma unroll 1
       for (int b = 0; b < nblk; ++b) {
         uint32_t acc[32];
@@ -170,13 +177,13 @@ flat_conv_kernel(const __grid_constant__ FlatLaunch L, const FlatGeom g) {
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
           if (e.bias) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(e.bias + i);
+            for (int i = 0; i < 32; ++i) v[i] += __ldg(e.bias + ych + i);
           }
           if (e.add1) {
             const float s1 = e.s1, be = e.beta;
 #pragma unroll
             for (int s4 = 0; s4 < 8; ++s4) {
-              const float4 rr = *reinterpret_cast<const float4*>(e.add1 + ((long)s4 * g.Pg + pos) * 4);
+              const float4 rr = *reinterpret_cast<const float4*>(e.add1 + yf + ((long)s4 * g.Pg + pos) * 4);
               v[4 * s4 + 0] = s1 * rr.x + be * v[4 * s4 + 0];
               v[4 * s4 + 1] = s1 * rr.y + be * v[4 * s4 + 1];
               v[4 * s4 + 2] = s1 * rr.z + be * v[4 * s4 + 2];
@@ -187,7 +194,7 @@ flat_conv_kernel(const __grid_constant__ FlatLaunch L, const FlatGeom g) {
             const float be = e.beta2;
 #pragma unroll
             for (int s4 = 0; s4 < 8; ++s4) {
-              const float4 rr = *reinterpret_cast<const float4*>(e.add2 + ((long)s4 * g.Pg + pos) * 4);
+              const float4 rr = *reinterpret_cast<const float4*>(e.add2 + yf + ((long)s4 * g.Pg + pos) * 4);
               v[4 * s4 + 0] = rr.x + be * v[4 * s4 + 0];
               v[4 * s4 + 1] = rr.y + be * v[4 * s4 + 1];
               v[4 * s4 + 2] = rr.z + be * v[4 * s4 + 2];
@@ -201,7 +208,7 @@ flat_conv_kernel(const __grid_constant__ FlatLaunch L, const FlatGeom g) {
           if (e.mask) {
 #pragma unroll
             for (int s8 = 0; s8 < 4; ++s8) {
-              const uint4 mm = *reinterpret_cast<const uint4*>(e.mask + ((long)s8 * g.Pg + pos) * 8);
+              const uint4 mm = *reinterpret_cast<const uint4*>(e.mask + yf + ((long)s8 * g.Pg + pos) * 8);
               const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -214,7 +221,7 @@ flat_conv_kernel(const __grid_constant__ FlatLaunch L, const FlatGeom g) {
           if (e.out_f32) {
 #pragma unroll
             for (int s4 = 0; s4 < 8; ++s4)
-              *reinterpret_cast<float4*>(e.out_f32 + ((long)s4 * g.Pg + pos) * 4) =
+              *reinterpret_cast<float4*>(e.out_f32 + yf + ((long)s4 * g.Pg + pos) * 4) =
                   make_float4(v[4 * s4], v[4 * s4 + 1], v[4 * s4 + 2], v[4 * s4 + 3]);
           }
           if (e.out_bf16) {
@@ -230,7 +237,7 @@ flat_conv_kernel(const __grid_constant__ FlatLaunch L, const FlatGeom g) {
               o.y = *reinterpret_cast<uint32_t*>(&t1);
               o.z = *reinterpret_cast<uint32_t*>(&t2);
               o.w = *reinterpret_cast<uint32_t*>(&t3);
-              *reinterpret_cast<uint4*>(e.out_bf16 + ((long)s8 * g.Pg + pos) * 8) = o;
+              *reinterpret_cast<uint4*>(e.out_bf16 + yf + ((long)s8 * g.Pg + pos) * 8) = o;
             }
           }
         }
@@ -381,21 +388,35 @@ struct WgradReduce {  // 48 bytes; dw[(o0 + o) * cin_total + c0 + c][tap] += sum
   const float* partial;
   float* dw;
   long split_stride;  // floats between consecutive splits
-  int nsplit, cin_total, c0, o0, nch, pad;
-};
+  int nsplit, cin_total, c0, o0, nch;
+  int mode;           // bits 0-7: 0 = 3x3 filter, 1 = 4x4 stride-2 filter embedded as 3x3 over the 4 space-to-depth
+};                    // phases (channel c0 + c = phase * cin_total + cc); bits 8-15: valid output rows (0 = 32)
 static_assert(sizeof(WgradReduce) == 48, "WgradReduce layout is part of the C ABI");
 
 __global__ void flat_wgrad_reduce_kernel(const WgradReduce* __restrict__ table) {
   const WgradReduce e = table[blockIdx.x];
   const int total = 9 * 32 * e.nch;
+  const int mode = e.mode & 0xFF;
+  const int ovalid = ((e.mode >> 8) & 0xFF) ? ((e.mode >> 8) & 0xFF) : 32;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int c = i % e.nch;
     const int t = i / e.nch;
     const int o = t & 31, tap = t >> 5;
+    if (o >= ovalid) continue;
+    long dst;
+    if (mode == 0) {
+      dst = ((long)(e.o0 + o) * e.cin_total + e.c0 + c) * 9 + tap;
+    } else {
+      const int cg = e.c0 + c;
+      const int ph = cg / e.cin_total, cc = cg - ph * e.cin_total;
+      const int ky = 2 * (tap / 3 - 1) + (ph >> 1) + 1, kx = 2 * (tap % 3 - 1) + (ph & 1) + 1;
+      if (ky < 0 || ky > 3 || kx < 0 || kx > 3) continue;   // structurally zero tap of the embedding
+      dst = ((long)(e.o0 + o) * e.cin_total + cc) * 16 + ky * 4 + kx;
+    }
     float s = 0.f;
     const float* src = e.partial + (tap * 32 + o) * 128 + c;
     for (int k = 0; k < e.nsplit; ++k) s += src[(long)k * e.split_stride];
-    e.dw[((long)(e.o0 + o) * e.cin_total + e.c0 + c) * 9 + tap] += s;
+    e.dw[dst] += s;
   }
 }
 
@@ -438,41 +459,56 @@ __global__ void flat_bias_grad_kernel(const BiasGradEntry* __restrict__ table, c
 }
 
 // ---- layout converters: NCHW fp32 <-> flat slabs (interior positions only) ---------------------
-__global__ void flat_from_nchw_kernel(const float* __restrict__ src, int C, __nv_bfloat16* dst8, float* dst4,
-                                      float scale, const FlatGeom g) {
-  const long total = (long)g.n * (C / 4) * g.H * g.W;
+// mode 0: the (sh, sw) source image sits in the top-left corner of the (H, W) interior;
+// mode 1: space-to-depth by 2: source pixel (y, x) of channel c -> channel ((y&1)*2 + (x&1)) * C + c at (y>>1, x>>1)
+//         (a 4x4 stride-2 pad-1 convolution becomes a 3x3 stride-1 pad-1 one over the 4C phase channels).
+__global__ void flat_from_nchw_kernel(const float* __restrict__ src, int C, int sh, int sw, int mode,
+                                      __nv_bfloat16* dst8, float* dst4, float scale, const FlatGeom g) {
+  const int c4n = (C + 3) / 4;
+  const long total = (long)g.n * c4n * sh * sw;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long t = i;
-    const int x = t % g.W; t /= g.W;
-    const int y = t % g.H; t /= g.H;
+    const int x = t % sw; t /= sw;
+    const int y = t % sh; t /= sh;
     const int n = t % g.n; t /= g.n;
     const int c4 = (int)t;
-    const long pos = (long)g.G0 + ((long)n * g.Hp + y + 1) * g.Wp + x + 1;
+    int gy = y, gx = x, ch = c4 * 4;
+    if (mode == 1) {
+      ch += (((y & 1) << 1) | (x & 1)) * C;
+      gy = y >> 1; gx = x >> 1;
+    }
+    const long pos = (long)g.G0 + ((long)n * g.Hp + gy + 1) * g.Wp + gx + 1;
     float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = scale * src[(((long)n * C + c4 * 4 + j) * g.H + y) * g.W + x];
-    if (dst4) *reinterpret_cast<float4*>(dst4 + ((long)c4 * g.Pg + pos) * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    for (int j = 0; j < 4; ++j)
+      v[j] = (c4 * 4 + j < C) ? scale * src[(((long)n * C + c4 * 4 + j) * sh + y) * sw + x] : 0.f;
+    if (dst4) *reinterpret_cast<float4*>(dst4 + ((long)(ch >> 2) * g.Pg + pos) * 4) = make_float4(v[0], v[1], v[2], v[3]);
     if (dst8) {
       __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]);
       __nv_bfloat162 t1 = __floats2bfloat162_rn(v[2], v[3]);
       uint2 o;
       o.x = *reinterpret_cast<uint32_t*>(&t0);
       o.y = *reinterpret_cast<uint32_t*>(&t1);
-      *reinterpret_cast<uint2*>(dst8 + ((long)(c4 >> 1) * g.Pg + pos) * 8 + (c4 & 1) * 4) = o;
+      *reinterpret_cast<uint2*>(dst8 + ((long)(ch >> 3) * g.Pg + pos) * 8 + (ch & 4)) = o;
     }
   }
 }
 
 __global__ void flat_to_nchw_kernel(const float* __restrict__ src4, const __nv_bfloat16* __restrict__ src8,
-                                    float* __restrict__ dst, int C, const FlatGeom g) {
-  const long total = (long)g.n * C * g.H * g.W;
+                                    float* __restrict__ dst, int C, int dh, int dw, int mode, const FlatGeom g) {
+  const long total = (long)g.n * C * dh * dw;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long t = i;
-    const int x = t % g.W; t /= g.W;
-    const int y = t % g.H; t /= g.H;
-    const int c = t % C; t /= C;
+    const int x = t % dw; t /= dw;
+    const int y = t % dh; t /= dh;
+    int c = t % C; t /= C;
     const int n = (int)t;
-    const long pos = (long)g.G0 + ((long)n * g.Hp + y + 1) * g.Wp + x + 1;
+    int gy = y, gx = x;
+    if (mode == 1) {
+      c += (((y & 1) << 1) | (x & 1)) * C;
+      gy = y >> 1; gx = x >> 1;
+    }
+    const long pos = (long)g.G0 + ((long)n * g.Hp + gy + 1) * g.Wp + gx + 1;
     dst[i] = src4 ? src4[((long)(c >> 2) * g.Pg + pos) * 4 + (c & 3)]
                   : __bfloat162float(src8[((long)(c >> 3) * g.Pg + pos) * 8 + (c & 7)]);
   }
@@ -512,22 +548,31 @@ static int check_flat_shape(const FlatGeom& g, const char* who) {
   return DBM_OK;
 }
 
-extern "C" int dbm_flat_conv3x3_seq(const void* launches_host, int count, int n, int h, int w, cudaStream_t stream) {
-  const FlatGeom g = flat_geom(n, h, w);
+extern "C" int dbm_flat_conv3x3_seq(const void* launches_host, int count, int n, int h, int w, int out_h, int out_w,
+                                    cudaStream_t stream) {
+  FlatGeom g = flat_geom(n, h, w);
   int rc = check_flat_shape(g, "flat_conv3x3");
   if (rc) return rc;
   rc = set_flat_attr();
   if (rc) return rc;
   DBM_REQUIRE(launches_host && count > 0, "flat_conv3x3: empty launch list");
+  DBM_REQUIRE(out_h >= 0 && out_h <= h && out_w >= 0 && out_w <= w, "flat_conv3x3: output window %dx%d exceeds %dx%d",
+              out_h, out_w, h, w);
+  if (out_h > 0) g.oh = out_h;
+  if (out_w > 0) g.ow = out_w;
   const FlatLaunch* L = (const FlatLaunch*)launches_host;
-  const int grid = g.tiles < num_sms() ? g.tiles : num_sms();
   for (int i = 0; i < count; ++i) {
     DBM_REQUIRE(L[i].cin % 16 == 0 && L[i].cin > 0, "flat_conv3x3[%d]: Cin=%d must be a multiple of 16", i, L[i].cin);
     DBM_REQUIRE(L[i].nout % 32 == 0 && L[i].nout >= 32 && L[i].nout <= 192,
                 "flat_conv3x3[%d]: N=%d must be a multiple of 32 in [32, 192]", i, L[i].nout);
     DBM_REQUIRE(L[i].in && L[i].wpacked && (((uintptr_t)L[i].in | (uintptr_t)L[i].wpacked) & 15) == 0,
                 "flat_conv3x3[%d]: null or unaligned operand", i);
-    flat_conv_kernel<<<grid, kFlatThreads, kFlatSmem, stream>>>(L[i], g);
+    const int ny = L[i].ny > 0 ? L[i].ny : 1;
+    DBM_REQUIRE(ny <= 64, "flat_conv3x3[%d]: %d output chunks", i, ny);
+    int gx = num_sms() / ny;
+    if (gx < 1) gx = 1;
+    if (gx > g.tiles) gx = g.tiles;
+    flat_conv_kernel<<<dim3(gx, ny), kFlatThreads, kFlatSmem, stream>>>(L[i], g);
   }
   return check_launch("flat_conv_kernel");
 }
@@ -558,25 +603,39 @@ extern "C" int dbm_flat_bias_grad(const void* entries_dev, int count, int n, int
   return check_launch("flat_bias_grad_kernel");
 }
 
-extern "C" int dbm_flat_from_nchw(const float* src, int c, void* dst_slab8, float* dst_slab4, float scale, int n, int h,
-                                  int w, cudaStream_t stream) {
-  DBM_REQUIRE(c % 8 == 0 && c > 0, "flat_from_nchw: C=%d must be a multiple of 8", c);
+extern "C" int dbm_flat_from_nchw_ex(const float* src, int c, int src_h, int src_w, int mode, void* dst_slab8,
+                                     float* dst_slab4, float scale, int n, int h, int w, cudaStream_t stream) {
+  DBM_REQUIRE(c > 0 && (mode == 0 || (mode == 1 && c % 8 == 0)), "flat_from_nchw: bad C=%d for mode %d", c, mode);
   DBM_REQUIRE(src && (dst_slab8 || dst_slab4), "flat_from_nchw: null pointer");
+  if (mode == 0) DBM_REQUIRE(src_h <= h && src_w <= w, "flat_from_nchw: %dx%d source exceeds the %dx%d interior", src_h, src_w, h, w);
+  else DBM_REQUIRE((src_h + 1) / 2 <= h && (src_w + 1) / 2 <= w, "flat_from_nchw: space-to-depth of %dx%d exceeds %dx%d", src_h, src_w, h, w);
   const FlatGeom g = flat_geom(n, h, w);
-  const long total = (long)n * (c / 4) * h * w;
+  const long total = (long)n * ((c + 3) / 4) * src_h * src_w;
   int grid = ceil_div(total, 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  flat_from_nchw_kernel<<<grid, 256, 0, stream>>>(src, c, (__nv_bfloat16*)dst_slab8, dst_slab4, scale, g);
+  flat_from_nchw_kernel<<<grid, 256, 0, stream>>>(src, c, src_h, src_w, mode, (__nv_bfloat16*)dst_slab8, dst_slab4, scale, g);
   return check_launch("flat_from_nchw_kernel");
+}
+
+extern "C" int dbm_flat_to_nchw_ex(const float* src_slab4, const void* src_slab8, float* dst, int c, int dst_h, int dst_w,
+                                   int mode, int n, int h, int w, cudaStream_t stream) {
+  DBM_REQUIRE((src_slab4 != nullptr) != (src_slab8 != nullptr) && dst, "flat_to_nchw: exactly one source expected");
+  if (mode == 0) DBM_REQUIRE(dst_h <= h && dst_w <= w, "flat_to_nchw: %dx%d window exceeds %dx%d", dst_h, dst_w, h, w);
+  else DBM_REQUIRE((dst_h + 1) / 2 <= h && (dst_w + 1) / 2 <= w, "flat_to_nchw: depth-to-space %dx%d exceeds %dx%d", dst_h, dst_w, h, w);
+  const FlatGeom g = flat_geom(n, h, w);
+  const long total = (long)n * c * dst_h * dst_w;
+  int grid = ceil_div(total, 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  flat_to_nchw_kernel<<<grid, 256, 0, stream>>>(src_slab4, (const __nv_bfloat16*)src_slab8, dst, c, dst_h, dst_w, mode, g);
+  return check_launch("flat_to_nchw_kernel");
+}
+
+extern "C" int dbm_flat_from_nchw(const float* src, int c, void* dst_slab8, float* dst_slab4, float scale, int n, int h,
+                                  int w, cudaStream_t stream) {
+  return dbm_flat_from_nchw_ex(src, c, h, w, 0, dst_slab8, dst_slab4, scale, n, h, w, stream);
 }
 
 extern "C" int dbm_flat_to_nchw(const float* src_slab4, const void* src_slab8, float* dst, int c, int n, int h, int w,
                                 cudaStream_t stream) {
-  DBM_REQUIRE((src_slab4 != nullptr) != (src_slab8 != nullptr) && dst, "flat_to_nchw: exactly one source expected");
-  const FlatGeom g = flat_geom(n, h, w);
-  const long total = (long)n * c * h * w;
-  int grid = ceil_div(total, 256);
-  if (grid > 148 * 8) grid = 148 * 8;
-  flat_to_nchw_kernel<<<grid, 256, 0, stream>>>(src_slab4, (const __nv_bfloat16*)src_slab8, dst, c, g);
-  return check_launch("flat_to_nchw_kernel");
+  return dbm_flat_to_nchw_ex(src_slab4, src_slab8, dst, c, h, w, 0, n, h, w, stream);
 }

@@ -20,13 +20,14 @@ EPI_DTYPE = np.dtype([("bias", "<u8"), ("add1", "<u8"), ("add2", "<u8"), ("mask"
                       ("out_bf16", "<u8"), ("s1", "<f4"), ("beta", "<f4"), ("beta2", "<f4"), ("out_scale", "<f4"),
                       ("act", "<i4"), ("pad", "<i4")])
 assert EPI_DTYPE.itemsize == 72
-LAUNCH_DTYPE = np.dtype([("in", "<u8"), ("wpacked", "<u8"), ("cin", "<i4"), ("nout", "<i4"), ("blk", EPI_DTYPE, (6,))])
-assert LAUNCH_DTYPE.itemsize == 456
+LAUNCH_DTYPE = np.dtype([("in", "<u8"), ("wpacked", "<u8"), ("cin", "<i4"), ("nout", "<i4"), ("ny", "<i4"), ("pad", "<i4"),
+                         ("w_chunk_stride", "<i8"), ("blk", EPI_DTYPE, (6,))])
+assert LAUNCH_DTYPE.itemsize == 472
 WGRAD_UNIT_DTYPE = np.dtype([("act", "<u8"), ("gout", "<u8"), ("partial", "<u8"), ("blk0", "<i4"), ("nblk", "<i4"),
                              ("nslab", "<i4"), ("pad", "<i4", (3,))])
 assert WGRAD_UNIT_DTYPE.itemsize == 48
 WGRAD_REDUCE_DTYPE = np.dtype([("partial", "<u8"), ("dw", "<u8"), ("split_stride", "<i8"), ("nsplit", "<i4"),
-                               ("cin_total", "<i4"), ("c0", "<i4"), ("o0", "<i4"), ("nch", "<i4"), ("pad", "<i4")])
+                               ("cin_total", "<i4"), ("c0", "<i4"), ("o0", "<i4"), ("nch", "<i4"), ("mode", "<i4")])
 assert WGRAD_REDUCE_DTYPE.itemsize == 48
 BIAS_GRAD_DTYPE = np.dtype([("gout", "<u8"), ("db", "<u8")])
 PARTIAL_FLOATS = 9 * 32 * 128
@@ -138,6 +139,7 @@ class FlatTrunk:
         L["wpacked"] = wq.data_ptr()
         L["cin"] = cin
         L["nout"] = nout
+        L["ny"] = 1
         assert len(blocks) == nout // 32
         for b, e in enumerate(blocks):
             L["blk"][b] = e
@@ -276,7 +278,7 @@ class FlatTrunk:
         n, H, W = self.n, self.H, self.W
         st = ops.stream()
         ops.call("dbm_flat_from_nchw", a0_nchw.data_ptr(), 128, self.s0.data_ptr(), None, 1.0, n, H, W, st)
-        ops.call("dbm_flat_conv3x3_seq", self.fwd.ctypes.data, len(self.fwd), n, H, W, st)
+        ops.call("dbm_flat_conv3x3_seq", self.fwd.ctypes.data, len(self.fwd), n, H, W, 0, 0, st)
         a3 = ops.empty(n, 64, H, W)
         ops.call("dbm_flat_to_nchw", self.a3f.data_ptr(), None, a3.data_ptr(), 64, n, H, W, st)
         return a3
@@ -288,7 +290,7 @@ class FlatTrunk:
         st = ops.stream()
         ops.call("dbm_flat_from_nchw", da3_nchw.data_ptr(), 64, self.gpost.data_ptr(), self.da3f.data_ptr(), 1.0, n, H, W,
                  st)
-        ops.call("dbm_flat_conv3x3_seq", self.bwd.ctypes.data, len(self.bwd), n, H, W, st)
+        ops.call("dbm_flat_conv3x3_seq", self.bwd.ctypes.data, len(self.bwd), n, H, W, 0, 0, st)
         ops.call("dbm_flat_wgrad", self.units_dev.data_ptr(), self.n_units, n, H, W, st)
         ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, st)
         ops.call("dbm_flat_bias_grad", self.bias_dev.data_ptr(), self.n_bias, n, H, W, st)
@@ -342,6 +344,166 @@ def conv3x3(inp: torch.Tensor, cin: int, wpacked: torch.Tensor, nout: int, block
     L[0]["wpacked"] = wpacked.data_ptr()
     L[0]["cin"] = cin
     L[0]["nout"] = nout
+    L[0]["ny"] = 1
     for b, kw in enumerate(blocks):
         L[0]["blk"][b] = FlatTrunk._epi(**kw)
-    ops.call("dbm_flat_conv3x3_seq", L.ctypes.data, 1, n, h, w, ops.stream())
+    ops.call("dbm_flat_conv3x3_seq", L.ctypes.data, 1, n, h, w, 0, 0, ops.stream())
+
+
+# ====================================================================================================
+# Single convolutions on the flat tensor-core kernels (discriminator, generator head)
+# ====================================================================================================
+def _round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+class ConvImages:
+    """bf16 operand images of ONE convolution's filter for the flat kernels: forward images (one per chunk of
+    <= 128 output channels) and data-gradient images (one per chunk of <= 128 input / phase channels).
+    ksize 3 (stride 1, pad 1) or ksize 4 (stride 2, pad 1: embedded as 3x3 over the 4 space-to-depth phases,
+    PackEntry modes 2 / 3). ``entries`` are PackEntry records for dbm_pack_conv3x3_table."""
+
+    def __init__(self, w: torch.Tensor, bias=None):
+        O, C, k, k2 = (int(v) for v in w.shape)
+        if (k, k2) not in ((3, 3), (4, 4)):
+            raise ValueError("flat convolutions implement 3x3 stride-1 and 4x4 stride-2 filters")
+        self.O, self.C, self.k = O, C, k
+        self.s2d = k == 4
+        self.Cg = 4 * C if self.s2d else C
+        if self.Cg % 16:
+            raise ValueError(f"flat convolution needs a multiple of 16 GEMM input channels, got {self.Cg}")
+        self.Opad = _round_up(O, 32)
+        self.Nf = min(self.Opad, 128)
+        self.ny_f = self.Opad // self.Nf
+        self.Nd = min(self.Cg, 128)
+        self.ny_d = self.Cg // self.Nd
+        assert self.Opad % self.Nf == 0 and self.Cg % self.Nd == 0 and self.Nd % 32 == 0
+        bf = torch.bfloat16
+        self.fwd_img = ops.zeros(self.ny_f, 9 * self.Cg * self.Nf, dtype=bf)
+        self.dgrad_img = ops.zeros(self.ny_d, 9 * self.Opad * self.Nd, dtype=bf)
+        self.bias = bias
+        self.bias_pad = None
+        if bias is not None:
+            self.bias_pad = bias if self.Opad == O else ops.zeros(self.Opad)
+        kk = k * k
+        self.entries = []
+        for y in range(self.ny_f):
+            rows = min(self.Nf, O - y * self.Nf)
+            self.entries.append((w.data_ptr() + 4 * y * self.Nf * C * kk, self.fwd_img[y].data_ptr(), rows, 0, self.Cg, C, 0,
+                                 self.Nf, 16, 2 if self.s2d else 0))
+        for y in range(self.ny_d):
+            self.entries.append((w.data_ptr(), self.dgrad_img[y].data_ptr(), self.Nd, O if O < self.Opad else 0,
+                                 self.Opad, C, y * self.Nd, self.Nd, 16, 3 if self.s2d else 1))
+        self.max_elements = max(9 * self.Cg * self.Nf, 9 * self.Opad * self.Nd)
+
+    def refresh_bias(self):
+        if self.bias_pad is not None and self.bias_pad is not self.bias:
+            self.bias_pad[: self.O].copy_(self.bias)
+
+
+def pack_images(images) -> None:
+    """One table-driven launch (re)packing the operand images of every ConvImages in ``images``."""
+    from .model import PACK_ENTRY_DTYPE
+    entries = [e for im in images for e in im.entries]
+    table = torch.from_numpy(np.array(entries, dtype=PACK_ENTRY_DTYPE).view(np.uint8).copy()).cuda()
+    ops.call("dbm_pack_conv3x3_table", table.data_ptr(), len(entries), max(im.max_elements for im in images),
+             ops.stream())
+    for im in images:
+        im.refresh_bias()
+    return table   # keep alive until the launch has run (callers cache it)
+
+
+class FlatConv:
+    """Forward / backward of one convolution for a fixed (batch, H, W), NCHW fp32 tensors in and out, on the flat
+    tcgen05 kernels (bf16 operands, fp32 accumulation). ``nslots`` forward inputs can be kept for backward (the
+    discriminator step runs two forward passes before its two backward passes, srgan_train.py:1145-1163)."""
+
+    TARGET_UNITS = 296
+
+    def __init__(self, im: ConvImages, gw: torch.Tensor, n: int, H: int, W: int, act: bool = False, nslots: int = 1):
+        self.im, self.n, self.H, self.W, self.act = im, n, H, W, act
+        s2d = im.s2d
+        self.Ho, self.Wo = (H // 2, W // 2) if s2d else (H, W)
+        self.gh, self.gw_ = ((H + 1) // 2, (W + 1) // 2) if s2d else (H, W)
+        if self.Ho < 1 or self.Wo < 1:
+            raise ValueError("input too small for this convolution")
+        self.geom = geometry(n, self.gh, self.gw_)
+        Pg = self.geom["Pg"]
+        self.Pg = Pg
+        self.xin = [alloc_bf16(im.Cg, self.geom) for _ in range(nslots)]
+        self.zf = alloc_f32(im.Opad, self.geom)
+        self.gin = alloc_bf16(im.Opad, self.geom)
+        self.dxf = alloc_f32(im.Cg, self.geom)
+        epi = FlatTrunk._epi
+        self.rec_f = []
+        for slot in range(nslots):
+            L = np.zeros(1, dtype=LAUNCH_DTYPE)
+            L[0]["in"] = self.xin[slot].data_ptr()
+            L[0]["wpacked"] = im.fwd_img.data_ptr()
+            L[0]["cin"], L[0]["nout"], L[0]["ny"] = im.Cg, im.Nf, im.ny_f
+            L[0]["w_chunk_stride"] = 9 * im.Cg * im.Nf
+            for b in range(im.Nf // 32):
+                L[0]["blk"][b] = epi(bias=(im.bias_pad.data_ptr() + 128 * b) if im.bias_pad is not None else 0,
+                                     act=int(act), out_f32=self.zf.data_ptr() + 4 * 32 * b * Pg)
+            self.rec_f.append(L)
+        L = np.zeros(1, dtype=LAUNCH_DTYPE)
+        L[0]["in"] = self.gin.data_ptr()
+        L[0]["wpacked"] = im.dgrad_img.data_ptr()
+        L[0]["cin"], L[0]["nout"], L[0]["ny"] = im.Opad, im.Nd, im.ny_d
+        L[0]["w_chunk_stride"] = 9 * im.Opad * im.Nd
+        for b in range(im.Nd // 32):
+            L[0]["blk"][b] = epi(out_f32=self.dxf.data_ptr() + 4 * 32 * b * Pg)
+        self.rec_d = L
+        # weight gradient: units = (input-channel chunk, 32 output channels, position range)
+        chunks = chunk_channels(im.Cg)
+        ogroups = im.Opad // 32
+        nsplit = max(1, min(self.geom["tiles"], round(self.TARGET_UNITS / (len(chunks) * ogroups))))
+        splits = split_blocks(self.geom["tiles"], nsplit)
+        self.units, self.n_units = [], 0
+        reduces = []
+        dev = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).cuda()
+        n_units = len(chunks) * ogroups * len(splits)
+        self.partial = torch.empty(n_units * PARTIAL_FLOATS, dtype=torch.float32, device="cuda")
+        base = self.partial.data_ptr()
+        for slot in range(nslots):
+            units = []
+            for og in range(ogroups):
+                for c0, nch in chunks:
+                    first = len(units)
+                    for blk0, nblk in splits:
+                        units.append((self.xin[slot].data_ptr() + 2 * c0 * Pg, self.gin.data_ptr() + 2 * 32 * og * Pg,
+                                      base + len(units) * PARTIAL_FLOATS * 4, blk0, nblk, nch // 8, (0, 0, 0)))
+                    if slot == 0:
+                        ovalid = min(32, im.O - 32 * og)
+                        mode = (1 if s2d else 0) | ((ovalid if ovalid < 32 else 0) << 8)
+                        reduces.append((base + first * PARTIAL_FLOATS * 4, gw.data_ptr(), PARTIAL_FLOATS, len(splits), im.C,
+                                        c0, 32 * og, nch, mode))
+            self.units.append(dev(np.array(units, dtype=WGRAD_UNIT_DTYPE)))
+            self.n_units = len(units)
+        self.reduce_dev, self.n_reduce = dev(np.array(reduces, dtype=WGRAD_REDUCE_DTYPE)), len(reduces)
+        self.flops = 2.0 * 9 * im.Cg * im.Opad * self.geom["P"]   # executed MMA FLOPs per GEMM pass
+
+    def forward(self, x: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        im, n, st = self.im, self.n, ops.stream()
+        ops.call("dbm_flat_from_nchw_ex", x.data_ptr(), im.C, self.H, self.W, int(im.s2d), self.xin[slot].data_ptr(), None,
+                 1.0, n, self.gh, self.gw_, st)
+        ops.call("dbm_flat_conv3x3_seq", self.rec_f[slot].ctypes.data, 1, n, self.gh, self.gw_, self.Ho, self.Wo, st)
+        z = ops.empty(n, im.O, self.Ho, self.Wo)
+        ops.call("dbm_flat_to_nchw_ex", self.zf.data_ptr(), None, z.data_ptr(), im.O, self.Ho, self.Wo, 0, n, self.gh,
+                 self.gw_, st)
+        return z
+
+    def backward(self, dz: torch.Tensor, slot: int = 0, need_dx: bool = True):
+        """dW += x (*) dz for the input kept in ``slot``; returns d(loss)/dx (n, C, H, W) or None."""
+        im, n, st = self.im, self.n, ops.stream()
+        ops.call("dbm_flat_from_nchw_ex", dz.data_ptr(), im.O, self.Ho, self.Wo, 0, self.gin.data_ptr(), None, 1.0, n,
+                 self.gh, self.gw_, st)
+        dx = None
+        if need_dx:
+            ops.call("dbm_flat_conv3x3_seq", self.rec_d.ctypes.data, 1, n, self.gh, self.gw_, 0, 0, st)
+            dx = ops.empty(n, im.C, self.H, self.W)
+            ops.call("dbm_flat_to_nchw_ex", self.dxf.data_ptr(), None, dx.data_ptr(), im.C, self.H, self.W, int(im.s2d), n,
+                     self.gh, self.gw_, st)
+        ops.call("dbm_flat_wgrad", self.units[slot].data_ptr(), self.n_units, n, self.gh, self.gw_, st)
+        ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, st)
+        return dx

@@ -170,6 +170,7 @@ class GeneratorModel(_Link):
         self.precision = precision
         self.train_precision = train_precision
         self._flat = {}
+        self._head_images, self._head_tc, self._head_packed_version, self._head_pack_table = None, {}, -1, None
         shapes = layout.generator_shapes(self.num_residual_blocks, self.inter_channels, self.out_channels)
         super().__init__(shapes, layout.init_values(shapes, seed, init_scale))
         self._packed_version = -1
@@ -293,28 +294,51 @@ class GeneratorModel(_Link):
         """Upsample convs + the two deformable layers (srgan_train.py:553-574), fp32."""
         P = self.p
         n, H, W = ctx["n"], ctx["H"], ctx["W"]
+        tc = self._head_convs(n, H, W) if (save and self.train_precision == "bf16") else None
+
+        def conv(key, x, act):
+            if tc is not None:   # tcgen05 (flat.FlatConv): bf16 operands, fp32 accumulation, bias (+ LeakyReLU) fused
+                return tc[key].forward(x)
+            w = P[f"{key}/W"]
+            out = ops.empty(n, w.shape[0], x.shape[2], x.shape[3])
+            ops.conv2d_fwd(x, 0, 64, w, P[f"{key}/b"], out, 0, 3, 1, 1, act=act)
+            return out
+
         u1 = ops.upsample2_fwd(a3)
-        c1 = ops.empty(n, 64, 2 * H, 2 * W)
-        ops.conv2d_fwd(u1, 0, 64, P["post_upsample_conv_layer_1/W"], P["post_upsample_conv_layer_1/b"], c1, 0, 3, 1, 1,
-                       act=True)
+        c1 = conv("post_upsample_conv_layer_1", u1, True)
         u2 = ops.upsample2_fwd(c1)
-        c2 = ops.empty(n, 64, 4 * H, 4 * W)
-        ops.conv2d_fwd(u2, 0, 64, P["post_upsample_conv_layer_2/W"], P["post_upsample_conv_layer_2/b"], c2, 0, 3, 1, 1,
-                       act=True)
-        off1 = ops.empty(n, 18, 4 * H, 4 * W)
-        ops.conv2d_fwd(c2, 0, 64, P["final_conv_layer1/offset_conv/W"], P["final_conv_layer1/offset_conv/b"], off1, 0, 3,
-                       1, 1)
+        c2 = conv("post_upsample_conv_layer_2", u2, True)
+        off1 = conv("final_conv_layer1/offset_conv", c2, False)
         d1, cols1 = ops.deform_conv_fwd(c2, off1, P["final_conv_layer1/deform_conv/W"],
                                         P["final_conv_layer1/deform_conv/b"], act=True)
-        off2 = ops.empty(n, 18, 4 * H, 4 * W)
-        ops.conv2d_fwd(d1, 0, 64, P["final_conv_layer2/offset_conv/W"], P["final_conv_layer2/offset_conv/b"], off2, 0, 3,
-                       1, 1)
+        off2 = conv("final_conv_layer2/offset_conv", d1, False)
         y, cols2 = ops.deform_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"],
                                        P["final_conv_layer2/deform_conv/b"], act=False)
         if save:
-            ctx.update(u1=u1, c1=c1, u2=u2, c2=c2, off1=off1, d1=d1, cols1=cols1, off2=off2, cols2=cols2)
+            ctx.update(u1=u1, c1=c1, u2=u2, c2=c2, off1=off1, d1=d1, cols1=cols1, off2=off2, cols2=cols2, head_tc=tc)
             self._ctx = ctx
         return y
+
+    HEAD_TC_KEYS = ("post_upsample_conv_layer_1", "post_upsample_conv_layer_2", "final_conv_layer1/offset_conv",
+                    "final_conv_layer2/offset_conv")
+
+    def _head_convs(self, n, H, W):
+        """flat.FlatConv objects of the four plain 3x3 convolutions of the head for this batch shape; their
+        operand images are re-packed (one launch) whenever the weights changed."""
+        from . import flat
+        if self._head_images is None:
+            self._head_images = {k: flat.ConvImages(self.p[f"{k}/W"], self.p[f"{k}/b"]) for k in self.HEAD_TC_KEYS}
+        if self._head_packed_version != self.version:
+            self._head_pack_table = flat.pack_images(list(self._head_images.values()))
+            self._head_packed_version = self.version
+        tc = self._head_tc.get((n, H, W))
+        if tc is None:
+            sizes = {"post_upsample_conv_layer_1": 2, "post_upsample_conv_layer_2": 4,
+                     "final_conv_layer1/offset_conv": 4, "final_conv_layer2/offset_conv": 4}
+            tc = {k: flat.FlatConv(self._head_images[k], self.g[f"{k}/W"], n, sizes[k] * H, sizes[k] * W,
+                                   act=k.startswith("post_upsample")) for k in self.HEAD_TC_KEYS}
+            self._head_tc[(n, H, W)] = tc
+        return tc
 
     def backward(self, dy: torch.Tensor, on_ready=None):
         """Accumulates d(loss)/d(params) into ``flat_grad`` given d(loss)/d(output) (N,1,4H,4W);
@@ -333,34 +357,45 @@ class GeneratorModel(_Link):
         n, H, W = c["n"], c["H"], c["W"]
         dy = dy.contiguous()
         # ---- final_conv_layer2 (deformable, no activation) ----
+        tc = c.get("head_tc")
+
+        def conv_bwd(key, x, dz, dx_accumulate_into=None):
+            """dW, db of a plain 3x3 conv of the head and its data gradient (added to ``dx_accumulate_into``
+            or returned)."""
+            if tc is not None:
+                ops.call("dbm_bias_grad_f32", dz.data_ptr(), dz.shape[1] * dz.shape[2] * dz.shape[3],
+                         G[f"{key}/b"].data_ptr(), n, dz.shape[1], dz.shape[2] * dz.shape[3], ops.stream())
+                dx = tc[key].backward(dz)
+                if dx_accumulate_into is None:
+                    return dx
+                ops.axpby(dx, 0, dx_accumulate_into, 0, dx_accumulate_into, 0, 64, 1.0, 1.0)
+                return dx_accumulate_into
+            ops.conv2d_bwd_weight(x, 0, 64, dz, 0, G[f"{key}/W"], 3, 1, 1, db=G[f"{key}/b"])
+            if dx_accumulate_into is not None:
+                ops.conv2d_bwd_data(dz, 0, P[f"{key}/W"], dx_accumulate_into, 0, 64, 3, 1, 1, accumulate=True)
+                return dx_accumulate_into
+            dx = ops.empty(*x.shape)
+            ops.conv2d_bwd_data(dz, 0, P[f"{key}/W"], dx, 0, 64, 3, 1, 1)
+            return dx
+
         dd1 = ops.zeros(n, 64, 4 * H, 4 * W)
         doff2 = ops.deform_conv_bwd(c["d1"], c["off2"], P["final_conv_layer2/deform_conv/W"], c["cols2"], dy,
                                     G["final_conv_layer2/deform_conv/W"], G["final_conv_layer2/deform_conv/b"], dd1)
-        ops.conv2d_bwd_weight(c["d1"], 0, 64, doff2, 0, G["final_conv_layer2/offset_conv/W"], 3, 1, 1,
-                              db=G["final_conv_layer2/offset_conv/b"])
-        ops.conv2d_bwd_data(doff2, 0, P["final_conv_layer2/offset_conv/W"], dd1, 0, 64, 3, 1, 1, accumulate=True)
+        conv_bwd("final_conv_layer2/offset_conv", c["d1"], doff2, dx_accumulate_into=dd1)
         ops.lrelu_bwd(dd1, 0, c["d1"], 0, dd1, 0, 64)
         # ---- final_conv_layer1 ----
         dc2 = ops.zeros(n, 64, 4 * H, 4 * W)
         doff1 = ops.deform_conv_bwd(c["c2"], c["off1"], P["final_conv_layer1/deform_conv/W"], c["cols1"], dd1,
                                     G["final_conv_layer1/deform_conv/W"], G["final_conv_layer1/deform_conv/b"], dc2)
-        ops.conv2d_bwd_weight(c["c2"], 0, 64, doff1, 0, G["final_conv_layer1/offset_conv/W"], 3, 1, 1,
-                              db=G["final_conv_layer1/offset_conv/b"])
-        ops.conv2d_bwd_data(doff1, 0, P["final_conv_layer1/offset_conv/W"], dc2, 0, 64, 3, 1, 1, accumulate=True)
+        conv_bwd("final_conv_layer1/offset_conv", c["c2"], doff1, dx_accumulate_into=dc2)
         del dd1, doff1, doff2
         # ---- upsample convs ----
         ops.lrelu_bwd(dc2, 0, c["c2"], 0, dc2, 0, 64)
-        ops.conv2d_bwd_weight(c["u2"], 0, 64, dc2, 0, G["post_upsample_conv_layer_2/W"], 3, 1, 1,
-                              db=G["post_upsample_conv_layer_2/b"])
-        du2 = ops.empty(n, 64, 4 * H, 4 * W)
-        ops.conv2d_bwd_data(dc2, 0, P["post_upsample_conv_layer_2/W"], du2, 0, 64, 3, 1, 1)
+        du2 = conv_bwd("post_upsample_conv_layer_2", c["u2"], dc2)
         dc1 = ops.upsample2_bwd(du2)
         del du2, dc2
         ops.lrelu_bwd(dc1, 0, c["c1"], 0, dc1, 0, 64)
-        ops.conv2d_bwd_weight(c["u1"], 0, 64, dc1, 0, G["post_upsample_conv_layer_1/W"], 3, 1, 1,
-                              db=G["post_upsample_conv_layer_1/b"])
-        du1 = ops.empty(n, 64, 2 * H, 2 * W)
-        ops.conv2d_bwd_data(dc1, 0, P["post_upsample_conv_layer_1/W"], du1, 0, 64, 3, 1, 1)
+        du1 = conv_bwd("post_upsample_conv_layer_1", c["u1"], dc1)
         da3 = ops.upsample2_bwd(du1)  # = d a1 (skip) = d (post-res conv output)
         del du1, dc1
         if "flat" in c:
@@ -667,7 +702,16 @@ class DiscriminatorModel(_Link):
     BN_EPS = 1e-5
     BN_DECAY = 0.9
 
-    def __init__(self, *, seed: int = 1, init_scale: float = 0.1):
+    def __init__(self, *, precision: str = "bf16", seed: int = 1, init_scale: float = 0.1):
+        """``precision``: "bf16" = conv_layer1..9 (99 % of the FLOPs) on the tcgen05 tensor cores (bf16 operands,
+        fp32 accumulation; flat.FlatConv, the 4x4 stride-2 layers as 3x3 GEMMs over space-to-depth phases);
+        "fp32" = exact CUDA-core path. conv_layer0, BatchNormalization, LeakyReLU and the two Linear layers are
+        fp32 in both."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
+        self._tc_images, self._tc, self._tc_packed_version, self._tc_pack_table = None, {}, -1, None
+        self._slot = 0
         shapes = layout.discriminator_shapes()
         super().__init__(shapes, layout.init_values(shapes, seed, init_scale))
         self.persistent = OrderedDict()
@@ -705,11 +749,19 @@ class DiscriminatorModel(_Link):
         stats = []
         hcur = 36
         cin = 64
+        tc = self._tc_convs(n) if self.precision == "bf16" else None
+        slot = 2   # forward inputs are kept per slot: 0 / 1 alternate for saved passes, 2 = no backward follows
+        if save:
+            slot = self._slot
+            self._slot ^= 1
         for i in range(1, 10):
             cout, k, s = layout.DISC_CONVS[i]
             ho, _ = ops.conv_out_hw(hcur, hcur, k, s, 1)
-            z = ops.empty(n, cout, ho, ho)
-            ops.conv2d_fwd(acts[-1], 0, cin, P[f"conv_layer{i}/W"], None, z, 0, k, s, 1)
+            if tc is not None:
+                z = tc[i].forward(acts[-1], slot)
+            else:
+                z = ops.empty(n, cout, ho, ho)
+                ops.conv2d_fwd(acts[-1], 0, cin, P[f"conv_layer{i}/W"], None, z, 0, k, s, 1)
             y = ops.empty(n, cout, ho, ho)
             mean, invstd = ops.empty(cout), ops.empty(cout)
             ops.call("dbm_bn_lrelu_fwd_f32", z.data_ptr(), y.data_ptr(), P[f"batch_norm{i}/gamma"].data_ptr(),
@@ -730,8 +782,25 @@ class DiscriminatorModel(_Link):
         if save:
             if not train:
                 raise ValueError("backward through eval-mode BatchNormalization is not needed by the reference")
-            self._ctx = dict(acts=acts, pres=pres, stats=stats, l1=l1, n=n)
+            self._ctx = dict(acts=acts, pres=pres, stats=stats, l1=l1, n=n, tc=tc, slot=slot)
         return Variable(out)
+
+    def _tc_convs(self, n):
+        from . import flat
+        if self._tc_images is None:
+            self._tc_images = {i: flat.ConvImages(self.p[f"conv_layer{i}/W"]) for i in range(1, 10)}
+        if self._tc_packed_version != self.version:
+            self._tc_pack_table = flat.pack_images(list(self._tc_images.values()))
+            self._tc_packed_version = self.version
+        tc = self._tc.get(n)
+        if tc is None:
+            tc, h = {}, 36
+            for i in range(1, 10):
+                _, k, s = layout.DISC_CONVS[i]
+                tc[i] = flat.FlatConv(self._tc_images[i], self.g[f"conv_layer{i}/W"], n, h, h, nslots=3)
+                h = ops.conv_out_hw(h, h, k, s, 1)[0]
+            self._tc[n] = tc
+        return tc
 
     def backward(self, dlogit: torch.Tensor, on_ready=None):
         """Accumulates parameter gradients for the most recent ``forward(save=True)`` given
@@ -772,9 +841,12 @@ class DiscriminatorModel(_Link):
                      cout, hw, ops.stream())
             xin = acts[i]
             cin = xin.shape[1]
-            ops.conv2d_bwd_weight(xin, 0, cin, dz, 0, G[f"conv_layer{i}/W"], k, s, 1)
-            dx = ops.empty(*xin.shape)
-            ops.conv2d_bwd_data(dz, 0, P[f"conv_layer{i}/W"], dx, 0, cin, k, s, 1)
+            if c.get("tc") is not None:
+                dx = c["tc"][i].backward(dz, c["slot"])
+            else:
+                ops.conv2d_bwd_weight(xin, 0, cin, dz, 0, G[f"conv_layer{i}/W"], k, s, 1)
+                dx = ops.empty(*xin.shape)
+                ops.conv2d_bwd_data(dz, 0, P[f"conv_layer{i}/W"], dx, 0, cin, k, s, 1)
             dy = dx
             if i == 9:
                 ready("linear_", "conv_layer9/", "batch_norm9/")

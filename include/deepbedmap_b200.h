@@ -130,9 +130,11 @@ int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, 
  *   bf16 slab8 [C/8][Pg][8], fp32 slab4 [C/4][Pg][4]; dbm_flat_geometry -> {P, tiles, G0, Pg, R}:
  *   Pg = slab stride in positions, G0 = leading zero guard. Buffers must be zero-initialised once;
  *   the kernels only ever write interior positions.
- * dbm_flat_conv3x3_seq runs `count` launches described by 456-byte HOST records (struct FlatLaunch:
- *   {const bf16* in; const bf16* wpacked; int cin, nout; FlatEpiBlock blk[6]}), each a 3x3 'same' conv
- *   with N = nout in {32..192} output columns whose epilogue is given per 32 columns by a 72-byte
+ * dbm_flat_conv3x3_seq runs `count` launches described by 472-byte HOST records (struct FlatLaunch:
+ *   {const bf16* in; const bf16* wpacked; int cin, nout, ny, pad; long w_chunk_stride; FlatEpiBlock blk[6]}),
+ *   each a 3x3 'same' conv with ny chunks (grid.y) of N = nout in {32..192} output columns (chunk y reads
+ *   filter image y and advances every epilogue pointer by y*N channels); only rows/columns 1..out_h/out_w of
+ *   the interior are written (0 = all). The epilogue is given per 32 columns by a 72-byte
  *   FlatEpiBlock {bias, add1, add2, mask, out_f32, out_bf16 (pointers to the block's first slab),
  *   s1, beta, beta2, out_scale, act}:
  *     v = acc + bias; v = s1*add1 + beta*v; v = add2 + beta2*v; act: v = lrelu(v);
@@ -142,15 +144,23 @@ int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, 
  * dbm_flat_wgrad: dW[o][c][tap] partial sums; units_dev = 48-byte records {const bf16* act; const bf16*
  *   gout; float* partial[9][32][128]; int blk0, nblk, nslab; pad} (struct WgradUnit);
  * dbm_flat_wgrad_reduce: 48-byte records {const float* partial; float* dw; long split_stride; int nsplit,
- *   cin_total, c0, o0, nch; pad}: dw[(o0+o)*cin_total + c0 + c][tap] += sum_s partial[s][tap][o][c];
+ *   cin_total, c0, o0, nch, mode}: dw[(o0+o)*cin_total + c0 + c][tap] += sum_s partial[s][tap][o][c];
  * dbm_flat_bias_grad: 16-byte records {const bf16* gout; float* db}: db[0:32] += sum_p gout[.][p]. */
 int dbm_flat_debug_set(int key, int value);
 int dbm_flat_geometry(int n, int h, int w, int* out5_host);
-int dbm_flat_conv3x3_seq(const void* launches_host, int count, int n, int h, int w, cudaStream_t stream);
+int dbm_flat_conv3x3_seq(const void* launches_host, int count, int n, int h, int w, int out_h, int out_w,
+                         cudaStream_t stream);
 int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h, int w, cudaStream_t stream);
 int dbm_flat_wgrad_reduce(const void* entries_dev, int count, cudaStream_t stream);
 int dbm_flat_bias_grad(const void* entries_dev, int count, int n, int h, int w, cudaStream_t stream);
-/* NCHW fp32 (n, c, h, w) -> scale * x into a flat slab8 and/or slab4 (either may be NULL), and back */
+/* NCHW fp32 (n, c, h, w) -> scale * x into a flat slab8 and/or slab4 (either may be NULL), and back.
+ * _ex: mode 0 = the (src_h, src_w) image sits in the top-left corner of the (h, w) interior; mode 1 = space-to-depth
+ * by 2 (pixel (y, x) of channel c -> channel ((y&1)*2 + (x&1))*C + c at (y>>1, x>>1)): with PackEntry.mode 2 / 3
+ * filters the 4x4 stride-2 pad-1 convolutions of the discriminator (srgan_train.py:626-634) run as 3x3 GEMMs. */
+int dbm_flat_from_nchw_ex(const float* src, int c, int src_h, int src_w, int mode, void* dst_slab8, float* dst_slab4,
+                          float scale, int n, int h, int w, cudaStream_t stream);
+int dbm_flat_to_nchw_ex(const float* src_slab4, const void* src_slab8, float* dst, int c, int dst_h, int dst_w, int mode,
+                        int n, int h, int w, cudaStream_t stream);
 int dbm_flat_from_nchw(const float* src, int c, void* dst_slab8, float* dst_slab4, float scale, int n, int h, int w,
                        cudaStream_t stream);
 int dbm_flat_to_nchw(const float* src_slab4, const void* src_slab8, float* dst, int c, int n, int h, int w,

@@ -375,12 +375,21 @@ def _generator_forward_exact(p: Params, x, w1, w2, w3, num_residual_blocks=12,
             a2 = rrdb(p, f"residual_network/{i}", a2, residual_scaling)
         a3 = a1 + F.conv2d(a2, p["post_residual_conv_layer/W"],
                            p["post_residual_conv_layer/b"], padding=1)          # :550-551
-    a4_1 = _lrelu(F.conv2d(upsample_nearest2(a3), p["post_upsample_conv_layer_1/W"],
-                           p["post_upsample_conv_layer_1/b"], padding=1))   # :556-560
-    a4_2 = _lrelu(F.conv2d(upsample_nearest2(a4_1), p["post_upsample_conv_layer_2/W"],
-                           p["post_upsample_conv_layer_2/b"], padding=1))   # :562-568
-    a5_1 = _lrelu(deformable_layer(p, "final_conv_layer1", a4_2))           # :572-573
-    a5_2 = deformable_layer(p, "final_conv_layer2", a5_1)                   # :574
+    # trunk_bf16 also rounds the operands of the head's four plain 3x3 convolutions (upsample convs, offset convs),
+    # which the product's training path runs on the tensor cores too; the deformable sampling + contraction is fp32
+    q = _q if trunk_bf16 else (lambda t: t)
+
+    def conv(x_, name):
+        return F.conv2d(q(x_), q(p[f"{name}/W"]), p[f"{name}/b"], padding=1)
+
+    def deform(x_, name):
+        return deformable_conv2d(x_, conv(x_, f"{name}/offset_conv"), p[f"{name}/deform_conv/W"],
+                                 p[f"{name}/deform_conv/b"])
+
+    a4_1 = _lrelu(conv(upsample_nearest2(a3), "post_upsample_conv_layer_1"))    # :556-560
+    a4_2 = _lrelu(conv(upsample_nearest2(a4_1), "post_upsample_conv_layer_2"))  # :562-568
+    a5_1 = _lrelu(deform(a4_2, "final_conv_layer1"))                            # :572-573
+    a5_2 = deform(a5_1, "final_conv_layer2")                                    # :574
     if return_intermediates:
         inter.update(a0=a0, a1=a1, a2=a2, a3=a3, a4_1=a4_1, a4_2=a4_2, a5_1=a5_1)
         return a5_2, inter
@@ -417,12 +426,16 @@ def batch_norm(p: Params, name: str, x, train: bool, stats_out: Optional[dict]):
     return xhat * g + b
 
 
-def discriminator_forward(p: Params, x, train: bool = True, stats_out: Optional[dict] = None):
-    """DiscriminatorModel.forward, srgan_train.py:649-699.  Returns logits (N,1)."""
+def discriminator_forward(p: Params, x, train: bool = True, stats_out: Optional[dict] = None,
+                          emulate_bf16: bool = False):
+    """DiscriminatorModel.forward, srgan_train.py:649-699.  Returns logits (N,1).
+    ``emulate_bf16``: operand rounding of the product's tensor-core discriminator (precision="bf16"): inputs and
+    filters of conv_layer1..9 rounded to bf16 (straight-through for autograd), everything else exact."""
+    q = _q if emulate_bf16 else (lambda t: t)
     a = _lrelu(F.conv2d(x, p["conv_layer0/W"], p["conv_layer0/b"], stride=1, padding=1))
     for i in range(1, 10):
         _, k, s = DISC_CONVS[i]
-        a = F.conv2d(a, p[f"conv_layer{i}/W"], None, stride=s, padding=1)
+        a = F.conv2d(q(a), q(p[f"conv_layer{i}/W"]), None, stride=s, padding=1)
         a = _lrelu(batch_norm(p, f"batch_norm{i}", a, train, stats_out))
     a = a.reshape(a.shape[0], -1)                                             # :693
     a = _lrelu(F.linear(a, p["linear_1/W"], p["linear_1/b"]))                # :694-695

@@ -71,7 +71,7 @@ def timings(nb=12, n=128):
         return e0.elapsed_time(e1) / reps
 
     t_f = timed(lambda: ft.forward(a0))
-    t_d = timed(lambda: ops.call("dbm_flat_conv3x3_seq", ft.bwd.ctypes.data, len(ft.bwd), n, 9, 9, st))
+    t_d = timed(lambda: ops.call("dbm_flat_conv3x3_seq", ft.bwd.ctypes.data, len(ft.bwd), n, 9, 9, 0, 0, st))
     t_w = timed(lambda: ops.call("dbm_flat_wgrad", ft.units_dev.data_ptr(), ft.n_units, n, 9, 9, st))
     t_r = timed(lambda: (ops.call("dbm_flat_wgrad_reduce", ft.reduce_dev.data_ptr(), ft.n_reduce, st),
                          ops.call("dbm_flat_bias_grad", ft.bias_dev.data_ptr(), ft.n_bias, n, 9, 9, st)))

@@ -146,10 +146,10 @@ def test_generator_reference_init_scale():
     assert rel_l2(m.forward(*ins).numpy(), ref) < 2e-2
 
 
-def _load_disc(seed=1):
+def _load_disc(seed=1, precision="fp32"):
     from deepbedmap_b200 import DiscriminatorModel
     params = O.init_discriminator_params(seed=seed, bias_std=0.1, scale=1.0)
-    d = DiscriminatorModel()
+    d = DiscriminatorModel(precision=precision)
     for k in d.p:
         d.set_param(k, params[k])
     return d, params
