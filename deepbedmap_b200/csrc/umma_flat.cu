@@ -393,12 +393,14 @@ struct WgradReduce {  // 48 bytes; dw[(o0 + o) * cin_total + c0 + c][tap] += sum
 };                    // phases (channel c0 + c = phase * cin_total + cc); bits 8-15: valid output rows (0 = 32)
 static_assert(sizeof(WgradReduce) == 48, "WgradReduce layout is part of the C ABI");
 
-__global__ void flat_wgrad_reduce_kernel(const WgradReduce* __restrict__ table) {
+// grid = (entries, slices): blockIdx.y strides over the entry's 9 x 32 x nch outputs, so that an entry with many
+// position splits (small layers: 4 entries x 74 splits) is still spread over every SM
+__global__ void __launch_bounds__(256) flat_wgrad_reduce_kernel(const WgradReduce* __restrict__ table) {
   const WgradReduce e = table[blockIdx.x];
   const int total = 9 * 32 * e.nch;
   const int mode = e.mode & 0xFF;
   const int ovalid = ((e.mode >> 8) & 0xFF) ? ((e.mode >> 8) & 0xFF) : 32;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
     const int c = i % e.nch;
     const int t = i / e.nch;
     const int o = t & 31, tap = t >> 5;
@@ -413,10 +415,17 @@ __global__ void flat_wgrad_reduce_kernel(const WgradReduce* __restrict__ table) 
       if (ky < 0 || ky > 3 || kx < 0 || kx > 3) continue;   // structurally zero tap of the embedding
       dst = ((long)(e.o0 + o) * e.cin_total + cc) * 16 + ky * 4 + kx;
     }
-    float s = 0.f;
     const float* src = e.partial + (tap * 32 + o) * 128 + c;
-    for (int k = 0; k < e.nsplit; ++k) s += src[(long)k * e.split_stride];
-    e.dw[dst] += s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= e.nsplit; k += 4) {   // four independent loads in flight per thread
+      s0 += __ldg(src + (long)k * e.split_stride);
+      s1 += __ldg(src + (long)(k + 1) * e.split_stride);
+      s2 += __ldg(src + (long)(k + 2) * e.split_stride);
+      s3 += __ldg(src + (long)(k + 3) * e.split_stride);
+    }
+    for (; k < e.nsplit; ++k) s0 += __ldg(src + (long)k * e.split_stride);
+    e.dw[dst] += (s0 + s1) + (s2 + s3);
   }
 }
 
@@ -592,7 +601,10 @@ extern "C" int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h
 
 extern "C" int dbm_flat_wgrad_reduce(const void* entries_dev, int count, cudaStream_t stream) {
   DBM_REQUIRE(entries_dev && count > 0, "flat_wgrad_reduce: empty table");
-  flat_wgrad_reduce_kernel<<<count, 256, 0, stream>>>((const WgradReduce*)entries_dev);
+  // >= 4 blocks per SM in total, at most one block per 256 outputs of the widest entry (9 x 32 x 128)
+  int slices = ceil_div(4L * num_sms(), count);
+  if (slices > 144) slices = 144;
+  flat_wgrad_reduce_kernel<<<dim3(count, slices), 256, 0, stream>>>((const WgradReduce*)entries_dev);
   return check_launch("flat_wgrad_reduce_kernel");
 }
 
