@@ -11,7 +11,7 @@ def __getattr__(name):  # lazy: importing the package must not require a GPU
         from . import model
         return getattr(model, name)
     if name in ("compile_srgan_model", "train_eval_discriminator", "train_eval_generator", "trainer", "Adam",
-                "ArrayIterator"):
+                "ArrayIterator", "DeviceArrayIterator", "save_model_weights_and_architecture"):
         from . import train
         return getattr(train, name)
     if name in ("predict_continent", "tile_plan", "ContinentGrids"):

@@ -62,6 +62,8 @@ SIGNATURES = {
     "dbm_adam_step_f32": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
     "dbm_crop_clip_f32": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "dbm_place_tile_f32": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dbm_f32_to_i16": [_P, _P, _L, _P],
+    "dbm_gather_rows_f32": [_P, _L, _P, _P, _L, _I, _P],
 }
 
 _lib: Optional[ctypes.CDLL] = None

@@ -209,6 +209,38 @@ __global__ void place_tile_kernel(const float* __restrict__ tile, int th, int tw
 __global__ void fill_kernel(float* __restrict__ p, float v, long n) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v;
 }
+// Y_hat.astype(np.int16) (deepbedmap.py:751) as NumPy's C cast does it on x86-64: truncate toward zero to a
+// 32-bit integer (NaN / |v| >= 2^31 give INT_MIN) and keep the low 16 bits. Four values per thread.
+__device__ __forceinline__ short f32_to_i16_numpy(float v) {
+  const int i = (v != v || v >= 2147483648.0f || v < -2147483648.0f) ? (int)0x80000000 : (int)v;
+  return (short)(i & 0xffff);
+}
+__global__ void f32_to_i16_kernel(const float* __restrict__ src, short* __restrict__ dst, long n) {
+  const long n4 = n >> 2;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    short4 o;
+    o.x = f32_to_i16_numpy(v.x), o.y = f32_to_i16_numpy(v.y), o.z = f32_to_i16_numpy(v.z), o.w = f32_to_i16_numpy(v.w);
+    reinterpret_cast<short4*>(dst)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n4 << 2) + threadIdx.x] = f32_to_i16_numpy(src[(n4 << 2) + threadIdx.x]);
+}
+// batch[j] = dataset[index[j]] for rows of `row` floats (on-device minibatch gather, srgan_train.py:132-166)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const long* __restrict__ index, float* __restrict__ dst,
+                                   long row, int nrows, long src_rows) {
+  for (int j = blockIdx.y; j < nrows; j += gridDim.y) {
+    const long r = index[j];
+    if (r < 0 || r >= src_rows) continue;  // validated on the host; never write from a bad row
+    const float* s = src + r * row;
+    float* d = dst + (long)j * row;
+    if ((row & 3) == 0) {
+      for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (row >> 2); i += (long)gridDim.x * blockDim.x)
+        reinterpret_cast<float4*>(d)[i] = reinterpret_cast<const float4*>(s)[i];
+    } else {
+      for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < row; i += (long)gridDim.x * blockDim.x) d[i] = s[i];
+    }
+  }
+}
 
 }  // namespace dbm
 
@@ -300,4 +332,20 @@ extern "C" int dbm_fill_f32(float* p, float v, long n, cudaStream_t st) {
   if (n <= 0) return DBM_OK;
   fill_kernel<<<ew_grid(n), 256, 0, st>>>(p, v, n);
   return check_launch("fill");
+}
+extern "C" int dbm_f32_to_i16(const float* src, void* dst, long n, cudaStream_t st) {
+  if (n <= 0) return DBM_OK;
+  DBM_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "f32_to_i16: buffers must be 16/8-byte aligned");
+  f32_to_i16_kernel<<<ew_grid((n + 3) / 4), 256, 0, st>>>(src, (short*)dst, n);
+  return check_launch("f32_to_i16");
+}
+extern "C" int dbm_gather_rows_f32(const float* src, long src_rows, const long* index_dev, float* dst, long row,
+                                   int nrows, cudaStream_t st) {
+  if (nrows <= 0 || row <= 0) return DBM_OK;
+  DBM_REQUIRE(src_rows > 0, "gather_rows: empty dataset");
+  DBM_REQUIRE((row & 3) != 0 || ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0), "gather_rows: buffers must be 16-byte aligned");
+  const int bx = (int)((((row & 3) ? row : (row >> 2)) + 255) / 256);
+  gather_rows_kernel<<<dim3(bx < 64 ? (bx < 1 ? 1 : bx) : 64, nrows < 65535 ? nrows : 65535), 256, 0, st>>>(
+      src, index_dev, dst, row, nrows, src_rows);
+  return check_launch("gather_rows");
 }

@@ -176,11 +176,16 @@ class StreamedGrids(ContinentGrids):
 
 def predict_continent(model, X, W1, W2, W3, final_shape=(18000, 22000), ary_shape=(1000, 1000),
                       stride=(1000, 1000), xtrapad=(18, 18), batch_tiles: int = 4, to_host: bool = True,
-                      grids: Optional[ContinentGrids] = None, out: Optional[torch.Tensor] = None):
+                      grids: Optional[ContinentGrids] = None, out: Optional[torch.Tensor] = None,
+                      out_dtype: str = "float32"):
     """Returns Y_hat (1, final_y, final_x) float32 (NumPy if ``to_host`` else a CUDA tensor), NaN
     where the reference leaves NaN. On ranks != 0 of a distributed run returns None.
     ``out``: optional pinned host tensor (1, final_y, final_x) to receive the result without a
-    pageable staging copy."""
+    pageable staging copy.
+    ``out_dtype="int16"`` returns ``Y_hat.astype(np.int16)`` -- what the reference writes to the GeoTIFF
+    (deepbedmap.py:751) -- converted on the device, which halves the device->host read."""
+    if out_dtype not in ("float32", "int16"):
+        raise ValueError("out_dtype must be 'float32' or 'int16'")
     from . import ops
     dist, rank, world = _dist()
     plan = tile_plan(final_shape, ary_shape, stride, xtrapad)
@@ -258,11 +263,15 @@ def predict_continent(model, X, W1, W2, W3, final_shape=(18000, 22000), ary_shap
         if canvas is None:
             return None
     res = canvas.view(1, final_shape[0], final_shape[1])
+    if out_dtype == "int16":
+        res16 = torch.empty(res.shape, dtype=torch.int16, device=res.device)
+        ops.call("dbm_f32_to_i16", res.data_ptr(), res16.data_ptr(), res.numel(), st())
+        res = res16
     if not to_host:
         return res
     if out is not None:
-        if tuple(out.shape) != tuple(res.shape) or out.dtype != torch.float32 or out.is_cuda:
-            raise ValueError("out must be a host float32 tensor of shape (1, final_y, final_x)")
+        if tuple(out.shape) != tuple(res.shape) or out.dtype != res.dtype or out.is_cuda:
+            raise ValueError(f"out must be a host {out_dtype} tensor of shape (1, final_y, final_x)")
         out.copy_(res, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out.numpy()

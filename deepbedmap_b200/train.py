@@ -43,6 +43,38 @@ class Adam:
                  float(grad_scale), ops.stream())
         link.mark_updated()
 
+    # -- optimizer-state checkpoint (extension: the reference saves weights only, srgan_train.py:1355-1361;
+    #    SURVEY 8f N3). Keys follow chainer.serializers.save_npz(optimizer): 't', '<param path>/m', '<param path>/v'.
+    def state_dict(self) -> Dict[str, np.ndarray]:
+        link = self.target
+        m, v = self.m.cpu().numpy(), self.v.cpu().numpy()
+        out = {"t": np.asarray(self.t, np.int64), "alpha": np.asarray(self.alpha, np.float64)}
+        for k, (o, n) in link._slices.items():
+            out[f"{k}/m"] = m[o:o + n].reshape(link._shapes[k])
+            out[f"{k}/v"] = v[o:o + n].reshape(link._shapes[k])
+        return out
+
+    def load_state_dict(self, state) -> None:
+        link = self.target
+        m = np.empty(link.flat.numel(), np.float32)
+        v = np.empty(link.flat.numel(), np.float32)
+        for k, (o, n) in link._slices.items():
+            for name, buf in (("m", m), ("v", v)):
+                a = np.asarray(state[f"{k}/{name}"], np.float32)
+                if tuple(a.shape) != tuple(link._shapes[k]):
+                    raise ValueError(f"{k}/{name}: shape {a.shape} != {link._shapes[k]}")
+                buf[o:o + n] = a.reshape(-1)
+        self.m.copy_(torch.from_numpy(m))
+        self.v.copy_(torch.from_numpy(v))
+        self.t = int(state["t"])
+
+    def save_npz(self, file, compression: bool = True) -> None:
+        (np.savez_compressed if compression else np.savez)(file, **self.state_dict())
+
+    def load_npz(self, file) -> None:
+        with np.load(file) as f:
+            self.load_state_dict({k: f[k] for k in f.files})
+
 
 _COMM_STREAM = None
 
@@ -260,3 +292,76 @@ class ArrayIterator:
             self._pos = 0
             self._order = self._new_order()
         return {k: v[idx] for k, v in self.arrays.items()}
+
+
+class DeviceArrayIterator:
+    """On-device minibatch iterator: the whole training set (3826 tiles x 58.4 KB = 235 MB with Y,
+    srgan_train.py:132-166) is uploaded once; ``next()`` gathers a shuffled batch with one
+    ``dbm_gather_rows_f32`` launch per array, so a step does no host-side array work. Same epoch counting
+    and (for the same seed) the same sample order as ``ArrayIterator``."""
+
+    def __init__(self, arrays: Dict[str, object], batch_size: int, shuffle: bool = True, seed: int = 42):
+        self.arrays = {k: as_device(v).contiguous() for k, v in arrays.items()}
+        lens = {int(v.shape[0]) for v in self.arrays.values()}
+        if len(lens) != 1:
+            raise ValueError(f"arrays differ in length: {sorted(lens)}")
+        self.n = lens.pop()
+        if self.n == 0:
+            raise ValueError("empty dataset")
+        self.batch_size = int(batch_size)
+        self.rng = np.random.RandomState(seed)
+        self.shuffle = shuffle
+        self.epoch = 0
+        self._pos = 0
+        self._order = self._new_order()
+
+    def _new_order(self):
+        order = self.rng.permutation(self.n) if self.shuffle else np.arange(self.n)
+        return torch.from_numpy(order.astype(np.int64)).cuda()   # one small upload per epoch
+
+    def next(self):
+        idx = self._order[self._pos:self._pos + self.batch_size]
+        nb = int(idx.numel())
+        out = {}
+        for k, v in self.arrays.items():
+            row = int(v[0].numel())
+            dst = ops.empty(nb, *v.shape[1:])
+            ops.call("dbm_gather_rows_f32", v.data_ptr(), self.n, idx.data_ptr(), dst.data_ptr(), row, nb, ops.stream())
+            out[k] = dst
+        self._pos += self.batch_size
+        if self._pos >= self.n:
+            self.epoch += 1
+            self._pos = 0
+            self._order = self._new_order()
+        return out
+
+
+def save_model_weights_and_architecture(generator_model, discriminator_model, save_path: str = "model/weights"):
+    """srgan_train.py:1333-1383: writes srgan_generator_model_weights.npz and
+    srgan_discriminator_model_weights.npz (Chainer key layout, loadable by chainer.serializers.load_npz) and
+    srgan_generator_model_architecture.dot. Chainer dumps its autograd graph; there is no autograd graph here, so
+    the .dot file lists the generator's layer chain (one node per parametrised layer, in forward order)."""
+    import os
+    os.makedirs(save_path, exist_ok=True)
+    g_path = os.path.join(save_path, "srgan_generator_model_weights.npz")
+    d_path = os.path.join(save_path, "srgan_discriminator_model_weights.npz")
+    a_path = os.path.join(save_path, "srgan_generator_model_architecture.dot")
+    generator_model.save_npz(g_path)
+    discriminator_model.save_npz(d_path)
+    layers = []
+    for k, shp in generator_model._shapes.items():
+        if k.endswith("/W"):
+            layers.append((k[:-2], tuple(shp)))
+    with open(a_path, "w") as fh:
+        fh.write("digraph generator {\n  rankdir=TB;\n")
+        for i, (name, shp) in enumerate(layers):
+            fh.write(f'  n{i} [shape=box, label="{name}\\nW{list(shp)}"];\n')
+        stem = [i for i, (nm, _) in enumerate(layers) if nm.startswith("input_block/")]
+        body = [i for i in range(len(layers)) if i not in stem]
+        for i in stem:
+            if body:
+                fh.write(f"  n{i} -> n{body[0]};\n")
+        for a, b in zip(body[:-1], body[1:]):
+            fh.write(f"  n{a} -> n{b};\n")
+        fh.write("}\n")
+    return g_path, d_path, a_path

@@ -227,6 +227,15 @@ int dbm_crop_clip_f32(const float* src, int hs, int ws, float* dst, int c, int y
 int dbm_place_tile_f32(const float* tile, int th, int tw, int cy, int cx, float* canvas, int ch, int cw, int ys,
                        int xs, int hh, int ww, cudaStream_t stream);
 
+/* Y_hat.astype(np.int16) on the device (deepbedmap.py:751): C-cast semantics of NumPy on x86-64
+ * (truncate toward zero to int32, NaN / out-of-range -> INT_MIN, keep the low 16 bits: NaN -> 0). */
+int dbm_f32_to_i16(const float* src, void* dst_i16, long n, cudaStream_t stream);
+
+/* ---- on-device minibatch assembly (chainer SerialIterator + concat_examples, srgan_train.py:132-166):
+ * dst[j, :] = src[index[j], :] for j < nrows; rows of `row` floats; index = int64 on the device. */
+int dbm_gather_rows_f32(const float* src, long src_rows, const long* index_dev, float* dst, long row, int nrows,
+                        cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

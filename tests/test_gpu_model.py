@@ -270,3 +270,83 @@ def test_tiled_predictor_matches_oracle_tiler():
     assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.isnan(ref).any()
     ok = ~np.isnan(ref)
     assert rel_l2(got[ok], ref[ok]) < 2e-5
+
+
+def test_int16_dem_matches_numpy_astype():
+    """the DEM the reference ships is Y_hat.astype(np.int16) (deepbedmap.py:751); bit-exact."""
+    from deepbedmap_b200 import ops, predict_continent
+    import warnings
+    rng = np.random.RandomState(3)
+    v = np.concatenate([rng.randn(100003).astype(np.float32) * 3000, np.float32(
+        [np.nan, 0.0, -0.0, 0.99, -0.99, 32767.9, -32768.9, 40000.5, -70000.25, 3e9, -3e9, np.inf, -np.inf, 1e20])])
+    pad = (-len(v)) % 4
+    src = torch.from_numpy(v).cuda()
+    dst = torch.empty(len(v), dtype=torch.int16, device="cuda")
+    ops.call("dbm_f32_to_i16", src.data_ptr(), dst.data_ptr(), len(v), ops.stream())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = v.astype(np.int32).astype(np.int16)   # NumPy 1.17's direct C cast on x86-64 == via int32
+    assert pad != 0 and np.array_equal(dst.cpu().numpy(), want)
+    assert want[100003] == 0                         # NaN frame -> 0
+    m, _ = make_generator(1, "fp32")
+    final, ary, padt = (80, 120), (40, 40), (3, 3)
+    H, W = 22, 32
+    X, W3 = rng.rand(1, 1, H, W).astype(np.float32) * 900 - 400, rng.rand(1, 1, H, W).astype(np.float32)
+    W1, W2 = rng.rand(1, 1, 10 * H, 10 * W).astype(np.float32), rng.rand(1, 2, 2 * H, 2 * W).astype(np.float32)
+    kw = dict(final_shape=final, ary_shape=ary, stride=ary, xtrapad=padt, batch_tiles=3)
+    f32 = predict_continent(m, X, W1, W2, W3, **kw)
+    i16 = predict_continent(m, X, W1, W2, W3, out_dtype="int16", **kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert i16.dtype == np.int16 and np.array_equal(i16, f32.astype(np.int32).astype(np.int16))
+    with pytest.raises(ValueError):
+        predict_continent(m, X, W1, W2, W3, out_dtype="int8", **kw)
+
+
+def test_device_iterator_matches_host_iterator():
+    """on-device shuffled batches == the host SerialIterator stand-in, incl. the ragged last batch."""
+    from deepbedmap_b200.train import ArrayIterator, DeviceArrayIterator
+    rng = np.random.RandomState(0)
+    n = 37
+    arrays = {"X": rng.rand(n, 1, 11, 11).astype(np.float32), "W1": rng.rand(n, 1, 110, 110).astype(np.float32),
+              "W2": rng.rand(n, 2, 22, 22).astype(np.float32), "Y": rng.rand(n, 1, 36, 36).astype(np.float32),
+              "odd": rng.rand(n, 3).astype(np.float32)}
+    for shuffle in (True, False):
+        a, b = ArrayIterator(arrays, 8, shuffle=shuffle, seed=7), DeviceArrayIterator(arrays, 8, shuffle=shuffle, seed=7)
+        for _ in range(11):                      # crosses two epoch boundaries
+            x, y = a.next(), b.next()
+            assert a.epoch == b.epoch
+            for k in arrays:
+                assert y[k].is_cuda and np.array_equal(x[k], y[k].cpu().numpy()), k
+    with pytest.raises(ValueError):
+        DeviceArrayIterator({"X": arrays["X"], "Y": arrays["Y"][:5]}, 8)
+
+
+def test_weights_and_optimizer_checkpoint(tmp_path):
+    """srgan_train.py:1333-1383 (files + key layout) and the Adam-state extension: a restored
+    (weights, optimizer) pair continues like the original (to fp32 atomic-accumulation-order noise)."""
+    from deepbedmap_b200 import train as T
+    g, g_opt, d, d_opt = T.compile_srgan_model(num_residual_blocks=1)
+    rng = np.random.RandomState(1)
+    arrays = {"X": rng.rand(4, 1, 11, 11).astype(np.float32), "W1": rng.rand(4, 1, 110, 110).astype(np.float32),
+              "W2": rng.rand(4, 2, 22, 22).astype(np.float32), "W3": rng.rand(4, 1, 11, 11).astype(np.float32),
+              "Y": rng.rand(4, 1, 36, 36).astype(np.float32)}
+    T.train_eval_discriminator(arrays, g, d, d_opt)
+    T.train_eval_generator(arrays, g, d, g_opt)
+    gp, dp, ap = T.save_model_weights_and_architecture(g, d, save_path=str(tmp_path / "weights"))
+    import os
+    assert os.path.basename(gp) == "srgan_generator_model_weights.npz" and os.path.exists(dp)
+    assert open(ap).read().startswith("digraph") and "final_conv_layer2" in open(ap).read()
+    with np.load(gp) as z:
+        assert len(z.files) == 2 * (4 + 1 + 15 + 1 + 2 + 4)       # W+b of every conv at 1 RRDB
+    g_opt.save_npz(tmp_path / "g_opt.npz")
+    d_opt.save_npz(tmp_path / "d_opt.npz")
+    g2, g2_opt, d2, d2_opt = T.compile_srgan_model(num_residual_blocks=1, seed=99)
+    g2.load_npz(gp), d2.load_npz(dp)
+    g2_opt.load_npz(tmp_path / "g_opt.npz"), d2_opt.load_npz(tmp_path / "d_opt.npz")
+    assert g2_opt.t == 1 and torch.equal(g2_opt.m, g_opt.m) and torch.equal(d2_opt.v, d_opt.v)
+    r1 = T.train_eval_discriminator(arrays, g, d, d_opt) + T.train_eval_generator(arrays, g, d, g_opt)
+    r2 = T.train_eval_discriminator(arrays, g2, d2, d2_opt) + T.train_eval_generator(arrays, g2, d2, g2_opt)
+    assert np.allclose(r1, r2, rtol=1e-4, atol=1e-6), (r1, r2)
+    assert rel_l2(g2.flat.cpu().numpy(), g.flat.cpu().numpy()) < 1e-5
+    assert rel_l2(d2.flat.cpu().numpy(), d.flat.cpu().numpy()) < 1e-5
