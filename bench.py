@@ -235,28 +235,34 @@ def instrumented_roofline(model, grids, kw, peak_tf):
                 "frac": v["tflops"] / peak_tf} for k, v in out.items()}}
 
 
-def train_bench(rank, world, steps=3, warmup=2, batch=128):
+def train_bench(rank, world, steps=20, warmup=3, batch=128):
     from deepbedmap_b200 import train as T
     g, g_opt, d, d_opt = T.compile_srgan_model()
     gen = torch.Generator(device="cuda").manual_seed(42 + rank)
     r = lambda *s: torch.rand(*s, generator=gen, device="cuda")
     arrays = {"X": r(batch, 1, 11, 11), "W1": r(batch, 1, 110, 110), "W2": r(batch, 2, 22, 22), "W3": r(batch, 1, 11, 11),
               "Y": r(batch, 1, 36, 36)}
-    for _ in range(warmup):
-        T.train_eval_discriminator(arrays, g, d, d_opt)
+    # the per-minibatch body of trainer() (srgan_train.py:1286-1308): both steps on the same device batch,
+    # the generator step reusing the graph-keeping forward the discriminator step ran (weights unchanged between)
+    def step():
+        T.train_eval_discriminator(arrays, g, d, d_opt, share_generator_forward=True)
         T.train_eval_generator(arrays, g, d, g_opt)
+    for _ in range(warmup):
+        step()
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        T.train_eval_discriminator(arrays, g, d, d_opt)
-        T.train_eval_generator(arrays, g, d, g_opt)
+        step()
     e1.record()
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     return {"metric": "train steps/s (D-step + G-step, batch 128 per GPU)", "value": steps / (ms * 1e-3),
             "unit": "steps/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "scaling": "weak",
-            "global_batch": batch * world, "dtype": "f32 backward / f32 forward (bf16 tcgen05 generator in the D-step)",
+            "global_batch": batch * world, "dtype": "bf16 tcgen05 operands / fp32 accumulation for every 3x3 conv of G and D (fwd, dgrad, wgrad); "
+                                               "fp32 stem, deformable layers, BN, losses, Adam",
+            "generator_forward": "one per step, shared by the D-step and the G-step (the reference runs it twice "
+                                 "with unchanged weights; SURVEY 8d counts it once)",
             "allreduce": "bucketed, launched from inside backward (NCCL, overlapped)" if world > 1 else "none (1 GPU)"}
 
 

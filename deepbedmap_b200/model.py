@@ -213,7 +213,22 @@ class GeneratorModel(_Link):
         (flat.py / csrc/umma_flat.cu) and in fp32 otherwise."""
         x, w1, w2, w3 = (as_device(a) for a in (x, w1, w2, w3))
         self._check_shapes(x, w1, w2, w3)
-        return Variable(self._forward_fp32(x, w1, w2, w3, save=True))
+        y = self._forward_fp32(x, w1, w2, w3, save=True)
+        # lets the generator step pick up the graph the discriminator step built from the same batch
+        # (train.train_eval_discriminator(share_generator_forward=True)); the context keeps the inputs alive,
+        # so equal pointers + equal weight version identify the same forward
+        self._ctx["y"] = y
+        self._ctx["key"] = (self.version,) + tuple((t.data_ptr(), tuple(t.shape)) for t in (x, w1, w2, w3))
+        return Variable(y)
+
+    def shared_forward(self, x, w1, w2, w3) -> Optional[torch.Tensor]:
+        """Output of a preceding ``forward_train`` on exactly these device tensors with the current weights
+        (its saved activations are still in place for ``backward``), else None."""
+        c = self._ctx
+        if c is None or "key" not in c or not all(isinstance(t, torch.Tensor) and t.is_cuda for t in (x, w1, w2, w3)):
+            return None
+        key = (self.version,) + tuple((t.data_ptr(), tuple(t.shape)) for t in (x, w1, w2, w3))
+        return c["y"] if key == c["key"] else None
 
     @staticmethod
     def _check_shapes(x, w1, w2, w3):

@@ -163,12 +163,23 @@ def _ragan(real_pred, fake_pred, t_rmf, t_fmr, want_grads, grad_scale=1.0):
 
 
 def train_eval_discriminator(input_arrays: Dict[str, object], g_model: GeneratorModel, d_model: DiscriminatorModel,
-                             d_optimizer: Optional[Adam] = None, train: bool = True):
-    """srgan_train.py:1084-1166 -> (d_loss, d_accu)."""
+                             d_optimizer: Optional[Adam] = None, train: bool = True,
+                             share_generator_forward: bool = False):
+    """srgan_train.py:1084-1166 -> (d_loss, d_accu).
+
+    ``share_generator_forward`` (used by ``trainer``): the reference runs G(x) here without a graph (:1131-1137)
+    and again with one in the generator step (:1222-1227) although G's weights do not change in between. With
+    the flag set, this step runs the graph-keeping forward once and ``train_eval_generator`` called next on the
+    SAME device arrays reuses its output and saved activations (``GeneratorModel.shared_forward``) -- the same
+    values the second forward would produce, one generator forward less per step."""
     if train:
         assert d_optimizer is not None  # :1127
-    fake = g_model.forward(x=input_arrays["X"], w1=input_arrays["W1"], w2=input_arrays["W2"],
-                           w3=input_arrays["W3"]).array                         # :1131-1137 (no graph)
+    if train and share_generator_forward:
+        fake = g_model.forward_train(input_arrays["X"], input_arrays["W1"], input_arrays["W2"],
+                                     input_arrays["W3"]).array
+    else:
+        fake = g_model.forward(x=input_arrays["X"], w1=input_arrays["W1"], w2=input_arrays["W2"],
+                               w3=input_arrays["W3"]).array                     # :1131-1137 (no graph)
     real = as_device(input_arrays["Y"])
     if train:
         d_model.cleargrads()                                                       # :1162
@@ -199,7 +210,9 @@ def train_eval_generator(input_arrays: Dict[str, object], g_model: GeneratorMode
         assert g_optimizer is not None  # :1218
     X = as_device(input_arrays["X"])
     if train:
-        fake = g_model.forward_train(X, input_arrays["W1"], input_arrays["W2"], input_arrays["W3"]).array
+        fake = g_model.shared_forward(X, input_arrays["W1"], input_arrays["W2"], input_arrays["W3"])
+        if fake is None:
+            fake = g_model.forward_train(X, input_arrays["W1"], input_arrays["W2"], input_arrays["W3"]).array
     else:
         fake = g_model.forward(X, input_arrays["W1"], input_arrays["W2"], input_arrays["W3"]).array
     # eval-mode BatchNorm and `.array`: the adversarial term carries no gradient (:1228-1229)
@@ -247,8 +260,9 @@ def trainer(i: int, columns: list, train_iter, dev_iter, g_model, g_optimizer, d
     ``.next()`` returning a dict of batched arrays {X, W1, W2, W3, Y}."""
     metrics = {mn: [] for mn in columns}
     while i == train_iter.epoch:
-        arrays = train_iter.next()
-        dl, da = train_eval_discriminator(arrays, g_model, d_model, d_optimizer)
+        # one device copy of the batch for both steps, so the generator step can reuse the forward of the first
+        arrays = {k: as_device(v) for k, v in train_iter.next().items()}
+        dl, da = train_eval_discriminator(arrays, g_model, d_model, d_optimizer, share_generator_forward=True)
         metrics["discriminator_loss"].append(dl)
         metrics["discriminator_accu"].append(da)
         gl, gp, gs = train_eval_generator(arrays, g_model, d_model, g_optimizer)
