@@ -55,6 +55,8 @@ SIGNATURES = {
     "dbm_conv3x3_umma": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P, _P],
     "dbm_deform_sample_f32": [_P, _P, _P, _I, _I, _I, _I, _P],
     "dbm_deform_bwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dbm_deform1_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dbm_deform1_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "dbm_bn_lrelu_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
     "dbm_bn_lrelu_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dbm_ragan_loss_f32": [_P, _P, _I, _F, _F, _F, _P, _P, _P, _P],

@@ -99,6 +99,153 @@ __global__ void deform_bwd_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+
+// ---- single-output deformable layer (final_conv_layer2, 64 -> 1; srgan_train.py:515-523, 574) -------------
+// With one output channel the contraction commutes with the bilinear sampler:
+//   y[p] = b + sum_t bilin(z_t, pos_t(p)),   z_t[q] = sum_c W[0,c,t] x[c][q]   ("tap projection"),
+// so the layer samples 9 projected planes instead of 64 x 9 input planes (64x fewer gathers, no cols buffer),
+// and its backward is the transpose: scatter dy into dz_t, then dx[c] = sum_t W[c,t] dz_t and
+// dW[c,t] = sum_q x[c][q] dz_t[q]. Only fp32 sums are re-associated.
+__global__ void __launch_bounds__(256) deform1_project_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              float* __restrict__ proj, int N, int C, int HW) {
+  extern __shared__ float sw[];  // [C][9]
+  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long total = (long)N * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / HW, px = i - n * HW;
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    const float* xp = x + n * C * HW + px;
+    for (int c = 0; c < C; ++c) {
+      const float v = __ldg(xp + (long)c * HW);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[t] = fmaf(v, sw[c * 9 + t], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) proj[(n * 9 + t) * HW + px] = acc[t];
+  }
+}
+
+__global__ void __launch_bounds__(256) deform1_sample_kernel(const float* __restrict__ proj, const float* __restrict__ off,
+                                                             const float* __restrict__ bias, float* __restrict__ y,
+                                                             int N, int H, int W) {
+  const int HW = H * W;
+  const long total = (long)N * HW;
+  const float b0 = bias ? bias[0] : 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int n = i / HW, p = i - (long)n * HW;
+    const int yy = p / W, xx = p - yy * W;
+    float acc = b0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const Bilin b = tap_position(off, (long)n * 18 * HW, HW, p, t, yy, xx, H, W);
+      const float* img = proj + ((long)n * 9 + t) * HW;
+      acc += (1.f - b.fy) * ((1.f - b.fx) * at(img, b.y0, b.x0, H, W) + b.fx * at(img, b.y0, b.x0 + 1, H, W)) +
+             b.fy * ((1.f - b.fx) * at(img, b.y0 + 1, b.x0, H, W) + b.fx * at(img, b.y0 + 1, b.x0 + 1, H, W));
+    }
+    y[i] = acc;
+  }
+}
+
+// dproj[n][t] += scatter of dy (atomics; dproj zeroed by the caller); doff[n][t | 9+t][p] = d/d(position)
+__global__ void __launch_bounds__(256) deform1_bwd_scatter_kernel(const float* __restrict__ proj,
+                                                                  const float* __restrict__ off,
+                                                                  const float* __restrict__ dy, float* __restrict__ dproj,
+                                                                  float* __restrict__ doff, int N, int H, int W) {
+  const int HW = H * W;
+  const long total = (long)N * 9 * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int p = i % HW;
+    const long r = i / HW;
+    const int t = r % 9;
+    const int n = r / 9;
+    const int y = p / W, xx = p - y * W;
+    const Bilin b = tap_position(off, (long)n * 18 * HW, HW, p, t, y, xx, H, W);
+    const float g = dy[(long)n * HW + p];
+    const long plane = ((long)n * 9 + t) * HW;
+    const float* img = proj + plane;
+    const bool v00 = b.y0 >= 0 && b.y0 < H && b.x0 >= 0 && b.x0 < W;
+    const bool v01 = b.y0 >= 0 && b.y0 < H && b.x0 + 1 >= 0 && b.x0 + 1 < W;
+    const bool v10 = b.y0 + 1 >= 0 && b.y0 + 1 < H && b.x0 >= 0 && b.x0 < W;
+    const bool v11 = b.y0 + 1 >= 0 && b.y0 + 1 < H && b.x0 + 1 >= 0 && b.x0 + 1 < W;
+    const float a00 = v00 ? __ldg(img + (long)b.y0 * W + b.x0) : 0.f;
+    const float a01 = v01 ? __ldg(img + (long)b.y0 * W + b.x0 + 1) : 0.f;
+    const float a10 = v10 ? __ldg(img + (long)(b.y0 + 1) * W + b.x0) : 0.f;
+    const float a11 = v11 ? __ldg(img + (long)(b.y0 + 1) * W + b.x0 + 1) : 0.f;
+    float gpx = g * ((1.f - b.fy) * (a01 - a00) + b.fy * (a11 - a10));
+    float gpy = g * ((1.f - b.fx) * (a10 - a00) + b.fx * (a11 - a01));
+    if (!b.in_range) { gpx = 0.f; gpy = 0.f; }
+    doff[(long)n * 18 * HW + (long)t * HW + p] = gpx;
+    doff[(long)n * 18 * HW + (long)(9 + t) * HW + p] = gpy;
+    float* d = dproj + plane;
+    if (v00) atomicAdd(d + (long)b.y0 * W + b.x0, g * (1.f - b.fy) * (1.f - b.fx));
+    if (v01) atomicAdd(d + (long)b.y0 * W + b.x0 + 1, g * (1.f - b.fy) * b.fx);
+    if (v10) atomicAdd(d + (long)(b.y0 + 1) * W + b.x0, g * b.fy * (1.f - b.fx));
+    if (v11) atomicAdd(d + (long)(b.y0 + 1) * W + b.x0 + 1, g * b.fy * b.fx);
+  }
+}
+
+// dx[n][c][q] (+)= sum_t W[c,t] dproj[n][t][q]
+__global__ void __launch_bounds__(256) deform1_bwd_data_kernel(const float* __restrict__ dproj, const float* __restrict__ w,
+                                                               float* __restrict__ dx, int N, int C, int HW,
+                                                               int accumulate) {
+  extern __shared__ float sw[];  // [C][9]
+  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long total = (long)N * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / HW, px = i - n * HW;
+    float dz[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) dz[t] = __ldg(dproj + (n * 9 + t) * HW + px);
+    float* dp = dx + n * C * HW + px;
+    for (int c = 0; c < C; ++c) {
+      float v = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) v = fmaf(dz[t], sw[c * 9 + t], v);
+      if (accumulate) v += dp[(long)c * HW];
+      dp[(long)c * HW] = v;
+    }
+  }
+}
+
+// dW[c][t] += sum_{n,q} x[n][c][q] dproj[n][t][q]: grid (C, image chunks), one atomicAdd per block and tap
+__global__ void __launch_bounds__(256) deform1_bwd_weight_kernel(const float* __restrict__ x,
+                                                                 const float* __restrict__ dproj, float* __restrict__ dw,
+                                                                 int N, int C, int HW) {
+  const int c = blockIdx.x;
+  const int per = (N + gridDim.y - 1) / gridDim.y;
+  const int n0 = blockIdx.y * per, n1 = min(N, n0 + per);
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  for (int n = n0; n < n1; ++n) {
+    const float* xp = x + ((long)n * C + c) * HW;
+    const float* dz = dproj + (long)n * 9 * HW;
+    for (int q = threadIdx.x; q < HW; q += blockDim.x) {
+      const float v = __ldg(xp + q);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[t] = fmaf(v, __ldg(dz + (long)t * HW + q), acc[t]);
+    }
+  }
+  __shared__ float red[9][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float v = acc[t];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[t][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9 && n0 < n1) {
+    float v = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) v += red[threadIdx.x][k];
+    atomicAdd(dw + c * 9 + threadIdx.x, v);
+  }
+}
+
 }  // namespace dbm
 
 using namespace dbm;
@@ -121,4 +268,49 @@ extern "C" int dbm_deform_bwd_f32(const float* x, const float* offset, const flo
   if (blocks > (long)num_sms() * 32) blocks = (long)num_sms() * 32;
   deform_bwd_kernel<<<(int)blocks, 256, 0, st>>>(x, offset, dcols, dx, doffset, n, c, h, w);
   return check_launch("deform_bwd");
+}
+
+static inline int deform1_blocks(long total) {
+  long blocks = (total + 255) / 256;
+  if (blocks > (long)num_sms() * 16) blocks = (long)num_sms() * 16;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+extern "C" int dbm_deform1_fwd_f32(const float* x, const float* offset, const float* w, const float* bias, float* y,
+                                   float* proj, int n, int c, int h, int wd, cudaStream_t st) {
+  DBM_REQUIRE(n > 0 && c > 0 && h > 0 && wd > 0, "deform1_fwd: empty input");
+  DBM_REQUIRE(c * 9 * sizeof(float) <= 40 * 1024, "deform1_fwd: too many input channels (%d)", c);
+  const long total = (long)n * h * wd;
+  deform1_project_kernel<<<deform1_blocks(total), 256, c * 9 * sizeof(float), st>>>(x, w, proj, n, c, h * wd);
+  int rc = check_launch("deform1_project");
+  if (rc) return rc;
+  deform1_sample_kernel<<<deform1_blocks(total), 256, 0, st>>>(proj, offset, bias, y, n, h, wd);
+  return check_launch("deform1_sample");
+}
+
+extern "C" int dbm_deform1_bwd_f32(const float* x, const float* offset, const float* w, const float* proj,
+                                   const float* dy, float* dw, float* dx, int accumulate_dx, float* doffset,
+                                   float* dproj_scratch, int n, int c, int h, int wd, cudaStream_t st) {
+  DBM_REQUIRE(n > 0 && c > 0 && h > 0 && wd > 0, "deform1_bwd: empty input");
+  DBM_REQUIRE(c * 9 * sizeof(float) <= 40 * 1024, "deform1_bwd: too many input channels (%d)", c);
+  const int hw = h * wd;
+  cudaError_t e = cudaMemsetAsync(dproj_scratch, 0, (size_t)n * 9 * hw * sizeof(float), st);
+  DBM_REQUIRE(e == cudaSuccess, "deform1_bwd: memset failed: %s", cudaGetErrorString(e));
+  deform1_bwd_scatter_kernel<<<deform1_blocks((long)n * 9 * hw), 256, 0, st>>>(proj, offset, dy, dproj_scratch, doffset,
+                                                                              n, h, wd);
+  int rc = check_launch("deform1_bwd_scatter");
+  if (rc) return rc;
+  if (dx) {
+    deform1_bwd_data_kernel<<<deform1_blocks((long)n * hw), 256, c * 9 * sizeof(float), st>>>(dproj_scratch, w, dx, n, c,
+                                                                                             hw, accumulate_dx);
+    rc = check_launch("deform1_bwd_data");
+    if (rc) return rc;
+  }
+  if (dw) {
+    int chunks = (4 * num_sms() + c - 1) / c;
+    if (chunks > n) chunks = n;
+    deform1_bwd_weight_kernel<<<dim3(c, chunks), 256, 0, st>>>(x, dproj_scratch, dw, n, c, hw);
+    rc = check_launch("deform1_bwd_weight");
+  }
+  return rc;
 }

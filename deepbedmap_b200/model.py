@@ -327,8 +327,12 @@ class GeneratorModel(_Link):
         d1, cols1 = ops.deform_conv_fwd(c2, off1, P["final_conv_layer1/deform_conv/W"],
                                         P["final_conv_layer1/deform_conv/b"], act=True)
         off2 = conv("final_conv_layer2/offset_conv", d1, False)
-        y, cols2 = ops.deform_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"],
-                                       P["final_conv_layer2/deform_conv/b"], act=False)
+        if self.out_channels == 1:   # tap projection: 9 projected planes instead of a 576-row cols buffer
+            y, cols2 = ops.deform1_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"],
+                                            P["final_conv_layer2/deform_conv/b"])
+        else:
+            y, cols2 = ops.deform_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"],
+                                           P["final_conv_layer2/deform_conv/b"], act=False)
         if save:
             ctx.update(u1=u1, c1=c1, u2=u2, c2=c2, off1=off1, d1=d1, cols1=cols1, off2=off2, cols2=cols2, head_tc=tc)
             self._ctx = ctx
@@ -393,9 +397,14 @@ class GeneratorModel(_Link):
             ops.conv2d_bwd_data(dz, 0, P[f"{key}/W"], dx, 0, 64, 3, 1, 1)
             return dx
 
-        dd1 = ops.zeros(n, 64, 4 * H, 4 * W)
-        doff2 = ops.deform_conv_bwd(c["d1"], c["off2"], P["final_conv_layer2/deform_conv/W"], c["cols2"], dy,
-                                    G["final_conv_layer2/deform_conv/W"], G["final_conv_layer2/deform_conv/b"], dd1)
+        if self.out_channels == 1:
+            dd1 = ops.empty(n, 64, 4 * H, 4 * W)
+            doff2 = ops.deform1_conv_bwd(c["d1"], c["off2"], P["final_conv_layer2/deform_conv/W"], c["cols2"], dy,
+                                         G["final_conv_layer2/deform_conv/W"], G["final_conv_layer2/deform_conv/b"], dd1)
+        else:
+            dd1 = ops.zeros(n, 64, 4 * H, 4 * W)
+            doff2 = ops.deform_conv_bwd(c["d1"], c["off2"], P["final_conv_layer2/deform_conv/W"], c["cols2"], dy,
+                                        G["final_conv_layer2/deform_conv/W"], G["final_conv_layer2/deform_conv/b"], dd1)
         conv_bwd("final_conv_layer2/offset_conv", c["d1"], doff2, dx_accumulate_into=dd1)
         ops.lrelu_bwd(dd1, 0, c["d1"], 0, dd1, 0, 64)
         # ---- final_conv_layer1 ----

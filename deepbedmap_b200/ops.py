@@ -209,3 +209,28 @@ def deform_conv_bwd(x, offset, w, cols, dy, dw, db, dx):
     call("dbm_deform_bwd_f32", x.data_ptr(), offset.data_ptr(), dcols.data_ptr(),
          dx.data_ptr() if dx is not None else None, doff.data_ptr(), n, c, h, wd, stream())
     return doff
+
+
+def deform1_conv_fwd(x, offset, w, b):
+    """Single-output deformable conv by tap projection: x (N,C,H,W), w (1,C,3,3) -> y (N,1,H,W) and the projected
+    planes (N,9,H,W) kept for backward."""
+    n, c, h, wd = x.shape
+    assert tuple(w.shape) == (1, c, 3, 3)
+    y = empty(n, 1, h, wd)
+    proj = empty(n, 9, h, wd)
+    call("dbm_deform1_fwd_f32", x.data_ptr(), offset.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(),
+         proj.data_ptr(), n, c, h, wd, stream())
+    return y, proj
+
+
+def deform1_conv_bwd(x, offset, w, proj, dy, dw, db, dx, accumulate_dx=False):
+    """Accumulates dw, db; dx = (or +=) d/dx; returns doffset (N,18,H,W)."""
+    n, c, h, wd = x.shape
+    hw = h * wd
+    call("dbm_bias_grad_f32", dy.data_ptr(), hw, db.data_ptr(), n, 1, hw, stream())
+    doff = empty(n, 18, h, wd)
+    scratch = empty(n, 9, h, wd)
+    call("dbm_deform1_bwd_f32", x.data_ptr(), offset.data_ptr(), w.data_ptr(), proj.data_ptr(), dy.data_ptr(),
+         dw.data_ptr(), dx.data_ptr() if dx is not None else None, int(accumulate_dx), doff.data_ptr(),
+         scratch.data_ptr(), n, c, h, wd, stream())
+    return doff

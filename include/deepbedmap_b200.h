@@ -197,6 +197,16 @@ int dbm_deform_sample_f32(const float* x, const float* offset, float* cols, int 
 int dbm_deform_bwd_f32(const float* x, const float* offset, const float* dcols, float* dx, float* doffset, int n,
                        int c, int h, int w, cudaStream_t stream);
 
+/* Single-output deformable layer (final_conv_layer2, 64 -> 1; srgan_train.py:515-523, 574) by tap projection:
+ * proj[n][t] = sum_c W[0,c,t] x[n][c] (kept for backward), y = bias + sum_t bilinear(proj[t], tap position).
+ * Backward: dw (1,C,3,3) accumulated, dx written (or accumulated), doffset (N,18,H,W) written;
+ * dproj_scratch = N*9*H*W floats. */
+int dbm_deform1_fwd_f32(const float* x, const float* offset, const float* w, const float* bias, float* y, float* proj,
+                        int n, int c, int h, int w_, cudaStream_t stream);
+int dbm_deform1_bwd_f32(const float* x, const float* offset, const float* w, const float* proj, const float* dy,
+                        float* dw, float* dx, int accumulate_dx, float* doffset, float* dproj_scratch, int n, int c,
+                        int h, int w_, cudaStream_t stream);
+
 /* ---- discriminator normalisation (L.BatchNormalization + F.leaky_relu, srgan_train.py:636-689) - */
 int dbm_bn_lrelu_fwd_f32(const float* x, float* y, const float* gamma, const float* beta, float* avg_mean,
                          float* avg_var, float* save_mean, float* save_invstd, int n, int c, int hw, float eps,

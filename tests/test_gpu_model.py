@@ -193,8 +193,11 @@ def test_training_step_matches_oracle():
     d0 = d.flat.clone()
     dl, da = T.train_eval_discriminator(arrays, g, d, d_opt)
     assert abs(dl - dl_ref) < 1e-4 * max(1, abs(dl_ref)) and abs(da - da_ref) < 1e-6
-    for k in ("conv_layer0/W", "conv_layer5/W", "batch_norm3/gamma", "batch_norm9/beta", "linear_1/W", "linear_2/b"):
+    for k in ("conv_layer0/W", "conv_layer5/W", "batch_norm3/gamma", "batch_norm9/beta", "linear_1/W"):
         assert rel_l2(d.g[k].cpu().numpy(), dgrads[k].numpy()) < 2e-3, k
+    # a bias shared by D(real) and D(fake) cancels in the relativistic loss: the exact gradient is 0 and the
+    # fp32 sum (atomic accumulation order) leaves rounding residue only
+    assert abs(float(dgrads["linear_2/b"])) < 1e-12 and abs(float(d.g["linear_2/b"])) < 1e-6
     for k in ("conv_layer0/W", "conv_layer9/W", "linear_2/W"):
         # the first Adam step is ~ alpha * sign(g): compare element-wise and allow the rare
         # sign flip of a gradient that is zero to within rounding

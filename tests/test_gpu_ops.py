@@ -251,6 +251,33 @@ def test_deform_conv_fwd_bwd(ops):
     assert rel_l2(doff, goff) < 5e-5
 
 
+@pytest.mark.parametrize("n,c,h,w", [(2, 6, 9, 11), (3, 64, 36, 36), (1, 64, 20, 52)])
+def test_deform1_tap_projection_fwd_bwd(ops, n, c, h, w):
+    """Single-output deformable layer by tap projection (final_conv_layer2) vs the oracle and its autograd."""
+    from oracle import deepbedmap_oracle as O
+    x = rnd(n, c, h, w, seed=1)
+    off = rnd(n, 18, h, w, seed=2, scale=1.5)
+    off[0, :, 0, 0] = 40.0   # far outside: clamped, zero value and zero offset-gradient
+    off[0, :9, 1, 1] = -3.25  # samples straddling the left border
+    wt = rnd(1, c, 3, 3, seed=3, scale=0.3)
+    b = rnd(1, seed=4)
+    y, proj = ops.deform1_conv_fwd(x, off, wt, b)
+    xs, os_, ws, bs = (t.double().cpu().requires_grad_(True) for t in (x, off, wt, b))
+    ref = O.deformable_conv2d(xs, os_, ws, bs)
+    assert y.shape == (n, 1, h, w) and rel_l2(y, ref) < 2e-6
+    dy = rnd(n, 1, h, w, seed=5)
+    gx, goff, gw, gb = torch.autograd.grad((ref * dy.double().cpu()).sum(), [xs, os_, ws, bs])
+    dw, db = torch.zeros_like(wt), torch.zeros_like(b)
+    dx = torch.full_like(x, float("nan"))            # written, not accumulated
+    doff = ops.deform1_conv_bwd(x, off, wt, proj, dy, dw, db, dx)
+    assert rel_l2(dw, gw) < 5e-6 and rel_l2(db, gb) < 5e-6
+    assert rel_l2(dx, gx) < 5e-6
+    assert rel_l2(doff, goff) < 5e-5
+    dx2 = torch.ones_like(x)
+    ops.deform1_conv_bwd(x, off, wt, proj, dy, torch.zeros_like(wt), torch.zeros_like(b), dx2, accumulate_dx=True)
+    assert rel_l2(dx2 - 1, gx) < 5e-5
+
+
 def test_bn_lrelu_fwd_bwd(ops):
     from oracle import deepbedmap_oracle as O
     n, c, h = 6, 10, 5
