@@ -41,6 +41,7 @@ SIGNATURES = {
     "dbm_flat_debug_set": [_I, _I],
     "dbm_flat_geometry": [_I, _I, _I, _P],
     "dbm_flat_conv3x3_seq": [_P, _I, _I, _I, _I, _I, _I, _P],
+    "dbm_flat_conv3x3_chain": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "dbm_flat_wgrad": [_P, _I, _I, _I, _I, _P],
     "dbm_flat_wgrad_reduce": [_P, _I, _P],
     "dbm_flat_bias_grad": [_P, _I, _I, _I, _I, _P],

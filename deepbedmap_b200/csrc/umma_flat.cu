@@ -71,6 +71,80 @@ __device__ __forceinline__ uint32_t idesc_bf16_rt(uint32_t M, uint32_t N, uint32
   return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major << 15) | (mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// One 32-column block of an accumulator row -> table-driven epilogue (bias, residual adds, LeakyReLU or its
+// derivative mask, fp32 / bf16 stores) at flat position ``pos``.
+__device__ __forceinline__ void flat_epi_apply(const FlatEpiBlock& e, const uint32_t (&acc)[32], long ych, long yf,
+                                               long pos, const FlatGeom& g) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+  if (e.bias) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += __ldg(e.bias + ych + i);
+  }
+  if (e.add1) {
+    const float s1 = e.s1, be = e.beta;
+#pragma unroll
+    for (int s4 = 0; s4 < 8; ++s4) {
+      const float4 rr = *reinterpret_cast<const float4*>(e.add1 + yf + ((long)s4 * g.Pg + pos) * 4);
+      v[4 * s4 + 0] = s1 * rr.x + be * v[4 * s4 + 0];
+      v[4 * s4 + 1] = s1 * rr.y + be * v[4 * s4 + 1];
+      v[4 * s4 + 2] = s1 * rr.z + be * v[4 * s4 + 2];
+      v[4 * s4 + 3] = s1 * rr.w + be * v[4 * s4 + 3];
+    }
+  }
+  if (e.add2) {
+    const float be = e.beta2;
+#pragma unroll
+    for (int s4 = 0; s4 < 8; ++s4) {
+      const float4 rr = *reinterpret_cast<const float4*>(e.add2 + yf + ((long)s4 * g.Pg + pos) * 4);
+      v[4 * s4 + 0] = rr.x + be * v[4 * s4 + 0];
+      v[4 * s4 + 1] = rr.y + be * v[4 * s4 + 1];
+      v[4 * s4 + 2] = rr.z + be * v[4 * s4 + 2];
+      v[4 * s4 + 3] = rr.w + be * v[4 * s4 + 3];
+    }
+  }
+  if (e.act) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
+  }
+  if (e.mask) {
+#pragma unroll
+    for (int s8 = 0; s8 < 4; ++s8) {
+      const uint4 mm = *reinterpret_cast<const uint4*>(e.mask + yf + ((long)s8 * g.Pg + pos) * 8);
+      const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // bf16 sign bits: low half = even channel, high half = odd channel
+        if (w4[j] & 0x00008000u) v[8 * s8 + 2 * j] *= kLreluSlope;
+        if (w4[j] & 0x80000000u) v[8 * s8 + 2 * j + 1] *= kLreluSlope;
+      }
+    }
+  }
+  if (e.out_f32) {
+#pragma unroll
+    for (int s4 = 0; s4 < 8; ++s4)
+      *reinterpret_cast<float4*>(e.out_f32 + yf + ((long)s4 * g.Pg + pos) * 4) =
+          make_float4(v[4 * s4], v[4 * s4 + 1], v[4 * s4 + 2], v[4 * s4 + 3]);
+  }
+  if (e.out_bf16) {
+    const float sc = e.out_scale;
+#pragma unroll
+    for (int s8 = 0; s8 < 4; ++s8) {
+      uint4 o;
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(sc * v[8 * s8 + 0], sc * v[8 * s8 + 1]);
+      __nv_bfloat162 t1 = __floats2bfloat162_rn(sc * v[8 * s8 + 2], sc * v[8 * s8 + 3]);
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(sc * v[8 * s8 + 4], sc * v[8 * s8 + 5]);
+      __nv_bfloat162 t3 = __floats2bfloat162_rn(sc * v[8 * s8 + 6], sc * v[8 * s8 + 7]);
+      o.x = *reinterpret_cast<uint32_t*>(&t0);
+      o.y = *reinterpret_cast<uint32_t*>(&t1);
+      o.z = *reinterpret_cast<uint32_t*>(&t2);
+      o.w = *reinterpret_cast<uint32_t*>(&t3);
+      *reinterpret_cast<uint4*>(e.out_bf16 + yf + ((long)s8 * g.Pg + pos) * 8) = o;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kFlatThreads, 1)
 flat_conv_kernel(const __grid_constant__ FlatLaunch L, const FlatGeom g) {
   extern __shared__ uint8_t smem_raw[];
@@ -172,79 +246,175 @@ flat_conv_kernel(const __grid_constant__ FlatLaunch L, const FlatGeom g) {
         tmem_wait_ld();
         if (interior) {
           const FlatEpiBlock& e = L.blk[b];
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-          if (e.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(e.bias + ych + i);
-          }
-          if (e.add1) {
-            const float s1 = e.s1, be = e.beta;
-#pragma unroll
-            for (int s4 = 0; s4 < 8; ++s4) {
-              const float4 rr = *reinterpret_cast<const float4*>(e.add1 + yf + ((long)s4 * g.Pg + pos) * 4);
-              v[4 * s4 + 0] = s1 * rr.x + be * v[4 * s4 + 0];
-              v[4 * s4 + 1] = s1 * rr.y + be * v[4 * s4 + 1];
-              v[4 * s4 + 2] = s1 * rr.z + be * v[4 * s4 + 2];
-              v[4 * s4 + 3] = s1 * rr.w + be * v[4 * s4 + 3];
-            }
-          }
-          if (e.add2) {
-            const float be = e.beta2;
-#pragma unroll
-            for (int s4 = 0; s4 < 8; ++s4) {
-              const float4 rr = *reinterpret_cast<const float4*>(e.add2 + yf + ((long)s4 * g.Pg + pos) * 4);
-              v[4 * s4 + 0] = rr.x + be * v[4 * s4 + 0];
-              v[4 * s4 + 1] = rr.y + be * v[4 * s4 + 1];
-              v[4 * s4 + 2] = rr.z + be * v[4 * s4 + 2];
-              v[4 * s4 + 3] = rr.w + be * v[4 * s4 + 3];
-            }
-          }
-          if (e.act) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
-          }
-          if (e.mask) {
-#pragma unroll
-            for (int s8 = 0; s8 < 4; ++s8) {
-              const uint4 mm = *reinterpret_cast<const uint4*>(e.mask + yf + ((long)s8 * g.Pg + pos) * 8);
-              const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                // bf16 sign bits: low half = even channel, high half = odd channel
-                if (w4[j] & 0x00008000u) v[8 * s8 + 2 * j] *= kLreluSlope;
-                if (w4[j] & 0x80000000u) v[8 * s8 + 2 * j + 1] *= kLreluSlope;
-              }
-            }
-          }
-          if (e.out_f32) {
-#pragma unroll
-            for (int s4 = 0; s4 < 8; ++s4)
-              *reinterpret_cast<float4*>(e.out_f32 + yf + ((long)s4 * g.Pg + pos) * 4) =
-                  make_float4(v[4 * s4], v[4 * s4 + 1], v[4 * s4 + 2], v[4 * s4 + 3]);
-          }
-          if (e.out_bf16) {
-            const float sc = e.out_scale;
-#pragma unroll
-            for (int s8 = 0; s8 < 4; ++s8) {
-              uint4 o;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(sc * v[8 * s8 + 0], sc * v[8 * s8 + 1]);
-              __nv_bfloat162 t1 = __floats2bfloat162_rn(sc * v[8 * s8 + 2], sc * v[8 * s8 + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(sc * v[8 * s8 + 4], sc * v[8 * s8 + 5]);
-              __nv_bfloat162 t3 = __floats2bfloat162_rn(sc * v[8 * s8 + 6], sc * v[8 * s8 + 7]);
-              o.x = *reinterpret_cast<uint32_t*>(&t0);
-              o.y = *reinterpret_cast<uint32_t*>(&t1);
-              o.z = *reinterpret_cast<uint32_t*>(&t2);
-              o.w = *reinterpret_cast<uint32_t*>(&t3);
-              *reinterpret_cast<uint4*>(e.out_bf16 + yf + ((long)s8 * g.Pg + pos) * 8) = o;
-            }
-          }
+          flat_epi_apply(e, acc, ych, yf, pos, g);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent chain: the same convolution pipeline over a DEVICE table of launches executed in order by one
+// grid (one CTA per SM, tile -> CTA mapping fixed), so a 182-layer forward or data-gradient chain is one
+// launch. Layer l may read what layers < l wrote within +-halo (< 128) positions of its tile: tile t of layer
+// l waits for tiles t-1, t, t+1 of layer l-1 (flag = 4 epilogue warps; transitively every earlier layer is then
+// complete on t-2..t+2, which also covers buffer re-use). Release/acquire as in umma_trunk.cu:
+// st.global -> __syncwarp -> lane-0 __threadfence -> atomicAdd / ld.acquire.gpu -> fence.proxy.async -> bulk copy.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int flat_ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kFlatThreads, 1)
+flat_chain_kernel(const FlatLaunch* __restrict__ table, int count, const FlatGeom g, unsigned int* __restrict__ done,
+                  uint32_t stage_bytes, int nst) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)smem;
+  uint64_t* empty = full + kFlatMaxStages;
+  uint64_t* tfull = empty + kFlatMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint8_t* stages = smem + 1024;
+
+  const uint32_t slab_bytes = (uint32_t)g.R * 16u;
+  const uint32_t a_bytes = 2u * slab_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- dependency wait + bulk-copy producer (converged warp; lanes 0..2 watch the three neighbour tiles) ----
+    int s = 0; uint32_t ph = 0;
+    for (int l = 0; l < count; ++l) {
+      const __nv_bfloat16* in = table[l].in;
+      const __nv_bfloat16* wp = table[l].wpacked;
+      const int num_kc = table[l].cin / 16;
+      const uint32_t b_bytes = 288u * (uint32_t)table[l].nout;
+      for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+        if (l > 0) {
+          const int nt = tile + lane - 1;
+          if (lane < 3 && nt >= 0 && nt < g.tiles) {
+            const unsigned int* f = done + (size_t)(l - 1) * g.tiles + nt;
+            uint32_t spins = 0;
+            while (flat_ld_acquire(f) < 4u) {
+              if (++spins > (1u << 24)) {
+                printf("dbm: flat chain dependency timeout layer %d tile %d\n", l, tile);
+                __trap();
+              }
+              __nanosleep(32);
+            }
+          }
+          __syncwarp();
+        }
+        const long pos0 = (long)g.G0 + (long)tile * 128 - g.halo;
+        for (int kc = 0; kc < num_kc; ++kc) {
+          mbar_wait(&empty[s], ph ^ 1);
+          if (lane == 0) {
+            // order the acquired flags (generic proxy) before the bulk-copy reads (async proxy)
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            mbar_arrive_expect_tx(&full[s], a_bytes + b_bytes);
+            uint8_t* st = stages + (size_t)s * stage_bytes;
+            bulk_load(st, in + ((long)(2 * kc) * g.Pg + pos0) * 8, slab_bytes, &full[s]);
+            bulk_load(st + slab_bytes, in + ((long)(2 * kc + 1) * g.Pg + pos0) * 8, slab_bytes, &full[s]);
+            bulk_load(st + a_bytes, wp + (size_t)kc * (b_bytes / 2), b_bytes, &full[s]);
+          }
+          __syncwarp();
+          if (++s == nst) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t a_hi = desc_hi(128), b_hi = desc_hi(128);
+    const uint32_t st_u = smem_u32(stages);
+    int s = 0, it = 0; uint32_t ph = 0;
+    for (int l = 0; l < count; ++l) {
+      const int N = table[l].nout;
+      const int num_kc = table[l].cin / 16;
+      const uint32_t idesc = idesc_bf16_rt(128, (uint32_t)N, 0);
+      const uint32_t b_lbo = (uint32_t)(N / 8) * 128u;
+      const uint32_t b_tap = (2u * b_lbo) >> 4;
+      for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
+        for (int kc = 0; kc < num_kc; ++kc) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_lo = desc_lo(st_u + s * stage_bytes, slab_bytes);
+          const uint32_t b_lo = desc_lo(st_u + s * stage_bytes + a_bytes, b_lbo);
+          if (elect_one_sync()) {
+#pragma unroll 1
+            for (uint32_t tap = 0; tap < 9; ++tap) {
+              const uint32_t a_off = (tap / 3) * (uint32_t)g.Wp + (tap % 3);
+              umma_bf16(d0, make_desc(a_lo + a_off, a_hi), make_desc(b_lo + tap * b_tap, b_hi), idesc,
+                        (kc | (int)tap) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);
+            if (kc == num_kc - 1) umma_commit(&tfull[buf]);
+          }
+          __syncwarp();
+          if (++s == nst) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = 32 * q + lane;
+    int it = 0;
+    for (int l = 0; l < count; ++l) {
+      const FlatLaunch& L = table[l];
+      const int nblk = L.nout / 32;
+      for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tfull[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const int p = tile * 128 + m;
+        const int r = p % g.img;
+        const int y = r / g.Wp, x = r - y * g.Wp;
+        const bool interior = (p < g.P) && y >= 1 && y <= g.oh && x >= 1 && x <= g.ow;
+        const long pos = (long)g.G0 + p;
+#pragma unroll 1
+        for (int b = 0; b < nblk; ++b) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 256 + b * 32), acc);
+          tmem_wait_ld();
+          if (b == nblk - 1) {   // accumulator fully in registers: hand the TMEM buffer back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+          }
+          if (interior) flat_epi_apply(L.blk[b], acc, 0, 0, pos, g);
+        }
+        // publish the tile: the warp's stores are ordered before lane 0's gpu-scope fence by __syncwarp
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          atomicAdd(done + (size_t)l * g.tiles + tile, 1u);
+        }
+      }
     }
   }
 
@@ -528,6 +698,7 @@ static int set_flat_attr() {
   if (!done) {
     DBM_CUDA(cudaFuncSetAttribute(flat_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlatSmem));
     DBM_CUDA(cudaFuncSetAttribute(flat_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlatSmem));
+    DBM_CUDA(cudaFuncSetAttribute(flat_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlatSmem));
     done = true;
   }
   return DBM_OK;
@@ -584,6 +755,43 @@ extern "C" int dbm_flat_conv3x3_seq(const void* launches_host, int count, int n,
     flat_conv_kernel<<<dim3(gx, ny), kFlatThreads, kFlatSmem, stream>>>(L[i], g);
   }
   return check_launch("flat_conv_kernel");
+}
+
+extern "C" int dbm_flat_conv3x3_chain(const void* launches_host, const void* launches_dev, int count, int n, int h,
+                                      int w, int out_h, int out_w, void* flags_dev, cudaStream_t stream) {
+  FlatGeom g = flat_geom(n, h, w);
+  int rc = check_flat_shape(g, "flat_chain");
+  if (rc) return rc;
+  rc = set_flat_attr();
+  if (rc) return rc;
+  DBM_REQUIRE(launches_host && launches_dev && flags_dev && count > 0, "flat_chain: empty launch list");
+  DBM_REQUIRE(out_h >= 0 && out_h <= h && out_w >= 0 && out_w <= w, "flat_chain: output window %dx%d exceeds %dx%d",
+              out_h, out_w, h, w);
+  DBM_REQUIRE(g.halo <= 128, "flat_chain: image width %d: the halo must stay within the neighbouring tile", w);
+  if (out_h > 0) g.oh = out_h;
+  if (out_w > 0) g.ow = out_w;
+  const FlatLaunch* L = (const FlatLaunch*)launches_host;
+  int nmax = 0;
+  for (int i = 0; i < count; ++i) {
+    DBM_REQUIRE(L[i].cin % 16 == 0 && L[i].cin > 0, "flat_chain[%d]: Cin=%d must be a multiple of 16", i, L[i].cin);
+    DBM_REQUIRE(L[i].nout % 32 == 0 && L[i].nout >= 32 && L[i].nout <= 192,
+                "flat_chain[%d]: N=%d must be a multiple of 32 in [32, 192]", i, L[i].nout);
+    DBM_REQUIRE(L[i].in && L[i].wpacked && (((uintptr_t)L[i].in | (uintptr_t)L[i].wpacked) & 15) == 0,
+                "flat_chain[%d]: null or unaligned operand", i);
+    DBM_REQUIRE(L[i].ny <= 1, "flat_chain[%d]: output-channel chunks are not supported in a chain", i);
+    if (L[i].nout > nmax) nmax = L[i].nout;
+  }
+  // one stage size for the whole chain (the widest layer's), so the ring layout never changes under in-flight stages
+  const uint32_t stage_bytes = 2u * (uint32_t)g.R * 16u + 288u * (uint32_t)nmax;
+  int nst = (kFlatSmem - 2048) / (int)stage_bytes;
+  if (nst > kFlatMaxStages) nst = kFlatMaxStages;
+  DBM_REQUIRE(nst >= 2, "flat_chain: stage of %u bytes does not fit twice", stage_bytes);
+  // every CTA must be co-resident (tiles spin on flags set by other CTAs): at most one CTA per SM
+  const int grid = g.tiles < num_sms() ? g.tiles : num_sms();
+  DBM_CUDA(cudaMemsetAsync(flags_dev, 0, (size_t)count * g.tiles * sizeof(unsigned int), stream));
+  flat_chain_kernel<<<grid, kFlatThreads, kFlatSmem, stream>>>((const FlatLaunch*)launches_dev, count, g,
+                                                               (unsigned int*)flags_dev, stage_bytes, nst);
+  return check_launch("flat_chain_kernel");
 }
 
 extern "C" int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h, int w, cudaStream_t stream) {

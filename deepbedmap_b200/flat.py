@@ -267,18 +267,31 @@ class FlatTrunk:
         self.bias_dev, self.n_bias = dev(bg), len(bg)
         self.fwd = np.ascontiguousarray(np.stack(fwd))
         self.bwd = np.ascontiguousarray(np.stack(bwd))
+        # device copies + dependency flags of the persistent chain launches (dbm_flat_conv3x3_chain)
+        self.fwd_dev, self.bwd_dev = dev(self.fwd), dev(self.bwd)
+        self.flags = torch.zeros(max(len(fwd), len(bwd)) * self.geom["tiles"], dtype=torch.int32, device="cuda")
         self.flops_fwd = float(sum(2.0 * 9 * int(L["cin"]) * int(L["nout"]) for L in fwd)) * self.n * self.H * self.W
         self._pack_gen = m._pack_gen
         self._built_beta = beta
 
     # ---- execution ----
+    persistent = True   # one persistent launch per chain (False: one launch per layer, the A/B reference)
+
+    def _chain(self, table, table_dev):
+        n, H, W = self.n, self.H, self.W
+        if self.persistent:
+            ops.call("dbm_flat_conv3x3_chain", table.ctypes.data, table_dev.data_ptr(), len(table), n, H, W, 0, 0,
+                     self.flags.data_ptr(), ops.stream())
+        else:
+            ops.call("dbm_flat_conv3x3_seq", table.ctypes.data, len(table), n, H, W, 0, 0, ops.stream())
+
     def forward(self, a0_nchw: torch.Tensor) -> torch.Tensor:
         """a0 = stem output (n,128,H,W) fp32 -> a3 = a1 + post_res(trunk(a1)) (n,64,H,W) fp32 (:541-551);
         keeps the bf16 activations of every dense block for backward()."""
         n, H, W = self.n, self.H, self.W
         st = ops.stream()
         ops.call("dbm_flat_from_nchw", a0_nchw.data_ptr(), 128, self.s0.data_ptr(), None, 1.0, n, H, W, st)
-        ops.call("dbm_flat_conv3x3_seq", self.fwd.ctypes.data, len(self.fwd), n, H, W, 0, 0, st)
+        self._chain(self.fwd, self.fwd_dev)
         a3 = ops.empty(n, 64, H, W)
         ops.call("dbm_flat_to_nchw", self.a3f.data_ptr(), None, a3.data_ptr(), 64, n, H, W, st)
         return a3
@@ -290,7 +303,7 @@ class FlatTrunk:
         st = ops.stream()
         ops.call("dbm_flat_from_nchw", da3_nchw.data_ptr(), 64, self.gpost.data_ptr(), self.da3f.data_ptr(), 1.0, n, H, W,
                  st)
-        ops.call("dbm_flat_conv3x3_seq", self.bwd.ctypes.data, len(self.bwd), n, H, W, 0, 0, st)
+        self._chain(self.bwd, self.bwd_dev)
         ops.call("dbm_flat_wgrad", self.units_dev.data_ptr(), self.n_units, n, H, W, st)
         ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, st)
         ops.call("dbm_flat_bias_grad", self.bias_dev.data_ptr(), self.n_bias, n, H, W, st)

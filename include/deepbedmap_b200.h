@@ -150,6 +150,10 @@ int dbm_flat_debug_set(int key, int value);
 int dbm_flat_geometry(int n, int h, int w, int* out5_host);
 int dbm_flat_conv3x3_seq(const void* launches_host, int count, int n, int h, int w, int out_h, int out_w,
                          cudaStream_t stream);
+/* The same launch list as ONE persistent launch: layer l's tile t waits for tiles t-1..t+1 of layer l-1
+ * (device flags, count * tiles uint32, zeroed here). launches_dev = device copy of launches_host. */
+int dbm_flat_conv3x3_chain(const void* launches_host, const void* launches_dev, int count, int n, int h, int w,
+                           int out_h, int out_w, void* flags_dev, cudaStream_t stream);
 int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h, int w, cudaStream_t stream);
 int dbm_flat_wgrad_reduce(const void* entries_dev, int count, cudaStream_t stream);
 int dbm_flat_bias_grad(const void* entries_dev, int count, int n, int h, int w, cudaStream_t stream);

@@ -187,6 +187,37 @@ def test_flat_trunk_alone_matches_oracle_autograd(nb, n, beta):
         assert float(np.median(list(errs.values()))) < tol_med
 
 
+@pytest.mark.parametrize("nb,n,H,W", [(1, 3, 9, 9), (12, 128, 9, 9), (2, 40, 30, 23), (1, 1, 5, 4)])
+def test_persistent_chain_equals_per_layer_launches(nb, n, H, W):
+    """The one-launch forward / data-gradient chains (flag-synchronised tiles) are bit-identical to launching
+    every layer on its own; (2, 40, 30, 23) gives several tiles per CTA (more than 148 tiles)."""
+    from oracle import deepbedmap_oracle as O
+    from deepbedmap_b200 import GeneratorModel
+    params = O.init_generator_params(nb, seed=5, bias_std=0.05, scale=0.7)
+    m = GeneratorModel(num_residual_blocks=nb)
+    for k, v in params.items():
+        m.set_param(k, v)
+    a0 = rnd(n, 128, H, W, seed=21)
+    da3 = rnd(n, 64, H, W, seed=22)
+    ft = m._flat_trunk(n, H, W)
+    out = {}
+    for persistent in (False, True, True):
+        ft.persistent = persistent
+        a3 = ft.forward(a0).clone()
+        m.cleargrads()
+        da0 = ft.backward(da3).clone()
+        res = (a3, da0, m.flat_grad.clone())
+        if persistent in out:
+            assert all(torch.equal(a, b) for a, b in zip(out[persistent][:2], res[:2]))   # re-run: flags reset
+        out[persistent] = res
+    assert torch.isfinite(out[True][0]).all() and out[True][0].abs().max() > 0
+    assert torch.equal(out[True][0], out[False][0]), "forward chain differs"
+    assert torch.equal(out[True][1], out[False][1]), "data-gradient chain differs"
+    # the weight gradients read the chains' bf16 outputs: same inputs -> same partial sums (fp32 split sums are
+    # reduced in a fixed order)
+    assert rel_l2(out[True][2], out[False][2]) < 1e-6
+
+
 @pytest.mark.parametrize("nb,n,scale", [(1, 3, 0.5), (2, 5, 0.5)])
 def test_generator_tensor_core_backward_matches_oracle(nb, n, scale):
     """Whole-generator G-step gradients with the trunk on the tensor cores (stem and head fp32):
