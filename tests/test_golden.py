@@ -113,7 +113,11 @@ def test_training_step_against_golden(golden):
     dl, da = T.train_eval_discriminator(arrays, g, d, d_opt)
     assert abs(dl - dl_ref) < 1e-4 * max(1, abs(dl_ref)) and abs(da - da_ref) < 1e-6
     for k in MG.STEP_GRAD_KEYS_D:
-        assert rel_l2(d.g[k].cpu().numpy(), golden[f"step/dgrad/{k}"]) < 2e-3, k
+        ref = golden[f"step/dgrad/{k}"]
+        if not np.any(ref):  # RaGAN: d loss / d linear_2/b is exactly 0 (a common logit shift cancels): absolute check
+            assert np.abs(d.g[k].cpu().numpy()).max() < 1e-6, k
+            continue
+        assert rel_l2(d.g[k].cpu().numpy(), ref) < 2e-3, k
     gl, psnr, ssim = T.train_eval_generator(arrays, g, d, g_opt)
     assert abs(gl - gl_ref) < 1e-4 * max(1, abs(gl_ref))
     assert abs(psnr - psnr_ref) < 1e-3 and abs(ssim - ssim_ref) < 1e-4
