@@ -12,11 +12,15 @@
 
 namespace dbm {
 
-constexpr int kDTileW = 32, kDTileH = 4;   // 128 output pixels per work item; a warp = one 32-px row
+// A work item is 32 x 8 = 256 output pixels = two M=128 MMA tiles (rows 0-3 / 4-7 of the item).
+// 24 gather warps (6 per SM sub-partition; the 12 of the 128-pixel version issued on 53 % of the
+// cycles, ncu r1g) : thread = (pixel, tap slot), all 64 channels of one tap per thread.
+constexpr int kDTileW = 32, kDTileH = 8;
+constexpr int kDPix = kDTileW * kDTileH;   // 256
 constexpr int kDStages = 3;                // stage s holds taps s, s+3, s+6 (filled by tap-slot s)
-constexpr int kDGatherThreads = 384;       // 12 warps: 128 px x 3 tap slots (each thread: all 64 channels of one tap)
-constexpr int kDThreads = kDGatherThreads + 32 + 128;  // + MMA warp + 4 epilogue warps
-constexpr int kDABytes = 128 * 64 * 2;                 // one tap: 128 px x 64 ch bf16
+constexpr int kDGatherThreads = 3 * kDPix; // 768
+constexpr int kDThreads = kDGatherThreads + 128 + 32;  // + 4 epilogue warps + MMA warp
+constexpr int kDABytes = kDPix * 64 * 2;               // one tap: 2 M-tiles x 128 px x 64 ch bf16
 constexpr int kDBBytes = 9 * 64 * 64 * 2;
 constexpr int kDSmem = kDBBytes + kDStages * kDABytes + 256 + 1024;
 
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDStages; ++s) {
-      mbar_init(&full[s], 4);   // one arrive per gather warp of the slot (128 threads)
+      mbar_init(&full[s], kDPix / 32);   // one arrive per gather warp of the slot (256 threads)
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) tmem_alloc<128>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -148,9 +152,10 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
     // thread = (pixel, tap slot): the sampling position of a tap is computed once per pixel and
     // all 8 slabs (64 channels) of that tap are gathered by the same thread.
     const int t = threadIdx.x;
-    const int pix = t & 127, slot = t >> 7;
+    const int pix = t & (kDPix - 1), slot = t >> 8;
     uint32_t fills = 0;
-    uint8_t* a = smA + slot * kDABytes;
+    // element (pixel m of M-tile j, slab q) of the stage lives at ((j * 8 + q) * 128 + m) * 16 bytes
+    uint8_t* a = smA + slot * kDABytes + (pix >> 7) * (kDABytes / 2) + (pix & 127) * 16;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int n = item / items_per_img;
       const int r = item - n * items_per_img;
@@ -174,21 +179,20 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
         if (valid) {
           const TapPos tp = tap_pos(odx[k], ody[k], x, y, tap, p.H, p.W);
 #pragma unroll
-          for (int s0 = 0; s0 < 8; s0 += 4) {
-            Corners cr[4];
+          for (int s0 = 0; s0 < 8; s0 += 2) {
+            Corners cr[2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cr[q] = load_corners(xin + (s0 + q) * plane, tp);
+            for (int q = 0; q < 2; ++q) cr[q] = load_corners(xin + (s0 + q) * plane, tp);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 2; ++q) {
               float v[8];
               blend8(cr[q], tp, v);
-              *reinterpret_cast<uint4*>(a + ((size_t)(s0 + q) * 128 + pix) * 16) = pack8(v);
+              *reinterpret_cast<uint4*>(a + (size_t)(s0 + q) * 2048) = pack8(v);
             }
           }
         } else {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(a + ((size_t)q * 128 + pix) * 16) = make_uint4(0, 0, 0, 0);
+          for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(a + (size_t)q * 2048) = make_uint4(0, 0, 0, 0);
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
       const int buf = it & 1;
       mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d = tmem_base + (uint32_t)(buf * 64);
+      const uint32_t d = tmem_base + (uint32_t)(buf * 128);
 #pragma unroll 1
       for (int tap = 0; tap < 9; ++tap) {
         const int s = tap % 3;
@@ -224,10 +228,16 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
         const uint32_t a_lo = desc_lo(smA_u + s * kDABytes, 2048u);
         const uint32_t bt_lo = b_lo + (uint32_t)(tap * 8 * 8 * 8);  // tap stride = 8 slabs x 8 groups x 128 B
         if (elect_one_sync()) {
-          umma_bf16_off<0u, 0u>(d, a_lo, a_hi, bt_lo, b_hi, idesc, tap != 0 ? 1u : 0u);
+          const uint32_t acc0 = tap != 0 ? 1u : 0u;
+          // M-tile 0 (item rows 0-3), then M-tile 1 (rows 4-7, 16 KB further = 1024 x 16 B): 4 K-steps of 16 channels
+          umma_bf16_off<0u, 0u>(d, a_lo, a_hi, bt_lo, b_hi, idesc, acc0);
           umma_bf16_off<256u, 128u>(d, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
           umma_bf16_off<512u, 256u>(d, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
           umma_bf16_off<768u, 384u>(d, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
+          umma_bf16_off<1024u, 0u>(d + 64, a_lo, a_hi, bt_lo, b_hi, idesc, acc0);
+          umma_bf16_off<1280u, 128u>(d + 64, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
+          umma_bf16_off<1536u, 256u>(d + 64, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
+          umma_bf16_off<1792u, 384u>(d + 64, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
           umma_commit(&empty[s]);
           if (tap == 8) umma_commit(&tfull[buf]);
         }
@@ -244,15 +254,17 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
       const int n = item / items_per_img;
       const int r = item - n * items_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      const int y = ty * kDTileH + (m >> 5), x = tx * kDTileW + (m & 31);
-      const bool valid = y < p.H && x < p.W;
+      const int x = tx * kDTileW + (m & 31);
       const int buf = it & 1;
       mbar_wait(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
+      for (int jc = 0; jc < 4; ++jc) {
+        const int j = jc >> 1, c0 = (jc & 1) * 32;
+        const int y = ty * kDTileH + 4 * j + (m >> 5);
+        const bool valid = y < p.H && x < p.W;
         uint32_t acc[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 64 + c0), acc);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 128 + j * 64 + c0), acc);
         tmem_wait_ld();
         if (valid) {
 #pragma unroll
@@ -277,7 +289,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<256>(tmem_base);
   }
 }
 

@@ -34,13 +34,13 @@ def rel_l2(a, b):
 STEM_PHYSICAL_SCALE = {"X": 1e-3, "W1": 5e-4, "W2": 5e-3, "W3": 2e-3}
 
 
-def make_generator(nb, precision, scale=1.0, bias_std=0.1, seed=0, physical=False):
+def make_generator(nb, precision, scale=1.0, bias_std=0.1, seed=0, physical=False, inter_channels=32):
     from deepbedmap_b200 import GeneratorModel
-    params = O.init_generator_params(nb, seed=seed, bias_std=bias_std, scale=scale)
+    params = O.init_generator_params(nb, seed=seed, bias_std=bias_std, scale=scale, inter_channels=inter_channels)
     if physical:
         for k, f in STEM_PHYSICAL_SCALE.items():
             params[f"input_block/conv_on_{k}/W"] = params[f"input_block/conv_on_{k}/W"] * np.float32(f)
-    m = GeneratorModel(num_residual_blocks=nb, residual_scaling=0.1, precision=precision)
+    m = GeneratorModel(num_residual_blocks=nb, residual_scaling=0.1, precision=precision, inter_channels=inter_channels)
     for k, v in params.items():
         m.set_param(k, v)
     return m, params
@@ -137,6 +137,46 @@ def test_paired_trunk_plan_is_deterministic_and_tracks_unpaired(nb, n, h, w):
     assert err < 6e-3
 
 
+@pytest.mark.parametrize("nb,inter,n,h,w", [(8, 32, 1, 11, 11), (14, 32, 1, 11, 11), (23, 32, 1, 11, 11),
+                                             (2, 64, 2, 11, 11), (8, 64, 1, 13, 10)])
+def test_scaled_generators_match_oracle(nb, inter, n, h, w):
+    """BASELINE.json configs[4] / SURVEY 8d config 5: the reference's hyperparameter search space
+    (num_residual_blocks 8-14 and beyond, srgan_train.py:454, 1540-1542; inter_channels 32 / 64,
+    :283-284) on the tensor-core path, same tolerances as the 12-block model."""
+    m, params = make_generator(nb, "bf16", scale=0.5, inter_channels=inter)
+    assert m.count_params() == O.count_params(O.generator_param_shapes(nb, inter))
+    ins = O.synthetic_inputs(n, h, w)
+    ref = O.generator_forward_numpy(params, *ins, num_residual_blocks=nb)
+    emu = O.generator_forward_numpy(params, *ins, num_residual_blocks=nb, emulate_bf16=True)
+    got = m.forward(*ins).numpy()
+    print(f"nb={nb} inter={inter}: vs bf16-emulating oracle {rel_l2(got, emu):.3e}, vs fp64 oracle {rel_l2(got, ref):.3e}")
+    assert rel_l2(got, emu) < 6e-3 and rel_l2(got, ref) < 2e-2
+
+
+def test_wide_generator_fp32_forward_and_training_step():
+    """inter_channels = 64 on the exact-arithmetic path, forward and one generator step
+    (gradients against autograd on the fp64 oracle)."""
+    from deepbedmap_b200 import train as T
+    nb, inter, n = 1, 64, 2
+    g, gparams = make_generator(nb, "fp32", scale=1.0, bias_std=0.05, inter_channels=inter)
+    ins = O.synthetic_inputs(n)
+    ref = O.generator_forward_numpy(gparams, *ins, num_residual_blocks=nb)
+    assert rel_l2(g.forward(*ins).numpy(), ref) < 2e-5
+    d, dparams = _load_disc()
+    rng = np.random.RandomState(7)
+    arrays = dict(zip(("X", "W1", "W2", "W3"), ins))
+    arrays["Y"] = rng.rand(n, 1, 36, 36).astype(np.float32)
+    ta = {k: torch.as_tensor(v, dtype=torch.float64) for k, v in arrays.items()}
+    gp, dp = O.to_torch(gparams), O.to_torch(dparams)
+    gl_ref, _, _, ggrads = O.train_eval_generator(ta, gp, dp, O.ChainerAdam(1.6e-4), num_residual_blocks=nb,
+                                                  return_grads=True)
+    gl, _, _ = T.train_eval_generator(arrays, g, d, T.Adam(1.6e-4).setup(g))
+    assert abs(gl - gl_ref) < 1e-4 * max(1, abs(gl_ref))
+    for k in ("residual_network/0/residual_dense_block2/conv_layer5/W",
+              "residual_network/0/residual_dense_block1/conv_layer3/W", "final_conv_layer2/deform_conv/W"):
+        assert rel_l2(g.g[k].cpu().numpy(), ggrads[k].numpy()) < 2e-2, k
+
+
 def test_generator_reference_init_scale():
     """Reference initialisation (HeNormal scale 0.1, zero biases): outputs are tiny but must
     still agree relatively."""
@@ -144,6 +184,18 @@ def test_generator_reference_init_scale():
     ins = O.synthetic_inputs(1)
     ref = O.generator_forward_numpy(params, *ins)
     assert rel_l2(m.forward(*ins).numpy(), ref) < 2e-2
+
+
+def test_test_area_window_forward_matches_oracle():
+    """the per-epoch test-window forward (get_deepbedmap_test_result, srgan_train.py:1444-1450)
+    runs the generator in eval mode on an arbitrary, non-square window (here 83 x 49 lowres)."""
+    nb, h, w = 2, 83, 49
+    m, params = make_generator(nb, "bf16", scale=0.7)
+    ins = O.synthetic_inputs(1, h, w)
+    emu = O.generator_forward_numpy(params, *ins, num_residual_blocks=nb, emulate_bf16=True)
+    got = m.forward(*ins).numpy()
+    assert got.shape == (1, 1, 4 * (h - 2), 4 * (w - 2))
+    assert rel_l2(got, emu) < 6e-3
 
 
 def _load_disc(seed=1, precision="fp32"):
