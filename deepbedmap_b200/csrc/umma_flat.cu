@@ -80,17 +80,19 @@ __device__ __forceinline__ void flat_epi_apply(const FlatEpiBlock& e, const uint
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
   if (e.bias) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += __ldg(e.bias + ych + i);
+    for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], __ldg(e.bias + ych + i));
   }
   if (e.add1) {
     const float s1 = e.s1, be = e.beta;
 #pragma unroll
     for (int s4 = 0; s4 < 8; ++s4) {
       const float4 rr = *reinterpret_cast<const float4*>(e.add1 + yf + ((long)s4 * g.Pg + pos) * 4);
-      v[4 * s4 + 0] = s1 * rr.x + be * v[4 * s4 + 0];
-      v[4 * s4 + 1] = s1 * rr.y + be * v[4 * s4 + 1];
-      v[4 * s4 + 2] = s1 * rr.z + be * v[4 * s4 + 2];
-      v[4 * s4 + 3] = s1 * rr.w + be * v[4 * s4 + 3];
+      // explicit fused form (one rounding when s1 == 1): the image-resident kernel (umma_local.cu) computes the
+      // same expression and is checked bit for bit against this one
+      v[4 * s4 + 0] = __fmaf_rn(be, v[4 * s4 + 0], s1 * rr.x);
+      v[4 * s4 + 1] = __fmaf_rn(be, v[4 * s4 + 1], s1 * rr.y);
+      v[4 * s4 + 2] = __fmaf_rn(be, v[4 * s4 + 2], s1 * rr.z);
+      v[4 * s4 + 3] = __fmaf_rn(be, v[4 * s4 + 3], s1 * rr.w);
     }
   }
   if (e.add2) {
@@ -98,10 +100,10 @@ __device__ __forceinline__ void flat_epi_apply(const FlatEpiBlock& e, const uint
 #pragma unroll
     for (int s4 = 0; s4 < 8; ++s4) {
       const float4 rr = *reinterpret_cast<const float4*>(e.add2 + yf + ((long)s4 * g.Pg + pos) * 4);
-      v[4 * s4 + 0] = rr.x + be * v[4 * s4 + 0];
-      v[4 * s4 + 1] = rr.y + be * v[4 * s4 + 1];
-      v[4 * s4 + 2] = rr.z + be * v[4 * s4 + 2];
-      v[4 * s4 + 3] = rr.w + be * v[4 * s4 + 3];
+      v[4 * s4 + 0] = __fmaf_rn(be, v[4 * s4 + 0], rr.x);
+      v[4 * s4 + 1] = __fmaf_rn(be, v[4 * s4 + 1], rr.y);
+      v[4 * s4 + 2] = __fmaf_rn(be, v[4 * s4 + 2], rr.z);
+      v[4 * s4 + 3] = __fmaf_rn(be, v[4 * s4 + 3], rr.w);
     }
   }
   if (e.act) {

@@ -30,6 +30,50 @@ WGRAD_REDUCE_DTYPE = np.dtype([("partial", "<u8"), ("dw", "<u8"), ("split_stride
                                ("cin_total", "<i4"), ("c0", "<i4"), ("o0", "<i4"), ("nch", "<i4"), ("mode", "<i4")])
 assert WGRAD_REDUCE_DTYPE.itemsize == 48
 BIAS_GRAD_DTYPE = np.dtype([("gout", "<u8"), ("db", "<u8")])
+# csrc/umma_local.cu LocalPass
+LOCAL_PASS_DTYPE = np.dtype([("w", "<u8"), ("bias", "<u8"), ("save", "<u8"), ("out_f32", "<u8"), ("mask", "<u8"),
+                             ("add_f32", "<u8"), ("slab0", "<i4"), ("nk", "<i4"), ("N", "<i4"), ("col0", "<i4"),
+                             ("type", "<i4"), ("ecol", "<i4"), ("out_slab", "<i4"), ("rr", "<i4"), ("beta", "<f4"),
+                             ("scale", "<f4"), ("first", "<i4"), ("pad", "<i4")])
+assert LOCAL_PASS_DTYPE.itemsize == 96
+LOC_PRE, LOC_ACT, LOC_RDB, LOC_POST, LOC_BPOST, LOC_BMASK, LOC_BD1, LOC_BPRE = range(8)
+
+
+def local_trunk_fits(H: int, W: int) -> bool:
+    """An image with its zero border is one M=128 UMMA tile: the image-resident kernel applies."""
+    return (H + 2) * (W + 2) <= 128
+
+
+def local_pass(**kw):
+    e = np.zeros((), dtype=LOCAL_PASS_DTYPE)
+    e["scale"] = 1.0
+    for k, v in kw.items():
+        e[k] = v
+    return e
+
+
+def local_forward_table(model, pk, nrdb, beta, cat_ptr=None, out_f32=0):
+    """Pass table of dbm_trunk_local_fwd for ``model``'s packed operands. ``cat_ptr(j, c)``: flat bf16 address of
+    channel c of dense-block buffer j (None: inference, nothing is kept); ``out_f32``: flat fp32 slab4 output."""
+    P = model.p
+    save = (lambda j, c: cat_ptr(j, c)) if cat_ptr is not None else (lambda j, c: 0)
+    passes = [local_pass(w=pk["pre_residual_conv_layer@trunk"][0].data_ptr(),
+                         bias=P["pre_residual_conv_layer/b"].data_ptr(), save=save(0, 0), slab0=0, nk=8, N=64, col0=0,
+                         type=LOC_PRE, ecol=0, out_slab=0, first=1)]
+    for j in range(nrdb):
+        r = j % 3 + 1
+        pre = model._rdb_prefix(j // 3, r)
+        for s in range(5):
+            last = s == 4
+            passes.append(local_pass(
+                w=pk[f"{pre}/stat{s}"].data_ptr(), bias=P[f"{pre}/conv_layer{s + 1}/b"].data_ptr(),
+                save=save(j + 1, 0) if last else save(j, 64 + 32 * s), slab0=0 if s == 0 else 8 + 4 * (s - 1),
+                nk=4 if s == 0 else 2, N=192 - 32 * s, col0=32 * s, type=LOC_RDB if last else LOC_ACT, ecol=32 * s,
+                out_slab=0 if last else 8 + 4 * s, rr=int(last and r == 3), beta=beta, first=int(s == 0)))
+    passes.append(local_pass(w=pk["post_residual_conv_layer@trunk"][0].data_ptr(),
+                             bias=P["post_residual_conv_layer/b"].data_ptr(), out_f32=out_f32, slab0=0, nk=4, N=64,
+                             col0=0, type=LOC_POST, ecol=0, first=1))
+    return np.ascontiguousarray(np.stack(passes))
 PARTIAL_FLOATS = 9 * 32 * 128
 
 
@@ -271,11 +315,46 @@ class FlatTrunk:
         self.fwd_dev, self.bwd_dev = dev(self.fwd), dev(self.bwd)
         self.flags = torch.zeros(max(len(fwd), len(bwd)) * self.geom["tiles"], dtype=torch.int32, device="cuda")
         self.flops_fwd = float(sum(2.0 * 9 * int(L["cin"]) * int(L["nout"]) for L in fwd)) * self.n * self.H * self.W
+        # image-resident forward (csrc/umma_local.cu) when a padded image is one UMMA tile
+        self.local_dev = None
+        if local_trunk_fits(self.H, self.W):
+            tab = local_forward_table(m, pk, nrdb, beta, cat_ptr=lambda j, c: pb(self.cat[j], c), out_f32=pf(self.a3f))
+            self.local_dev, self.n_local = dev(tab), len(tab)
+            if getattr(self, "x_scratch", None) is None:
+                self.x_scratch = torch.empty(2, self.n * 16 * 128 * 4, dtype=torch.float32, device="cuda")
+            # data-gradient chain, image-resident: same passes as ``bwd`` above (conv5's gradient opens the block's
+            # accumulator d[a0..a4], conv4..conv1's add onto its leading columns); operand slabs in shared memory:
+            # g5 -> 0..7, g4 -> 8, g3 -> 12, g2 -> 16, g1 -> 20
+            gp = lambda key: pk[key].data_ptr()
+            bt = [local_pass(w=gp("post_residual_conv_layer@dgrad"), save=pb(self.gcat[nrdb - 1], 128), slab0=0, nk=4,
+                             N=64, col0=0, type=LOC_BPOST, ecol=0, out_slab=0, scale=plan[nrdb - 1]["g5_scale"], first=1)]
+            for d in reversed(plan):
+                j, r, sigma = d["j"], d["r"], d["sigma"]
+                pre = m._rdb_prefix(j // 3, r)
+                cat, gcat = self.cat[j], self.gcat[j]
+                bt.append(local_pass(w=gp(f"{pre}/conv_layer5@dgrad"), mask=pb(cat, 160), save=pb(gcat, 96), slab0=0, nk=4,
+                                     N=192, col0=0, type=LOC_BMASK, ecol=160, out_slab=8, first=1))
+                for k in (4, 3, 2):
+                    nout = 64 + 32 * (k - 1)
+                    bt.append(local_pass(w=gp(f"{pre}/conv_layer{k}@dgrad"), mask=pb(cat, nout - 32),
+                                         save=pb(gcat, 32 * (k - 2)), slab0=8 + 4 * (4 - k), nk=2, N=nout, col0=0,
+                                         type=LOC_BMASK, ecol=nout - 32, out_slab=8 + 4 * (5 - k), first=0))
+                kw = dict(w=gp(f"{pre}/conv_layer1@dgrad"), slab0=20, nk=2, N=64, col0=0, type=LOC_BD1, ecol=0, out_slab=0,
+                          beta=sigma, rr=int(r == 1), first=0)
+                if j > 0:
+                    kw.update(save=pb(self.gcat[j - 1], 128), scale=plan[j - 1]["g5_scale"])
+                else:
+                    kw.update(mask=pb(self.cat[0], 0), save=pb(self.gpre), add_f32=pf(self.da3f))
+                bt.append(local_pass(**kw))
+            bt.append(local_pass(w=gp("pre_residual_conv_layer@dgrad"), out_f32=pf(self.da0f), slab0=0, nk=4, N=128, col0=0,
+                                 type=LOC_BPRE, ecol=0, first=1))
+            self.local_bwd_dev, self.n_local_bwd = dev(np.ascontiguousarray(np.stack(bt))), len(bt)
         self._pack_gen = m._pack_gen
         self._built_beta = beta
 
     # ---- execution ----
     persistent = True   # one persistent launch per chain (False: one launch per layer, the A/B reference)
+    local = True        # forward: image-resident kernel when the tile fits (False: the flat chain, the A/B reference)
 
     def _chain(self, table, table_dev):
         n, H, W = self.n, self.H, self.W
@@ -291,7 +370,11 @@ class FlatTrunk:
         n, H, W = self.n, self.H, self.W
         st = ops.stream()
         ops.call("dbm_flat_from_nchw", a0_nchw.data_ptr(), 128, self.s0.data_ptr(), None, 1.0, n, H, W, st)
-        self._chain(self.fwd, self.fwd_dev)
+        if self.local and self.local_dev is not None:
+            ops.call("dbm_trunk_local_fwd", self.local_dev.data_ptr(), self.n_local, n, H, W, self.s0.data_ptr(),
+                     self.x_scratch[0].data_ptr(), self.x_scratch[1].data_ptr(), st)
+        else:
+            self._chain(self.fwd, self.fwd_dev)
         a3 = ops.empty(n, 64, H, W)
         ops.call("dbm_flat_to_nchw", self.a3f.data_ptr(), None, a3.data_ptr(), 64, n, H, W, st)
         return a3
@@ -303,7 +386,11 @@ class FlatTrunk:
         st = ops.stream()
         ops.call("dbm_flat_from_nchw", da3_nchw.data_ptr(), 64, self.gpost.data_ptr(), self.da3f.data_ptr(), 1.0, n, H, W,
                  st)
-        self._chain(self.bwd, self.bwd_dev)
+        if self.local and self.local_dev is not None:
+            ops.call("dbm_trunk_local_bwd", self.local_bwd_dev.data_ptr(), self.n_local_bwd, n, H, W,
+                     self.gpost.data_ptr(), self.x_scratch[1].data_ptr(), st)
+        else:
+            self._chain(self.bwd, self.bwd_dev)
         ops.call("dbm_flat_wgrad", self.units_dev.data_ptr(), self.n_units, n, H, W, st)
         ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, st)
         ops.call("dbm_flat_bias_grad", self.bias_dev.data_ptr(), self.n_bias, n, H, W, st)

@@ -555,6 +555,20 @@ class GeneratorModel(_Link):
                             tail = image(32, 32)
                             entry(wb, tail, 32, 0, 32, cin + 32, cin, 32, 16)
                             pk[f"{pre}/tail{k + 1}"] = (tail, P[f"{pre}/conv_layer{k + 1}/b"])
+                # input-stationary slices for the image-resident small-tile trunk (csrc/umma_local.cu): pass s
+                # contracts block a_s (a0 = 64 channels, a1..a4 = 32) against its rows in conv_{s+1}..conv_5
+                # stacked along N = 192 - 32 s
+                for i in range(self.num_residual_blocks):
+                    for r in (1, 2, 3):
+                        pre = self._rdb_prefix(i, r)
+                        for s_ in range(5):
+                            cblk, c0 = (64, 0) if s_ == 0 else (32, 64 + 32 * (s_ - 1))
+                            ncol = 192 - 32 * s_
+                            stat = image(cblk, ncol)
+                            for k in range(s_ + 1, 6):
+                                entry(P[f"{pre}/conv_layer{k}/W"], stat, 64 if k == 5 else 32, 32 * (k - 1 - s_), cblk,
+                                      64 + 32 * (k - 1), c0, ncol, 16)
+                            pk[f"{pre}/stat{s_}"] = stat
             for key in ("post_upsample_conv_layer_1", "post_upsample_conv_layer_2"):
                 add(key, 64)
             add("final_conv_layer1/offset_conv", 32)

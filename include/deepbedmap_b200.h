@@ -154,6 +154,19 @@ int dbm_flat_conv3x3_seq(const void* launches_host, int count, int n, int h, int
  * (device flags, count * tiles uint32, zeroed here). launches_dev = device copy of launches_host. */
 int dbm_flat_conv3x3_chain(const void* launches_host, const void* launches_dev, int count, int n, int h, int w,
                            int out_h, int out_w, void* flags_dev, cudaStream_t stream);
+/* Image-resident trunk forward for small tiles ((h+2)*(w+2) <= 128 flat positions per image): the whole chain
+ * pre-residual conv -> residual dense blocks -> post-residual conv in one launch with the activations of an image
+ * pair held in shared memory / TMEM (csrc/umma_local.cu). passes_dev: device array of 96-byte LocalPass records
+ * (deepbedmap_b200/flat.py LOCAL_PASS_DTYPE); s0_flat: stem output, flat bf16 [16][Pg][8]; x0 / xrr scratch:
+ * n * 16 * 128 * 4 floats each. Replaces the same reference ops as dbm_flat_conv3x3_chain's forward table
+ * (srgan_train.py:339-358, 397-402, 541-551). */
+int dbm_trunk_local_fwd(const void* passes_dev, int count, int n, int h, int w, const void* s0_flat,
+                        float* x0_scratch, float* xrr_scratch, cudaStream_t stream);
+/* The data-gradient chain of the same trunk (autograd of the links above in g_loss.backward(), srgan_train.py:1256),
+ * image-resident: gradients wrt the dense-block slots accumulate in TMEM, the bf16 gradients wrt every conv output
+ * are written to the flat buffers dbm_flat_wgrad reads. gpost_flat: bf16(d loss / d a3), flat [8][Pg][8]. */
+int dbm_trunk_local_bwd(const void* passes_dev, int count, int n, int h, int w, const void* gpost_flat,
+                        float* dxrr_scratch, cudaStream_t stream);
 int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h, int w, cudaStream_t stream);
 int dbm_flat_wgrad_reduce(const void* entries_dev, int count, cudaStream_t stream);
 int dbm_flat_bias_grad(const void* entries_dev, int count, int n, int h, int w, cudaStream_t stream);

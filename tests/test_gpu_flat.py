@@ -200,6 +200,7 @@ def test_persistent_chain_equals_per_layer_launches(nb, n, H, W):
     a0 = rnd(n, 128, H, W, seed=21)
     da3 = rnd(n, 64, H, W, seed=22)
     ft = m._flat_trunk(n, H, W)
+    ft.local = False   # the flat chain itself (small tiles default to the image-resident kernel)
     out = {}
     for persistent in (False, True, True):
         ft.persistent = persistent
@@ -216,6 +217,50 @@ def test_persistent_chain_equals_per_layer_launches(nb, n, H, W):
     # the weight gradients read the chains' bf16 outputs: same inputs -> same partial sums (fp32 split sums are
     # reduced in a fixed order)
     assert rel_l2(out[True][2], out[False][2]) < 1e-6
+
+
+@pytest.mark.parametrize("nb,n,H,W", [(1, 3, 9, 9), (12, 128, 9, 9), (2, 5, 9, 9), (3, 301, 9, 9), (1, 2, 6, 14),
+                                      (1, 1, 5, 4)])
+def test_image_resident_trunk_equals_flat_chain(nb, n, H, W):
+    """csrc/umma_local.cu (activations of an image pair resident in shared memory / TMEM, input-stationary
+    passes of N = 192..64) against the layer-by-layer flat chain: every conv column accumulates the same
+    products in the same order and the fused skip adds are the same explicit fma, so the fp32 output and
+    the bf16 activations kept for backward are BIT-IDENTICAL; (3, 301) = odd batch, several image pairs
+    per CTA."""
+    from oracle import deepbedmap_oracle as O
+    from deepbedmap_b200 import GeneratorModel
+    params = O.init_generator_params(nb, seed=5, bias_std=0.05, scale=0.7)
+    m = GeneratorModel(num_residual_blocks=nb)
+    for k, v in params.items():
+        m.set_param(k, v)
+    a0 = rnd(n, 128, H, W, seed=21)
+    da3 = rnd(n, 64, H, W, seed=22)
+    ft = m._flat_trunk(n, H, W)
+    assert ft.local_dev is not None
+    res = {}
+    for local in (False, True, True):
+        ft.local = local
+        for c in ft.cat:
+            c.zero_()
+        a3 = ft.forward(a0).clone()
+        cats = [c.clone() for c in ft.cat]
+        m.cleargrads()
+        da0 = ft.backward(da3).clone()
+        cur = (a3, cats, da0, m.flat_grad.clone())
+        if local in res:   # second run of the image-resident kernel: bit-identical
+            assert torch.equal(res[local][0], a3) and all(torch.equal(a, b) for a, b in zip(res[local][1], cats))
+        res[local] = cur
+    ref, got = res[False], res[True]
+    assert torch.isfinite(got[0]).all() and got[0].abs().max() > 0
+    assert torch.equal(got[0], ref[0]), "a3 differs"
+    for j, (a, b) in enumerate(zip(got[1], ref[1])):
+        assert torch.equal(a, b), f"kept activations of dense block {j} differ"
+    # backward: the image-resident data-gradient chain accumulates the five convs' contributions to a slot in ONE
+    # TMEM accumulator (the flat chain adds five separately rounded fp32 sums): equal up to fp32 association and the
+    # rare bf16 flips it causes downstream
+    e_da0, e_grad = rel_l2(got[2], ref[2]), rel_l2(got[3], ref[3])
+    print(f"image-resident backward vs flat chain: d a0 rel_l2 {e_da0:.2e}, weight/bias gradients rel_l2 {e_grad:.2e}")
+    assert e_da0 < 2e-3 and e_grad < 2e-3
 
 
 @pytest.mark.parametrize("nb,n,scale", [(1, 3, 0.5), (2, 5, 0.5)])
