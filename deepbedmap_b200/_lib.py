@@ -43,6 +43,7 @@ SIGNATURES = {
     "dbm_flat_conv3x3_seq": [_P, _I, _I, _I, _I, _I, _I, _P],
     "dbm_flat_conv3x3_chain": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "dbm_trunk_local_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "dbm_local_debug_set": [_I],
     "dbm_trunk_local_bwd": [_P, _I, _I, _I, _I, _P, _P, _P],
     "dbm_flat_wgrad": [_P, _I, _I, _I, _I, _P],
     "dbm_flat_wgrad_reduce": [_P, _I, _P],

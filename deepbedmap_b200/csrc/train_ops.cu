@@ -17,40 +17,89 @@ __device__ __forceinline__ float block_sum(float s, float* red) {
 }
 
 // ---- BatchNormalization(axis=(0,2,3), eps=1e-5, decay=0.9) -------------------------------------
-// One block per channel. train: batch mean / biased variance (two-pass), running stats updated
-// with the unbiased variance; eval: running stats. Writes mean[c], invstd[c] for apply/backward.
+// train: batch mean / biased variance, running stats updated with the unbiased variance; eval: running stats.
+// Writes mean[c], invstd[c] for apply/backward.
+// Per-channel reductions are split over the batch (grid = C x S blocks, S ~ 4 blocks per SM / C): one block per
+// channel left 64-channel layers on 64 of 148 SMs. Partials are double and are combined in a fixed order by the
+// last block of the channel to arrive (deterministic); scratch is a library-owned static buffer, so BN calls must
+// not run concurrently on different streams (the training step issues them on one stream).
+constexpr int kBnMaxC = 1024, kBnMaxSplit = 32;
+__device__ double g_bn_part[kBnMaxC * kBnMaxSplit * 2];
+__device__ unsigned int g_bn_count[kBnMaxC];
+
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];   // fixed order, every thread gets the total
+  return t;
+}
+// returns true in the LAST block of channel c to finish (its view of every partial is complete)
+__device__ __forceinline__ bool bn_publish(int c, int split, int S, double a, double b) {
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    g_bn_part[((size_t)c * kBnMaxSplit + split) * 2] = a;
+    g_bn_part[((size_t)c * kBnMaxSplit + split) * 2 + 1] = b;
+    __threadfence();
+    last = atomicAdd(&g_bn_count[c], 1u) == (unsigned)(S - 1);
+    if (last) {
+      g_bn_count[c] = 0;   // ready for the next call
+      __threadfence();
+    }
+  }
+  __syncthreads();
+  return last;
+}
+
+static int bn_split(int n, int c) {
+  int s = (4 * num_sms() + c - 1) / c;
+  if (s > n) s = n;
+  if (s > kBnMaxSplit) s = kBnMaxSplit;
+  return s < 1 ? 1 : s;
+}
+
 __global__ void bn_stats_kernel(const float* __restrict__ x, int N, int C, int HW, float eps, float decay, int train,
                                 float* __restrict__ avg_mean, float* __restrict__ avg_var,
                                 float* __restrict__ mean_out, float* __restrict__ invstd_out) {
-  __shared__ float red[32];
-  const int c = blockIdx.x;
+  __shared__ double red[32];
+  const int c = blockIdx.x, split = blockIdx.y, S = gridDim.y;
   if (!train) {
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && split == 0) {
       mean_out[c] = avg_mean[c];
       invstd_out[c] = rsqrtf(avg_var[c] + eps);
     }
     return;
   }
-  const long m = (long)N * HW;
-  float s = 0.f;
-  for (long i = threadIdx.x; i < m; i += blockDim.x) {
-    const long n = i / HW, r = i - n * HW;
-    s += x[(n * C + c) * HW + r];
+  const long n0 = (long)N * split / S, n1 = (long)N * (split + 1) / S;
+  const long cnt = (n1 - n0) * HW;
+  double s = 0.0, q = 0.0;   // sum and sum of squares in double: var = E[x^2] - mean^2 without cancellation trouble
+  for (int i = threadIdx.x; i < (int)cnt; i += blockDim.x) {
+    const int n = i / HW, r = i - n * HW;
+    const double v = (double)x[((n0 + n) * C + c) * HW + r];
+    s += v;
+    q += v * v;
   }
-  const float mean = block_sum(s, red) / (float)m;
-  float q = 0.f;
-  for (long i = threadIdx.x; i < m; i += blockDim.x) {
-    const long n = i / HW, r = i - n * HW;
-    const float d = x[(n * C + c) * HW + r] - mean;
-    q += d * d;
-  }
-  const float var = block_sum(q, red) / (float)m;
+  s = block_sum_d(s, red);
+  q = block_sum_d(q, red);
+  if (!bn_publish(c, split, S, s, q)) return;
   if (threadIdx.x == 0) {
-    mean_out[c] = mean;
-    invstd_out[c] = 1.0f / sqrtf(var + eps);
-    const float adjust = (float)m / fmaxf((float)m - 1.f, 1.f);
-    avg_mean[c] = decay * avg_mean[c] + (1.f - decay) * mean;
-    avg_var[c] = decay * avg_var[c] + (1.f - decay) * var * adjust;
+    double ts = 0.0, tq = 0.0;
+    for (int k = 0; k < S; ++k) {
+      ts += g_bn_part[((size_t)c * kBnMaxSplit + k) * 2];
+      tq += g_bn_part[((size_t)c * kBnMaxSplit + k) * 2 + 1];
+    }
+    const double m = (double)N * HW;
+    const double mean = ts / m;
+    double var = tq / m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_out[c] = (float)mean;
+    invstd_out[c] = (float)(1.0 / sqrt(var + (double)eps));
+    const float adjust = (float)(m / fmax(m - 1.0, 1.0));
+    avg_mean[c] = decay * avg_mean[c] + (1.f - decay) * (float)mean;
+    avg_var[c] = decay * avg_var[c] + (1.f - decay) * (float)var * adjust;
   }
 }
 // y = lrelu(gamma * (x - mean) * invstd + beta)
@@ -69,26 +118,33 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                      float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat) {
-  __shared__ float red[32];
-  const int c = blockIdx.x;
-  const long m = (long)N * HW;
+  __shared__ double red[32];
+  const int c = blockIdx.x, split = blockIdx.y, S = gridDim.y;
+  const long n0 = (long)N * split / S, n1 = (long)N * (split + 1) / S;
+  const long cnt = (n1 - n0) * HW;
   const float mu = mean[c], is = invstd[c];
-  float s1 = 0.f, s2 = 0.f;
-  for (long i = threadIdx.x; i < m; i += blockDim.x) {
-    const long n = i / HW, r = i - n * HW;
-    const long idx = (n * C + c) * HW + r;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < (int)cnt; i += blockDim.x) {
+    const int n = i / HW, r = i - n * HW;
+    const long idx = ((n0 + n) * C + c) * HW + r;
     float dz = dy[idx];
     if (y[idx] < 0.f) dz *= kLreluSlope;
-    s1 += dz;
-    s2 += dz * (x[idx] - mu) * is;
+    s1 += (double)dz;
+    s2 += (double)(dz * (x[idx] - mu) * is);
   }
-  s1 = block_sum(s1, red);
-  s2 = block_sum(s2, red);
+  s1 = block_sum_d(s1, red);
+  s2 = block_sum_d(s2, red);
+  if (!bn_publish(c, split, S, s1, s2)) return;
   if (threadIdx.x == 0) {
-    sum_dz[c] = s1;
-    sum_dz_xhat[c] = s2;
-    dbeta[c] += s1;
-    dgamma[c] += s2;
+    double t1 = 0.0, t2 = 0.0;
+    for (int k = 0; k < S; ++k) {
+      t1 += g_bn_part[((size_t)c * kBnMaxSplit + k) * 2];
+      t2 += g_bn_part[((size_t)c * kBnMaxSplit + k) * 2 + 1];
+    }
+    sum_dz[c] = (float)t1;
+    sum_dz_xhat[c] = (float)t2;
+    dbeta[c] += (float)t1;
+    dgamma[c] += (float)t2;
   }
 }
 // ... then dx = gamma * invstd * (dz - sum_dz/m - xhat * sum_dz_xhat/m)
@@ -293,7 +349,8 @@ extern "C" int dbm_bn_lrelu_fwd_f32(const float* x, float* y, const float* gamma
                                     float* avg_var, float* save_mean, float* save_invstd, int n, int c, int hw,
                                     float eps, float decay, int train, cudaStream_t st) {
   DBM_REQUIRE(n > 0 && c > 0 && hw > 0, "bn: empty input");
-  bn_stats_kernel<<<c, 256, 0, st>>>(x, n, c, hw, eps, decay, train, avg_mean, avg_var, save_mean, save_invstd);
+  DBM_REQUIRE(c <= kBnMaxC && (long)n * hw < (1L << 31), "bn: %d channels / %d x %d elements exceed the reduction scratch", c, n, hw);
+  bn_stats_kernel<<<dim3(c, train ? bn_split(n, c) : 1), 256, 0, st>>>(x, n, c, hw, eps, decay, train, avg_mean, avg_var, save_mean, save_invstd);
   int rc = check_launch("bn_stats");
   if (rc) return rc;
   const long total = (long)n * c * hw;
@@ -305,7 +362,8 @@ extern "C" int dbm_bn_lrelu_bwd_f32(const float* x, const float* y, const float*
                                     const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
                                     float* scratch2c, int n, int c, int hw, cudaStream_t st) {
   DBM_REQUIRE(n > 0 && c > 0 && hw > 0, "bn_bwd: empty input");
-  bn_bwd_reduce_kernel<<<c, 256, 0, st>>>(x, y, dy, n, c, hw, save_mean, save_invstd, dgamma, dbeta, scratch2c,
+  DBM_REQUIRE(c <= kBnMaxC && (long)n * hw < (1L << 31), "bn_bwd: %d channels / %d x %d elements exceed the reduction scratch", c, n, hw);
+  bn_bwd_reduce_kernel<<<dim3(c, bn_split(n, c)), 256, 0, st>>>(x, y, dy, n, c, hw, save_mean, save_invstd, dgamma, dbeta, scratch2c,
                                           scratch2c + c);
   int rc = check_launch("bn_bwd_reduce");
   if (rc) return rc;

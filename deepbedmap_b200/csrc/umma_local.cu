@@ -56,6 +56,7 @@ struct LocalParams {
   int n, H, W, Wp, img, halo, G0, Pg, RA;
   const __nv_bfloat16* s0;  // flat bf16 [in_slabs][Pg][8]: stem output (forward) / bf16 d(loss)/d(a3) (backward)
   int in_slabs;             // 16 / 8
+  int group;                // images a CTA carries in lock step: 2, or 1 when the batch has fewer images than 2 x SMs
   float* x0;                // scratch [n][16][128][4]: pre-residual output (fp32)                  (forward)
   float* xrr;               // scratch [n][16][128][4]: input of the current RRDB (fp32) / gradient wrt the input
                             // of the RRDB behind the current one (backward)
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kLocThreads, 1) local_trunk_kernel(const Local
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int npairs = (p.n + 1) >> 1;
+  const int npairs = (p.n + p.group - 1) / p.group;
   const uint32_t load_rows = (uint32_t)(2 * p.halo + p.img);
 
   if (warp == 0) {
@@ -130,10 +131,10 @@ __global__ void __launch_bounds__(kLocThreads, 1) local_trunk_kernel(const Local
       int s = 0; uint32_t ph = 0; int it = 0;
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
         if (it > 0) mbar_wait(a_free, (uint32_t)((it - 1) & 1));
-        const int nact = (2 * pair + 1 < p.n) ? 2 : 1;
+        const int nact = min(p.group, p.n - p.group * pair);
         mbar_arrive_expect_tx(in_full, (uint32_t)(nact * p.in_slabs) * load_rows * 16u);
         for (int g = 0; g < nact; ++g) {
-          const long pos0 = (long)p.G0 + (long)(2 * pair + g) * p.img - p.halo;
+          const long pos0 = (long)p.G0 + (long)(p.group * pair + g) * p.img - p.halo;
           for (int sl = 0; sl < p.in_slabs; ++sl)
             bulk_load(abuf + g * abuf_bytes + sl * slab_bytes, p.s0 + ((long)sl * p.Pg + pos0) * 8, load_rows * 16u,
                       in_full);
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(kLocThreads, 1) local_trunk_kernel(const Local
     const uint32_t ab_u = smem_u32(abuf), st_u = smem_u32(stages);
     int s = 0; uint32_t ph = 0, actph = 0; int it = 0; long gp = 0;
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
-      const int nact = (2 * pair + 1 < p.n) ? 2 : 1;
+      const int nact = min(p.group, p.n - p.group * pair);
       mbar_wait(in_full, (uint32_t)(it & 1));
       for (int l = 0; l < p.count; ++l, ++gp) {
         const int N = p.passes[l].N, nk = p.passes[l].nk, slab0 = p.passes[l].slab0, col0 = p.passes[l].col0;
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kLocThreads, 1) local_trunk_kernel(const Local
     const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(g * kLocSlot);
     uint32_t tph = 0;
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      const int im = 2 * pair + g;
+      const int im = g < p.group ? p.group * pair + g : p.n;   // slot 1 idles when group == 1
       const bool interior = im < p.n && m < p.img && y >= 1 && y <= p.H && x >= 1 && x <= p.W;
       const long gpos = (long)p.G0 + (long)im * p.img + m;                 // flat position
       float* x0p = p.x0 + ((size_t)im * 16 * 128 + m) * 4;                 // + c4 * 512
@@ -434,6 +435,8 @@ __global__ void __launch_bounds__(kLocThreads, 1) local_trunk_kernel(const Local
 
 using namespace dbm;
 
+static int g_local_group = 0;  // dbm_debug_set(4, v): force images per CTA (tuning)
+
 static int local_trunk_launch(bool bwd, const void* passes_dev, int count, int n, int h, int w, const void* in_flat,
                               float* x0_scratch, float* xrr_scratch, cudaStream_t stream) {
   const char* who = bwd ? "trunk_local_bwd" : "trunk_local_fwd";
@@ -460,11 +463,19 @@ static int local_trunk_launch(bool bwd, const void* passes_dev, int count, int n
     else DBM_CUDA(cudaFuncSetAttribute(local_trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem[bwd] = smem;
   }
-  const int npairs = (n + 1) / 2;
+  // one image per CTA while that still leaves SMs idle (the filter stream is then read once per image instead of
+  // once per pair, but twice as many SMs work), else pairs
+  p.group = (g_local_group > 0) ? g_local_group : (n <= num_sms() ? 1 : 2);
+  const int npairs = (n + p.group - 1) / p.group;
   const int grid = npairs < num_sms() ? npairs : num_sms();
   if (bwd) local_trunk_kernel<true><<<grid, kLocThreads, smem, stream>>>(p);
   else local_trunk_kernel<false><<<grid, kLocThreads, smem, stream>>>(p);
   return check_launch(bwd ? "local_trunk_kernel<bwd>" : "local_trunk_kernel<fwd>");
+}
+
+extern "C" int dbm_local_debug_set(int value) {
+  g_local_group = value;
+  return DBM_OK;
 }
 
 extern "C" int dbm_trunk_local_fwd(const void* passes_dev, int count, int n, int h, int w, const void* s0_flat,

@@ -165,6 +165,8 @@ int dbm_trunk_local_fwd(const void* passes_dev, int count, int n, int h, int w, 
 /* The data-gradient chain of the same trunk (autograd of the links above in g_loss.backward(), srgan_train.py:1256),
  * image-resident: gradients wrt the dense-block slots accumulate in TMEM, the bf16 gradients wrt every conv output
  * are written to the flat buffers dbm_flat_wgrad reads. gpost_flat: bf16(d loss / d a3), flat [8][Pg][8]. */
+/* tuning: force the number of images a CTA carries (1 or 2; 0 = automatic) */
+int dbm_local_debug_set(int value);
 int dbm_trunk_local_bwd(const void* passes_dev, int count, int n, int h, int w, const void* gpost_flat,
                         float* dxrr_scratch, cudaStream_t stream);
 int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h, int w, cudaStream_t stream);

@@ -62,6 +62,11 @@ for e in ev:
     agg[k][1] += e.time_range.end - e.time_range.start
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{v[1] / steps:9.1f} us/step  n/step={v[0] / steps:6.1f}  avg={v[1] / v[0]:8.1f} us  {k}")
+# per-launch durations of the multi-launch tensor-core kernels (one step's worth, in launch order)
+per = len(ev) // steps
+for key in ("flat_wgrad_kernel", "flat_wgrad_reduce", "flat_conv_kernel", "gemm_f32_kernel", "bn_", "flat_to_nchw", "flat_from_nchw"):
+    d = [round(e.time_range.end - e.time_range.start, 1) for e in sorted(ev, key=lambda e: e.time_range.start)[:per] if key in e.name]
+    print(f"{key}: {d}")
 # the largest gaps in the timeline (host-bound stretches)
 gaps = sorted(((iv[i + 1][0] - max(x[1] for x in iv[max(0, i - 3):i + 1]), i) for i in range(len(iv) - 1)), reverse=True)[:10]
 print("largest idle gaps (us):", [round(gp, 1) for gp, _ in gaps])
