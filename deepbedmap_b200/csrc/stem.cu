@@ -25,6 +25,7 @@ struct StemParams {
   __nv_bfloat16* out;              // slab8 [N][out_cs_total][H][W][8], channels written at slab out_cs0..+16
   int out_cs_total, out_cs0;
   int N, h, w, H, W, tiles_x, tiles_y;
+  int flat_Pg, flat_G0;            // > 0: write the flat-padded layout [16][Pg][8] of umma_flat.cu / umma_local.cu instead
 };
 
 __device__ __forceinline__ void store_pair(const StemParams& p, int n, int slab, int y, int x, const float (&a)[2][8],
@@ -36,8 +37,10 @@ __device__ __forceinline__ void store_pair(const StemParams& p, int n, int slab,
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         v[k] = __floats2bfloat162_rn(a[i][2 * k] + bias8[2 * k], a[i][2 * k + 1] + bias8[2 * k + 1]);
-      *reinterpret_cast<uint4*>(p.out + ((((size_t)n * p.out_cs_total + p.out_cs0 + slab) * p.H + y) * p.W + x + i) * 8) =
-          *reinterpret_cast<uint4*>(v);
+      const size_t at = p.flat_Pg > 0
+                            ? (size_t)slab * p.flat_Pg + p.flat_G0 + ((size_t)n * (p.H + 2) + y + 1) * (p.W + 2) + x + i + 1
+                            : (((size_t)n * p.out_cs_total + p.out_cs0 + slab) * p.H + y) * p.W + x + i;
+      *reinterpret_cast<uint4*>(p.out + at * 8) = *reinterpret_cast<uint4*>(v);
     }
   }
 }
@@ -194,10 +197,9 @@ extern "C" int dbm_transpose_f32(const float* src, float* dst, int rows, int col
   return check_launch("transpose");
 }
 
-extern "C" int dbm_stem_fwd_slab8(const float* x, const float* w1, const float* w2, const float* w3,
-                                  const float* w1_filter_tapmajor, const float* small_filters_tapmajor,
-                                  const float* bias128, void* out_slab8, int out_cs_total, int out_cs0, int n, int h,
-                                  int w, cudaStream_t stream) {
+static int stem_launch(const float* x, const float* w1, const float* w2, const float* w3,
+                       const float* w1_filter_tapmajor, const float* small_filters_tapmajor, const float* bias128,
+                       void* out_slab8, int out_cs_total, int out_cs0, int n, int h, int w, int flat, cudaStream_t stream) {
   DBM_REQUIRE(n > 0 && h >= 3 && w >= 3, "stem: input %dx%d too small (need >= 3x3)", h, w);
   DBM_REQUIRE(out_cs_total >= out_cs0 + 16, "stem: output needs 16 slabs");
   static bool attr_done = false;
@@ -210,9 +212,30 @@ extern "C" int dbm_stem_fwd_slab8(const float* x, const float* w1, const float* 
   p.wt1 = w1_filter_tapmajor; p.wts = small_filters_tapmajor; p.bias = bias128;
   p.out = (__nv_bfloat16*)out_slab8; p.out_cs_total = out_cs_total; p.out_cs0 = out_cs0;
   p.N = n; p.h = h; p.w = w; p.H = h - 2; p.W = w - 2;
+  p.flat_Pg = 0; p.flat_G0 = 0;
+  if (flat) {   // geometry of flat_geom() in umma_flat.cu for n images of H x W
+    const int halo = p.W + 3;
+    p.flat_G0 = (halo + 7) & ~7;
+    p.flat_Pg = 2 * p.flat_G0 + 128 * ceil_div((long)n * (p.H + 2) * (p.W + 2), 128);
+  }
   p.tiles_x = ceil_div(p.W, kSTW); p.tiles_y = ceil_div(p.H, kSTH);
   const long blocks = (long)n * p.tiles_x * p.tiles_y;
   DBM_REQUIRE(blocks < (1L << 31), "stem: too many tiles");
   stem_kernel<<<(int)blocks, 256, kStemSmem, stream>>>(p);
   return check_launch("stem_kernel");
+}
+
+extern "C" int dbm_stem_fwd_slab8(const float* x, const float* w1, const float* w2, const float* w3,
+                                  const float* w1_filter_tapmajor, const float* small_filters_tapmajor,
+                                  const float* bias128, void* out_slab8, int out_cs_total, int out_cs0, int n, int h,
+                                  int w, cudaStream_t stream) {
+  return stem_launch(x, w1, w2, w3, w1_filter_tapmajor, small_filters_tapmajor, bias128, out_slab8, out_cs_total, out_cs0,
+                     n, h, w, 0, stream);
+}
+
+extern "C" int dbm_stem_fwd_flat(const float* x, const float* w1, const float* w2, const float* w3,
+                                 const float* w1_filter_tapmajor, const float* small_filters_tapmajor,
+                                 const float* bias128, void* out_flat, int n, int h, int w, cudaStream_t stream) {
+  return stem_launch(x, w1, w2, w3, w1_filter_tapmajor, small_filters_tapmajor, bias128, out_flat, 16, 0, n, h, w, 1,
+                     stream);
 }

@@ -378,8 +378,25 @@ __global__ void __launch_bounds__(kLocThreads, 1) local_trunk_kernel(const Local
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4) {
                 const float4 t = *reinterpret_cast<const float4*>(x0p + (size_t)(8 * h + c4) * 512);
-                *reinterpret_cast<float4*>(P.out_f32 + ((size_t)(8 * h + c4) * p.Pg + gpos) * 4) =
-                    make_float4(t.x + v[4 * c4], t.y + v[4 * c4 + 1], t.z + v[4 * c4 + 2], t.w + v[4 * c4 + 3]);
+                v[4 * c4] += t.x; v[4 * c4 + 1] += t.y; v[4 * c4 + 2] += t.z; v[4 * c4 + 3] += t.w;   // a3 = a1 + conv (:551)
+                if (P.out_f32 != nullptr)
+                  *reinterpret_cast<float4*>(P.out_f32 + ((size_t)(8 * h + c4) * p.Pg + gpos) * 4) =
+                      make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+              }
+              if (P.save != nullptr) {
+                // inference: a3 goes straight to the first upsample conv as bf16 slab8 [n][8][2H][2W][8], nearest x2
+                // (F.resize_images, srgan_train.py:556-558) fused into the store
+                const int Ho = 2 * p.H, Wo = 2 * p.W;
+#pragma unroll
+                for (int s8 = 0; s8 < 4; ++s8) {
+                  const uint4 o = pack8f(v + 8 * s8);
+                  __nv_bfloat16* base =
+                      P.save + ((((size_t)im * 8 + 4 * h + s8) * Ho + 2 * (y - 1)) * Wo + 2 * (x - 1)) * 8;
+                  *reinterpret_cast<uint4*>(base) = o;
+                  *reinterpret_cast<uint4*>(base + 8) = o;
+                  *reinterpret_cast<uint4*>(base + (size_t)Wo * 8) = o;
+                  *reinterpret_cast<uint4*>(base + (size_t)Wo * 8 + 8) = o;
+                }
               }
             }
             continue;

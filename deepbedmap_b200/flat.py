@@ -52,9 +52,10 @@ def local_pass(**kw):
     return e
 
 
-def local_forward_table(model, pk, nrdb, beta, cat_ptr=None, out_f32=0):
+def local_forward_table(model, pk, nrdb, beta, cat_ptr=None, out_f32=0, up2_out=0):
     """Pass table of dbm_trunk_local_fwd for ``model``'s packed operands. ``cat_ptr(j, c)``: flat bf16 address of
-    channel c of dense-block buffer j (None: inference, nothing is kept); ``out_f32``: flat fp32 slab4 output."""
+    channel c of dense-block buffer j (None: inference, nothing is kept); ``out_f32``: flat fp32 slab4 output;
+    ``up2_out``: bf16 slab8 (n, 8, 2H, 2W, 8) output, nearest-upsampled x2 (inference head)."""
     P = model.p
     save = (lambda j, c: cat_ptr(j, c)) if cat_ptr is not None else (lambda j, c: 0)
     passes = [local_pass(w=pk["pre_residual_conv_layer@trunk"][0].data_ptr(),
@@ -71,7 +72,8 @@ def local_forward_table(model, pk, nrdb, beta, cat_ptr=None, out_f32=0):
                 nk=4 if s == 0 else 2, N=192 - 32 * s, col0=32 * s, type=LOC_RDB if last else LOC_ACT, ecol=32 * s,
                 out_slab=0 if last else 8 + 4 * s, rr=int(last and r == 3), beta=beta, first=int(s == 0)))
     passes.append(local_pass(w=pk["post_residual_conv_layer@trunk"][0].data_ptr(),
-                             bias=P["post_residual_conv_layer/b"].data_ptr(), out_f32=out_f32, slab0=0, nk=4, N=64,
+                             bias=P["post_residual_conv_layer/b"].data_ptr(), out_f32=out_f32, save=up2_out, slab0=0,
+                             nk=4, N=64,
                              col0=0, type=LOC_POST, ecol=0, first=1))
     return np.ascontiguousarray(np.stack(passes))
 PARTIAL_FLOATS = 9 * 32 * 128
@@ -374,6 +376,7 @@ class FlatTrunk:
             ops.call("dbm_trunk_local_fwd", self.local_dev.data_ptr(), self.n_local, n, H, W, self.s0.data_ptr(),
                      self.x_scratch[0].data_ptr(), self.x_scratch[1].data_ptr(), st)
         else:
+            self.model._pack(self.model.PACK_TRAIN_CHAIN)   # the chain reads the per-layer 16-channel images
             self._chain(self.fwd, self.fwd_dev)
         a3 = ops.empty(n, 64, H, W)
         ops.call("dbm_flat_to_nchw", self.a3f.data_ptr(), None, a3.data_ptr(), 64, n, H, W, st)
@@ -390,6 +393,7 @@ class FlatTrunk:
             ops.call("dbm_trunk_local_bwd", self.local_bwd_dev.data_ptr(), self.n_local_bwd, n, H, W,
                      self.gpost.data_ptr(), self.x_scratch[1].data_ptr(), st)
         else:
+            self.model._pack(self.model.PACK_TRAIN_CHAIN)
             self._chain(self.bwd, self.bwd_dev)
         ops.call("dbm_flat_wgrad", self.units_dev.data_ptr(), self.n_units, n, H, W, st)
         ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, st)

@@ -181,6 +181,7 @@ class GeneratorModel(_Link):
         self.persistent_trunk = True   # one-launch trunk kernel (False: one launch per layer, for A/B tests)
         self.paired_trunk = True       # dense-block layer pairing inside the persistent kernel
         self.per_layer_ck16 = False    # per-layer launches in the trunk kernel's 16-channel chunks (bit-exact A/B)
+        self.local_trunk = True        # tiles of <= 128 padded positions: image-resident trunk kernel (umma_local.cu)
         self._ctx = None
 
     # ---- serialisation (chainer.serializers.load_npz / save_npz, App. C layout) ----
@@ -298,7 +299,7 @@ class GeneratorModel(_Link):
 
     def _flat_trunk(self, n, H, W):
         from . import flat
-        pk = self._pack()
+        pk = self._pack(self.PACK_TRAIN_LOCAL if flat.local_trunk_fits(H, W) else self.PACK_TRAIN_CHAIN)
         ft = self._flat.get((n, H, W))
         if ft is None:
             ft = self._flat[(n, H, W)] = flat.FlatTrunk(self, n, H, W)
@@ -491,25 +492,36 @@ class GeneratorModel(_Link):
         self._ctx = None
 
     # ---------------- bf16 tensor-core path (inference) ----------------
-    def _pack(self):
+    # groups of packed operand images (a training step must not pay for the inference-only ones)
+    PACK_INFER = ("io", "trunk16", "infer")                 # tiled / persistent tensor-core inference
+    PACK_INFER_LOCAL = ("io", "stat", "infer")              # inference on tiles that fit the image-resident kernel
+    PACK_TRAIN_LOCAL = ("io", "stat", "dgrad")              # training, image-resident trunk
+    PACK_TRAIN_CHAIN = ("io", "trunk16", "stat", "dgrad")   # training, flat chain (any tile size)
+
+    def _pack(self, groups=None):
         """bf16 UMMA operand images of every 3x3 filter (+ the stem's tap-major fp32 filters). The
-        buffers and a device table describing them are created once; after a weight update (training)
-        the whole set is refreshed by ONE table-driven launch (dbm_pack_conv3x3_table)."""
-        if self._packed_version == self.version:
-            return self._packed
+        buffers and device tables describing them are created once; after a weight update (training)
+        the groups a caller needs are refreshed by one table-driven launch each (dbm_pack_conv3x3_table):
+          io      pre-/post-residual conv in 16-channel chunks (every trunk kernel)
+          trunk16 dense-block convs in 16-channel chunks (persistent inference trunk, flat training chain)
+          infer   32-channel-chunk images, pair/tail images, head convs, stem filters, padded biases
+          stat    input-stationary slices (image-resident small-tile trunk)
+          dgrad   transposed + flipped filters (data gradients)"""
+        if groups is None:
+            groups = self.PACK_INFER
         P = self.p
         if self._pack_plan is None:
             pk = {}
-            entries = []      # (w, out, O, o0, Cin, CinTotal, c0, COUTP, CK)
+            entries = {g: [] for g in ("io", "trunk16", "infer", "stat", "dgrad")}
             pad_biases = []   # (padded bias buffer, source bias)
 
             def image(cin, cout_padded):
                 return ops.zeros(9 * cin * cout_padded, dtype=torch.bfloat16)
 
-            def entry(w, out, o, o0, cin, cin_total, c0, coutp, ck, mode=0):
-                entries.append((w.data_ptr(), out.data_ptr(), o, o0, cin, cin_total, c0, coutp, ck, mode))
+            def entry(grp, w, out, o, o0, cin, cin_total, c0, coutp, ck, mode=0):
+                entries[grp].append((w.data_ptr(), out.data_ptr(), o, o0, cin, cin_total, c0, coutp, ck, mode))
 
-            def add(key, cout_padded, trunk=False, ck=32):
+            def add(key, cout_padded, trunk=None, ck=32):
                 w, b = P[f"{key}/W"], P[f"{key}/b"]
                 o, cin = w.shape[0], w.shape[1]
                 if b.numel() < cout_padded:
@@ -518,27 +530,27 @@ class GeneratorModel(_Link):
                 else:
                     bp = b
                 img = image(cin, cout_padded)
-                entry(w, img, o, 0, cin, cin, 0, cout_padded, ck)
+                entry("infer", w, img, o, 0, cin, cin, 0, cout_padded, ck)
                 pk[key] = (img, bp)
-                if trunk:
-                    # the persistent trunk kernel streams every layer in 16-channel chunks
+                if trunk is not None:
+                    # the trunk kernels stream every layer in 16-channel chunks
                     img16 = image(cin, cout_padded)
-                    entry(w, img16, o, 0, cin, cin, 0, cout_padded, 16)
+                    entry(trunk, w, img16, o, 0, cin, cin, 0, cout_padded, 16)
                     pk[key + "@trunk"] = (img16, bp)
                     if self.train_precision == "bf16":
                         # data-gradient operand (transposed + flipped filter): GEMM N = cin, K = cout
                         imgd = image(cin, o)
-                        entry(w, imgd, cin, 0, o, cin, 0, cin, 16, mode=1)
+                        entry("dgrad", w, imgd, cin, 0, o, cin, 0, cin, 16, mode=1)
                         pk[key + "@dgrad"] = imgd
 
-            add("pre_residual_conv_layer", 64, trunk=True)
+            add("pre_residual_conv_layer", 64, trunk="io")
             for i in range(self.num_residual_blocks):
                 for r in (1, 2, 3):
                     pre = self._rdb_prefix(i, r)
                     for k in (1, 2, 3, 4):
-                        add(f"{pre}/conv_layer{k}", self.inter_channels, trunk=True)
-                    add(f"{pre}/conv_layer5", 64, trunk=True)
-            add("post_residual_conv_layer", 64, trunk=True)
+                        add(f"{pre}/conv_layer{k}", self.inter_channels, trunk="trunk16")
+                    add(f"{pre}/conv_layer5", 64, trunk="trunk16")
+            add("post_residual_conv_layer", 64, trunk="io")
             if self.inter_channels == 32:
                 # dense-block pairing (see _trunk_workspace): conv_k and the partial sums of conv_{k+1}
                 # over their shared inputs are one 64-wide MMA pass; conv_{k+1} then only contracts a_k
@@ -549,11 +561,11 @@ class GeneratorModel(_Link):
                             cin = 64 + (k - 1) * 32
                             wa, wb = P[f"{pre}/conv_layer{k}/W"], P[f"{pre}/conv_layer{k + 1}/W"]
                             both = image(cin, 64)
-                            entry(wa, both, 32, 0, cin, cin, 0, 64, 16)
-                            entry(wb, both, 32, 32, cin, cin + 32, 0, 64, 16)
+                            entry("infer", wa, both, 32, 0, cin, cin, 0, 64, 16)
+                            entry("infer", wb, both, 32, 32, cin, cin + 32, 0, 64, 16)
                             pk[f"{pre}/pair{k}"] = (both, P[f"{pre}/conv_layer{k}/b"])
                             tail = image(32, 32)
-                            entry(wb, tail, 32, 0, 32, cin + 32, cin, 32, 16)
+                            entry("infer", wb, tail, 32, 0, 32, cin + 32, cin, 32, 16)
                             pk[f"{pre}/tail{k + 1}"] = (tail, P[f"{pre}/conv_layer{k + 1}/b"])
                 # input-stationary slices for the image-resident small-tile trunk (csrc/umma_local.cu): pass s
                 # contracts block a_s (a0 = 64 channels, a1..a4 = 32) against its rows in conv_{s+1}..conv_5
@@ -566,8 +578,8 @@ class GeneratorModel(_Link):
                             ncol = 192 - 32 * s_
                             stat = image(cblk, ncol)
                             for k in range(s_ + 1, 6):
-                                entry(P[f"{pre}/conv_layer{k}/W"], stat, 64 if k == 5 else 32, 32 * (k - 1 - s_), cblk,
-                                      64 + 32 * (k - 1), c0, ncol, 16)
+                                entry("stat", P[f"{pre}/conv_layer{k}/W"], stat, 64 if k == 5 else 32, 32 * (k - 1 - s_),
+                                      cblk, 64 + 32 * (k - 1), c0, ncol, 16)
                             pk[f"{pre}/stat{s_}"] = stat
             for key in ("post_upsample_conv_layer_1", "post_upsample_conv_layer_2"):
                 add(key, 64)
@@ -577,29 +589,38 @@ class GeneratorModel(_Link):
             # stem filters, tap-major, and the concatenated stem bias
             taps = {k: int(P[f"input_block/conv_on_{k}/W"][0].numel()) for k in ("X", "W1", "W2", "W3")}
             pk["stem"] = (ops.empty(taps["W1"], 32), ops.empty(taps["X"] + taps["W2"] + taps["W3"], 32), ops.empty(128))
-            table = np.array(entries, dtype=PACK_ENTRY_DTYPE)
-            self._pack_plan = dict(table=torch.from_numpy(table.view(np.uint8).copy()).cuda(), n=len(entries),
-                                   max_elements=max(9 * e[4] * e[7] for e in entries), pad_biases=pad_biases,
-                                   taps=taps)
+            tables = {}
+            for g, ent in entries.items():
+                if ent:
+                    table = np.array(ent, dtype=PACK_ENTRY_DTYPE)
+                    tables[g] = dict(table=torch.from_numpy(table.view(np.uint8).copy()).cuda(), n=len(ent),
+                                     max_elements=max(9 * e[4] * e[7] for e in ent))
+            self._pack_plan = dict(tables=tables, pad_biases=pad_biases, taps=taps)
             self._packed = pk
+            self._pack_versions = {g: -1 for g in tables}
             self._pack_gen += 1
         plan, pk = self._pack_plan, self._packed
-        ops.call("dbm_pack_conv3x3_table", plan["table"].data_ptr(), plan["n"], plan["max_elements"], ops.stream())
-        for bp, b in plan["pad_biases"]:
-            ops.axpby(b.view(1, b.numel(), 1, 1), 0, None, 0, bp.view(1, bp.numel(), 1, 1), 0, b.numel(), 1.0, 0.0)
-        wt1, wts, bias128 = pk["stem"]
-        r0 = 0
-        for k, dst in (("W1", wt1), ("X", wts), ("W2", wts), ("W3", wts)):
-            nt = plan["taps"][k]
-            row = 0 if k == "W1" else r0
-            ops.call("dbm_transpose_f32", P[f"input_block/conv_on_{k}/W"].data_ptr(), dst[row:].data_ptr(), 32, nt,
-                     ops.stream())
-            if k != "W1":
-                r0 += nt
-        for j, k in enumerate(("X", "W1", "W2", "W3")):
-            ops.axpby(P[f"input_block/conv_on_{k}/b"].view(1, 32, 1, 1), 0, None, 0,
-                      bias128.view(1, 128, 1, 1), 32 * j, 32, 1.0, 0.0)
-        self._packed_version = self.version
+        for g in groups:
+            t = plan["tables"].get(g)
+            if t is None or self._pack_versions[g] == self.version:
+                continue
+            ops.call("dbm_pack_conv3x3_table", t["table"].data_ptr(), t["n"], t["max_elements"], ops.stream())
+            if g == "infer":
+                for bp, b in plan["pad_biases"]:
+                    ops.axpby(b.view(1, b.numel(), 1, 1), 0, None, 0, bp.view(1, bp.numel(), 1, 1), 0, b.numel(), 1.0, 0.0)
+                wt1, wts, bias128 = pk["stem"]
+                r0 = 0
+                for k, dst in (("W1", wt1), ("X", wts), ("W2", wts), ("W3", wts)):
+                    nt = plan["taps"][k]
+                    row = 0 if k == "W1" else r0
+                    ops.call("dbm_transpose_f32", P[f"input_block/conv_on_{k}/W"].data_ptr(), dst[row:].data_ptr(), 32, nt,
+                             ops.stream())
+                    if k != "W1":
+                        r0 += nt
+                for j, k in enumerate(("X", "W1", "W2", "W3")):
+                    ops.axpby(P[f"input_block/conv_on_{k}/b"].view(1, 32, 1, 1), 0, None, 0,
+                              bias128.view(1, 128, 1, 1), 32 * j, 32, 1.0, 0.0)
+            self._pack_versions[g] = self.version
         return pk
 
     def _trunk_workspace(self, n, H, W):
@@ -692,17 +713,47 @@ class GeneratorModel(_Link):
                      out or None, out_cs_total, out_cs0, out_f32 or None, 16, 0, res1 or None, res2 or None, ops.stream())
         ops.call("dbm_debug_set", 2, 0)
 
+    def _local_workspace(self, n, H, W, pk):
+        """Buffers + pass table of the image-resident trunk (csrc/umma_local.cu) for inference on small tiles."""
+        from . import flat
+        key = ("local", n, H, W)
+        ws = self._ws.get(key)
+        if ws is None or ws["version"] != (self._pack_gen, self.residual_scaling):
+            geom = flat.geometry(n, H, W)
+            if ws is None:
+                ws = dict(s0=torch.zeros(16, geom["Pg"], 8, dtype=torch.bfloat16, device="cuda"),
+                          x=torch.empty(2, n * 16 * 128 * 4, dtype=torch.float32, device="cuda"),
+                          u1=ops.empty(n, 8, 2 * H, 2 * W, 8, dtype=torch.bfloat16))
+            tab = flat.local_forward_table(self, pk, 3 * self.num_residual_blocks, self.residual_scaling,
+                                           up2_out=ws["u1"].data_ptr())
+            ws["table"] = torch.from_numpy(tab.view(np.uint8).reshape(-1).copy()).cuda()
+            ws["count"] = len(tab)
+            ws["version"] = (self._pack_gen, self.residual_scaling)
+            self._ws[key] = ws
+        return ws
+
     def _forward_bf16(self, x, w1, w2, w3):
+        from . import flat
         P = self.p
-        pk = self._pack()
         n, _, h, w = x.shape
         H, W = h - 2, w - 2
         bf = torch.bfloat16
-        ws = self._trunk_workspace(n, H, W)
+        local = self.local_trunk and self.inter_channels == 32 and flat.local_trunk_fits(H, W)
+        pk = self._pack(self.PACK_INFER_LOCAL if local else self.PACK_INFER)
         wt1, wts, bias128 = pk["stem"]
-        ops.call("dbm_stem_fwd_slab8", x.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), wt1.data_ptr(),
-                 wts.data_ptr(), bias128.data_ptr(), ws["s0"].data_ptr(), 16, 0, n, h, w, ops.stream())
-        self._run_trunk(ws, n, H, W)
+        if local:
+            # small tiles (the reference's 11x11 training / doctest windows): stem -> flat layout -> the whole trunk
+            # with the activations of an image resident in shared memory / TMEM
+            ws = self._local_workspace(n, H, W, pk)
+            ops.call("dbm_stem_fwd_flat", x.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), wt1.data_ptr(),
+                     wts.data_ptr(), bias128.data_ptr(), ws["s0"].data_ptr(), n, h, w, ops.stream())
+            ops.call("dbm_trunk_local_fwd", ws["table"].data_ptr(), ws["count"], n, H, W, ws["s0"].data_ptr(),
+                     ws["x"][0].data_ptr(), ws["x"][1].data_ptr(), ops.stream())
+        else:
+            ws = self._trunk_workspace(n, H, W)
+            ops.call("dbm_stem_fwd_slab8", x.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), wt1.data_ptr(),
+                     wts.data_ptr(), bias128.data_ptr(), ws["s0"].data_ptr(), 16, 0, n, h, w, ops.stream())
+            self._run_trunk(ws, n, H, W)
         u1 = ws["u1"]
         u2 = ops.empty(n, 8, 4 * H, 4 * W, 8, dtype=bf)
         wq, bq = pk["post_upsample_conv_layer_1"]

@@ -194,6 +194,11 @@ int dbm_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStre
 int dbm_stem_fwd_slab8(const float* x, const float* w1, const float* w2, const float* w3,
                        const float* w1_filter_tapmajor, const float* small_filters_tapmajor, const float* bias128,
                        void* out_slab8, int out_cs_total, int out_cs0, int n, int h, int w, cudaStream_t stream);
+/* Same fused input block, written in the flat-padded layout [16][Pg][8] (geometry of dbm_flat_geometry(n, h-2, w-2));
+ * borders / guards of out_flat must be zero (they are never written). Feeds dbm_trunk_local_fwd on small tiles. */
+int dbm_stem_fwd_flat(const float* x, const float* w1, const float* w2, const float* w3, const float* w1_filter_tapmajor,
+                      const float* small_filters_tapmajor, const float* bias128, void* out_flat, int n, int h, int w,
+                      cudaStream_t stream);
 
 /* ---- deformable convolution, tensor-core inference path (L.DeformableConvolution2D 64->64 and 64->1,
  * srgan_train.py:506-523, 572-574): bilinear gather straight into the UMMA operand layout in SMEM,

@@ -27,6 +27,7 @@ def timed(fn):
 
 
 ft.forward(a0)
+m._pack(m.PACK_TRAIN_CHAIN)
 for label, local, group in (("flat chain", False, 0), ("image-resident, 1 image/CTA", True, 1), ("image-resident, 2 images/CTA", True, 2)):
     ft.local = local
     ops.call("dbm_local_debug_set", group)

@@ -14,7 +14,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from deepbedmap_b200 import GeneratorModel  # noqa: E402
+from deepbedmap_b200 import GeneratorModel, flat, ops  # noqa: E402
 
 
 def macs_per_trunk_px(nb, g):
@@ -46,7 +46,7 @@ def main():
     depths = (8, 12, 23) if quick else (8, 10, 12, 14, 23)
     shapes = [("128 tiles 11x11", 128, 11, 11), ("1024 tiles 11x11", 1024, 11, 11), ("1 tile 288x288", 1, 288, 288)]
     print(f"bf16 sustained peak {peak:.1f} TFLOP/s (MEASURED_PEAKS.json); activations exceed L2 at every size below "
-          f"except 128 tiles; forward = whole generator, trunk = umma_trunk_kernel alone (CUDA events)")
+          f"except 128 tiles; forward = whole generator, trunk = the trunk kernel forward() runs, alone: local_trunk_kernel on 11x11 tiles with inter_channels 32, else umma_trunk_kernel (CUDA events)")
     print(f"{'workload':18s} {'nb':>3s} {'inter':>5s} {'GFLOP fwd':>10s} {'fwd ms':>8s} {'fwd TF/s':>9s} {'frac':>6s} "
           f"{'trunk ms':>9s} {'trunk TF/s':>10s} {'frac':>6s}")
     for label, n, h, w in shapes:
@@ -59,9 +59,16 @@ def main():
                 total, trunk = macs_per_trunk_px(nb, inter)
                 px = n * (h - 2) * (w - 2)
                 ms = timed(lambda: m.forward(*ins))
-                ws = m._trunk_workspace(n, h - 2, w - 2)
-                assert abs(ws["flops"] - 2.0 * trunk * px) < 1e-6 * ws["flops"]
-                tms = timed(lambda: m._run_trunk(ws, n, h - 2, w - 2))
+                if m.local_trunk and inter == 32 and flat.local_trunk_fits(h - 2, w - 2):
+                    # small tiles: the image-resident kernel (csrc/umma_local.cu) is the trunk forward() runs
+                    ws = m._local_workspace(n, h - 2, w - 2, m._pack(m.PACK_INFER_LOCAL))
+                    tms = timed(lambda: ops.call("dbm_trunk_local_fwd", ws["table"].data_ptr(), ws["count"], n, h - 2, w - 2,
+                                                 ws["s0"].data_ptr(), ws["x"][0].data_ptr(), ws["x"][1].data_ptr(),
+                                                 ops.stream()))
+                else:
+                    ws = m._trunk_workspace(n, h - 2, w - 2)
+                    assert abs(ws["flops"] - 2.0 * trunk * px) < 1e-6 * ws["flops"]
+                    tms = timed(lambda: m._run_trunk(ws, n, h - 2, w - 2))
                 tf, ttf = 2.0 * total * px / ms / 1e9, 2.0 * trunk * px / tms / 1e9
                 print(f"{label:18s} {nb:3d} {inter:5d} {2.0 * total * px / 1e9:10.2f} {ms:8.3f} {tf:9.1f} {tf / peak:6.3f} "
                       f"{tms:9.3f} {ttf:10.1f} {ttf / peak:6.3f}", flush=True)

@@ -87,7 +87,7 @@ def test_generator_bf16_against_golden(golden, case):
     params, ins = MG.generator_case(nb, n, h, w, regime, scale, bias_std)
     got = _load_gen(nb, params, "bf16").forward(*ins).numpy()
     ref = golden[f"{name}/y"]
-    assert rel_l2(got, golden[f"{name}/y_bf16_emulated"]) < 6e-3
+    assert rel_l2(got, golden[f"{name}/y_bf16_emulated"]) < 8e-3
     assert rel_l2(got, ref) < 2e-2 and np.abs(got - ref).max() < 3e-2 * np.abs(ref).max()
 
 
