@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MPX = 396.0  # 18000 x 22000 output pixels
-TRUNK_DRAM_BYTES_PER_FLOP = 25.05e9 / 5.717e12  # measured, see instrumented_roofline()
+TRUNK_DRAM_BYTES_PER_FLOP = 24.515e9 / 5.717e12  # measured, see instrumented_roofline()
 FULL = dict(final_shape=(18000, 22000), ary_shape=(1000, 1000), grid=(4502, 5502))
 
 
@@ -129,7 +129,7 @@ def max_over_ranks(ms, world):
 # --------------------------------------------------------------------------------------------
 # CPU baseline (the oracle port; the only place besides tests where oracle/ is executed)
 # --------------------------------------------------------------------------------------------
-def cpu_reference_rate(crop=96, reps=2, warm=1, nb=12):
+def cpu_reference_rate(crop=192, reps=3, warm=1, nb=12):
     """Times the reference graph (torch-CPU fp32 restatement) on one crop x crop lowres window
     and extrapolates to the continent by computed-pixel count. Returns (Mpx/s, cores, sample)."""
     from oracle import deepbedmap_oracle as O
@@ -224,11 +224,11 @@ def instrumented_roofline(model, grids, kw, peak_tf):
     dom = max(out, key=lambda k: out[k]["ms_total"])
     ach = out[dom]["tflops"]
     # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one
-    # `ncu --set full` capture (profiles/r1c_trunk_kernel_ncu_full_raw.csv: 14.17 + 10.88 GB for a launch of
+    # `ncu --set full` capture (profiles/r1h_trunk_kernel_ncu_full_raw.csv: 13.67 + 10.84 GB for a launch of
     # 4 interior tiles = 5.72 TFLOP), scaled to this run's average launch by its algorithmic FLOPs
     traffic = TRUNK_DRAM_BYTES_PER_FLOP * out[dom]["flops_per_launch_avg"] if dom == "umma_trunk_kernel" else None
     return {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-            "traffic": traffic, "traffic_source": "ncu --set full, profiles/r1c_trunk_kernel_ncu_full_raw.csv",
+            "traffic": traffic, "traffic_source": "ncu --set full, profiles/r1h_trunk_kernel_ncu_full_raw.csv",
             "kernel": dom, "launches_timed": out[dom]["launches_timed"],
             "avg_launch_us": out[dom]["avg_launch_us"], "flops_per_launch_avg": out[dom]["flops_per_launch_avg"],
             "all_tcgen05_conv_kernels": {k: {kk: vv for kk, vv in v.items() if kk != "ms_total"} | {
@@ -273,7 +273,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch-tiles", type=int, default=4)
-    ap.add_argument("--cpu-crop", type=int, default=96)
+    ap.add_argument("--cpu-crop", type=int, default=192)
     ap.add_argument("--scale", type=float, default=1.0, help="debug only: shrink the continent (invalid as a result)")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
