@@ -24,6 +24,7 @@ SIGNATURES = {
     "dbm_conv2d_bwd_weight_f32": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dbm_bias_grad_f32": [_P, _L, _P, _I, _I, _I, _P],
     "dbm_gemm_f32": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dbm_gemm_bf16": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _I, _I, _I, _I, _I, _I, _P],
     "dbm_axpby_f32": [_P, _L, _P, _L, _P, _L, _F, _F, _I, _L, _P],
     "dbm_lrelu_fwd_f32": [_P, _P, _L, _P],
     "dbm_lrelu_bwd_f32": [_P, _L, _P, _L, _P, _L, _I, _L, _I, _P],

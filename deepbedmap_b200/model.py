@@ -326,7 +326,7 @@ class GeneratorModel(_Link):
         c2 = conv("post_upsample_conv_layer_2", u2, True)
         off1 = conv("final_conv_layer1/offset_conv", c2, False)
         d1, cols1 = ops.deform_conv_fwd(c2, off1, P["final_conv_layer1/deform_conv/W"],
-                                        P["final_conv_layer1/deform_conv/b"], act=True)
+                                        P["final_conv_layer1/deform_conv/b"], act=True, tc=tc is not None)
         off2 = conv("final_conv_layer2/offset_conv", d1, False)
         if self.out_channels == 1:   # tap projection: 9 projected planes instead of a 576-row cols buffer
             y, cols2 = ops.deform1_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"],
@@ -411,7 +411,8 @@ class GeneratorModel(_Link):
         # ---- final_conv_layer1 ----
         dc2 = ops.zeros(n, 64, 4 * H, 4 * W)
         doff1 = ops.deform_conv_bwd(c["c2"], c["off1"], P["final_conv_layer1/deform_conv/W"], c["cols1"], dd1,
-                                    G["final_conv_layer1/deform_conv/W"], G["final_conv_layer1/deform_conv/b"], dc2)
+                                    G["final_conv_layer1/deform_conv/W"], G["final_conv_layer1/deform_conv/b"], dc2,
+                                    tc=c.get("head_tc") is not None)
         conv_bwd("final_conv_layer1/offset_conv", c["c2"], doff1, dx_accumulate_into=dc2)
         del dd1, doff1, doff2
         # ---- upsample convs ----

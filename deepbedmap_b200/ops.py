@@ -78,8 +78,9 @@ def conv2d_bwd_weight(x, x_c0, cin, dy, dy_c0, dw, k, s, p, db=None):
 
 
 def gemm(a, lda_m, lda_k, a_bs, b, ldb_k, ldb_n, b_bs, c, ldc_m, ldc_n, c_bs, bias, m, n, k, batch=1, act=False,
-         accumulate=0):
-    call("dbm_gemm_f32", a.data_ptr(), lda_m, lda_k, a_bs, b.data_ptr(), ldb_k, ldb_n, b_bs, c.data_ptr(), ldc_m,
+         accumulate=0, tc=False):
+    """Batched strided GEMM (+ bias per n, LeakyReLU). tc: operands rounded to bf16, tensor cores (dbm_gemm_bf16)."""
+    call("dbm_gemm_bf16" if tc else "dbm_gemm_f32", a.data_ptr(), lda_m, lda_k, a_bs, b.data_ptr(), ldb_k, ldb_n, b_bs, c.data_ptr(), ldc_m,
          ldc_n, c_bs, bias.data_ptr() if bias is not None else None, m, n, k, batch, int(act), accumulate, stream())
 
 
@@ -179,8 +180,9 @@ def conv3x3_umma(inp, cin, wpacked, bias, cout_padded, *, beta=0.0, act=False, u
 
 
 # ---- deformable conv (fp32 path) -----------------------------------------------------------------
-def deform_conv_fwd(x, offset, w, b, act=False):
-    """x (N,C,H,W), offset (N,18,H,W), w (O,C,3,3) -> y (N,O,H,W), cols (N, C*9, H*W) kept for backward."""
+def deform_conv_fwd(x, offset, w, b, act=False, tc=False):
+    """x (N,C,H,W), offset (N,18,H,W), w (O,C,3,3) -> y (N,O,H,W), cols (N, C*9, H*W) kept for backward.
+    tc: the contraction on the tensor cores with bf16-rounded operands (bf16 training path)."""
     n, c, h, wd = x.shape
     o = w.shape[0]
     hw = h * wd
@@ -189,22 +191,22 @@ def deform_conv_fwd(x, offset, w, b, act=False):
     y = empty(n, o, h, wd)
     k = c * 9
     # per image: y[o, p] = sum_k cols[k, p] * w[o, k]   (M = pixels, N = O)
-    gemm(cols, 1, hw, k * hw, w, 1, k, 0, y, 1, hw, o * hw, b, hw, o, k, batch=n, act=act)
+    gemm(cols, 1, hw, k * hw, w, 1, k, 0, y, 1, hw, o * hw, b, hw, o, k, batch=n, act=act, tc=tc)
     return y, cols
 
 
-def deform_conv_bwd(x, offset, w, cols, dy, dw, db, dx):
+def deform_conv_bwd(x, offset, w, cols, dy, dw, db, dx, tc=False):
     """Accumulates dw, db; dx += d/dx; returns doffset (N,18,H,W)."""
     n, c, h, wd = x.shape
     o = w.shape[0]
     hw = h * wd
     k = c * 9
     # dw[o, kk] += sum_{n,p} dy[n,o,p] * cols[n,kk,p]   (atomic across the batch)
-    gemm(dy, hw, 1, o * hw, cols, 1, hw, k * hw, dw, k, 1, 0, None, o, k, hw, batch=n, accumulate=2)
+    gemm(dy, hw, 1, o * hw, cols, 1, hw, k * hw, dw, k, 1, 0, None, o, k, hw, batch=n, accumulate=2, tc=tc)
     call("dbm_bias_grad_f32", dy.data_ptr(), o * hw, db.data_ptr(), n, o, hw, stream())
     # dcols[n, kk, p] = sum_o w[o, kk] * dy[n, o, p]
     dcols = empty(n, k, hw)
-    gemm(dy, 1, hw, o * hw, w, k, 1, 0, dcols, 1, hw, k * hw, None, hw, k, o, batch=n)
+    gemm(dy, 1, hw, o * hw, w, k, 1, 0, dcols, 1, hw, k * hw, None, hw, k, o, batch=n, tc=tc)
     doff = empty(n, 18, h, wd)
     call("dbm_deform_bwd_f32", x.data_ptr(), offset.data_ptr(), dcols.data_ptr(),
          dx.data_ptr() if dx is not None else None, doff.data_ptr(), n, c, h, wd, stream())

@@ -66,6 +66,11 @@ int dbm_bias_grad_f32(const float* dy, long dy_batch_stride, float* db, int n, i
 int dbm_gemm_f32(const float* a, long lda_m, long lda_k, long a_batch_stride, const float* b, long ldb_k, long ldb_n,
                  long b_batch_stride, float* c, long ldc_m, long ldc_n, long c_batch_stride, const float* bias, int m,
                  int n, int k, int batch, int act, int accumulate, cudaStream_t stream);
+/* Same contract, operands rounded to bf16 on the fly, fp32 accumulation on the tensor cores (the contractions of the
+ * deformable layer on the bf16 training path, srgan_train.py:506-514). accumulate: 0 overwrite, 2 atomic batch sum. */
+int dbm_gemm_bf16(const float* a, long lda_m, long lda_k, long a_batch_stride, const float* b, long ldb_k, long ldb_n,
+                  long b_batch_stride, float* c, long ldc_m, long ldc_n, long c_batch_stride, const float* bias, int m,
+                  int n, int k, int batch, int act, int accumulate, cudaStream_t stream);
 
 /* ---- element-wise / layout ------------------------------------------------------------------ */
 /* out = a*x + b*y on (batch, inner) views: F.add(a5 * residual_scaling, a0), srgan_train.py:358, 402, 551 */

@@ -82,6 +82,34 @@ def test_gemm_variants(ops):
     assert rel_l2(acc, (ab.double() @ b.double()).sum(0)) < 2e-6
 
 
+@pytest.mark.parametrize("n,hw,o,k", [(3, 1296, 64, 576), (2, 100, 64, 576), (5, 81, 40, 72)])
+def test_gemm_bf16_deformable_contractions(ops, n, hw, o, k):
+    """dbm_gemm_bf16 on the three strided contractions of the deformable layer (forward, weight gradient summed
+    over the batch, cols gradient): fp32 memory, operands rounded to bf16, fp32 accumulation."""
+    g = torch.Generator().manual_seed(3)
+    cols = torch.randn(n, k, hw, generator=g).cuda()
+    w = (torch.randn(o, k, generator=g) * 0.1).cuda()
+    b = torch.randn(o, generator=g).cuda()
+    dy = torch.randn(n, o, hw, generator=g).cuda()
+    q = lambda t: t.to(torch.bfloat16).double()
+    # y[n, o, p] = lrelu(sum_k cols[n, k, p] w[o, k] + b[o])
+    y = torch.empty(n, o, hw, device="cuda")
+    ops.gemm(cols, 1, hw, k * hw, w, 1, k, 0, y, 1, hw, o * hw, b, hw, o, k, batch=n, act=True, tc=True)
+    ref = torch.einsum("nkp,ok->nop", q(cols), q(w)) + b.double().view(1, o, 1)
+    ref = torch.where(ref >= 0, ref, 0.2 * ref)
+    assert rel_l2(y, ref) < 1e-5
+    # dw[o, kk] += sum_{n, p} dy[n, o, p] cols[n, kk, p]
+    dw = torch.ones(o, k, device="cuda")
+    ops.gemm(dy, hw, 1, o * hw, cols, 1, hw, k * hw, dw, k, 1, 0, None, o, k, hw, batch=n, accumulate=2, tc=True)
+    ref = 1.0 + torch.einsum("nop,nkp->ok", q(dy), q(cols))
+    assert rel_l2(dw, ref) < 1e-5
+    # dcols[n, kk, p] = sum_o w[o, kk] dy[n, o, p]
+    dcols = torch.empty(n, k, hw, device="cuda")
+    ops.gemm(dy, 1, hw, o * hw, w, k, 1, 0, dcols, 1, hw, k * hw, None, hw, k, o, batch=n, tc=True)
+    ref = torch.einsum("ok,nop->nkp", q(w), q(dy))
+    assert rel_l2(dcols, ref) < 1e-5
+
+
 def test_elementwise_and_layouts(ops):
     x = rnd(3, 16, 7, 5, seed=1)
     y = rnd(3, 24, 7, 5, seed=2)
