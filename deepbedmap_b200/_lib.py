@@ -68,6 +68,7 @@ SIGNATURES = {
     "dbm_ragan_loss_f32": [_P, _P, _I, _F, _F, _F, _P, _P, _P, _P],
     "dbm_gen_image_loss_f32": [_P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P],
     "dbm_adam_step_f32": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
+    "dbm_adam_step_dev_f32": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _P, _F, _P],
     "dbm_crop_clip_f32": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "dbm_place_tile_f32": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "dbm_f32_to_i16": [_P, _P, _L, _P],

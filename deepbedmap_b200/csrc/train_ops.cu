@@ -335,6 +335,24 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Device-side step counter variant (CUDA-graph replays: a host-computed bias correction would be frozen into the graph)
+__global__ void adam_tick_kernel(int* __restrict__ t) { *t += 1; }
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long n, double alpha, float beta1, float beta2, float eps,
+                                const int* __restrict__ t_dev, float grad_scale) {
+  const int t = *t_dev;
+  const double fix1 = 1.0 - pow((double)beta1, (double)t), fix2 = 1.0 - pow((double)beta2, (double)t);
+  const float lr_t = (float)(alpha * sqrt(fix2) / fix1);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = m[i] + (1.f - beta1) * (gi - m[i]);
+    const float vi = v[i] + (1.f - beta2) * (gi * gi - v[i]);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
 }  // namespace dbm
 
 using namespace dbm;
@@ -413,4 +431,13 @@ extern "C" int dbm_adam_step_f32(float* params, const float* grads, float* m, fl
   const float lr_t = (float)(alpha * sqrt(fix2) / fix1);
   adam_kernel<<<grid_for(n), 256, 0, st>>>(params, grads, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
   return check_launch("adam");
+}
+
+extern "C" int dbm_adam_step_dev_f32(float* params, const float* grads, float* m, float* v, long n, float alpha,
+                                     float beta1, float beta2, float eps, int* t_dev, float grad_scale,
+                                     cudaStream_t st) {
+  DBM_REQUIRE(n > 0 && t_dev != nullptr, "adam_dev: bad arguments (n=%ld)", n);
+  adam_tick_kernel<<<1, 1, 0, st>>>(t_dev);
+  adam_dev_kernel<<<grid_for(n), 256, 0, st>>>(params, grads, m, v, n, (double)alpha, beta1, beta2, eps, t_dev, grad_scale);
+  return check_launch("adam_dev");
 }

@@ -328,6 +328,26 @@ static_assert(sizeof(PackEntry) == 48, "PackEntry layout is part of the C ABI");
 
 __global__ void pack_w3x3_table_kernel(const PackEntry* __restrict__ table) {
   const PackEntry e = table[blockIdx.y];
+  if (e.mode == 0 && (e.O & 7) == 0 && (e.o0 & 7) == 0) {
+    // stacked forward slices (pair / tail / input-stationary images): visit only this entry's own rows -- the general
+    // loop below scans the whole image for every entry that writes into it
+    const int og = e.O / 8;
+    const long total = (long)9 * e.Cin * e.O;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+      long t = i;
+      const int c8 = t % 8; t /= 8;
+      const int o8 = t % 8; t /= 8;
+      const int cgl = t % og; t /= og;
+      const int ksl = t % (e.CK / 8); t /= (e.CK / 8);
+      const int tap = t % 9; t /= 9;
+      const int kc = (int)t;
+      const int o = cgl * 8 + o8;
+      const int c = kc * e.CK + ksl * 8 + c8;
+      const long dst = ((((long)(kc * 9 + tap) * (e.CK / 8) + ksl) * (e.COUTP / 8) + (e.o0 / 8 + cgl)) * 8 + o8) * 8 + c8;
+      e.out[dst] = __float2bfloat16_rn(e.w[((long)o * e.CinTotal + e.c0 + c) * 9 + tap]);
+    }
+    return;
+  }
   const long total = (long)9 * e.Cin * e.COUTP;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long t = i;

@@ -27,6 +27,7 @@ class Adam:
     def __init__(self, alpha: float = 1.6e-4, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8):
         self.alpha, self.beta1, self.beta2, self.eps = alpha, beta1, beta2, eps
         self.t = 0
+        self.t_dev = None
         self.target = None
 
     def setup(self, link):
@@ -38,10 +39,20 @@ class Adam:
     def update(self, grad_scale: float = 1.0):
         link = self.target
         self.t += 1
-        ops.call("dbm_adam_step_f32", link.flat.data_ptr(), link.flat_grad.data_ptr(), self.m.data_ptr(),
-                 self.v.data_ptr(), link.flat.numel(), self.alpha, self.beta1, self.beta2, self.eps, self.t,
-                 float(grad_scale), ops.stream())
+        if self.t_dev is not None:
+            # step count on the device (CUDA-graph replays, GraphedTrainStep): the kernel increments it itself
+            ops.call("dbm_adam_step_dev_f32", link.flat.data_ptr(), link.flat_grad.data_ptr(), self.m.data_ptr(),
+                     self.v.data_ptr(), link.flat.numel(), self.alpha, self.beta1, self.beta2, self.eps,
+                     self.t_dev.data_ptr(), float(grad_scale), ops.stream())
+        else:
+            ops.call("dbm_adam_step_f32", link.flat.data_ptr(), link.flat_grad.data_ptr(), self.m.data_ptr(),
+                     self.v.data_ptr(), link.flat.numel(), self.alpha, self.beta1, self.beta2, self.eps, self.t,
+                     float(grad_scale), ops.stream())
         link.mark_updated()
+
+    def use_device_step(self, on: bool = True):
+        """Keep the step count t in device memory (needed when update() is replayed from a CUDA graph)."""
+        self.t_dev = torch.full((1,), self.t, dtype=torch.int32, device="cuda") if on else None
 
     # -- optimizer-state checkpoint (extension: the reference saves weights only, srgan_train.py:1355-1361;
     #    SURVEY 8f N3). Keys follow chainer.serializers.save_npz(optimizer): 't', '<param path>/m', '<param path>/v'.
@@ -172,6 +183,14 @@ def train_eval_discriminator(input_arrays: Dict[str, object], g_model: Generator
     the flag set, this step runs the graph-keeping forward once and ``train_eval_generator`` called next on the
     SAME device arrays reuses its output and saved activations (``GeneratorModel.shared_forward``) -- the same
     values the second forward would produce, one generator forward less per step."""
+    out = _discriminator_step_enqueue(input_arrays, g_model, d_model, d_optimizer, train, share_generator_forward)
+    res = out.cpu()                                                                # :1166 (host sync)
+    return float(res[0]), float(res[1])
+
+
+def _discriminator_step_enqueue(input_arrays, g_model, d_model, d_optimizer, train, share_generator_forward):
+    """Everything train_eval_discriminator launches, without the host read: returns the device pair
+    (d_loss, d_accu)."""
     if train:
         assert d_optimizer is not None  # :1127
     if train and share_generator_forward:
@@ -197,8 +216,7 @@ def train_eval_discriminator(input_arrays: Dict[str, object], g_model: Generator
         d_model.backward(d_real, on_ready=reducer.bucket)   # gradients are final after the second pass
         d_optimizer.update(grad_scale=reducer.finish())                            # :1164
     d_model._ctx = None
-    res = out.cpu()                                                                # :1166 (host sync)
-    return float(res[0]), float(res[1])
+    return out
 
 
 def train_eval_generator(input_arrays: Dict[str, object], g_model: GeneratorModel, d_model: DiscriminatorModel,
@@ -206,6 +224,16 @@ def train_eval_generator(input_arrays: Dict[str, object], g_model: GeneratorMode
                          content_loss_weighting: float = 1e-2, adversarial_loss_weighting: float = 2e-2,
                          topographic_loss_weighting: float = 2e-3, structural_loss_weighting: float = 5.25):
     """srgan_train.py:1170-1263 -> (g_loss, g_psnr, g_ssim)."""
+    sums, adv, shape = _generator_step_enqueue(input_arrays, g_model, d_model, g_optimizer, train, content_loss_weighting,
+                                               topographic_loss_weighting, structural_loss_weighting)
+    return _generator_step_finalize(sums.cpu().double().numpy(), float(adv.cpu()[0]), shape, content_loss_weighting,
+                                    adversarial_loss_weighting, topographic_loss_weighting, structural_loss_weighting)
+
+
+def _generator_step_enqueue(input_arrays, g_model, d_model, g_optimizer, train, content_loss_weighting,
+                            topographic_loss_weighting, structural_loss_weighting):
+    """Everything train_eval_generator launches, without the host reads: returns the device partial sums
+    (content, topographic, ssim, squared error), the device adversarial loss and the prediction shape."""
     if train:
         assert g_optimizer is not None  # :1218
     X = as_device(input_arrays["X"])
@@ -241,8 +269,13 @@ def train_eval_generator(input_arrays: Dict[str, object], g_model: GeneratorMode
         reducer = GradBucketReducer(g_model)
         g_model.backward(dy, on_ready=reducer.bucket)                              # :1256
         g_optimizer.update(grad_scale=reducer.finish())                            # :1257
-    s = sums.cpu().double().numpy()                                                # host sync (:1259-1263)
-    adv_v = float(adv.cpu()[0])
+    return sums, adv, (n, H, W)
+
+
+def _generator_step_finalize(s, adv_v, shape, content_loss_weighting, adversarial_loss_weighting,
+                             topographic_loss_weighting, structural_loss_weighting):
+    """Host arithmetic of the metrics (:1259-1263) from the partial sums read back from the device."""
+    n, H, W = shape
     npx = n * H * W
     content = s[0] / npx
     topo = s[1] / (n * (H // 4) * (W // 4))
@@ -279,6 +312,85 @@ def trainer(i: int, columns: list, train_iter, dev_iter, g_model, g_optimizer, d
         metrics["val_generator_psnr"].append(gp)
         metrics["val_generator_ssim"].append(gs)
     return metrics
+
+
+class GraphedTrainStep:
+    """The per-minibatch body of ``trainer`` (discriminator step, then generator step on the same batch,
+    srgan_train.py:1286-1308) captured ONCE as a CUDA graph and replayed per minibatch: the ~400 kernel launches
+    of a step become one graph launch (the eager step leaves the GPU idle ~10 % of the time between launches).
+
+    The batch shapes are fixed at construction; ``step(arrays)`` copies the new minibatch into the static input
+    buffers, replays, and returns the same five metrics as the eager functions
+    ((d_loss, d_accu), (g_loss, g_psnr, g_ssim)). Model weights, BatchNorm statistics and Adam state live in the
+    same buffers as in eager mode, so eager calls (evaluation, checkpoints) can be mixed with replays.
+    Single-GPU only (the bucketed NCCL all-reduce of the data-parallel step stays eager)."""
+
+    LOSS_WEIGHTS = dict(content_loss_weighting=1e-2, adversarial_loss_weighting=2e-2,
+                        topographic_loss_weighting=2e-3, structural_loss_weighting=5.25)
+
+    def __init__(self, input_arrays: Dict[str, object], g_model, g_optimizer, d_model, d_optimizer, warmup: int = 2):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            raise ValueError("GraphedTrainStep is single-GPU; use the eager step functions for data-parallel training")
+        self.g, self.g_opt, self.d, self.d_opt = g_model, g_optimizer, d_model, d_optimizer
+        self.arrays = {k: as_device(v).clone() for k, v in input_arrays.items()}
+        for opt in (g_optimizer, d_optimizer):
+            opt.use_device_step(True)
+        # Warm-up runs real steps (workspaces, packed-image plans, kernel attributes must exist before capture);
+        # the training state is restored afterwards so that constructing the object does not train.
+        state = self._snapshot()
+        for _ in range(max(1, warmup)):
+            self._body()
+        torch.cuda.synchronize()
+        self.host = torch.empty(8, dtype=torch.float32).pin_memory()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            out, sums, adv, self.shape = self._body()
+            dev = torch.cat([out.reshape(-1)[:2], sums.reshape(-1)[:4], adv.reshape(-1)[:1]])
+            self.host[:7].copy_(dev, non_blocking=True)
+        self._restore(state)
+
+    def _body(self):
+        out = _discriminator_step_enqueue(self.arrays, self.g, self.d, self.d_opt, True, True)
+        w = self.LOSS_WEIGHTS
+        sums, adv, shape = _generator_step_enqueue(self.arrays, self.g, self.d, self.g_opt, True,
+                                                   w["content_loss_weighting"], w["topographic_loss_weighting"],
+                                                   w["structural_loss_weighting"])
+        return out, sums, adv, shape
+
+    def _snapshot(self):
+        st = []
+        for link, opt in ((self.g, self.g_opt), (self.d, self.d_opt)):
+            pers = {k: v.clone() for k, v in getattr(link, "persistent", {}).items()}
+            st.append((link.flat.clone(), opt.m.clone(), opt.v.clone(), opt.t, pers))
+        return st
+
+    def _restore(self, st):
+        for (link, opt), (flat, m, v, t, pers) in zip(((self.g, self.g_opt), (self.d, self.d_opt)), st):
+            link.flat.copy_(flat)
+            opt.m.copy_(m)
+            opt.v.copy_(v)
+            opt.t = t
+            opt.t_dev.fill_(t)
+            for k, val in pers.items():
+                link.persistent[k].copy_(val)
+            link.mark_updated()
+        torch.cuda.synchronize()
+
+    def step(self, input_arrays: Optional[Dict[str, object]] = None):
+        if input_arrays is not None:
+            for k, dst in self.arrays.items():
+                src = input_arrays[k]
+                if src is not dst:
+                    dst.copy_(as_device(src), non_blocking=True)
+        self.graph.replay()
+        for link, opt in ((self.g, self.g_opt), (self.d, self.d_opt)):
+            opt.t += 1
+            link.mark_updated()      # eager calls made between replays must re-pack their operand images
+        torch.cuda.current_stream().synchronize()
+        h = self.host.double().numpy()
+        gl = _generator_step_finalize(h[2:6], float(h[6]), self.shape, **self.LOSS_WEIGHTS)
+        return (float(h[0]), float(h[1])), gl
 
 
 class ArrayIterator:

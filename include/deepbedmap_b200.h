@@ -259,6 +259,10 @@ int dbm_gen_image_loss_f32(const float* y_pred, const float* y_true, const float
 /* ---- chainer.optimizers.Adam(alpha, beta1, beta2, eps) over a flat parameter buffer (:1043-1048) */
 int dbm_adam_step_f32(float* params, const float* grads, float* m, float* v, long n, float alpha, float beta1,
                       float beta2, float eps, int t, float grad_scale, cudaStream_t stream);
+/* Same update with the step count t kept on the device (incremented here, before the update): the form a CUDA-graph
+ * replay of the training step needs -- a host-side t would freeze the bias correction into the graph. */
+int dbm_adam_step_dev_f32(float* params, const float* grads, float* m, float* v, long n, float alpha, float beta1,
+                          float beta2, float eps, int* t_dev, float grad_scale, cudaStream_t stream);
 
 /* ---- continent tiler staging (deepbedmap.py:663-665, 715-722, 731-736) ------------------------- */
 int dbm_crop_clip_f32(const float* src, int hs, int ws, float* dst, int c, int y0, int x0, int h, int w, int clip0,
