@@ -244,9 +244,14 @@ def train_bench(rank, world, steps=20, warmup=3, batch=128):
               "Y": r(batch, 1, 36, 36)}
     # the per-minibatch body of trainer() (srgan_train.py:1286-1308): both steps on the same device batch,
     # the generator step reusing the graph-keeping forward the discriminator step ran (weights unchanged between)
-    def step():
-        T.train_eval_discriminator(arrays, g, d, d_opt, share_generator_forward=True)
-        T.train_eval_generator(arrays, g, d, g_opt)
+    if world == 1:
+        # single GPU: the step is captured once as a CUDA graph and replayed (same kernels, one launch)
+        graphed = T.GraphedTrainStep(arrays, g, g_opt, d, d_opt)
+        step = lambda: graphed.step(arrays)
+    else:
+        def step():
+            T.train_eval_discriminator(arrays, g, d, d_opt, share_generator_forward=True)
+            T.train_eval_generator(arrays, g, d, g_opt)
     for _ in range(warmup):
         step()
     barrier(world)
@@ -259,10 +264,11 @@ def train_bench(rank, world, steps=20, warmup=3, batch=128):
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     return {"metric": "train steps/s (D-step + G-step, batch 128 per GPU)", "value": steps / (ms * 1e-3),
             "unit": "steps/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "scaling": "weak",
-            "global_batch": batch * world, "dtype": "bf16 tcgen05 operands / fp32 accumulation for every 3x3 conv of G and D (fwd, dgrad, wgrad); "
-                                               "fp32 stem, deformable layers, BN, losses, Adam",
+            "global_batch": batch * world, "dtype": "bf16 tensor-core operands / fp32 accumulation for every 3x3 conv of G and D (fwd, dgrad, wgrad) and the "
+                                               "deformable contraction; fp32 stem, bilinear sampling, BN, losses, Adam",
             "generator_forward": "one per step, shared by the D-step and the G-step (the reference runs it twice "
                                  "with unchanged weights; SURVEY 8d counts it once)",
+            "launch": "CUDA graph replay (deepbedmap_b200.train.GraphedTrainStep)" if world == 1 else "eager",
             "allreduce": "bucketed, launched from inside backward (NCCL, overlapped)" if world > 1 else "none (1 GPU)"}
 
 

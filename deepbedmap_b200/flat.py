@@ -505,12 +505,15 @@ class ConvImages:
             self.bias_pad[: self.O].copy_(self.bias)
 
 
-def pack_images(images) -> None:
-    """One table-driven launch (re)packing the operand images of every ConvImages in ``images``."""
+def pack_images(images, table=None):
+    """One table-driven launch (re)packing the operand images of every ConvImages in ``images``. Returns the device
+    table; pass it back in on later calls (the entries only hold pointers, which do not change)."""
     from .model import PACK_ENTRY_DTYPE
-    entries = [e for im in images for e in im.entries]
-    table = torch.from_numpy(np.array(entries, dtype=PACK_ENTRY_DTYPE).view(np.uint8).copy()).cuda()
-    ops.call("dbm_pack_conv3x3_table", table.data_ptr(), len(entries), max(im.max_elements for im in images),
+    n_entries = sum(len(im.entries) for im in images)
+    if table is None:
+        entries = [e for im in images for e in im.entries]
+        table = torch.from_numpy(np.array(entries, dtype=PACK_ENTRY_DTYPE).view(np.uint8).copy()).cuda()
+    ops.call("dbm_pack_conv3x3_table", table.data_ptr(), n_entries, max(im.max_elements for im in images),
              ops.stream())
     for im in images:
         im.refresh_bias()

@@ -349,7 +349,7 @@ class GeneratorModel(_Link):
         if self._head_images is None:
             self._head_images = {k: flat.ConvImages(self.p[f"{k}/W"], self.p[f"{k}/b"]) for k in self.HEAD_TC_KEYS}
         if self._head_packed_version != self.version:
-            self._head_pack_table = flat.pack_images(list(self._head_images.values()))
+            self._head_pack_table = flat.pack_images(list(self._head_images.values()), self._head_pack_table)
             self._head_packed_version = self.version
         tc = self._head_tc.get((n, H, W))
         if tc is None:
@@ -880,7 +880,7 @@ class DiscriminatorModel(_Link):
         if self._tc_images is None:
             self._tc_images = {i: flat.ConvImages(self.p[f"conv_layer{i}/W"]) for i in range(1, 10)}
         if self._tc_packed_version != self.version:
-            self._tc_pack_table = flat.pack_images(list(self._tc_images.values()))
+            self._tc_pack_table = flat.pack_images(list(self._tc_images.values()), self._tc_pack_table)
             self._tc_packed_version = self.version
         tc = self._tc.get(n)
         if tc is None:

@@ -375,6 +375,11 @@ class GraphedTrainStep:
             for k, val in pers.items():
                 link.persistent[k].copy_(val)
             link.mark_updated()
+        # The graph re-packs the generator's operand images at its start and the discriminator's after the
+        # discriminator update (where the eager step does); the discriminator images its first pass reads are the
+        # ones the PREVIOUS step packed, so they must match the restored weights before the first replay:
+        # an eval-mode forward re-packs them and changes no state.
+        self.d.forward(self.arrays["Y"], train=False)
         torch.cuda.synchronize()
 
     def step(self, input_arrays: Optional[Dict[str, object]] = None):
