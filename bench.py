@@ -244,14 +244,17 @@ def train_bench(rank, world, steps=20, warmup=3, batch=128):
               "Y": r(batch, 1, 36, 36)}
     # the per-minibatch body of trainer() (srgan_train.py:1286-1308): both steps on the same device batch,
     # the generator step reusing the graph-keeping forward the discriminator step ran (weights unchanged between)
-    if world == 1:
-        # single GPU: the step is captured once as a CUDA graph and replayed (same kernels, one launch)
+    def eager_step():
+        T.train_eval_discriminator(arrays, g, d, d_opt, share_generator_forward=True)
+        T.train_eval_generator(arrays, g, d, g_opt)
+    launch = "CUDA graph replay (deepbedmap_b200.train.GraphedTrainStep)"
+    try:
+        # the step (and, data parallel, its bucketed NCCL all-reduces) is captured once as a CUDA graph and replayed
         graphed = T.GraphedTrainStep(arrays, g, g_opt, d, d_opt)
         step = lambda: graphed.step(arrays)
-    else:
-        def step():
-            T.train_eval_discriminator(arrays, g, d, d_opt, share_generator_forward=True)
-            T.train_eval_generator(arrays, g, d, g_opt)
+    except Exception as ex:   # reported in the line, never hidden
+        launch = f"eager (graph capture failed: {repr(ex)[:120]})"
+        step = eager_step
     for _ in range(warmup):
         step()
     barrier(world)
@@ -268,7 +271,7 @@ def train_bench(rank, world, steps=20, warmup=3, batch=128):
                                                "deformable contraction; fp32 stem, bilinear sampling, BN, losses, Adam",
             "generator_forward": "one per step, shared by the D-step and the G-step (the reference runs it twice "
                                  "with unchanged weights; SURVEY 8d counts it once)",
-            "launch": "CUDA graph replay (deepbedmap_b200.train.GraphedTrainStep)" if world == 1 else "eager",
+            "launch": launch,
             "allreduce": "bucketed, launched from inside backward (NCCL, overlapped)" if world > 1 else "none (1 GPU)"}
 
 

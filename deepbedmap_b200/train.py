@@ -323,15 +323,12 @@ class GraphedTrainStep:
     buffers, replays, and returns the same five metrics as the eager functions
     ((d_loss, d_accu), (g_loss, g_psnr, g_ssim)). Model weights, BatchNorm statistics and Adam state live in the
     same buffers as in eager mode, so eager calls (evaluation, checkpoints) can be mixed with replays.
-    Single-GPU only (the bucketed NCCL all-reduce of the data-parallel step stays eager)."""
+    Data parallel: the bucketed NCCL all-reduces (GradBucketReducer, side stream) are captured with the step."""
 
     LOSS_WEIGHTS = dict(content_loss_weighting=1e-2, adversarial_loss_weighting=2e-2,
                         topographic_loss_weighting=2e-3, structural_loss_weighting=5.25)
 
     def __init__(self, input_arrays: Dict[str, object], g_model, g_optimizer, d_model, d_optimizer, warmup: int = 2):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            raise ValueError("GraphedTrainStep is single-GPU; use the eager step functions for data-parallel training")
         self.g, self.g_opt, self.d, self.d_opt = g_model, g_optimizer, d_model, d_optimizer
         self.arrays = {k: as_device(v).clone() for k, v in input_arrays.items()}
         for opt in (g_optimizer, d_optimizer):
