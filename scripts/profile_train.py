@@ -14,7 +14,7 @@ arrays = {"X": r(batch, 1, 11, 11), "W1": r(batch, 1, 110, 110), "W2": r(batch, 
 import time
 for i in range(steps):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    dl = T.train_eval_discriminator(arrays, g, d, d_opt)
+    dl = T.train_eval_discriminator(arrays, g, d, d_opt, share_generator_forward=True)   # as trainer() / bench.py
     torch.cuda.synchronize(); t1 = time.perf_counter()
     gl = T.train_eval_generator(arrays, g, d, g_opt)
     torch.cuda.synchronize(); t2 = time.perf_counter()
