@@ -823,7 +823,11 @@ class DiscriminatorModel(_Link):
     def __call__(self, x, train: Optional[bool] = None):
         return self.forward(x, train=train)
 
-    def forward(self, x, train: Optional[bool] = None, save: bool = False) -> Variable:
+    def forward(self, x, train: Optional[bool] = None, save: bool = False, groups: int = 1) -> Variable:
+        """``groups`` > 1: the batch is ``groups`` independent passes stacked along N (the discriminator step feeds
+        D(real) and D(fake), srgan_train.py:1145-1146): convolutions and linear layers run once over the whole
+        stack, BatchNormalization takes its batch statistics (and updates the running ones, in order) per group --
+        the same values as separate calls, half the kernel launches."""
         train = self.train if train is None else bool(train)
         x = as_device(x)
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, 36, 36):
@@ -831,6 +835,9 @@ class DiscriminatorModel(_Link):
             raise ValueError(f"DiscriminatorModel expects (N,1,36,36) input, got {tuple(x.shape)}")
         P = self.p
         n = x.shape[0]
+        if groups < 1 or n % groups:
+            raise ValueError(f"batch of {n} does not split into {groups} groups")
+        ng = n // groups
         acts = [x]
         pres = []
         a = ops.empty(n, 64, 36, 36)
@@ -853,13 +860,15 @@ class DiscriminatorModel(_Link):
                 z = ops.empty(n, cout, ho, ho)
                 ops.conv2d_fwd(acts[-1], 0, cin, P[f"conv_layer{i}/W"], None, z, 0, k, s, 1)
             y = ops.empty(n, cout, ho, ho)
-            mean, invstd = ops.empty(cout), ops.empty(cout)
-            ops.call("dbm_bn_lrelu_fwd_f32", z.data_ptr(), y.data_ptr(), P[f"batch_norm{i}/gamma"].data_ptr(),
-                     P[f"batch_norm{i}/beta"].data_ptr(), self.persistent[f"batch_norm{i}/avg_mean"].data_ptr(),
-                     self.persistent[f"batch_norm{i}/avg_var"].data_ptr(), mean.data_ptr(), invstd.data_ptr(), n, cout,
-                     ho * ho, self.BN_EPS, self.BN_DECAY, int(train), ops.stream())
+            mean, invstd = ops.empty(groups, cout), ops.empty(groups, cout)
+            for gi in range(groups):
+                o = 4 * gi * ng * cout * ho * ho
+                ops.call("dbm_bn_lrelu_fwd_f32", z.data_ptr() + o, y.data_ptr() + o, P[f"batch_norm{i}/gamma"].data_ptr(),
+                         P[f"batch_norm{i}/beta"].data_ptr(), self.persistent[f"batch_norm{i}/avg_mean"].data_ptr(),
+                         self.persistent[f"batch_norm{i}/avg_var"].data_ptr(), mean[gi].data_ptr(),
+                         invstd[gi].data_ptr(), ng, cout, ho * ho, self.BN_EPS, self.BN_DECAY, int(train), ops.stream())
             if train:
-                self.bn_N[i] += 1
+                self.bn_N[i] += groups
             pres.append(z)
             stats.append((mean, invstd))
             acts.append(y)
@@ -872,7 +881,7 @@ class DiscriminatorModel(_Link):
         if save:
             if not train:
                 raise ValueError("backward through eval-mode BatchNormalization is not needed by the reference")
-            self._ctx = dict(acts=acts, pres=pres, stats=stats, l1=l1, n=n, tc=tc, slot=slot)
+            self._ctx = dict(acts=acts, pres=pres, stats=stats, l1=l1, n=n, tc=tc, slot=slot, groups=groups)
         return Variable(out)
 
     def _tc_convs(self, n):
@@ -924,11 +933,15 @@ class DiscriminatorModel(_Link):
             mean, invstd = stats[i - 1]
             hw = z.shape[2] * z.shape[3]
             dz = ops.empty(*z.shape)
-            scratch = ops.empty(2 * cout)
-            ops.call("dbm_bn_lrelu_bwd_f32", z.data_ptr(), y.data_ptr(), dy.data_ptr(), dz.data_ptr(),
-                     P[f"batch_norm{i}/gamma"].data_ptr(), mean.data_ptr(), invstd.data_ptr(),
-                     G[f"batch_norm{i}/gamma"].data_ptr(), G[f"batch_norm{i}/beta"].data_ptr(), scratch.data_ptr(), n,
-                     cout, hw, ops.stream())
+            groups = c.get("groups", 1)
+            ng = n // groups
+            scratch = ops.empty(groups, 2 * cout)
+            for gi in range(groups):
+                o = 4 * gi * ng * cout * hw
+                ops.call("dbm_bn_lrelu_bwd_f32", z.data_ptr() + o, y.data_ptr() + o, dy.data_ptr() + o, dz.data_ptr() + o,
+                         P[f"batch_norm{i}/gamma"].data_ptr(), mean[gi].data_ptr(), invstd[gi].data_ptr(),
+                         G[f"batch_norm{i}/gamma"].data_ptr(), G[f"batch_norm{i}/beta"].data_ptr(),
+                         scratch[gi].data_ptr(), ng, cout, hw, ops.stream())
             xin = acts[i]
             cin = xin.shape[1]
             if c.get("tc") is not None:

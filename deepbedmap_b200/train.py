@@ -162,11 +162,14 @@ def compile_srgan_model(num_residual_blocks: int = 12, residual_scaling: float =
     return g, g_opt, d, d_opt
 
 
-def _ragan(real_pred, fake_pred, t_rmf, t_fmr, want_grads, grad_scale=1.0):
+def _ragan(real_pred, fake_pred, t_rmf, t_fmr, want_grads, grad_scale=1.0, grads_out=None):
     n = real_pred.shape[0]
     out = ops.empty(2)
-    d_real = ops.empty(n, 1) if want_grads else None
-    d_fake = ops.empty(n, 1) if want_grads else None
+    if want_grads and grads_out is not None:      # (2n, 1): gradients wrt [real; fake] logits
+        d_real, d_fake = grads_out[:n], grads_out[n:]
+    else:
+        d_real = ops.empty(n, 1) if want_grads else None
+        d_fake = ops.empty(n, 1) if want_grads else None
     ops.call("dbm_ragan_loss_f32", real_pred.data_ptr(), fake_pred.data_ptr(), n, float(t_rmf), float(t_fmr),
              float(grad_scale), out.data_ptr(), d_real.data_ptr() if want_grads else None,
              d_fake.data_ptr() if want_grads else None, ops.stream())
@@ -202,18 +205,18 @@ def _discriminator_step_enqueue(input_arrays, g_model, d_model, d_optimizer, tra
     real = as_device(input_arrays["Y"])
     if train:
         d_model.cleargrads()                                                       # :1162
-    # two separate passes with their own batch statistics, real first (:1145-1146)
-    real_pred = d_model.forward(real, train=train, save=train).array
-    ctx_real = d_model._ctx
-    fake_pred = d_model.forward(fake, train=train, save=train).array
-    ctx_fake = d_model._ctx
-    out, d_real, d_fake = _ragan(real_pred, fake_pred, 1.0, 0.0, want_grads=train)  # :1149-1158
+    # D(real) then D(fake), each with its own batch statistics (:1145-1146): one stacked pass, BatchNormalization
+    # per group (DiscriminatorModel.forward, ``groups``)
+    n = real.shape[0]
+    if tuple(real.shape) != tuple(fake.shape):
+        raise ValueError("Input images must have the same dimensions.")
+    pred = d_model.forward(torch.cat([real, fake]), train=train, save=train, groups=2).array
+    real_pred, fake_pred = pred[:n], pred[n:]
+    dlogit = ops.empty(2 * n, 1) if train else None
+    out, _, _ = _ragan(real_pred, fake_pred, 1.0, 0.0, want_grads=train, grads_out=dlogit)  # :1149-1158
     if train:
         reducer = GradBucketReducer(d_model)
-        d_model._ctx = ctx_fake
-        d_model.backward(d_fake)                                                   # :1163
-        d_model._ctx = ctx_real
-        d_model.backward(d_real, on_ready=reducer.bucket)   # gradients are final after the second pass
+        d_model.backward(dlogit, on_ready=reducer.bucket)                          # :1163
         d_optimizer.update(grad_scale=reducer.finish())                            # :1164
     d_model._ctx = None
     return out

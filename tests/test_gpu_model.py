@@ -247,6 +247,36 @@ def test_discriminator_matches_oracle():
     assert rel_l2(d.forward(x, train=False).numpy(), ref_eval) < 5e-5
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_discriminator_stacked_groups_equal_separate_passes(precision):
+    """forward(cat([real, fake]), groups=2) -- what the discriminator step runs -- against D(real) then D(fake)
+    (srgan_train.py:1145-1146): same logits, same BatchNormalization running statistics, same gradients."""
+    rng = np.random.RandomState(5)
+    real = torch.as_tensor(rng.rand(6, 1, 36, 36).astype(np.float32)).cuda()
+    fake = torch.as_tensor(rng.rand(6, 1, 36, 36).astype(np.float32)).cuda()
+    dl = torch.as_tensor(rng.randn(12, 1).astype(np.float32)).cuda()
+    da, _ = _load_disc(precision=precision)
+    db, _ = _load_disc(precision=precision)
+    # separate passes (fake's backward first, as the old step did; order is irrelevant for the sums)
+    ra = da.forward(real, train=True, save=True).array.clone()
+    ctx_r = da._ctx
+    fa = da.forward(fake, train=True, save=True).array.clone()
+    da.cleargrads()
+    da.backward(dl[6:])
+    da._ctx = ctx_r
+    da.backward(dl[:6])
+    # stacked
+    pb = db.forward(torch.cat([real, fake]), train=True, save=True, groups=2).array.clone()
+    db.cleargrads()
+    db.backward(dl)
+    assert torch.equal(pb[:6], ra) and torch.equal(pb[6:], fa)
+    for k in da.persistent:
+        assert torch.equal(da.persistent[k], db.persistent[k]), k
+    assert rel_l2(db.flat_grad.cpu().numpy(), da.flat_grad.cpu().numpy()) < 1e-5
+    ev = db.forward(torch.cat([real, fake]), train=False, groups=2).array
+    assert torch.equal(ev[:6], da.forward(real, train=False).array)
+
+
 def test_training_step_matches_oracle():
     """One D-step then one G-step (srgan_train.py:1286-1308) on a batch of 3, 1 RRDB: losses,
     metrics, gradients and post-Adam weights against autograd on the fp64 oracle."""
