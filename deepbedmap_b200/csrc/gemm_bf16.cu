@@ -6,8 +6,8 @@
 //     dcols [px, kk] = sum_o  dy[o, px]   * W[o, kk]               (M = H W, N = 576, K = 64)
 // Same arithmetic contract as every other conv of the bf16 training path (DESIGN.md "Numerics"): operands
 // rounded to bf16, fp32 accumulation. These GEMMs stream the fp32 cols buffer (382 MB per pass at batch 128):
-// the fp32 CUDA-core kernel (gemm_f32.cu) spent 430 / 510 / 430 us on them, this one 250 / 400 / 420 us -- still
-// latency bound (one 16-deep K step per barrier, two CTAs per SM), 3-4x the HBM time: open item.
+// the fp32 CUDA-core kernel (gemm_f32.cu) spent 430 / 510 / 430 us on them; here 250 / 320 / 190 us (general
+// kernel, wide-K variant, short-K kernel) -- still 2-3x the HBM time (one K tile per barrier, no async copies).
 // Operands keep their natural strides: a tile is staged in shared memory in the orientation it has in global
 // memory (coalesced loads along the unit-stride dimension) and wmma's row/col-major fragment loads do the rest.
 #include <mma.h>
@@ -33,17 +33,20 @@ struct GemmBf16P {
   int kchunks;         // atomic: K chunks per image
 };
 
-constexpr int kGBK = 16;   // (32 was measured slower: 175 registers, one CTA per SM)
+// K depth of a shared-memory tile: 16, except 32 when both operands are unit-stride along k (the weight gradient):
+// a 16-deep tile is then a 64-byte run per row -- half-used sectors on the 382 MB cols stream (measured 400 -> 340 us);
+// for the other layouts 32 costs registers (175, one CTA per SM) and was slower.
+constexpr int kGBK = 16, kGBKWide = 32;
 
 // A_COL: A(m, k) is unit-stride along m; else along k.  B_ROW: B(k, n) is unit-stride along n; else along k.
-template <int BM, int BN, bool A_COL, bool B_ROW>
+template <int BM, int BN, bool A_COL, bool B_ROW, int BK>
 __global__ void __launch_bounds__(256) gemm_bf16_kernel(const GemmBf16P p) {
   constexpr int WM = BM / 32, WN = BN / 32;          // warps along m / n, 32 x 32 outputs each
   static_assert(WM * WN == 8, "eight warps");
-  constexpr int LDA = A_COL ? BM + 8 : kGBK + 8;     // bf16 elements; +8 keeps 16-byte row alignment, skews banks
-  constexpr int LDB = B_ROW ? BN + 8 : kGBK + 8;
+  constexpr int LDA = A_COL ? BM + 8 : BK + 8;     // bf16 elements; +8 keeps 16-byte row alignment, skews banks
+  constexpr int LDB = B_ROW ? BN + 8 : BK + 8;
   constexpr int LDC = BM + 4;                         // epilogue staging, column-major (m fastest)
-  constexpr int kAElems = A_COL ? kGBK * LDA : BM * LDA, kBElems = B_ROW ? kGBK * LDB : BN * LDB;
+  constexpr int kAElems = A_COL ? BK * LDA : BM * LDA, kBElems = B_ROW ? BK * LDB : BN * LDB;
   constexpr int kABBytes = 2 * (kAElems + kBElems) * 2, kCBytes = BN * LDC * 4;
   // the epilogue staging tile re-uses the operand buffers (static shared memory stays under 48 KB)
   __shared__ __align__(128) unsigned char raw[kABBytes > kCBytes ? kABBytes : kCBytes];
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(256) gemm_bf16_kernel(const GemmBf16P p) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) wmma::fill_fragment(acc[i][j], 0.f);
 
-  constexpr int NA = BM * kGBK / 256, NB = BN * kGBK / 256;   // elements per thread per tile
+  constexpr int NA = BM * BK / 256, NB = BN * BK / 256;   // elements per thread per tile
   float ra[NA], rb[NB];
   const float* Ab = nullptr;
   const float* Bb = nullptr;
@@ -81,14 +84,14 @@ __global__ void __launch_bounds__(256) gemm_bf16_kernel(const GemmBf16P p) {
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
       const int e = t + 256 * i;
-      const int ml = A_COL ? e % BM : e / kGBK, kl = A_COL ? e / BM : e % kGBK;
+      const int ml = A_COL ? e % BM : e / BK, kl = A_COL ? e / BM : e % BK;
       const int m = m0 + ml, k = k0 + kl;
       ra[i] = (m < p.M && k < kend) ? __ldg(Ab + m * p.lda_m + k * p.lda_k) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
       const int e = t + 256 * i;
-      const int nl = B_ROW ? e % BN : e / kGBK, kl = B_ROW ? e / BN : e % kGBK;
+      const int nl = B_ROW ? e % BN : e / BK, kl = B_ROW ? e / BN : e % BK;
       const int n = n0 + nl, k = k0 + kl;
       rb[i] = (n < p.N && k < kend) ? __ldg(Bb + k * p.ldb_k + n * p.ldb_n) : 0.f;
     }
@@ -97,13 +100,13 @@ __global__ void __launch_bounds__(256) gemm_bf16_kernel(const GemmBf16P p) {
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
       const int e = t + 256 * i;
-      const int ml = A_COL ? e % BM : e / kGBK, kl = A_COL ? e / BM : e % kGBK;
+      const int ml = A_COL ? e % BM : e / BK, kl = A_COL ? e / BM : e % BK;
       As[buf][A_COL ? kl * LDA + ml : ml * LDA + kl] = __float2bfloat16_rn(ra[i]);
     }
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
       const int e = t + 256 * i;
-      const int nl = B_ROW ? e % BN : e / kGBK, kl = B_ROW ? e / BN : e % kGBK;
+      const int nl = B_ROW ? e % BN : e / BK, kl = B_ROW ? e / BN : e % BK;
       Bs[buf][B_ROW ? kl * LDB + nl : nl * LDB + kl] = __float2bfloat16_rn(rb[i]);
     }
   };
@@ -117,12 +120,12 @@ __global__ void __launch_bounds__(256) gemm_bf16_kernel(const GemmBf16P p) {
     const int kbeg = ca * klen, kend = min(p.K, cb * klen);
     if (kbeg >= kend) continue;
     fetch(kbeg, kend);
-    for (int k0 = kbeg; k0 < kend; k0 += kGBK) {
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
       commit(buf);
       __syncthreads();
-      if (k0 + kGBK < kend) fetch(k0 + kGBK, kend);
+      if (k0 + BK < kend) fetch(k0 + BK, kend);
 #pragma unroll
-      for (int ks = 0; ks < kGBK; ks += 16) {
+      for (int ks = 0; ks < BK; ks += 16) {
         wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16,
                        typename std::conditional<A_COL, wmma::col_major, wmma::row_major>::type> fa[2];
         wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16,
@@ -171,12 +174,89 @@ __global__ void __launch_bounds__(256) gemm_bf16_kernel(const GemmBf16P p) {
   }
 }
 
+// Short-K form (K <= 64: the cols gradient, K = 64 output channels, N = 576): a CTA keeps its 128 x K block of A
+// (unit stride along m) in shared memory and walks over ALL of N in 64-column tiles, B (unit stride along n) fetched
+// per tile from L2 -- A is read once, and the kernel is what it should be, a stream of C writes (382 MB at batch 128).
+// The general kernel above re-read A per N tile and paid a barrier + a global-load latency per 16-deep K step.
+constexpr int kSKMax = 64;
+__global__ void __launch_bounds__(256) gemm_bf16_shortk_kernel(const GemmBf16P p) {
+  constexpr int BM = 128, BN = 64, LDA = BM + 8, LDB = BN + 8, LDC = BM + 4;
+  extern __shared__ __align__(128) unsigned char sk_raw[];       // 60 KB: dynamic (over the 48 KB static limit)
+  __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(sk_raw);                       // col-major: (m, k) at k * LDA + m
+  __nv_bfloat16* Bs = As + kSKMax * LDA;                                               // row-major: (k, n) at k * LDB + n
+  float* Cs = reinterpret_cast<float*>(sk_raw + (kSKMax * LDA + kSKMax * LDB) * 2);   // col-major staging
+  const int t = threadIdx.x, warp = t >> 5;
+  const int wm = warp & 3, wn = warp >> 2;                        // 4 x 2 warps, 32 x 32 outputs each
+  const int m0 = blockIdx.x * BM;
+  const float* Ab = p.A + (long)blockIdx.z * p.a_bs;
+  const float* Bb = p.B + (long)blockIdx.z * p.b_bs;
+  float* Cb = p.C + (long)blockIdx.z * p.c_bs;
+  const int K16 = (p.K + 15) & ~15;
+  for (int e = t; e < K16 * BM; e += 256) {
+    const int ml = e % BM, kl = e / BM;
+    const int m = m0 + ml;
+    As[kl * LDA + ml] = __float2bfloat16_rn((m < p.M && kl < p.K) ? __ldg(Ab + m + kl * p.lda_k) : 0.f);
+  }
+  const bool m_fast = p.ldc_m == 1;
+  const bool vec4 = m_fast && p.bias == nullptr && !p.act && (p.M & 3) == 0 && (p.ldc_n & 3) == 0 && (p.c_bs & 3) == 0 &&
+                    ((uintptr_t)p.C & 15) == 0;
+  for (int n0 = 0; n0 < p.N; n0 += BN) {
+    for (int e = t; e < K16 * BN; e += 256) {
+      const int nl = e % BN, kl = e / BN;
+      const int n = n0 + nl;
+      Bs[kl * LDB + nl] = __float2bfloat16_rn((n < p.N && kl < p.K) ? __ldg(Bb + kl * p.ldb_k + n) : 0.f);
+    }
+    __syncthreads();   // As (first tile) / Bs written; the previous tile's Cs reads are done
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) wmma::fill_fragment(acc[i][j], 0.f);
+    for (int ks = 0; ks < K16; ks += 16) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> fa[2];
+      wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) wmma::load_matrix_sync(fa[i], &As[ks * LDA + wm * 32 + 16 * i], LDA);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) wmma::load_matrix_sync(fb[j], &Bs[ks * LDB + wn * 32 + 16 * j], LDB);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) wmma::mma_sync(acc[i][j], fa[i], fb[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        wmma::store_matrix_sync(&Cs[(wn * 32 + 16 * j) * LDC + wm * 32 + 16 * i], acc[i][j], LDC, wmma::mem_col_major);
+    __syncthreads();   // Cs complete; every warp is done reading Bs
+    if (vec4) {   // C unit-stride along m, rows 16-byte aligned: 16-byte stores, no bias / activation on this path
+      for (int e = t; e < BM * BN / 4; e += 256) {
+        const int ml = (e % (BM / 4)) * 4, nl = e / (BM / 4);
+        const int m = m0 + ml, n = n0 + nl;
+        if (m < p.M && n < p.N)
+          *reinterpret_cast<float4*>(Cb + m + n * p.ldc_n) = *reinterpret_cast<const float4*>(&Cs[nl * LDC + ml]);
+      }
+      continue;
+    }
+    for (int e = t; e < BM * BN; e += 256) {
+      const int ml = m_fast ? e % BM : e / BN, nl = m_fast ? e / BM : e % BN;
+      const int m = m0 + ml, n = n0 + nl;
+      if (m >= p.M || n >= p.N) continue;
+      float v = Cs[nl * LDC + ml];
+      if (p.bias) v += __ldg(p.bias + n);
+      if (p.act) v = lrelu(v);
+      Cb[m * p.ldc_m + n * p.ldc_n] = v;
+    }
+  }
+}
+
 template <int BM, int BN>
 static int launch_gemm_bf16(const GemmBf16P& p, bool a_col, bool b_row, dim3 grid, cudaStream_t st) {
-  if (a_col && b_row) gemm_bf16_kernel<BM, BN, true, true><<<grid, 256, 0, st>>>(p);
-  else if (a_col) gemm_bf16_kernel<BM, BN, true, false><<<grid, 256, 0, st>>>(p);
-  else if (b_row) gemm_bf16_kernel<BM, BN, false, true><<<grid, 256, 0, st>>>(p);
-  else gemm_bf16_kernel<BM, BN, false, false><<<grid, 256, 0, st>>>(p);
+  if (a_col && b_row) gemm_bf16_kernel<BM, BN, true, true, kGBK><<<grid, 256, 0, st>>>(p);
+  else if (a_col) gemm_bf16_kernel<BM, BN, true, false, kGBK><<<grid, 256, 0, st>>>(p);
+  else if (b_row) gemm_bf16_kernel<BM, BN, false, true, kGBK><<<grid, 256, 0, st>>>(p);
+  else gemm_bf16_kernel<BM, BN, false, false, kGBKWide><<<grid, 256, 0, st>>>(p);
   return check_launch("gemm_bf16_kernel");
 }
 
@@ -202,6 +282,16 @@ extern "C" int dbm_gemm_bf16(const float* a, long lda_m, long lda_k, long a_batc
   p.a_bs = a_batch_stride; p.b_bs = b_batch_stride; p.c_bs = c_batch_stride;
   p.act = act; p.atomic = accumulate == 2;
   const bool a_col = lda_m == 1, b_row = ldb_n == 1;
+  if (!p.atomic && a_col && b_row && k <= kSKMax && n >= 128) {
+    constexpr int kSKSmem = (kSKMax * (128 + 8) + kSKMax * (64 + 8)) * 2 + 64 * (128 + 4) * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+      DBM_CUDA(cudaFuncSetAttribute(gemm_bf16_shortk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSKSmem));
+      attr_done = true;
+    }
+    gemm_bf16_shortk_kernel<<<dim3(ceil_div(m, 128), 1, batch), 256, kSKSmem, st>>>(p);
+    return check_launch("gemm_bf16_shortk_kernel");
+  }
   const bool wide_n = m <= 64;   // M = 64 (weight gradient): 64 x 128 tiles; else 128 x 64
   const int bm = wide_n ? 64 : 128, bn = wide_n ? 128 : 64;
   dim3 grid(ceil_div(m, bm), ceil_div(n, bn), batch);
@@ -211,11 +301,12 @@ extern "C" int dbm_gemm_bf16(const float* a, long lda_m, long lda_k, long a_batc
     long tiles = (long)grid.x * grid.y;
     long z = (4L * num_sms() + tiles - 1) / tiles;
     if (z < 1) z = 1;
-    while ((long)batch * p.kchunks < z && p.kchunks < 64 && k / (p.kchunks * 2) >= 4 * kGBK) p.kchunks *= 2;
+    const int bk = (!a_col && !b_row) ? kGBKWide : kGBK;
+    while ((long)batch * p.kchunks < z && p.kchunks < 64 && k / (p.kchunks * 2) >= 4 * bk) p.kchunks *= 2;
     if (z > (long)batch * p.kchunks) z = (long)batch * p.kchunks;
     // K chunks must be whole K tiles so that tiles never straddle a chunk boundary
     const int klen = (k + p.kchunks - 1) / p.kchunks;
-    if (klen % kGBK != 0 && p.kchunks > 1) p.kchunks = 1;
+    if (klen % bk != 0 && p.kchunks > 1) p.kchunks = 1;
     if (z > (long)batch * p.kchunks) z = (long)batch * p.kchunks;
     grid.z = (unsigned)z;
   }
