@@ -88,6 +88,16 @@ class Adam:
 
 
 _COMM_STREAM = None
+_AUX_STREAM = None
+
+
+def _aux_stream():
+    """Side stream for work the step's critical path does not depend on (the metric-only discriminator pass)."""
+    global _AUX_STREAM
+    if _AUX_STREAM is None:
+        _AUX_STREAM = torch.cuda.Stream()
+    return _AUX_STREAM
+
 
 
 def _comm_stream():
@@ -246,16 +256,23 @@ def _generator_step_enqueue(input_arrays, g_model, d_model, g_optimizer, train, 
             fake = g_model.forward_train(X, input_arrays["W1"], input_arrays["W2"], input_arrays["W3"]).array
     else:
         fake = g_model.forward(X, input_arrays["W1"], input_arrays["W2"], input_arrays["W3"]).array
-    # eval-mode BatchNorm and `.array`: the adversarial term carries no gradient (:1228-1229)
-    fake_labels = d_model.forward(fake, train=False).array
     real = as_device(input_arrays["Y"])
     if tuple(real.shape) != tuple(fake.shape):
         raise ValueError("Input images must have the same dimensions.")            # :950-951
     n, _, H, W = fake.shape
-    real_labels = ops.empty(n, 1)
-    ops.fill(real_labels, 1.0)                                                     # :1233
-    # adversarial: calculate_discriminator_loss(real=real_labels, fake=fake_labels, rmf=0, fmr=1) (:874-879)
-    adv, _, _ = _ragan(real_labels, fake_labels, 0.0, 1.0, want_grads=False)
+    # eval-mode BatchNorm and `.array`: the adversarial term carries no gradient (:1228-1229), so the generator's
+    # backward does not wait for it -- when training, the discriminator pass runs on a side stream next to the image
+    # losses, backward and Adam (dozens of small kernels on either side) and joins before the results are read
+    cur = torch.cuda.current_stream()
+    side = _aux_stream() if train else cur
+    if side is not cur:
+        side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        fake_labels = d_model.forward(fake, train=False).array
+        real_labels = ops.empty(n, 1)
+        ops.fill(real_labels, 1.0)                                                 # :1233
+        # adversarial: calculate_discriminator_loss(real=real_labels, fake=fake_labels, rmf=0, fmr=1) (:874-879)
+        adv, _, _ = _ragan(real_labels, fake_labels, 0.0, 1.0, want_grads=False)
     # x_topo = X[:, :, 1:-1, 1:-1] (:1248)
     h, w = X.shape[2], X.shape[3]
     x_topo = ops.empty(n, 1, h - 2, w - 2)
@@ -272,6 +289,8 @@ def _generator_step_enqueue(input_arrays, g_model, d_model, g_optimizer, train, 
         reducer = GradBucketReducer(g_model)
         g_model.backward(dy, on_ready=reducer.bucket)                              # :1256
         g_optimizer.update(grad_scale=reducer.finish())                            # :1257
+    if side is not cur:
+        cur.wait_stream(side)
     return sums, adv, (n, H, W)
 
 
