@@ -201,12 +201,15 @@ def train_eval_discriminator(input_arrays: Dict[str, object], g_model: Generator
     return float(res[0]), float(res[1])
 
 
-def _discriminator_step_enqueue(input_arrays, g_model, d_model, d_optimizer, train, share_generator_forward):
+def _discriminator_step_enqueue(input_arrays, g_model, d_model, d_optimizer, train, share_generator_forward,
+                                fake=None):
     """Everything train_eval_discriminator launches, without the host read: returns the device pair
-    (d_loss, d_accu)."""
+    (d_loss, d_accu). ``fake``: the generator output if the caller already ran the forward."""
     if train:
         assert d_optimizer is not None  # :1127
-    if train and share_generator_forward:
+    if fake is not None:
+        pass
+    elif train and share_generator_forward:
         fake = g_model.forward_train(input_arrays["X"], input_arrays["W1"], input_arrays["W2"],
                                      input_arrays["W3"]).array
     else:
@@ -370,7 +373,18 @@ class GraphedTrainStep:
         self._restore(state)
 
     def _body(self):
-        out = _discriminator_step_enqueue(self.arrays, self.g, self.d, self.d_opt, True, True)
+        # Neither step's gradients depend on the other model's update: the discriminator step needs G(x) only, and
+        # the generator's backward needs the image losses only (the adversarial term is detached, :1228-1229). So
+        # after the one generator forward the step forks: the whole discriminator work (stacked forward, RaGAN,
+        # backward, Adam, then the metric-only eval pass on the updated weights) runs on a side stream next to
+        # image losses -> generator backward -> Adam on the main one, and joins before the metrics are read.
+        # Same values as the sequential order of trainer() (:1286-1308).
+        a = self.arrays
+        fake = self.g.forward_train(a["X"], a["W1"], a["W2"], a["W3"]).array
+        cur, side = torch.cuda.current_stream(), _aux_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out = _discriminator_step_enqueue(a, self.g, self.d, self.d_opt, True, True, fake=fake)
         w = self.LOSS_WEIGHTS
         sums, adv, shape = _generator_step_enqueue(self.arrays, self.g, self.d, self.g_opt, True,
                                                    w["content_loss_weighting"], w["topographic_loss_weighting"],
