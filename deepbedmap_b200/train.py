@@ -313,17 +313,27 @@ def _generator_step_finalize(s, adv_v, shape, content_loss_weighting, adversaria
     return float(g_loss), g_psnr, float(ssim)
 
 
-def trainer(i: int, columns: list, train_iter, dev_iter, g_model, g_optimizer, d_model, d_optimizer):
+def trainer(i: int, columns: list, train_iter, dev_iter, g_model, g_optimizer, d_model, d_optimizer,
+            graphed_step: Optional["GraphedTrainStep"] = None):
     """srgan_train.py:1267-1329. ``train_iter`` / ``dev_iter`` are objects with ``.epoch`` and
-    ``.next()`` returning a dict of batched arrays {X, W1, W2, W3, Y}."""
+    ``.next()`` returning a dict of batched arrays {X, W1, W2, W3, Y}. ``graphed_step`` (extension): a
+    GraphedTrainStep built on the same models / optimizers; minibatches of its batch shape are replayed from the
+    captured CUDA graph, any other (e.g. a short last minibatch) takes the eager functions."""
     metrics = {mn: [] for mn in columns}
     while i == train_iter.epoch:
         # one device copy of the batch for both steps, so the generator step can reuse the forward of the first
         arrays = {k: as_device(v) for k, v in train_iter.next().items()}
-        dl, da = train_eval_discriminator(arrays, g_model, d_model, d_optimizer, share_generator_forward=True)
+        if graphed_step is not None and graphed_step.accepts(arrays):
+            (dl, da), (gl, gp, gs) = graphed_step.step(arrays)
+        else:
+            if graphed_step is not None:
+                graphed_step.refresh()     # eager updates follow: see GraphedTrainStep.refresh
+            dl, da = train_eval_discriminator(arrays, g_model, d_model, d_optimizer, share_generator_forward=True)
+            gl, gp, gs = train_eval_generator(arrays, g_model, d_model, g_optimizer)
+            if graphed_step is not None:
+                graphed_step.refresh()
         metrics["discriminator_loss"].append(dl)
         metrics["discriminator_accu"].append(da)
-        gl, gp, gs = train_eval_generator(arrays, g_model, d_model, g_optimizer)
         metrics["generator_loss"].append(gl)
         metrics["generator_psnr"].append(gp)
         metrics["generator_ssim"].append(gs)
@@ -414,6 +424,20 @@ class GraphedTrainStep:
         # an eval-mode forward re-packs them and changes no state.
         self.d.forward(self.arrays["Y"], train=False)
         torch.cuda.synchronize()
+
+    def accepts(self, input_arrays: Dict[str, object]) -> bool:
+        """True when the minibatch has the shapes the graph was captured for."""
+        return all(k in input_arrays and tuple(np.shape(input_arrays[k])) == tuple(v.shape)
+                   for k, v in self.arrays.items())
+
+    def refresh(self):
+        """Call after the weights or Adam state were changed OUTSIDE the graph (eager training steps, load_npz,
+        load_state_dict): re-synchronises the device step counts and the discriminator's packed operand images
+        (the graph re-packs them only after its own discriminator update)."""
+        for opt in (self.g_opt, self.d_opt):
+            opt.t_dev.fill_(opt.t)
+        self.d.mark_updated()
+        self.d.forward(self.arrays["Y"], train=False)
 
     def step(self, input_arrays: Optional[Dict[str, object]] = None):
         if input_arrays is not None:

@@ -373,6 +373,35 @@ def test_graphed_train_step_matches_eager():
     assert np.allclose(ev, ev_ref, rtol=5e-3, atol=1e-5), (ev, ev_ref)
 
 
+def test_trainer_epoch_eager_and_graphed_is_nan_free():
+    """An epoch of trainer() (srgan_train.py:1267-1329) on a tiny dataset: every metric finite (the reference's
+    behave test, features/steps/test_srgan_train.py:60-67), weights change; second epoch through the captured graph
+    with a short last minibatch falling back to the eager functions."""
+    from deepbedmap_b200 import train as T
+    rng = np.random.RandomState(0)
+    def data(n):
+        return {"X": rng.rand(n, 1, 11, 11).astype(np.float32), "W1": rng.rand(n, 1, 110, 110).astype(np.float32),
+                "W2": rng.rand(n, 2, 22, 22).astype(np.float32), "W3": rng.rand(n, 1, 11, 11).astype(np.float32),
+                "Y": rng.rand(n, 1, 36, 36).astype(np.float32)}
+    g, g_opt, d, d_opt = T.compile_srgan_model(num_residual_blocks=1)
+    train_iter = T.ArrayIterator(data(10), 4, shuffle=True)     # 4 + 4 + 2 per epoch
+    dev_iter = T.ArrayIterator(data(4), 4, shuffle=False)
+    columns = ["discriminator_loss", "discriminator_accu", "generator_loss", "generator_psnr", "generator_ssim"]
+    columns += ["val_" + c for c in columns]
+    w0 = g.flat.clone()
+    m0 = T.trainer(0, columns, train_iter, dev_iter, g, g_opt, d, d_opt)
+    assert all(len(m0[c]) == (3 if not c.startswith("val_") else 1) for c in columns)
+    assert all(np.isfinite(v) for c in columns for v in m0[c])
+    assert not torch.equal(w0, g.flat) and g_opt.t == 3
+    first = {k: v[:4] for k, v in train_iter.arrays.items()}
+    step = T.GraphedTrainStep(first, g, g_opt, d, d_opt)
+    w1 = g.flat.clone()
+    m1 = T.trainer(1, columns, train_iter, dev_iter, g, g_opt, d, d_opt, graphed_step=step)
+    assert all(len(m1[c]) == (3 if not c.startswith("val_") else 1) for c in columns)
+    assert all(np.isfinite(v) for c in columns for v in m1[c])
+    assert not torch.equal(w1, g.flat) and g_opt.t == 6 and int(g_opt.t_dev[0]) == 6 and d_opt.t == 6
+
+
 def test_npz_roundtrip(tmp_path):
     from deepbedmap_b200 import DiscriminatorModel, GeneratorModel
     from deepbedmap_b200.npz import peek_num_residual_blocks
