@@ -382,9 +382,10 @@ class FlatTrunk:
         ops.call("dbm_flat_to_nchw", self.a3f.data_ptr(), None, a3.data_ptr(), 64, n, H, W, st)
         return a3
 
-    def backward(self, da3_nchw: torch.Tensor) -> torch.Tensor:
+    def backward(self, da3_nchw: torch.Tensor, wgrad_stream=None) -> torch.Tensor:
         """da3 (n,64,H,W) -> accumulates the trunk's weight/bias gradients into the model's flat_grad and
-        returns d(loss)/d(a0) (n,128,H,W)."""
+        returns d(loss)/d(a0) (n,128,H,W). ``wgrad_stream``: torch stream for the weight / bias gradient launches
+        (they start after the data-gradient chain; the CALLER joins that stream before using the gradients)."""
         n, H, W = self.n, self.H, self.W
         st = ops.stream()
         ops.call("dbm_flat_from_nchw", da3_nchw.data_ptr(), 64, self.gpost.data_ptr(), self.da3f.data_ptr(), 1.0, n, H, W,
@@ -395,9 +396,13 @@ class FlatTrunk:
         else:
             self.model._pack(self.model.PACK_TRAIN_CHAIN)
             self._chain(self.bwd, self.bwd_dev)
-        ops.call("dbm_flat_wgrad", self.units_dev.data_ptr(), self.n_units, n, H, W, st)
-        ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, st)
-        ops.call("dbm_flat_bias_grad", self.bias_dev.data_ptr(), self.n_bias, n, H, W, st)
+        if wgrad_stream is not None:
+            wgrad_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(wgrad_stream if wgrad_stream is not None else torch.cuda.current_stream()):
+            ws = ops.stream()
+            ops.call("dbm_flat_wgrad", self.units_dev.data_ptr(), self.n_units, n, H, W, ws)
+            ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, ws)
+            ops.call("dbm_flat_bias_grad", self.bias_dev.data_ptr(), self.n_bias, n, H, W, ws)
         da0 = ops.empty(n, 128, H, W)
         ops.call("dbm_flat_to_nchw", self.da0f.data_ptr(), None, da0.data_ptr(), 128, n, H, W, st)
         return da0

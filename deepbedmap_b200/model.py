@@ -426,11 +426,16 @@ class GeneratorModel(_Link):
         del du1, dc1
         if "flat" in c:
             # tensor-core trunk: data-gradient chain, batched weight/bias gradients (flat.py)
-            da0 = c["flat"].backward(da3)
+            # The trunk's weight / bias gradients (one batched launch + reduction) only feed the optimizer: they run on
+            # a side stream beside the stem's backward and are joined before any gradient bucket is handed on.
+            cur, aux = torch.cuda.current_stream(), ops._aux_stream()
+            da0 = c["flat"].backward(da3, wgrad_stream=aux)
+            self._stem_bwd(c, da0, lambda *pre: None)
+            cur.wait_stream(aux)
             ready("post_residual_conv_layer", "post_upsample_conv_layer", "final_conv_layer")
             for i in reversed(range(self.num_residual_blocks)):
                 ready(f"residual_network/{i}/")
-            self._stem_bwd(c, da0, ready)
+            ready("input_block/", "pre_residual_conv_layer")
             return
         # ---- post-residual conv ----
         cats = c["cats"]

@@ -9,6 +9,17 @@ from . import _lib
 call = _lib.call
 
 
+_AUX = None
+
+
+def _aux_stream():
+    """Side stream for gradient work nothing downstream in backward waits for (always joined by its caller)."""
+    global _AUX
+    if _AUX is None:
+        _AUX = torch.cuda.Stream()
+    return _AUX
+
+
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -202,14 +213,20 @@ def deform_conv_bwd(x, offset, w, cols, dy, dw, db, dx, tc=False):
     hw = h * wd
     k = c * 9
     # dw[o, kk] += sum_{n,p} dy[n,o,p] * cols[n,kk,p]   (atomic across the batch)
-    gemm(dy, hw, 1, o * hw, cols, 1, hw, k * hw, dw, k, 1, 0, None, o, k, hw, batch=n, accumulate=2, tc=tc)
-    call("dbm_bias_grad_f32", dy.data_ptr(), o * hw, db.data_ptr(), n, o, hw, stream())
+    # The weight / bias gradients only feed the optimizer: they run on a side stream beside the cols gradient and
+    # its scatter (an atomics-bound kernel that leaves most of the GPU idle), joined before returning.
+    cur, aux = torch.cuda.current_stream(), _aux_stream()
+    aux.wait_stream(cur)
+    with torch.cuda.stream(aux):
+        gemm(dy, hw, 1, o * hw, cols, 1, hw, k * hw, dw, k, 1, 0, None, o, k, hw, batch=n, accumulate=2, tc=tc)
+        call("dbm_bias_grad_f32", dy.data_ptr(), o * hw, db.data_ptr(), n, o, hw, stream())
     # dcols[n, kk, p] = sum_o w[o, kk] * dy[n, o, p]
     dcols = empty(n, k, hw)
     gemm(dy, 1, hw, o * hw, w, k, 1, 0, dcols, 1, hw, k * hw, None, hw, k, o, batch=n, tc=tc)
     doff = empty(n, 18, h, wd)
     call("dbm_deform_bwd_f32", x.data_ptr(), offset.data_ptr(), dcols.data_ptr(),
          dx.data_ptr() if dx is not None else None, doff.data_ptr(), n, c, h, wd, stream())
+    cur.wait_stream(aux)
     return doff
 
 
