@@ -22,7 +22,7 @@ constexpr int kDGatherThreads = 3 * kDPix; // 768
 constexpr int kDThreads = kDGatherThreads + 128 + 32;  // + 4 epilogue warps + MMA warp
 constexpr int kDABytes = kDPix * 64 * 2;               // one tap: 2 M-tiles x 128 px x 64 ch bf16
 constexpr int kDBBytes = 9 * 64 * 64 * 2;
-constexpr int kDSmem = kDBBytes + kDStages * kDABytes + 256 + 1024;
+constexpr int kDSmem = kDBBytes + kDStages * kDABytes + 256 + 9 * 64 * 4 + 1024;
 
 struct DeformParams {
   int N, H, W;
@@ -35,6 +35,10 @@ struct DeformParams {
   int act;
   __nv_bfloat16* out;           // slab8 [N][out_cs_total][H][W][8] at slab offset out_cs0
   int out_cs_total, out_cs0;
+  // optional fused "tap projection" of the FOLLOWING single-output deformable layer (deform_out1_*): proj[n][t][p] =
+  // sum_c proj_w[c][t] * out[c][p] computed from the bf16-rounded outputs while they are in registers
+  const float* proj_w;          // (1, 64, 3, 3) filter of the next layer, or NULL
+  float* proj_out;              // [N][9][H*W]
 };
 
 // Sampling position of one tap: the four corner addresses are CLAMPED into the image and the
@@ -111,6 +115,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   return o;
 }
 
+template <bool PROJ>   // PROJ: also compute the following single-output layer's tap projection in the epilogue
 __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -123,6 +128,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
   uint64_t* tempty = bars + 2 * kDStages + 2;
   uint64_t* wbar = bars + 2 * kDStages + 4;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kDStages + 5);
+  float* sproj = (float*)(smem + kDBBytes + kDStages * kDABytes + 256);   // [9][64] projection filter, tap-major
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kMmaWarp = kDGatherThreads / 32;
@@ -139,6 +145,8 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
+  if (PROJ)
+    for (int i = threadIdx.x; i < 576; i += kDThreads) sproj[(i % 9) * 64 + i / 9] = p.proj_w[i];
   if (warp == kMmaWarp) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -258,6 +266,7 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
       const int buf = it & 1;
       mbar_wait(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
+      float pr[9];
 #pragma unroll
       for (int jc = 0; jc < 4; ++jc) {
         const int j = jc >> 1, c0 = (jc & 1) * 32;
@@ -266,6 +275,10 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 128 + j * 64 + c0), acc);
         tmem_wait_ld();
+        if (PROJ && c0 == 0) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) pr[t] = 0.f;
+        }
         if (valid) {
 #pragma unroll
           for (int s8 = 0; s8 < 4; ++s8) {
@@ -276,7 +289,24 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
               if (p.act) v[i] = lrelu(v[i]);
             }
             const size_t cs = (size_t)n * p.out_cs_total + (p.out_cs0 + c0 / 8 + s8);
-            *reinterpret_cast<uint4*>(p.out + ((cs * p.H + y) * p.W + x) * 8) = pack8(v);
+            const uint4 o = pack8(v);
+            *reinterpret_cast<uint4*>(p.out + ((cs * p.H + y) * p.W + x) * 8) = o;
+            if (PROJ) {
+              // same operands (the bf16-rounded outputs) and the same channel order as deform_out1_project_kernel
+              const float f[8] = {__uint_as_float(o.x << 16), __uint_as_float(o.x & 0xffff0000u),
+                                  __uint_as_float(o.y << 16), __uint_as_float(o.y & 0xffff0000u),
+                                  __uint_as_float(o.z << 16), __uint_as_float(o.z & 0xffff0000u),
+                                  __uint_as_float(o.w << 16), __uint_as_float(o.w & 0xffff0000u)};
+#pragma unroll
+              for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) pr[t] = fmaf(f[c], sproj[t * 64 + c0 + 8 * s8 + c], pr[t]);
+            }
+          }
+          if (PROJ && c0 == 32) {
+            const size_t hw = (size_t)p.H * p.W;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) p.proj_out[((size_t)n * 9 + t) * hw + (size_t)y * p.W + x] = pr[t];
           }
         }
       }
@@ -367,7 +397,10 @@ using namespace dbm;
 
 extern "C" int dbm_deform_conv_umma(const void* x_slab8, const float* offset_slab4, int offset_cs_total,
                                     const void* wpacked_ck64, const float* bias, int n, int h, int w, int act,
-                                    void* out_slab8, int out_cs_total, int out_cs0, cudaStream_t stream) {
+                                    void* out_slab8, int out_cs_total, int out_cs0, const float* next_out1_filter,
+                                    float* next_out1_proj, cudaStream_t stream) {
+  DBM_REQUIRE((next_out1_filter == nullptr) == (next_out1_proj == nullptr),
+              "deform_conv_umma: the fused tap projection needs both the filter and the output buffer");
   DBM_REQUIRE(n > 0 && h > 0 && w > 0, "deform_conv_umma: empty input");
   DBM_REQUIRE(offset_cs_total >= 5, "deform_conv_umma: offset tensor needs >= 18 channels (5 slabs)");
   DBM_REQUIRE(((uintptr_t)x_slab8 & 15) == 0 && ((uintptr_t)wpacked_ck64 & 15) == 0 &&
@@ -375,7 +408,8 @@ extern "C" int dbm_deform_conv_umma(const void* x_slab8, const float* offset_sla
               "deform_conv_umma: unaligned pointer");
   static bool attr_done = false;
   if (!attr_done) {
-    DBM_CUDA(cudaFuncSetAttribute(deform_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
+    DBM_CUDA(cudaFuncSetAttribute(deform_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
+    DBM_CUDA(cudaFuncSetAttribute(deform_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
     attr_done = true;
   }
   DeformParams p;
@@ -385,9 +419,25 @@ extern "C" int dbm_deform_conv_umma(const void* x_slab8, const float* offset_sla
   p.x = (const __nv_bfloat16*)x_slab8; p.off = offset_slab4; p.off_cs = offset_cs_total;
   p.wpacked = (const __nv_bfloat16*)wpacked_ck64; p.bias = bias; p.act = act;
   p.out = (__nv_bfloat16*)out_slab8; p.out_cs_total = out_cs_total; p.out_cs0 = out_cs0;
+  p.proj_w = next_out1_filter; p.proj_out = next_out1_proj;
   const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
-  deform_umma_kernel<<<grid, kDThreads, kDSmem, stream>>>(p);
+  if (p.proj_w != nullptr) deform_umma_kernel<true><<<grid, kDThreads, kDSmem, stream>>>(p);
+  else deform_umma_kernel<false><<<grid, kDThreads, kDSmem, stream>>>(p);
   return check_launch("deform_umma_kernel");
+}
+
+// The sampling half of dbm_deform_conv_out1 alone: the nine projected planes were already produced by the preceding
+// layer's fused epilogue (dbm_deform_conv_umma with next_out1_filter).
+extern "C" int dbm_deform_out1_sample(const float* proj, const float* offset_slab4, int offset_cs_total,
+                                      const float* bias, float* y, int n, int h, int w, cudaStream_t stream) {
+  DBM_REQUIRE(n > 0 && h > 0 && w > 0 && proj && y, "deform_out1_sample: empty input");
+  DBM_REQUIRE(offset_cs_total >= 5, "deform_out1_sample: offset tensor needs >= 18 channels (5 slabs)");
+  const long total = (long)n * h * w;
+  long blocks = (total + 255) / 256;
+  const long cap = (long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  deform_out1_sample_kernel<<<(int)blocks, 256, 0, stream>>>(proj, offset_slab4, offset_cs_total, bias, y, n, h, w);
+  return check_launch("deform_out1_sample_kernel");
 }
 
 extern "C" int dbm_deform_conv_out1(const void* x_slab8, const float* offset_slab4, int offset_cs_total,

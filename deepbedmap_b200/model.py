@@ -182,6 +182,9 @@ class GeneratorModel(_Link):
         self.paired_trunk = True       # dense-block layer pairing inside the persistent kernel
         self.per_layer_ck16 = False    # per-layer launches in the trunk kernel's 16-channel chunks (bit-exact A/B)
         self.local_trunk = True        # tiles of <= 128 padded positions: image-resident trunk kernel (umma_local.cu)
+        # output layer's tap projection inside the first deformable layer's epilogue: bit-identical, but measured
+        # SLOWER (the four epilogue warps become the bottleneck: 2.11 -> 2.57 ms to save a 0.25 ms kernel) -> off
+        self.fuse_out_projection = False
         self._ctx = None
 
     # ---- serialisation (chainer.serializers.load_npz / save_npz, App. C layout) ----
@@ -774,12 +777,16 @@ class GeneratorModel(_Link):
         ops.conv3x3_umma(f1, 64, wq, bq, 32, out_f32=off_s)
         d1 = ops.empty(n, 8, 4 * H, 4 * W, 8, dtype=bf)
         wq, bq = pk["final_conv_layer1/deform_conv"]
-        ops.deform_conv_umma(f1, off_s, wq, bq, d1, act=True)
+        if self.out_channels != 1:
+            raise ValueError("the tensor-core path implements out_channels == 1 (the reference's only use)")
+        # the output layer's tap projection (64 -> 9 planes) is computed in this layer's epilogue
+        proj = ops.deform_conv_umma(f1, off_s, wq, bq, d1, act=True,
+                                    next_out1_w=P["final_conv_layer2/deform_conv/W"] if self.fuse_out_projection else None)
         del f1
         wq, bq = pk["final_conv_layer2/offset_conv"]
         ops.conv3x3_umma(d1, 64, wq, bq, 32, out_f32=off_s)
-        if self.out_channels != 1:
-            raise ValueError("the tensor-core path implements out_channels == 1 (the reference's only use)")
+        if proj is not None:
+            return ops.deform_out1_sample(proj, off_s, P["final_conv_layer2/deform_conv/b"])
         return ops.deform_conv_out1(d1, off_s, P["final_conv_layer2/deform_conv/W"],
                                     P["final_conv_layer2/deform_conv/b"])
 

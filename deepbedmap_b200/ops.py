@@ -159,12 +159,29 @@ def pack_conv3x3(w, cout_padded, ck=32):
     return packed
 
 
-def deform_conv_umma(x_s8, off_s4, wpacked, bias, out_s8, act=False, out_cs0=0):
-    """Deformable 3x3 conv 64->64 on the tensor cores: x (N,8,H,W,8) bf16, offsets (N,>=5,H,W,4) fp32."""
+def deform_conv_umma(x_s8, off_s4, wpacked, bias, out_s8, act=False, out_cs0=0, next_out1_w=None):
+    """Deformable 3x3 conv 64->64 on the tensor cores: x (N,8,H,W,8) bf16, offsets (N,>=5,H,W,4) fp32.
+    ``next_out1_w``: (1,64,3,3) filter of a following single-output deformable layer -> also returns its nine
+    projected planes (N,9,H,W), computed in the epilogue (finish with deform_out1_sample)."""
     n, cs, h, w, _ = x_s8.shape
     assert cs == 8, "deform_conv_umma needs 64 input channels"
+    proj = None
+    if next_out1_w is not None:
+        assert tuple(next_out1_w.shape) == (1, 64, 3, 3)
+        proj = empty(n, 9, h, w)
     call("dbm_deform_conv_umma", x_s8.data_ptr(), off_s4.data_ptr(), off_s4.shape[1], wpacked.data_ptr(),
-         bias.data_ptr(), n, h, w, int(act), out_s8.data_ptr(), out_s8.shape[1], out_cs0, stream())
+         bias.data_ptr(), n, h, w, int(act), out_s8.data_ptr(), out_s8.shape[1], out_cs0,
+         next_out1_w.data_ptr() if proj is not None else None, proj.data_ptr() if proj is not None else None, stream())
+    return proj
+
+
+def deform_out1_sample(proj, off_s4, bias):
+    """Sampling half of the single-output deformable layer on planes projected by deform_conv_umma."""
+    n, _, h, wd = proj.shape
+    y = empty(n, 1, h, wd)
+    call("dbm_deform_out1_sample", proj.data_ptr(), off_s4.data_ptr(), off_s4.shape[1], bias.data_ptr(), y.data_ptr(),
+         n, h, wd, stream())
+    return y
 
 
 def deform_conv_out1(x_s8, off_s4, w, bias):

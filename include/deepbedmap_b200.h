@@ -212,7 +212,13 @@ int dbm_stem_fwd_flat(const float* x, const float* w1, const float* w2, const fl
  * offset_slab4: fp32 slab4 with >= 18 channels ([0:9] = dx, [9:18] = dy). */
 int dbm_deform_conv_umma(const void* x_slab8, const float* offset_slab4, int offset_cs_total,
                          const void* wpacked_ck64, const float* bias, int n, int h, int w, int act, void* out_slab8,
-                         int out_cs_total, int out_cs0, cudaStream_t stream);
+                         int out_cs_total, int out_cs0, const float* next_out1_filter, float* next_out1_proj,
+                         cudaStream_t stream);
+/* next_out1_filter / next_out1_proj (both or neither): the (1, 64, 3, 3) filter of a FOLLOWING single-output
+ * deformable layer and a [n][9][h*w] buffer -- the layer's "tap projection" (see dbm_deform_conv_out1) is then
+ * computed in this kernel's epilogue from the outputs in registers; finish that layer with dbm_deform_out1_sample. */
+int dbm_deform_out1_sample(const float* proj, const float* offset_slab4, int offset_cs_total, const float* bias,
+                           float* y, int n, int h, int w, cudaStream_t stream);
 /* proj_scratch: n*9*h*w floats (the 64 channels projected onto the 9 taps before sampling) */
 int dbm_deform_conv_out1(const void* x_slab8, const float* offset_slab4, int offset_cs_total, const float* w_f32,
                          const float* bias, float* y, float* proj_scratch, int n, int h, int w, cudaStream_t stream);

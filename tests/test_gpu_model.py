@@ -201,6 +201,18 @@ def test_image_resident_inference_trunk_tracks_tiled_kernels(nb, n, h, w):
         assert rel_l2(got.cpu().numpy(), emu) < 8e-3
 
 
+def test_fused_output_projection_is_bit_identical():
+    """The output layer's tap projection computed in the first deformable layer's epilogue (same bf16-rounded
+    operands, same channel order) against the separate projection kernel."""
+    m, params = make_generator(2, "bf16", scale=0.7)
+    for n, h, w in ((2, 11, 11), (1, 37, 29)):
+        ins = O.synthetic_inputs(n, h, w)
+        m.fuse_out_projection = False
+        ref = m.forward(*ins).array.clone()
+        m.fuse_out_projection = True
+        assert torch.equal(m.forward(*ins).array, ref)
+
+
 def test_generator_reference_init_scale():
     """Reference initialisation (HeNormal scale 0.1, zero biases): outputs are tiny but must
     still agree relatively."""
