@@ -26,6 +26,11 @@ namespace dbm {
 
 constexpr int kLocThreads = 320;           // warp 0 bulk-copy producer, warp 1 MMA issuer, warps 2-9 epilogue
 constexpr int kLocStages = 5;
+// SOLO form (batches larger than the SM count): one image per CTA, 192 threads (four epilogue warps), 3 stages,
+// 256 TMEM columns and a shared-memory footprint under half an SM, so TWO CTAs share an SM: one image's pass
+// hand-off (commit -> epilogue -> fence -> next MMA, ~2/3 of a pass at batch 128) hides under the other's MMAs.
+constexpr int kLocSoloThreads = 192;
+constexpr int kLocSoloStages = 3;
 constexpr int kLocStageBytes = 96 * 192;   // 3 taps x 2 slabs x (N/8) x 128 B at N = 192
 constexpr int kLocSlabs = 24;              // 192 channels
 constexpr int kLocAcc = 192, kLocXcur = 192, kLocSlot = 256;  // TMEM columns per image slot
@@ -88,12 +93,16 @@ __device__ __forceinline__ uint4 pack8f(const float* v) {
   return o;
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(kLocThreads, 1) local_trunk_kernel(const LocalParams p) {
+template <bool BWD, bool SOLO>
+__global__ void __launch_bounds__(SOLO ? kLocSoloThreads : kLocThreads, SOLO ? 2 : 1)
+local_trunk_kernel(const LocalParams p) {
+  constexpr int kStages = SOLO ? kLocSoloStages : kLocStages;
+  constexpr int kThreads = SOLO ? kLocSoloThreads : kLocThreads;
+  constexpr int kSlots = SOLO ? 1 : 2;          // image slots (operand buffers, TMEM column blocks, epilogue groups)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)smem;
-  uint64_t* empty = full + kLocStages;
+  uint64_t* empty = full + kLocStages;          // (barrier area sized for the larger ring in both forms)
   uint64_t* tfull = empty + kLocStages;   // MMA -> epilogue: a pass is complete
   uint64_t* act_ready = tfull + 1;        // epilogue -> MMA: outputs are in smem, accumulator columns are free
   uint64_t* in_full = act_ready + 1;      // producer -> MMA: the stem outputs of the image pair are in smem
@@ -102,22 +111,22 @@ __global__ void __launch_bounds__(kLocThreads, 1) local_trunk_kernel(const Local
   const uint32_t slab_bytes = (uint32_t)p.RA * 16u;
   const uint32_t abuf_bytes = (uint32_t)kLocSlabs * slab_bytes;
   uint8_t* abuf = smem + 256;                       // [2 images][24 slabs][RA rows][16 B]
-  uint8_t* stages = abuf + 2 * abuf_bytes;          // [kLocStages][kLocStageBytes]
+  uint8_t* stages = abuf + kSlots * abuf_bytes;     // [kStages][kLocStageBytes]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // borders, guard rows and the slabs no bulk copy touches must read as zero
-  for (uint32_t i = threadIdx.x; i < 2 * abuf_bytes / 16; i += kLocThreads)
+  for (uint32_t i = threadIdx.x; i < kSlots * abuf_bytes / 16; i += kThreads)
     reinterpret_cast<uint4*>(abuf)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kLocStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tfull, 1);
-    mbar_init(act_ready, 8);
+    mbar_init(act_ready, 4 * kSlots);
     mbar_init(in_full, 1);
     mbar_init(a_free, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc<SOLO ? 256 : 512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(kLocThreads, 1) local_trunk_kernel(const Local
             mbar_wait(&empty[s], ph ^ 1);
             mbar_arrive_expect_tx(&full[s], bytes);
             bulk_load(stages + s * kLocStageBytes, w + (size_t)g3 * (bytes / 2), bytes, &full[s]);
-            if (++s == kLocStages) { s = 0; ph ^= 1; }
+            if (++s == kStages) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(kLocThreads, 1) local_trunk_kernel(const Local
               if (last) umma_commit(tfull);
             }
             __syncwarp();
-            if (++s == kLocStages) { s = 0; ph ^= 1; }
+            if (++s == kStages) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -444,7 +453,7 @@ __global__ void __launch_bounds__(kLocThreads, 1) local_trunk_kernel(const Local
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<SOLO ? 256 : 512>(tmem_base);
   }
 }
 
@@ -469,24 +478,40 @@ static int local_trunk_launch(bool bwd, const void* passes_dev, int count, int n
   p.G0 = (p.halo + 7) & ~7;                                    // as flat_geom() in umma_flat.cu
   const int tiles = (n * p.img + 127) / 128;
   p.Pg = p.G0 + tiles * 128 + p.G0;
-  p.RA = 128 + 2 * p.halo;
   p.s0 = (const __nv_bfloat16*)in_flat; p.in_slabs = bwd ? 8 : 16;
   p.x0 = x0_scratch; p.xrr = xrr_scratch;
-  const size_t smem = 1024 + 256 + 2 * (size_t)kLocSlabs * p.RA * 16 + (size_t)kLocStages * kLocStageBytes;
-  DBM_REQUIRE(smem <= 227 * 1024, "%s: image width %d needs %zu bytes of shared memory", who, w, smem);
-  static size_t attr_smem[2] = {0, 0};
-  if (smem > attr_smem[bwd]) {
-    if (bwd) DBM_CUDA(cudaFuncSetAttribute(local_trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else DBM_CUDA(cudaFuncSetAttribute(local_trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem[bwd] = smem;
+  // Form: batches that fit the SMs take one image per CTA (320 threads, 5 stages); larger ones the SOLO form, two
+  // CTAs per SM (dbm_local_debug_set: 1 / 2 = force 1 / 2 images per CTA in lock step, 3 = force SOLO).
+  const bool solo = g_local_group == 3 || (g_local_group == 0 && n > num_sms());
+  size_t smem;
+  if (solo) {
+    // slab stride = exactly the rows a bulk copy fills: the <= 2 halo rows an MMA reads past a slab's end alias the
+    // next slab's leading (zero) halo rows -- or, after the last slab, ring bytes that only reach discarded rows
+    p.RA = 2 * p.halo + p.img;
+    p.group = 1;
+    smem = 1024 + 256 + (size_t)kLocSlabs * p.RA * 16 + (size_t)kLocSoloStages * kLocStageBytes;
+  } else {
+    p.RA = 128 + 2 * p.halo;
+    p.group = (g_local_group == 1 || g_local_group == 2) ? g_local_group : 1;
+    smem = 1024 + 256 + 2 * (size_t)kLocSlabs * p.RA * 16 + (size_t)kLocStages * kLocStageBytes;
   }
-  // one image per CTA while that still leaves SMs idle (the filter stream is then read once per image instead of
-  // once per pair, but twice as many SMs work), else pairs
-  p.group = (g_local_group > 0) ? g_local_group : (n <= num_sms() ? 1 : 2);
+  DBM_REQUIRE(smem <= 227 * 1024, "%s: image width %d needs %zu bytes of shared memory", who, w, smem);
+  static size_t attr_smem[2][2] = {{0, 0}, {0, 0}};
+  if (smem > attr_smem[bwd][solo]) {
+    const int v = (int)smem;
+    if (bwd && solo) DBM_CUDA(cudaFuncSetAttribute(local_trunk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+    else if (bwd) DBM_CUDA(cudaFuncSetAttribute(local_trunk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+    else if (solo) DBM_CUDA(cudaFuncSetAttribute(local_trunk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+    else DBM_CUDA(cudaFuncSetAttribute(local_trunk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+    attr_smem[bwd][solo] = smem;
+  }
   const int npairs = (n + p.group - 1) / p.group;
-  const int grid = npairs < num_sms() ? npairs : num_sms();
-  if (bwd) local_trunk_kernel<true><<<grid, kLocThreads, smem, stream>>>(p);
-  else local_trunk_kernel<false><<<grid, kLocThreads, smem, stream>>>(p);
+  const int cap = solo ? 2 * num_sms() : num_sms();
+  const int grid = npairs < cap ? npairs : cap;
+  if (bwd && solo) local_trunk_kernel<true, true><<<grid, kLocSoloThreads, smem, stream>>>(p);
+  else if (bwd) local_trunk_kernel<true, false><<<grid, kLocThreads, smem, stream>>>(p);
+  else if (solo) local_trunk_kernel<false, true><<<grid, kLocSoloThreads, smem, stream>>>(p);
+  else local_trunk_kernel<false, false><<<grid, kLocThreads, smem, stream>>>(p);
   return check_launch(bwd ? "local_trunk_kernel<bwd>" : "local_trunk_kernel<fwd>");
 }
 

@@ -28,7 +28,8 @@ def timed(fn):
 
 ft.forward(a0)
 m._pack(m.PACK_TRAIN_CHAIN)
-for label, local, group in (("flat chain", False, 0), ("image-resident, 1 image/CTA", True, 1), ("image-resident, 2 images/CTA", True, 2)):
+for label, local, group in (("flat chain", False, 0), ("image-resident, 1 image/CTA", True, 1), ("image-resident, 2 images/CTA in lock step", True, 2),
+                            ("image-resident, SOLO (2 CTAs/SM)", True, 3)):
     ft.local = local
     ops.call("dbm_local_debug_set", group)
     if local:
