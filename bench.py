@@ -265,7 +265,10 @@ def train_bench(rank, world, steps=20, warmup=3, batch=128):
     e1.record()
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world)
+    # algorithmic work of a step: 6.4995 GFLOP per sample with the generator forward counted once
+    gflop_step = 6.4995 * batch * world
     return {"metric": "train steps/s (D-step + G-step, batch 128 per GPU)", "value": steps / (ms * 1e-3),
+            "algorithmic_tflops": gflop_step * steps / (ms * 1e-3) / 1e3,
             "unit": "steps/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "scaling": "weak",
             "global_batch": batch * world, "dtype": "bf16 tensor-core operands / fp32 accumulation for every 3x3 conv of G and D (fwd, dgrad, wgrad) and the "
                                                "deformable contraction; fp32 stem, bilinear sampling, BN, losses, Adam",
