@@ -3,7 +3,7 @@ discriminator, training step, tiled continent predictor) behind the reference's 
 from ._lib import DeepBedMapError, LIB_PATH  # noqa: F401
 
 __all__ = ["GeneratorModel", "DiscriminatorModel", "compile_srgan_model", "train_eval_discriminator",
-           "train_eval_generator", "trainer", "predict_continent", "Adam", "DeepBedMapError"]
+           "train_eval_generator", "trainer", "GraphedTrainStep", "predict_continent", "Adam", "DeepBedMapError"]
 
 
 def __getattr__(name):  # lazy: importing the package must not require a GPU
@@ -11,7 +11,7 @@ def __getattr__(name):  # lazy: importing the package must not require a GPU
         from . import model
         return getattr(model, name)
     if name in ("compile_srgan_model", "train_eval_discriminator", "train_eval_generator", "trainer", "Adam",
-                "ArrayIterator", "DeviceArrayIterator", "save_model_weights_and_architecture"):
+                "ArrayIterator", "DeviceArrayIterator", "save_model_weights_and_architecture", "GraphedTrainStep"):
         from . import train
         return getattr(train, name)
     if name in ("predict_continent", "tile_plan", "ContinentGrids"):
