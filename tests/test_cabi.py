@@ -92,3 +92,29 @@ def test_flat_layout_geometry_host_formula_matches_library():
     assert flat.chunk_channels(160) == [(0, 128), (128, 32)]
     # d(x_{j+1}) -> conv5 output gradient scale: beta, beta, beta^2 within every RRDB (srgan_train.py:358, 402)
     assert [round(d["g5_scale"], 6) for d in flat.rdb_plan(6, 0.1)] == [0.1, 0.1, 0.01, 0.1, 0.1, 0.01]
+
+
+def test_table_records_match_the_kernels_struct_sizes():
+    """The device tables the host builds (numpy record dtypes) must have the byte size the kernels static_assert
+    for their structs -- a drifted field would shift every pointer behind it."""
+    from deepbedmap_b200 import flat, model
+    csrc = os.path.join(ROOT, "deepbedmap_b200", "csrc")
+    sizes = {}
+    for f in os.listdir(csrc):
+        for name, size in re.findall(r"static_assert\(sizeof\((\w+)\) == (\d+)", open(os.path.join(csrc, f)).read()):
+            sizes[name] = int(size)
+    pairs = {"PackEntry": model.PACK_ENTRY_DTYPE, "TrunkLayer": model.TRUNK_LAYER_DTYPE, "FlatEpiBlock": flat.EPI_DTYPE,
+             "FlatLaunch": flat.LAUNCH_DTYPE, "WgradUnit": flat.WGRAD_UNIT_DTYPE, "WgradReduce": flat.WGRAD_REDUCE_DTYPE,
+             "LocalPass": flat.LOCAL_PASS_DTYPE}
+    assert set(pairs) <= set(sizes), sorted(set(pairs) - set(sizes))
+    for name, dt in pairs.items():
+        assert dt.itemsize == sizes[name], (name, dt.itemsize, sizes[name])
+
+
+def test_image_resident_trunk_applicability():
+    """flat.local_trunk_fits: a padded image must be one M=128 MMA tile (the reference's 11x11 windows are)."""
+    from deepbedmap_b200 import flat
+    assert flat.local_trunk_fits(9, 9) and flat.local_trunk_fits(6, 14) and flat.local_trunk_fits(1, 1)
+    assert not flat.local_trunk_fits(10, 10) and not flat.local_trunk_fits(286, 286)
+    g = flat.geometry_host(128, 9, 9)
+    assert g["P"] == 128 * 121 and g["G0"] >= 12 and g["Pg"] == 2 * g["G0"] + 128 * g["tiles"]
