@@ -3,7 +3,7 @@ discriminator, training step, tiled continent predictor) behind the reference's 
 from ._lib import DeepBedMapError, LIB_PATH  # noqa: F401
 
 __all__ = ["GeneratorModel", "DiscriminatorModel", "compile_srgan_model", "train_eval_discriminator",
-           "train_eval_generator", "trainer", "GraphedTrainStep", "predict_continent", "Adam", "DeepBedMapError"]
+           "train_eval_generator", "trainer", "GraphedTrainStep", "predict_continent", "HostBand", "HostDEM", "Adam", "DeepBedMapError"]
 
 
 def __getattr__(name):  # lazy: importing the package must not require a GPU
@@ -14,7 +14,7 @@ def __getattr__(name):  # lazy: importing the package must not require a GPU
                 "ArrayIterator", "DeviceArrayIterator", "save_model_weights_and_architecture", "GraphedTrainStep"):
         from . import train
         return getattr(train, name)
-    if name in ("predict_continent", "tile_plan", "ContinentGrids"):
+    if name in ("predict_continent", "tile_plan", "ContinentGrids", "HostBand", "HostDEM"):
         from . import tiler
         return getattr(tiler, name)
     raise AttributeError(name)

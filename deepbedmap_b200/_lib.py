@@ -73,6 +73,7 @@ SIGNATURES = {
     "dbm_crop_clip_f32": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "dbm_place_tile_f32": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "dbm_f32_to_i16": [_P, _P, _L, _P],
+    "dbm_copy2d_async": [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P],
     "dbm_gather_rows_f32": [_P, _L, _P, _P, _L, _I, _P],
 }
 

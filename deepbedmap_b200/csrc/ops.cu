@@ -328,6 +328,19 @@ extern "C" int dbm_place_tile_f32(const float* tile, int th, int tw, int cy, int
   place_tile_kernel<<<ew_grid((long)hh * ww), 256, 0, st>>>(tile, th, tw, cy, cx, canvas, ch, cw, ys, xs, hh, ww);
   return check_launch("place_tile");
 }
+extern "C" int dbm_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                                size_t rows, cudaStream_t st) {
+  if (width_bytes == 0 || rows == 0) return DBM_OK;
+  DBM_REQUIRE(dst != nullptr && src != nullptr, "copy2d: null pointer");
+  DBM_REQUIRE(dst_pitch >= width_bytes && src_pitch >= width_bytes, "copy2d: pitch smaller than the row width");
+  if (dst_pitch == width_bytes && src_pitch == width_bytes) {
+    DBM_CUDA(cudaMemcpyAsync(dst, src, width_bytes * rows, cudaMemcpyDefault, st));
+  } else {
+    DBM_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDefault, st));
+  }
+  return DBM_OK;
+}
+
 extern "C" int dbm_fill_f32(float* p, float v, long n, cudaStream_t st) {
   if (n <= 0) return DBM_OK;
   fill_kernel<<<ew_grid(n), 256, 0, st>>>(p, v, n);

@@ -21,11 +21,12 @@ __device__ __forceinline__ float block_sum(float s, float* red) {
 // Writes mean[c], invstd[c] for apply/backward.
 // Per-channel reductions are split over the batch (grid = C x S blocks, S ~ 4 blocks per SM / C): one block per
 // channel left 64-channel layers on 64 of 148 SMs. Partials are double and are combined in a fixed order by the
-// last block of the channel to arrive (deterministic); scratch is a library-owned static buffer, so BN calls must
-// not run concurrently on different streams (the training step issues them on one stream).
-constexpr int kBnMaxC = 1024, kBnMaxSplit = 32;
-__device__ double g_bn_part[kBnMaxC * kBnMaxSplit * 2];
-__device__ unsigned int g_bn_count[kBnMaxC];
+// last block of the channel to arrive (deterministic); scratch is a library-owned static buffer with one slot per
+// stream that has ever issued a BN call (kBnSlots of them), so BN calls on different streams -- a second
+// discriminator, a D pass overlapping another -- never share partials or counters; calls on ONE stream are ordered.
+constexpr int kBnMaxC = 1024, kBnMaxSplit = 32, kBnSlots = 8;
+__device__ double g_bn_part_all[kBnSlots][kBnMaxC * kBnMaxSplit * 2];
+__device__ unsigned int g_bn_count_all[kBnSlots][kBnMaxC];
 
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -38,7 +39,8 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
   return t;
 }
 // returns true in the LAST block of channel c to finish (its view of every partial is complete)
-__device__ __forceinline__ bool bn_publish(int c, int split, int S, double a, double b) {
+__device__ __forceinline__ bool bn_publish(double* g_bn_part, unsigned int* g_bn_count, int c, int split, int S,
+                                           double a, double b) {
   __shared__ bool last;
   if (threadIdx.x == 0) {
     g_bn_part[((size_t)c * kBnMaxSplit + split) * 2] = a;
@@ -54,6 +56,17 @@ __device__ __forceinline__ bool bn_publish(int c, int split, int S, double a, do
   return last;
 }
 
+// scratch slot of a stream (assigned on first use; -1 when more than kBnSlots streams issue BN calls)
+static int bn_slot(cudaStream_t st) {
+  static cudaStream_t owners[kBnSlots];
+  static int used = 0;
+  for (int i = 0; i < used; ++i)
+    if (owners[i] == st) return i;
+  if (used == kBnSlots) return -1;
+  owners[used] = st;
+  return used++;
+}
+
 static int bn_split(int n, int c) {
   int s = (4 * num_sms() + c - 1) / c;
   if (s > n) s = n;
@@ -63,8 +76,10 @@ static int bn_split(int n, int c) {
 
 __global__ void bn_stats_kernel(const float* __restrict__ x, int N, int C, int HW, float eps, float decay, int train,
                                 float* __restrict__ avg_mean, float* __restrict__ avg_var,
-                                float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+                                float* __restrict__ mean_out, float* __restrict__ invstd_out, int slot) {
   __shared__ double red[32];
+  double* g_bn_part = g_bn_part_all[slot];
+  unsigned int* g_bn_count = g_bn_count_all[slot];
   const int c = blockIdx.x, split = blockIdx.y, S = gridDim.y;
   if (!train) {
     if (threadIdx.x == 0 && split == 0) {
@@ -84,7 +99,7 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int N, int C, int H
   }
   s = block_sum_d(s, red);
   q = block_sum_d(q, red);
-  if (!bn_publish(c, split, S, s, q)) return;
+  if (!bn_publish(g_bn_part, g_bn_count, c, split, S, s, q)) return;
   if (threadIdx.x == 0) {
     double ts = 0.0, tq = 0.0;
     for (int k = 0; k < S; ++k) {
@@ -117,8 +132,10 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
                                      const float* __restrict__ dy, int N, int C, int HW,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat) {
+                                     float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat, int slot) {
   __shared__ double red[32];
+  double* g_bn_part = g_bn_part_all[slot];
+  unsigned int* g_bn_count = g_bn_count_all[slot];
   const int c = blockIdx.x, split = blockIdx.y, S = gridDim.y;
   const long n0 = (long)N * split / S, n1 = (long)N * (split + 1) / S;
   const long cnt = (n1 - n0) * HW;
@@ -134,7 +151,7 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
   }
   s1 = block_sum_d(s1, red);
   s2 = block_sum_d(s2, red);
-  if (!bn_publish(c, split, S, s1, s2)) return;
+  if (!bn_publish(g_bn_part, g_bn_count, c, split, S, s1, s2)) return;
   if (threadIdx.x == 0) {
     double t1 = 0.0, t2 = 0.0;
     for (int k = 0; k < S; ++k) {
@@ -368,7 +385,9 @@ extern "C" int dbm_bn_lrelu_fwd_f32(const float* x, float* y, const float* gamma
                                     float eps, float decay, int train, cudaStream_t st) {
   DBM_REQUIRE(n > 0 && c > 0 && hw > 0, "bn: empty input");
   DBM_REQUIRE(c <= kBnMaxC && (long)n * hw < (1L << 31), "bn: %d channels / %d x %d elements exceed the reduction scratch", c, n, hw);
-  bn_stats_kernel<<<dim3(c, train ? bn_split(n, c) : 1), 256, 0, st>>>(x, n, c, hw, eps, decay, train, avg_mean, avg_var, save_mean, save_invstd);
+  const int slot = bn_slot(st);
+  DBM_REQUIRE(slot >= 0, "bn: more than %d streams issue BatchNormalization calls", kBnSlots);
+  bn_stats_kernel<<<dim3(c, train ? bn_split(n, c) : 1), 256, 0, st>>>(x, n, c, hw, eps, decay, train, avg_mean, avg_var, save_mean, save_invstd, slot);
   int rc = check_launch("bn_stats");
   if (rc) return rc;
   const long total = (long)n * c * hw;
@@ -381,8 +400,10 @@ extern "C" int dbm_bn_lrelu_bwd_f32(const float* x, const float* y, const float*
                                     float* scratch2c, int n, int c, int hw, cudaStream_t st) {
   DBM_REQUIRE(n > 0 && c > 0 && hw > 0, "bn_bwd: empty input");
   DBM_REQUIRE(c <= kBnMaxC && (long)n * hw < (1L << 31), "bn_bwd: %d channels / %d x %d elements exceed the reduction scratch", c, n, hw);
+  const int slot = bn_slot(st);
+  DBM_REQUIRE(slot >= 0, "bn_bwd: more than %d streams issue BatchNormalization calls", kBnSlots);
   bn_bwd_reduce_kernel<<<dim3(c, bn_split(n, c)), 256, 0, st>>>(x, y, dy, n, c, hw, save_mean, save_invstd, dgamma, dbeta, scratch2c,
-                                          scratch2c + c);
+                                          scratch2c + c, slot);
   int rc = check_launch("bn_bwd_reduce");
   if (rc) return rc;
   const long total = (long)n * c * hw;

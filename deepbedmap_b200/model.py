@@ -220,10 +220,16 @@ class GeneratorModel(_Link):
         y = self._forward_fp32(x, w1, w2, w3, save=True)
         # lets the generator step pick up the graph the discriminator step built from the same batch
         # (train.train_eval_discriminator(share_generator_forward=True)); the context keeps the inputs alive,
-        # so equal pointers + equal weight version identify the same forward
+        # so equal pointers + equal in-place version counters + equal weight version identify the same forward
         self._ctx["y"] = y
-        self._ctx["key"] = (self.version,) + tuple((t.data_ptr(), tuple(t.shape)) for t in (x, w1, w2, w3))
+        self._ctx["key"] = self._forward_key(x, w1, w2, w3)
         return Variable(y)
+
+    def _forward_key(self, x, w1, w2, w3):
+        """Identity of a forward: weight version + for every input its address, shape and torch's in-place version
+        counter -- an in-place refresh of an input buffer (``copy_``, ``+=`` ...) between the two step functions bumps
+        the counter, so stale activations are never reused for new data."""
+        return (self.version,) + tuple((t.data_ptr(), tuple(t.shape), t._version) for t in (x, w1, w2, w3))
 
     def shared_forward(self, x, w1, w2, w3) -> Optional[torch.Tensor]:
         """Output of a preceding ``forward_train`` on exactly these device tensors with the current weights
@@ -231,8 +237,7 @@ class GeneratorModel(_Link):
         c = self._ctx
         if c is None or "key" not in c or not all(isinstance(t, torch.Tensor) and t.is_cuda for t in (x, w1, w2, w3)):
             return None
-        key = (self.version,) + tuple((t.data_ptr(), tuple(t.shape)) for t in (x, w1, w2, w3))
-        return c["y"] if key == c["key"] else None
+        return c["y"] if self._forward_key(x, w1, w2, w3) == c["key"] else None
 
     @staticmethod
     def _check_shapes(x, w1, w2, w3):
@@ -367,8 +372,9 @@ class GeneratorModel(_Link):
         """Accumulates d(loss)/d(params) into ``flat_grad`` given d(loss)/d(output) (N,1,4H,4W);
         replaces g_loss.backward() for the generator (srgan_train.py:1256). No gradient wrt the
         inputs is produced (no caller needs it). ``on_ready(lo, hi)`` is called as soon as the
-        gradients of flat_grad[lo:hi] are final (head, then each RRDB from last to first, then the
-        stem), so a data-parallel caller can all-reduce that bucket while the rest of backward runs."""
+        gradients of flat_grad[lo:hi] are final, on the stream that produced them, so a data-parallel caller can
+        all-reduce that bucket while the rest of backward runs: tensor-core path = three buckets (head, whole trunk,
+        stem; see below), fp32 path = head, then each RRDB from last to first, then the stem."""
         if self._ctx is None:
             raise RuntimeError("backward() needs a preceding forward_train()")
         ready = (lambda *pre: on_ready(*self.grad_range(pre))) if on_ready is not None else (lambda *pre: None)
@@ -428,17 +434,22 @@ class GeneratorModel(_Link):
         da3 = ops.upsample2_bwd(du1)  # = d a1 (skip) = d (post-res conv output)
         del du1, dc1
         if "flat" in c:
-            # tensor-core trunk: data-gradient chain, batched weight/bias gradients (flat.py)
-            # The trunk's weight / bias gradients (one batched launch + reduction) only feed the optimizer: they run on
-            # a side stream beside the stem's backward and are joined before any gradient bucket is handed on.
+            # tensor-core trunk: data-gradient chain, batched weight/bias gradients (flat.py).
+            # Three gradient buckets, each handed on the moment it is final so that a data-parallel caller's
+            # all-reduce (GradBucketReducer: the comm stream waits for the stream current at the hand-over) runs
+            # under what is still to come:
+            #   head  (upsample + deformable layers): final here, reduced under the whole trunk backward;
+            #   trunk (pre-residual conv .. post-residual conv): one batched launch + reduction on the side stream
+            #         ``aux`` beside the stem's backward, handed over ON that stream;
+            #   stem  (input_block): after the stem's weight gradients on the main stream.
+            ready("post_upsample_conv_layer", "final_conv_layer")
             cur, aux = torch.cuda.current_stream(), ops._aux_stream()
             da0 = c["flat"].backward(da3, wgrad_stream=aux)
+            with torch.cuda.stream(aux):
+                ready("pre_residual_conv_layer", "residual_network/", "post_residual_conv_layer")
             self._stem_bwd(c, da0, lambda *pre: None)
+            ready("input_block/")
             cur.wait_stream(aux)
-            ready("post_residual_conv_layer", "post_upsample_conv_layer", "final_conv_layer")
-            for i in reversed(range(self.num_residual_blocks)):
-                ready(f"residual_network/{i}/")
-            ready("input_block/", "pre_residual_conv_layer")
             return
         # ---- post-residual conv ----
         cats = c["cats"]
@@ -879,8 +890,8 @@ class DiscriminatorModel(_Link):
                          P[f"batch_norm{i}/beta"].data_ptr(), self.persistent[f"batch_norm{i}/avg_mean"].data_ptr(),
                          self.persistent[f"batch_norm{i}/avg_var"].data_ptr(), mean[gi].data_ptr(),
                          invstd[gi].data_ptr(), ng, cout, ho * ho, self.BN_EPS, self.BN_DECAY, int(train), ops.stream())
-            if train:
-                self.bn_N[i] += groups
+            # batch_norm{i}/N: Chainer increments it in finetune mode only, which the reference never enters
+            # (srgan_train.py:1125, 1228 toggle `train` alone) -> the loaded value (0 by default) is kept as is
             pres.append(z)
             stats.append((mean, invstd))
             acts.append(y)

@@ -55,6 +55,124 @@ def rank_row_band(plan, rank: int, world: int) -> Tuple[int, int]:
     return min(t[0] for t in plan[a:b]), max(t[1] for t in plan[a:b])
 
 
+def output_segments(plan, a: int, b: int, final_shape, tiles_x: int):
+    """Host-DEM rectangles owned by the contiguous tile run [a, b): one (ys, ye, xs, xe) per tile row the run
+    touches, covering the canvas windows of the run's tiles in that row and extended to the canvas border where the
+    run holds the row's first / last tile (columns) or the first / last tile row (rows), so that the NaN frame the
+    reference leaves around its product (deepbedmap.py:696, 731-736) travels with the data. Over all ranks the
+    rectangles partition the canvas exactly (asserted by tests/test_dist_cpu.py) provided the tile windows abut,
+    i.e. stride == ary_shape as in the reference (checked by ``windows_abut``)."""
+    n_rows = len(plan) // tiles_x
+    segs = []
+    i = a
+    while i < b:
+        ty = i // tiles_x
+        j = min(b, (ty + 1) * tiles_x)
+        ys, ye = plan[i][4], plan[i][5]
+        xs, xe = plan[i][6], plan[j - 1][7]
+        if i % tiles_x == 0:
+            xs = 0
+        if j % tiles_x == 0:
+            xe = final_shape[1]
+        if ty == 0:
+            ys = 0
+        if ty == n_rows - 1:
+            ye = final_shape[0]
+        segs.append((ys, ye, xs, xe, i, j))
+        i = j
+    return segs
+
+
+def windows_abut(plan, tiles_x: int) -> bool:
+    """True when consecutive tiles' canvas windows touch without gap or overlap in both directions."""
+    n_rows = len(plan) // tiles_x
+    for ty in range(n_rows):
+        for tx in range(tiles_x):
+            t = plan[ty * tiles_x + tx]
+            if tx + 1 < tiles_x and plan[ty * tiles_x + tx + 1][6] != t[7]:
+                return False
+            if ty + 1 < n_rows and plan[(ty + 1) * tiles_x + tx][4] != t[5]:
+                return False
+            if t[4] != plan[ty * tiles_x][4] or t[5] != plan[ty * tiles_x][5]:
+                return False
+    return True
+
+
+class HostBand:
+    """Host copies of the lowres rows [row0, row0 + X.shape[2]) of the four continent grids (X (1,1,h,W), W1
+    (1,1,10h,10W), W2 (1,2,2h,2W), W3 (1,1,h,W)) of a grid with ``full_rows`` lowres rows: what a rank of a
+    multi-GPU run keeps (and pins) on the host instead of the whole 10.9 GB continent -- ``rank_row_band`` says which
+    rows its tiles read."""
+
+    def __init__(self, X, W1, W2, W3, row0: int = 0, full_rows: Optional[int] = None):
+        self.arrays = (X, W1, W2, W3)
+        self.row0 = int(row0)
+        self.full_rows = int(full_rows) if full_rows is not None else int(X.shape[2]) + self.row0
+        h = X.shape[2]
+        if tuple(W1.shape[2:]) != (10 * h, 10 * X.shape[3]) or W2.shape[2] != 2 * h or W3.shape[2] != h:
+            raise ValueError("W1/W2/W3 must be 10x/2x/1x the BEDMAP2 band")
+
+
+class HostDEM:
+    """Pinned host output grid (1, final_y, final_x) that every rank of a run can write: one process -> a pinned
+    torch tensor; torch.distributed initialised -> POSIX shared memory created by rank 0, mapped by every rank and
+    registered with the CUDA driver (cudaHostRegister), so each GPU copies its finished tile rows straight into the
+    final DEM over its own PCIe link (no gather, no re-placement on rank 0). ``array`` is the NumPy view."""
+
+    def __init__(self, final_shape, dtype: str = "float32"):
+        self.dtype = {"float32": torch.float32, "int16": torch.int16}[dtype]
+        self.shape = (1, int(final_shape[0]), int(final_shape[1]))
+        dist, rank, world = _dist()
+        self._shm = None
+        self._registered = False
+        nbytes = self.shape[1] * self.shape[2] * (4 if dtype == "float32" else 2)
+        if world == 1:
+            self.tensor = torch.empty(self.shape, dtype=self.dtype, pin_memory=torch.cuda.is_available())
+        else:
+            from multiprocessing import resource_tracker, shared_memory
+            name = [None]
+            if rank == 0:
+                self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+                name = [self._shm.name]
+            dist.broadcast_object_list(name, src=0)
+            if rank != 0:
+                self._shm = shared_memory.SharedMemory(name=name[0])
+                try:   # Python < 3.13 registers attachments too and would unlink at this process's exit
+                    resource_tracker.unregister(self._shm._name, "shared_memory")
+                except Exception:
+                    pass
+            np_dtype = np.float32 if dtype == "float32" else np.int16
+            arr = np.ndarray(self.shape, dtype=np_dtype, buffer=self._shm.buf)
+            self.tensor = torch.from_numpy(arr)
+            if torch.cuda.is_available():
+                rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0)
+                if int(rc) != 0:
+                    raise RuntimeError(f"cudaHostRegister of the shared host DEM failed ({rc})")
+                self._registered = True
+            dist.barrier()
+        self.owner = rank == 0
+        self.array = self.tensor.numpy()
+
+    def close(self):
+        dist, rank, world = _dist()
+        if self._registered:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self._registered = False
+        if self._shm is not None:
+            if dist is not None:
+                dist.barrier()
+            self.array = None
+            self.tensor = None
+            try:
+                self._shm.close()
+            except BufferError:
+                pass
+            if self.owner:
+                self._shm.unlink()
+            self._shm = None
+
+
 def group_by_shape(indexed_tiles):
     groups: "OrderedDict[Tuple[int, int], List]" = OrderedDict()
     for i, t in indexed_tiles:
@@ -128,11 +246,15 @@ class StreamedGrids(ContinentGrids):
     """Host grids uploaded band by band on a side stream while earlier tile rows are computing
     (the host->device copy of the 10.9 GB continent overlaps the generator)."""
 
-    def __init__(self, X, W1, W2, W3, rows: Optional[Tuple[int, int]] = None):
+    def __init__(self, X, W1, W2, W3, rows: Optional[Tuple[int, int]] = None, host_row0: int = 0):
+        """``host_row0``: lowres row of the full grid that row 0 of the HOST arrays corresponds to (a HostBand)."""
         from . import ops
         Hs, Ws = _check_grids(X, W1, W2, W3)
-        r0, r1 = rows if rows is not None else (0, Hs)
+        r0, r1 = rows if rows is not None else (host_row0, host_row0 + Hs)
+        if r0 < host_row0 or r1 > host_row0 + Hs:
+            raise ValueError(f"host band rows [{host_row0}, {host_row0 + Hs}) do not cover the needed rows [{r0}, {r1})")
         self.row0 = r0
+        self._host_row0 = host_row0
         nr = r1 - r0
         to_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a, dtype=np.float32))
         self._host = [to_t(a) for a in (X, W1, W2, W3)]
@@ -155,7 +277,7 @@ class StreamedGrids(ContinentGrids):
             with torch.cuda.stream(self._stream):
                 for host, dev, sc in zip(self._host, self._dev, self._scale):
                     a, b = sc * self._done, sc * upto
-                    ha = sc * self.row0
+                    ha = sc * (self.row0 - self._host_row0)
                     for c in range(dev.shape[1]):
                         dev[0, c, a:b].copy_(host[0, c, ha + a:ha + b], non_blocking=True)
                 self._events.append((upto, self._stream.record_event()))
@@ -174,14 +296,16 @@ class StreamedGrids(ContinentGrids):
             self._enqueue(prefetch_upto)
 
 
-def predict_continent(model, X, W1, W2, W3, final_shape=(18000, 22000), ary_shape=(1000, 1000),
+def predict_continent(model, X, W1=None, W2=None, W3=None, final_shape=(18000, 22000), ary_shape=(1000, 1000),
                       stride=(1000, 1000), xtrapad=(18, 18), batch_tiles: int = 4, to_host: bool = True,
-                      grids: Optional[ContinentGrids] = None, out: Optional[torch.Tensor] = None,
-                      out_dtype: str = "float32"):
+                      grids: Optional[ContinentGrids] = None, out=None, out_dtype: str = "float32"):
     """Returns Y_hat (1, final_y, final_x) float32 (NumPy if ``to_host`` else a CUDA tensor), NaN
     where the reference leaves NaN. On ranks != 0 of a distributed run returns None.
-    ``out``: optional pinned host tensor (1, final_y, final_x) to receive the result without a
-    pageable staging copy.
+    ``X`` may be a ``HostBand`` (then W1..W3 are omitted): the rows of the host grids this rank reads.
+    ``out``: optional pinned host tensor (1, final_y, final_x) to receive the result without a pageable staging
+    copy, or a ``HostDEM``: then every rank copies each finished tile row of its device canvas straight into that
+    (shared, pinned) host grid on a copy stream while the next tiles compute, and the run ends with a barrier instead
+    of a gather + re-placement + one 1.58 GB read-back on rank 0.
     ``out_dtype="int16"`` returns ``Y_hat.astype(np.int16)`` -- what the reference writes to the GeoTIFF
     (deepbedmap.py:751) -- converted on the device, which halves the device->host read."""
     if out_dtype not in ("float32", "int16"):
@@ -189,11 +313,18 @@ def predict_continent(model, X, W1, W2, W3, final_shape=(18000, 22000), ary_shap
     from . import ops
     dist, rank, world = _dist()
     plan = tile_plan(final_shape, ary_shape, stride, xtrapad)
+    tiles_x = len(range(0, final_shape[1], stride[1]))
     a, b = rank_tile_range(len(plan), rank, world)
     if grids is None:
         band = rank_row_band(plan, rank, world) if world > 1 else None
-        on_device = all(isinstance(t, torch.Tensor) and t.is_cuda for t in (X, W1, W2, W3))
-        grids = (ContinentGrids if on_device else StreamedGrids)(X, W1, W2, W3, rows=band)
+        if isinstance(X, HostBand):
+            hb = X
+            if band is None:
+                band = (hb.row0, hb.row0 + hb.arrays[0].shape[2])
+            grids = StreamedGrids(*hb.arrays, rows=band, host_row0=hb.row0)
+        else:
+            on_device = all(isinstance(t, torch.Tensor) and t.is_cuda for t in (X, W1, W2, W3))
+            grids = (ContinentGrids if on_device else StreamedGrids)(X, W1, W2, W3, rows=band)
     g = grids
     Hs, Ws = g.X.shape[2], g.X.shape[3]
     r0, r1 = g.rows
@@ -203,20 +334,37 @@ def predict_continent(model, X, W1, W2, W3, final_shape=(18000, 22000), ary_shap
     # tile rows in order (so a streamed upload can stay just ahead), same-shape tiles batched
     rows_of_tiles: "OrderedDict[int, List]" = OrderedDict()
     for i in range(a, b):
-        rows_of_tiles.setdefault(plan[i][0], []).append((i, plan[i]))
+        rows_of_tiles.setdefault(i // tiles_x, []).append((i, plan[i]))
     py, px = xtrapad[0] * 4, xtrapad[1] * 4
-    single = world == 1
     st = ops.stream
-    if single:
+    stream_out = isinstance(out, HostDEM)
+    if stream_out:
+        if not to_host or tuple(out.shape) != (1, final_shape[0], final_shape[1]):
+            raise ValueError("HostDEM output needs to_host=True and a DEM of shape (1, final_y, final_x)")
+        if out.dtype != (torch.int16 if out_dtype == "int16" else torch.float32):
+            raise ValueError(f"HostDEM dtype does not match out_dtype={out_dtype}")
+        if not windows_abut(plan, tiles_x):
+            raise ValueError("a HostDEM needs abutting tile windows (stride == ary_shape, as in the reference)")
+        segs = {sg[4] // tiles_x: sg for sg in output_segments(plan, a, b, final_shape, tiles_x)}
+        # local canvas: the rows this rank's segments span, full width, NaN where no tile is placed
+        row_lo = min(sg[0] for sg in segs.values()) if segs else 0
+        row_hi = max(sg[1] for sg in segs.values()) if segs else 0
+        canvas = ops.empty(max(row_hi - row_lo, 1), final_shape[1])
+        ops.fill(canvas, float("nan"))
+        canvas16 = torch.empty(canvas.shape, dtype=torch.int16, device="cuda") if out_dtype == "int16" else None
+        copy_stream = _copy_stream()
+        results = None
+    elif world == 1:
+        row_lo = 0
         canvas = ops.empty(final_shape[0], final_shape[1])
         ops.fill(canvas, float("nan"))
         results = None
     else:
         results = ops.empty(max_tiles_per_rank(len(plan), world), ary_shape[0], ary_shape[1])
         ops.fill(results, float("nan"))
-    row_list = list(rows_of_tiles.values())
-    for k, row_tiles in enumerate(row_list):
-        nxt = max(t[1] for _, t in row_list[k + 1]) if k + 1 < len(row_list) else None
+    row_list = list(rows_of_tiles.items())
+    for k, (ty, row_tiles) in enumerate(row_list):
+        nxt = max(t[1] for _, t in row_list[k + 1][1]) if k + 1 < len(row_list) else None
         g.ensure_rows(max(t[1] for _, t in row_tiles), prefetch_upto=nxt)
         for (h, w), tiles in group_by_shape(row_tiles).items():
             for b0 in range(0, len(tiles), batch_tiles):
@@ -242,14 +390,33 @@ def predict_continent(model, X, W1, W2, W3, final_shape=(18000, 22000), ary_shap
                     # ValueError on a shape mismatch (deepbedmap.py:734-738)
                     if (th - 2 * py, tw - 2 * px) != (hh, ww):
                         raise ValueError(f"could not broadcast tile {(th - 2 * py, tw - 2 * px)} into {(hh, ww)}")
-                    if single:
+                    if results is None:
                         ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, canvas.data_ptr(),
-                                 final_shape[0], final_shape[1], ys, xs, hh, ww, st())
+                                 canvas.shape[0], final_shape[1], ys - row_lo, xs, hh, ww, st())
                     else:
                         ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, results[i - a].data_ptr(),
                                  ary_shape[0], ary_shape[1], 0, 0, hh, ww, st())
                 del y, xb, w1b, w2b, w3b
-    if not single:
+        if stream_out:
+            # this tile row of the local canvas is final: hand its rectangle to the copy stream
+            ys, ye, xs, xe, _, _ = segs[ty]
+            src, esz = canvas, 4
+            if canvas16 is not None:
+                o = (ys - row_lo) * final_shape[1]
+                ops.call("dbm_f32_to_i16", canvas.data_ptr() + 4 * o, canvas16.data_ptr() + 2 * o,
+                         (ye - ys) * final_shape[1], st())
+                src, esz = canvas16, 2
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            pitch = final_shape[1] * esz
+            ops.call("dbm_copy2d_async", out.tensor.data_ptr() + ys * pitch + xs * esz, pitch,
+                     src.data_ptr() + (ys - row_lo) * pitch + xs * esz, pitch, (xe - xs) * esz, ye - ys,
+                     copy_stream.cuda_stream)
+    if stream_out:
+        copy_stream.synchronize()
+        if dist is not None:
+            dist.barrier()
+        return out.array if rank == 0 else None
+    if world > 1:
         def new_canvas():
             c = ops.empty(final_shape[0], final_shape[1])
             ops.fill(c, float("nan"))
@@ -276,3 +443,13 @@ def predict_continent(model, X, W1, W2, W3, final_shape=(18000, 22000), ary_shap
         torch.cuda.current_stream().synchronize()
         return out.numpy()
     return res.cpu().numpy()
+
+
+_COPY_STREAM = None
+
+
+def _copy_stream():
+    global _COPY_STREAM
+    if _COPY_STREAM is None:
+        _COPY_STREAM = torch.cuda.Stream()
+    return _COPY_STREAM

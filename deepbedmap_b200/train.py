@@ -78,6 +78,8 @@ class Adam:
         self.m.copy_(torch.from_numpy(m))
         self.v.copy_(torch.from_numpy(v))
         self.t = int(state["t"])
+        if self.t_dev is not None:   # CUDA-graph replays read the step count from the device
+            self.t_dev.fill_(self.t)
 
     def save_npz(self, file, compression: bool = True) -> None:
         (np.savez_compressed if compression else np.savez)(file, **self.state_dict())
@@ -443,8 +445,12 @@ class GraphedTrainStep:
         if input_arrays is not None:
             for k, dst in self.arrays.items():
                 src = input_arrays[k]
-                if src is not dst:
-                    dst.copy_(as_device(src), non_blocking=True)
+                if src is dst:
+                    continue
+                if isinstance(src, np.ndarray):
+                    src = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32))
+                # host tensors (pinned: asynchronous) go straight into the graph's static input buffers
+                dst.copy_(src.array if isinstance(src, Variable) else src, non_blocking=True)
         self.graph.replay()
         for link, opt in ((self.g, self.g_opt), (self.d, self.d_opt)):
             opt.t += 1
@@ -456,8 +462,9 @@ class GraphedTrainStep:
 
 
 class ArrayIterator:
-    """Minimal SerialIterator stand-in (chainer.iterators.SerialIterator as used at
-    srgan_train.py:132-166): batches a dict of equally long arrays, counts epochs."""
+    """Minimal SerialIterator stand-in (chainer.iterators.SerialIterator(repeat=True, shuffle=True) as used at
+    srgan_train.py:132-166): batches a dict of equally long arrays, counts epochs; batches are always full (the last
+    one of an epoch is completed from the next epoch's order, as Chainer does)."""
 
     def __init__(self, arrays: Dict[str, np.ndarray], batch_size: int, shuffle: bool = True, seed: int = 42):
         self.arrays = arrays
@@ -472,13 +479,22 @@ class ArrayIterator:
     def _new_order(self):
         return self.rng.permutation(self.n) if self.shuffle else np.arange(self.n)
 
-    def next(self):
+    def _next_indices(self):
+        """chainer SerialIterator(repeat=True): a batch that reaches the end of the epoch is completed from the head
+        of the next epoch's (freshly drawn) order, so every batch is full; the epoch counter advances there."""
         idx = self._order[self._pos:self._pos + self.batch_size]
         self._pos += self.batch_size
         if self._pos >= self.n:
+            rest = self._pos - self.n
             self.epoch += 1
-            self._pos = 0
             self._order = self._new_order()
+            if rest > 0:
+                idx = np.concatenate([idx, self._order[:rest]])
+            self._pos = rest
+        return idx
+
+    def next(self):
+        idx = self._next_indices()
         return {k: v[idx] for k, v in self.arrays.items()}
 
 
@@ -504,11 +520,12 @@ class DeviceArrayIterator:
         self._order = self._new_order()
 
     def _new_order(self):
-        order = self.rng.permutation(self.n) if self.shuffle else np.arange(self.n)
-        return torch.from_numpy(order.astype(np.int64)).cuda()   # one small upload per epoch
+        return self.rng.permutation(self.n) if self.shuffle else np.arange(self.n)
+
+    _next_indices = ArrayIterator._next_indices
 
     def next(self):
-        idx = self._order[self._pos:self._pos + self.batch_size]
+        idx = torch.from_numpy(np.ascontiguousarray(self._next_indices(), dtype=np.int64)).cuda()   # batch_size int64
         nb = int(idx.numel())
         out = {}
         for k, v in self.arrays.items():
@@ -516,11 +533,6 @@ class DeviceArrayIterator:
             dst = ops.empty(nb, *v.shape[1:])
             ops.call("dbm_gather_rows_f32", v.data_ptr(), self.n, idx.data_ptr(), dst.data_ptr(), row, nb, ops.stream())
             out[k] = dst
-        self._pos += self.batch_size
-        if self._pos >= self.n:
-            self.epoch += 1
-            self._pos = 0
-            self._order = self._new_order()
         return out
 
 

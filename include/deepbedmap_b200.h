@@ -280,6 +280,13 @@ int dbm_place_tile_f32(const float* tile, int th, int tw, int cy, int cx, float*
  * (truncate toward zero to int32, NaN / out-of-range -> INT_MIN, keep the low 16 bits: NaN -> 0). */
 int dbm_f32_to_i16(const float* src, void* dst_i16, long n, cudaStream_t stream);
 
+/* Strided 2-D copy (cudaMemcpy2DAsync, kind inferred from the pointers): `rows` rows of `width_bytes`, pitches in
+ * bytes. The tiler streams every finished tile row of its device canvas into the caller's pinned (or
+ * cudaHostRegister-ed shared) host DEM with it while later tiles compute (Y_hat[:, y_slice, x_slice] = ...,
+ * deepbedmap.py:733-736). dst / src may be host or device pointers. */
+int dbm_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                     cudaStream_t stream);
+
 /* ---- on-device minibatch assembly (chainer SerialIterator + concat_examples, srgan_train.py:132-166):
  * dst[j, :] = src[index[j], :] for j < nrows; rows of `row` floats; index = int64 on the device. */
 int dbm_gather_rows_f32(const float* src, long src_rows, const long* index_dev, float* dst, long row, int nrows,

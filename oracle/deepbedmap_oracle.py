@@ -264,6 +264,42 @@ def deformable_conv2d(x, offset, W, b, quantize=None):
     return y + b.view(1, O, 1, 1)
 
 
+def deformable_conv2d_fast(x, offset, W, b):
+    """Same function as ``deformable_conv2d`` (forward only, no autograd use), arranged for speed: used where the
+    oracle is TIMED (bench.py's CPU baseline) and for full-size 288x288 tiles, where the form above would
+    materialise four (N, C, 9, H, W) gathers. Pixels are rows of a channels-last matrix (one extra all-zero row
+    stands for "outside the padded image"), each tap gathers its four bilinear corners with ``index_select`` and is
+    contracted by one GEMM. Same coordinate arithmetic (no [-1, 1] normalisation), so it agrees with the form
+    above to rounding; equality of the two and of torchvision's deform_conv2d is asserted in
+    tests/test_oracle_kat.py."""
+    N, C, H, Wd = x.shape
+    Oc = W.shape[0]
+    dt = x.dtype
+    ys = torch.arange(H, dtype=dt).view(H, 1)
+    xs = torch.arange(Wd, dtype=dt).view(1, Wd)
+    out = []
+    for n in range(N):
+        rows = torch.cat([x[n].permute(1, 2, 0).reshape(H * Wd, C), torch.zeros(1, C, dtype=dt)], 0)
+        acc = torch.zeros(H * Wd, Oc, dtype=dt)
+        for t in range(9):
+            ky, kx = divmod(t, 3)
+            px = (xs + (kx - 1.0) + offset[n, t]).clamp(-2.0, Wd + 1.0)
+            py = (ys + (ky - 1.0) + offset[n, 9 + t]).clamp(-2.0, H + 1.0)
+            x0, y0 = torch.floor(px), torch.floor(py)
+            fx, fy = (px - x0).reshape(-1, 1), (py - y0).reshape(-1, 1)
+            x0, y0 = x0.long(), y0.long()
+
+            def corner(yi, xi):
+                ok = (yi >= 0) & (yi < H) & (xi >= 0) & (xi < Wd)
+                return rows.index_select(0, torch.where(ok, yi * Wd + xi, torch.full_like(yi, H * Wd)).reshape(-1))
+
+            smp = (corner(y0, x0) * ((1 - fy) * (1 - fx)) + corner(y0, x0 + 1) * ((1 - fy) * fx)
+                   + corner(y0 + 1, x0) * (fy * (1 - fx)) + corner(y0 + 1, x0 + 1) * (fy * fx))
+            acc.addmm_(smp, W[:, :, ky, kx].t())
+        out.append(acc.t().reshape(Oc, H, Wd))
+    return torch.stack(out) + b.view(1, Oc, 1, 1)
+
+
 def deformable_layer(p: Params, name: str, x):
     """L.DeformableConvolution2D = offset_conv (64->18, k3 p1, bias) + sampler."""
     off = F.conv2d(x, p[f"{name}/offset_conv/W"], p[f"{name}/offset_conv/b"], padding=1)
@@ -276,7 +312,7 @@ def _q(t):
 
 
 def generator_forward(p: Params, x, w1, w2, w3, num_residual_blocks=12,
-                      residual_scaling=0.1, return_intermediates=False, emulate_bf16=False):
+                      residual_scaling=0.1, return_intermediates=False, emulate_bf16=False, fast_deform=False):
     """GeneratorModel.forward, srgan_train.py:525-576.
 
     ``emulate_bf16=True`` restates the SAME graph with the operand rounding of the product's
@@ -289,7 +325,7 @@ def generator_forward(p: Params, x, w1, w2, w3, num_residual_blocks=12,
     """
     if not emulate_bf16:
         return _generator_forward_exact(p, x, w1, w2, w3, num_residual_blocks, residual_scaling,
-                                        return_intermediates)
+                                        return_intermediates, fast_deform=fast_deform)
     beta = residual_scaling
     q = _q
 
@@ -359,7 +395,7 @@ def trunk_forward(p: Params, a0, num_residual_blocks=12, residual_scaling=0.1, e
 
 
 def _generator_forward_exact(p: Params, x, w1, w2, w3, num_residual_blocks=12,
-                             residual_scaling=0.1, return_intermediates=False, trunk_bf16=False):
+                             residual_scaling=0.1, return_intermediates=False, trunk_bf16=False, fast_deform=False):
     """GeneratorModel.forward, srgan_train.py:525-576. ``trunk_bf16``: the trunk with the operand rounding
     of the product's tensor-core training path (see trunk_forward), everything else exact."""
     inter = {}
@@ -383,8 +419,8 @@ def _generator_forward_exact(p: Params, x, w1, w2, w3, num_residual_blocks=12,
         return F.conv2d(q(x_), q(p[f"{name}/W"]), p[f"{name}/b"], padding=1)
 
     def deform(x_, name):
-        return deformable_conv2d(x_, conv(x_, f"{name}/offset_conv"), p[f"{name}/deform_conv/W"],
-                                 p[f"{name}/deform_conv/b"])
+        fn = deformable_conv2d_fast if fast_deform else deformable_conv2d
+        return fn(x_, conv(x_, f"{name}/offset_conv"), p[f"{name}/deform_conv/W"], p[f"{name}/deform_conv/b"])
 
     a4_1 = _lrelu(conv(upsample_nearest2(a3), "post_upsample_conv_layer_1"))    # :556-560
     a4_2 = _lrelu(conv(upsample_nearest2(a4_1), "post_upsample_conv_layer_2"))  # :562-568
@@ -669,16 +705,40 @@ def predict_continent(forward: Callable, X, W1, W2, W3, final_shape=(18000, 2200
     return Y_hat
 
 
+def synthetic_continent(grid=(4502, 5502), seed: int = 42):
+    """SURVEY 8(d) config 3 inputs on the host, physical regime: X (1,1,H,W) BEDMAP2-like metres,
+    W1 (1,1,10H,10W) REMA-like metres, W2 (1,2,2H,2W) velocities (signed: the tiler's clip matters),
+    W3 (1,1,H,W). NumPy RandomState, so the same values on every machine."""
+    H, W = grid
+    rng = np.random.RandomState(seed)
+    X = np.clip(rng.normal(-500.0, 800.0, (1, 1, H, W)), -5000.0, 4500.0)
+    W1 = rng.uniform(0.0, 4000.0, (1, 1, 10 * H, 10 * W))
+    W2 = rng.normal(0.0, 200.0, (1, 2, 2 * H, 2 * W))
+    W3 = rng.uniform(-50.0, 1000.0, (1, 1, H, W))
+    return tuple(a.astype(np.float32) for a in (X, W1, W2, W3))
+
+
+def continent_tile_inputs(X, W1, W2, W3, tile):
+    """The four crops the reference feeds the generator for one tile of ``tile_plan`` (deepbedmap.py:715-722),
+    W1..W3 clipped at zero as the reference does for the whole arrays beforehand (deepbedmap.py:663-665)."""
+    y0, y1, x0, x1 = tile[:4]
+    return (np.ascontiguousarray(X[:, :, y0:y1, x0:x1], dtype=np.float32),
+            np.clip(W1[:, :, y0 * 10:y1 * 10, x0 * 10:x1 * 10], 0, None).astype(np.float32),
+            np.clip(W2[:, :, y0 * 2:y1 * 2, x0 * 2:x1 * 2], 0, None).astype(np.float32),
+            np.clip(W3[:, :, y0:y1, x0:x1], 0, None).astype(np.float32))
+
+
 # --------------------------------------------------------------------------------------
 # Convenience wrappers used by tests / bench
 # --------------------------------------------------------------------------------------
 def generator_forward_numpy(params_np, x, w1, w2, w3, num_residual_blocks=12,
-                            residual_scaling=0.1, dtype=torch.float64, emulate_bf16=False) -> np.ndarray:
+                            residual_scaling=0.1, dtype=torch.float64, emulate_bf16=False,
+                            fast_deform=False) -> np.ndarray:
     p = to_torch(params_np, dtype)
     with torch.no_grad():
         y = generator_forward(p, *(torch.as_tensor(np.asarray(a)).to(dtype) for a in (x, w1, w2, w3)),
                               num_residual_blocks=num_residual_blocks,
-                              residual_scaling=residual_scaling, emulate_bf16=emulate_bf16)
+                              residual_scaling=residual_scaling, emulate_bf16=emulate_bf16, fast_deform=fast_deform)
     return y.numpy()
 
 

@@ -33,6 +33,30 @@ def test_rank_tile_ranges_partition_the_plan():
     assert max(b - a for a, b in bands) < 4500 // 2
 
 
+def test_output_segments_partition_the_canvas():
+    """Streaming host output: over all ranks, the rectangles each rank copies into the shared host DEM cover every
+    canvas pixel exactly once (tile windows + the NaN frame), for the reference geometry and a small ragged one."""
+    from deepbedmap_b200.tiler import output_segments, rank_tile_range, tile_plan, windows_abut
+    for final, ary, pad in (((18000, 22000), (1000, 1000), (18, 18)), ((120, 200), (40, 40), (3, 3))):
+        plan = tile_plan(final, ary, ary, pad)
+        tiles_x = final[1] // ary[1]
+        assert windows_abut(plan, tiles_x)
+        for world in (1, 2, 3, 5, 8):
+            cover = np.zeros((final[0] // 4, final[1] // 4), np.int32)   # all windows are multiples of 4 px
+            for r in range(world):
+                a, b = rank_tile_range(len(plan), r, world)
+                for ys, ye, xs, xe, i, j in output_segments(plan, a, b, final, tiles_x):
+                    assert a <= i < j <= b and i // tiles_x == (j - 1) // tiles_x
+                    assert ys % 4 == 0 and ye % 4 == 0 and xs % 4 == 0 and xe % 4 == 0
+                    # the segment contains the windows of its own tiles
+                    for t in plan[i:j]:
+                        assert ys <= t[4] and t[5] <= ye and xs <= t[6] and t[7] <= xe
+                    cover[ys // 4:ye // 4, xs // 4:xe // 4] += 1
+            assert cover.min() == 1 and cover.max() == 1, (final, world)
+    # overlapping windows (stride < ary_shape) are refused by the streaming path
+    assert not windows_abut(tile_plan((120, 200), (40, 40), (20, 20), (3, 3)), len(range(0, 200, 20)))
+
+
 def _fake_tile(i, hh, ww):
     yy, xx = np.meshgrid(np.arange(hh), np.arange(ww), indexing="ij")
     return (i * 1000.0 + yy * 0.5 + xx * 0.25).astype(np.float32)
@@ -63,6 +87,20 @@ def _worker(rank, world, port, q):
             q.put(("tiler", bool(np.array_equal(canvas.numpy(), ref, equal_nan=True))))
         else:
             assert canvas is None
+
+        # shared host DEM: every rank writes its own segments; rank 0 reads the assembled grid
+        dem = tiler.HostDEM(final)
+        segs = tiler.output_segments(plan, a, b, final, final[1] // ary[1])
+        local = np.full(final, np.nan, np.float32)
+        for i in range(a, b):
+            _, _, _, _, ys, ye, xs, xe = plan[i]
+            local[ys:ye, xs:xe] = _fake_tile(i, ye - ys, xe - xs)
+        for ys, ye, xs, xe, _, _ in segs:
+            dem.array[0, ys:ye, xs:xe] = local[ys:ye, xs:xe]
+        dist.barrier()
+        if rank == 0:
+            q.put(("hostdem", bool(np.array_equal(dem.array[0], ref, equal_nan=True))))
+        dem.close()
 
         class Link:  # only what allreduce_grads touches
             flat_grad = torch.arange(10, dtype=torch.float32) * (rank + 1)
@@ -101,8 +139,8 @@ def test_two_rank_gather_and_allreduce_gloo():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    got = dict(q.get(timeout=10) for _ in range(2))
-    assert got == {"tiler": True, "allreduce": True}
+    got = dict(q.get(timeout=10) for _ in range(3))
+    assert got == {"tiler": True, "hostdem": True, "allreduce": True}
 
 
 def test_single_process_defaults():

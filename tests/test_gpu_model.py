@@ -387,8 +387,9 @@ def test_graphed_train_step_matches_eager():
 
 def test_trainer_epoch_eager_and_graphed_is_nan_free():
     """An epoch of trainer() (srgan_train.py:1267-1329) on a tiny dataset: every metric finite (the reference's
-    behave test, features/steps/test_srgan_train.py:60-67), weights change; second epoch through the captured graph
-    with a short last minibatch falling back to the eager functions."""
+    behave test, features/steps/test_srgan_train.py:60-67), weights change; second epoch through the captured graph.
+    Batches are always full (SerialIterator(repeat=True) completes the last batch of an epoch from the next epoch's
+    order): 10 samples in batches of 4 -> epoch 0 ends inside its third batch, epoch 1 inside its second."""
     from deepbedmap_b200 import train as T
     rng = np.random.RandomState(0)
     def data(n):
@@ -396,7 +397,7 @@ def test_trainer_epoch_eager_and_graphed_is_nan_free():
                 "W2": rng.rand(n, 2, 22, 22).astype(np.float32), "W3": rng.rand(n, 1, 11, 11).astype(np.float32),
                 "Y": rng.rand(n, 1, 36, 36).astype(np.float32)}
     g, g_opt, d, d_opt = T.compile_srgan_model(num_residual_blocks=1)
-    train_iter = T.ArrayIterator(data(10), 4, shuffle=True)     # 4 + 4 + 2 per epoch
+    train_iter = T.ArrayIterator(data(10), 4, shuffle=True)     # 4 + 4 + (2 + 2 of the next epoch)
     dev_iter = T.ArrayIterator(data(4), 4, shuffle=False)
     columns = ["discriminator_loss", "discriminator_accu", "generator_loss", "generator_psnr", "generator_ssim"]
     columns += ["val_" + c for c in columns]
@@ -409,9 +410,36 @@ def test_trainer_epoch_eager_and_graphed_is_nan_free():
     step = T.GraphedTrainStep(first, g, g_opt, d, d_opt)
     w1 = g.flat.clone()
     m1 = T.trainer(1, columns, train_iter, dev_iter, g, g_opt, d, d_opt, graphed_step=step)
-    assert all(len(m1[c]) == (3 if not c.startswith("val_") else 1) for c in columns)
+    assert all(len(m1[c]) == (2 if not c.startswith("val_") else 1) for c in columns)
     assert all(np.isfinite(v) for c in columns for v in m1[c])
-    assert not torch.equal(w1, g.flat) and g_opt.t == 6 and int(g_opt.t_dev[0]) == 6 and d_opt.t == 6
+    assert not torch.equal(w1, g.flat) and g_opt.t == 5 and int(g_opt.t_dev[0]) == 5 and d_opt.t == 5
+    # a minibatch of another shape takes the eager functions and leaves the graph usable
+    odd = {k: v[:3] for k, v in train_iter.arrays.items()}
+    assert not step.accepts(odd)
+    step.refresh()
+    T.train_eval_discriminator(odd, g, d, d_opt, share_generator_forward=True)
+    T.train_eval_generator(odd, g, d, g_opt)
+    step.refresh()
+    (dl, da), (gl, gp, gs) = step.step(first)
+    assert all(np.isfinite(v) for v in (dl, da, gl, gp, gs)) and int(g_opt.t_dev[0]) == 7 and g_opt.t == 7
+
+
+def test_shared_generator_forward_is_not_reused_for_refreshed_inputs():
+    """train_eval_discriminator(share_generator_forward=True) leaves its graph-keeping forward for the generator
+    step; an in-place refresh of an input buffer in between must invalidate it (same address, new data)."""
+    from deepbedmap_b200 import train as T
+    from deepbedmap_b200.model import as_device
+    g, g_opt, d, d_opt = T.compile_srgan_model(num_residual_blocks=1)
+    rng = np.random.RandomState(5)
+    arrays = {k: as_device(rng.rand(*s).astype(np.float32)) for k, s in
+              (("X", (2, 1, 11, 11)), ("W1", (2, 1, 110, 110)), ("W2", (2, 2, 22, 22)), ("W3", (2, 1, 11, 11)),
+               ("Y", (2, 1, 36, 36)))}
+    T.train_eval_discriminator(arrays, g, d, d_opt, share_generator_forward=True)
+    assert g.shared_forward(arrays["X"], arrays["W1"], arrays["W2"], arrays["W3"]) is not None
+    arrays["W1"].copy_(as_device(rng.rand(2, 1, 110, 110).astype(np.float32)))      # same buffer, new minibatch
+    assert g.shared_forward(arrays["X"], arrays["W1"], arrays["W2"], arrays["W3"]) is None
+    gl, gp, gs = T.train_eval_generator(arrays, g, d, g_opt)                         # runs its own forward
+    assert np.isfinite(gl) and np.isfinite(gp) and np.isfinite(gs)
 
 
 def test_npz_roundtrip(tmp_path):
@@ -492,7 +520,8 @@ def test_int16_dem_matches_numpy_astype():
 
 
 def test_device_iterator_matches_host_iterator():
-    """on-device shuffled batches == the host SerialIterator stand-in, incl. the ragged last batch."""
+    """on-device shuffled batches == the host SerialIterator stand-in, incl. the batch that wraps into
+    the next epoch's order."""
     from deepbedmap_b200.train import ArrayIterator, DeviceArrayIterator
     rng = np.random.RandomState(0)
     n = 37

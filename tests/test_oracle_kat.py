@@ -123,6 +123,12 @@ def test_deformable_conv_against_naive_and_torchvision():
     off_tv[:, 1::2] = off[:, :9]
     ref = tv.deform_conv2d(T(x), T(off_tv), T(W), T(b), padding=1).numpy()
     np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9)
+    # the row-gather form bench.py times (and the full-size golden tile uses) is the same function,
+    # also for offsets far outside the image
+    for scale in (1.0, 6.0):
+        fast = O.deformable_conv2d_fast(T(x), T(off * scale), T(W), T(b)).numpy()
+        np.testing.assert_allclose(fast, O.deformable_conv2d(T(x), T(off * scale), T(W), T(b)).numpy(),
+                                   rtol=1e-10, atol=1e-10)
 
 
 def test_chainer_adam_formula():
