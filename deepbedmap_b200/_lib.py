@@ -55,6 +55,9 @@ SIGNATURES = {
     "dbm_flat_to_nchw_ex": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dbm_transpose_f32": [_P, _P, _I, _I, _P],
     "dbm_stem_fwd_slab8": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dbm_stem_w1_s2d": [_P, _P, _I, _I, _I, _P],
+    "dbm_pack_stem_w1": [_P, _P, _P],
+    "dbm_conv3x3_umma_valid": [_P, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _P],
     "dbm_stem_fwd_flat": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dbm_deform_conv_umma": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P],
     "dbm_deform_out1_sample": [_P, _P, _I, _P, _P, _I, _I, _I, _P],

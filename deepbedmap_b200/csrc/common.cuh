@@ -38,6 +38,12 @@ __device__ __forceinline__ float lrelu(float v) { return v >= 0.f ? v : v * kLre
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 int num_sms();
+// Co-residency bound of a persistent kernel whose CTAs wait for each other through global flags (umma_trunk_kernel,
+// flat_chain_kernel): opts the kernel in to `smem` bytes of dynamic shared memory on the CURRENT device and returns in
+// *resident the number of CTAs that device holds at once for (threads, smem) -- occupancy query x SM count, cached per
+// (device, kernel, smem). A launch must not use a larger grid: a CTA that is not resident can never publish the flags
+// the resident ones spin on. Fails if not even one CTA fits.
+int resident_ctas(const void* kernel, int threads, size_t smem, int* resident);
 
 // ---------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA, tcgen05 (Blackwell). Raw PTX so that nothing but the CUDA
@@ -75,6 +81,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Wall-clock bound for the spins on inter-CTA flags: a co-tenant kernel (NCCL, a side stream) may legitimately hold an
+// SM a resident CTA is waiting for, so the bound is 20 s of %globaltimer, not a spin count; a protocol bug still
+// traps instead of hanging the GPU box.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct SpinGuard {
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  __device__ __forceinline__ bool expired() {
+    if ((++spins & 1023u) != 0) return false;
+    const unsigned long long now = globaltimer_ns();
+    if (t0 == 0) { t0 = now; return false; }
+    return now - t0 > 20000000000ull;
+  }
+};
+
 // Bounded spin: a broken pipeline traps instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;

@@ -35,6 +35,28 @@ int num_sms() {
   return n;
 }
 
+int resident_ctas(const void* kernel, int threads, size_t smem, int* resident) {
+  struct Entry { int dev; const void* k; size_t smem; int threads; int value; };
+  static Entry cache[64];
+  static int used = 0;
+  int dev = 0;
+  DBM_CUDA(cudaGetDevice(&dev));
+  for (int i = 0; i < used; ++i)
+    if (cache[i].dev == dev && cache[i].k == kernel && cache[i].smem == smem && cache[i].threads == threads) {
+      *resident = cache[i].value;
+      return DBM_OK;
+    }
+  DBM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0, sms = 0;
+  DBM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  DBM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DBM_REQUIRE(per_sm >= 1 && sms >= 1, "persistent kernel cannot be resident (%d CTAs/SM with %d threads, %zu B smem)",
+              per_sm, threads, smem);
+  *resident = per_sm * sms;
+  if (used < 64) cache[used++] = Entry{dev, kernel, smem, threads, *resident};
+  return DBM_OK;
+}
+
 static inline int ew_grid(long total, int per_block = 256) {
   long b = (total + per_block - 1) / per_block;
   long cap = (long)num_sms() * 16;

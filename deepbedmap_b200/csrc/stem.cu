@@ -16,6 +16,7 @@ constexpr int kXRows = kSTH + 2, kXCols = kSTW + 2;                    // 10 x 1
 constexpr int kW2Rows = (kSTH - 1) * 2 + 6, kW2Cols = (kSTW - 1) * 2 + 6;  // 20 x 36
 constexpr int kStemSmemFloats = kW1Rows * kW1Cols + 900 * 32 + 2 * kXRows * kXCols + 2 * kW2Rows * kW2Cols + 90 * 32;
 constexpr int kStemSmem = kStemSmemFloats * 4;
+constexpr int kStemSmallSmem = (2 * kXRows * kXCols + 2 * kW2Rows * kW2Cols + 90 * 32) * 4;   // without the W1 parts
 
 struct StemParams {
   const float *x, *w1, *w2, *w3;   // (N,1,h,w) (N,1,10h,10w) (N,2,2h,2w) (N,1,h,w)
@@ -56,11 +57,14 @@ __device__ __forceinline__ void fma_pair(float (&a)[2][8], float i0, float i1, c
   }
 }
 
-__global__ void __launch_bounds__(256, 1) stem_kernel(const StemParams p) {
+// kW1 = false: conv_on_X / W2 / W3 only (18 KB of shared memory, several blocks per SM); conv_on_W1 then runs on
+// the tensor cores (w1_s2d_split_kernel + umma_conv3x3_kernel, below).
+template <bool kW1>
+__global__ void __launch_bounds__(256, kW1 ? 1 : 4) stem_kernel(const StemParams p) {
   extern __shared__ __align__(16) float sm[];
   float* s_w1in = sm;                                   // [100][180]
-  float* s_w1w = s_w1in + kW1Rows * kW1Cols;            // [900][32]
-  float* s_x = s_w1w + 900 * 32;                        // [10][18]
+  float* s_w1w = s_w1in + (kW1 ? kW1Rows * kW1Cols : 0);  // [900][32]
+  float* s_x = s_w1w + (kW1 ? 900 * 32 : 0);            // [10][18]
   float* s_w3 = s_x + kXRows * kXCols;                  // [10][18]
   float* s_w2 = s_w3 + kXRows * kXCols;                 // [2][20][36]
   float* s_ws = s_w2 + 2 * kW2Rows * kW2Cols;           // [90][32]
@@ -73,11 +77,12 @@ __global__ void __launch_bounds__(256, 1) stem_kernel(const StemParams p) {
   const int oy0 = ty * kSTH, ox0 = tx * kSTW;
 
   // ---- stage filters and input windows (zero fill beyond the image; never read for valid outputs)
-  for (int i = t; i < 900 * 32 / 4; i += 256)
-    reinterpret_cast<float4*>(s_w1w)[i] = __ldg(reinterpret_cast<const float4*>(p.wt1) + i);
+  if (kW1)
+    for (int i = t; i < 900 * 32 / 4; i += 256)
+      reinterpret_cast<float4*>(s_w1w)[i] = __ldg(reinterpret_cast<const float4*>(p.wt1) + i);
   for (int i = t; i < 90 * 32 / 4; i += 256)
     reinterpret_cast<float4*>(s_ws)[i] = __ldg(reinterpret_cast<const float4*>(p.wts) + i);
-  {
+  if (kW1) {
     const int H1 = 10 * p.h, W1 = 10 * p.w;
     const float* src = p.w1 + (size_t)n * H1 * W1;
     const int r0 = oy0 * 10, c0 = ox0 * 10;
@@ -112,11 +117,11 @@ __global__ void __launch_bounds__(256, 1) stem_kernel(const StemParams p) {
   float a[2][8];
 
   // ---- conv_on_W1: k30 s10 ----
+  if (kW1) {
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a[i][k] = 0.f;
-  {
+      for (int k = 0; k < 8; ++k) a[i][k] = 0.f;
     const float* in = s_w1in + (r * 10) * kW1Cols + c * 10;
     const float* wq = s_w1w + cg * 8;
     // The two pixels' windows are columns [0, 30) and [10, 40) of the same 40 floats: one row of the
@@ -134,8 +139,8 @@ __global__ void __launch_bounds__(256, 1) stem_kernel(const StemParams p) {
 #pragma unroll
       for (int kx = 0; kx < 30; ++kx) fma_pair(a, row[kx], row[kx + 10], wq + (ky * 30 + kx) * 32);
     }
+    store_pair(p, n, 4 + cg, y, x, a, p.bias + 32 + cg * 8);
   }
-  store_pair(p, n, 4 + cg, y, x, a, p.bias + 32 + cg * 8);
 
   // ---- conv_on_X: k3 s1 ----
 #pragma unroll
@@ -178,6 +183,75 @@ __global__ void __launch_bounds__(256, 1) stem_kernel(const StemParams p) {
   store_pair(p, n, 12 + cg, y, x, a, p.bias + 96 + cg * 8);
 }
 
+// ---- conv_on_W1 (1 -> 32, k30 s10, valid) on the tensor cores -----------------------------------------------
+// A k30 s10 convolution is a 3x3 stride-1 valid convolution over the 10x10 space-to-depth of its input: cell
+// (cy, cx) holds the 100 values W1[10cy + dy][10cx + dx]. REMA elevations are metres (0 .. 4500) and must not lose
+// their low bits to bf16, so every operand is split into two bf16 terms, x = x_hi + x_lo, w = w_hi + w_lo (each
+// split exact to 2^-18), and the GEMM contracts the 320-channel operand
+//   [x_hi (100 -> 104) | x_lo (104) | x_hi (104) | 0 (8)]  against  [w_hi | w_hi | w_lo | 0]
+// = x_hi w_hi + x_lo w_hi + x_hi w_lo in fp32 accumulators: only the x_lo w_lo term (2^-18 relative) is dropped,
+// far below the bf16 rounding the 128-channel stem output gets anyway as the pre-residual conv's operand.
+constexpr int kW1Jp = 104, kW1Cs = 40;   // padded cell size, slabs of the split operand
+
+__global__ void __launch_bounds__(256) w1_s2d_split_kernel(const float* __restrict__ w1,
+                                                           __nv_bfloat16* __restrict__ out, int h, int w) {
+  __shared__ float cell[10][32 * 10 + 2];
+  const int cx0 = blockIdx.x * 32, cy = blockIdx.y, n = blockIdx.z;
+  const int W1 = 10 * w;
+  const float* src = w1 + ((size_t)n * 10 * h + (size_t)10 * cy) * W1 + (size_t)10 * cx0;
+  const int ncol = min(320, W1 - 10 * cx0);
+  for (int i = threadIdx.x; i < 10 * 320; i += 256) {
+    const int r = i / 320, c = i - r * 320;
+    cell[r][c] = c < ncol ? __ldg(src + (size_t)r * W1 + c) : 0.f;
+  }
+  __syncthreads();
+  const size_t plane = (size_t)h * w;
+  for (int i = threadIdx.x; i < 14 * 32; i += 256) {
+    const int sl = i >> 5, cx = cx0 + (i & 31);
+    if (cx >= w) continue;
+    __nv_bfloat16* dst = out + (((size_t)n * kW1Cs) * plane + (size_t)cy * w + cx) * 8;
+    if (sl == 13) {   // slab 39: zero padding of the K axis
+      *reinterpret_cast<uint4*>(dst + 39 * plane * 8) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = 8 * sl + k;
+      const float v = j < 100 ? cell[j / 10][(i & 31) * 10 + j % 10] : 0.f;
+      hi[k] = __float2bfloat16_rn(v);
+      lo[k] = __float2bfloat16_rn(v - __bfloat162float(hi[k]));
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)sl * plane * 8) = *reinterpret_cast<uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + (size_t)(13 + sl) * plane * 8) = *reinterpret_cast<uint4*>(lo);
+    *reinterpret_cast<uint4*>(dst + (size_t)(26 + sl) * plane * 8) = *reinterpret_cast<uint4*>(hi);
+  }
+}
+
+// conv_on_W1 filter (32, 1, 30, 30) fp32 -> bf16 UMMA operand image [320/32][9 taps][4][4][8 cout][8 cin] of the
+// split contraction above (K index c: group c / 104 in {w_hi, w_hi, w_lo, 0}, cell element j = c % 104).
+__global__ void pack_stem_w1_kernel(const float* __restrict__ wf, __nv_bfloat16* __restrict__ out) {
+  const int total = 9 * 320 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t = i;
+    const int c8 = t % 8; t /= 8;
+    const int o8 = t % 8; t /= 8;
+    const int cg = t % 4; t /= 4;
+    const int ksl = t % 4; t /= 4;
+    const int tap = t % 9; t /= 9;
+    const int kc = t;
+    const int o = cg * 8 + o8, c = kc * 32 + ksl * 8 + c8;
+    const int g = c / kW1Jp, j = c - g * kW1Jp;
+    float v = 0.f;
+    if (g < 3 && j < 100) {
+      const float wv = wf[o * 900 + (10 * (tap / 3) + j / 10) * 30 + 10 * (tap % 3) + j % 10];
+      const float h = __bfloat162float(__float2bfloat16_rn(wv));
+      v = g < 2 ? h : wv - h;
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // dst[c][r] = src[r][c]  (filter (32, taps) -> tap-major (taps, 32)); tiny, run once per weight update
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
   const int total = rows * cols;
@@ -202,9 +276,10 @@ static int stem_launch(const float* x, const float* w1, const float* w2, const f
                        void* out_slab8, int out_cs_total, int out_cs0, int n, int h, int w, int flat, cudaStream_t stream) {
   DBM_REQUIRE(n > 0 && h >= 3 && w >= 3, "stem: input %dx%d too small (need >= 3x3)", h, w);
   DBM_REQUIRE(out_cs_total >= out_cs0 + 16, "stem: output needs 16 slabs");
+  const bool with_w1 = w1 != nullptr;
   static bool attr_done = false;
   if (!attr_done) {
-    DBM_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
+    DBM_CUDA(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
     attr_done = true;
   }
   StemParams p;
@@ -221,8 +296,23 @@ static int stem_launch(const float* x, const float* w1, const float* w2, const f
   p.tiles_x = ceil_div(p.W, kSTW); p.tiles_y = ceil_div(p.H, kSTH);
   const long blocks = (long)n * p.tiles_x * p.tiles_y;
   DBM_REQUIRE(blocks < (1L << 31), "stem: too many tiles");
-  stem_kernel<<<(int)blocks, 256, kStemSmem, stream>>>(p);
+  if (with_w1)
+    stem_kernel<true><<<(int)blocks, 256, kStemSmem, stream>>>(p);
+  else
+    stem_kernel<false><<<(int)blocks, 256, kStemSmallSmem, stream>>>(p);
   return check_launch("stem_kernel");
+}
+
+extern "C" int dbm_stem_w1_s2d(const float* w1, void* s2d_slab8, int n, int h, int w, cudaStream_t stream) {
+  DBM_REQUIRE(n > 0 && h >= 3 && w >= 3 && h < 65536 && n < 65536, "stem_w1_s2d: bad shape %d x %d x %d", n, h, w);
+  DBM_REQUIRE(((uintptr_t)s2d_slab8 & 15) == 0, "stem_w1_s2d: unaligned output");
+  w1_s2d_split_kernel<<<dim3(ceil_div(w, 32), h, n), 256, 0, stream>>>(w1, (__nv_bfloat16*)s2d_slab8, h, w);
+  return check_launch("w1_s2d_split_kernel");
+}
+
+extern "C" int dbm_pack_stem_w1(const float* w1_filter, void* packed_bf16, cudaStream_t stream) {
+  pack_stem_w1_kernel<<<90, 256, 0, stream>>>(w1_filter, (__nv_bfloat16*)packed_bf16);
+  return check_launch("pack_stem_w1_kernel");
 }
 
 extern "C" int dbm_stem_fwd_slab8(const float* x, const float* w1, const float* w2, const float* w3,

@@ -32,6 +32,8 @@ struct UmmaConvParams {
   const float* bias;             // [COUT]
   float beta;
   int act, up2, swap;
+  int in_off;                    // 0: 'same' conv (zero padding by TMA out-of-bounds fill); 1: 'valid' conv -- output
+                                 // (y, x) of the (H, W) grid is centred on input (y + 1, x + 1) of an (H+2, W+2) one
   __nv_bfloat16* out_bf16;
   int out_cs_total, out_cs0;
   float* out_f32;
@@ -99,8 +101,8 @@ umma_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const UmmaConvP
         for (int kc = 0; kc < num_kc; ++kc) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES);
-          tma_load_4d(smA + s * Cfg::A_BYTES, &tmap_in, &full[s], (tx * kTile - 1) * 8, ty * kTile - 1,
-                      kc * (CK / 8), n);
+          tma_load_4d(smA + s * Cfg::A_BYTES, &tmap_in, &full[s], (tx * kTile - 1 + p.in_off) * 8,
+                      ty * kTile - 1 + p.in_off, kc * (CK / 8), n);
           bulk_load(smB + s * Cfg::B_BYTES, p.wpacked + (size_t)kc * (Cfg::B_BYTES / 2), Cfg::B_BYTES,
                     &full[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -479,6 +481,7 @@ extern "C" int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, 
   p.num_items = n * p.tiles_x * p.tiles_y;
   p.wpacked = (const __nv_bfloat16*)wpacked; p.bias = bias; p.beta = beta; p.act = act; p.up2 = up2;
   p.swap = g_debug_swap_lbo_sbo;
+  p.in_off = 0;
   p.out_bf16 = (__nv_bfloat16*)out_slab8; p.out_cs_total = out_cs_total; p.out_cs0 = out_cs0;
   p.out_f32 = out_f32_slab4; p.out_f32_cs_total = out_f32_cs_total; p.out_f32_cs0 = out_f32_cs0;
   p.res1 = res1_slab4; p.res2 = res2_slab4;
@@ -490,4 +493,30 @@ extern "C" int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, 
   }
   if (cout_padded == 32) return launch_umma<32, 32, 5>(tm, p, stream);
   return launch_umma<64, 32, 3>(tm, p, stream);
+}
+
+// 3x3 VALID convolution (no padding) with 32 output channels: out (n, h_in - 2, w_in - 2) bf16 slab8 slot =
+// conv(in (n, h_in, w_in) slab8) + bias. Used for conv_on_W1 of the input block (srgan_train.py:231, 259) over the
+// 10x10 space-to-depth split operand built by dbm_stem_w1_s2d (csrc/stem.cu).
+extern "C" int dbm_conv3x3_umma_valid(const void* in_slab8, int in_cs_total, int cin, const void* wpacked,
+                                      const float* bias, int n, int h_in, int w_in, void* out_slab8, int out_cs_total,
+                                      int out_cs0, cudaStream_t stream) {
+  DBM_REQUIRE(cin % 32 == 0 && cin <= in_cs_total * 8, "conv3x3_umma_valid: bad Cin=%d (slabs %d)", cin, in_cs_total);
+  DBM_REQUIRE(n > 0 && h_in >= 3 && w_in >= 3, "conv3x3_umma_valid: input %dx%d too small", h_in, w_in);
+  DBM_REQUIRE(out_slab8 != nullptr && out_cs0 + 4 <= out_cs_total, "conv3x3_umma_valid: bad output slot");
+  DBM_REQUIRE(((uintptr_t)in_slab8 & 15) == 0 && ((uintptr_t)wpacked & 15) == 0, "conv3x3_umma_valid: unaligned");
+  CUtensorMap tm;
+  int rc = make_slab8_tmap(&tm, in_slab8, n, in_cs_total, h_in, w_in, 32);
+  if (rc) return rc;
+  UmmaConvParams p;
+  p.N = n; p.H = h_in - 2; p.W = w_in - 2; p.Cin = cin;
+  p.tiles_x = ceil_div(p.W, kTile); p.tiles_y = ceil_div(p.H, kTile);
+  p.num_items = n * p.tiles_x * p.tiles_y;
+  p.wpacked = (const __nv_bfloat16*)wpacked; p.bias = bias; p.beta = 0.f; p.act = 0; p.up2 = 0;
+  p.swap = g_debug_swap_lbo_sbo;
+  p.in_off = 1;
+  p.out_bf16 = (__nv_bfloat16*)out_slab8; p.out_cs_total = out_cs_total; p.out_cs0 = out_cs0;
+  p.out_f32 = nullptr; p.out_f32_cs_total = 0; p.out_f32_cs0 = 0;
+  p.res1 = nullptr; p.res2 = nullptr;
+  return launch_umma<32, 32, 5>(tm, p, stream);
 }

@@ -319,9 +319,9 @@ flat_chain_kernel(const FlatLaunch* __restrict__ table, int count, const FlatGeo
           const int nt = tile + lane - 1;
           if (lane < 3 && nt >= 0 && nt < g.tiles) {
             const unsigned int* f = done + (size_t)(l - 1) * g.tiles + nt;
-            uint32_t spins = 0;
+            SpinGuard guard;
             while (flat_ld_acquire(f) < 4u) {
-              if (++spins > (1u << 24)) {
+              if (guard.expired()) {
                 printf("dbm: flat chain dependency timeout layer %d tile %d\n", l, tile);
                 __trap();
               }
@@ -859,8 +859,14 @@ extern "C" int dbm_flat_conv3x3_chain(const void* launches_host, const void* lau
   int nst = (kFlatSmem - 2048) / (int)stage_bytes;
   if (nst > kFlatMaxStages) nst = kFlatMaxStages;
   DBM_REQUIRE(nst >= 2, "flat_chain: stage of %u bytes does not fit twice", stage_bytes);
-  // every CTA must be co-resident (tiles spin on flags set by other CTAs): at most one CTA per SM
-  const int grid = g.tiles < num_sms() ? g.tiles : num_sms();
+  // every CTA must be co-resident (tiles spin on flags set by other CTAs): bounded by the occupancy query
+  int resident = 0;
+  {
+    int rc2 = resident_ctas((const void*)flat_chain_kernel, kFlatThreads, kFlatSmem, &resident);
+    if (rc2) return rc2;
+  }
+  if (resident > num_sms()) resident = num_sms();
+  const int grid = g.tiles < resident ? g.tiles : resident;
   DBM_CUDA(cudaMemsetAsync(flags_dev, 0, (size_t)count * g.tiles * sizeof(unsigned int), stream));
   flat_chain_kernel<<<grid, kFlatThreads, kFlatSmem, stream>>>((const FlatLaunch*)launches_dev, count, g,
                                                                (unsigned int*)flags_dev, stage_bytes, nst);

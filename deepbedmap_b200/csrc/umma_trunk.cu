@@ -182,9 +182,9 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
           const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
           if (ny >= 0 && ny < p.tiles_y && nx >= 0 && nx < p.tiles_x) {
             const unsigned int* f = p.done + (size_t)(L - 1) * I + (size_t)n * per_img + ny * p.tiles_x + nx;
-            uint32_t spins = 0;
+            SpinGuard guard;
             while (ld_acquire_gpu(f) < (unsigned)(kEpiWarps / 2)) {
-              if (++spins > (1u << 24)) {
+              if (guard.expired()) {
                 printf("dbm: trunk dependency timeout layer %d item %d\n", L, item);
                 __trap();
               }
@@ -303,9 +303,9 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       if (L > 0 && (ly.res1 || ly.res2) && !(p.debug & 1)) {
         if (lane == 0) {
           const unsigned int* f = p.done + (size_t)(L - 1) * I + item;
-          uint32_t spins = 0;
+          SpinGuard guard;
           while (ld_acquire_gpu(f) < (unsigned)(kEpiWarps / 2)) {
-            if (++spins > (1u << 24)) {
+            if (guard.expired()) {
               printf("dbm: trunk epilogue dependency timeout layer %d item %d\n", L, item);
               __trap();
             }
@@ -485,14 +485,13 @@ extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int
   p.debug = g_trunk_debug;
   p.prof = g_trunk_prof;
   DBM_CUDA(cudaMemsetAsync(flags_dev, 0, (size_t)num_layers * p.items_per_layer * sizeof(unsigned int), stream));
-  static bool attr_done = false;
-  if (!attr_done) {
-    DBM_CUDA(cudaFuncSetAttribute(umma_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmem));
-    attr_done = true;
-  }
   const long total = (long)num_layers * p.items_per_layer;
-  // every CTA must be co-resident (items spin on flags set by other CTAs): one CTA per SM
-  const int grid = total < num_sms() ? (int)total : num_sms();
+  // every CTA must be co-resident (items spin on flags set by other CTAs): the grid never exceeds what the occupancy
+  // query says this device holds at once (one CTA per SM with 200+ KB of shared memory)
+  int resident = 0;
+  int rc2 = resident_ctas((const void*)umma_trunk_kernel, kTrunkThreads, kTrunkSmem, &resident);
+  if (rc2) return rc2;
+  const int grid = total < resident ? (int)total : resident;
   umma_trunk_kernel<<<grid, kTrunkThreads, kTrunkSmem, stream>>>(maps, p);
   return check_launch("umma_trunk_kernel");
 }

@@ -185,6 +185,8 @@ class GeneratorModel(_Link):
         # output layer's tap projection inside the first deformable layer's epilogue: bit-identical, but measured
         # SLOWER (the four epilogue warps become the bottleneck: 2.11 -> 2.57 ms to save a 0.25 ms kernel) -> off
         self.fuse_out_projection = False
+        # conv_on_W1 (k30 s10) as a split-bf16 tcgen05 GEMM over the 10x10 space-to-depth (False: fp32 CUDA cores)
+        self.stem_w1_tensor_core = True
         self._ctx = None
 
     # ---- serialisation (chainer.serializers.load_npz / save_npz, App. C layout) ----
@@ -609,6 +611,8 @@ class GeneratorModel(_Link):
             # stem filters, tap-major, and the concatenated stem bias
             taps = {k: int(P[f"input_block/conv_on_{k}/W"][0].numel()) for k in ("X", "W1", "W2", "W3")}
             pk["stem"] = (ops.empty(taps["W1"], 32), ops.empty(taps["X"] + taps["W2"] + taps["W3"], 32), ops.empty(128))
+            # conv_on_W1 on the tensor cores (3x3 valid conv over the 10x10 space-to-depth, split-bf16 operands)
+            pk["stem_w1_tc"] = ops.empty(9 * 320 * 32, dtype=torch.bfloat16)
             tables = {}
             for g, ent in entries.items():
                 if ent:
@@ -640,6 +644,8 @@ class GeneratorModel(_Link):
                 for j, k in enumerate(("X", "W1", "W2", "W3")):
                     ops.axpby(P[f"input_block/conv_on_{k}/b"].view(1, 32, 1, 1), 0, None, 0,
                               bias128.view(1, 128, 1, 1), 32 * j, 32, 1.0, 0.0)
+                ops.call("dbm_pack_stem_w1", P["input_block/conv_on_W1/W"].data_ptr(), pk["stem_w1_tc"].data_ptr(),
+                         ops.stream())
             self._pack_versions[g] = self.version
         return pk
 
@@ -771,8 +777,18 @@ class GeneratorModel(_Link):
                      ws["x"][0].data_ptr(), ws["x"][1].data_ptr(), ops.stream())
         else:
             ws = self._trunk_workspace(n, H, W)
-            ops.call("dbm_stem_fwd_slab8", x.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), wt1.data_ptr(),
-                     wts.data_ptr(), bias128.data_ptr(), ws["s0"].data_ptr(), 16, 0, n, h, w, ops.stream())
+            if self.stem_w1_tensor_core:
+                # conv_on_X / W2 / W3: small fp32 direct convs; conv_on_W1 (99 % of the stem's FLOPs): tcgen05
+                s2d = ops.empty(n, 40, h, w, 8, dtype=bf)
+                ops.call("dbm_stem_w1_s2d", w1.data_ptr(), s2d.data_ptr(), n, h, w, ops.stream())
+                ops.call("dbm_stem_fwd_slab8", x.data_ptr(), None, w2.data_ptr(), w3.data_ptr(), None,
+                         wts.data_ptr(), bias128.data_ptr(), ws["s0"].data_ptr(), 16, 0, n, h, w, ops.stream())
+                ops.call("dbm_conv3x3_umma_valid", s2d.data_ptr(), 40, 320, pk["stem_w1_tc"].data_ptr(),
+                         P["input_block/conv_on_W1/b"].data_ptr(), n, h, w, ws["s0"].data_ptr(), 16, 4, ops.stream())
+                del s2d
+            else:
+                ops.call("dbm_stem_fwd_slab8", x.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), wt1.data_ptr(),
+                         wts.data_ptr(), bias128.data_ptr(), ws["s0"].data_ptr(), 16, 0, n, h, w, ops.stream())
             self._run_trunk(ws, n, H, W)
         u1 = ws["u1"]
         u2 = ops.empty(n, 8, 4 * H, 4 * W, 8, dtype=bf)

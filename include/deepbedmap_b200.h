@@ -199,6 +199,19 @@ int dbm_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStre
 int dbm_stem_fwd_slab8(const float* x, const float* w1, const float* w2, const float* w3,
                        const float* w1_filter_tapmajor, const float* small_filters_tapmajor, const float* bias128,
                        void* out_slab8, int out_cs_total, int out_cs0, int n, int h, int w, cudaStream_t stream);
+/* conv_on_W1 (1 -> 32, k30 s10 p0, srgan_train.py:231, 259) on the tensor cores: a k30 s10 convolution is a 3x3
+ * valid convolution over the 10x10 space-to-depth of its input. With w1 == NULL (and w1_filter_tapmajor == NULL)
+ * dbm_stem_fwd_slab8 computes conv_on_X / W2 / W3 only (slabs 0-3, 8-15 of the output); slabs 4-7 then come from
+ *   dbm_stem_w1_s2d        w1 (n,1,10h,10w) fp32 -> split operand, bf16 slab8 (n, 40 slabs, h, w):
+ *                          channels [x_hi(100->104) | x_lo(104) | x_hi(104) | 0(8)], x = x_hi + x_lo to 2^-18;
+ *   dbm_pack_stem_w1       filter (32,1,30,30) fp32 -> UMMA operand image (9*320*32 bf16) [w_hi | w_hi | w_lo | 0];
+ *   dbm_conv3x3_umma_valid 3x3 valid conv, 32 output channels, + bias -> bf16 slab8 slot (n, h-2, w-2).
+ * fp32-grade accuracy for metre-valued REMA inputs (only the x_lo*w_lo term is dropped). */
+int dbm_stem_w1_s2d(const float* w1, void* s2d_slab8, int n, int h, int w, cudaStream_t stream);
+int dbm_pack_stem_w1(const float* w1_filter, void* packed_bf16, cudaStream_t stream);
+int dbm_conv3x3_umma_valid(const void* in_slab8, int in_cs_total, int cin, const void* wpacked, const float* bias,
+                           int n, int h_in, int w_in, void* out_slab8, int out_cs_total, int out_cs0,
+                           cudaStream_t stream);
 /* Same fused input block, written in the flat-padded layout [16][Pg][8] (geometry of dbm_flat_geometry(n, h-2, w-2));
  * borders / guards of out_flat must be zero (they are never written). Feeds dbm_trunk_local_fwd on small tiles. */
 int dbm_stem_fwd_flat(const float* x, const float* w1, const float* w2, const float* w3, const float* w1_filter_tapmajor,
