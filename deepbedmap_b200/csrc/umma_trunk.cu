@@ -28,7 +28,7 @@ constexpr int kTStages = 5;
 constexpr int kTABytes = kHW * kHH * 16 * 2;         // 19584
 constexpr int kTBBytesMax = 9 * 16 * 64 * 2;         // 18432
 constexpr int kMaxTrunkLayers = 512;                 // 23 RRDB (config 5's deepest) = 347 passes
-constexpr int kTrunkSmem = kTStages * (kTABytes + kTBBytesMax) + 256 + kMaxTrunkLayers * 24 + kEpiWarps * 256 + 1024;
+constexpr int kTrunkSmem = kTStages * (kTABytes + kTBBytesMax) + 256 + kMaxTrunkLayers * 28 + kEpiWarps * 256 + 1024;
 
 struct TrunkMaps {  // one 18 px x 34 rows x 16-channel box map per input buffer
   CUtensorMap m[3];
@@ -54,9 +54,13 @@ __device__ __forceinline__ void issue_stage_wide(uint32_t d0, uint32_t a_lo, uin
 }
 
 // One MMA pass: out[:, 0:cout] = conv3x3(in[:, 8*in_cs0 : 8*in_cs0 + cin]) with the packed filter.
-// Columns [0, cout_main) take the fused epilogue (bias, residuals, LeakyReLU, bf16 / fp32 stores);
-// columns [cout_main, cout) are a *partial* pre-activation of a later layer that shares this
-// layer's input (dense-block pairing, see model.py) and are stashed raw as fp32 slab4.
+// mode 0: a layer of its own: all `cout` columns take the fused epilogue (bias, residuals, LeakyReLU, stores).
+// Dense-block pairing (see model.py): conv_k and the partial sums of conv_{k+1} over their shared inputs are ONE
+// N = 64 pass (mode 1, "head"): columns [0, 32) = conv_k take the epilogue, columns [32, 64) -- a partial
+// pre-activation of conv_{k+1} -- STAY IN TENSOR MEMORY; the next table entry (mode 2, "tail") contracts only a_k
+// (K = 32 * 9, N = 32) and accumulates onto those very columns, then takes the epilogue of conv_{k+1}. Head and tail
+// of a unit run on the same CTA (see the schedule below), so the partial sums never leave the SM: no fp32 stash in
+// HBM (round 1 wrote and re-read 128 B per pixel per pair), and the tail's epilogue has nothing to load.
 struct TrunkLayer {  // 128 bytes, mirrored by deepbedmap_b200/model.py (TRUNK_LAYER_DTYPE)
   const __nv_bfloat16* wpacked;
   const float* bias;
@@ -71,7 +75,8 @@ struct TrunkLayer {  // 128 bytes, mirrored by deepbedmap_b200/model.py (TRUNK_L
   int out_cs_total, out_cs0;
   int cout_main, res1_cs_total;
   float beta;
-  int pad[7];
+  int mode;            // 0 single pass, 1 pair head, 2 pair tail (must directly follow its head)
+  int pad[6];
 };
 static_assert(sizeof(TrunkLayer) == 128, "TrunkLayer layout is part of the C ABI");
 
@@ -85,9 +90,16 @@ struct TrunkParams {
   unsigned int* done;  // [num_layers][items_per_layer], zeroed before the launch; complete == kEpiWarps
   unsigned long long* prof;  // tuning only (NULL = off): [num_layers][8] cycle counters, see scripts/trunk_ablate.py
   int debug;           // ablation mask for tuning runs (results invalid): 1 no dependency wait, 2 no epilogue
-                       // memory traffic, 4 no TMA loads
+                       // memory traffic (32 fp32 stores only, 64 bf16 stores only, 128 residual loads only), 4 no TMA
+                       // loads, 8 / 16 fence placement
 };
 
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -115,6 +127,44 @@ __device__ __forceinline__ void st_f8(float* p, float a0, float a1, float a2, fl
                : "memory");
 }
 
+// ---- schedule -----------------------------------------------------------------------------------------------
+// The pass table is cut into GROUPS: a pair (head, tail) or a single pass. Within a group the I = N x tiles units are
+// dealt to the Gd = gridDim.x resident CTAs in rounds of Gd; a rotation that advances by I mod Gd per group moves the
+// CTAs that get the short last round around, as the pass-major numbering of round 1 did. A CTA walks a pair group two
+// rounds at a time:   head(u1) head(u2) tail(u1) tail(u2)   with u1 / u2 in TMEM accumulator buffers 0 / 1, so the
+// neighbours' head epilogues (the tail's halo) have a whole head item to land in L2 before the tail asks for them.
+// All three warp roles walk the same sequence with their own cursor; (group, step) -> item is a pure function.
+struct Cursor {
+  int grp = 0, step = 0;
+};
+struct Sched {
+  const int* groups;   // shared memory: first table index of the group, bit 30 set for a pair
+  int ng, I, Gd, rounds, bid;
+  __device__ __forceinline__ bool next(Cursor& c, int& L, int& unit, int& buf) const {
+    while (c.grp < ng) {
+      const int e = groups[c.grp];
+      const bool pair = (e >> 30) & 1;
+      const int nsteps = pair ? 4 * ((rounds + 1) >> 1) : rounds;
+      if (c.step >= nsteps) {
+        ++c.grp;
+        c.step = 0;
+        continue;
+      }
+      const int t = c.step++;
+      const int round = pair ? 2 * (t >> 2) + (t & 1) : t;
+      if (round >= rounds) continue;
+      int r = bid - (int)(((long)c.grp * I) % Gd);
+      if (r < 0) r += Gd;
+      unit = round * Gd + r;
+      if (unit >= I) continue;
+      L = (e & 0x3FFFFFFF) + (pair ? (t >> 1) & 1 : 0);
+      buf = t & 1;
+      return true;
+    }
+    return false;
+  }
+};
+
 __global__ void __launch_bounds__(kTrunkThreads, 1)
 umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -127,19 +177,38 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
   uint64_t* tfull = bars + 2 * kTStages;
   uint64_t* tempty = bars + 2 * kTStages + 2;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kTStages + 4);
+  int* ng_slot = (int*)(tmem_slot + 1);
   // per-layer scalars the producer / MMA warps need for every item, staged once in shared memory
   // (the epilogue's gpu-scope fences keep invalidating L1, a global read per item costs an L2 trip)
-  int4* linfo = (int4*)(smem + kTStages * (kTABytes + kTBBytesMax) + 256);         // {cin, cout, in_map, in_cs0}
+  int4* linfo = (int4*)(smem + kTStages * (kTABytes + kTBBytesMax) + 256);         // {cin, cout, in_map | mode << 8, in_cs0}
   const __nv_bfloat16** lw = (const __nv_bfloat16**)(linfo + kMaxTrunkLayers);
   float* sbias_all = (float*)(lw + kMaxTrunkLayers);  // [kEpiWarps][64]
+  int* groups = (int*)(sbias_all + kEpiWarps * 64);   // [kMaxTrunkLayers]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   for (int L = threadIdx.x; L < p.num_layers; L += kTrunkThreads) {
     const TrunkLayer* ly = p.layers + L;
-    linfo[L] = make_int4(ly->cin, ly->cout, ly->in_map, ly->in_cs0);
+    linfo[L] = make_int4(ly->cin, ly->cout, ly->in_map | (ly->mode << 8), ly->in_cs0);
     lw[L] = ly->wpacked;
+  }
+  if (threadIdx.x == 0) {
+    int ng = 0;
+    for (int L = 0; L < p.num_layers; ++L) {
+      const int mode = p.layers[L].mode;
+      // a pair head (N = 64, the upper 32 columns stay in TMEM) must be followed directly by its tail (N = 32)
+      const bool ok = mode == 0 || (mode == 1 && p.layers[L].cout == 64 && L + 1 < p.num_layers &&
+                                    p.layers[L + 1].mode == 2 && p.layers[L + 1].cout == 32) ||
+                      (mode == 2 && L > 0 && p.layers[L - 1].mode == 1);
+      if (!ok) {
+        if (blockIdx.x == 0) printf("dbm: trunk pass table entry %d: bad pairing (mode %d)\n", L, mode);
+        __trap();
+      }
+      if (mode == 2) continue;                       // belongs to the head before it
+      groups[ng++] = L | (mode == 1 ? (1 << 30) : 0);
+    }
+    *ng_slot = ng;
   }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 3; ++i) tma_prefetch_desc(&maps.m[i]);
@@ -161,39 +230,61 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
 
   const int I = p.items_per_layer;
   const int per_img = p.tiles_x * p.tiles_y;
-  const long total_items = (long)p.num_layers * I;
+  Sched sc;
+  sc.groups = groups; sc.ng = *ng_slot; sc.I = I; sc.Gd = (int)gridDim.x; sc.bid = (int)blockIdx.x;
+  sc.rounds = (I + sc.Gd - 1) / sc.Gd;
+  const unsigned int need = (unsigned)(kEpiWarps / 2);   // warps that publish a unit
 
   if (warp == 0) {
     // ================= dependency wait + TMA producer (converged warp) =================
+    // Lanes 0..8 each watch one neighbouring unit of the previous pass. The flags of the NEXT item are requested
+    // (relaxed gpu-scope loads, no ordering attached) before this item's stages are issued, so that whenever the
+    // previous pass finished long ago the L2 round trip of the dependency check is paid under the TMA loop instead of
+    // in front of every item (round 1: 1.3-2.0k cycles of operand wait per item at the MMA issuer). The acquire side
+    // is the gpu-scope fence after the observed values.
     int s = 0;
     uint32_t ph = 0;
-    for (long g = blockIdx.x; g < total_items; g += gridDim.x) {
-      const int L = (int)(g / I);
-      const int item = (int)(g - (long)L * I);
-      const int n = item / per_img;
-      const int r = item - n * per_img;
+    auto flag_of = [&](int L, int unit) -> const unsigned int* {
+      if (L == 0 || lane >= 9) return nullptr;
+      const int n = unit / per_img;
+      const int r = unit - n * per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
+      if (ny < 0 || ny >= p.tiles_y || nx < 0 || nx >= p.tiles_x) return nullptr;
+      return p.done + (size_t)(L - 1) * I + (size_t)n * per_img + ny * p.tiles_x + nx;
+    };
+    Cursor cur;
+    int L, unit, buf;
+    bool have = sc.next(cur, L, unit, buf);
+    const unsigned int* f_cur = have ? flag_of(L, unit) : nullptr;
+    unsigned int v_cur = f_cur != nullptr ? ld_relaxed_gpu(f_cur) : need;
+    while (have) {
+      const int n = unit / per_img;
+      const int r = unit - n * per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const int4 li = linfo[L];
-      const int cin = li.x, cout = li.y, in_map = li.z, in_cs0 = li.w;
+      const int cin = li.x, cout = li.y, in_map = li.z & 0xFF, in_cs0 = li.w;
       const __nv_bfloat16* wp = lw[L];
       if (L > 0 && !(p.debug & 1)) {
-        // lanes 0..8 each watch one neighbouring unit of the previous layer
-        if (lane < 9) {
-          const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
-          if (ny >= 0 && ny < p.tiles_y && nx >= 0 && nx < p.tiles_x) {
-            const unsigned int* f = p.done + (size_t)(L - 1) * I + (size_t)n * per_img + ny * p.tiles_x + nx;
-            SpinGuard guard;
-            while (ld_acquire_gpu(f) < (unsigned)(kEpiWarps / 2)) {
-              if (guard.expired()) {
-                printf("dbm: trunk dependency timeout layer %d item %d\n", L, item);
-                __trap();
-              }
-              __nanosleep(64);
+        if (f_cur != nullptr) {
+          SpinGuard guard;
+          while (v_cur < need) {
+            if (guard.expired()) {
+              printf("dbm: trunk dependency timeout layer %d unit %d\n", L, unit);
+              __trap();
             }
+            __nanosleep(64);
+            v_cur = ld_relaxed_gpu(f_cur);
           }
         }
         __syncwarp();
+        fence_acq_rel_gpu();   // acquire: orders the observed flags before everything below (all lanes)
       }
+      // request the next item's flags now; they are consumed at the top of the next iteration
+      int Ln, unitn, bufn;
+      have = sc.next(cur, Ln, unitn, bufn);
+      f_cur = have ? flag_of(Ln, unitn) : nullptr;
+      v_cur = f_cur != nullptr ? ld_relaxed_gpu(f_cur) : need;
       const CUtensorMap* tm = &maps.m[in_map];
       const uint32_t b_bytes = (uint32_t)(9 * 16 * 2) * (uint32_t)cout;
       const int num_kc = cin >> 4;
@@ -213,6 +304,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         __syncwarp();
         if (++s == kTStages) { s = 0; ph ^= 1; }
       }
+      L = Ln; unit = unitn; buf = bufn;
     }
   } else if (warp == 1) {
     // ================= MMA issuer: converged warp, one elected lane issues =================
@@ -221,26 +313,28 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
     const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
     int s = 0;
     uint32_t ph = 0;
-    int it = 0;
-    for (long g = blockIdx.x; g < total_items; g += gridDim.x, ++it) {
-      const int L = (int)(g / I);
+    uint32_t use[2] = {0, 0};   // how often each accumulator buffer was handed over (mbarrier phases)
+    Cursor cur;
+    int L, unit, buf;
+    while (sc.next(cur, L, unit, buf)) {
       const int4 li = linfo[L];
-      const int cin = li.x, cout = li.y;
+      const int cin = li.x, cout = li.y, mode = li.z >> 8;
       const int num_kc = cin >> 4;
-      const int buf = it & 1;
       const long long t0 = p.prof ? clock64() : 0;
-      mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&tempty[buf], (use[buf] & 1) ^ 1);
+      ++use[buf];
       tc_fence_after();
       const long long t1 = p.prof ? clock64() : 0;
       long long tw = 0;
-      const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
+      // a tail accumulates onto columns [32, 64) of every sub-tile, where its head left the partial sums
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * 256 + (mode == 2 ? 32 : 0));
       for (int kc = 0; kc < num_kc; ++kc) {
         const long long tw0 = p.prof ? clock64() : 0;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         if (p.prof) tw += clock64() - tw0;
         const uint32_t a_lo = desc_lo(smA_u + s * kTABytes, kHW * kHH * 16);
-        const uint32_t acc0 = kc != 0 ? 1u : 0u;
+        const uint32_t acc0 = (kc != 0 || mode == 2) ? 1u : 0u;
         if (cout == 32) {
           const uint32_t b_lo = desc_lo(smB_u + s * kTBBytesMax, 4 * 128);
           if (elect_one_sync()) {
@@ -268,35 +362,41 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
     }
   } else {
     // ================= epilogue: TMEM -> registers -> HBM, then publish the unit =================
-    // Two groups of four warps (warp w may touch TMEM lanes 32*(w%4)..+31). Group e handles the
-    // CTA's items with (it & 1) == e, i.e. always TMEM accumulator buffer e, so consecutive items'
-    // epilogues (residual loads, stores, the release fence) overlap each other. The accumulator is
-    // handed back to the MMA warp as soon as its last column block is in registers.
+    // Two groups of four warps (warp w may touch TMEM lanes 32*(w%4)..+31). Group e owns TMEM accumulator buffer e
+    // and handles the CTA's items on that buffer, so the epilogues of consecutive items (residual loads, stores, the
+    // release fence) overlap each other. The accumulator is handed back to the MMA warp as soon as its last column
+    // block is in registers.
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
     const int m = 32 * q + lane;
     const int gy = m >> 3, xr = m & 7;
     const bool mem = !(p.debug & 2);
+    const bool mem_f32 = mem && !(p.debug & 32), mem_bf16 = mem && !(p.debug & 64), mem_res = mem && !(p.debug & 128);
     const size_t plane = (size_t)p.H * p.W;
     float* sbias = sbias_all + (warp - 2) * 64;
-    int it = grp;
-    for (long g = blockIdx.x + (long)grp * gridDim.x; g < total_items; g += 2L * gridDim.x, it += 2) {
-      const int L = (int)(g / I);
-      const int item = (int)(g - (long)L * I);
+    uint32_t use = 0;
+    Cursor cur;
+    int L, item, buf;
+    while (sc.next(cur, L, item, buf)) {
+      if (buf != grp) continue;
       const int n = item / per_img;
       const int r = item - n * per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const TrunkLayer ly = p.layers[L];
       const int y0 = ty * kTH + gy;
       const int x0 = tx * kTW + xr;
-      const int nbc = ly.cout >> 5;            // 32-column blocks per sub-tile
+      // 32-column blocks per sub-tile that take the epilogue now: a pair head leaves its upper 32 columns in TMEM,
+      // a pair tail reads exactly those
+      const int nbc = ly.mode == 0 ? (ly.cout >> 5) : 1;
+      const int col_off = ly.mode == 2 ? 32 : 0;
       const int nblk = 4 * nbc;                // sub-tile-major
+      const int cmain = nbc << 5;
       F8 r1[4], r1n[4];
       // this pass's bias, staged per warp in shared memory (a global read per block would cost an
       // L2 round trip each: the gpu-scope fences keep invalidating L1)
-      if (lane < ly.cout_main) sbias[lane] = __ldg(ly.bias + lane);
-      if (lane + 32 < ly.cout_main) sbias[lane + 32] = __ldg(ly.bias + lane + 32);
-      // Addends (residual stream / stash) were written by the same unit of earlier passes;
+      if (lane < cmain) sbias[lane] = __ldg(ly.bias + lane);
+      if (lane + 32 < cmain) sbias[lane + 32] = __ldg(ly.bias + lane + 32);
+      // Addends (residual stream) were written by the same unit of earlier passes;
       // (L-1, item) complete implies all of those are (dependencies are transitive), and this warp
       // must acquire that flag itself: the producer warp's acquire is only inherited through tfull,
       // which has not been waited on yet.
@@ -304,7 +404,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         if (lane == 0) {
           const unsigned int* f = p.done + (size_t)(L - 1) * I + item;
           SpinGuard guard;
-          while (ld_acquire_gpu(f) < (unsigned)(kEpiWarps / 2)) {
+          while (ld_acquire_gpu(f) < need) {
             if (guard.expired()) {
               printf("dbm: trunk epilogue dependency timeout layer %d item %d\n", L, item);
               __trap();
@@ -319,7 +419,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         const int j = nbc == 2 ? (b >> 1) : b;
         const int c0 = (b - j * nbc) << 5;
         const int x = x0 + 8 * (j & 1), y = y0 + 16 * (j >> 1);
-        if (ly.res1 != nullptr && c0 < ly.cout_main && mem && y < p.H && x < p.W) {
+        if (ly.res1 != nullptr && mem_res && y < p.H && x < p.W) {
           const float* rp =
               ly.res1 + (((size_t)n * (ly.res1_cs_total >> 1) + (c0 >> 3)) * plane + (size_t)y * p.W + x) * 8;
 #pragma unroll
@@ -328,7 +428,8 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       };
       load_r1(0, r1);
       const long long e0 = p.prof ? clock64() : 0;
-      mbar_wait(&tfull[grp], (it >> 1) & 1);
+      mbar_wait(&tfull[grp], use & 1);
+      ++use;
       tc_fence_after();
       const long long e1 = p.prof ? clock64() : 0;
       long long e2 = 0;
@@ -337,30 +438,20 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         const int c0 = (b - j * nbc) << 5;
         const int x = x0 + 8 * (j & 1);
         const int y = y0 + 16 * (j >> 1);
-        const bool valid = mem && (y < p.H) && (x < p.W);
+        const bool valid = (y < p.H) && (x < p.W);
         const size_t pix = (size_t)y * p.W + x;
-        const bool main_blk = c0 < ly.cout_main;
         uint32_t acc[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(grp * 256 + j * 64 + c0), acc);
-        const bool has1 = main_blk && ly.res1 != nullptr && valid, has2 = main_blk && ly.res2 != nullptr && valid;
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(grp * 256 + j * 64 + col_off + c0), acc);
+        const bool has1 = ly.res1 != nullptr && valid && mem_res, has2 = ly.res2 != nullptr && valid && mem_res;
         if (b + 1 < nblk) load_r1(b + 1, r1n);
         tmem_wait_ld();
-        if (b == nblk - 1) {  // accumulator fully in registers: release it to the MMA warp
+        if (b == nblk - 1) {  // everything this item reads is in registers: release the buffer to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[grp]);
           if (p.prof) e2 = clock64();
         }
-        if (valid && !main_blk) {
-          // raw partial sums of the paired layer -> fp32 stash
-          const int scs = (ly.cout - ly.cout_main) >> 3;
-          float* sp = ly.stash_out + (((size_t)n * scs + ((c0 - ly.cout_main) >> 3)) * plane + pix) * 8;
-#pragma unroll
-          for (int s8 = 0; s8 < 4; ++s8)
-            st_f8(sp + (size_t)s8 * plane * 8, __uint_as_float(acc[8 * s8]), __uint_as_float(acc[8 * s8 + 1]),
-                  __uint_as_float(acc[8 * s8 + 2]), __uint_as_float(acc[8 * s8 + 3]), __uint_as_float(acc[8 * s8 + 4]),
-                  __uint_as_float(acc[8 * s8 + 5]), __uint_as_float(acc[8 * s8 + 6]), __uint_as_float(acc[8 * s8 + 7]));
-        } else if (valid) {
+        if (valid) {
         float v[32];
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
@@ -387,14 +478,14 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
         }
-        if (ly.out_f32) {
+        if (ly.out_f32 && mem_f32) {
           float* op = ly.out_f32 + (((size_t)n * 8 + (c0 >> 3)) * plane + pix) * 8;
 #pragma unroll
           for (int s8 = 0; s8 < 4; ++s8)
             st_f8(op + (size_t)s8 * plane * 8, v[8 * s8], v[8 * s8 + 1], v[8 * s8 + 2], v[8 * s8 + 3], v[8 * s8 + 4],
                   v[8 * s8 + 5], v[8 * s8 + 6], v[8 * s8 + 7]);
         }
-        if (ly.out_bf16) {
+        if (ly.out_bf16 && mem_bf16) {
 #pragma unroll
           for (int s8 = 0; s8 < 4; ++s8) {
             uint4 o;
@@ -485,7 +576,7 @@ extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int
   p.debug = g_trunk_debug;
   p.prof = g_trunk_prof;
   DBM_CUDA(cudaMemsetAsync(flags_dev, 0, (size_t)num_layers * p.items_per_layer * sizeof(unsigned int), stream));
-  const long total = (long)num_layers * p.items_per_layer;
+  const long total = p.items_per_layer;   // units per pass: the schedule deals them to the CTAs pass group by pass group
   // every CTA must be co-resident (items spin on flags set by other CTAs): the grid never exceeds what the occupancy
   // query says this device holds at once (one CTA per SM with 200+ KB of shared memory)
   int resident = 0;

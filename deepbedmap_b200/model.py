@@ -24,7 +24,7 @@ TRUNK_LAYER_DTYPE = np.dtype([("wpacked", "<u8"), ("bias", "<u8"), ("out_bf16", 
                               ("res1", "<u8"), ("res2", "<u8"), ("stash_out", "<u8"), ("cin", "<i4"), ("cout", "<i4"),
                               ("in_map", "<i4"), ("in_cs0", "<i4"), ("act", "<i4"), ("up2", "<i4"),
                               ("out_cs_total", "<i4"), ("out_cs0", "<i4"), ("cout_main", "<i4"),
-                              ("res1_cs_total", "<i4"), ("beta", "<f4"), ("pad", "<i4", (7,))])
+                              ("res1_cs_total", "<i4"), ("beta", "<f4"), ("mode", "<i4"), ("pad", "<i4", (6,))])
 assert TRUNK_LAYER_DTYPE.itemsize == 128
 # mirror of struct PackEntry in csrc/umma_conv3x3.cu (48 bytes)
 PACK_ENTRY_DTYPE = np.dtype([("w", "<u8"), ("out", "<u8"), ("O", "<i4"), ("o0", "<i4"), ("Cin", "<i4"),
@@ -663,23 +663,26 @@ class GeneratorModel(_Link):
         cc = 64 + 4 * g
         ccs = cc // 8
         beta = self.residual_scaling
-        paired = self.persistent_trunk and self.paired_trunk and g == 32
+        # pairing keeps partial sums in tensor memory between a head and its tail on the same CTA; the schedule's
+        # deadlock-freedom argument needs a unit's neighbours (+- one row of 16-pixel-wide units) to lie within one
+        # round of CTAs, i.e. images narrower than ~2000 px (csrc/umma_trunk.cu, "schedule")
+        paired = self.persistent_trunk and self.paired_trunk and g == 32 and (W + 15) // 16 + 2 <= 128
         if ws is None:
             ws = dict(s0=ops.empty(n, 16, H, W, 8, dtype=bf), cat=[ops.empty(n, ccs, H, W, 8, dtype=bf) for _ in range(2)],
                       a1_f32=ops.empty(n, 16, H, W, 4), f32=[ops.empty(n, 16, H, W, 4) for _ in range(3)],
-                      u1=ops.empty(n, 8, 2 * H, 2 * W, 8, dtype=bf), stash=ops.empty(n, 8, H, W, 4))
-        cat, f32, a1_f32, stash = ws["cat"], ws["f32"], ws["a1_f32"], ws["stash"]
+                      u1=ops.empty(n, 8, 2 * H, 2 * W, 8, dtype=bf))
+        cat, f32, a1_f32 = ws["cat"], ws["f32"], ws["a1_f32"]
         layers = []
         flops = []
 
         def layer(wkey, cin, cout, in_map, act=0, beta_=0.0, out=None, out_cs0=0, out_f32=None, res1=None, res2=None,
-                  up2=0, in_cs0=0, cout_main=None, res1_cs=16, stash_out=None, raw=False):
+                  up2=0, in_cs0=0, cout_main=None, res1_cs=16, stash_out=None, raw=False, mode=0):
             trunk_pack = self.persistent_trunk or self.per_layer_ck16
             wq, bq = pk[wkey] if raw else (pk[wkey + "@trunk"] if trunk_pack else pk[wkey])
             ptr = lambda t: t.data_ptr() if t is not None else 0
             layers.append((wq.data_ptr(), bq.data_ptr(), ptr(out), ptr(out_f32), ptr(res1), ptr(res2), ptr(stash_out),
                            cin, cout, in_map, in_cs0, act, up2, out.shape[1] if out is not None else 0, out_cs0,
-                           cout if cout_main is None else cout_main, res1_cs, beta_, (0,) * 7))
+                           cout if cout_main is None else cout_main, res1_cs, beta_, mode, (0,) * 6))
             flops.append(2.0 * 9 * cin * cout * n * H * W)
 
         layer("pre_residual_conv_layer", 128, 64, 0, act=1, out=cat[0], out_f32=a1_f32)
@@ -690,17 +693,19 @@ class GeneratorModel(_Link):
                 pre = self._rdb_prefix(i, r)
                 if paired:
                     # a_k = lrelu(conv_k([a0..a_{k-1}])) for k = 1..4 (srgan_train.py:339-352) in four passes:
-                    #   k odd : N = 64 over [a0..a_{k-1}] -> a_k (32 cols, fused epilogue) and the partial sums of
-                    #           conv_{k+1} over the same inputs (32 cols, raw fp32 stash)
-                    #   k even: N = 32 over a_{k-1} only, stash added in the epilogue -> a_k
+                    #   k odd  ("head", mode 1): N = 64 over [a0..a_{k-1}] -> a_k (32 columns, fused epilogue); the
+                    #           other 32 columns -- the partial sums of conv_{k+1} over the same inputs -- stay in
+                    #           tensor memory
+                    #   k even ("tail", mode 2): N = 32 over a_{k-1} only, accumulated onto those columns -> a_k
                     # Same FLOPs; 252 N=32 MMAs per 128-pixel tile become 108 N=64 + 36 N=32 MMAs (each MMA
-                    # re-reads its 4 KB A operand from shared memory whatever N is).
+                    # re-reads its 4 KB A operand from shared memory whatever N is), and nothing but the bf16
+                    # features a_k ever leaves the SM.
                     for k in (1, 3):
                         cin = 64 + (k - 1) * g
                         layer(f"{pre}/pair{k}", cin, 64, 1 + cur, act=1, out=cat[cur], out_cs0=cin // 8, cout_main=32,
-                              stash_out=stash, raw=True)
-                        layer(f"{pre}/tail{k + 1}", 32, 32, 1 + cur, in_cs0=cin // 8, act=1, beta_=1.0, out=cat[cur],
-                              out_cs0=cin // 8 + 4, res1=stash, res1_cs=8, raw=True)
+                              raw=True, mode=1)
+                        layer(f"{pre}/tail{k + 1}", 32, 32, 1 + cur, in_cs0=cin // 8, act=1, out=cat[cur],
+                              out_cs0=cin // 8 + 4, raw=True, mode=2)
                 else:
                     for k in (1, 2, 3, 4):
                         cin = 64 + (k - 1) * g
@@ -733,7 +738,7 @@ class GeneratorModel(_Link):
         srcs = (ws["s0"], ws["cat"][0], ws["cat"][1])
         ops.call("dbm_debug_set", 2, int(self.per_layer_ck16))
         for (wq, bq, out, out_f32, res1, res2, _stash, cin, cout, in_map, _cs0, act, up2, out_cs_total, out_cs0, _cm,
-             _r1cs, beta_, _pad) in ws["layers"]:
+             _r1cs, beta_, _mode, _pad) in ws["layers"]:
             inp = srcs[in_map]
             ops.call("dbm_conv3x3_umma", inp.data_ptr(), inp.shape[1], cin, wq, bq, cout, n, H, W, float(beta_), act, up2,
                      out or None, out_cs_total, out_cs0, out_f32 or None, 16, 0, res1 or None, res2 or None, ops.stream())

@@ -123,7 +123,7 @@ def test_persistent_trunk_kernel_equals_per_layer_launches(nb, n, h, w):
 
 @pytest.mark.parametrize("nb,n,h,w", [(2, 3, 40, 37), (12, 2, 11, 11), (1, 1, 70, 90), (3, 2, 35, 52)])
 def test_paired_trunk_plan_is_deterministic_and_tracks_unpaired(nb, n, h, w):
-    """Dense-block pairing (conv_k + partial sums of conv_{k+1} in one 64-wide pass, fp32 stash) only
+    """Dense-block pairing (conv_k + partial sums of conv_{k+1} in one 64-wide pass, kept in tensor memory) only
     re-associates fp32 sums: run-to-run bit-identical (a dependency race would not be), and as close
     to the unpaired plan as one flipped bf16 storage rounding per few thousand activations allows."""
     m, params = make_generator(nb, "bf16", scale=0.7)

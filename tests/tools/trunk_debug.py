@@ -18,7 +18,7 @@ def run(persistent, paired, dbg=0):
     m.persistent_trunk, m.paired_trunk = persistent, paired
     ws = m._trunk_workspace(n, H, W)
     ws["s0"].copy_(s0)
-    for t in ws["cat"] + ws["f32"] + [ws["a1_f32"], ws["u1"], ws["stash"]]:
+    for t in ws["cat"] + ws["f32"] + [ws["a1_f32"], ws["u1"]]:
         t.zero_()
     _lib.call("dbm_debug_set", 3, dbg)
     m._run_trunk(ws, n, H, W)
