@@ -130,9 +130,14 @@ __device__ __forceinline__ void st_f8(float* p, float a0, float a1, float a2, fl
 // ---- schedule -----------------------------------------------------------------------------------------------
 // The pass table is cut into GROUPS: a pair (head, tail) or a single pass. Within a group the I = N x tiles units are
 // dealt to the Gd = gridDim.x resident CTAs in rounds of Gd; a rotation that advances by I mod Gd per group moves the
-// CTAs that get the short last round around, as the pass-major numbering of round 1 did. A CTA walks a pair group two
-// rounds at a time:   head(u1) head(u2) tail(u1) tail(u2)   with u1 / u2 in TMEM accumulator buffers 0 / 1, so the
-// neighbours' head epilogues (the tail's halo) have a whole head item to land in L2 before the tail asks for them.
+// CTAs that get the short last round around, as the pass-major numbering of round 1 did. A CTA walks the rounds
+// r0, r1, ... of a pair group software-pipelined over the two TMEM accumulator buffers (round k in buffer k & 1):
+//     head(r0) head(r1) tail(r0) head(r2) tail(r1) head(r3) tail(r2) ... head(rR-1) tail(rR-2) tail(rR-1)
+// so a tail runs one head AND one tail item after its own head: the neighbours' head epilogues (the tail's halo) have
+// ~13k cycles to land in L2 before the tail asks for them (their epilogue + flag + TMA round trip is ~8k), and only the
+// last tail of a group follows its head closely. Every dependency of an item points to a strictly earlier step of
+// another CTA's walk (neighbouring units sit in the same or an adjacent round), so the walk cannot deadlock as long as
+// all CTAs are resident.
 // All three warp roles walk the same sequence with their own cursor; (group, step) -> item is a pure function.
 struct Cursor {
   int grp = 0, step = 0;
@@ -144,21 +149,26 @@ struct Sched {
     while (c.grp < ng) {
       const int e = groups[c.grp];
       const bool pair = (e >> 30) & 1;
-      const int nsteps = pair ? 4 * ((rounds + 1) >> 1) : rounds;
+      const int nsteps = pair ? 2 * rounds : rounds;
       if (c.step >= nsteps) {
         ++c.grp;
         c.step = 0;
         continue;
       }
       const int t = c.step++;
-      const int round = pair ? 2 * (t >> 2) + (t & 1) : t;
-      if (round >= rounds) continue;
+      int round = t, tail = 0;
+      if (pair) {
+        if (t == 0) round = 0;
+        else if (t == nsteps - 1) { round = rounds - 1; tail = 1; }
+        else if (t & 1) round = (t + 1) >> 1;
+        else { round = (t >> 1) - 1; tail = 1; }
+      }
       int r = bid - (int)(((long)c.grp * I) % Gd);
       if (r < 0) r += Gd;
       unit = round * Gd + r;
       if (unit >= I) continue;
-      L = (e & 0x3FFFFFFF) + (pair ? (t >> 1) & 1 : 0);
-      buf = t & 1;
+      L = (e & 0x3FFFFFFF) + tail;
+      buf = round & 1;
       return true;
     }
     return false;
@@ -433,6 +443,61 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       tc_fence_after();
       const long long e1 = p.prof ? clock64() : 0;
       long long e2 = 0;
+      // Passes whose only output is a 32-channel bf16 feature slot (every dense-block conv_1..4: pair heads, pair
+      // tails, the unpaired layers) read their sub-tiles out with two tcgen05.ld in flight per wait
+      // (two sub-tiles at a time) and hand the accumulator back after the second pair of loads: the buffer is held for
+      // ~1k cycles instead of the ~4k of the block-by-block loop below, which matters because in the pair schedule the next head on this very
+      // buffer is the next item the MMA warp issues.
+      const bool quick = nbc == 1 && ly.res1 == nullptr && ly.res2 == nullptr && ly.out_f32 == nullptr && !ly.up2 &&
+                         ly.out_bf16 != nullptr;
+      if (quick) {
+        const uint32_t tb = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(grp * 256 + col_off);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {   // two sub-tiles (64 registers) per round: 168 registers is the cap
+          uint32_t acc2[2][32];
+          tmem_ld_32x32b_x32(tb + (uint32_t)((2 * half) * 64), acc2[0]);
+          tmem_ld_32x32b_x32(tb + (uint32_t)((2 * half + 1) * 64), acc2[1]);
+          tmem_wait_ld();
+          if (half == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[grp]);
+            if (p.prof) e2 = clock64();
+          }
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int x = x0 + 8 * jj;
+            const int y = y0 + 16 * half;
+            if (y < p.H && x < p.W && mem_bf16) {
+              const size_t pix = (size_t)y * p.W + x;
+#pragma unroll
+              for (int s8 = 0; s8 < 4; ++s8) {
+                const float4 ba = *reinterpret_cast<const float4*>(sbias + 8 * s8);
+                const float4 bb = *reinterpret_cast<const float4*>(sbias + 8 * s8 + 4);
+                float v[8] = {__uint_as_float(acc2[jj][8 * s8 + 0]) + ba.x, __uint_as_float(acc2[jj][8 * s8 + 1]) + ba.y,
+                              __uint_as_float(acc2[jj][8 * s8 + 2]) + ba.z, __uint_as_float(acc2[jj][8 * s8 + 3]) + ba.w,
+                              __uint_as_float(acc2[jj][8 * s8 + 4]) + bb.x, __uint_as_float(acc2[jj][8 * s8 + 5]) + bb.y,
+                              __uint_as_float(acc2[jj][8 * s8 + 6]) + bb.z, __uint_as_float(acc2[jj][8 * s8 + 7]) + bb.w};
+                if (ly.act) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = lrelu(v[i]);
+                }
+                uint4 o;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[2], v[3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]);
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[6], v[7]);
+                o.x = *reinterpret_cast<uint32_t*>(&t0);
+                o.y = *reinterpret_cast<uint32_t*>(&t1);
+                o.z = *reinterpret_cast<uint32_t*>(&t2);
+                o.w = *reinterpret_cast<uint32_t*>(&t3);
+                const size_t cs = (size_t)n * ly.out_cs_total + (ly.out_cs0 + s8);
+                *reinterpret_cast<uint4*>(ly.out_bf16 + (cs * plane + pix) * 8) = o;
+              }
+            }
+          }
+        }
+      } else
       for (int b = 0; b < nblk; ++b) {
         const int j = nbc == 2 ? (b >> 1) : b;
         const int c0 = (b - j * nbc) << 5;

@@ -39,7 +39,7 @@ for n, paired in [(n, pl) for n in ns for pl in plans]:
         nl = len(ws["layers"])
         prof = torch.zeros(nl * 8, dtype=torch.int64, device="cuda")
         _lib.call("dbm_debug_set_ptr", 1, prof.data_ptr())
-        _lib.call("dbm_debug_set", 3, masks[-1])
+        _lib.call("dbm_debug_set", 3, masks[0])
         m._run_trunk(ws, n, H, W)
         torch.cuda.synchronize()
         _lib.call("dbm_debug_set", 3, 0)
@@ -49,7 +49,7 @@ for n, paired in [(n, pl) for n in ns for pl in plans]:
         for L, ly in enumerate(ws["layers"]):
             key = (ly[7], ly[8], ly[15])  # cin, cout, cout_main
             kinds.setdefault(key, []).append(L)
-        print(f"n={n} paired={paired} mask={masks[-1]}: per pass kind, cycles per item: MMA[wait tmem, wait operands, total] "
+        print(f"n={n} paired={paired} mask={masks[0]}: per pass kind, cycles per item: MMA[wait tmem, wait operands, total] "
               f"EPI[wait acc, read-out, stores+fence]")
         for key, Ls in kinds.items():
             a = pr[Ls].sum(0)
