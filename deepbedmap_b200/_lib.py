@@ -17,6 +17,7 @@ _P, _L, _I, _F = ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_float
 # name -> argument ctypes, in the order of include/deepbedmap_b200.h
 SIGNATURES = {
     "dbm_version": [],
+    "dbm_launch_count": [],
     "dbm_debug_set": [_I, _I],
     "dbm_debug_set_ptr": [_I, _P],
     "dbm_conv2d_fwd_f32": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -78,7 +79,21 @@ SIGNATURES = {
     "dbm_f32_to_i16": [_P, _P, _L, _P],
     "dbm_copy2d_async": [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P],
     "dbm_gather_rows_f32": [_P, _L, _P, _P, _L, _I, _P],
+    # model-level entry points (handles are opaque pointers)
+    "dbm_gen_create": [_I, _F, _I, ctypes.POINTER(_P)],
+    "dbm_gen_destroy": [_P],
+    "dbm_gen_count_params": [_P],
+    "dbm_gen_num_arrays": [_P],
+    "dbm_gen_array_info": [_P, _I, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_I), ctypes.POINTER(_I),
+                           ctypes.POINTER(_L)],
+    "dbm_gen_set_param": [_P, ctypes.c_char_p, _P, _I, ctypes.POINTER(_I)],
+    "dbm_gen_bind_params": [_P, _P],
+    "dbm_gen_mark_updated": [_P],
+    "dbm_gen_workspace_bytes": [_P, _I, _I, _I],
+    "dbm_gen_forward": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, ctypes.c_size_t, _P],
 }
+# entry points that return a value instead of a status
+RESTYPES = {"dbm_launch_count": _L, "dbm_gen_count_params": _L, "dbm_gen_num_arrays": _I, "dbm_gen_workspace_bytes": ctypes.c_size_t}
 
 _lib: Optional[ctypes.CDLL] = None
 launch_count = 0  # number of library calls that enqueue kernels (bench.py reports it)
@@ -103,9 +118,14 @@ def load() -> ctypes.CDLL:
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.argtypes = args
-        fn.restype = ctypes.c_int
+        fn.restype = RESTYPES.get(name, ctypes.c_int)
     _lib = lib
     return lib
+
+
+def kernel_launches() -> int:
+    """Kernels launched by the library so far (counted inside the library, one per launch)."""
+    return int(load().dbm_launch_count())
 
 
 def call(name: str, *args) -> None:

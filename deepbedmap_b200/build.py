@@ -14,7 +14,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libdeepbedmap_b200.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 
-SOURCES = ["ops.cu", "gemm_f32.cu", "gemm_bf16.cu", "umma_conv3x3.cu", "umma_trunk.cu", "umma_flat.cu", "umma_local.cu", "umma_deform.cu", "stem.cu", "deform_f32.cu", "train_ops.cu", "debug_bench.cu"]
+SOURCES = ["ops.cu", "gemm_f32.cu", "gemm_bf16.cu", "umma_conv3x3.cu", "umma_trunk.cu", "umma_flat.cu", "umma_local.cu", "umma_deform.cu", "stem.cu", "deform_f32.cu", "train_ops.cu", "debug_bench.cu", "gen_api.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 

@@ -15,7 +15,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long g_launches = 0;   // kernels launched by this library since it was loaded (every launch ends in check_launch)
+
 int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s launch failed: %s", what, cudaGetErrorString(e));
@@ -269,7 +272,8 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const long* __
 using namespace dbm;
 
 extern "C" const char* dbm_last_error(void) { return g_err; }
-extern "C" int dbm_version(void) { return 100; }
+extern "C" int dbm_version(void) { return 200; }
+extern "C" long dbm_launch_count(void) { return g_launches; }
 
 extern "C" int dbm_nchw_to_slab8(const float* src, long src_batch_stride, void* dst, int n, int c, int h, int w,
                                  int dst_cs_total, int dst_cs0, cudaStream_t st) {

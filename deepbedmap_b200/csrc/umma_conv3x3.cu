@@ -321,13 +321,6 @@ __global__ void pack_w3x3_slice_kernel(const float* __restrict__ w, __nv_bfloat1
 // Table-driven form: one launch re-packs every filter of a model (blockIdx.y = table entry). The
 // training step re-packs the generator's ~600 operand images after every Adam update; one launch
 // instead of ~1200 keeps that off the critical path.
-struct PackEntry {  // 48 bytes, mirrored by deepbedmap_b200/model.py (PACK_ENTRY_DTYPE)
-  const float* w;
-  __nv_bfloat16* out;
-  int O, o0, Cin, CinTotal, c0, COUTP, CK, mode;  // mode: see pack_w3x3_table_kernel
-};
-static_assert(sizeof(PackEntry) == 48, "PackEntry layout is part of the C ABI");
-
 __global__ void pack_w3x3_table_kernel(const PackEntry* __restrict__ table) {
   const PackEntry e = table[blockIdx.y];
   if (e.mode == 0 && (e.O & 7) == 0 && (e.o0 & 7) == 0) {

@@ -53,33 +53,6 @@ __device__ __forceinline__ void issue_stage_wide(uint32_t d0, uint32_t a_lo, uin
   }
 }
 
-// One MMA pass: out[:, 0:cout] = conv3x3(in[:, 8*in_cs0 : 8*in_cs0 + cin]) with the packed filter.
-// mode 0: a layer of its own: all `cout` columns take the fused epilogue (bias, residuals, LeakyReLU, stores).
-// Dense-block pairing (see model.py): conv_k and the partial sums of conv_{k+1} over their shared inputs are ONE
-// N = 64 pass (mode 1, "head"): columns [0, 32) = conv_k take the epilogue, columns [32, 64) -- a partial
-// pre-activation of conv_{k+1} -- STAY IN TENSOR MEMORY; the next table entry (mode 2, "tail") contracts only a_k
-// (K = 32 * 9, N = 32) and accumulates onto those very columns, then takes the epilogue of conv_{k+1}. Head and tail
-// of a unit run on the same CTA (see the schedule below), so the partial sums never leave the SM: no fp32 stash in
-// HBM (round 1 wrote and re-read 128 B per pixel per pair), and the tail's epilogue has nothing to load.
-struct TrunkLayer {  // 128 bytes, mirrored by deepbedmap_b200/model.py (TRUNK_LAYER_DTYPE)
-  const __nv_bfloat16* wpacked;
-  const float* bias;
-  __nv_bfloat16* out_bf16;
-  float* out_f32;      // slab8f (fp32 [N][8][H][W][8]), 64 channels
-  const float* res1;   // slab8f, 4 * res1_cs_total channels
-  const float* res2;   // slab8f, 64 channels
-  float* stash_out;    // slab8f, cout - cout_main channels
-  int cin, cout;       // cout (MMA N) in {32, 64}
-  int in_map, in_cs0;  // in_map: 0 = stem output (16 slabs), 1 / 2 = dense-block buffers
-  int act, up2;
-  int out_cs_total, out_cs0;
-  int cout_main, res1_cs_total;
-  float beta;
-  int mode;            // 0 single pass, 1 pair head, 2 pair tail (must directly follow its head)
-  int pad[6];
-};
-static_assert(sizeof(TrunkLayer) == 128, "TrunkLayer layout is part of the C ABI");
-
 extern int g_trunk_debug;
 extern unsigned long long* g_trunk_prof;
 

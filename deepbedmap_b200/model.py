@@ -187,6 +187,11 @@ class GeneratorModel(_Link):
         self.fuse_out_projection = False
         # conv_on_W1 (k30 s10) as a split-bf16 tcgen05 GEMM over the 10x10 space-to-depth (False: fp32 CUDA cores)
         self.stem_w1_tensor_core = True
+        # tiled tensor-core inference through the model-level C entry points (dbm_gen_forward, csrc/gen_api.cu): the
+        # pass / pack tables and the workspace layout are built in C++; False (or any A/B switch above off its
+        # default): the same kernels composed call by call from this file
+        self.c_model_api = True
+        self._cgen, self._cgen_version, self._cgen_ws = None, -1, {}
         self._ctx = None
 
     # ---- serialisation (chainer.serializers.load_npz / save_npz, App. C layout) ----
@@ -763,6 +768,51 @@ class GeneratorModel(_Link):
             self._ws[key] = ws
         return ws
 
+    def _c_forward_applies(self):
+        return (self.c_model_api and self.persistent_trunk and self.paired_trunk and not self.per_layer_ck16
+                and self.stem_w1_tensor_core and not self.fuse_out_projection and self.inter_channels == 32
+                and self.out_channels == 1)
+
+    def _forward_c_api(self, x, w1, w2, w3):
+        """GeneratorModel.forward through dbm_gen_forward: this class only owns the flat parameter buffer (bound into
+        the handle) and the workspace allocation."""
+        import ctypes
+        n, _, h, w = x.shape
+        if self._cgen is None or self._cgen[1] != self.residual_scaling:
+            self._c_release()
+            hnd = ctypes.c_void_p()
+            ops.call("dbm_gen_create", self.num_residual_blocks, float(self.residual_scaling), self.inter_channels,
+                     ctypes.byref(hnd))
+            ops.call("dbm_gen_bind_params", hnd, self.flat.data_ptr())
+            self._cgen, self._cgen_version = (hnd, self.residual_scaling), -1
+        hnd = self._cgen[0]
+        if self._cgen_version != self.version:
+            ops.call("dbm_gen_mark_updated", hnd)
+            self._cgen_version = self.version
+        ws = self._cgen_ws.get((n, h, w))
+        if ws is None:
+            from . import _lib
+            nbytes = int(_lib.load().dbm_gen_workspace_bytes(hnd, n, h, w))
+            buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device="cuda")
+            ptr = (buf.data_ptr() + 1023) & ~1023
+            ws = self._cgen_ws[(n, h, w)] = (buf, ptr, nbytes)
+        y = ops.empty(n, 1, 4 * (h - 2), 4 * (w - 2))
+        ops.call("dbm_gen_forward", hnd, x.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), n, h, w,
+                 y.data_ptr(), ws[1], ws[2], ops.stream())
+        return y
+
+    def _c_release(self):
+        if getattr(self, "_cgen", None) is not None:
+            try:
+                torch.cuda.synchronize()
+                ops.call("dbm_gen_destroy", self._cgen[0])
+            except Exception:
+                pass
+            self._cgen, self._cgen_ws = None, {}
+
+    def __del__(self):
+        self._c_release()
+
     def _forward_bf16(self, x, w1, w2, w3):
         from . import flat
         P = self.p
@@ -770,6 +820,8 @@ class GeneratorModel(_Link):
         H, W = h - 2, w - 2
         bf = torch.bfloat16
         local = self.local_trunk and self.inter_channels == 32 and flat.local_trunk_fits(H, W)
+        if not local and self._c_forward_applies():
+            return self._forward_c_api(x, w1, w2, w3)
         pk = self._pack(self.PACK_INFER_LOCAL if local else self.PACK_INFER)
         wt1, wts, bias128 = pk["stem"]
         if local:

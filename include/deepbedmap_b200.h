@@ -39,6 +39,7 @@ typedef struct CUstream_st* cudaStream_t;
 #define DBM_ERR_CUDA (-2)
 
 int dbm_version(void);
+long dbm_launch_count(void); /* kernels this library has launched since it was loaded (bench.py reports the difference) */
 const char* dbm_last_error(void);
 int dbm_debug_set(int key, int value);
 int dbm_debug_set_ptr(int key, void* device_ptr); /* tuning only: 1 = trunk-kernel cycle counters */
@@ -304,6 +305,33 @@ int dbm_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pi
  * dst[j, :] = src[index[j], :] for j < nrows; rows of `row` floats; index = int64 on the device. */
 int dbm_gather_rows_f32(const float* src, long src_rows, const long* index_dev, float* dst, long row, int nrows,
                         cudaStream_t stream);
+
+/* ---- model-level entry points: GeneratorModel (srgan_train.py:421-576) without the Python shim ------------
+ * A host in any language runs the generator's inference forward with
+ *     dbm_gen_create -> dbm_gen_set_param (every array of the Chainer .npz, keys of SURVEY App. C:
+ *     dbm_gen_array_info lists them in file order) -> dbm_gen_workspace_bytes -> dbm_gen_forward.
+ * The handle owns the fp32 master weights (device; or views a caller-owned flat device buffer of
+ * dbm_gen_count_params floats in App. C order, dbm_gen_bind_params), their re-packed bf16 UMMA operand images and
+ * the pass table of the persistent trunk kernel -- the only device memory this library ever allocates. Activations
+ * live in the caller's `workspace` (device, 1024-byte aligned, dbm_gen_workspace_bytes(n, h, w) bytes); everything is
+ * enqueued on `stream`. Arithmetic: the tensor-core inference path (bf16 operands, fp32 accumulation, fp32 residual
+ * stream; conv_on_W1 as a split-bf16 GEMM), inter_channels == 32 and out_channels == 1 as in the reference.
+ *   x (n,1,h,w), w1 (n,1,10h,10w), w2 (n,2,2h,2w), w3 (n,1,h,w) fp32 NCHW device -> y_out (n,1,4(h-2),4(w-2)).
+ * A handle is bound to the device current at creation and is not thread-safe (one host thread per GPU, as the
+ * reference's one process per GPU, srgan_train.py:58-61). The first forward on a new (workspace, shape) uploads the
+ * pass table and synchronises the stream once; later calls only enqueue (CUDA-graph capturable). */
+typedef struct dbm_gen dbm_gen;
+int dbm_gen_create(int num_residual_blocks, float residual_scaling, int inter_channels, dbm_gen** out);
+int dbm_gen_destroy(dbm_gen* gen);
+long dbm_gen_count_params(const dbm_gen* gen);              /* 8 907 749 for 12 blocks (srgan_train.py:446-447) */
+int dbm_gen_num_arrays(const dbm_gen* gen);                 /* 384 for 12 blocks */
+int dbm_gen_array_info(const dbm_gen* gen, int index, const char** key, int* ndim, int* dims4, long* flat_offset);
+int dbm_gen_set_param(dbm_gen* gen, const char* key, const float* host_values, int ndim, const int* dims);
+int dbm_gen_bind_params(dbm_gen* gen, float* device_flat);
+int dbm_gen_mark_updated(dbm_gen* gen);                     /* after writing into a bound parameter buffer */
+size_t dbm_gen_workspace_bytes(const dbm_gen* gen, int n, int h, int w);
+int dbm_gen_forward(dbm_gen* gen, const float* x, const float* w1, const float* w2, const float* w3, int n, int h,
+                    int w, float* y_out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 #ifdef __cplusplus
 }
