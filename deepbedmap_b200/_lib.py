@@ -61,6 +61,7 @@ SIGNATURES = {
     "dbm_conv3x3_umma_valid": [_P, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _P],
     "dbm_stem_fwd_flat": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dbm_deform_conv_umma": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P],
+    "dbm_deform_conv_umma_nchw": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     "dbm_deform_out1_sample": [_P, _P, _I, _P, _P, _I, _I, _I, _P],
     "dbm_deform_conv_out1": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P],
     "dbm_conv3x3_umma": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P, _P],

@@ -321,69 +321,97 @@ __global__ void pack_w3x3_slice_kernel(const float* __restrict__ w, __nv_bfloat1
 // Table-driven form: one launch re-packs every filter of a model (blockIdx.y = table entry). The
 // training step re-packs the generator's ~600 operand images after every Adam update; one launch
 // instead of ~1200 keeps that off the critical path.
+// One thread produces one 16-byte vector (8 consecutive GEMM-K indices c8 of one output row): an eighth of the index
+// arithmetic and of the store instructions of the element-per-thread form, which cost the training step 0.38 ms per
+// weight update (five launches re-packing ~34 M bf16 values, bound by integer division, not by memory).
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)[8]) {
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 t1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]);
+  __nv_bfloat162 t3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&t0);
+  o.y = *reinterpret_cast<uint32_t*>(&t1);
+  o.z = *reinterpret_cast<uint32_t*>(&t2);
+  o.w = *reinterpret_cast<uint32_t*>(&t3);
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+
 __global__ void pack_w3x3_table_kernel(const PackEntry* __restrict__ table) {
   const PackEntry e = table[blockIdx.y];
   if (e.mode == 0 && (e.O & 7) == 0 && (e.o0 & 7) == 0) {
     // stacked forward slices (pair / tail / input-stationary images): visit only this entry's own rows -- the general
     // loop below scans the whole image for every entry that writes into it
     const int og = e.O / 8;
-    const long total = (long)9 * e.Cin * e.O;
+    const long total = (long)9 * (e.Cin / 8) * e.O;   // vectors
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
       long t = i;
-      const int c8 = t % 8; t /= 8;
       const int o8 = t % 8; t /= 8;
       const int cgl = t % og; t /= og;
       const int ksl = t % (e.CK / 8); t /= (e.CK / 8);
       const int tap = t % 9; t /= 9;
       const int kc = (int)t;
       const int o = cgl * 8 + o8;
-      const int c = kc * e.CK + ksl * 8 + c8;
-      const long dst = ((((long)(kc * 9 + tap) * (e.CK / 8) + ksl) * (e.COUTP / 8) + (e.o0 / 8 + cgl)) * 8 + o8) * 8 + c8;
-      e.out[dst] = __float2bfloat16_rn(e.w[((long)o * e.CinTotal + e.c0 + c) * 9 + tap]);
+      const int c = kc * e.CK + ksl * 8;
+      const long dst = ((((long)(kc * 9 + tap) * (e.CK / 8) + ksl) * (e.COUTP / 8) + (e.o0 / 8 + cgl)) * 8 + o8) * 8;
+      const float* src = e.w + ((long)o * e.CinTotal + e.c0 + c) * 9 + tap;
+      float v[8];
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) v[c8] = src[c8 * 9];
+      store8_bf16(e.out + dst, v);
     }
     return;
   }
-  const long total = (long)9 * e.Cin * e.COUTP;
+  const long total = (long)9 * (e.Cin / 8) * e.COUTP;   // vectors: element index = vector * 8 + c8
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long t = i;
-    const int c8 = t % 8; t /= 8;
     const int o8 = t % 8; t /= 8;
     const int cg = t % (e.COUTP / 8); t /= (e.COUTP / 8);
     const int ksl = t % (e.CK / 8); t /= (e.CK / 8);
     const int tap = t % 9; t /= 9;
     const int kc = (int)t;
     const int on = cg * 8 + o8;                 // GEMM N index (row of the operand image)
-    const int c = kc * e.CK + ksl * 8 + c8;     // GEMM K index
+    const int cb = kc * e.CK + ksl * 8;         // GEMM K index of element 0 of the vector
+    float v[8];
     if (e.mode == 0) {
       // forward operand; rows [o0, o0 + O) <- w[o][c0 + c][tap], other rows untouched (stacked filters)
       const int o = on - e.o0;
-      if (o >= 0 && o < e.O) e.out[i] = __float2bfloat16_rn(e.w[((long)o * e.CinTotal + e.c0 + c) * 9 + tap]);
+      if (o < 0 || o >= e.O) continue;
+      const float* src = e.w + ((long)o * e.CinTotal + e.c0 + cb) * 9 + tap;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) v[c8] = src[c8 * 9];
+      store8_bf16(e.out + i * 8, v);
       continue;
     }
     // modes 1-3 write the whole image. o0 = number of REAL filter output channels along the padded
     // output-channel axis (0 = all): the remaining rows / K-lines are zero.
-    float v = 0.f;
-    if (e.mode == 1) {
-      // data-gradient operand of a 3x3 filter w (Oreal, CinTotal, 3, 3): N index = input channel c0 + on,
-      // K index c = output channel, taps flipped
-      const int kvalid = e.o0 > 0 ? e.o0 : e.Cin;
-      if (on < e.O && c < kvalid) v = e.w[((long)c * e.CinTotal + e.c0 + on) * 9 + (8 - tap)];
-    } else {
-      // 4x4 stride-2 pad-1 filter w4 (Oreal, C, 4, 4), C = CinTotal, embedded as a 3x3 stride-1 filter over the four
-      // space-to-depth phases (channel = phase * C + cc): tap (ty, tx) of phase (py, px) is
-      // w4[.., 2(ty-1)+py+1, 2(tx-1)+px+1] when that index exists, else 0.
-      // mode 2: forward operand (N = output channel on, K = phase channel c; the w pointer is pre-offset per
-      // output chunk); mode 3: data-gradient operand (N = phase channel c0 + on, K = output channel c, taps flipped).
-      const int oc = e.mode == 2 ? on : c;             // filter output channel
-      const int pc = e.mode == 2 ? c : e.c0 + on;      // phase channel
-      const int ovalid = e.o0 > 0 ? e.o0 : (e.mode == 2 ? e.O : e.Cin);
-      const int t3 = e.mode == 2 ? tap : 8 - tap;
-      const int ph = pc / e.CinTotal, cc = pc - ph * e.CinTotal;
-      const int ky = 2 * (t3 / 3 - 1) + (ph >> 1) + 1, kx = 2 * (t3 % 3 - 1) + (ph & 1) + 1;
-      if (on < e.O && oc < ovalid && ph < 4 && ky >= 0 && ky <= 3 && kx >= 0 && kx <= 3)
-        v = e.w[(((long)oc * e.CinTotal + cc) * 4 + ky) * 4 + kx];
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+      const int c = cb + c8;
+      float x = 0.f;
+      if (e.mode == 1) {
+        // data-gradient operand of a 3x3 filter w (Oreal, CinTotal, 3, 3): N index = input channel c0 + on,
+        // K index c = output channel, taps flipped
+        const int kvalid = e.o0 > 0 ? e.o0 : e.Cin;
+        if (on < e.O && c < kvalid) x = e.w[((long)c * e.CinTotal + e.c0 + on) * 9 + (8 - tap)];
+      } else {
+        // 4x4 stride-2 pad-1 filter w4 (Oreal, C, 4, 4), C = CinTotal, embedded as a 3x3 stride-1 filter over the four
+        // space-to-depth phases (channel = phase * C + cc): tap (ty, tx) of phase (py, px) is
+        // w4[.., 2(ty-1)+py+1, 2(tx-1)+px+1] when that index exists, else 0.
+        // mode 2: forward operand (N = output channel on, K = phase channel c; the w pointer is pre-offset per
+        // output chunk); mode 3: data-gradient operand (N = phase channel c0 + on, K = output channel c, taps flipped).
+        const int oc = e.mode == 2 ? on : c;             // filter output channel
+        const int pc = e.mode == 2 ? c : e.c0 + on;      // phase channel
+        const int ovalid = e.o0 > 0 ? e.o0 : (e.mode == 2 ? e.O : e.Cin);
+        const int t3 = e.mode == 2 ? tap : 8 - tap;
+        const int ph = pc / e.CinTotal, cc = pc - ph * e.CinTotal;
+        const int ky = 2 * (t3 / 3 - 1) + (ph >> 1) + 1, kx = 2 * (t3 % 3 - 1) + (ph & 1) + 1;
+        if (on < e.O && oc < ovalid && ph < 4 && ky >= 0 && ky <= 3 && kx >= 0 && kx <= 3)
+          x = e.w[(((long)oc * e.CinTotal + cc) * 4 + ky) * 4 + kx];
+      }
+      v[c8] = x;
     }
-    e.out[i] = __float2bfloat16_rn(v);
+    store8_bf16(e.out + i * 8, v);
   }
 }
 
@@ -449,8 +477,9 @@ extern "C" int dbm_pack_conv3x3_table(const void* table_dev, int num_entries, lo
   DBM_REQUIRE(num_entries > 0 && num_entries <= 65535 && max_elements > 0, "pack table: bad size (%d entries)",
               num_entries);
   DBM_REQUIRE(((uintptr_t)table_dev & 7) == 0, "pack table: unaligned");
-  int gx = ceil_div(max_elements, 256 * 4);
+  int gx = ceil_div(max_elements / 8, 256 * 2);   // one thread per 8-element vector, ~2 vectors per thread
   if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
   pack_w3x3_table_kernel<<<dim3(gx, num_entries), 256, 0, stream>>>((const PackEntry*)table_dev);
   return check_launch("pack_w3x3_table_kernel");
 }

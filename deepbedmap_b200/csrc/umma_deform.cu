@@ -30,6 +30,8 @@ struct DeformParams {
   const __nv_bfloat16* x;       // slab8 [N][8][H][W][8]
   const float* off;             // slab4 [N][off_cs][H][W][4], channels 0..17 used
   int off_cs;
+  const float* off_nchw;        // alternative (training path): offsets as fp32 NCHW (N,18,H,W); `off` is then unused
+  float* out_nchw;              // alternative (training path): fp32 NCHW (N,64,H,W) output, no bf16 rounding; `out` unused
   const __nv_bfloat16* wpacked; // [9][8][8][8][8]
   const float* bias;
   int act;
@@ -175,8 +177,14 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const int tap = slot + 3 * k;
-          odx[k] = __ldg(p.off + ((((size_t)n * p.off_cs + (tap >> 2)) * p.H + y) * p.W + x) * 4 + (tap & 3));
-          ody[k] = __ldg(p.off + ((((size_t)n * p.off_cs + ((9 + tap) >> 2)) * p.H + y) * p.W + x) * 4 + ((9 + tap) & 3));
+          if (p.off_nchw != nullptr) {
+            const size_t hw = (size_t)p.H * p.W, at = (size_t)y * p.W + x;
+            odx[k] = __ldg(p.off_nchw + ((size_t)n * 18 + tap) * hw + at);
+            ody[k] = __ldg(p.off_nchw + ((size_t)n * 18 + 9 + tap) * hw + at);
+          } else {
+            odx[k] = __ldg(p.off + ((((size_t)n * p.off_cs + (tap >> 2)) * p.H + y) * p.W + x) * 4 + (tap & 3));
+            ody[k] = __ldg(p.off + ((((size_t)n * p.off_cs + ((9 + tap) >> 2)) * p.H + y) * p.W + x) * 4 + ((9 + tap) & 3));
+          }
         }
       }
       const __nv_bfloat16* xin = p.x + (size_t)n * 8 * plane;
@@ -287,6 +295,13 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
             for (int i = 0; i < 8; ++i) {
               v[i] = __uint_as_float(acc[8 * s8 + i]) + __ldg(p.bias + c0 + 8 * s8 + i);
               if (p.act) v[i] = lrelu(v[i]);
+            }
+            if (!PROJ && p.out_nchw != nullptr) {   // consecutive lanes = consecutive x: 128-byte rows per channel
+              const size_t hw = (size_t)p.H * p.W;
+              float* op = p.out_nchw + ((size_t)n * 64 + c0 + 8 * s8) * hw + (size_t)y * p.W + x;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) op[(size_t)i * hw] = v[i];
+              continue;
             }
             const size_t cs = (size_t)n * p.out_cs_total + (p.out_cs0 + c0 / 8 + s8);
             const uint4 o = pack8(v);
@@ -420,9 +435,40 @@ extern "C" int dbm_deform_conv_umma(const void* x_slab8, const float* offset_sla
   p.wpacked = (const __nv_bfloat16*)wpacked_ck64; p.bias = bias; p.act = act;
   p.out = (__nv_bfloat16*)out_slab8; p.out_cs_total = out_cs_total; p.out_cs0 = out_cs0;
   p.proj_w = next_out1_filter; p.proj_out = next_out1_proj;
+  p.off_nchw = nullptr; p.out_nchw = nullptr;
   const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
   if (p.proj_w != nullptr) deform_umma_kernel<true><<<grid, kDThreads, kDSmem, stream>>>(p);
   else deform_umma_kernel<false><<<grid, kDThreads, kDSmem, stream>>>(p);
+  return check_launch("deform_umma_kernel");
+}
+
+// Training-path form of the same kernel (forward of final_conv_layer1 in GeneratorModel.forward_train): offsets read as
+// the fp32 NCHW (N,18,H,W) tensor the offset convolution produced, output written as fp32 NCHW (N,64,H,W) without the
+// bf16 storage rounding. Same arithmetic as the sampler + bf16 GEMM pair it replaces (bilinear samples and filter
+// rounded to bf16, fp32 accumulation), without the 382 MB `cols` round trip through HBM.
+extern "C" int dbm_deform_conv_umma_nchw(const void* x_slab8, const float* offset_nchw18, const void* wpacked_ck64,
+                                         const float* bias, int n, int h, int w, int act, float* out_nchw,
+                                         cudaStream_t stream) {
+  DBM_REQUIRE(n > 0 && h > 0 && w > 0, "deform_conv_umma_nchw: empty input");
+  DBM_REQUIRE(x_slab8 && offset_nchw18 && wpacked_ck64 && bias && out_nchw, "deform_conv_umma_nchw: null pointer");
+  DBM_REQUIRE(((uintptr_t)x_slab8 & 15) == 0 && ((uintptr_t)wpacked_ck64 & 15) == 0,
+              "deform_conv_umma_nchw: unaligned pointer");
+  static bool attr_done = false;
+  if (!attr_done) {
+    DBM_CUDA(cudaFuncSetAttribute(deform_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
+    attr_done = true;
+  }
+  DeformParams p;
+  p.N = n; p.H = h; p.W = w;
+  p.tiles_x = ceil_div(w, kDTileW); p.tiles_y = ceil_div(h, kDTileH);
+  p.num_items = n * p.tiles_x * p.tiles_y;
+  p.x = (const __nv_bfloat16*)x_slab8; p.off = nullptr; p.off_cs = 0;
+  p.wpacked = (const __nv_bfloat16*)wpacked_ck64; p.bias = bias; p.act = act;
+  p.out = nullptr; p.out_cs_total = 0; p.out_cs0 = 0;
+  p.proj_w = nullptr; p.proj_out = nullptr;
+  p.off_nchw = offset_nchw18; p.out_nchw = out_nchw;
+  const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
+  deform_umma_kernel<false><<<grid, kDThreads, kDSmem, stream>>>(p);
   return check_launch("deform_umma_kernel");
 }
 

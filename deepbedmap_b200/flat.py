@@ -605,17 +605,26 @@ class FlatConv:
                  self.gw_, st)
         return z
 
-    def backward(self, dz: torch.Tensor, slot: int = 0, need_dx: bool = True):
-        """dW += x (*) dz for the input kept in ``slot``; returns d(loss)/dx (n, C, H, W) or None."""
+    def backward(self, dz: torch.Tensor, slot: int = 0, need_dx: bool = True, wgrad_stream=None):
+        """dW += x (*) dz for the input kept in ``slot``; returns d(loss)/dx (n, C, H, W) or None.
+        ``wgrad_stream``: torch stream for the weight-gradient launches (nothing downstream in backward needs them: they
+        run beside the data-gradient chain; the CALLER joins that stream before using the gradients)."""
         im, n, st = self.im, self.n, ops.stream()
         ops.call("dbm_flat_from_nchw_ex", dz.data_ptr(), im.O, self.Ho, self.Wo, 0, self.gin.data_ptr(), None, 1.0, n,
                  self.gh, self.gw_, st)
+        if wgrad_stream is not None:
+            wgrad_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(wgrad_stream):
+                ws = ops.stream()
+                ops.call("dbm_flat_wgrad", self.units[slot].data_ptr(), self.n_units, n, self.gh, self.gw_, ws)
+                ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, ws)
         dx = None
         if need_dx:
             ops.call("dbm_flat_conv3x3_seq", self.rec_d.ctypes.data, 1, n, self.gh, self.gw_, 0, 0, st)
             dx = ops.empty(n, im.C, self.H, self.W)
             ops.call("dbm_flat_to_nchw_ex", self.dxf.data_ptr(), None, dx.data_ptr(), im.C, self.H, self.W, int(im.s2d), n,
                      self.gh, self.gw_, st)
-        ops.call("dbm_flat_wgrad", self.units[slot].data_ptr(), self.n_units, n, self.gh, self.gw_, st)
-        ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, st)
+        if wgrad_stream is None:
+            ops.call("dbm_flat_wgrad", self.units[slot].data_ptr(), self.n_units, n, self.gh, self.gw_, st)
+            ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, st)
         return dx

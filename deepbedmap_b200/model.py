@@ -192,6 +192,8 @@ class GeneratorModel(_Link):
         # default): the same kernels composed call by call from this file
         self.c_model_api = True
         self._cgen, self._cgen_version, self._cgen_ws = None, -1, {}
+        # training forward of the first deformable layer as one fused tcgen05 kernel (False: sampler + bf16 GEMM, cols kept)
+        self.fused_deform_forward = True
         self._ctx = None
 
     # ---- serialisation (chainer.serializers.load_npz / save_npz, App. C layout) ----
@@ -340,8 +342,15 @@ class GeneratorModel(_Link):
         u2 = ops.upsample2_fwd(c1)
         c2 = conv("post_upsample_conv_layer_2", u2, True)
         off1 = conv("final_conv_layer1/offset_conv", c2, False)
-        d1, cols1 = ops.deform_conv_fwd(c2, off1, P["final_conv_layer1/deform_conv/W"],
-                                        P["final_conv_layer1/deform_conv/b"], act=True, tc=tc is not None)
+        if tc is not None and self.fused_deform_forward:
+            # gather + tcgen05 contraction + bias + LeakyReLU in one kernel; backward re-samples (no 382 MB cols buffer
+            # on the forward's critical path)
+            wq, _ = self._packed["final_conv_layer1/deform_conv"]
+            d1 = ops.deform_conv_fwd_fused(c2, off1, wq, P["final_conv_layer1/deform_conv/b"], act=True)
+            cols1 = None
+        else:
+            d1, cols1 = ops.deform_conv_fwd(c2, off1, P["final_conv_layer1/deform_conv/W"],
+                                            P["final_conv_layer1/deform_conv/b"], act=True, tc=tc is not None)
         off2 = conv("final_conv_layer2/offset_conv", d1, False)
         if self.out_channels == 1:   # tap projection: 9 projected planes instead of a 576-row cols buffer
             y, cols2 = ops.deform1_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"],
@@ -399,9 +408,12 @@ class GeneratorModel(_Link):
             """dW, db of a plain 3x3 conv of the head and its data gradient (added to ``dx_accumulate_into``
             or returned)."""
             if tc is not None:
-                ops.call("dbm_bias_grad_f32", dz.data_ptr(), dz.shape[1] * dz.shape[2] * dz.shape[3],
-                         G[f"{key}/b"].data_ptr(), n, dz.shape[1], dz.shape[2] * dz.shape[3], ops.stream())
-                dx = tc[key].backward(dz)
+                aux = ops._aux_stream()
+                aux.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(aux):   # bias / weight gradients beside the data-gradient chain
+                    ops.call("dbm_bias_grad_f32", dz.data_ptr(), dz.shape[1] * dz.shape[2] * dz.shape[3],
+                             G[f"{key}/b"].data_ptr(), n, dz.shape[1], dz.shape[2] * dz.shape[3], ops.stream())
+                dx = tc[key].backward(dz, wgrad_stream=aux)
                 if dx_accumulate_into is None:
                     return dx
                 ops.axpby(dx, 0, dx_accumulate_into, 0, dx_accumulate_into, 0, 64, 1.0, 1.0)
@@ -426,7 +438,8 @@ class GeneratorModel(_Link):
         ops.lrelu_bwd(dd1, 0, c["d1"], 0, dd1, 0, 64)
         # ---- final_conv_layer1 ----
         dc2 = ops.zeros(n, 64, 4 * H, 4 * W)
-        doff1 = ops.deform_conv_bwd(c["c2"], c["off1"], P["final_conv_layer1/deform_conv/W"], c["cols1"], dd1,
+        cols1 = c["cols1"] if c["cols1"] is not None else ops.deform_sample(c["c2"], c["off1"])
+        doff1 = ops.deform_conv_bwd(c["c2"], c["off1"], P["final_conv_layer1/deform_conv/W"], cols1, dd1,
                                     G["final_conv_layer1/deform_conv/W"], G["final_conv_layer1/deform_conv/b"], dc2,
                                     tc=c.get("head_tc") is not None)
         conv_bwd("final_conv_layer1/offset_conv", c["c2"], doff1, dx_accumulate_into=dc2)
@@ -445,12 +458,14 @@ class GeneratorModel(_Link):
             # Three gradient buckets, each handed on the moment it is final so that a data-parallel caller's
             # all-reduce (GradBucketReducer: the comm stream waits for the stream current at the hand-over) runs
             # under what is still to come:
-            #   head  (upsample + deformable layers): final here, reduced under the whole trunk backward;
+            #   head  (upsample + deformable layers): its weight / bias gradients were launched on ``aux`` beside the
+            #         data-gradient chain; handed over on that stream, reduced under the whole trunk backward;
             #   trunk (pre-residual conv .. post-residual conv): one batched launch + reduction on the side stream
             #         ``aux`` beside the stem's backward, handed over ON that stream;
             #   stem  (input_block): after the stem's weight gradients on the main stream.
-            ready("post_upsample_conv_layer", "final_conv_layer")
             cur, aux = torch.cuda.current_stream(), ops._aux_stream()
+            with torch.cuda.stream(aux):
+                ready("post_upsample_conv_layer", "final_conv_layer")
             da0 = c["flat"].backward(da3, wgrad_stream=aux)
             with torch.cuda.stream(aux):
                 ready("pre_residual_conv_layer", "residual_network/", "post_residual_conv_layer")
@@ -520,10 +535,10 @@ class GeneratorModel(_Link):
 
     # ---------------- bf16 tensor-core path (inference) ----------------
     # groups of packed operand images (a training step must not pay for the inference-only ones)
-    PACK_INFER = ("io", "trunk16", "infer")                 # tiled / persistent tensor-core inference
-    PACK_INFER_LOCAL = ("io", "stat", "infer")              # inference on tiles that fit the image-resident kernel
-    PACK_TRAIN_LOCAL = ("io", "stat", "dgrad")              # training, image-resident trunk
-    PACK_TRAIN_CHAIN = ("io", "trunk16", "stat", "dgrad")   # training, flat chain (any tile size)
+    PACK_INFER = ("io", "trunk16", "infer", "deform")                 # tiled / persistent tensor-core inference
+    PACK_INFER_LOCAL = ("io", "stat", "infer", "deform")              # inference on tiles that fit the image-resident kernel
+    PACK_TRAIN_LOCAL = ("io", "stat", "dgrad", "deform")              # training, image-resident trunk
+    PACK_TRAIN_CHAIN = ("io", "trunk16", "stat", "dgrad", "deform")   # training, flat chain (any tile size)
 
     def _pack(self, groups=None):
         """bf16 UMMA operand images of every 3x3 filter (+ the stem's tap-major fp32 filters). The
@@ -533,13 +548,14 @@ class GeneratorModel(_Link):
           trunk16 dense-block convs in 16-channel chunks (persistent inference trunk, flat training chain)
           infer   32-channel-chunk images, pair/tail images, head convs, stem filters, padded biases
           stat    input-stationary slices (image-resident small-tile trunk)
-          dgrad   transposed + flipped filters (data gradients)"""
+          dgrad   transposed + flipped filters (data gradients)
+          deform  the first deformable layer's 64-channel-chunk image (inference and the fused training forward)"""
         if groups is None:
             groups = self.PACK_INFER
         P = self.p
         if self._pack_plan is None:
             pk = {}
-            entries = {g: [] for g in ("io", "trunk16", "infer", "stat", "dgrad")}
+            entries = {g: [] for g in ("io", "trunk16", "infer", "stat", "dgrad", "deform")}
             pad_biases = []   # (padded bias buffer, source bias)
 
             def image(cin, cout_padded):
@@ -548,7 +564,7 @@ class GeneratorModel(_Link):
             def entry(grp, w, out, o, o0, cin, cin_total, c0, coutp, ck, mode=0):
                 entries[grp].append((w.data_ptr(), out.data_ptr(), o, o0, cin, cin_total, c0, coutp, ck, mode))
 
-            def add(key, cout_padded, trunk=None, ck=32):
+            def add(key, cout_padded, trunk=None, ck=32, grp="infer"):
                 w, b = P[f"{key}/W"], P[f"{key}/b"]
                 o, cin = w.shape[0], w.shape[1]
                 if b.numel() < cout_padded:
@@ -557,7 +573,7 @@ class GeneratorModel(_Link):
                 else:
                     bp = b
                 img = image(cin, cout_padded)
-                entry("infer", w, img, o, 0, cin, cin, 0, cout_padded, ck)
+                entry(grp, w, img, o, 0, cin, cin, 0, cout_padded, ck)
                 pk[key] = (img, bp)
                 if trunk is not None:
                     # the trunk kernels stream every layer in 16-channel chunks
@@ -612,7 +628,7 @@ class GeneratorModel(_Link):
                 add(key, 64)
             add("final_conv_layer1/offset_conv", 32)
             add("final_conv_layer2/offset_conv", 32)
-            add("final_conv_layer1/deform_conv", 64, ck=64)
+            add("final_conv_layer1/deform_conv", 64, ck=64, grp="deform")
             # stem filters, tap-major, and the concatenated stem bias
             taps = {k: int(P[f"input_block/conv_on_{k}/W"][0].numel()) for k in ("X", "W1", "W2", "W3")}
             pk["stem"] = (ops.empty(taps["W1"], 32), ops.empty(taps["X"] + taps["W2"] + taps["W3"], 32), ops.empty(128))
@@ -1023,6 +1039,11 @@ class DiscriminatorModel(_Link):
         dflat = ops.empty(n, 512, 1, 1)
         ops.gemm(dl1, 100, 1, 0, P["linear_1/W"], 512, 1, 0, dflat, 512, 1, 0, None, n, 512, 100)
         dy = dflat
+        # The nine tensor-core weight gradients (+ their reductions) feed only the optimizer: they run on a side stream
+        # beside the BatchNorm / data-gradient chain -- ~100 us per layer off this model's critical path -- and are
+        # joined before each gradient bucket is handed on.
+        cur = torch.cuda.current_stream()
+        wg = ops._aux_stream2() if c.get("tc") is not None else None
         for i in range(9, 0, -1):
             cout, k, s = layout.DISC_CONVS[i]
             z, y = pres[i - 1], acts[i + 1]
@@ -1041,12 +1062,14 @@ class DiscriminatorModel(_Link):
             xin = acts[i]
             cin = xin.shape[1]
             if c.get("tc") is not None:
-                dx = c["tc"][i].backward(dz, c["slot"])
+                dx = c["tc"][i].backward(dz, c["slot"], wgrad_stream=wg)
             else:
                 ops.conv2d_bwd_weight(xin, 0, cin, dz, 0, G[f"conv_layer{i}/W"], k, s, 1)
                 dx = ops.empty(*xin.shape)
                 ops.conv2d_bwd_data(dz, 0, P[f"conv_layer{i}/W"], dx, 0, cin, k, s, 1)
             dy = dx
+            if i in (9, 5) and wg is not None:
+                cur.wait_stream(wg)
             if i == 9:
                 ready("linear_", "conv_layer9/", "batch_norm9/")
             elif i == 5:
@@ -1055,6 +1078,8 @@ class DiscriminatorModel(_Link):
         # conv_layer0 + LeakyReLU
         ops.lrelu_bwd(dy, 0, acts[1], 0, dy, 0, 64)
         ops.conv2d_bwd_weight(acts[0], 0, 1, dy, 0, G["conv_layer0/W"], 3, 1, 1, db=G["conv_layer0/b"])
+        if wg is not None:
+            cur.wait_stream(wg)
         ready("conv_layer0/", "conv_layer1/", "batch_norm1/", "conv_layer2/", "batch_norm2/", "conv_layer3/",
               "batch_norm3/", "conv_layer4/", "batch_norm4/")
         self._ctx = None

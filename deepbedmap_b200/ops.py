@@ -10,6 +10,15 @@ call = _lib.call
 
 
 _AUX = None
+_AUX2 = None
+
+
+def _aux_stream2():
+    """Second side stream (the discriminator's weight gradients; the generator's use _aux_stream)."""
+    global _AUX2
+    if _AUX2 is None:
+        _AUX2 = torch.cuda.Stream()
+    return _AUX2
 
 
 def _aux_stream():
@@ -208,6 +217,28 @@ def conv3x3_umma(inp, cin, wpacked, bias, cout_padded, *, beta=0.0, act=False, u
 
 
 # ---- deformable conv (fp32 path) -----------------------------------------------------------------
+def deform_sample(x, offset):
+    """Bilinear samples of every (channel, tap): cols (N, C*9, H*W) fp32 (the operand of the weight gradient)."""
+    n, c, h, wd = x.shape
+    cols = empty(n, c * 9, h * wd)
+    call("dbm_deform_sample_f32", x.data_ptr(), offset.data_ptr(), cols.data_ptr(), n, c, h, wd, stream())
+    return cols
+
+
+def deform_conv_fwd_fused(x, offset, wpacked_ck64, b, act=False):
+    """Forward of a 64 -> 64 deformable conv in one tcgen05 kernel (gather -> UMMA -> bias / LeakyReLU): x (N,64,H,W)
+    fp32, offset (N,18,H,W) fp32 -> y (N,64,H,W) fp32. Bilinear samples and filter are rounded to bf16 exactly as
+    deform_conv_fwd(tc=True) does; no cols buffer is produced (backward re-samples, deform_sample)."""
+    n, c, h, wd = x.shape
+    assert c == 64 and tuple(offset.shape) == (n, 18, h, wd)
+    x8 = empty(n, 8, h, wd, 8, dtype=torch.bfloat16)
+    nchw_to_slab8(x, x8)
+    y = empty(n, 64, h, wd)
+    call("dbm_deform_conv_umma_nchw", x8.data_ptr(), offset.data_ptr(), wpacked_ck64.data_ptr(), b.data_ptr(), n, h, wd,
+         int(act), y.data_ptr(), stream())
+    return y
+
+
 def deform_conv_fwd(x, offset, w, b, act=False, tc=False):
     """x (N,C,H,W), offset (N,18,H,W), w (O,C,3,3) -> y (N,O,H,W), cols (N, C*9, H*W) kept for backward.
     tc: the contraction on the tensor cores with bf16-rounded operands (bf16 training path)."""

@@ -228,6 +228,11 @@ int dbm_deform_conv_umma(const void* x_slab8, const float* offset_slab4, int off
                          const void* wpacked_ck64, const float* bias, int n, int h, int w, int act, void* out_slab8,
                          int out_cs_total, int out_cs0, const float* next_out1_filter, float* next_out1_proj,
                          cudaStream_t stream);
+/* Training-path form (forward of final_conv_layer1 under forward_train): offsets as the fp32 NCHW (n,18,h,w) tensor of
+ * the offset convolution, output fp32 NCHW (n,64,h,w) without bf16 storage rounding; same operand rounding as the
+ * sampler + bf16 GEMM pair it replaces, no `cols` buffer. */
+int dbm_deform_conv_umma_nchw(const void* x_slab8, const float* offset_nchw18, const void* wpacked_ck64,
+                              const float* bias, int n, int h, int w, int act, float* out_nchw, cudaStream_t stream);
 /* next_out1_filter / next_out1_proj (both or neither): the (1, 64, 3, 3) filter of a FOLLOWING single-output
  * deformable layer and a [n][9][h*w] buffer -- the layer's "tap projection" (see dbm_deform_conv_out1) is then
  * computed in this kernel's epilogue from the outputs in registers; finish that layer with dbm_deform_out1_sample. */
