@@ -97,7 +97,9 @@ def _aux_stream():
     """Side stream for work the step's critical path does not depend on (the metric-only discriminator pass)."""
     global _AUX_STREAM
     if _AUX_STREAM is None:
-        _AUX_STREAM = torch.cuda.Stream()
+        # high priority: the discriminator chain is ~150 small, dependent kernels; whenever one is ready it should get
+        # SMs ahead of the thousands of pending CTAs of the generator's big gather / GEMM kernels on the main stream
+        _AUX_STREAM = torch.cuda.Stream(priority=-1)
     return _AUX_STREAM
 
 
