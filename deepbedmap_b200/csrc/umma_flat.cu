@@ -781,8 +781,11 @@ static int set_flat_attr() {
 
 using namespace dbm;
 
+static int g_flat_sm_reserve = 0;   // SMs the persistent weight-gradient kernel leaves to concurrent streams
+
 extern "C" int dbm_flat_debug_set(int key, int value) {
   if (key == 1) g_flat_swap_wgrad = value;
+  if (key == 2) g_flat_sm_reserve = value < 0 ? 0 : value;
   return DBM_OK;
 }
 
@@ -880,7 +883,12 @@ extern "C" int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h
   rc = set_flat_attr();
   if (rc) return rc;
   DBM_REQUIRE(units_dev && num_units > 0, "flat_wgrad: empty unit table");
-  const int grid = num_units < num_sms() ? num_units : num_sms();
+  // The training step runs the discriminator's ~150 small dependent kernels on a high-priority stream beside this
+  // kernel; a persistent grid on every SM would stall that chain for the whole launch, so a few SMs can be left free
+  // (dbm_flat_debug_set(2, n): the units are dealt round-robin, results do not depend on the grid size)
+  int cap = num_sms() - g_flat_sm_reserve;
+  if (cap < 1) cap = 1;
+  const int grid = num_units < cap ? num_units : cap;
   flat_wgrad_kernel<<<grid, kFlatThreads, kFlatSmem, stream>>>((const WgradUnit*)units_dev, num_units, g,
                                                                 g_flat_swap_wgrad);
   return check_launch("flat_wgrad_kernel");

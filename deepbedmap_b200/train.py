@@ -91,6 +91,7 @@ class Adam:
 
 _COMM_STREAM = None
 _AUX_STREAM = None
+WGRAD_SM_RESERVE = 16
 
 
 def _aux_stream():
@@ -171,6 +172,8 @@ def compile_srgan_model(num_residual_blocks: int = 12, residual_scaling: float =
     """srgan_train.py:1014-1055: returns (g_model, g_optimizer, d_model, d_optimizer)."""
     g = GeneratorModel(num_residual_blocks=num_residual_blocks, residual_scaling=residual_scaling, seed=seed)
     d = DiscriminatorModel(seed=seed + 1)
+    # the generator's persistent weight-gradient kernel leaves a few SMs to the discriminator chain that runs beside it
+    ops.call("dbm_flat_debug_set", 2, WGRAD_SM_RESERVE)
     g_opt = Adam(alpha=learning_rate, eps=1e-8).setup(g)
     d_opt = Adam(alpha=learning_rate, eps=1e-8).setup(d)
     return g, g_opt, d, d_opt

@@ -151,7 +151,9 @@ int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, 
  *   gout; float* partial[9][32][128]; int blk0, nblk, nslab; pad} (struct WgradUnit);
  * dbm_flat_wgrad_reduce: 48-byte records {const float* partial; float* dw; long split_stride; int nsplit,
  *   cin_total, c0, o0, nch, mode}: dw[(o0+o)*cin_total + c0 + c][tap] += sum_s partial[s][tap][o][c];
- * dbm_flat_bias_grad: 16-byte records {const bf16* gout; float* db}: db[0:32] += sum_p gout[.][p]. */
+ * dbm_flat_bias_grad: 16-byte records {const bf16* gout; float* db}: db[0:32] += sum_p gout[.][p].
+ * dbm_flat_debug_set(2, n): the persistent weight-gradient kernel leaves n SMs to concurrently running streams (the
+ *   training step's discriminator chain); results do not depend on it. Key 1 is a tuning switch. */
 int dbm_flat_debug_set(int key, int value);
 int dbm_flat_geometry(int n, int h, int w, int* out5_host);
 int dbm_flat_conv3x3_seq(const void* launches_host, int count, int n, int h, int w, int out_h, int out_w,
