@@ -18,8 +18,7 @@ _P, _L, _I, _F = ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_float
 SIGNATURES = {
     "dbm_version": [],
     "dbm_launch_count": [],
-    "dbm_debug_set": [_I, _I],
-    "dbm_debug_set_ptr": [_I, _P],
+    "dbm_set_sm_reserve": [_I],
     "dbm_conv2d_fwd_f32": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dbm_conv2d_bwd_data_f32": [_P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dbm_conv2d_bwd_weight_f32": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -40,12 +39,10 @@ SIGNATURES = {
     "dbm_pack_conv3x3_weights_slice": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     "dbm_pack_conv3x3_table": [_P, _I, _L, _P],
     "dbm_trunk_umma": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P],
-    "dbm_flat_debug_set": [_I, _I],
     "dbm_flat_geometry": [_I, _I, _I, _P],
     "dbm_flat_conv3x3_seq": [_P, _I, _I, _I, _I, _I, _I, _P],
     "dbm_flat_conv3x3_chain": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "dbm_trunk_local_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
-    "dbm_local_debug_set": [_I],
     "dbm_trunk_local_bwd": [_P, _I, _I, _I, _I, _P, _P, _P],
     "dbm_flat_wgrad": [_P, _I, _I, _I, _I, _P],
     "dbm_flat_wgrad_reduce": [_P, _I, _P],
@@ -93,6 +90,13 @@ SIGNATURES = {
     "dbm_gen_workspace_bytes": [_P, _I, _I, _I],
     "dbm_gen_forward": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, ctypes.c_size_t, _P],
 }
+# tuning / A-B switches (include/deepbedmap_b200_tuning.h): exported by the same library, not part of the boundary
+TUNING_SIGNATURES = {
+    "dbm_debug_set": [_I, _I],
+    "dbm_debug_set_ptr": [_I, _P],
+    "dbm_flat_debug_set": [_I, _I],
+    "dbm_local_debug_set": [_I],
+}
 # entry points that return a value instead of a status
 RESTYPES = {"dbm_launch_count": _L, "dbm_gen_count_params": _L, "dbm_gen_num_arrays": _I, "dbm_gen_workspace_bytes": ctypes.c_size_t}
 
@@ -116,7 +120,7 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(LIB_PATH)
     lib.dbm_last_error.restype = ctypes.c_char_p
     lib.dbm_last_error.argtypes = []
-    for name, args in SIGNATURES.items():
+    for name, args in list(SIGNATURES.items()) + list(TUNING_SIGNATURES.items()):
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.argtypes = args
         fn.restype = RESTYPES.get(name, ctypes.c_int)

@@ -12,9 +12,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libdeepbedmap_b200.so")
+TUNING_LIB = os.path.join(HERE, "libdeepbedmap_b200_tuning.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 
-SOURCES = ["ops.cu", "gemm_f32.cu", "gemm_bf16.cu", "umma_conv3x3.cu", "umma_trunk.cu", "umma_flat.cu", "umma_local.cu", "umma_deform.cu", "stem.cu", "deform_f32.cu", "train_ops.cu", "debug_bench.cu", "gen_api.cu"]
+SOURCES = ["ops.cu", "gemm_f32.cu", "gemm_bf16.cu", "umma_conv3x3.cu", "umma_trunk.cu", "umma_flat.cu", "umma_local.cu", "umma_deform.cu", "stem.cu", "deform_f32.cu", "train_ops.cu", "gen_api.cu"]
+TUNING_SOURCES = ["debug_bench.cu"]   # libdeepbedmap_b200_tuning.so: microbenchmarks, never loaded by the product
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
@@ -62,6 +64,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
     subprocess.run(cmd, check=True)
+    for src in TUNING_SOURCES:   # links against the product library for the shared helpers (set_error, check_launch)
+        cmd = [nvcc, *NVCC_FLAGS, "-shared", "-I", INCLUDE, os.path.join(CSRC, src), "-o", TUNING_LIB, "-L", HERE,
+               "-ldeepbedmap_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+        subprocess.run(cmd, check=True)
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB

@@ -785,7 +785,12 @@ static int g_flat_sm_reserve = 0;   // SMs the persistent weight-gradient kernel
 
 extern "C" int dbm_flat_debug_set(int key, int value) {
   if (key == 1) g_flat_swap_wgrad = value;
-  if (key == 2) g_flat_sm_reserve = value < 0 ? 0 : value;
+  return DBM_OK;
+}
+
+extern "C" int dbm_set_sm_reserve(int n) {
+  DBM_REQUIRE(n >= 0 && n < num_sms(), "set_sm_reserve: %d of %d SMs", n, num_sms());
+  g_flat_sm_reserve = n;
   return DBM_OK;
 }
 
@@ -885,7 +890,7 @@ extern "C" int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h
   DBM_REQUIRE(units_dev && num_units > 0, "flat_wgrad: empty unit table");
   // The training step runs the discriminator's ~150 small dependent kernels on a high-priority stream beside this
   // kernel; a persistent grid on every SM would stall that chain for the whole launch, so a few SMs can be left free
-  // (dbm_flat_debug_set(2, n): the units are dealt round-robin, results do not depend on the grid size)
+  // (dbm_set_sm_reserve(n): the units are dealt round-robin, results do not depend on the grid size)
   int cap = num_sms() - g_flat_sm_reserve;
   if (cap < 1) cap = 1;
   const int grid = num_units < cap ? num_units : cap;

@@ -173,7 +173,7 @@ def compile_srgan_model(num_residual_blocks: int = 12, residual_scaling: float =
     g = GeneratorModel(num_residual_blocks=num_residual_blocks, residual_scaling=residual_scaling, seed=seed)
     d = DiscriminatorModel(seed=seed + 1)
     # the generator's persistent weight-gradient kernel leaves a few SMs to the discriminator chain that runs beside it
-    ops.call("dbm_flat_debug_set", 2, WGRAD_SM_RESERVE)
+    ops.call("dbm_set_sm_reserve", WGRAD_SM_RESERVE)
     g_opt = Adam(alpha=learning_rate, eps=1e-8).setup(g)
     d_opt = Adam(alpha=learning_rate, eps=1e-8).setup(d)
     return g, g_opt, d, d_opt

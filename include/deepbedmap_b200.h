@@ -41,8 +41,9 @@ typedef struct CUstream_st* cudaStream_t;
 int dbm_version(void);
 long dbm_launch_count(void); /* kernels this library has launched since it was loaded (bench.py reports the difference) */
 const char* dbm_last_error(void);
-int dbm_debug_set(int key, int value);
-int dbm_debug_set_ptr(int key, void* device_ptr); /* tuning only: 1 = trunk-kernel cycle counters */
+/* Persistent kernels of the TRAINING step (weight gradients) leave `n` SMs to concurrently running streams (the
+ * discriminator chain on its high-priority stream); results do not depend on it. Default 0. */
+int dbm_set_sm_reserve(int n);
 
 /* ---- fp32 convolution family -------------------------------------------------------------
  * L.Convolution2D forward (+ optional fused F.leaky_relu(slope=0.2)):
@@ -151,10 +152,7 @@ int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, 
  *   gout; float* partial[9][32][128]; int blk0, nblk, nslab; pad} (struct WgradUnit);
  * dbm_flat_wgrad_reduce: 48-byte records {const float* partial; float* dw; long split_stride; int nsplit,
  *   cin_total, c0, o0, nch, mode}: dw[(o0+o)*cin_total + c0 + c][tap] += sum_s partial[s][tap][o][c];
- * dbm_flat_bias_grad: 16-byte records {const bf16* gout; float* db}: db[0:32] += sum_p gout[.][p].
- * dbm_flat_debug_set(2, n): the persistent weight-gradient kernel leaves n SMs to concurrently running streams (the
- *   training step's discriminator chain); results do not depend on it. Key 1 is a tuning switch. */
-int dbm_flat_debug_set(int key, int value);
+ * dbm_flat_bias_grad: 16-byte records {const bf16* gout; float* db}: db[0:32] += sum_p gout[.][p]. */
 int dbm_flat_geometry(int n, int h, int w, int* out5_host);
 int dbm_flat_conv3x3_seq(const void* launches_host, int count, int n, int h, int w, int out_h, int out_w,
                          cudaStream_t stream);
@@ -173,8 +171,6 @@ int dbm_trunk_local_fwd(const void* passes_dev, int count, int n, int h, int w, 
 /* The data-gradient chain of the same trunk (autograd of the links above in g_loss.backward(), srgan_train.py:1256),
  * image-resident: gradients wrt the dense-block slots accumulate in TMEM, the bf16 gradients wrt every conv output
  * are written to the flat buffers dbm_flat_wgrad reads. gpost_flat: bf16(d loss / d a3), flat [8][Pg][8]. */
-/* tuning: force the number of images a CTA carries (1 or 2; 0 = automatic) */
-int dbm_local_debug_set(int value);
 int dbm_trunk_local_bwd(const void* passes_dev, int count, int n, int h, int w, const void* gpost_flat,
                         float* dxrr_scratch, cudaStream_t stream);
 int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h, int w, cudaStream_t stream);

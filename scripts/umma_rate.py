@@ -2,8 +2,11 @@
 import ctypes, sys
 import torch
 sys.path.insert(0, ".")
-from deepbedmap_b200 import _lib
-lib = _lib.load()
+import os
+from deepbedmap_b200 import _lib, build
+_lib.load()
+lib = ctypes.CDLL(build.TUNING_LIB)   # the microbenchmark lives in its own library, not in the product one
+lib.dbm_last_error = _lib.load().dbm_last_error
 lib.dbm_debug_umma_rate.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
 lib.dbm_debug_umma_rate.restype = ctypes.c_int
 out = torch.zeros(148, dtype=torch.int64, device="cuda")

@@ -9,8 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "deepbedmap_b200.h")).read()
+def _declared_symbols(header="deepbedmap_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(dbm_[a-z0-9_]+)\s*\(", text)))
 
@@ -26,6 +26,12 @@ def test_library_builds_and_exports_every_declared_symbol():
     # every declared entry point has a ctypes signature (and vice versa)
     assert set(names) - {"dbm_last_error"} == set(_lib.SIGNATURES)
     assert lib.dbm_version() >= 100
+    # the boundary header declares no tuning / ablation hook; those live in their own header (and the microbenchmark in
+    # its own library)
+    assert not any("debug" in n for n in names)
+    tuning = set(_declared_symbols("deepbedmap_b200_tuning.h"))
+    assert tuning - {"dbm_debug_umma_rate"} == set(_lib.TUNING_SIGNATURES)
+    assert not hasattr(lib, "dbm_debug_umma_rate")
 
 
 def test_signature_arity_matches_header():
