@@ -11,7 +11,8 @@ def __getattr__(name):  # lazy: importing the package must not require a GPU
         from . import model
         return getattr(model, name)
     if name in ("compile_srgan_model", "train_eval_discriminator", "train_eval_generator", "trainer", "Adam",
-                "ArrayIterator", "DeviceArrayIterator", "save_model_weights_and_architecture", "GraphedTrainStep"):
+                "ArrayIterator", "DeviceArrayIterator", "save_model_weights_and_architecture", "GraphedTrainStep",
+                "set_deterministic"):
         from . import train
         return getattr(train, name)
     if name in ("predict_continent", "tile_plan", "ContinentGrids", "HostBand", "HostDEM"):

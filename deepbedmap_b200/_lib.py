@@ -19,6 +19,7 @@ SIGNATURES = {
     "dbm_version": [],
     "dbm_launch_count": [],
     "dbm_set_sm_reserve": [_I],
+    "dbm_set_deterministic": [_I],
     "dbm_conv2d_fwd_f32": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dbm_conv2d_bwd_data_f32": [_P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dbm_conv2d_bwd_weight_f32": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

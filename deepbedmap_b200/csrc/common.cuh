@@ -38,6 +38,13 @@ __device__ __forceinline__ float lrelu(float v) { return v >= 0.f ? v : v * kLre
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 int num_sms();
+// dbm_set_deterministic(1): every reduction that would otherwise combine partial sums with floating-point atomics (in an
+// order the hardware picks) runs in a fixed order instead -- single-contributor launches, ordered two-level sums, or,
+// for the deformable scatter, exact 64-bit fixed-point accumulation. The reference trains with
+// chainer.global_config.cudnn_deterministic = True (srgan_train.py:69).
+bool deterministic();
+// library-owned, grow-only device scratch of the deterministic mode (int64 shadow of a scatter target)
+int det_scratch(size_t bytes, void** out);
 // Co-residency bound of a persistent kernel whose CTAs wait for each other through global flags (umma_trunk_kernel,
 // flat_chain_kernel): opts the kernel in to `smem` bytes of dynamic shared memory on the CURRENT device and returns in
 // *resident the number of CTAs that device holds at once for (threads, smem) -- occupancy query x SM count, cached per

@@ -62,10 +62,45 @@ __global__ void deform_sample_kernel(const float* __restrict__ x, const float* _
   }
 }
 
+// ---- deterministic scatter (dbm_set_deterministic): exact 64-bit fixed-point accumulation --------------------------
+// Floating-point atomicAdd makes the result depend on the order the hardware serves colliding updates. Integer
+// addition is associative, so the scatter accumulates round(v * 2^s) into an int64 shadow of the target and converts
+// once at the end: bit-identical from run to run. s is chosen from max|g| of the incoming gradient (one ordered
+// max-reduction) so that every addend is below 2^46 -- 2^16 colliding addends fit before 2^62, and the quantum is
+// 2^-46 of the largest gradient (fp32 keeps 2^-24).
+__global__ void absmax_bits_kernel(const float* __restrict__ x, long n, unsigned int* __restrict__ out) {
+  unsigned int m = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(x[i]) & 0x7FFFFFFFu);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);   // max is order-independent
+}
+__device__ __forceinline__ int det_scale_exp(unsigned int maxbits) {
+  const int e = (int)(maxbits >> 23) - 126;   // |g| < 2^e
+  const int s = 46 - e;
+  return s > 100 ? 100 : (s < -100 ? -100 : s);
+}
+__device__ __forceinline__ void det_add(long long* shadow, long idx, float v, float scale) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(shadow + idx), (unsigned long long)__float2ll_rn(v * scale));
+}
+// target[i] = (accumulate ? target[i] : 0) + shadow[i] * 2^-s
+__global__ void det_finalize_kernel(const long long* __restrict__ shadow, float* __restrict__ target, long n,
+                                    const unsigned int* __restrict__ maxbits, int accumulate) {
+  const float inv = exp2f((float)-det_scale_exp(*maxbits));
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = (float)((double)shadow[i] * (double)inv);
+    target[i] = accumulate ? target[i] + v : v;
+  }
+}
+
 // Given dcols[n][c*9+t][p]: dx[n][c] += scatter (atomics), doff[n][t|9+t][p] = d/d(position).
+// DET: the scatter goes to the int64 shadow `sh` with scale 2^det_scale_exp(*maxbits) instead of dx.
+template <bool DET>
 __global__ void deform_bwd_kernel(const float* __restrict__ x, const float* __restrict__ off,
                                   const float* __restrict__ dcols, float* __restrict__ dx,
-                                  float* __restrict__ doff, int N, int C, int H, int W) {
+                                  float* __restrict__ doff, int N, int C, int H, int W, long long* __restrict__ sh,
+                                  const unsigned int* __restrict__ maxbits) {
+  const float dscale = DET ? exp2f((float)det_scale_exp(*maxbits)) : 0.f;
   const int HW = H * W;
   const long total = (long)N * 9 * HW;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -93,11 +128,18 @@ __global__ void deform_bwd_kernel(const float* __restrict__ x, const float* __re
       gpx += g * ((1.f - b.fy) * (a01 - a00) + b.fy * (a11 - a10));
       gpy += g * ((1.f - b.fx) * (a10 - a00) + b.fx * (a11 - a01));
       if (dx) {
-        float* d = dx + plane;
-        if (v00) atomicAdd(d + (long)b.y0 * W + b.x0, g * w00);
-        if (v01) atomicAdd(d + (long)b.y0 * W + b.x0 + 1, g * w01);
-        if (v10) atomicAdd(d + (long)(b.y0 + 1) * W + b.x0, g * w10);
-        if (v11) atomicAdd(d + (long)(b.y0 + 1) * W + b.x0 + 1, g * w11);
+        if (DET) {
+          if (v00) det_add(sh, plane + (long)b.y0 * W + b.x0, g * w00, dscale);
+          if (v01) det_add(sh, plane + (long)b.y0 * W + b.x0 + 1, g * w01, dscale);
+          if (v10) det_add(sh, plane + (long)(b.y0 + 1) * W + b.x0, g * w10, dscale);
+          if (v11) det_add(sh, plane + (long)(b.y0 + 1) * W + b.x0 + 1, g * w11, dscale);
+        } else {
+          float* d = dx + plane;
+          if (v00) atomicAdd(d + (long)b.y0 * W + b.x0, g * w00);
+          if (v01) atomicAdd(d + (long)b.y0 * W + b.x0 + 1, g * w01);
+          if (v10) atomicAdd(d + (long)(b.y0 + 1) * W + b.x0, g * w10);
+          if (v11) atomicAdd(d + (long)(b.y0 + 1) * W + b.x0 + 1, g * w11);
+        }
       }
     }
     if (!b.in_range) { gpx = 0.f; gpy = 0.f; }
@@ -157,10 +199,14 @@ __global__ void __launch_bounds__(256) deform1_sample_kernel(const float* __rest
 }
 
 // dproj[n][t] += scatter of dy (atomics; dproj zeroed by the caller); doff[n][t | 9+t][p] = d/d(position)
+template <bool DET>
 __global__ void __launch_bounds__(256) deform1_bwd_scatter_kernel(const float* __restrict__ proj,
                                                                   const float* __restrict__ off,
                                                                   const float* __restrict__ dy, float* __restrict__ dproj,
-                                                                  float* __restrict__ doff, int N, int H, int W) {
+                                                                  float* __restrict__ doff, int N, int H, int W,
+                                                                  long long* __restrict__ sh,
+                                                                  const unsigned int* __restrict__ maxbits) {
+  const float dscale = DET ? exp2f((float)det_scale_exp(*maxbits)) : 0.f;
   const int HW = H * W;
   const long total = (long)N * 9 * HW;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -186,11 +232,18 @@ __global__ void __launch_bounds__(256) deform1_bwd_scatter_kernel(const float* _
     if (!b.in_range) { gpx = 0.f; gpy = 0.f; }
     doff[(long)n * 18 * HW + (long)t * HW + p] = gpx;
     doff[(long)n * 18 * HW + (long)(9 + t) * HW + p] = gpy;
-    float* d = dproj + plane;
-    if (v00) atomicAdd(d + (long)b.y0 * W + b.x0, g * (1.f - b.fy) * (1.f - b.fx));
-    if (v01) atomicAdd(d + (long)b.y0 * W + b.x0 + 1, g * (1.f - b.fy) * b.fx);
-    if (v10) atomicAdd(d + (long)(b.y0 + 1) * W + b.x0, g * b.fy * (1.f - b.fx));
-    if (v11) atomicAdd(d + (long)(b.y0 + 1) * W + b.x0 + 1, g * b.fy * b.fx);
+    if (DET) {
+      if (v00) det_add(sh, plane + (long)b.y0 * W + b.x0, g * (1.f - b.fy) * (1.f - b.fx), dscale);
+      if (v01) det_add(sh, plane + (long)b.y0 * W + b.x0 + 1, g * (1.f - b.fy) * b.fx, dscale);
+      if (v10) det_add(sh, plane + (long)(b.y0 + 1) * W + b.x0, g * b.fy * (1.f - b.fx), dscale);
+      if (v11) det_add(sh, plane + (long)(b.y0 + 1) * W + b.x0 + 1, g * b.fy * b.fx, dscale);
+    } else {
+      float* d = dproj + plane;
+      if (v00) atomicAdd(d + (long)b.y0 * W + b.x0, g * (1.f - b.fy) * (1.f - b.fx));
+      if (v01) atomicAdd(d + (long)b.y0 * W + b.x0 + 1, g * (1.f - b.fy) * b.fx);
+      if (v10) atomicAdd(d + (long)(b.y0 + 1) * W + b.x0, g * b.fy * (1.f - b.fx));
+      if (v11) atomicAdd(d + (long)(b.y0 + 1) * W + b.x0 + 1, g * b.fy * b.fx);
+    }
   }
 }
 
@@ -273,7 +326,20 @@ extern "C" int dbm_deform_bwd_f32(const float* x, const float* offset, const flo
   const long total = (long)n * 9 * h * w;
   long blocks = (total + 255) / 256;
   if (blocks > (long)num_sms() * 32) blocks = (long)num_sms() * 32;
-  deform_bwd_kernel<<<(int)blocks, 256, 0, st>>>(x, offset, dcols, dx, doffset, n, c, h, w);
+  if (deterministic() && dx != nullptr) {
+    const long nt = (long)n * c * h * w, ng = (long)n * c * 9 * h * w;
+    void* scratch;
+    int rc = det_scratch((size_t)nt * 8 + 256, &scratch);
+    if (rc) return rc;
+    unsigned int* maxbits = (unsigned int*)scratch;
+    long long* shadow = (long long*)((char*)scratch + 256);
+    DBM_CUDA(cudaMemsetAsync(scratch, 0, (size_t)nt * 8 + 256, st));
+    absmax_bits_kernel<<<num_sms() * 8, 256, 0, st>>>(dcols, ng, maxbits);
+    deform_bwd_kernel<true><<<(int)blocks, 256, 0, st>>>(x, offset, dcols, dx, doffset, n, c, h, w, shadow, maxbits);
+    det_finalize_kernel<<<num_sms() * 8, 256, 0, st>>>(shadow, dx, nt, maxbits, 1);
+    return check_launch("deform_bwd (deterministic)");
+  }
+  deform_bwd_kernel<false><<<(int)blocks, 256, 0, st>>>(x, offset, dcols, dx, doffset, n, c, h, w, nullptr, nullptr);
   return check_launch("deform_bwd");
 }
 
@@ -303,9 +369,24 @@ extern "C" int dbm_deform1_bwd_f32(const float* x, const float* offset, const fl
   const int hw = h * wd;
   cudaError_t e = cudaMemsetAsync(dproj_scratch, 0, (size_t)n * 9 * hw * sizeof(float), st);
   DBM_REQUIRE(e == cudaSuccess, "deform1_bwd: memset failed: %s", cudaGetErrorString(e));
-  deform1_bwd_scatter_kernel<<<deform1_blocks((long)n * 9 * hw), 256, 0, st>>>(proj, offset, dy, dproj_scratch, doffset,
-                                                                              n, h, wd);
-  int rc = check_launch("deform1_bwd_scatter");
+  int rc;
+  if (deterministic()) {
+    const long nt = (long)n * 9 * hw;
+    void* scratch;
+    rc = det_scratch((size_t)nt * 8 + 256, &scratch);
+    if (rc) return rc;
+    unsigned int* maxbits = (unsigned int*)scratch;
+    long long* shadow = (long long*)((char*)scratch + 256);
+    DBM_CUDA(cudaMemsetAsync(scratch, 0, (size_t)nt * 8 + 256, st));
+    absmax_bits_kernel<<<num_sms() * 4, 256, 0, st>>>(dy, (long)n * hw, maxbits);
+    deform1_bwd_scatter_kernel<true><<<deform1_blocks(nt), 256, 0, st>>>(proj, offset, dy, dproj_scratch, doffset, n, h, wd,
+                                                                        shadow, maxbits);
+    det_finalize_kernel<<<num_sms() * 4, 256, 0, st>>>(shadow, dproj_scratch, nt, maxbits, 0);
+  } else {
+    deform1_bwd_scatter_kernel<false><<<deform1_blocks((long)n * 9 * hw), 256, 0, st>>>(proj, offset, dy, dproj_scratch,
+                                                                                       doffset, n, h, wd, nullptr, nullptr);
+  }
+  rc = check_launch("deform1_bwd_scatter");
   if (rc) return rc;
   if (dx) {
     deform1_bwd_data_kernel<<<deform1_blocks((long)n * hw), 256, c * 9 * sizeof(float), st>>>(dproj_scratch, w, dx, n, c,
@@ -316,6 +397,7 @@ extern "C" int dbm_deform1_bwd_f32(const float* x, const float* offset, const fl
   if (dw) {
     int chunks = (4 * num_sms() + c - 1) / c;
     if (chunks > n) chunks = n;
+    if (deterministic()) chunks = 1;   // one block per channel: a single contributor per dW element
     deform1_bwd_weight_kernel<<<dim3(c, chunks), 256, 0, st>>>(x, dproj_scratch, dw, n, c, hw);
     rc = check_launch("deform1_bwd_weight");
   }

@@ -295,6 +295,19 @@ extern "C" int dbm_gemm_bf16(const float* a, long lda_m, long lda_k, long a_batc
   const bool wide_n = m <= 64;   // M = 64 (weight gradient): 64 x 128 tiles; else 128 x 64
   const int bm = wide_n ? 64 : 128, bn = wide_n ? 128 : 64;
   dim3 grid(ceil_div(m, bm), ceil_div(n, bn), batch);
+  if (p.atomic && deterministic()) {
+    // batch-reduced C in a fixed order: one launch per image, whole K per CTA -> a single contributor per output
+    // element per launch, launches ordered by the stream
+    for (int bi = 0; bi < batch; ++bi) {
+      GemmBf16P q = p;
+      q.A = a + (long)bi * a_batch_stride; q.B = b + (long)bi * b_batch_stride; q.C = c + (long)bi * c_batch_stride;
+      q.batch = 1; q.kchunks = 1;
+      int rc = wide_n ? launch_gemm_bf16<64, 128>(q, a_col, b_row, dim3(grid.x, grid.y, 1), st)
+                      : launch_gemm_bf16<128, 64>(q, a_col, b_row, dim3(grid.x, grid.y, 1), st);
+      if (rc) return rc;
+    }
+    return DBM_OK;
+  }
   if (p.atomic) {
     // split (image, K chunk) pairs over ~4 CTAs per SM in total
     p.kchunks = 1;

@@ -372,6 +372,11 @@ extern "C" int dbm_conv2d_bwd_weight_f32(const float* x, long x_batch_stride, co
   int splits = (4 * num_sms() + tiles - 1) / tiles;
   int max_splits = ceil_div(p.K, 4 * BK);
   if (splits > max_splits) splits = max_splits;
+  if (deterministic()) {   // one CTA owns the whole K range of its tile: dW += in a fixed order
+    p.kchunk = ceil_div(p.K, BK) * BK;
+    p.accumulate = 1;
+    return dispatch<kWgrad>(p, ksize, stride, 1, st);
+  }
   if (splits < 2) splits = 2;  // always the atomicAdd (accumulating) epilogue
   p.kchunk = ceil_div(ceil_div(p.K, splits), BK) * BK;
   splits = ceil_div(p.K, p.kchunk);
@@ -395,5 +400,17 @@ extern "C" int dbm_gemm_f32(const float* a, long lda_m, long lda_k, long a_batch
   p.lda_m = lda_m; p.lda_k = lda_k; p.ldb_k = ldb_k; p.ldb_n = ldb_n; p.ldc_m = ldc_m; p.ldc_n = ldc_n;
   p.a_bs = a_batch_stride; p.b_bs = b_batch_stride; p.c_bs = c_batch_stride;
   p.HO = p.WO = p.H = p.W = 1;
+  if (p.atomic && deterministic() && batch > 1) {
+    // batch-reduced C: one launch per batch element, each a single contributor per output element, in stream order
+    for (int bi = 0; bi < batch; ++bi) {
+      GemmP q = p;
+      q.A = a + (long)bi * a_batch_stride;
+      q.B = b + (long)bi * b_batch_stride;
+      q.Cc = c + (long)bi * c_batch_stride;
+      int rc = dispatch<kPlain>(q, 1, 1, 1, st);
+      if (rc) return rc;
+    }
+    return DBM_OK;
+  }
   return dispatch<kPlain>(p, 1, 1, batch, st);
 }

@@ -15,6 +15,22 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static bool g_deterministic = false;
+bool deterministic() { return g_deterministic; }
+
+int det_scratch(size_t bytes, void** out) {
+  static void* buf = nullptr;
+  static size_t cap = 0;
+  if (bytes > cap) {
+    if (buf) DBM_CUDA(cudaFree(buf));
+    buf = nullptr; cap = 0;
+    DBM_CUDA(cudaMalloc(&buf, bytes));
+    cap = bytes;
+  }
+  *out = buf;
+  return DBM_OK;
+}
+
 static long g_launches = 0;   // kernels launched by this library since it was loaded (every launch ends in check_launch)
 
 int check_launch(const char* what) {
@@ -274,6 +290,10 @@ using namespace dbm;
 extern "C" const char* dbm_last_error(void) { return g_err; }
 extern "C" int dbm_version(void) { return 200; }
 extern "C" long dbm_launch_count(void) { return g_launches; }
+extern "C" int dbm_set_deterministic(int on) {
+  g_deterministic = on != 0;
+  return DBM_OK;
+}
 
 extern "C" int dbm_nchw_to_slab8(const float* src, long src_batch_stride, void* dst, int n, int c, int h, int w,
                                  int dst_cs_total, int dst_cs0, cudaStream_t st) {
@@ -336,7 +356,7 @@ extern "C" int dbm_bias_grad_f32(const float* dy, long dy_bs, float* db, int n, 
   const int threads = hw >= 1024 ? 256 : (hw >= 256 ? 128 : 64);
   int chunks = (8 * num_sms() + o - 1) / o;
   if (chunks > n) chunks = n;
-  if (chunks < 1) chunks = 1;
+  if (chunks < 1 || deterministic()) chunks = 1;   // one block (fixed reduction tree) per channel: a single contributor
   bias_grad_kernel<<<dim3(o, chunks), threads, 0, st>>>(dy, dy_bs ? dy_bs : (long)o * hw, db, n, hw);
   return check_launch("bias_grad");
 }

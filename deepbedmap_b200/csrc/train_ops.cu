@@ -232,6 +232,10 @@ constexpr int kMaxImg = 48;
 constexpr int kWin = 9;
 __constant__ float c_gauss[kWin];  // normalised 1-D Gaussian, sigma 1.5
 
+constexpr int kLossMaxN = 65536;
+__device__ float g_loss_part[kLossMaxN * 4];   // per-image partial sums of gen_image_loss_kernel
+__device__ unsigned int g_loss_count;
+
 __global__ void gen_image_loss_kernel(const float* __restrict__ yp, const float* __restrict__ yt,
                                       const float* __restrict__ xt, int N, int H, int W, float w_content,
                                       float w_topo, float w_struct, float* __restrict__ sums,
@@ -330,11 +334,21 @@ __global__ void gen_image_loss_kernel(const float* __restrict__ yp, const float*
   s_topo = block_sum(s_topo, red);
   s_ssim = block_sum(s_ssim, red);
   s_sq = block_sum(s_sq, red);
+  // per-image partials, summed in image order by the last block to arrive: the four sums are the same bits every run
+  __shared__ bool last;
   if (threadIdx.x == 0) {
-    atomicAdd(sums + 0, s_l1);
-    atomicAdd(sums + 1, s_topo);
-    atomicAdd(sums + 2, s_ssim);
-    atomicAdd(sums + 3, s_sq);
+    float* part = g_loss_part + (size_t)n * 4;
+    part[0] = s_l1; part[1] = s_topo; part[2] = s_ssim; part[3] = s_sq;
+    __threadfence();
+    last = atomicAdd(&g_loss_count, 1u) == (unsigned)(N - 1);
+    if (last) g_loss_count = 0;
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 4) {
+    __threadfence();
+    double t = 0.0;
+    for (int k = 0; k < N; ++k) t += (double)g_loss_part[(size_t)k * 4 + threadIdx.x];
+    sums[threadIdx.x] = (float)t;
   }
 }
 
@@ -440,6 +454,7 @@ extern "C" int dbm_gen_image_loss_f32(const float* y_pred, const float* y_true, 
     DBM_CUDA(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
     init = true;
   }
+  DBM_REQUIRE(n <= kLossMaxN, "gen_image_loss: batch %d exceeds %d", n, kLossMaxN);
   DBM_CUDA(cudaMemsetAsync(sums4, 0, 4 * sizeof(float), st));
   gen_image_loss_kernel<<<n, 256, 0, st>>>(y_pred, y_true, x_topo, n, h, w, w_content, w_topo, w_struct, sums4, dy);
   return check_launch("gen_image_loss");

@@ -167,6 +167,13 @@ def allreduce_grads(link) -> float:
     return r.finish()
 
 
+def set_deterministic(on: bool = True) -> None:
+    """chainer.global_config.cudnn_deterministic = True (srgan_train.py:69): fixed-order gradient reductions and an
+    exact fixed-point scatter in the deformable layers' backward -- two runs of the same steps give bit-identical
+    weights and metrics. Process-wide; slower (the batch-reduced GEMMs run image by image)."""
+    ops.call("dbm_set_deterministic", int(bool(on)))
+
+
 def compile_srgan_model(num_residual_blocks: int = 12, residual_scaling: float = 0.1,
                         learning_rate: float = 1.6e-4, seed: int = 0):
     """srgan_train.py:1014-1055: returns (g_model, g_optimizer, d_model, d_optimizer)."""

@@ -41,6 +41,12 @@ typedef struct CUstream_st* cudaStream_t;
 int dbm_version(void);
 long dbm_launch_count(void); /* kernels this library has launched since it was loaded (bench.py reports the difference) */
 const char* dbm_last_error(void);
+/* Deterministic training arithmetic (the reference sets chainer.global_config.cudnn_deterministic = True,
+ * srgan_train.py:69): with on != 0 every reduction that otherwise combines partial sums with floating-point atomics
+ * runs in a fixed order -- single-contributor launches for split-K / batch-reduced weight and bias gradients, exact
+ * 64-bit fixed-point accumulation for the deformable layers' scatter (the library then owns a grow-only device scratch
+ * of 8 bytes per scattered element). Two runs of the same steps give bit-identical weights; slower. Default off. */
+int dbm_set_deterministic(int on);
 /* Persistent kernels of the TRAINING step (weight gradients) leave `n` SMs to concurrently running streams (the
  * discriminator chain on its high-priority stream); results do not depend on it. Default 0. */
 int dbm_set_sm_reserve(int n);

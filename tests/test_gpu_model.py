@@ -442,6 +442,46 @@ def test_shared_generator_forward_is_not_reused_for_refreshed_inputs():
     assert np.isfinite(gl) and np.isfinite(gp) and np.isfinite(gs)
 
 
+def test_deterministic_mode_gives_bit_identical_training():
+    """cudnn_deterministic=True of the reference (srgan_train.py:69): with set_deterministic(True) two runs of the same
+    three training steps -- eager, then the captured graph -- end in bit-identical weights, Adam state and metrics; the
+    default (atomics) mode agrees with it to accumulation-order noise."""
+    from deepbedmap_b200 import train as T
+    rng = np.random.RandomState(11)
+    batches = [{k: rng.rand(*s).astype(np.float32) for k, s in
+                (("X", (4, 1, 11, 11)), ("W1", (4, 1, 110, 110)), ("W2", (4, 2, 22, 22)), ("W3", (4, 1, 11, 11)),
+                 ("Y", (4, 1, 36, 36)))} for _ in range(3)]
+
+    def run(graphed):
+        g, g_opt, d, d_opt = T.compile_srgan_model(num_residual_blocks=1, seed=3)
+        step = T.GraphedTrainStep(batches[0], g, g_opt, d, d_opt) if graphed else None
+        metrics = []
+        for b in batches:
+            if graphed:
+                (dl, da), (gl, gp, gs) = step.step(b)
+            else:
+                dl, da = T.train_eval_discriminator(b, g, d, d_opt, share_generator_forward=False)
+                gl, gp, gs = T.train_eval_generator(b, g, d, g_opt)
+            metrics.append((dl, da, gl, gp, gs))
+        torch.cuda.synchronize()
+        return g.flat.clone(), d.flat.clone(), g_opt.m.clone(), d_opt.v.clone(), metrics
+
+    T.set_deterministic(True)
+    try:
+        for graphed in (False, True):
+            a, b = run(graphed), run(graphed)
+            for x, y in zip(a[:4], b[:4]):
+                assert torch.equal(x, y)
+            assert a[4] == b[4]
+        det = run(False)
+    finally:
+        T.set_deterministic(False)
+    free = run(False)
+    assert rel_l2(free[0].cpu().numpy(), det[0].cpu().numpy()) < 1e-5
+    assert rel_l2(free[1].cpu().numpy(), det[1].cpu().numpy()) < 1e-5
+    assert np.allclose(np.array(free[4]), np.array(det[4]), rtol=2e-3, atol=1e-5)
+
+
 def test_npz_roundtrip(tmp_path):
     from deepbedmap_b200 import DiscriminatorModel, GeneratorModel
     from deepbedmap_b200.npz import peek_num_residual_blocks
