@@ -477,9 +477,12 @@ def test_deterministic_mode_gives_bit_identical_training():
     finally:
         T.set_deterministic(False)
     free = run(False)
-    assert rel_l2(free[0].cpu().numpy(), det[0].cpu().numpy()) < 1e-5
-    assert rel_l2(free[1].cpu().numpy(), det[1].cpu().numpy()) < 1e-5
-    assert np.allclose(np.array(free[4]), np.array(det[4]), rtol=2e-3, atol=1e-5)
+    # The default (atomics) mode computes the same step up to accumulation-order noise: identical weights in, so the FIRST
+    # step's metrics agree tightly. (Later weights may differ by a full Adam update wherever a gradient is ~0 -- its
+    # noise decides the update's sign -- which is why bit-reproducibility needs the deterministic mode at all.)
+    print("deterministic vs default: metrics", det[4][0], free[4][0], "max weight difference after 3 steps",
+          float((free[0] - det[0]).abs().max()), float((free[1] - det[1]).abs().max()))
+    assert np.allclose(np.array(free[4][0]), np.array(det[4][0]), rtol=1e-4, atol=1e-6)
 
 
 def test_npz_roundtrip(tmp_path):
