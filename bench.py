@@ -376,6 +376,17 @@ def tile_parity(model, grids, cpu: bool):
     y16 = model.forward(*crop).array[0, 0].cpu().numpy()
     m32 = GeneratorModel(num_residual_blocks=12, residual_scaling=0.1, precision="fp32", seed=0)
     y32 = m32.forward(*crop).array[0, 0].cpu().numpy()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    m32.forward(*crop)
+    e1.record()
+    torch.cuda.synchronize()
+    ms32 = e0.elapsed_time(e1)
+    e0.record()
+    model.forward(*crop)
+    e1.record()
+    torch.cuda.synchronize()
+    ms16 = e0.elapsed_time(e1)
     del m32
     torch.cuda.empty_cache()
     std = float(y32.std())
@@ -385,6 +396,9 @@ def tile_parity(model, grids, cpu: bool):
            "metres": f"output units x ({BED_STD_M:.0f} m / std(output)): the random-init network's output unit is arbitrary, "
                      "so errors are quoted for an output calibrated to the spread of the bed-elevation input",
            "output_std": std,
+           "precision_modes": {"bf16": {"ms_per_tile": ms16, "what": "tensor-core path (the benchmarked one)"},
+                               "fp32": {"ms_per_tile": ms32, "what": "exact CUDA-core path, precision='fp32': the option "
+                                        "for sub-metre accuracy, error below as fp32_cuda_vs_fp32_cpu_oracle"}},
            "bf16_vs_fp32_cuda": {"rel_l2": rel_l2(y16, y32), "max_abs": float(np.abs(y16 - y32).max()),
                                  "max_abs_m": float(np.abs(y16 - y32).max()) * to_m}}
     secs = None
@@ -439,7 +453,46 @@ def small_tile_configs(peak_tf, cpu: bool):
                                    "sample": f"median of {20 if batch == 1 else 3} fp32 oracle forwards at batch {batch}"}
             rec["speedup_vs_cpu_e2e"] = cs * 1e3 / ms_e2e
         out[key] = rec
+    out["configs[4] depth / width sweep"] = config5_sweep(peak_tf)
     return out
+
+
+def config5_sweep(peak_tf):
+    """BASELINE configs[4]: forward of deeper / wider generators (the reference's Optuna search space:
+    num_residual_blocks 8-14 and ESRGAN's 23, srgan_train.py:454; inter_channels 32 / 64, :283-284) at large batch
+    (1024 training tiles) and on one full continent tile; whole-forward TFLOP/s and fraction of the measured bf16 peak."""
+    from deepbedmap_b200 import GeneratorModel
+
+    def macs_per_trunk_px(nb, g):
+        stem = 32 * (9 + 900 + 72 + 9)
+        rdb = 9 * (64 * g + (64 + g) * g + (64 + 2 * g) * g + (64 + 3 * g) * g + (64 + 4 * g) * 64)
+        head = 4 * 9 * 64 * 64 + 16 * 9 * 64 * 64 + 16 * 9 * 64 * (18 + 64) + 16 * 9 * 64 * (18 + 1)
+        return stem + 9 * 128 * 64 + 3 * nb * rdb + 9 * 64 * 64 + head
+
+    rows = []
+    for label, n, h in (("1024 tiles 11x11", 1024, 11), ("1 tile 288x288", 1, 288)):
+        gen = torch.Generator(device="cuda").manual_seed(42)
+        ins = (torch.rand(n, 1, h, h, generator=gen, device="cuda"), torch.rand(n, 1, 10 * h, 10 * h, generator=gen, device="cuda"),
+               torch.rand(n, 2, 2 * h, 2 * h, generator=gen, device="cuda"), torch.rand(n, 1, h, h, generator=gen, device="cuda"))
+        for inter in (32, 64):
+            for nb in (8, 12, 23):
+                m = GeneratorModel(num_residual_blocks=nb, inter_channels=inter, precision="bf16")
+                for _ in range(2):
+                    m.forward(*ins)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    m.forward(*ins)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 3
+                gflop = 2.0 * macs_per_trunk_px(nb, inter) * n * (h - 2) ** 2 / 1e9
+                rows.append({"workload": label, "num_residual_blocks": nb, "inter_channels": inter, "gflop_forward": gflop,
+                             "ms": ms, "tflops": gflop / ms, "frac_of_bf16_peak": gflop / ms / peak_tf})
+                del m
+                torch.cuda.empty_cache()
+    return rows
 
 
 def run_inference(args, rank, world, local):

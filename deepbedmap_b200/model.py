@@ -180,6 +180,7 @@ class GeneratorModel(_Link):
         self._ws = {}
         self.persistent_trunk = True   # one-launch trunk kernel (False: one launch per layer, for A/B tests)
         self.paired_trunk = True       # dense-block layer pairing inside the persistent kernel
+        self.paired_convs = (1, 3)     # which pairs (conv_k, conv_k+1) are fused: (1, 3) both, (3,) the second only
         self.per_layer_ck16 = False    # per-layer launches in the trunk kernel's 16-channel chunks (bit-exact A/B)
         self.local_trunk = True        # tiles of <= 128 padded positions: image-resident trunk kernel (umma_local.cu)
         # output layer's tap projection inside the first deformable layer's epilogue: bit-identical, but measured
@@ -677,7 +678,7 @@ class GeneratorModel(_Link):
         ws = self._ws.get(key)
         pk = self._pack()
         if ws is not None and ws["version"] == (self._pack_gen, self.persistent_trunk, self.paired_trunk,
-                                                self.per_layer_ck16):
+                                                self.per_layer_ck16, self.paired_convs):
             return ws
         bf = torch.bfloat16
         g = self.inter_channels
@@ -723,6 +724,11 @@ class GeneratorModel(_Link):
                     # features a_k ever leaves the SM.
                     for k in (1, 3):
                         cin = 64 + (k - 1) * g
+                        if k not in self.paired_convs:     # A/B: this pair as two layers of their own
+                            for kk in (k, k + 1):
+                                ci = 64 + (kk - 1) * g
+                                layer(f"{pre}/conv_layer{kk}", ci, g, 1 + cur, act=1, out=cat[cur], out_cs0=ci // 8)
+                            continue
                         layer(f"{pre}/pair{k}", cin, 64, 1 + cur, act=1, out=cat[cur], out_cs0=cin // 8, cout_main=32,
                               raw=True, mode=1)
                         layer(f"{pre}/tail{k + 1}", 32, 32, 1 + cur, in_cs0=cin // 8, act=1, out=cat[cur],
@@ -745,7 +751,7 @@ class GeneratorModel(_Link):
         ws["table"] = torch.from_numpy(table.view(np.uint8).copy()).cuda()
         tiles = ((H + 31) // 32) * ((W + 15) // 16)   # 32-row x 16-column units (kTH x kTW in umma_trunk.cu)
         ws["flags"] = ops.empty(len(layers) * n * tiles, dtype=torch.int32)
-        ws["version"] = (self._pack_gen, self.persistent_trunk, self.paired_trunk, self.per_layer_ck16)
+        ws["version"] = (self._pack_gen, self.persistent_trunk, self.paired_trunk, self.per_layer_ck16, self.paired_convs)
         self._ws[key] = ws
         return ws
 
@@ -785,7 +791,8 @@ class GeneratorModel(_Link):
         return ws
 
     def _c_forward_applies(self):
-        return (self.c_model_api and self.persistent_trunk and self.paired_trunk and not self.per_layer_ck16
+        return (self.c_model_api and self.persistent_trunk and self.paired_trunk and self.paired_convs == (1, 3)
+                and not self.per_layer_ck16
                 and self.stem_w1_tensor_core and not self.fuse_out_projection and self.inter_channels == 32
                 and self.out_channels == 1)
 

@@ -12,13 +12,22 @@ Pinning status
 --------------
 Chainer / CuPy / ssim-chainer are third-party dependencies whose sources are not under
 /root/reference (Pipfile:8,10,30) and none of them is installable in this image, so the
-reference itself cannot be executed here.  The reference's own tests pin only:
-  * output shapes and parameter counts (srgan_train.py:444-447, 605-608),
-  * four loss / metric known answers (srgan_train.py:868, 920, 948, 991).
-All of those are reproduced by tests/test_oracle_kat.py.  No reference test, fixture or
-weight file pins a forward/backward *value* of any conv / RRDB / deformable-conv / BN
-layer, hence for those layers:  **parity unpinned**  (the deformable convolution is
-additionally cross-checked against torchvision.ops.deform_conv2d and a naive NumPy loop).
+reference as a whole cannot be executed here.  What pins this file:
+  * the reference's own test values: output shapes and parameter counts (srgan_train.py:444-447,
+    605-608) and the four loss / metric known answers (srgan_train.py:868, 920, 948, 991)
+    -- tests/test_oracle_kat.py;
+  * the reference's own CODE, executed: srgan_train.py's model classes, loss functions and both
+    step functions and deepbedmap.py's tiler cell, compiled unmodified from /root/reference and run
+    on a float64 stand-in for the Chainer calls they make (tests/tools/minichainer.py,
+    tests/golden/make_reference_golden.py -> tests/golden/reference_graph_golden.npz).  This
+    file reproduces those vectors to 1e-10 (forward, losses) / 1e-8 (parameter gradients of a
+    D-step + G-step) and the tile geometry exactly -- tests/test_reference_graph.py.
+So the graph, the step logic and the key layout are pinned to the reference by execution.  The
+arithmetic of the Chainer PRIMITIVES under them (convolution, deformable sampler,
+BatchNormalization, Adam) is restated both here and in the stand-in; no
+Chainer-computed value of a conv / RRDB / deformable / BN layer exists to compare with, so at the
+primitive level:  **parity unpinned**  (cross-checks: torch functional ops, a naive NumPy loop and
+torchvision.ops.deform_conv2d for the deformable convolution).
 
 Every function cites the reference lines it follows.
 """
