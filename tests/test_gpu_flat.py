@@ -263,10 +263,11 @@ def test_image_resident_trunk_equals_flat_chain(nb, n, H, W):
     assert e_da0 < 2e-3 and e_grad < 2e-3
 
 
-@pytest.mark.parametrize("nb,n,scale", [(1, 3, 0.5), (2, 5, 0.5)])
+@pytest.mark.parametrize("nb,n,scale", [(1, 3, 0.5), (2, 5, 0.5), (12, 2, 0.5)])
 def test_generator_tensor_core_backward_matches_oracle(nb, n, scale):
     """Whole-generator G-step gradients with the trunk on the tensor cores (stem and head fp32):
-    against autograd on the oracle graph whose trunk carries the same operand rounding."""
+    against autograd on the oracle graph whose trunk carries the same operand rounding. (12, 2, 0.5) is the
+    reference's full depth: all 384 parameter arrays of the 12-RRDB generator."""
     from oracle import deepbedmap_oracle as O
     from deepbedmap_b200 import GeneratorModel
     params = O.init_generator_params(nb, seed=0, bias_std=0.05, scale=scale)
