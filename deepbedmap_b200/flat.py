@@ -408,6 +408,85 @@ class FlatTrunk:
         return da0
 
 
+class FlatChainForward:
+    """Inference forward of the trunk (srgan_train.py:541-551) on the flat-padded layout through the persistent layer
+    chain (dbm_flat_conv3x3_chain), for either dense-block width (inter_channels 32 or 64, srgan_train.py:283-284):
+    the path of SMALL tiles -- an image with its border is at most one 128-position MMA tile -- when the image-resident
+    kernel (inter_channels = 32 only) does not apply. On such tiles the tiled trunk kernel would use 81 of the 512 pixels
+    of its 32 x 16 work units; here all padded images are one flat position axis."""
+
+    def __init__(self, model, n: int, H: int, W: int):
+        self.model, self.n, self.H, self.W = model, n, H, W
+        self.geom = geometry(n, H, W)
+        self.Pg = Pg = self.geom["Pg"]
+        g = model.inter_channels
+        self.cc = 64 + 4 * g
+        bf = torch.bfloat16
+        zb = lambda c: torch.zeros(c // 8, Pg, 8, dtype=bf, device="cuda")
+        zf = lambda c: torch.zeros(c // 4, Pg, 4, dtype=torch.float32, device="cuda")
+        self.s0 = zb(128)
+        self.cat = [zb(self.cc), zb(self.cc)]
+        self.x0 = zf(64)
+        self.xring = [zf(64) for _ in range(4)]
+        self.a3f = zf(64)
+        self._key = None
+
+    def _x(self, j):
+        return self.x0 if j == 0 else self.xring[j % 4]
+
+    def build(self, pk):
+        m = self.model
+        key = (m._pack_gen, m.residual_scaling)
+        if self._key == key:
+            return
+        beta, g, Pg = m.residual_scaling, m.inter_channels, self.Pg
+        pb = lambda t, c=0: t.data_ptr() + 2 * c * Pg
+        pf = lambda t, c=0: t.data_ptr() + 4 * c * Pg
+        epi, launch = FlatTrunk._epi, FlatTrunk._launch
+        nrdb = 3 * m.num_residual_blocks
+        tab = []
+        wq, bq = pk["pre_residual_conv_layer@trunk"]
+        tab.append(launch(self, pb(self.s0), wq, 128, 64, [
+            epi(bias=bq.data_ptr() + 128 * b, act=1, out_f32=pf(self.x0, 32 * b), out_bf16=pb(self.cat[0], 32 * b))
+            for b in range(2)]))
+        for j in range(nrdb):
+            r = j % 3 + 1
+            pre = m._rdb_prefix(j // 3, r)
+            cat, nxt = self.cat[j % 2], self.cat[(j + 1) % 2]
+            for k in (1, 2, 3, 4):
+                cin = 64 + g * (k - 1)
+                wq, bq = pk[f"{pre}/conv_layer{k}@trunk"]
+                tab.append(launch(self, pb(cat), wq, cin, g, [
+                    epi(bias=bq.data_ptr() + 128 * b, act=1, out_bf16=pb(cat, cin + 32 * b)) for b in range(g // 32)]))
+            wq, bq = pk[f"{pre}/conv_layer5@trunk"]
+            blocks = []
+            for b in range(2):
+                kw = dict(bias=bq.data_ptr() + 128 * b, add1=pf(self._x(j), 32 * b), s1=1.0, beta=beta,
+                          out_f32=pf(self._x(j + 1), 32 * b), out_bf16=pb(nxt, 32 * b))
+                if r == 3:   # out = rrdb_in + beta * (x + beta * a5)  (srgan_train.py:358, 402)
+                    kw.update(add2=pf(self._x(j - 2), 32 * b), beta2=beta)
+                blocks.append(epi(**kw))
+            tab.append(launch(self, pb(cat), wq, self.cc, 64, blocks))
+        wq, bq = pk["post_residual_conv_layer@trunk"]
+        tab.append(launch(self, pb(self.cat[nrdb % 2]), wq, 64, 64, [
+            epi(bias=bq.data_ptr() + 128 * b, add1=pf(self.x0, 32 * b), s1=1.0, beta=1.0, out_f32=pf(self.a3f, 32 * b))
+            for b in range(2)]))
+        self.table = np.ascontiguousarray(np.stack(tab))
+        self.table_dev = torch.from_numpy(self.table.view(np.uint8).reshape(-1).copy()).cuda()
+        self.flags = ops.empty(len(tab) * self.geom["tiles"], dtype=torch.int32)
+        self._key = key
+
+    def forward(self) -> torch.Tensor:
+        """s0 (flat bf16 stem output, filled by dbm_stem_fwd_flat) -> a3 (n, 64, H, W) fp32 NCHW."""
+        n, H, W = self.n, self.H, self.W
+        st = ops.stream()
+        ops.call("dbm_flat_conv3x3_chain", self.table.ctypes.data, self.table_dev.data_ptr(), len(self.table), n, H, W,
+                 0, 0, self.flags.data_ptr(), st)
+        a3 = ops.empty(n, 64, H, W)
+        ops.call("dbm_flat_to_nchw", self.a3f.data_ptr(), None, a3.data_ptr(), 64, n, H, W, st)
+        return a3
+
+
 # ---- single-layer helpers (tests, diagnostics) -----------------------------------------------------
 def pack_dgrad(w: torch.Tensor) -> torch.Tensor:
     """Data-gradient operand image of an fp32 (O, Cin, 3, 3) filter: GEMM N = Cin, K = O, taps flipped."""

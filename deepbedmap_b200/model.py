@@ -843,11 +843,25 @@ class GeneratorModel(_Link):
         H, W = h - 2, w - 2
         bf = torch.bfloat16
         local = self.local_trunk and self.inter_channels == 32 and flat.local_trunk_fits(H, W)
-        if not local and self._c_forward_applies():
+        chain = self.local_trunk and self.inter_channels != 32 and flat.local_trunk_fits(H, W)
+        if not local and not chain and self._c_forward_applies():
             return self._forward_c_api(x, w1, w2, w3)
         pk = self._pack(self.PACK_INFER_LOCAL if local else self.PACK_INFER)
         wt1, wts, bias128 = pk["stem"]
-        if local:
+        if chain:
+            # small tiles, wide dense blocks (inter_channels = 64, config 5): the flat layer chain on the padded-image
+            # position axis instead of 32 x 16-pixel work units that a 9 x 9 tile fills to 16 %
+            fc = self._ws.get(("chain", n, H, W))
+            if fc is None:
+                fc = self._ws[("chain", n, H, W)] = flat.FlatChainForward(self, n, H, W)
+            fc.build(pk)
+            ops.call("dbm_stem_fwd_flat", x.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), wt1.data_ptr(),
+                     wts.data_ptr(), bias128.data_ptr(), fc.s0.data_ptr(), n, h, w, ops.stream())
+            a3 = fc.forward()
+            u1 = ops.empty(n, 8, 2 * H, 2 * W, 8, dtype=bf)
+            ops.nchw_to_slab8(ops.upsample2_fwd(a3), u1)
+            ws = dict(u1=u1)
+        elif local:
             # small tiles (the reference's 11x11 training / doctest windows): stem -> flat layout -> the whole trunk
             # with the activations of an image resident in shared memory / TMEM
             ws = self._local_workspace(n, H, W, pk)

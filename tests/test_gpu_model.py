@@ -156,6 +156,28 @@ def test_scaled_generators_match_oracle(nb, inter, n, h, w):
     assert rel_l2(got, emu) < 8e-3 and rel_l2(got, ref) < 2e-2
 
 
+def test_wide_generator_small_tiles_take_the_flat_chain():
+    """inter_channels = 64 on 11x11 tiles (config 5): the flat layer chain (one position axis over all padded images)
+    against the tiled trunk kernel on the same weights -- same MMAs per output, different work decomposition -- and
+    against the oracle."""
+    nb, inter, n = 3, 64, 5
+    m, params = make_generator(nb, "bf16", scale=0.5, inter_channels=inter)
+    ins = O.synthetic_inputs(n, 11, 11)
+    chain = m.forward(*ins).array.clone()
+    assert ("chain", n, 9, 9) in m._ws
+    for _ in range(2):
+        assert torch.equal(m.forward(*ins).array, chain)          # flag protocol: run-to-run identical
+    m.local_trunk = False
+    tiled = m.forward(*ins).array.clone()
+    ref = O.generator_forward_numpy(params, *ins, num_residual_blocks=nb, inter_channels=inter) \
+        if "inter_channels" in O.generator_forward_numpy.__code__.co_varnames else \
+        O.generator_forward_numpy(params, *ins, num_residual_blocks=nb)
+    print(f"inter=64 flat chain vs tiled kernel {rel_l2(chain.cpu().numpy(), tiled.cpu().numpy()):.3e}; "
+          f"vs fp64 oracle {rel_l2(chain.cpu().numpy(), ref):.3e}")
+    assert rel_l2(chain.cpu().numpy(), tiled.cpu().numpy()) < 8e-3
+    assert rel_l2(chain.cpu().numpy(), ref) < 2e-2
+
+
 def test_wide_generator_fp32_forward_and_training_step():
     """inter_channels = 64 on the exact-arithmetic path, forward and one generator step
     (gradients against autograd on the fp64 oracle)."""
