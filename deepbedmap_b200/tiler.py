@@ -241,6 +241,12 @@ class ContinentGrids:
     def ensure_rows(self, upto: int, prefetch_upto: Optional[int] = None):
         """Resident grids: nothing to do."""
 
+    def enqueue_rows(self, upto: int, prefetch_upto: Optional[int] = None):
+        """Resident grids: nothing to do."""
+
+    def wait_for(self, upto: int, x_upto: int):
+        """Resident grids: nothing to do."""
+
 
 class StreamedGrids(ContinentGrids):
     """Host grids uploaded band by band on a side stream while earlier tile rows are computing
@@ -271,27 +277,54 @@ class StreamedGrids(ContinentGrids):
         self._stream = torch.cuda.Stream()
         self._stream.wait_stream(torch.cuda.current_stream())
 
+    COL_BLOCKS = 6   # a band is uploaded in column blocks so that the first tiles of a row need not wait for all of it
+
     def _enqueue(self, upto: int):
+        from . import ops
         upto = min(upto - self.row0, self.X.shape[2])
-        if upto > self._done:
-            with torch.cuda.stream(self._stream):
+        if upto <= self._done:
+            return
+        Ws = self.X.shape[3]
+        edges = [Ws * k // self.COL_BLOCKS for k in range(self.COL_BLOCKS + 1)]
+        pinned = all(t.is_pinned() for t in self._host)
+        with torch.cuda.stream(self._stream):
+            st = self._stream.cuda_stream
+            for xa, xb in zip(edges[:-1], edges[1:]):
                 for host, dev, sc in zip(self._host, self._dev, self._scale):
                     a, b = sc * self._done, sc * upto
                     ha = sc * (self.row0 - self._host_row0)
                     for c in range(dev.shape[1]):
-                        dev[0, c, a:b].copy_(host[0, c, ha + a:ha + b], non_blocking=True)
-                self._events.append((upto, self._stream.record_event()))
-            self._done = upto
+                        src, dst = host[0, c, ha + a:ha + b, sc * xa:sc * xb], dev[0, c, a:b, sc * xa:sc * xb]
+                        if pinned:   # strided 2-D copy straight from the pinned grid (cudaMemcpy2DAsync)
+                            ops.call("dbm_copy2d_async", dst.data_ptr(), dev.shape[3] * 4, src.data_ptr(),
+                                     host.shape[3] * 4, (xb - xa) * sc * 4, b - a, st)
+                        else:
+                            dst.copy_(src, non_blocking=True)
+                self._events.append((upto, xb, self._stream.record_event()))
+        self._done = upto
+
+    def enqueue_rows(self, upto: int, prefetch_upto: Optional[int] = None):
+        """Enqueue (without waiting) the upload of lowres rows < ``upto``, then of rows < ``prefetch_upto`` (one tile
+        row ahead), on the copy stream."""
+        self._enqueue(upto)
+        if prefetch_upto is not None:
+            self._enqueue(prefetch_upto)
+
+    def wait_for(self, upto: int, x_upto: int):
+        """Make the compute stream wait for rows < ``upto`` (absolute lowres row) x columns < ``x_upto`` only. The copy
+        stream is in order, so the event of the column block holding ``x_upto`` in the band that completes ``upto``
+        covers every earlier band and block."""
+        need = min(upto - self.row0, self.X.shape[2])
+        for rows_done, x_done, ev in self._events:
+            if rows_done >= need and x_done >= x_upto:
+                torch.cuda.current_stream().wait_event(ev)
+                return
 
     def ensure_rows(self, upto: int, prefetch_upto: Optional[int] = None):
         """Enqueue the upload of lowres rows up to ``prefetch_upto`` (one tile row ahead) on the copy
         stream and make the compute stream wait only for the rows < ``upto`` it is about to read."""
         self._enqueue(upto)
-        need = min(upto - self.row0, self.X.shape[2])
-        for rows_done, ev in self._events:
-            if rows_done >= need:
-                torch.cuda.current_stream().wait_event(ev)
-                break
+        self.wait_for(upto, self.X.shape[3])
         if prefetch_upto is not None:
             self._enqueue(prefetch_upto)
 
@@ -365,38 +398,45 @@ def predict_continent(model, X, W1=None, W2=None, W3=None, final_shape=(18000, 2
     row_list = list(rows_of_tiles.items())
     for k, (ty, row_tiles) in enumerate(row_list):
         nxt = max(t[1] for _, t in row_list[k + 1][1]) if k + 1 < len(row_list) else None
-        g.ensure_rows(max(t[1] for _, t in row_tiles), prefetch_upto=nxt)
+        rows_upto = max(t[1] for _, t in row_tiles)
+        g.enqueue_rows(rows_upto, prefetch_upto=nxt)
+        # same-shape tiles in batches, batches ordered by their right-most grid column: a streamed upload arrives in
+        # column blocks, so the left batches of a tile row start while its right part is still on the wire
+        chunks = []
         for (h, w), tiles in group_by_shape(row_tiles).items():
             for b0 in range(0, len(tiles), batch_tiles):
-                chunk = tiles[b0:b0 + batch_tiles]
-                nb = len(chunk)
-                xb = ops.empty(nb, 1, h, w)
-                w1b = ops.empty(nb, 1, 10 * h, 10 * w)
-                w2b = ops.empty(nb, 2, 2 * h, 2 * w)
-                w3b = ops.empty(nb, 1, h, w)
-                for j, (_, (y0, y1, x0, x1, *_r)) in enumerate(chunk):
-                    yy = y0 - r0
-                    ops.call("dbm_crop_clip_f32", g.X.data_ptr(), Hs, Ws, xb[j].data_ptr(), 1, yy, x0, h, w, 0, st())
-                    ops.call("dbm_crop_clip_f32", g.W1.data_ptr(), 10 * Hs, 10 * Ws, w1b[j].data_ptr(), 1, 10 * yy,
-                             10 * x0, 10 * h, 10 * w, 1, st())
-                    ops.call("dbm_crop_clip_f32", g.W2.data_ptr(), 2 * Hs, 2 * Ws, w2b[j].data_ptr(), 2, 2 * yy, 2 * x0,
-                             2 * h, 2 * w, 1, st())
-                    ops.call("dbm_crop_clip_f32", g.W3.data_ptr(), Hs, Ws, w3b[j].data_ptr(), 1, yy, x0, h, w, 1, st())
-                y = model.forward(xb, w1b, w2b, w3b).array  # (nb, 1, 4(h-2), 4(w-2))
-                th, tw = y.shape[2], y.shape[3]
-                for j, (i, (y0, y1, x0, x1, ys, ye, xs, xe)) in enumerate(chunk):
-                    hh, ww = ye - ys, xe - xs
-                    # the reference assigns Y_pred[72:-72, 72:-72] into Y_hat[ys:ye, xs:xe] and raises
-                    # ValueError on a shape mismatch (deepbedmap.py:734-738)
-                    if (th - 2 * py, tw - 2 * px) != (hh, ww):
-                        raise ValueError(f"could not broadcast tile {(th - 2 * py, tw - 2 * px)} into {(hh, ww)}")
-                    if results is None:
-                        ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, canvas.data_ptr(),
-                                 canvas.shape[0], final_shape[1], ys - row_lo, xs, hh, ww, st())
-                    else:
-                        ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, results[i - a].data_ptr(),
-                                 ary_shape[0], ary_shape[1], 0, 0, hh, ww, st())
-                del y, xb, w1b, w2b, w3b
+                chunks.append(((h, w), tiles[b0:b0 + batch_tiles]))
+        chunks.sort(key=lambda c: max(t[3] for _, t in c[1]))
+        for (h, w), chunk in chunks:
+            g.wait_for(rows_upto, max(t[3] for _, t in chunk))
+            nb = len(chunk)
+            xb = ops.empty(nb, 1, h, w)
+            w1b = ops.empty(nb, 1, 10 * h, 10 * w)
+            w2b = ops.empty(nb, 2, 2 * h, 2 * w)
+            w3b = ops.empty(nb, 1, h, w)
+            for j, (_, (y0, y1, x0, x1, *_r)) in enumerate(chunk):
+                yy = y0 - r0
+                ops.call("dbm_crop_clip_f32", g.X.data_ptr(), Hs, Ws, xb[j].data_ptr(), 1, yy, x0, h, w, 0, st())
+                ops.call("dbm_crop_clip_f32", g.W1.data_ptr(), 10 * Hs, 10 * Ws, w1b[j].data_ptr(), 1, 10 * yy,
+                         10 * x0, 10 * h, 10 * w, 1, st())
+                ops.call("dbm_crop_clip_f32", g.W2.data_ptr(), 2 * Hs, 2 * Ws, w2b[j].data_ptr(), 2, 2 * yy, 2 * x0,
+                         2 * h, 2 * w, 1, st())
+                ops.call("dbm_crop_clip_f32", g.W3.data_ptr(), Hs, Ws, w3b[j].data_ptr(), 1, yy, x0, h, w, 1, st())
+            y = model.forward(xb, w1b, w2b, w3b).array  # (nb, 1, 4(h-2), 4(w-2))
+            th, tw = y.shape[2], y.shape[3]
+            for j, (i, (y0, y1, x0, x1, ys, ye, xs, xe)) in enumerate(chunk):
+                hh, ww = ye - ys, xe - xs
+                # the reference assigns Y_pred[72:-72, 72:-72] into Y_hat[ys:ye, xs:xe] and raises
+                # ValueError on a shape mismatch (deepbedmap.py:734-738)
+                if (th - 2 * py, tw - 2 * px) != (hh, ww):
+                    raise ValueError(f"could not broadcast tile {(th - 2 * py, tw - 2 * px)} into {(hh, ww)}")
+                if results is None:
+                    ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, canvas.data_ptr(),
+                             canvas.shape[0], final_shape[1], ys - row_lo, xs, hh, ww, st())
+                else:
+                    ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, results[i - a].data_ptr(),
+                             ary_shape[0], ary_shape[1], 0, 0, hh, ww, st())
+            del y, xb, w1b, w2b, w3b
         if stream_out:
             # this tile row of the local canvas is final: hand its rectangle to the copy stream
             ys, ye, xs, xe, _, _ = segs[ty]

@@ -554,6 +554,29 @@ def test_tiled_predictor_matches_oracle_tiler():
     assert rel_l2(got[ok], ref[ok]) < 2e-5
 
 
+def test_streamed_host_grids_and_host_dem_equal_resident_path():
+    """Pinned host grids uploaded in row bands x column blocks on the copy stream (cudaMemcpy2DAsync), finished tile
+    rows streamed into a pinned HostDEM: bit-identical to the device-resident grids / device canvas path; so is the
+    pageable (NumPy) host path."""
+    from deepbedmap_b200 import predict_continent, tiler
+    m, _ = make_generator(1, "fp32")
+    final, ary, pad = (120, 160), (40, 40), (3, 3)
+    H, W = 32, 42
+    rng = np.random.RandomState(11)
+    X = rng.rand(1, 1, H, W).astype(np.float32)
+    W1 = (rng.rand(1, 1, 10 * H, 10 * W) - 0.3).astype(np.float32)
+    W2 = (rng.rand(1, 2, 2 * H, 2 * W) - 0.3).astype(np.float32)
+    W3 = (rng.rand(1, 1, H, W) - 0.3).astype(np.float32)
+    kw = dict(final_shape=final, ary_shape=ary, stride=ary, xtrapad=pad, batch_tiles=2)
+    want = predict_continent(m, *[torch.from_numpy(a).cuda() for a in (X, W1, W2, W3)], **kw)
+    pinned = [torch.from_numpy(a).pin_memory() for a in (X, W1, W2, W3)]
+    dem = tiler.HostDEM(final)
+    dem.tensor.fill_(7.0)
+    got = predict_continent(m, tiler.HostBand(*pinned), out=dem, **kw)
+    assert np.array_equal(got, want, equal_nan=True) and np.isnan(got).any()
+    assert np.array_equal(predict_continent(m, X, W1, W2, W3, **kw), want, equal_nan=True)
+
+
 def test_int16_dem_matches_numpy_astype():
     """the DEM the reference ships is Y_hat.astype(np.int16) (deepbedmap.py:751); bit-exact."""
     from deepbedmap_b200 import ops, predict_continent
