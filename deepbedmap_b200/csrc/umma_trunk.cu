@@ -64,7 +64,7 @@ struct TrunkParams {
   unsigned long long* prof;  // tuning only (NULL = off): [num_layers][8] cycle counters, see scripts/trunk_ablate.py
   int debug;           // ablation mask for tuning runs (results invalid): 1 no dependency wait, 2 no epilogue
                        // memory traffic (32 fp32 stores only, 64 bf16 stores only, 128 residual loads only), 4 no TMA
-                       // loads, 8 / 16 fence placement
+                       // loads, 8 / 16 fence placement, 256 all images alias image 0 (what an L2-resident working set would buy)
 };
 
 __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
@@ -280,7 +280,8 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
             // order the acquired flags (generic proxy) before the TMA reads (async proxy)
             asm volatile("fence.proxy.async.global;" ::: "memory");
             mbar_arrive_expect_tx(&full[s], (uint32_t)kTABytes + b_bytes);
-            tma_load_4d(smA + s * kTABytes, tm, &full[s], (tx * kTW - 1) * 8, ty * kTH - 1, in_cs0 + kc * 2, n);
+            tma_load_4d(smA + s * kTABytes, tm, &full[s], (tx * kTW - 1) * 8, ty * kTH - 1, in_cs0 + kc * 2,
+                        (p.debug & 256) ? 0 : n);
             bulk_load(smB + s * kTBBytesMax, wp + (size_t)kc * (b_bytes / 2), b_bytes, &full[s]);
           }
         }
@@ -362,8 +363,9 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
     int L, item, buf;
     while (sc.next(cur, L, item, buf)) {
       if (buf != grp) continue;
-      const int n = item / per_img;
-      const int r = item - n * per_img;
+      const int n_img = item / per_img;
+      const int r = item - n_img * per_img;
+      const int n = (p.debug & 256) ? 0 : n_img;   // tuning: every image aliases image 0 (L2-resident working set)
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const TrunkLayer ly = p.layers[L];
       const int y0 = ty * kTH + gy;

@@ -132,9 +132,11 @@ class FlatTrunk:
     NSPLIT = 3
 
     def __init__(self, model, n: int, H: int, W: int):
-        if model.inter_channels != 32:
-            raise ValueError("the tensor-core training trunk implements inter_channels == 32")
+        if model.inter_channels not in (32, 64):
+            raise ValueError("the tensor-core training trunk implements inter_channels 32 or 64")
         self.model = model
+        self.G = G = model.inter_channels   # dense-block growth (srgan_train.py:283-284)
+        self.cc = cc = 64 + 4 * G           # channels of a dense-block buffer [a0 (64) | a1 .. a4 (G each)]
         self.n, self.H, self.W = n, H, W
         self.geom = geometry(n, H, W)
         Pg = self.geom["Pg"]
@@ -145,15 +147,15 @@ class FlatTrunk:
         zb = lambda c: torch.zeros(c // 8, Pg, 8, dtype=bf, device="cuda")
         zf = lambda c: torch.zeros(c // 4, Pg, 4, dtype=torch.float32, device="cuda")
         self.s0 = zb(128)
-        self.cat = [zb(192) for _ in range(nrdb + 1)]       # cat[j][:64] = bf16 input of RDB j, slots a1..a4 follow
-        self.gcat = [zb(192) for _ in range(nrdb)]          # [g1 | g2 | g3 | g4 | g5 (64)] gradients wrt conv outputs
+        self.cat = [zb(cc) for _ in range(nrdb + 1)]        # cat[j][:64] = bf16 input of RDB j, slots a1..a4 follow
+        self.gcat = [zb(cc) for _ in range(nrdb)]           # [g1 | g2 | g3 | g4 (G each) | g5 (64)] gradients wrt conv outputs
         self.x0 = zf(64)
         self.xring = [zf(64) for _ in range(4)]
         self.a3f = zf(64)
         self.gpost, self.gpre = zb(64), zb(64)
         self.da3f = zf(64)
         self.dX = [zf(64) for _ in range(4)]
-        self.dcat = zf(192)
+        self.dcat = zf(cc)
         self.da0f = zf(128)
         self._pack_gen = -1
         self._built_beta = None
@@ -179,6 +181,14 @@ class FlatTrunk:
             e[k] = v
         return e
 
+    def _launches(self, inp_ptr, slices, cin, blocks):
+        """One conv whose N exceeds the kernels' 192 columns as consecutive launches over N-slices of its operand
+        (``slices``: [(n0, width, packed image)], model._pack's ``@dgrad_slices``); ``blocks`` cover all of N."""
+        out = []
+        for n0, width, img in slices:
+            out.append(self._launch(inp_ptr, img, cin, width, blocks[n0 // 32:(n0 + width) // 32]))
+        return out
+
     def _launch(self, inp_ptr, wq, cin, nout, blocks):
         L = np.zeros((), dtype=LAUNCH_DTYPE)
         L["in"] = inp_ptr
@@ -197,7 +207,8 @@ class FlatTrunk:
         beta = m.residual_scaling
         if self._pack_gen == m._pack_gen and self._built_beta == beta:
             return
-        P, G = m.p, m.g
+        P, Gr = m.p, m.g
+        G, cc = self.G, self.cc
         nrdb = self.nrdb
         pb, pf, epi = self._pb, self._pf, self._epi
         plan = rdb_plan(nrdb, beta)
@@ -214,9 +225,10 @@ class FlatTrunk:
             pre = m._rdb_prefix(j // 3, r)
             cat = self.cat[j]
             for k in (1, 2, 3, 4):
-                cin = 64 + 32 * (k - 1)
+                cin = 64 + G * (k - 1)
                 wq, bq = pk[f"{pre}/conv_layer{k}@trunk"]
-                fwd.append(self._launch(pb(cat), wq, cin, 32, [epi(bias=bq.data_ptr(), act=1, out_bf16=pb(cat, cin))]))
+                fwd.append(self._launch(pb(cat), wq, cin, G, [
+                    epi(bias=bq.data_ptr() + 128 * b, act=1, out_bf16=pb(cat, cin + 32 * b)) for b in range(G // 32)]))
             wq, bq = pk[f"{pre}/conv_layer5@trunk"]
             blocks = []
             for b in range(2):
@@ -225,7 +237,7 @@ class FlatTrunk:
                 if r == 3:
                     kw.update(add2=pf(self._x(j - 2), 32 * b), beta2=beta)
                 blocks.append(epi(**kw))
-            fwd.append(self._launch(pb(cat), wq, 192, 64, blocks))
+            fwd.append(self._launch(pb(cat), wq, cc, 64, blocks))
         wq, bq = pk["post_residual_conv_layer@trunk"]
         fwd.append(self._launch(pb(self.cat[nrdb]), wq, 64, 64, [
             epi(bias=bq.data_ptr() + 128 * b, add1=pf(self.x0, 32 * b), s1=1.0, beta=1.0, out_f32=pf(self.a3f, 32 * b))
@@ -233,55 +245,58 @@ class FlatTrunk:
 
         # ---------------- data-gradient chain ----------------
         dX = lambda j: self.dX[j % 4]
+        gb = G // 32                       # 32-channel epilogue blocks per dense-block slot
+        nb5 = cc // 32                     # blocks of conv5's data gradient d[a0 .. a4]
         wq = pk["post_residual_conv_layer@dgrad"]
         bwd.append(self._launch(pb(self.gpost), wq, 64, 64, [
-            epi(out_f32=pf(dX(nrdb), 32 * b), out_bf16=pb(self.gcat[nrdb - 1], 128 + 32 * b),
+            epi(out_f32=pf(dX(nrdb), 32 * b), out_bf16=pb(self.gcat[nrdb - 1], 4 * G + 32 * b),
                 out_scale=plan[nrdb - 1]["g5_scale"]) for b in range(2)]))
         convs.append(("post_residual_conv_layer", self.cat[nrdb], 64, self.gpost, 0, 64))
         for d in reversed(plan):
             j, r, sigma = d["j"], d["r"], d["sigma"]
             pre = m._rdb_prefix(j // 3, r)
             cat, gcat = self.cat[j], self.gcat[j]
-            # conv5: g5 (64) -> d[a0..a4] (192); + skip sigma * dX_{j+1} on a0; slot a4 finalised -> g4
+            # conv5: g5 (64) -> d[a0..a4] (64 + 4G); + skip sigma * dX_{j+1} on a0; slot a4 finalised -> g4
             blocks = []
-            for b in range(6):
+            for b in range(nb5):
                 kw = {}
                 if b < 2:
                     kw.update(add1=pf(dX(j + 1), 32 * b), s1=sigma, beta=1.0)
                     if j == 0:  # the skip a3 = a1 + post_res(...) (:551) reaches a1 = input of RDB 0
                         kw.update(add2=pf(self.da3f, 32 * b), beta2=1.0)
-                if b < 5:
+                if b < nb5 - gb:
                     kw.update(out_f32=pf(self.dcat, 32 * b))
                 else:
-                    kw.update(mask=pb(cat, 32 * b), out_bf16=pb(gcat, 96))
+                    kw.update(mask=pb(cat, 32 * b), out_bf16=pb(gcat, 3 * G + 32 * (b - (nb5 - gb))))
                 blocks.append(epi(**kw))
-            bwd.append(self._launch(pb(gcat, 128), pk[f"{pre}/conv_layer5@dgrad"], 64, 192, blocks))
-            convs.append((f"{pre}/conv_layer5", cat, 192, gcat, 128, 64))
+            bwd.extend(self._launches(pb(gcat, 4 * G), pk[f"{pre}/conv_layer5@dgrad_slices"], 64, blocks))
+            convs.append((f"{pre}/conv_layer5", cat, cc, gcat, 4 * G, 64))
             for k in (4, 3, 2):
-                nout = 64 + 32 * (k - 1)
+                nout = 64 + G * (k - 1)
+                nbk = nout // 32
                 blocks = []
-                for b in range(nout // 32):
+                for b in range(nbk):
                     kw = dict(add1=pf(self.dcat, 32 * b), s1=1.0, beta=1.0)
-                    if b < nout // 32 - 1:
+                    if b < nbk - gb:
                         kw.update(out_f32=pf(self.dcat, 32 * b))
                     else:  # slot a_{k-1} is final: apply lrelu' and emit the bf16 operand of the next dgrad
-                        kw.update(mask=pb(cat, 32 * b), out_bf16=pb(gcat, 32 * (k - 2)))
+                        kw.update(mask=pb(cat, 32 * b), out_bf16=pb(gcat, G * (k - 2) + 32 * (b - (nbk - gb))))
                     blocks.append(epi(**kw))
-                bwd.append(self._launch(pb(gcat, 32 * (k - 1)), pk[f"{pre}/conv_layer{k}@dgrad"], 32, nout, blocks))
-                convs.append((f"{pre}/conv_layer{k}", cat, nout, gcat, 32 * (k - 1), 32))
+                bwd.extend(self._launches(pb(gcat, G * (k - 1)), pk[f"{pre}/conv_layer{k}@dgrad_slices"], G, blocks))
+                convs.append((f"{pre}/conv_layer{k}", cat, nout, gcat, G * (k - 1), G))
             blocks = []
             for b in range(2):
                 kw = dict(add1=pf(self.dcat, 32 * b), s1=1.0, beta=1.0)
                 if r == 1:  # RRDB skip: d x_{3i} += d x_{3i+3} (:402)
                     kw.update(add2=pf(dX(j + 3), 32 * b), beta2=1.0)
                 if j > 0:
-                    kw.update(out_f32=pf(dX(j), 32 * b), out_bf16=pb(self.gcat[j - 1], 128 + 32 * b),
+                    kw.update(out_f32=pf(dX(j), 32 * b), out_bf16=pb(self.gcat[j - 1], 4 * G + 32 * b),
                               out_scale=plan[j - 1]["g5_scale"])
                 else:   # a1 = lrelu(pre_res(a0)) (:541-544)
                     kw.update(mask=pb(self.cat[0], 32 * b), out_bf16=pb(self.gpre, 32 * b))
                 blocks.append(epi(**kw))
-            bwd.append(self._launch(pb(gcat, 0), pk[f"{pre}/conv_layer1@dgrad"], 32, 64, blocks))
-            convs.append((f"{pre}/conv_layer1", cat, 64, gcat, 0, 32))
+            bwd.append(self._launch(pb(gcat, 0), pk[f"{pre}/conv_layer1@dgrad"], G, 64, blocks))
+            convs.append((f"{pre}/conv_layer1", cat, 64, gcat, 0, G))
         bwd.append(self._launch(pb(self.gpre), pk["pre_residual_conv_layer@dgrad"], 64, 128,
                                 [epi(out_f32=pf(self.da0f, 32 * b)) for b in range(4)]))
         convs.append(("pre_residual_conv_layer", self.s0, 128, self.gpre, 0, 64))
@@ -291,12 +306,12 @@ class FlatTrunk:
         units, reduces, biases = [], [], []
         for key, act, cin, gt, g0, cout in convs:
             for half in range(cout // 32):
-                biases.append((pb(gt, g0 + 32 * half), G[f"{key}/b"].data_ptr() + 128 * half))
+                biases.append((pb(gt, g0 + 32 * half), Gr[f"{key}/b"].data_ptr() + 128 * half))
                 for c0, nch in chunk_channels(cin):
                     first = len(units)
                     for blk0, nblk in splits:
                         units.append((pb(act, c0), pb(gt, g0 + 32 * half), len(units), blk0, nblk, nch // 8, (0, 0, 0)))
-                    reduces.append((first, G[f"{key}/W"].data_ptr(), PARTIAL_FLOATS, len(splits), cin, c0, 32 * half,
+                    reduces.append((first, Gr[f"{key}/W"].data_ptr(), PARTIAL_FLOATS, len(splits), cin, c0, 32 * half,
                                     nch, 0))
         need = len(units) * PARTIAL_FLOATS
         if getattr(self, "partial", None) is None or self.partial.numel() < need:
@@ -319,7 +334,7 @@ class FlatTrunk:
         self.flops_fwd = float(sum(2.0 * 9 * int(L["cin"]) * int(L["nout"]) for L in fwd)) * self.n * self.H * self.W
         # image-resident forward (csrc/umma_local.cu) when a padded image is one UMMA tile
         self.local_dev = None
-        if local_trunk_fits(self.H, self.W):
+        if G == 32 and local_trunk_fits(self.H, self.W):
             tab = local_forward_table(m, pk, nrdb, beta, cat_ptr=lambda j, c: pb(self.cat[j], c), out_f32=pf(self.a3f))
             self.local_dev, self.n_local = dev(tab), len(tab)
             if getattr(self, "x_scratch", None) is None:

@@ -155,12 +155,9 @@ class GeneratorModel(_Link):
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
         if train_precision is None:
-            # the tensor-core training trunk (flat.py) covers the reference's inter_channels = 32
-            train_precision = "bf16" if (precision == "bf16" and inter_channels == 32) else "fp32"
+            train_precision = "bf16" if precision == "bf16" else "fp32"
         if train_precision not in ("bf16", "fp32"):
             raise ValueError("train_precision must be 'bf16' or 'fp32'")
-        if train_precision == "bf16" and inter_channels != 32:
-            raise ValueError("train_precision='bf16' implements inter_channels == 32 only")
         if inter_channels not in (32, 64):
             raise ValueError("inter_channels must be 32 or 64 (reference search space, srgan_train.py:283-284)")
         self.num_residual_blocks = int(num_residual_blocks)
@@ -317,7 +314,8 @@ class GeneratorModel(_Link):
 
     def _flat_trunk(self, n, H, W):
         from . import flat
-        pk = self._pack(self.PACK_TRAIN_LOCAL if flat.local_trunk_fits(H, W) else self.PACK_TRAIN_CHAIN)
+        pk = self._pack(self.PACK_TRAIN_LOCAL if (flat.local_trunk_fits(H, W) and self.inter_channels == 32)
+                        else self.PACK_TRAIN_CHAIN)
         ft = self._flat.get((n, H, W))
         if ft is None:
             ft = self._flat[(n, H, W)] = flat.FlatTrunk(self, n, H, W)
@@ -582,10 +580,18 @@ class GeneratorModel(_Link):
                     entry(trunk, w, img16, o, 0, cin, cin, 0, cout_padded, 16)
                     pk[key + "@trunk"] = (img16, bp)
                     if self.train_precision == "bf16":
-                        # data-gradient operand (transposed + flipped filter): GEMM N = cin, K = cout
-                        imgd = image(cin, o)
-                        entry("dgrad", w, imgd, cin, 0, o, cin, 0, cin, 16, mode=1)
-                        pk[key + "@dgrad"] = imgd
+                        # data-gradient operand (transposed + flipped filter): GEMM N = cin, K = cout; the flat kernels
+                        # take N <= 192, so wider filters (inter_channels = 64: conv4 256, conv5 320) are packed as
+                        # N-slices, one launch each
+                        slices = []
+                        for c0 in range(0, cin, 192):
+                            wdt = min(192, cin - c0)
+                            imgd = image(wdt, o)
+                            entry("dgrad", w, imgd, wdt, 0, o, cin, c0, wdt, 16, mode=1)
+                            slices.append((c0, wdt, imgd))
+                        if len(slices) == 1:
+                            pk[key + "@dgrad"] = slices[0][2]
+                        pk[key + "@dgrad_slices"] = slices
 
             add("pre_residual_conv_layer", 64, trunk="io")
             for i in range(self.num_residual_blocks):

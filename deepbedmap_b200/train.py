@@ -175,9 +175,13 @@ def set_deterministic(on: bool = True) -> None:
 
 
 def compile_srgan_model(num_residual_blocks: int = 12, residual_scaling: float = 0.1,
-                        learning_rate: float = 1.6e-4, seed: int = 0):
-    """srgan_train.py:1014-1055: returns (g_model, g_optimizer, d_model, d_optimizer)."""
-    g = GeneratorModel(num_residual_blocks=num_residual_blocks, residual_scaling=residual_scaling, seed=seed)
+                        learning_rate: float = 1.6e-4, seed: int = 0, *, inter_channels: int = 32,
+                        train_precision: Optional[str] = None):
+    """srgan_train.py:1014-1055: returns (g_model, g_optimizer, d_model, d_optimizer). ``inter_channels`` is the
+    dense-block growth of ResidualDenseBlock (srgan_train.py:283-284; 32 in the reference's final model, 64 the other
+    value of its search space); ``train_precision`` as in GeneratorModel ("bf16" tensor-core training by default)."""
+    g = GeneratorModel(num_residual_blocks=num_residual_blocks, residual_scaling=residual_scaling, seed=seed,
+                       inter_channels=inter_channels, train_precision=train_precision)
     d = DiscriminatorModel(seed=seed + 1)
     # the generator's persistent weight-gradient kernel leaves a few SMs to the discriminator chain that runs beside it
     ops.call("dbm_set_sm_reserve", WGRAD_SM_RESERVE)

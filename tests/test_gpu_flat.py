@@ -151,16 +151,18 @@ def test_flat_wgrad_and_bias_grad(flat, n, h, w, cin, nsplit):
     assert rel_l2(db, bf(g).sum(dim=(0, 2, 3))) < 1e-5
 
 
-@pytest.mark.parametrize("nb,n,beta", [(1, 3, 0.1), (2, 5, 0.2), (12, 2, 0.1)])
-def test_flat_trunk_alone_matches_oracle_autograd(nb, n, beta):
+@pytest.mark.parametrize("nb,n,beta,ic", [(1, 3, 0.1, 32), (2, 5, 0.2, 32), (12, 2, 0.1, 32), (1, 3, 0.1, 64), (2, 4, 0.2, 64)])
+def test_flat_trunk_alone_matches_oracle_autograd(nb, n, beta, ic):
     """The trunk in isolation (no deformable head in the way): a3 = a1 + post_res(RRDB^nb(a1)),
     a1 = lrelu(pre_res(a0)) forward, and d/d(a0), d/d(every trunk parameter) of sum(a3 * da3), against
     autograd on the oracle's trunk (a) with the SAME stated operand rounding (tight) and (b) exact (loose:
-    LeakyReLU sign flips, see oracle.trunk_forward)."""
+    LeakyReLU sign flips, see oracle.trunk_forward). ``ic`` = inter_channels (srgan_train.py:283-284): 64 is the wide
+    setting of the reference's search space -- the flat layer chain, data gradients of conv4 / conv5 in two N-slices."""
     from oracle import deepbedmap_oracle as O
     from deepbedmap_b200 import GeneratorModel
-    params = O.init_generator_params(nb, seed=3, bias_std=0.05, scale=1.0)
-    m = GeneratorModel(num_residual_blocks=nb, residual_scaling=beta)
+    params = O.init_generator_params(nb, seed=3, bias_std=0.05, scale=1.0, inter_channels=ic)
+    m = GeneratorModel(num_residual_blocks=nb, residual_scaling=beta, inter_channels=ic)
+    assert m.train_precision == "bf16"
     for k, v in params.items():
         m.set_param(k, v)
     H = W = 9
@@ -179,7 +181,7 @@ def test_flat_trunk_alone_matches_oracle_autograd(nb, n, beta):
         e_fwd, e_da0 = rel_l2(a3, a3r.detach()), rel_l2(da0, a0r.grad)
         errs = {k: rel_l2(m.g[k], p64[k].grad) for k in trunk_keys}
         worst = max(errs, key=errs.get)
-        print(f"trunk alone nb={nb} vs {'bf16-operand' if emulate else 'exact'} oracle: forward {e_fwd:.2e}, "
+        print(f"trunk alone nb={nb} ic={ic} vs {'bf16-operand' if emulate else 'exact'} oracle: forward {e_fwd:.2e}, "
               f"d/d(a0) {e_da0:.2e}, worst parameter gradient {worst} {errs[worst]:.2e}, "
               f"median {float(np.median(list(errs.values()))):.2e}")
         assert e_fwd < tol_fwd and e_da0 < tol_da0
@@ -187,14 +189,15 @@ def test_flat_trunk_alone_matches_oracle_autograd(nb, n, beta):
         assert float(np.median(list(errs.values()))) < tol_med
 
 
-@pytest.mark.parametrize("nb,n,H,W", [(1, 3, 9, 9), (12, 128, 9, 9), (2, 40, 30, 23), (1, 1, 5, 4)])
-def test_persistent_chain_equals_per_layer_launches(nb, n, H, W):
+@pytest.mark.parametrize("nb,n,H,W,ic", [(1, 3, 9, 9, 32), (12, 128, 9, 9, 32), (2, 40, 30, 23, 32), (1, 1, 5, 4, 32),
+                                         (2, 128, 9, 9, 64), (1, 7, 12, 10, 64)])
+def test_persistent_chain_equals_per_layer_launches(nb, n, H, W, ic):
     """The one-launch forward / data-gradient chains (flag-synchronised tiles) are bit-identical to launching
     every layer on its own; (2, 40, 30, 23) gives several tiles per CTA (more than 148 tiles)."""
     from oracle import deepbedmap_oracle as O
     from deepbedmap_b200 import GeneratorModel
-    params = O.init_generator_params(nb, seed=5, bias_std=0.05, scale=0.7)
-    m = GeneratorModel(num_residual_blocks=nb)
+    params = O.init_generator_params(nb, seed=5, bias_std=0.05, scale=0.7, inter_channels=ic)
+    m = GeneratorModel(num_residual_blocks=nb, inter_channels=ic)
     for k, v in params.items():
         m.set_param(k, v)
     a0 = rnd(n, 128, H, W, seed=21)
@@ -229,8 +232,8 @@ def test_image_resident_trunk_equals_flat_chain(nb, n, H, W):
     per CTA."""
     from oracle import deepbedmap_oracle as O
     from deepbedmap_b200 import GeneratorModel
-    params = O.init_generator_params(nb, seed=5, bias_std=0.05, scale=0.7)
-    m = GeneratorModel(num_residual_blocks=nb)
+    params = O.init_generator_params(nb, seed=5, bias_std=0.05, scale=0.7, inter_channels=ic)
+    m = GeneratorModel(num_residual_blocks=nb, inter_channels=ic)
     for k, v in params.items():
         m.set_param(k, v)
     a0 = rnd(n, 128, H, W, seed=21)
@@ -263,15 +266,16 @@ def test_image_resident_trunk_equals_flat_chain(nb, n, H, W):
     assert e_da0 < 2e-3 and e_grad < 2e-3
 
 
-@pytest.mark.parametrize("nb,n,scale", [(1, 3, 0.5), (2, 5, 0.5), (12, 2, 0.5)])
-def test_generator_tensor_core_backward_matches_oracle(nb, n, scale):
+@pytest.mark.parametrize("nb,n,scale,ic", [(1, 3, 0.5, 32), (2, 5, 0.5, 32), (12, 2, 0.5, 32), (2, 3, 0.5, 64)])
+def test_generator_tensor_core_backward_matches_oracle(nb, n, scale, ic):
     """Whole-generator G-step gradients with the trunk on the tensor cores (stem and head fp32):
     against autograd on the oracle graph whose trunk carries the same operand rounding. (12, 2, 0.5) is the
     reference's full depth: all 384 parameter arrays of the 12-RRDB generator."""
     from oracle import deepbedmap_oracle as O
     from deepbedmap_b200 import GeneratorModel
-    params = O.init_generator_params(nb, seed=0, bias_std=0.05, scale=scale)
-    m = GeneratorModel(num_residual_blocks=nb, residual_scaling=0.1, precision="bf16", train_precision="bf16")
+    params = O.init_generator_params(nb, seed=0, bias_std=0.05, scale=scale, inter_channels=ic)
+    m = GeneratorModel(num_residual_blocks=nb, residual_scaling=0.1, precision="bf16", train_precision="bf16",
+                       inter_channels=ic)
     for k, v in params.items():
         m.set_param(k, v)
     ins = O.synthetic_inputs(n, 11, 11)
@@ -287,7 +291,7 @@ def test_generator_tensor_core_backward_matches_oracle(nb, n, scale):
         e_fwd = rel_l2(y, y_ref.detach())
         errs = {k: rel_l2(m.g[k], p64[k].grad) for k in m.p}
         worst = max(errs, key=errs.get)
-        print(f"generator nb={nb} vs {'bf16-trunk' if emulate else 'exact'} oracle: forward {e_fwd:.2e}, worst "
+        print(f"generator nb={nb} ic={ic} vs {'bf16-trunk' if emulate else 'exact'} oracle: forward {e_fwd:.2e}, worst "
               f"parameter gradient {worst} {errs[worst]:.2e}, median {float(np.median(list(errs.values()))):.2e}")
         assert e_fwd < tol_fwd
         assert errs[worst] < tol_grad, (worst, errs[worst])
