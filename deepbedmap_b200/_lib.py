@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeepbedmap_b200.so")
+# DEEPBEDMAP_B200_LIB: another build of the same library (A/B timing of two builds on one box, scripts/)
+LIB_PATH = os.environ.get("DEEPBEDMAP_B200_LIB") or os.path.join(_HERE, "libdeepbedmap_b200.so")
 
 _P, _L, _I, _F = ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_float
 
@@ -40,6 +41,9 @@ SIGNATURES = {
     "dbm_pack_conv3x3_weights_slice": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     "dbm_pack_conv3x3_table": [_P, _I, _L, _P],
     "dbm_trunk_umma": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P],
+    "dbm_trunk_umma_split": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P],
+    "dbm_nchw_to_slab8_split": [_P, _L, _P, _I, _I, _I, _I, _P],
+    "dbm_slab8f_to_nchw": [_P, _P, _L, _I, _I, _I, _I, _P],
     "dbm_flat_geometry": [_I, _I, _I, _P],
     "dbm_flat_conv3x3_seq": [_P, _I, _I, _I, _I, _I, _I, _P],
     "dbm_flat_conv3x3_chain": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
@@ -122,7 +126,12 @@ def load() -> ctypes.CDLL:
     lib.dbm_last_error.restype = ctypes.c_char_p
     lib.dbm_last_error.argtypes = []
     for name, args in list(SIGNATURES.items()) + list(TUNING_SIGNATURES.items()):
-        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        try:
+            fn = getattr(lib, name)  # AttributeError if the library does not export it
+        except AttributeError:
+            if os.environ.get("DEEPBEDMAP_B200_LIB"):   # an older build under A/B test may lack newer entry points
+                continue
+            raise
         fn.argtypes = args
         fn.restype = RESTYPES.get(name, ctypes.c_int)
     _lib = lib

@@ -145,6 +145,48 @@ __global__ void slab4_to_nchw_kernel(const float* __restrict__ src, float* __res
   }
 }
 
+// fp32 NCHW -> split-bf16 slab8 (dbm_trunk_umma_split): per 16 channels the slabs [hi a | hi b | lo a | lo b],
+// v = hi + lo, hi = bf16(v), lo = bf16(v - hi)
+__global__ void nchw_to_slab8_split_kernel(const float* __restrict__ src, long src_bs, __nv_bfloat16* __restrict__ dst,
+                                           int N, int C, int HW) {
+  const long total = (long)N * (C / 8) * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int px = i % HW;
+    const long t = i / HW;
+    const int cs = t % (C / 8);
+    const int n = t / (C / 8);
+    const float* s = src + n * src_bs + (long)cs * 8 * HW + px;
+    __nv_bfloat162 hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = s[(2 * k) * (long)HW], b = s[(2 * k + 1) * (long)HW];
+      hi[k] = __floats2bfloat162_rn(a, b);
+      const float2 f = __bfloat1622float2(hi[k]);
+      lo[k] = __floats2bfloat162_rn(a - f.x, b - f.y);
+    }
+    const long ps = ((cs >> 1) << 2) + (cs & 1);   // physical slab of the hi part
+    *reinterpret_cast<uint4*>(dst + (((long)n * (C / 4) + ps) * HW + px) * 8) = *reinterpret_cast<uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + (((long)n * (C / 4) + ps + 2) * HW + px) * 8) = *reinterpret_cast<uint4*>(lo);
+  }
+}
+// fp32 slab8f [N][C/8][HW][8] (the trunk kernels' fp32 outputs) -> NCHW
+__global__ void slab8f_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, long dst_bs, int N, int C,
+                                      int HW) {
+  const long total = (long)N * (C / 8) * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int px = i % HW;
+    const long t = i / HW;
+    const int cs = t % (C / 8);
+    const int n = t / (C / 8);
+    const float4 v0 = *reinterpret_cast<const float4*>(src + i * 8);
+    const float4 v1 = *reinterpret_cast<const float4*>(src + i * 8 + 4);
+    float* d = dst + n * dst_bs + (long)cs * 8 * HW + px;
+    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k * (long)HW] = vv[k];
+  }
+}
+
 // ---- strided element-wise ops on (batch, inner) views of NCHW tensors --------------------------
 // out = a*x + b*y   (F.add(a5 * residual_scaling, a0), srgan_train.py:358, 402, 551)
 __global__ void axpby_kernel(const float* __restrict__ x, long x_bs, const float* __restrict__ y, long y_bs,
@@ -311,6 +353,22 @@ extern "C" int dbm_slab8_to_nchw(const void* src, int src_cs_total, int src_cs0,
                                                        dst_batch_stride ? dst_batch_stride : (long)c * h * w, n, c,
                                                        h * w);
   return check_launch("slab8_to_nchw");
+}
+extern "C" int dbm_nchw_to_slab8_split(const float* src, long src_batch_stride, void* dst, int n, int c, int h, int w,
+                                       cudaStream_t st) {
+  DBM_REQUIRE(c % 16 == 0, "nchw_to_slab8_split: C=%d not a multiple of 16", c);
+  const long total = (long)n * (c / 8) * h * w;
+  nchw_to_slab8_split_kernel<<<ew_grid(total), 256, 0, st>>>(
+      src, src_batch_stride ? src_batch_stride : (long)c * h * w, (__nv_bfloat16*)dst, n, c, h * w);
+  return check_launch("nchw_to_slab8_split");
+}
+extern "C" int dbm_slab8f_to_nchw(const float* src, float* dst, long dst_batch_stride, int n, int c, int h, int w,
+                                  cudaStream_t st) {
+  DBM_REQUIRE(c % 8 == 0, "slab8f_to_nchw: C=%d not a multiple of 8", c);
+  const long total = (long)n * (c / 8) * h * w;
+  slab8f_to_nchw_kernel<<<ew_grid(total), 256, 0, st>>>(src, dst, dst_batch_stride ? dst_batch_stride : (long)c * h * w,
+                                                        n, c, h * w);
+  return check_launch("slab8f_to_nchw");
 }
 extern "C" int dbm_nchw_to_slab4(const float* src, long src_batch_stride, float* dst, int n, int c, int h, int w,
                                  cudaStream_t st) {

@@ -338,7 +338,12 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)
 }
 
 __global__ void pack_w3x3_table_kernel(const PackEntry* __restrict__ table) {
-  const PackEntry e = table[blockIdx.y];
+  PackEntry e = table[blockIdx.y];
+  // mode bit 16: split-bf16 image for dbm_trunk_umma_split -- every 16-channel chunk kc becomes three chunks
+  // [w_hi | w_hi | w_lo] (w = w_hi + w_lo, both bf16); forward slices with 8-aligned rows only
+  const bool split = (e.mode & 16) != 0;
+  e.mode &= 15;
+  if (split && !(e.mode == 0 && (e.O & 7) == 0 && (e.o0 & 7) == 0 && e.CK == 16)) return;   // rejected on the host
   if (e.mode == 0 && (e.O & 7) == 0 && (e.o0 & 7) == 0) {
     // stacked forward slices (pair / tail / input-stationary images): visit only this entry's own rows -- the general
     // loop below scans the whole image for every entry that writes into it
@@ -353,12 +358,20 @@ __global__ void pack_w3x3_table_kernel(const PackEntry* __restrict__ table) {
       const int kc = (int)t;
       const int o = cgl * 8 + o8;
       const int c = kc * e.CK + ksl * 8;
-      const long dst = ((((long)(kc * 9 + tap) * (e.CK / 8) + ksl) * (e.COUTP / 8) + (e.o0 / 8 + cgl)) * 8 + o8) * 8;
+      const int kcd = split ? 3 * kc : kc;
+      const long dst = ((((long)(kcd * 9 + tap) * (e.CK / 8) + ksl) * (e.COUTP / 8) + (e.o0 / 8 + cgl)) * 8 + o8) * 8;
       const float* src = e.w + ((long)o * e.CinTotal + e.c0 + c) * 9 + tap;
       float v[8];
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) v[c8] = src[c8 * 9];
       store8_bf16(e.out + dst, v);
+      if (split) {
+        const long chunk = (long)9 * (e.CK / 8) * (e.COUTP / 8) * 64;
+        store8_bf16(e.out + dst + chunk, v);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) v[c8] -= __bfloat162float(__float2bfloat16_rn(v[c8]));
+        store8_bf16(e.out + dst + 2 * chunk, v);
+      }
     }
     return;
   }

@@ -100,6 +100,23 @@ __device__ __forceinline__ void st_f8(float* p, float a0, float a1, float a2, fl
                : "memory");
 }
 
+// Split-bf16 storage: v = hi + lo with hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits together).
+__device__ __forceinline__ void split_bf16x8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 f = __bfloat1622float2(t);
+    const __nv_bfloat162 u = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&t);
+    l[i] = *reinterpret_cast<const uint32_t*>(&u);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// physical slab of logical 8-channel slab L in a split buffer: per 16 channels [hi a | hi b | lo a | lo b]
+__device__ __forceinline__ int split_slab(int L) { return ((L >> 1) << 2) + (L & 1); }
+
 // ---- schedule -----------------------------------------------------------------------------------------------
 // The pass table is cut into GROUPS: a pair (head, tail) or a single pass. Within a group the I = N x tiles units are
 // dealt to the Gd = gridDim.x resident CTAs in rounds of Gd; a rotation that advances by I mod Gd per group moves the
@@ -148,6 +165,9 @@ struct Sched {
   }
 };
 
+// SPLIT: split-bf16 arithmetic (dbm_trunk_umma_split) -- a template parameter so that the bf16 instantiation carries
+// none of its address arithmetic (a run-time flag cost the bf16 path 6 %: 739 -> 694 TFLOP/s on the same box)
+template <bool SPLIT>
 __global__ void __launch_bounds__(kTrunkThreads, 1)
 umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -270,8 +290,15 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
       v_cur = f_cur != nullptr ? ld_relaxed_gpu(f_cur) : need;
       const CUtensorMap* tm = &maps.m[in_map];
       const uint32_t b_bytes = (uint32_t)(9 * 16 * 2) * (uint32_t)cout;
-      const int num_kc = cin >> 4;
+      // split mode: per 16 input channels three K chunks  x_hi.w_hi + x_lo.w_hi + x_hi.w_lo  (the packed filter holds
+      // [w_hi | w_hi | w_lo] per chunk; the activation buffers hold [hi a | hi b | lo a | lo b] slabs per 16 channels)
+      const int num_kc = SPLIT ? 3 * (cin >> 4) : (cin >> 4);
       for (int kc = 0; kc < num_kc; ++kc) {
+        int slab = in_cs0 + kc * 2;
+        if constexpr (SPLIT) {
+          const int c16 = kc / 3, t = kc - 3 * c16;
+          slab = 2 * in_cs0 + 4 * c16 + (t == 1 ? 2 : 0);
+        }
         mbar_wait(&empty[s], ph ^ 1);
         if (elect_one_sync()) {
           if (p.debug & 4) {
@@ -280,7 +307,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
             // order the acquired flags (generic proxy) before the TMA reads (async proxy)
             asm volatile("fence.proxy.async.global;" ::: "memory");
             mbar_arrive_expect_tx(&full[s], (uint32_t)kTABytes + b_bytes);
-            tma_load_4d(smA + s * kTABytes, tm, &full[s], (tx * kTW - 1) * 8, ty * kTH - 1, in_cs0 + kc * 2,
+            tma_load_4d(smA + s * kTABytes, tm, &full[s], (tx * kTW - 1) * 8, ty * kTH - 1, slab,
                         (p.debug & 256) ? 0 : n);
             bulk_load(smB + s * kTBBytesMax, wp + (size_t)kc * (b_bytes / 2), b_bytes, &full[s]);
           }
@@ -303,7 +330,7 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
     while (sc.next(cur, L, unit, buf)) {
       const int4 li = linfo[L];
       const int cin = li.x, cout = li.y, mode = li.z >> 8;
-      const int num_kc = cin >> 4;
+      const int num_kc = SPLIT ? 3 * (cin >> 4) : (cin >> 4);
       const long long t0 = p.prof ? clock64() : 0;
       mbar_wait(&tempty[buf], (use[buf] & 1) ^ 1);
       ++use[buf];
@@ -457,6 +484,14 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v[i] = lrelu(v[i]);
                 }
+                if constexpr (SPLIT) {
+                  uint4 hi, lo;
+                  split_bf16x8(v, hi, lo);
+                  const size_t cs = (size_t)n * (2 * ly.out_cs_total) + split_slab(ly.out_cs0 + s8);
+                  *reinterpret_cast<uint4*>(ly.out_bf16 + (cs * plane + pix) * 8) = hi;
+                  *reinterpret_cast<uint4*>(ly.out_bf16 + ((cs + 2) * plane + pix) * 8) = lo;
+                  continue;
+                }
                 uint4 o;
                 __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]);
                 __nv_bfloat162 t1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -528,25 +563,36 @@ umma_trunk_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
         if (ly.out_bf16 && mem_bf16) {
 #pragma unroll
           for (int s8 = 0; s8 < 4; ++s8) {
-            uint4 o;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * s8 + 0], v[8 * s8 + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * s8 + 2], v[8 * s8 + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * s8 + 4], v[8 * s8 + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * s8 + 6], v[8 * s8 + 7]);
-            o.x = *reinterpret_cast<uint32_t*>(&t0);
-            o.y = *reinterpret_cast<uint32_t*>(&t1);
-            o.z = *reinterpret_cast<uint32_t*>(&t2);
-            o.w = *reinterpret_cast<uint32_t*>(&t3);
-            const size_t cs = (size_t)n * ly.out_cs_total + (ly.out_cs0 + c0 / 8 + s8);
-            if (!ly.up2) {
-              *reinterpret_cast<uint4*>(ly.out_bf16 + (cs * plane + pix) * 8) = o;
+            uint4 o, o_lo = make_uint4(0, 0, 0, 0);
+            size_t cs;
+            if constexpr (SPLIT) {
+              split_bf16x8(v + 8 * s8, o, o_lo);
+              cs = (size_t)n * (2 * ly.out_cs_total) + split_slab(ly.out_cs0 + c0 / 8 + s8);
             } else {
-              const int Ho = 2 * p.H, Wo = 2 * p.W;
-              __nv_bfloat16* base = ly.out_bf16 + ((cs * Ho + 2 * y) * Wo + 2 * x) * 8;
-              *reinterpret_cast<uint4*>(base) = o;
-              *reinterpret_cast<uint4*>(base + 8) = o;
-              *reinterpret_cast<uint4*>(base + (size_t)Wo * 8) = o;
-              *reinterpret_cast<uint4*>(base + (size_t)Wo * 8 + 8) = o;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * s8 + 0], v[8 * s8 + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * s8 + 2], v[8 * s8 + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * s8 + 4], v[8 * s8 + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * s8 + 6], v[8 * s8 + 7]);
+              o.x = *reinterpret_cast<uint32_t*>(&t0);
+              o.y = *reinterpret_cast<uint32_t*>(&t1);
+              o.z = *reinterpret_cast<uint32_t*>(&t2);
+              o.w = *reinterpret_cast<uint32_t*>(&t3);
+              cs = (size_t)n * ly.out_cs_total + (ly.out_cs0 + c0 / 8 + s8);
+            }
+#pragma unroll 1
+            for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {   // split: the lo slab lies two slabs further
+              const uint4 ov = part ? o_lo : o;
+              const size_t csp = cs + 2 * part;
+              if (!ly.up2) {
+                *reinterpret_cast<uint4*>(ly.out_bf16 + (csp * plane + pix) * 8) = ov;
+              } else {
+                const int Ho = 2 * p.H, Wo = 2 * p.W;
+                __nv_bfloat16* base = ly.out_bf16 + ((csp * Ho + 2 * y) * Wo + 2 * x) * 8;
+                *reinterpret_cast<uint4*>(base) = ov;
+                *reinterpret_cast<uint4*>(base + 8) = ov;
+                *reinterpret_cast<uint4*>(base + (size_t)Wo * 8) = ov;
+                *reinterpret_cast<uint4*>(base + (size_t)Wo * 8 + 8) = ov;
+              }
             }
           }
         }
@@ -592,16 +638,17 @@ extern "C" int dbm_debug_set_ptr(int key, void* ptr) {
   return DBM_OK;
 }
 
-extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
-                              int stem_cs_total, const void* cat_a_slab8, const void* cat_b_slab8, int cat_cs_total,
-                              unsigned int* flags_dev, cudaStream_t stream) {
+static int trunk_umma_launch(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
+                             int stem_cs_total, const void* cat_a_slab8, const void* cat_b_slab8, int cat_cs_total,
+                             unsigned int* flags_dev, int split, cudaStream_t stream) {
   DBM_REQUIRE(num_layers > 0 && n > 0 && h > 0 && w > 0, "trunk: empty problem");
   DBM_REQUIRE(num_layers <= kMaxTrunkLayers, "trunk: %d passes exceed the kernel's table of %d", num_layers,
               kMaxTrunkLayers);
   DBM_REQUIRE(((uintptr_t)layers_dev & 7) == 0, "trunk: layer table must be 8-byte aligned");
   TrunkMaps maps;
   const void* bases[3] = {stem_slab8, cat_a_slab8, cat_b_slab8};
-  const int cs_tot[3] = {stem_cs_total, cat_cs_total, cat_cs_total};
+  // split buffers hold a hi and a lo slab per logical slab
+  const int cs_tot[3] = {stem_cs_total << split, cat_cs_total << split, cat_cs_total << split};
   for (int i = 0; i < 3; ++i) {
     int rc = make_slab8_tmap(&maps.m[i], bases[i], n, cs_tot[i], h, w, 16, kHW, kHH);
     if (rc) return rc;
@@ -620,9 +667,34 @@ extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int
   // every CTA must be co-resident (items spin on flags set by other CTAs): the grid never exceeds what the occupancy
   // query says this device holds at once (one CTA per SM with 200+ KB of shared memory)
   int resident = 0;
-  int rc2 = resident_ctas((const void*)umma_trunk_kernel, kTrunkThreads, kTrunkSmem, &resident);
+  const void* kfn = split ? (const void*)umma_trunk_kernel<true> : (const void*)umma_trunk_kernel<false>;
+  int rc2 = resident_ctas(kfn, kTrunkThreads, kTrunkSmem, &resident);
   if (rc2) return rc2;
   const int grid = total < resident ? (int)total : resident;
-  umma_trunk_kernel<<<grid, kTrunkThreads, kTrunkSmem, stream>>>(maps, p);
+  if (split)
+    umma_trunk_kernel<true><<<grid, kTrunkThreads, kTrunkSmem, stream>>>(maps, p);
+  else
+    umma_trunk_kernel<false><<<grid, kTrunkThreads, kTrunkSmem, stream>>>(maps, p);
   return check_launch("umma_trunk_kernel");
+}
+
+extern "C" int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
+                              int stem_cs_total, const void* cat_a_slab8, const void* cat_b_slab8, int cat_cs_total,
+                              unsigned int* flags_dev, cudaStream_t stream) {
+  return trunk_umma_launch(layers_dev, num_layers, n, h, w, stem_slab8, stem_cs_total, cat_a_slab8, cat_b_slab8,
+                           cat_cs_total, flags_dev, 0, stream);
+}
+
+// The same pass table in split-bf16 arithmetic (precision "bf16x3"): every activation and filter is carried as
+// hi + lo bf16 terms and each 16-channel K chunk is contracted three times (x_hi w_hi + x_lo w_hi + x_hi w_lo; the
+// dropped x_lo w_lo term is 2^-16 relative), accumulating in fp32 -- fp32-grade results on the bf16 tensor pipe at three
+// times the MMA work. Buffers: bf16 slab8 with 2 x cs_total slabs, per 16 channels [hi a | hi b | lo a | lo b];
+// filters packed by dbm_pack_conv3x3_table entries with mode bit 16 ([w_hi | w_hi | w_lo] per 16-channel chunk).
+// Table fields (in_cs0, out_cs0, out_cs_total, cin) stay LOGICAL.
+extern "C" int dbm_trunk_umma_split(const void* layers_dev, int num_layers, int n, int h, int w,
+                                    const void* stem_slab8, int stem_cs_total, const void* cat_a_slab8,
+                                    const void* cat_b_slab8, int cat_cs_total, unsigned int* flags_dev,
+                                    cudaStream_t stream) {
+  return trunk_umma_launch(layers_dev, num_layers, n, h, w, stem_slab8, stem_cs_total, cat_a_slab8, cat_b_slab8,
+                           cat_cs_total, flags_dev, 1, stream);
 }

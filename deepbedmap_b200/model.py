@@ -152,10 +152,10 @@ class GeneratorModel(_Link):
                  residual_scaling: float = 0.1, out_channels: int = 1, *, inter_channels: int = 32,
                  precision: str = "bf16", train_precision: Optional[str] = None, seed: int = 0,
                  init_scale: float = 0.1):
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision not in ("bf16", "bf16x3", "fp32"):
+            raise ValueError("precision must be 'bf16', 'bf16x3' or 'fp32'")
         if train_precision is None:
-            train_precision = "bf16" if precision == "bf16" else "fp32"
+            train_precision = "fp32" if precision == "fp32" else "bf16"
         if train_precision not in ("bf16", "fp32"):
             raise ValueError("train_precision must be 'bf16' or 'fp32'")
         if inter_channels not in (32, 64):
@@ -213,6 +213,8 @@ class GeneratorModel(_Link):
         self._check_shapes(x, w1, w2, w3)
         if self.precision == "bf16":
             y = self._forward_bf16(x, w1, w2, w3)
+        elif self.precision == "bf16x3":
+            y = self._forward_split(x, w1, w2, w3)
         else:
             y = self._forward_fp32(x, w1, w2, w3, save=False)
         return Variable(y)
@@ -538,6 +540,7 @@ class GeneratorModel(_Link):
     PACK_INFER_LOCAL = ("io", "stat", "infer", "deform")              # inference on tiles that fit the image-resident kernel
     PACK_TRAIN_LOCAL = ("io", "stat", "dgrad", "deform")              # training, image-resident trunk
     PACK_TRAIN_CHAIN = ("io", "trunk16", "stat", "dgrad", "deform")   # training, flat chain (any tile size)
+    PACK_SPLIT = ("split",)                                           # precision="bf16x3": split-bf16 trunk + upsample convs
 
     def _pack(self, groups=None):
         """bf16 UMMA operand images of every 3x3 filter (+ the stem's tap-major fp32 filters). The
@@ -554,7 +557,7 @@ class GeneratorModel(_Link):
         P = self.p
         if self._pack_plan is None:
             pk = {}
-            entries = {g: [] for g in ("io", "trunk16", "infer", "stat", "dgrad", "deform")}
+            entries = {g: [] for g in ("io", "trunk16", "infer", "stat", "dgrad", "deform", "split")}
             pad_biases = []   # (padded bias buffer, source bias)
 
             def image(cin, cout_padded):
@@ -631,6 +634,38 @@ class GeneratorModel(_Link):
                                 entry("stat", P[f"{pre}/conv_layer{k}/W"], stat, 64 if k == 5 else 32, 32 * (k - 1 - s_),
                                       cblk, 64 + 32 * (k - 1), c0, ncol, 16)
                             pk[f"{pre}/stat{s_}"] = stat
+            if self.precision == "bf16x3":
+                # split-bf16 operand images (dbm_trunk_umma_split): per 16-channel chunk [w_hi | w_hi | w_lo], 3x the
+                # size of a bf16 image; the trunk's passes (paired plan for inter_channels = 32) and the upsample convs
+                def add_split(name, slices, cin, coutp, bias):
+                    img = ops.zeros(3 * 9 * cin * coutp, dtype=torch.bfloat16)
+                    for wkey, o, o0, cin_total, c0 in slices:
+                        entry("split", P[wkey], img, o, o0, cin, cin_total, c0, coutp, 16, mode=16)
+                    pk[name + "@split"] = (img, bias)
+
+                g_ = self.inter_channels
+                for key in ("pre_residual_conv_layer", "post_residual_conv_layer", "post_upsample_conv_layer_1",
+                            "post_upsample_conv_layer_2"):
+                    w = P[f"{key}/W"]
+                    add_split(key, [(f"{key}/W", w.shape[0], 0, w.shape[1], 0)], w.shape[1], 64, P[f"{key}/b"])
+                for i in range(self.num_residual_blocks):
+                    for r in (1, 2, 3):
+                        pre = self._rdb_prefix(i, r)
+                        add_split(f"{pre}/conv_layer5", [(f"{pre}/conv_layer5/W", 64, 0, 64 + 4 * g_, 0)], 64 + 4 * g_, 64,
+                                  P[f"{pre}/conv_layer5/b"])
+                        if g_ == 32:
+                            for k in (1, 3):
+                                cin = 64 + (k - 1) * 32
+                                add_split(f"{pre}/pair{k}", [(f"{pre}/conv_layer{k}/W", 32, 0, cin, 0),
+                                                             (f"{pre}/conv_layer{k + 1}/W", 32, 32, cin + 32, 0)], cin, 64,
+                                          P[f"{pre}/conv_layer{k}/b"])
+                                add_split(f"{pre}/tail{k + 1}", [(f"{pre}/conv_layer{k + 1}/W", 32, 0, cin + 32, cin)], 32,
+                                          32, P[f"{pre}/conv_layer{k + 1}/b"])
+                        else:
+                            for k in (1, 2, 3, 4):
+                                cin = 64 + (k - 1) * g_
+                                add_split(f"{pre}/conv_layer{k}", [(f"{pre}/conv_layer{k}/W", g_, 0, cin, 0)], cin, g_,
+                                          P[f"{pre}/conv_layer{k}/b"])
             for key in ("post_upsample_conv_layer_1", "post_upsample_conv_layer_2"):
                 add(key, 64)
             add("final_conv_layer1/offset_conv", 32)
@@ -841,6 +876,129 @@ class GeneratorModel(_Link):
 
     def __del__(self):
         self._c_release()
+
+    # ---- precision="bf16x3": split-bf16 tensor-core path (fp32-grade results) ----
+    def _split_workspace(self, n, H, W, pk):
+        """Buffers + pass tables of the split-bf16 path: the trunk table (same passes as the bf16 path, dense-block
+        pairing included) and one single-pass table per upsample conv (the same kernel at 2x / 4x the resolution)."""
+        key = ("split", n, H, W)
+        ws = self._ws.get(key)
+        if ws is not None and ws["version"] == (self._pack_gen, self.residual_scaling):
+            return ws
+        bf = torch.bfloat16
+        g = self.inter_channels
+        cc = 64 + 4 * g
+        ccs = cc // 8
+        beta = self.residual_scaling
+        if ws is None:
+            ws = dict(s0=ops.empty(n, 32, H, W, 8, dtype=bf), cat=[ops.empty(n, 2 * ccs, H, W, 8, dtype=bf) for _ in range(2)],
+                      a1_f32=ops.empty(n, 16, H, W, 4), f32=[ops.empty(n, 16, H, W, 4) for _ in range(3)],
+                      u1=ops.empty(n, 16, 2 * H, 2 * W, 8, dtype=bf), u2=ops.empty(n, 16, 4 * H, 4 * W, 8, dtype=bf),
+                      c2f=ops.empty(n, 16, 4 * H, 4 * W, 4))
+        cat, f32, a1_f32 = ws["cat"], ws["f32"], ws["a1_f32"]
+        paired = g == 32 and (W + 15) // 16 + 2 <= 128
+
+        def rec(wkey, cin, cout, in_map, act=0, beta_=0.0, out=None, out_cs0=0, out_f32=None, res1=None, res2=None,
+                up2=0, in_cs0=0, cout_main=None, mode=0):
+            wq, bq = pk[wkey + "@split"]
+            ptr = lambda t: t.data_ptr() if t is not None else 0
+            # out_cs_total is LOGICAL (the buffers hold a hi and a lo slab per logical slab)
+            return (wq.data_ptr(), bq.data_ptr(), ptr(out), ptr(out_f32), ptr(res1), ptr(res2), 0, cin, cout, in_map,
+                    in_cs0, act, up2, out.shape[1] // 2 if out is not None else 0, out_cs0,
+                    cout if cout_main is None else cout_main, 16, beta_, mode, (0,) * 6)
+
+        layers = [rec("pre_residual_conv_layer", 128, 64, 0, act=1, out=cat[0], out_f32=a1_f32)]
+        cur, cur_f32, fi = 0, a1_f32, 0
+        for i in range(self.num_residual_blocks):
+            rrdb_in = cur_f32
+            for r in (1, 2, 3):
+                pre = self._rdb_prefix(i, r)
+                if paired:
+                    for k in (1, 3):
+                        cin = 64 + (k - 1) * g
+                        layers.append(rec(f"{pre}/pair{k}", cin, 64, 1 + cur, act=1, out=cat[cur], out_cs0=cin // 8,
+                                          cout_main=32, mode=1))
+                        layers.append(rec(f"{pre}/tail{k + 1}", 32, 32, 1 + cur, in_cs0=cin // 8, act=1, out=cat[cur],
+                                          out_cs0=cin // 8 + 4, mode=2))
+                else:
+                    if g == 32:   # only the paired images are packed for the split path
+                        raise ValueError("precision='bf16x3': tiles wider than ~2000 px are not supported")
+                    for k in (1, 2, 3, 4):
+                        cin = 64 + (k - 1) * g
+                        layers.append(rec(f"{pre}/conv_layer{k}", cin, g, 1 + cur, act=1, out=cat[cur], out_cs0=cin // 8))
+                while f32[fi] is cur_f32 or f32[fi] is rrdb_in:
+                    fi = (fi + 1) % 3
+                nxt_f32 = f32[fi]
+                layers.append(rec(f"{pre}/conv_layer5", cc, 64, 1 + cur, beta_=beta, out=cat[1 - cur], out_f32=nxt_f32,
+                                  res1=cur_f32, res2=rrdb_in if r == 3 else None))
+                cur, cur_f32 = 1 - cur, nxt_f32
+        layers.append(rec("post_residual_conv_layer", 64, 64, 1 + cur, beta_=1.0, out=ws["u1"], res1=a1_f32, up2=1))
+        up1 = [rec("post_upsample_conv_layer_1", 64, 64, 0, act=1, out=ws["u2"], up2=1)]
+        up2 = [rec("post_upsample_conv_layer_2", 64, 64, 0, act=1, out_f32=ws["c2f"])]
+        dev = lambda rows: torch.from_numpy(np.array(rows, dtype=TRUNK_LAYER_DTYPE).view(np.uint8).copy()).cuda()
+        units = lambda h_, w_: n * ((h_ + 31) // 32) * ((w_ + 15) // 16)
+        ws.update(tables=[dev(layers), dev(up1), dev(up2)], counts=[len(layers), 1, 1],
+                  flags=[ops.empty(len(layers) * units(H, W), dtype=torch.int32),
+                         ops.empty(units(2 * H, 2 * W), dtype=torch.int32), ops.empty(units(4 * H, 4 * W), dtype=torch.int32)],
+                  version=(self._pack_gen, self.residual_scaling))
+        self._ws[key] = ws
+        return ws
+
+    def _forward_split(self, x, w1, w2, w3):
+        """``precision="bf16x3"``: the reference's fp32 arithmetic (srgan_train.py:525-576) at tensor-core speed for the
+        convolutions that hold 91 % of the FLOPs. Stem (fp32 CUDA cores) -> trunk and both upsample convs in split-bf16
+        (csrc/umma_trunk.cu, dbm_trunk_umma_split: hi + lo bf16 terms of every activation and filter, three MMAs per K
+        chunk, fp32 accumulation and residual stream) -> deformable layers in fp32."""
+        n, _, h, w = x.shape
+        H, W = h - 2, w - 2
+        pk = self._pack(self.PACK_SPLIT)
+        ws = self._split_workspace(n, H, W, pk)
+        st = ops.stream()
+        a0 = ops.empty(n, 128, H, W)
+        self._stem_fp32(x, w1, w2, w3, a0)
+        ops.call("dbm_nchw_to_slab8_split", a0.data_ptr(), 0, ws["s0"].data_ptr(), n, 128, H, W, st)
+        del a0
+        cat = ws["cat"]
+        t, c, f = ws["tables"], ws["counts"], ws["flags"]
+        ops.call("dbm_trunk_umma_split", t[0].data_ptr(), c[0], n, H, W, ws["s0"].data_ptr(), 16, cat[0].data_ptr(),
+                 cat[1].data_ptr(), cat[0].shape[1] // 2, f[0].data_ptr(), st)
+        u1, u2 = ws["u1"], ws["u2"]
+        ops.call("dbm_trunk_umma_split", t[1].data_ptr(), 1, n, 2 * H, 2 * W, u1.data_ptr(), 8, u1.data_ptr(),
+                 u1.data_ptr(), 8, f[1].data_ptr(), st)
+        ops.call("dbm_trunk_umma_split", t[2].data_ptr(), 1, n, 4 * H, 4 * W, u2.data_ptr(), 8, u2.data_ptr(),
+                 u2.data_ptr(), 8, f[2].data_ptr(), st)
+        # deformable layers (srgan_train.py:572-574) in fp32, image by image (the fp32 sampler keeps a 576-row cols buffer)
+        P = self.p
+        y = ops.empty(n, self.out_channels, 4 * H, 4 * W)
+        c2 = ops.empty(1, 64, 4 * H, 4 * W)
+        per = 64 * 16 * H * W   # floats of one image in c2f (slab8f)
+        for i in range(n):
+            ops.call("dbm_slab8f_to_nchw", ws["c2f"].data_ptr() + 4 * per * i, c2.data_ptr(), 0, 1, 64, 4 * H, 4 * W, st)
+            y[i:i + 1].copy_(self._deform_head_fp32(c2))
+        return y
+
+    def _deform_head_fp32(self, c2):
+        """final_conv_layer1 (+ LeakyReLU) and final_conv_layer2 on c2 (n,64,4H,4W), fp32 CUDA cores."""
+        P = self.p
+        n = c2.shape[0]
+
+        def conv(key, x_):
+            wt = P[f"{key}/W"]
+            out = ops.empty(n, wt.shape[0], x_.shape[2], x_.shape[3])
+            ops.conv2d_fwd(x_, 0, 64, wt, P[f"{key}/b"], out, 0, 3, 1, 1, act=False)
+            return out
+
+        off1 = conv("final_conv_layer1/offset_conv", c2)
+        d1, _ = ops.deform_conv_fwd(c2, off1, P["final_conv_layer1/deform_conv/W"], P["final_conv_layer1/deform_conv/b"],
+                                    act=True, tc=False)
+        del _
+        off2 = conv("final_conv_layer2/offset_conv", d1)
+        if self.out_channels == 1:
+            y, _ = ops.deform1_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"], P["final_conv_layer2/deform_conv/b"])
+        else:
+            y, _ = ops.deform_conv_fwd(d1, off2, P["final_conv_layer2/deform_conv/W"], P["final_conv_layer2/deform_conv/b"],
+                                       act=False)
+        return y
 
     def _forward_bf16(self, x, w1, w2, w3):
         from . import flat

@@ -100,6 +100,12 @@ int dbm_nchw_to_slab4(const float* src, long src_batch_stride, float* dst_slab4,
                       cudaStream_t stream);
 int dbm_slab4_to_nchw(const float* src_slab4, float* dst, long dst_batch_stride, int n, int c_slab, int c_keep, int h,
                       int w, cudaStream_t stream);
+/* split-bf16 operand buffers of dbm_trunk_umma_split: v = hi + lo (two bf16 terms), slabs per 16 channels
+ * [hi a | hi b | lo a | lo b] (2 * c / 8 slabs per image); and the trunk kernels' fp32 slab8f [N][C/8][H][W][8] -> NCHW */
+int dbm_nchw_to_slab8_split(const float* src, long src_batch_stride, void* dst_slab8_split, int n, int c, int h, int w,
+                            cudaStream_t stream);
+int dbm_slab8f_to_nchw(const float* src_slab8f, float* dst, long dst_batch_stride, int n, int c, int h, int w,
+                       cudaStream_t stream);
 
 /* ---- tensor-core trunk: 3x3 'same' conv, tcgen05 implicit GEMM ---------------------------------
  * Replaces L.Convolution2D(k3,s1,p1) + F.leaky_relu + F.concat + (x*beta, F.add) +
@@ -134,6 +140,14 @@ int dbm_conv3x3_umma(const void* in_slab8, int in_cs_total, int cin, const void*
 int dbm_trunk_umma(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
                    int stem_cs_total, const void* cat_a_slab8, const void* cat_b_slab8, int cat_cs_total,
                    unsigned int* flags_dev, cudaStream_t stream);
+/* The same pass table in split-bf16 arithmetic (GeneratorModel(precision="bf16x3")): the reference computes these
+ * convolutions in fp32 (srgan_train.py:339-358); here every activation and filter is carried as two bf16 terms and each
+ * 16-channel K chunk is contracted three times (x_hi w_hi + x_lo w_hi + x_hi w_lo, fp32 accumulation): fp32-grade
+ * results on the bf16 tensor pipe at three times the MMA work. Buffers hold 2 x cs_total slabs (layout above), filters
+ * are packed by dbm_pack_conv3x3_table entries with mode bit 16; the cs / channel fields of the table stay logical. */
+int dbm_trunk_umma_split(const void* layers_dev, int num_layers, int n, int h, int w, const void* stem_slab8,
+                         int stem_cs_total, const void* cat_a_slab8, const void* cat_b_slab8, int cat_cs_total,
+                         unsigned int* flags_dev, cudaStream_t stream);
 
 /* ---- tensor-core TRAINING trunk ("flat-padded" layout, csrc/umma_flat.cu) --------------------------
  * Forward, data gradient and weight gradient of the trunk's L.Convolution2D(k3,s1,p1) links

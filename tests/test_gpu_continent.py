@@ -148,3 +148,29 @@ def test_persistent_trunk_more_items_than_ctas_equals_per_layer_launches():
     first = m.forward(*ins).array.clone()
     assert torch.equal(m.forward(*ins).array, first)
     assert rel_l2(first.cpu().numpy(), ref.cpu().numpy()) < 8e-3
+
+
+@pytest.mark.parametrize("case", ["bench_interior", "trainedlike_edge"])
+def test_split_bf16_path_matches_oracle_golden(case, grids, gold):
+    """precision="bf16x3" (split-bf16 trunk + upsample convs on the tensor cores, stem and deformable layers fp32): the
+    full-size tile against the fp64 golden and against the fp32 CUDA path -- fp32-grade: relative L2 <= 1e-4 (stated);
+    a tile in a batch of 2 equals the tile alone bit for bit."""
+    idx, scale, bias_std, physical = CASES[case]
+    plan = O.tile_plan(FINAL)
+    crop = O.continent_tile_inputs(*grids, plan[idx])
+    h, w = crop[0].shape[2:]
+    batch = [np.concatenate([np.roll(a, 5 * (a.shape[2] // h), axis=2), a]) for a in crop]
+    ref_sub = gold[f"{case}/y_sub"]
+    _, std, amax, _ = gold[f"{case}/stats"]
+    m3 = make_model(scale, bias_std, physical, "bf16x3")
+    y3 = m3.forward(*batch).array
+    assert tuple(y3.shape) == (2, 1, 4 * (h - 2), 4 * (w - 2))
+    alone = m3.forward(*crop).array
+    assert torch.equal(alone[0], y3[1])
+    got3 = y3[1, 0].cpu().numpy()
+    e3 = rel_l2(got3[::STRIDE, ::STRIDE], ref_sub)
+    max3 = float(np.abs(got3[::STRIDE, ::STRIDE] - ref_sub).max())
+    to_m = BED_STD_M / std
+    print(f"\n[{case}] bf16x3 path vs fp64 golden: rel_l2 {e3:.3e}  max_abs {max3:.3e} = {max3 * to_m:.4f} m")
+    assert e3 < 1e-4
+    assert max3 * to_m < 1.0   # sub-metre for an output calibrated to BEDMAP2's 800 m spread

@@ -554,6 +554,24 @@ def test_tiled_predictor_matches_oracle_tiler():
     assert rel_l2(got[ok], ref[ok]) < 2e-5
 
 
+@pytest.mark.parametrize("nb,inter,n,h,w", [(2, 32, 2, 20, 27), (1, 64, 1, 35, 18), (1, 32, 3, 11, 11)])
+def test_split_bf16_forward_matches_oracle(nb, inter, n, h, w):
+    """precision="bf16x3": hi + lo bf16 terms of every trunk / upsample-conv activation and filter, three MMAs per K
+    chunk, fp32 accumulation: fp32-grade agreement with the fp64 oracle (stated: relative L2 <= 5e-5; the plain bf16
+    path is at 5e-3 ... 1e-2), for both dense-block widths, ragged tile sizes and the 11 x 11 training tile."""
+    m, params = make_generator(nb, "bf16x3", scale=0.7, inter_channels=inter)
+    ins = O.synthetic_inputs(n, h, w)
+    y = m.forward(*ins).array
+    ref = O.generator_forward_numpy(params, *ins, num_residual_blocks=nb)
+    e = rel_l2(y.cpu().numpy(), ref)
+    m16, _ = make_generator(nb, "bf16", scale=0.7, inter_channels=inter)
+    e16 = rel_l2(m16.forward(*ins).array.cpu().numpy(), ref)
+    print(f"bf16x3 nb={nb} inter={inter} {n}x{h}x{w}: rel_l2 vs fp64 oracle {e:.2e} (bf16 path {e16:.2e})")
+    assert tuple(y.shape) == (n, 1, 4 * (h - 2), 4 * (w - 2))
+    assert e < 5e-5
+    assert torch.equal(m.forward(*ins).array, y)
+
+
 def test_streamed_host_grids_and_host_dem_equal_resident_path():
     """Pinned host grids uploaded in row bands x column blocks on the copy stream (cudaMemcpy2DAsync), finished tile
     rows streamed into a pinned HostDEM: bit-identical to the device-resident grids / device canvas path; so is the
