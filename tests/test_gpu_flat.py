@@ -232,8 +232,8 @@ def test_image_resident_trunk_equals_flat_chain(nb, n, H, W):
     per CTA."""
     from oracle import deepbedmap_oracle as O
     from deepbedmap_b200 import GeneratorModel
-    params = O.init_generator_params(nb, seed=5, bias_std=0.05, scale=0.7, inter_channels=ic)
-    m = GeneratorModel(num_residual_blocks=nb, inter_channels=ic)
+    params = O.init_generator_params(nb, seed=5, bias_std=0.05, scale=0.7)
+    m = GeneratorModel(num_residual_blocks=nb)
     for k, v in params.items():
         m.set_param(k, v)
     a0 = rnd(n, 128, H, W, seed=21)

@@ -532,11 +532,13 @@ def test_npz_roundtrip(tmp_path):
                                                         d2.persistent["batch_norm4/avg_var"])
 
 
-def test_tiled_predictor_matches_oracle_tiler():
-    """Reference tile geometry at reduced size: 3x3 tiles of 40x40 output px, halo 3+1."""
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16x3", 5e-5)])
+def test_tiled_predictor_matches_oracle_tiler(precision, tol):
+    """Reference tile geometry at reduced size: 3x3 tiles of 40x40 output px, halo 3+1; the exact fp32 path and the
+    split-bf16 tensor-core path."""
     from deepbedmap_b200 import predict_continent
     nb = 1
-    m, params = make_generator(nb, "fp32")
+    m, params = make_generator(nb, precision)
     final, ary, pad = (120, 120), (40, 40), (3, 3)
     H = W = 32
     rng = np.random.RandomState(5)
@@ -551,7 +553,7 @@ def test_tiled_predictor_matches_oracle_tiler():
     assert got.shape == ref.shape == (1, 120, 120)
     assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.isnan(ref).any()
     ok = ~np.isnan(ref)
-    assert rel_l2(got[ok], ref[ok]) < 2e-5
+    assert rel_l2(got[ok], ref[ok]) < tol
 
 
 @pytest.mark.parametrize("nb,inter,n,h,w", [(2, 32, 2, 20, 27), (1, 64, 1, 35, 18), (1, 32, 3, 11, 11)])
