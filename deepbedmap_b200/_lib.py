@@ -50,6 +50,7 @@ SIGNATURES = {
     "dbm_trunk_local_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
     "dbm_trunk_local_bwd": [_P, _I, _I, _I, _I, _P, _P, _P],
     "dbm_flat_wgrad": [_P, _I, _I, _I, _I, _P],
+    "dbm_flat_wgrad_ctas": [_P, _I, _I, _I, _I, _I, _P],
     "dbm_flat_wgrad_reduce": [_P, _I, _P],
     "dbm_flat_bias_grad": [_P, _I, _I, _I, _I, _P],
     "dbm_flat_from_nchw": [_P, _I, _P, _P, _F, _I, _I, _I, _P],
@@ -64,6 +65,7 @@ SIGNATURES = {
     "dbm_stem_fwd_flat": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dbm_deform_conv_umma": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P],
     "dbm_deform_conv_umma_nchw": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "dbm_deform_sample_slab8_f32": [_P, _P, _P, _I, _I, _I, _P],
     "dbm_deform_out1_sample": [_P, _P, _I, _P, _P, _I, _I, _I, _P],
     "dbm_deform_conv_out1": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P],
     "dbm_conv3x3_umma": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P, _P],
@@ -73,6 +75,8 @@ SIGNATURES = {
     "dbm_deform1_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "dbm_bn_lrelu_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
     "dbm_bn_lrelu_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dbm_bn_lrelu_fwd_groups_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _P],
+    "dbm_bn_lrelu_bwd_groups_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dbm_ragan_loss_f32": [_P, _P, _I, _F, _F, _F, _P, _P, _P, _P],
     "dbm_gen_image_loss_f32": [_P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P],
     "dbm_adam_step_f32": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],

@@ -27,6 +27,21 @@ __device__ __forceinline__ float block_sum(float s, float* red) {
 constexpr int kBnMaxC = 1024, kBnMaxSplit = 32, kBnSlots = 8;
 __device__ double g_bn_part_all[kBnSlots][kBnMaxC * kBnMaxSplit * 2];
 __device__ unsigned int g_bn_count_all[kBnSlots][kBnMaxC];
+// grouped calls (G independent BatchNormalization passes over one stacked batch in ONE launch): per (group, channel)
+// batch variance and a per-channel counter of finished groups -- the group that finishes last applies the running-
+// statistics updates / gradient accumulations of all groups in group order, exactly as G consecutive calls would
+__device__ float g_bn_var_all[kBnSlots][kBnMaxC];
+__device__ unsigned int g_bn_gcount_all[kBnSlots][kBnMaxC];
+// true in the last group of channel c to get here (everything the other groups wrote before is visible: read with __ldcg)
+__device__ __forceinline__ bool bn_last_group(unsigned int* gcount, int c, int G) {
+  __threadfence();
+  const bool last = atomicAdd(&gcount[c], 1u) == (unsigned)(G - 1);
+  if (last) {
+    gcount[c] = 0;
+    __threadfence();
+  }
+  return last;
+}
 
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -77,17 +92,20 @@ static int bn_split(int n, int c) {
 __global__ void bn_stats_kernel(const float* __restrict__ x, int N, int C, int HW, float eps, float decay, int train,
                                 float* __restrict__ avg_mean, float* __restrict__ avg_var,
                                 float* __restrict__ mean_out, float* __restrict__ invstd_out, int slot) {
+  // N = samples PER GROUP; group g = blockIdx.z owns samples [g N, (g + 1) N) and rows g of mean_out / invstd_out
   __shared__ double red[32];
   double* g_bn_part = g_bn_part_all[slot];
   unsigned int* g_bn_count = g_bn_count_all[slot];
-  const int c = blockIdx.x, split = blockIdx.y, S = gridDim.y;
+  const int c = blockIdx.x, split = blockIdx.y, S = gridDim.y, g = blockIdx.z, G = gridDim.z;
+  const int cg = g * C + c;
   if (!train) {
     if (threadIdx.x == 0 && split == 0) {
-      mean_out[c] = avg_mean[c];
-      invstd_out[c] = rsqrtf(avg_var[c] + eps);
+      mean_out[cg] = avg_mean[c];
+      invstd_out[cg] = rsqrtf(avg_var[c] + eps);
     }
     return;
   }
+  x += (size_t)g * N * C * HW;
   const long n0 = (long)N * split / S, n1 = (long)N * (split + 1) / S;
   const long cnt = (n1 - n0) * HW;
   double s = 0.0, q = 0.0;   // sum and sum of squares in double: var = E[x^2] - mean^2 without cancellation trouble
@@ -99,32 +117,48 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int N, int C, int H
   }
   s = block_sum_d(s, red);
   q = block_sum_d(q, red);
-  if (!bn_publish(g_bn_part, g_bn_count, c, split, S, s, q)) return;
+  if (!bn_publish(g_bn_part, g_bn_count, cg, split, S, s, q)) return;
   if (threadIdx.x == 0) {
     double ts = 0.0, tq = 0.0;
     for (int k = 0; k < S; ++k) {
-      ts += g_bn_part[((size_t)c * kBnMaxSplit + k) * 2];
-      tq += g_bn_part[((size_t)c * kBnMaxSplit + k) * 2 + 1];
+      ts += g_bn_part[((size_t)cg * kBnMaxSplit + k) * 2];
+      tq += g_bn_part[((size_t)cg * kBnMaxSplit + k) * 2 + 1];
     }
     const double m = (double)N * HW;
     const double mean = ts / m;
     double var = tq / m - mean * mean;
     if (var < 0.0) var = 0.0;
-    mean_out[c] = (float)mean;
-    invstd_out[c] = (float)(1.0 / sqrt(var + (double)eps));
+    mean_out[cg] = (float)mean;
+    invstd_out[cg] = (float)(1.0 / sqrt(var + (double)eps));
     const float adjust = (float)(m / fmax(m - 1.0, 1.0));
-    avg_mean[c] = decay * avg_mean[c] + (1.f - decay) * (float)mean;
-    avg_var[c] = decay * avg_var[c] + (1.f - decay) * (float)var * adjust;
+    // explicit roundings: the single-group and the grouped path must produce the same bits (no compiler-chosen fma)
+    auto running = [decay](float avg, float v) { return __fmaf_rn(decay, avg, __fmul_rn(1.f - decay, v)); };
+    if (G == 1) {
+      avg_mean[c] = running(avg_mean[c], (float)mean);
+      avg_var[c] = running(avg_var[c], __fmul_rn((float)var, adjust));
+    } else {
+      g_bn_var_all[slot][cg] = (float)var;
+      if (bn_last_group(g_bn_gcount_all[slot], c, G)) {
+        float am = avg_mean[c], av = avg_var[c];
+        for (int gg = 0; gg < G; ++gg) {   // group order = the order of G consecutive calls
+          am = running(am, __ldcg(mean_out + gg * C + c));
+          av = running(av, __fmul_rn(__ldcg(&g_bn_var_all[slot][gg * C + c]), adjust));
+        }
+        avg_mean[c] = am;
+        avg_var[c] = av;
+      }
+    }
   }
 }
 // y = lrelu(gamma * (x - mean) * invstd + beta)
 __global__ void bn_apply_lrelu_kernel(const float* __restrict__ x, float* __restrict__ y,
                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ mean, const float* __restrict__ invstd, int C, int HW,
-                                      long total) {
+                                      long total, long group_elems) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (i / HW) % C;
-    y[i] = lrelu(gamma[c] * (x[i] - mean[c]) * invstd[c] + beta[c]);
+    const int cg = (int)(i / group_elems) * C + c;
+    y[i] = lrelu(gamma[c] * (x[i] - mean[cg]) * invstd[cg] + beta[c]);
   }
 }
 // Backward of y = lrelu(BN_train(x)): per-channel reductions (dgamma += , dbeta +=) ...
@@ -132,14 +166,18 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
                                      const float* __restrict__ dy, int N, int C, int HW,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat, int slot) {
+                                     float* __restrict__ scratch, int slot) {
+  // N = samples PER GROUP (group = blockIdx.z); scratch [G][2 C]: sum_dz | sum_dz_xhat of every group
   __shared__ double red[32];
   double* g_bn_part = g_bn_part_all[slot];
   unsigned int* g_bn_count = g_bn_count_all[slot];
-  const int c = blockIdx.x, split = blockIdx.y, S = gridDim.y;
+  const int c = blockIdx.x, split = blockIdx.y, S = gridDim.y, g = blockIdx.z, G = gridDim.z;
+  const int cg = g * C + c;
+  const size_t goff = (size_t)g * N * C * HW;
+  x += goff; y += goff; dy += goff;
   const long n0 = (long)N * split / S, n1 = (long)N * (split + 1) / S;
   const long cnt = (n1 - n0) * HW;
-  const float mu = mean[c], is = invstd[c];
+  const float mu = mean[cg], is = invstd[cg];
   double s1 = 0.0, s2 = 0.0;
   for (int i = threadIdx.x; i < (int)cnt; i += blockDim.x) {
     const int n = i / HW, r = i - n * HW;
@@ -151,31 +189,45 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
   }
   s1 = block_sum_d(s1, red);
   s2 = block_sum_d(s2, red);
-  if (!bn_publish(g_bn_part, g_bn_count, c, split, S, s1, s2)) return;
+  if (!bn_publish(g_bn_part, g_bn_count, cg, split, S, s1, s2)) return;
   if (threadIdx.x == 0) {
     double t1 = 0.0, t2 = 0.0;
     for (int k = 0; k < S; ++k) {
-      t1 += g_bn_part[((size_t)c * kBnMaxSplit + k) * 2];
-      t2 += g_bn_part[((size_t)c * kBnMaxSplit + k) * 2 + 1];
+      t1 += g_bn_part[((size_t)cg * kBnMaxSplit + k) * 2];
+      t2 += g_bn_part[((size_t)cg * kBnMaxSplit + k) * 2 + 1];
     }
+    float* sum_dz = scratch + (size_t)g * 2 * C;
     sum_dz[c] = (float)t1;
-    sum_dz_xhat[c] = (float)t2;
-    dbeta[c] += (float)t1;
-    dgamma[c] += (float)t2;
+    sum_dz[C + c] = (float)t2;
+    if (G == 1) {
+      dbeta[c] += (float)t1;
+      dgamma[c] += (float)t2;
+    } else if (bn_last_group(g_bn_gcount_all[slot], c, G)) {
+      float db = dbeta[c], dg = dgamma[c];
+      for (int gg = 0; gg < G; ++gg) {   // group order = the order of G consecutive calls
+        db = __fadd_rn(db, __ldcg(scratch + (size_t)gg * 2 * C + c));
+        dg = __fadd_rn(dg, __ldcg(scratch + (size_t)gg * 2 * C + C + c));
+      }
+      dbeta[c] = db;
+      dgamma[c] = dg;
+    }
   }
 }
 // ... then dx = gamma * invstd * (dz - sum_dz/m - xhat * sum_dz_xhat/m)
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                     const float* __restrict__ dy, float* __restrict__ dx,
                                     const float* __restrict__ gamma, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ sum_dz,
-                                    const float* __restrict__ sum_dz_xhat, int C, int HW, long total, float inv_m) {
+                                    const float* __restrict__ invstd, const float* __restrict__ scratch, int C, int HW,
+                                    long total, long group_elems, float inv_m) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (i / HW) % C;
+    const int g = (int)(i / group_elems);
+    const int cg = g * C + c;
+    const float* sum_dz = scratch + (size_t)g * 2 * C;
     float dz = dy[i];
     if (y[i] < 0.f) dz *= kLreluSlope;
-    const float xhat = (x[i] - mean[c]) * invstd[c];
-    dx[i] = gamma[c] * invstd[c] * (dz - sum_dz[c] * inv_m - xhat * sum_dz_xhat[c] * inv_m);
+    const float xhat = (x[i] - mean[cg]) * invstd[cg];
+    dx[i] = gamma[c] * invstd[cg] * (dz - sum_dz[c] * inv_m - xhat * sum_dz[C + c] * inv_m);
   }
 }
 
@@ -394,36 +446,60 @@ static inline int grid_for(long total) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+// `groups` independent BatchNormalization passes over a batch stacked along N (group g = samples [g n, (g + 1) n)) in
+// ONE pair of launches: batch statistics per group (save_mean / save_invstd: [groups][c]), running statistics updated
+// group after group -- the values of `groups` consecutive single-group calls, bit for bit.
+extern "C" int dbm_bn_lrelu_fwd_groups_f32(const float* x, float* y, const float* gamma, const float* beta,
+                                           float* avg_mean, float* avg_var, float* save_mean, float* save_invstd,
+                                           int groups, int n, int c, int hw, float eps, float decay, int train,
+                                           cudaStream_t st) {
+  DBM_REQUIRE(groups > 0 && n > 0 && c > 0 && hw > 0, "bn: empty input");
+  DBM_REQUIRE(groups * c <= kBnMaxC && (long)n * hw < (1L << 31),
+              "bn: %d x %d channels / %d x %d elements exceed the reduction scratch", groups, c, n, hw);
+  const int slot = bn_slot(st);
+  DBM_REQUIRE(slot >= 0, "bn: more than %d streams issue BatchNormalization calls", kBnSlots);
+  bn_stats_kernel<<<dim3(c, train ? bn_split(n, c) : 1, groups), 256, 0, st>>>(
+      x, n, c, hw, eps, decay, train, avg_mean, avg_var, save_mean, save_invstd, slot);
+  int rc = check_launch("bn_stats");
+  if (rc) return rc;
+  const long group_elems = (long)n * c * hw, total = group_elems * groups;
+  bn_apply_lrelu_kernel<<<grid_for(total), 256, 0, st>>>(x, y, gamma, beta, save_mean, save_invstd, c, hw, total,
+                                                         group_elems);
+  return check_launch("bn_apply_lrelu");
+}
+
 extern "C" int dbm_bn_lrelu_fwd_f32(const float* x, float* y, const float* gamma, const float* beta, float* avg_mean,
                                     float* avg_var, float* save_mean, float* save_invstd, int n, int c, int hw,
                                     float eps, float decay, int train, cudaStream_t st) {
-  DBM_REQUIRE(n > 0 && c > 0 && hw > 0, "bn: empty input");
-  DBM_REQUIRE(c <= kBnMaxC && (long)n * hw < (1L << 31), "bn: %d channels / %d x %d elements exceed the reduction scratch", c, n, hw);
+  return dbm_bn_lrelu_fwd_groups_f32(x, y, gamma, beta, avg_mean, avg_var, save_mean, save_invstd, 1, n, c, hw, eps,
+                                     decay, train, st);
+}
+
+// backward of the grouped call: scratch [groups][2 c]; dgamma / dbeta accumulate the groups' sums in group order
+extern "C" int dbm_bn_lrelu_bwd_groups_f32(const float* x, const float* y, const float* dy, float* dx,
+                                           const float* gamma, const float* save_mean, const float* save_invstd,
+                                           float* dgamma, float* dbeta, float* scratch, int groups, int n, int c,
+                                           int hw, cudaStream_t st) {
+  DBM_REQUIRE(groups > 0 && n > 0 && c > 0 && hw > 0, "bn_bwd: empty input");
+  DBM_REQUIRE(groups * c <= kBnMaxC && (long)n * hw < (1L << 31),
+              "bn_bwd: %d x %d channels / %d x %d elements exceed the reduction scratch", groups, c, n, hw);
   const int slot = bn_slot(st);
-  DBM_REQUIRE(slot >= 0, "bn: more than %d streams issue BatchNormalization calls", kBnSlots);
-  bn_stats_kernel<<<dim3(c, train ? bn_split(n, c) : 1), 256, 0, st>>>(x, n, c, hw, eps, decay, train, avg_mean, avg_var, save_mean, save_invstd, slot);
-  int rc = check_launch("bn_stats");
+  DBM_REQUIRE(slot >= 0, "bn_bwd: more than %d streams issue BatchNormalization calls", kBnSlots);
+  bn_bwd_reduce_kernel<<<dim3(c, bn_split(n, c), groups), 256, 0, st>>>(x, y, dy, n, c, hw, save_mean,
+                                                                                 save_invstd, dgamma, dbeta, scratch, slot);
+  int rc = check_launch("bn_bwd_reduce");
   if (rc) return rc;
-  const long total = (long)n * c * hw;
-  bn_apply_lrelu_kernel<<<grid_for(total), 256, 0, st>>>(x, y, gamma, beta, save_mean, save_invstd, c, hw, total);
-  return check_launch("bn_apply_lrelu");
+  const long group_elems = (long)n * c * hw, total = group_elems * groups;
+  bn_bwd_apply_kernel<<<grid_for(total), 256, 0, st>>>(x, y, dy, dx, gamma, save_mean, save_invstd, scratch, c, hw,
+                                                       total, group_elems, 1.f / ((float)n * hw));
+  return check_launch("bn_bwd_apply");
 }
 
 extern "C" int dbm_bn_lrelu_bwd_f32(const float* x, const float* y, const float* dy, float* dx, const float* gamma,
                                     const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
                                     float* scratch2c, int n, int c, int hw, cudaStream_t st) {
-  DBM_REQUIRE(n > 0 && c > 0 && hw > 0, "bn_bwd: empty input");
-  DBM_REQUIRE(c <= kBnMaxC && (long)n * hw < (1L << 31), "bn_bwd: %d channels / %d x %d elements exceed the reduction scratch", c, n, hw);
-  const int slot = bn_slot(st);
-  DBM_REQUIRE(slot >= 0, "bn_bwd: more than %d streams issue BatchNormalization calls", kBnSlots);
-  bn_bwd_reduce_kernel<<<dim3(c, bn_split(n, c)), 256, 0, st>>>(x, y, dy, n, c, hw, save_mean, save_invstd, dgamma, dbeta, scratch2c,
-                                          scratch2c + c, slot);
-  int rc = check_launch("bn_bwd_reduce");
-  if (rc) return rc;
-  const long total = (long)n * c * hw;
-  bn_bwd_apply_kernel<<<grid_for(total), 256, 0, st>>>(x, y, dy, dx, gamma, save_mean, save_invstd, scratch2c,
-                                                       scratch2c + c, c, hw, total, 1.f / ((float)n * hw));
-  return check_launch("bn_bwd_apply");
+  return dbm_bn_lrelu_bwd_groups_f32(x, y, dy, dx, gamma, save_mean, save_invstd, dgamma, dbeta, scratch2c, 1, n, c, hw,
+                                     st);
 }
 
 extern "C" int dbm_ragan_loss_f32(const float* real_pred, const float* fake_pred, int n, float t_real_minus_fake,

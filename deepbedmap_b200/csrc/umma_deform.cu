@@ -472,6 +472,54 @@ extern "C" int dbm_deform_conv_umma_nchw(const void* x_slab8, const float* offse
   return check_launch("deform_umma_kernel");
 }
 
+// Re-sampling for the backward of the fused forward above: cols[n][c * 9 + tap][p] (fp32, the operand of the weight
+// gradient GEMM) from the SAME bf16 slab8 copy of the input the forward gathered from, with the same 16-byte corner
+// loads (one per 8 channels instead of one 4-byte load per channel from the fp32 NCHW tensor: dbm_deform_sample_f32
+// took 0.60 ms at batch 128 on the generator's critical path). The values are the forward's samples before their bf16
+// rounding, which the GEMM applies.
+__global__ void __launch_bounds__(256) deform_sample_slab8_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                  const float* __restrict__ off_nchw,
+                                                                  float* __restrict__ cols, int N, int H, int W) {
+  const long hw = (long)H * W;
+  const long total = (long)N * 9 * hw;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pp = i % hw;
+    const int tap = (int)((i / hw) % 9);
+    const long n = i / (9 * hw);
+    const int y = (int)(pp / W), xx = (int)(pp - (long)y * W);
+    const float dx = __ldg(off_nchw + (n * 18 + tap) * hw + pp);
+    const float dy = __ldg(off_nchw + (n * 18 + 9 + tap) * hw + pp);
+    const TapPos tp = tap_pos(dx, dy, xx, y, tap, H, W);
+    const __nv_bfloat16* xin = x + (size_t)n * 8 * hw * 8;
+    float* out = cols + ((size_t)n * 576 + tap) * hw + pp;
+#pragma unroll
+    for (int s0 = 0; s0 < 8; s0 += 2) {
+      Corners cr[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) cr[q] = load_corners(xin + (size_t)(s0 + q) * hw * 8, tp);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float v[8];
+        blend8(cr[q], tp, v);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) out[(size_t)((s0 + q) * 8 + c8) * 9 * hw] = v[c8];
+      }
+    }
+  }
+}
+
+extern "C" int dbm_deform_sample_slab8_f32(const void* x_slab8, const float* offset_nchw18, float* cols, int n, int h,
+                                           int w, cudaStream_t stream) {
+  DBM_REQUIRE(n > 0 && h > 0 && w > 0 && x_slab8 && offset_nchw18 && cols, "deform_sample_slab8: bad arguments");
+  DBM_REQUIRE(((uintptr_t)x_slab8 & 15) == 0, "deform_sample_slab8: unaligned input");
+  const long total = (long)n * 9 * h * w;
+  long blocks = (total + 255) / 256;
+  const long cap = (long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  deform_sample_slab8_kernel<<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)x_slab8, offset_nchw18, cols, n, h, w);
+  return check_launch("deform_sample_slab8_kernel");
+}
+
 // The sampling half of dbm_deform_conv_out1 alone: the nine projected planes were already produced by the preceding
 // layer's fused epilogue (dbm_deform_conv_umma with next_out1_filter).
 extern "C" int dbm_deform_out1_sample(const float* proj, const float* offset_slab4, int offset_cs_total,

@@ -881,7 +881,16 @@ extern "C" int dbm_flat_conv3x3_chain(const void* launches_host, const void* lau
   return check_launch("flat_chain_kernel");
 }
 
+extern "C" int dbm_flat_wgrad_ctas(const void* units_dev, int num_units, int n, int h, int w, int max_ctas,
+                                   cudaStream_t stream);
 extern "C" int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h, int w, cudaStream_t stream) {
+  return dbm_flat_wgrad_ctas(units_dev, num_units, n, h, w, 0, stream);
+}
+
+// max_ctas > 0: upper bound of the persistent grid for THIS launch (two weight-gradient kernels of different models
+// running side by side each get a share of the SMs instead of the second one squeezing into what the first left free)
+extern "C" int dbm_flat_wgrad_ctas(const void* units_dev, int num_units, int n, int h, int w, int max_ctas,
+                                   cudaStream_t stream) {
   const FlatGeom g = flat_geom(n, h, w);
   int rc = check_flat_shape(g, "flat_wgrad");
   if (rc) return rc;
@@ -892,6 +901,7 @@ extern "C" int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h
   // kernel; a persistent grid on every SM would stall that chain for the whole launch, so a few SMs can be left free
   // (dbm_set_sm_reserve(n): the units are dealt round-robin, results do not depend on the grid size)
   int cap = num_sms() - g_flat_sm_reserve;
+  if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;
   if (cap < 1) cap = 1;
   const int grid = num_units < cap ? num_units : cap;
   flat_wgrad_kernel<<<grid, kFlatThreads, kFlatSmem, stream>>>((const WgradUnit*)units_dev, num_units, g,

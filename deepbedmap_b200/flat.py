@@ -415,7 +415,8 @@ class FlatTrunk:
             wgrad_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(wgrad_stream if wgrad_stream is not None else torch.cuda.current_stream()):
             ws = ops.stream()
-            ops.call("dbm_flat_wgrad", self.units_dev.data_ptr(), self.n_units, n, H, W, ws)
+            ops.call("dbm_flat_wgrad_ctas", self.units_dev.data_ptr(), self.n_units, n, H, W,
+                     int(getattr(self.model, "trunk_wgrad_ctas", 0)), ws)
             ops.call("dbm_flat_wgrad_reduce", self.reduce_dev.data_ptr(), self.n_reduce, ws)
             ops.call("dbm_flat_bias_grad", self.bias_dev.data_ptr(), self.n_bias, n, H, W, ws)
         da0 = ops.empty(n, 128, H, W)

@@ -192,6 +192,12 @@ class GeneratorModel(_Link):
         self._cgen, self._cgen_version, self._cgen_ws = None, -1, {}
         # training forward of the first deformable layer as one fused tcgen05 kernel (False: sampler + bf16 GEMM, cols kept)
         self.fused_deform_forward = True
+        # its backward re-samples the weight-gradient operand from the forward's bf16 slab8 input with 16-byte gathers
+        # (False: from the fp32 NCHW tensor, one 4-byte gather per channel and corner)
+        self.resample_from_slab8 = True
+        # upper bound of the persistent grid of the trunk's batched weight-gradient launch (0 = every SM but the
+        # reserve): in the training step the discriminator's weight gradients run beside it and end the step
+        self.trunk_wgrad_ctas = 0
         self._ctx = None
 
     # ---- serialisation (chainer.serializers.load_npz / save_npz, App. C layout) ----
@@ -347,8 +353,11 @@ class GeneratorModel(_Link):
             # gather + tcgen05 contraction + bias + LeakyReLU in one kernel; backward re-samples (no 382 MB cols buffer
             # on the forward's critical path)
             wq, _ = self._packed["final_conv_layer1/deform_conv"]
-            d1 = ops.deform_conv_fwd_fused(c2, off1, wq, P["final_conv_layer1/deform_conv/b"], act=True)
+            d1, c2_slab8 = ops.deform_conv_fwd_fused(c2, off1, wq, P["final_conv_layer1/deform_conv/b"], act=True,
+                                                     keep_slab8=True)
             cols1 = None
+            if save:
+                ctx["c2_slab8"] = c2_slab8   # backward re-samples from the very operand the forward gathered from
         else:
             d1, cols1 = ops.deform_conv_fwd(c2, off1, P["final_conv_layer1/deform_conv/W"],
                                             P["final_conv_layer1/deform_conv/b"], act=True, tc=tc is not None)
@@ -439,7 +448,12 @@ class GeneratorModel(_Link):
         ops.lrelu_bwd(dd1, 0, c["d1"], 0, dd1, 0, 64)
         # ---- final_conv_layer1 ----
         dc2 = ops.zeros(n, 64, 4 * H, 4 * W)
-        cols1 = c["cols1"] if c["cols1"] is not None else ops.deform_sample(c["c2"], c["off1"])
+        if c["cols1"] is not None:
+            cols1 = c["cols1"]
+        elif c.get("c2_slab8") is not None and self.resample_from_slab8:
+            cols1 = ops.deform_sample_slab8(c["c2_slab8"], c["off1"])
+        else:
+            cols1 = ops.deform_sample(c["c2"], c["off1"])
         doff1 = ops.deform_conv_bwd(c["c2"], c["off1"], P["final_conv_layer1/deform_conv/W"], cols1, dd1,
                                     G["final_conv_layer1/deform_conv/W"], G["final_conv_layer1/deform_conv/b"], dc2,
                                     tc=c.get("head_tc") is not None)
@@ -1158,12 +1172,11 @@ class DiscriminatorModel(_Link):
                 ops.conv2d_fwd(acts[-1], 0, cin, P[f"conv_layer{i}/W"], None, z, 0, k, s, 1)
             y = ops.empty(n, cout, ho, ho)
             mean, invstd = ops.empty(groups, cout), ops.empty(groups, cout)
-            for gi in range(groups):
-                o = 4 * gi * ng * cout * ho * ho
-                ops.call("dbm_bn_lrelu_fwd_f32", z.data_ptr() + o, y.data_ptr() + o, P[f"batch_norm{i}/gamma"].data_ptr(),
-                         P[f"batch_norm{i}/beta"].data_ptr(), self.persistent[f"batch_norm{i}/avg_mean"].data_ptr(),
-                         self.persistent[f"batch_norm{i}/avg_var"].data_ptr(), mean[gi].data_ptr(),
-                         invstd[gi].data_ptr(), ng, cout, ho * ho, self.BN_EPS, self.BN_DECAY, int(train), ops.stream())
+            # all groups in one pair of launches (statistics per group, running statistics updated in group order)
+            ops.call("dbm_bn_lrelu_fwd_groups_f32", z.data_ptr(), y.data_ptr(), P[f"batch_norm{i}/gamma"].data_ptr(),
+                     P[f"batch_norm{i}/beta"].data_ptr(), self.persistent[f"batch_norm{i}/avg_mean"].data_ptr(),
+                     self.persistent[f"batch_norm{i}/avg_var"].data_ptr(), mean.data_ptr(), invstd.data_ptr(), groups, ng,
+                     cout, ho * ho, self.BN_EPS, self.BN_DECAY, int(train), ops.stream())
             # batch_norm{i}/N: Chainer increments it in finetune mode only, which the reference never enters
             # (srgan_train.py:1125, 1228 toggle `train` alone) -> the loaded value (0 by default) is kept as is
             pres.append(z)
@@ -1238,12 +1251,10 @@ class DiscriminatorModel(_Link):
             groups = c.get("groups", 1)
             ng = n // groups
             scratch = ops.empty(groups, 2 * cout)
-            for gi in range(groups):
-                o = 4 * gi * ng * cout * hw
-                ops.call("dbm_bn_lrelu_bwd_f32", z.data_ptr() + o, y.data_ptr() + o, dy.data_ptr() + o, dz.data_ptr() + o,
-                         P[f"batch_norm{i}/gamma"].data_ptr(), mean[gi].data_ptr(), invstd[gi].data_ptr(),
-                         G[f"batch_norm{i}/gamma"].data_ptr(), G[f"batch_norm{i}/beta"].data_ptr(),
-                         scratch[gi].data_ptr(), ng, cout, hw, ops.stream())
+            ops.call("dbm_bn_lrelu_bwd_groups_f32", z.data_ptr(), y.data_ptr(), dy.data_ptr(), dz.data_ptr(),
+                     P[f"batch_norm{i}/gamma"].data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                     G[f"batch_norm{i}/gamma"].data_ptr(), G[f"batch_norm{i}/beta"].data_ptr(), scratch.data_ptr(),
+                     groups, ng, cout, hw, ops.stream())
             xin = acts[i]
             cin = xin.shape[1]
             if c.get("tc") is not None:
@@ -1253,13 +1264,19 @@ class DiscriminatorModel(_Link):
                 dx = ops.empty(*xin.shape)
                 ops.conv2d_bwd_data(dz, 0, P[f"conv_layer{i}/W"], dx, 0, cin, k, s, 1)
             dy = dx
-            if i in (9, 5) and wg is not None:
-                cur.wait_stream(wg)
-            if i == 9:
-                ready("linear_", "conv_layer9/", "batch_norm9/")
-            elif i == 5:
-                ready("conv_layer5/", "batch_norm5/", "conv_layer6/", "batch_norm6/", "conv_layer7/", "batch_norm7/",
-                      "conv_layer8/", "batch_norm8/")
+            if i in (9, 5) and on_ready is not None:
+                # Hand the finished buckets over ON the weight-gradient stream (after it has caught up with the
+                # BatchNorm / linear gradients produced on this one): the data-gradient chain -- the critical path of
+                # the whole training step -- never waits for a weight gradient. (Round 2: joining the streams here
+                # stalled the chain for 0.7 ms behind the 512-channel layers' weight gradients.)
+                with torch.cuda.stream(wg if wg is not None else cur):
+                    if wg is not None:
+                        wg.wait_stream(cur)
+                    if i == 9:
+                        ready("linear_", "conv_layer9/", "batch_norm9/")
+                    else:
+                        ready("conv_layer5/", "batch_norm5/", "conv_layer6/", "batch_norm6/", "conv_layer7/",
+                              "batch_norm7/", "conv_layer8/", "batch_norm8/")
         # conv_layer0 + LeakyReLU
         ops.lrelu_bwd(dy, 0, acts[1], 0, dy, 0, 64)
         ops.conv2d_bwd_weight(acts[0], 0, 1, dy, 0, G["conv_layer0/W"], 3, 1, 1, db=G["conv_layer0/b"])

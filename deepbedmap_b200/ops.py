@@ -225,7 +225,15 @@ def deform_sample(x, offset):
     return cols
 
 
-def deform_conv_fwd_fused(x, offset, wpacked_ck64, b, act=False):
+def deform_sample_slab8(x8, offset):
+    """The same cols from the bf16 slab8 copy of the input the fused forward gathered from (16-byte corner loads)."""
+    n, _, h, wd, _ = x8.shape
+    cols = empty(n, 576, h * wd)
+    call("dbm_deform_sample_slab8_f32", x8.data_ptr(), offset.data_ptr(), cols.data_ptr(), n, h, wd, stream())
+    return cols
+
+
+def deform_conv_fwd_fused(x, offset, wpacked_ck64, b, act=False, keep_slab8=False):
     """Forward of a 64 -> 64 deformable conv in one tcgen05 kernel (gather -> UMMA -> bias / LeakyReLU): x (N,64,H,W)
     fp32, offset (N,18,H,W) fp32 -> y (N,64,H,W) fp32. Bilinear samples and filter are rounded to bf16 exactly as
     deform_conv_fwd(tc=True) does; no cols buffer is produced (backward re-samples, deform_sample)."""
@@ -236,7 +244,7 @@ def deform_conv_fwd_fused(x, offset, wpacked_ck64, b, act=False):
     y = empty(n, 64, h, wd)
     call("dbm_deform_conv_umma_nchw", x8.data_ptr(), offset.data_ptr(), wpacked_ck64.data_ptr(), b.data_ptr(), n, h, wd,
          int(act), y.data_ptr(), stream())
-    return y
+    return (y, x8) if keep_slab8 else y
 
 
 def deform_conv_fwd(x, offset, w, b, act=False, tc=False):

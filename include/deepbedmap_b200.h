@@ -194,6 +194,9 @@ int dbm_trunk_local_fwd(const void* passes_dev, int count, int n, int h, int w, 
 int dbm_trunk_local_bwd(const void* passes_dev, int count, int n, int h, int w, const void* gpost_flat,
                         float* dxrr_scratch, cudaStream_t stream);
 int dbm_flat_wgrad(const void* units_dev, int num_units, int n, int h, int w, cudaStream_t stream);
+/* the same with an upper bound on the persistent grid of this launch (0 = none): lets two models' weight-gradient
+ * kernels share the SMs side by side */
+int dbm_flat_wgrad_ctas(const void* units_dev, int num_units, int n, int h, int w, int max_ctas, cudaStream_t stream);
 int dbm_flat_wgrad_reduce(const void* entries_dev, int count, cudaStream_t stream);
 int dbm_flat_bias_grad(const void* entries_dev, int count, int n, int h, int w, cudaStream_t stream);
 /* NCHW fp32 (n, c, h, w) -> scale * x into a flat slab8 and/or slab4 (either may be NULL), and back.
@@ -254,6 +257,10 @@ int dbm_deform_conv_umma_nchw(const void* x_slab8, const float* offset_nchw18, c
 /* next_out1_filter / next_out1_proj (both or neither): the (1, 64, 3, 3) filter of a FOLLOWING single-output
  * deformable layer and a [n][9][h*w] buffer -- the layer's "tap projection" (see dbm_deform_conv_out1) is then
  * computed in this kernel's epilogue from the outputs in registers; finish that layer with dbm_deform_out1_sample. */
+/* cols (n, 64*9, h*w) fp32 for the backward of dbm_deform_conv_umma_nchw: the same bilinear samples, gathered from
+ * the same bf16 slab8 input (L.DeformableConvolution2D's weight gradient operand, srgan_train.py:506-523). */
+int dbm_deform_sample_slab8_f32(const void* x_slab8, const float* offset_nchw18, float* cols, int n, int h, int w,
+                                cudaStream_t stream);
 int dbm_deform_out1_sample(const float* proj, const float* offset_slab4, int offset_cs_total, const float* bias,
                            float* y, int n, int h, int w, cudaStream_t stream);
 /* proj_scratch: n*9*h*w floats (the 64 channels projected onto the 9 taps before sampling) */
@@ -286,6 +293,16 @@ int dbm_bn_lrelu_fwd_f32(const float* x, float* y, const float* gamma, const flo
 int dbm_bn_lrelu_bwd_f32(const float* x, const float* y, const float* dy, float* dx, const float* gamma,
                          const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
                          float* scratch2c, int n, int c, int hw, cudaStream_t stream);
+/* `groups` independent BatchNormalization (+ LeakyReLU) passes over a batch stacked along N in one pair of launches
+ * (the discriminator step's D(real) | D(fake), srgan_train.py:1145-1146): x, y (groups * n, c, hw); save_mean /
+ * save_invstd [groups][c]; running statistics updated group after group; backward scratch [groups][2 c]. Values equal
+ * `groups` consecutive single-group calls bit for bit. */
+int dbm_bn_lrelu_fwd_groups_f32(const float* x, float* y, const float* gamma, const float* beta, float* avg_mean,
+                                float* avg_var, float* save_mean, float* save_invstd, int groups, int n, int c, int hw,
+                                float eps, float decay, int train, cudaStream_t stream);
+int dbm_bn_lrelu_bwd_groups_f32(const float* x, const float* y, const float* dy, float* dx, const float* gamma,
+                                const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
+                                float* scratch, int groups, int n, int c, int hw, cudaStream_t stream);
 
 /* ---- losses (srgan_train.py:841-1009) -------------------------------------------------------- */
 /* out2[0] = RaGAN loss (calculate_discriminator_loss), out2[1] = F.binary_accuracy of

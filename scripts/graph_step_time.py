@@ -6,6 +6,15 @@ from deepbedmap_b200 import train as T
 
 batch = 128
 g, g_opt, d, d_opt = T.compile_srgan_model()
+for kv in sys.argv[1:]:          # A/B switches of the generator, e.g. resample_from_slab8=0; sm_reserve=N
+    k, v = kv.split("=")
+    if k == "graph_wgrad_ctas":
+        T.GraphedTrainStep.TRUNK_WGRAD_CTAS = int(v)
+    elif k == "sm_reserve":
+        from deepbedmap_b200 import ops
+        ops.call("dbm_set_sm_reserve", int(v))
+    else:
+        setattr(g, k, type(getattr(g, k))(int(v)))
 gen = torch.Generator(device="cuda").manual_seed(42)
 r = lambda *s: torch.rand(*s, generator=gen, device="cuda")
 arrays = {"X": r(batch, 1, 11, 11), "W1": r(batch, 1, 110, 110), "W2": r(batch, 2, 22, 22), "W3": r(batch, 1, 11, 11),

@@ -63,3 +63,8 @@ for e in one:
         print(f"   {e.time_range.start - t0:8.1f} {dur:7.1f}  s{getattr(e, 'device_resource_id', 0)}  "
               f"{e.name.replace('void ', '').replace('dbm::', '')[:60]}")
 print(f"   step ends at {one[-1].time_range.end - t0:.1f} us")
+if len(sys.argv) > 3:   # full kernel list of the last step (every launch): offset, duration, stream, name
+    with open(sys.argv[3], "w") as fh:
+        for e in one:
+            fh.write(f"{e.time_range.start - t0:9.1f} {e.time_range.end - e.time_range.start:8.1f} "
+                     f"s{getattr(e, 'device_resource_id', 0)} {e.name.replace('void ', '').replace('dbm::', '')[:70]}\n")

@@ -258,6 +258,23 @@ def test_deform_conv_tensor_core_path(ops, n, h, w):
     assert rel_l2(y, ref1) < 1e-5
 
 
+@pytest.mark.parametrize("n,h,w", [(1, 8, 16), (2, 37, 45), (3, 36, 36)])
+def test_deform_sample_from_slab8_equals_fp32_sampler(ops, n, h, w):
+    """dbm_deform_sample_slab8_f32 (16-byte corner gathers from the bf16 slab8 input of the fused forward) against
+    dbm_deform_sample_f32 on the same bf16-representable values: the same bilinear samples, incl. out-of-image corners
+    (large offsets) -- up to fp32 association."""
+    x = rnd(n, 64, h, w, seed=1).bfloat16().float()
+    off = rnd(n, 18, h, w, seed=2, scale=1.5)
+    off[0, :, 0, 0] = 50.0
+    off[0, :9, 1, 1] = -30.0
+    x8 = ops.empty(n, 8, h, w, 8, dtype=torch.bfloat16)
+    ops.nchw_to_slab8(x, x8)
+    got = ops.deform_sample_slab8(x8, off)
+    want = ops.deform_sample(x, off)
+    assert tuple(got.shape) == tuple(want.shape) == (n, 576, h * w)
+    assert rel_l2(got, want) < 1e-6 and float((got - want).abs().max()) < 1e-5
+
+
 def test_deform_conv_fwd_bwd(ops):
     from oracle import deepbedmap_oracle as O
     n, c, h, w, o = 2, 6, 9, 11, 5
