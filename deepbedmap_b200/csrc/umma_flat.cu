@@ -437,8 +437,9 @@ struct WgradUnit {  // 48 bytes; mirrored by flat.py (WGRAD_UNIT_DTYPE)
   float* partial;             // [9][32][128] fp32: partial[tap][o][c]
   int blk0, nblk;             // range of 128-position blocks
   int nslab;                  // input slabs in this chunk (<= 16)
-  int pad[3];
-};
+  int tapmask;                // bit t set: tap t is computed (0 = all nine). A 4x4 stride-2 filter embedded as a 3x3
+  int pad[2];                 // filter over the four space-to-depth phases has 4 non-zero taps per phase: the other
+};                            // five accumulators are neither computed nor written (the reduction skips them too)
 static_assert(sizeof(WgradUnit) == 48, "WgradUnit layout is part of the C ABI");
 
 constexpr int kWgradMaxStages = 6;
@@ -501,6 +502,7 @@ flat_wgrad_kernel(const WgradUnit* __restrict__ units, int num_units, const Flat
     int s = 0, it = 0; uint32_t ph = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
       const int nblk = units[u].nblk;
+      const uint32_t tapmask = units[u].tapmask ? (uint32_t)units[u].tapmask : 0x1FFu;
       mbar_wait(tempty, (it & 1) ^ 1);
       tc_fence_after();
       for (int b = 0; b < nblk; ++b) {
@@ -511,6 +513,7 @@ flat_wgrad_kernel(const WgradUnit* __restrict__ units, int num_units, const Flat
         if (elect_one_sync()) {
 #pragma unroll 1
           for (uint32_t tap = 0; tap < 9; ++tap) {
+            if (!((tapmask >> tap) & 1u)) continue;
             const uint32_t a_tap = a_lo + (tap / 3) * (uint32_t)g.Wp + (tap % 3);
 #pragma unroll 1
             for (uint32_t ks = 0; ks < 8; ++ks)
@@ -534,6 +537,7 @@ flat_wgrad_kernel(const WgradUnit* __restrict__ units, int num_units, const Flat
       tc_fence_after();
 #pragma unroll 1
       for (int tap = 0; tap < 9; ++tap) {
+        if (un.tapmask && !((un.tapmask >> tap) & 1)) continue;
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(tap * 32), acc);
         tmem_wait_ld();

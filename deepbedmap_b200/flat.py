@@ -24,7 +24,7 @@ LAUNCH_DTYPE = np.dtype([("in", "<u8"), ("wpacked", "<u8"), ("cin", "<i4"), ("no
                          ("w_chunk_stride", "<i8"), ("blk", EPI_DTYPE, (6,))])
 assert LAUNCH_DTYPE.itemsize == 472
 WGRAD_UNIT_DTYPE = np.dtype([("act", "<u8"), ("gout", "<u8"), ("partial", "<u8"), ("blk0", "<i4"), ("nblk", "<i4"),
-                             ("nslab", "<i4"), ("pad", "<i4", (3,))])
+                             ("nslab", "<i4"), ("tapmask", "<i4"), ("pad", "<i4", (2,))])
 assert WGRAD_UNIT_DTYPE.itemsize == 48
 WGRAD_REDUCE_DTYPE = np.dtype([("partial", "<u8"), ("dw", "<u8"), ("split_stride", "<i8"), ("nsplit", "<i4"),
                                ("cin_total", "<i4"), ("c0", "<i4"), ("o0", "<i4"), ("nch", "<i4"), ("mode", "<i4")])
@@ -107,6 +107,19 @@ def split_blocks(tiles: int, nsplit: int):
         out.append((b, k))
         b += k
     return out
+
+
+def s2d_tap_mask(c0: int, nch: int, C: int) -> int:
+    """Taps (bit t = tap t = ky * 3 + kx of the embedding 3x3 filter) that are not structurally zero for the phase
+    channels [c0, c0 + nch) of a 4x4 stride-2 filter over C input channels (phase = channel // C = py * 2 + px):
+    filter row 2 (ky - 1) + py + 1 must lie in 0..3, i.e. ky in {1, 2} for py = 0 and {0, 1} for py = 1; same in x."""
+    mask = 0
+    for ph in range(c0 // C, (c0 + nch - 1) // C + 1):
+        py, px = ph >> 1, ph & 1
+        for ky in ((1, 2) if py == 0 else (0, 1)):
+            for kx in ((1, 2) if px == 0 else (0, 1)):
+                mask |= 1 << (ky * 3 + kx)
+    return mask
 
 
 def chunk_channels(cin: int, chunk: int = 128):
@@ -310,7 +323,7 @@ class FlatTrunk:
                 for c0, nch in chunk_channels(cin):
                     first = len(units)
                     for blk0, nblk in splits:
-                        units.append((pb(act, c0), pb(gt, g0 + 32 * half), len(units), blk0, nblk, nch // 8, (0, 0, 0)))
+                        units.append((pb(act, c0), pb(gt, g0 + 32 * half), len(units), blk0, nblk, nch // 8, 0, (0, 0)))
                     reduces.append((first, Gr[f"{key}/W"].data_ptr(), PARTIAL_FLOATS, len(splits), cin, c0, 32 * half,
                                     nch, 0))
         need = len(units) * PARTIAL_FLOATS
@@ -679,7 +692,8 @@ class FlatConv:
                     first = len(units)
                     for blk0, nblk in splits:
                         units.append((self.xin[slot].data_ptr() + 2 * c0 * Pg, self.gin.data_ptr() + 2 * 32 * og * Pg,
-                                      base + len(units) * PARTIAL_FLOATS * 4, blk0, nblk, nch // 8, (0, 0, 0)))
+                                      base + len(units) * PARTIAL_FLOATS * 4, blk0, nblk, nch // 8,
+                                      s2d_tap_mask(c0, nch, im.C) if s2d else 0, (0, 0)))
                     if slot == 0:
                         ovalid = min(32, im.O - 32 * og)
                         mode = (1 if s2d else 0) | ((ovalid if ovalid < 32 else 0) << 8)

@@ -131,7 +131,7 @@ def test_flat_wgrad_and_bias_grad(flat, n, h, w, cin, nsplit):
     for c0, nch in chunks:
         first = len(units)
         for blk0, nblk in splits:
-            units.append((ab.data_ptr() + 2 * c0 * pg, gb.data_ptr(), len(units), blk0, nblk, nch // 8, (0, 0, 0)))
+            units.append((ab.data_ptr() + 2 * c0 * pg, gb.data_ptr(), len(units), blk0, nblk, nch // 8, 0, (0, 0)))
         reduces.append((first, dw.data_ptr(), flat.PARTIAL_FLOATS, len(splits), cin, c0, 0, nch, 0))
     partial = torch.full((len(units) * flat.PARTIAL_FLOATS,), float("nan"), device="cuda")
     u = np.array(units, dtype=flat.WGRAD_UNIT_DTYPE)
