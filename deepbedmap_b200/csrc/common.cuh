@@ -51,6 +51,9 @@ int det_scratch(size_t bytes, void** out);
 // (device, kernel, smem). A launch must not use a larger grid: a CTA that is not resident can never publish the flags
 // the resident ones spin on. Fails if not even one CTA fits.
 int resident_ctas(const void* kernel, int threads, size_t smem, int* resident);
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (device, kernel): the attribute is per device, a
+// per-process flag would leave the second GPU of a multi-device process without it
+int ensure_dyn_smem(const void* kernel, size_t smem);
 
 // ---------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA, tcgen05 (Blackwell). Raw PTX so that nothing but the CUDA

@@ -284,11 +284,7 @@ extern "C" int dbm_gemm_bf16(const float* a, long lda_m, long lda_k, long a_batc
   const bool a_col = lda_m == 1, b_row = ldb_n == 1;
   if (!p.atomic && a_col && b_row && k <= kSKMax && n >= 128) {
     constexpr int kSKSmem = (kSKMax * (128 + 8) + kSKMax * (64 + 8)) * 2 + 64 * (128 + 4) * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
-      DBM_CUDA(cudaFuncSetAttribute(gemm_bf16_shortk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSKSmem));
-      attr_done = true;
-    }
+    if (int rc = ensure_dyn_smem((const void*)gemm_bf16_shortk_kernel, kSKSmem)) return rc;
     gemm_bf16_shortk_kernel<<<dim3(ceil_div(m, 128), 1, batch), 256, kSKSmem, st>>>(p);
     return check_launch("gemm_bf16_shortk_kernel");
   }

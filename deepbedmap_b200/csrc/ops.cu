@@ -76,6 +76,19 @@ int resident_ctas(const void* kernel, int threads, size_t smem, int* resident) {
   return DBM_OK;
 }
 
+int ensure_dyn_smem(const void* kernel, size_t smem) {
+  struct Entry { int dev; const void* k; size_t smem; };
+  static Entry cache[128];
+  static int used = 0;
+  int dev = 0;
+  DBM_CUDA(cudaGetDevice(&dev));
+  for (int i = 0; i < used; ++i)
+    if (cache[i].dev == dev && cache[i].k == kernel && cache[i].smem >= smem) return DBM_OK;
+  DBM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (used < 128) cache[used++] = Entry{dev, kernel, smem};
+  return DBM_OK;
+}
+
 static inline int ew_grid(long total, int per_block = 256) {
   long b = (total + per_block - 1) / per_block;
   long cap = (long)num_sms() * 16;

@@ -277,11 +277,7 @@ static int stem_launch(const float* x, const float* w1, const float* w2, const f
   DBM_REQUIRE(n > 0 && h >= 3 && w >= 3, "stem: input %dx%d too small (need >= 3x3)", h, w);
   DBM_REQUIRE(out_cs_total >= out_cs0 + 16, "stem: output needs 16 slabs");
   const bool with_w1 = w1 != nullptr;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DBM_CUDA(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)stem_kernel<true>, kStemSmem)) return rc;
   StemParams p;
   p.x = x; p.w1 = w1; p.w2 = w2; p.w3 = w3;
   p.wt1 = w1_filter_tapmajor; p.wts = small_filters_tapmajor; p.bias = bias128;

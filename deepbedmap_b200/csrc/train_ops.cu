@@ -517,7 +517,10 @@ extern "C" int dbm_gen_image_loss_f32(const float* y_pred, const float* y_true, 
   DBM_REQUIRE(n > 0, "gen_image_loss: empty batch");
   DBM_REQUIRE(h >= kWin && w >= kWin && h <= kMaxImg && w <= kMaxImg && h % 4 == 0 && w % 4 == 0,
               "gen_image_loss: image %dx%d unsupported (need 9..48, multiple of 4)", h, w);
-  static bool init = false;
+  static bool init_dev[64] = {};   // __constant__ memory is per device
+  int dev = 0;
+  DBM_CUDA(cudaGetDevice(&dev));
+  bool& init = init_dev[dev & 63];
   if (!init) {
     float g[kWin];
     double s = 0;

@@ -286,12 +286,7 @@ int make_slab8_tmap(CUtensorMap* tm, const void* base, int N, int CS, int H, int
 template <int COUT, int CK, int STAGES>
 static int launch_umma(const CUtensorMap& tm, const UmmaConvParams& p, cudaStream_t st) {
   using Cfg = UmmaCfg<COUT, CK, STAGES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DBM_CUDA(cudaFuncSetAttribute(umma_conv3x3_kernel<COUT, CK, STAGES>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)umma_conv3x3_kernel<COUT, CK, STAGES>, Cfg::SMEM)) return rc;
   int grid = p.num_items < num_sms() ? p.num_items : num_sms();
   umma_conv3x3_kernel<COUT, CK, STAGES><<<grid, kThreads, Cfg::SMEM, st>>>(tm, p);
   return check_launch("umma_conv3x3_kernel");

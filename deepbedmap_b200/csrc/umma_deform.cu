@@ -421,12 +421,8 @@ extern "C" int dbm_deform_conv_umma(const void* x_slab8, const float* offset_sla
   DBM_REQUIRE(((uintptr_t)x_slab8 & 15) == 0 && ((uintptr_t)wpacked_ck64 & 15) == 0 &&
                   ((uintptr_t)offset_slab4 & 15) == 0 && ((uintptr_t)out_slab8 & 15) == 0,
               "deform_conv_umma: unaligned pointer");
-  static bool attr_done = false;
-  if (!attr_done) {
-    DBM_CUDA(cudaFuncSetAttribute(deform_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
-    DBM_CUDA(cudaFuncSetAttribute(deform_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)deform_umma_kernel<false>, kDSmem)) return rc;
+  if (int rc = ensure_dyn_smem((const void*)deform_umma_kernel<true>, kDSmem)) return rc;
   DeformParams p;
   p.N = n; p.H = h; p.W = w;
   p.tiles_x = ceil_div(w, kDTileW); p.tiles_y = ceil_div(h, kDTileH);
@@ -453,11 +449,7 @@ extern "C" int dbm_deform_conv_umma_nchw(const void* x_slab8, const float* offse
   DBM_REQUIRE(x_slab8 && offset_nchw18 && wpacked_ck64 && bias && out_nchw, "deform_conv_umma_nchw: null pointer");
   DBM_REQUIRE(((uintptr_t)x_slab8 & 15) == 0 && ((uintptr_t)wpacked_ck64 & 15) == 0,
               "deform_conv_umma_nchw: unaligned pointer");
-  static bool attr_done = false;
-  if (!attr_done) {
-    DBM_CUDA(cudaFuncSetAttribute(deform_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)deform_umma_kernel<false>, kDSmem)) return rc;
   DeformParams p;
   p.N = n; p.H = h; p.W = w;
   p.tiles_x = ceil_div(w, kDTileW); p.tiles_y = ceil_div(h, kDTileH);

@@ -771,14 +771,9 @@ __global__ void flat_from_nchw_vec8_kernel(const float* __restrict__ src, int C,
 }
 
 static int set_flat_attr() {
-  static bool done = false;
-  if (!done) {
-    DBM_CUDA(cudaFuncSetAttribute(flat_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlatSmem));
-    DBM_CUDA(cudaFuncSetAttribute(flat_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlatSmem));
-    DBM_CUDA(cudaFuncSetAttribute(flat_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlatSmem));
-    done = true;
-  }
-  return DBM_OK;
+  if (int rc = ensure_dyn_smem((const void*)flat_conv_kernel, kFlatSmem)) return rc;
+  if (int rc = ensure_dyn_smem((const void*)flat_wgrad_kernel, kFlatSmem)) return rc;
+  return ensure_dyn_smem((const void*)flat_chain_kernel, kFlatSmem);
 }
 
 }  // namespace dbm

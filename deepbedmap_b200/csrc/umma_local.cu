@@ -496,15 +496,9 @@ static int local_trunk_launch(bool bwd, const void* passes_dev, int count, int n
     smem = 1024 + 256 + 2 * (size_t)kLocSlabs * p.RA * 16 + (size_t)kLocStages * kLocStageBytes;
   }
   DBM_REQUIRE(smem <= 227 * 1024, "%s: image width %d needs %zu bytes of shared memory", who, w, smem);
-  static size_t attr_smem[2][2] = {{0, 0}, {0, 0}};
-  if (smem > attr_smem[bwd][solo]) {
-    const int v = (int)smem;
-    if (bwd && solo) DBM_CUDA(cudaFuncSetAttribute(local_trunk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
-    else if (bwd) DBM_CUDA(cudaFuncSetAttribute(local_trunk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
-    else if (solo) DBM_CUDA(cudaFuncSetAttribute(local_trunk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
-    else DBM_CUDA(cudaFuncSetAttribute(local_trunk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
-    attr_smem[bwd][solo] = smem;
-  }
+  const void* kfn = bwd ? (solo ? (const void*)local_trunk_kernel<true, true> : (const void*)local_trunk_kernel<true, false>)
+                        : (solo ? (const void*)local_trunk_kernel<false, true> : (const void*)local_trunk_kernel<false, false>);
+  if (int rc = ensure_dyn_smem(kfn, smem)) return rc;
   const int npairs = (n + p.group - 1) / p.group;
   const int cap = solo ? 2 * num_sms() : num_sms();
   const int grid = npairs < cap ? npairs : cap;
