@@ -14,6 +14,8 @@ stacks: the only collective.
 """
 from __future__ import annotations
 
+import os
+
 from collections import OrderedDict
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -241,10 +243,10 @@ class ContinentGrids:
     def ensure_rows(self, upto: int, prefetch_upto: Optional[int] = None):
         """Resident grids: nothing to do."""
 
-    def enqueue_rows(self, upto: int, prefetch_upto: Optional[int] = None):
+    def enqueue_rows(self, upto: int, prefetch_upto: Optional[int] = None, x_first: int = 0):
         """Resident grids: nothing to do."""
 
-    def wait_for(self, upto: int, x_upto: int):
+    def wait_for(self, upto: int, x_upto: int, x_from: int = 0):
         """Resident grids: nothing to do."""
 
 
@@ -277,19 +279,25 @@ class StreamedGrids(ContinentGrids):
         self._stream = torch.cuda.Stream()
         self._stream.wait_stream(torch.cuda.current_stream())
 
-    COL_BLOCKS = 6   # a band is uploaded in column blocks so that the first tiles of a row need not wait for all of it
+    COL_BLOCKS = 11  # a band is uploaded in column blocks (two tiles wide) so that the first tiles of a row need not wait for all of it
 
-    def _enqueue(self, upto: int):
+    def _enqueue(self, upto: int, x_first: int = 0):
+        """Upload of lowres rows [done, upto) in column blocks, starting with the block that holds lowres column
+        ``x_first`` (a rank whose tile run starts in the middle of a tile row needs that part of the band first; the
+        blocks to its left follow, the next tile row reads them)."""
         from . import ops
         upto = min(upto - self.row0, self.X.shape[2])
         if upto <= self._done:
             return
         Ws = self.X.shape[3]
         edges = [Ws * k // self.COL_BLOCKS for k in range(self.COL_BLOCKS + 1)]
+        blocks = list(zip(edges[:-1], edges[1:]))
+        k0 = max((k for k, (xa, _) in enumerate(blocks) if xa <= x_first), default=0)
+        blocks = blocks[k0:] + blocks[:k0]
         pinned = all(t.is_pinned() for t in self._host)
         with torch.cuda.stream(self._stream):
             st = self._stream.cuda_stream
-            for xa, xb in zip(edges[:-1], edges[1:]):
+            for xa, xb in blocks:
                 for host, dev, sc in zip(self._host, self._dev, self._scale):
                     a, b = sc * self._done, sc * upto
                     ha = sc * (self.row0 - self._host_row0)
@@ -300,25 +308,28 @@ class StreamedGrids(ContinentGrids):
                                      host.shape[3] * 4, (xb - xa) * sc * 4, b - a, st)
                         else:
                             dst.copy_(src, non_blocking=True)
-                self._events.append((upto, xb, self._stream.record_event()))
+                # (first row of the band, columns of the block, event): appended in stream order
+                self._events.append((self._done, xa, xb, self._stream.record_event()))
         self._done = upto
 
-    def enqueue_rows(self, upto: int, prefetch_upto: Optional[int] = None):
+    def enqueue_rows(self, upto: int, prefetch_upto: Optional[int] = None, x_first: int = 0):
         """Enqueue (without waiting) the upload of lowres rows < ``upto``, then of rows < ``prefetch_upto`` (one tile
         row ahead), on the copy stream."""
-        self._enqueue(upto)
+        self._enqueue(upto, x_first)
         if prefetch_upto is not None:
             self._enqueue(prefetch_upto)
 
-    def wait_for(self, upto: int, x_upto: int):
-        """Make the compute stream wait for rows < ``upto`` (absolute lowres row) x columns < ``x_upto`` only. The copy
-        stream is in order, so the event of the column block holding ``x_upto`` in the band that completes ``upto``
-        covers every earlier band and block."""
+    def wait_for(self, upto: int, x_upto: int, x_from: int = 0):
+        """Make the compute stream wait for rows < ``upto`` (absolute lowres row) x columns [``x_from``, ``x_upto``)
+        only. The copy stream is in order, so the LAST enqueued block that holds any of those elements covers every
+        earlier one."""
         need = min(upto - self.row0, self.X.shape[2])
-        for rows_done, x_done, ev in self._events:
-            if rows_done >= need and x_done >= x_upto:
-                torch.cuda.current_stream().wait_event(ev)
-                return
+        last = None
+        for row_start, xa, xb, ev in self._events:
+            if row_start < need and xa < x_upto and xb > x_from:
+                last = ev
+        if last is not None:
+            torch.cuda.current_stream().wait_event(last)
 
     def ensure_rows(self, upto: int, prefetch_upto: Optional[int] = None):
         """Enqueue the upload of lowres rows up to ``prefetch_upto`` (one tile row ahead) on the copy
@@ -396,10 +407,18 @@ def predict_continent(model, X, W1=None, W2=None, W3=None, final_shape=(18000, 2
         results = ops.empty(max_tiles_per_rank(len(plan), world), ary_shape[0], ary_shape[1])
         ops.fill(results, float("nan"))
     row_list = list(rows_of_tiles.items())
+    trace = [] if os.environ.get("DBM_TILER_TRACE") else None   # (label, host seconds, CUDA event on the compute stream)
+    if trace is not None:
+        import time as _time
+        def mark(label):
+            trace.append((label, _time.perf_counter(), torch.cuda.current_stream().record_event(
+                torch.cuda.Event(enable_timing=True))))
+        mark("start")
     for k, (ty, row_tiles) in enumerate(row_list):
         nxt = max(t[1] for _, t in row_list[k + 1][1]) if k + 1 < len(row_list) else None
         rows_upto = max(t[1] for _, t in row_tiles)
-        g.enqueue_rows(rows_upto, prefetch_upto=nxt)
+        # the first tile row of a run may start in the middle of the row: its part of the band is uploaded first
+        g.enqueue_rows(rows_upto, prefetch_upto=nxt, x_first=min(t[2] for _, t in row_tiles) if k == 0 else 0)
         # same-shape tiles in batches, batches ordered by their right-most grid column: a streamed upload arrives in
         # column blocks, so the left batches of a tile row start while its right part is still on the wire
         chunks = []
@@ -408,7 +427,7 @@ def predict_continent(model, X, W1=None, W2=None, W3=None, final_shape=(18000, 2
                 chunks.append(((h, w), tiles[b0:b0 + batch_tiles]))
         chunks.sort(key=lambda c: max(t[3] for _, t in c[1]))
         for (h, w), chunk in chunks:
-            g.wait_for(rows_upto, max(t[3] for _, t in chunk))
+            g.wait_for(rows_upto, max(t[3] for _, t in chunk), min(t[2] for _, t in chunk))
             nb = len(chunk)
             xb = ops.empty(nb, 1, h, w)
             w1b = ops.empty(nb, 1, 10 * h, 10 * w)
@@ -437,8 +456,24 @@ def predict_continent(model, X, W1=None, W2=None, W3=None, final_shape=(18000, 2
                     ops.call("dbm_place_tile_f32", y[j].data_ptr(), th, tw, py, px, results[i - a].data_ptr(),
                              ary_shape[0], ary_shape[1], 0, 0, hh, ww, st())
             del y, xb, w1b, w2b, w3b
-        if stream_out:
-            # this tile row of the local canvas is final: hand its rectangle to the copy stream
+            if trace is not None:
+                mark(f"row{ty} batch x<={max(t[3] for _, t in chunk)}")
+            if stream_out and canvas16 is None:
+                # these tiles' rectangles of the local canvas are final: hand them to the copy stream now (per batch, not
+                # per tile row: the device->host stream of a row overlaps the rest of that row, and what is left
+                # after the last batch of a run is one batch, not 88 MB)
+                sg = segs[ty]
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                pitch = final_shape[1] * 4
+                for i, t in chunk:
+                    xs_t = sg[2] if i == sg[4] else t[6]
+                    xe_t = sg[3] if i == sg[5] - 1 else t[7]
+                    ops.call("dbm_copy2d_async", out.tensor.data_ptr() + sg[0] * pitch + xs_t * 4, pitch,
+                             canvas.data_ptr() + (sg[0] - row_lo) * pitch + xs_t * 4, pitch, (xe_t - xs_t) * 4,
+                             sg[1] - sg[0], copy_stream.cuda_stream)
+        if stream_out and canvas16 is not None:
+            # int16 product: this tile row of the local canvas is final -- convert it and hand its rectangle to the copy
+            # stream (the float32 product went out batch by batch above)
             ys, ye, xs, xe, _, _ = segs[ty]
             src, esz = canvas, 4
             if canvas16 is not None:
@@ -452,9 +487,20 @@ def predict_continent(model, X, W1=None, W2=None, W3=None, final_shape=(18000, 2
                      src.data_ptr() + (ys - row_lo) * pitch + xs * esz, pitch, (xe - xs) * esz, ye - ys,
                      copy_stream.cuda_stream)
     if stream_out:
+        if trace is not None:
+            mark("enqueued")
         copy_stream.synchronize()
+        if trace is not None:
+            t_copy = _time.perf_counter()
         if dist is not None:
             dist.barrier()
+        if trace is not None:
+            t_end = _time.perf_counter()
+            torch.cuda.synchronize()
+            h0, e0 = trace[0][1], trace[0][2]
+            print(f"[tiler trace rank {rank}] host: all enqueued {1e3 * (trace[-1][1] - h0):.1f} ms, copies done "
+                  f"{1e3 * (t_copy - h0):.1f} ms, barrier done {1e3 * (t_end - h0):.1f} ms; device (compute stream): "
+                  + ", ".join(f"{lab} {e0.elapsed_time(ev):.1f}" for lab, _, ev in trace[1:]), flush=True)
         return out.array if rank == 0 else None
     if world > 1:
         def new_canvas():

@@ -597,6 +597,37 @@ def test_streamed_host_grids_and_host_dem_equal_resident_path():
     assert np.array_equal(predict_continent(m, X, W1, W2, W3, **kw), want, equal_nan=True)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_streamed_grids_upload_order_and_waits(pinned):
+    """StreamedGrids: bands of rows in column blocks, the block holding ``x_first`` first (a rank whose tile run starts
+    in the middle of a tile row); after ``wait_for(rows, x_upto, x_from)`` exactly that window is guaranteed on the
+    compute stream, and once everything was enqueued the device copies equal the host grids."""
+    from deepbedmap_b200 import tiler
+    rng = np.random.RandomState(3)
+    H, W = 40, 57
+    host = [rng.rand(1, 1, H, W), rng.rand(1, 1, 10 * H, 10 * W), rng.rand(1, 2, 2 * H, 2 * W), rng.rand(1, 1, H, W)]
+    host = [torch.from_numpy(a.astype(np.float32)) for a in host]
+    if pinned:
+        host = [t.pin_memory() for t in host]
+    g = tiler.StreamedGrids(*host)
+    for d in g._dev:
+        d.fill_(-1.0)
+    g.enqueue_rows(25, prefetch_upto=None, x_first=31)
+    first = g._events[0]
+    assert first[1] <= 31 < first[2] and len(g._events) == g.COL_BLOCKS        # the block holding x_first leads
+    g.wait_for(25, 45, 31)
+    win = [(g.X, host[0], 1), (g.W1, host[1], 10), (g.W2, host[2], 2), (g.W3, host[3], 1)]
+    got = [(d[:, :, :s * 25, s * 31:s * 45].clone(), h[:, :, :s * 25, s * 31:s * 45]) for d, h, s in win]
+    torch.cuda.synchronize()
+    for a, b in got:
+        assert torch.equal(a.cpu(), b)
+    g.enqueue_rows(H)
+    g.wait_for(H, W)
+    torch.cuda.synchronize()
+    for d, h, _ in win:
+        assert torch.equal(d.cpu(), h)
+
+
 def test_int16_dem_matches_numpy_astype():
     """the DEM the reference ships is Y_hat.astype(np.int16) (deepbedmap.py:751); bit-exact."""
     from deepbedmap_b200 import ops, predict_continent
