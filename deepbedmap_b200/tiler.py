@@ -243,7 +243,8 @@ class ContinentGrids:
     def ensure_rows(self, upto: int, prefetch_upto: Optional[int] = None):
         """Resident grids: nothing to do."""
 
-    def enqueue_rows(self, upto: int, prefetch_upto: Optional[int] = None, x_first: int = 0):
+    def enqueue_rows(self, upto: int, prefetch_upto: Optional[int] = None, x_first: int = 0,
+                     x_last: Optional[int] = None, keep_from: Optional[int] = None):
         """Resident grids: nothing to do."""
 
     def wait_for(self, upto: int, x_upto: int, x_from: int = 0):
@@ -281,10 +282,12 @@ class StreamedGrids(ContinentGrids):
 
     COL_BLOCKS = 11  # a band is uploaded in column blocks (two tiles wide) so that the first tiles of a row need not wait for all of it
 
-    def _enqueue(self, upto: int, x_first: int = 0):
+    def _enqueue(self, upto: int, x_first: int = 0, x_last: Optional[int] = None, keep_from: Optional[int] = None):
         """Upload of lowres rows [done, upto) in column blocks, starting with the block that holds lowres column
-        ``x_first`` (a rank whose tile run starts in the middle of a tile row needs that part of the band first; the
-        blocks to its left follow, the next tile row reads them)."""
+        ``x_first``: a rank whose tile run starts in the middle of a tile row needs that part of the band first. The
+        blocks to its left follow, and only from absolute row ``keep_from`` on (the first row the NEXT tile row reads;
+        None: not at all) -- nothing of this run reads the rest. Blocks wholly right of ``x_last`` (a run ending in the
+        middle of its last tile row) are not uploaded."""
         from . import ops
         upto = min(upto - self.row0, self.X.shape[2])
         if upto <= self._done:
@@ -293,13 +296,19 @@ class StreamedGrids(ContinentGrids):
         edges = [Ws * k // self.COL_BLOCKS for k in range(self.COL_BLOCKS + 1)]
         blocks = list(zip(edges[:-1], edges[1:]))
         k0 = max((k for k, (xa, _) in enumerate(blocks) if xa <= x_first), default=0)
-        blocks = blocks[k0:] + blocks[:k0]
+        todo = [(xa, xb, self._done) for xa, xb in blocks[k0:] if x_last is None or xa < x_last]
+        if k0 > 0 and keep_from is not None:
+            r0 = max(self._done, min(keep_from - self.row0, upto))
+            if r0 < upto:
+                todo += [(xa, xb, r0) for xa, xb in blocks[:k0]]
+        elif k0 > 0 and x_first == 0:
+            todo += [(xa, xb, self._done) for xa, xb in blocks[:k0]]
         pinned = all(t.is_pinned() for t in self._host)
         with torch.cuda.stream(self._stream):
             st = self._stream.cuda_stream
-            for xa, xb in blocks:
+            for xa, xb, r0 in todo:
                 for host, dev, sc in zip(self._host, self._dev, self._scale):
-                    a, b = sc * self._done, sc * upto
+                    a, b = sc * r0, sc * upto
                     ha = sc * (self.row0 - self._host_row0)
                     for c in range(dev.shape[1]):
                         src, dst = host[0, c, ha + a:ha + b, sc * xa:sc * xb], dev[0, c, a:b, sc * xa:sc * xb]
@@ -308,14 +317,15 @@ class StreamedGrids(ContinentGrids):
                                      host.shape[3] * 4, (xb - xa) * sc * 4, b - a, st)
                         else:
                             dst.copy_(src, non_blocking=True)
-                # (first row of the band, columns of the block, event): appended in stream order
-                self._events.append((self._done, xa, xb, self._stream.record_event()))
+                # (first row of the upload, columns of the block, event): appended in stream order
+                self._events.append((r0, xa, xb, self._stream.record_event()))
         self._done = upto
 
-    def enqueue_rows(self, upto: int, prefetch_upto: Optional[int] = None, x_first: int = 0):
-        """Enqueue (without waiting) the upload of lowres rows < ``upto``, then of rows < ``prefetch_upto`` (one tile
-        row ahead), on the copy stream."""
-        self._enqueue(upto, x_first)
+    def enqueue_rows(self, upto: int, prefetch_upto: Optional[int] = None, x_first: int = 0,
+                     x_last: Optional[int] = None, keep_from: Optional[int] = None):
+        """Enqueue (without waiting) the upload of lowres rows < ``upto`` (see ``_enqueue`` for the column window of a
+        run's first / last tile row), then of rows < ``prefetch_upto`` (one tile row ahead), on the copy stream."""
+        self._enqueue(upto, x_first, x_last, keep_from)
         if prefetch_upto is not None:
             self._enqueue(prefetch_upto)
 
@@ -417,8 +427,17 @@ def predict_continent(model, X, W1=None, W2=None, W3=None, final_shape=(18000, 2
     for k, (ty, row_tiles) in enumerate(row_list):
         nxt = max(t[1] for _, t in row_list[k + 1][1]) if k + 1 < len(row_list) else None
         rows_upto = max(t[1] for _, t in row_tiles)
-        # the first tile row of a run may start in the middle of the row: its part of the band is uploaded first
-        g.enqueue_rows(rows_upto, prefetch_upto=nxt, x_first=min(t[2] for _, t in row_tiles) if k == 0 else 0)
+        # A run may start / end in the middle of a tile row: of its first row's band the part it needs goes first (the
+        # rest only as far as the next tile row reads it), of its last row's band only the part it needs is uploaded.
+        def band(kk):
+            tl = row_list[kk][1]
+            last = kk == len(row_list) - 1
+            return dict(x_first=min(t[2] for _, t in tl) if kk == 0 else 0,
+                        x_last=max(t[3] for _, t in tl) if last else None,
+                        keep_from=min(t[0] for _, t in row_list[kk + 1][1]) if (kk == 0 and not last) else None)
+        g.enqueue_rows(rows_upto, **band(k))
+        if nxt is not None:
+            g.enqueue_rows(nxt, **band(k + 1))
         # same-shape tiles in batches, batches ordered by their right-most grid column: a streamed upload arrives in
         # column blocks, so the left batches of a tile row start while its right part is still on the wire
         chunks = []

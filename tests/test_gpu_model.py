@@ -612,9 +612,10 @@ def test_streamed_grids_upload_order_and_waits(pinned):
     g = tiler.StreamedGrids(*host)
     for d in g._dev:
         d.fill_(-1.0)
-    g.enqueue_rows(25, prefetch_upto=None, x_first=31)
+    g.enqueue_rows(25, prefetch_upto=None, x_first=31, keep_from=10)
     first = g._events[0]
     assert first[1] <= 31 < first[2] and len(g._events) == g.COL_BLOCKS        # the block holding x_first leads
+    xa0 = first[1]                                                             # left edge of that block
     g.wait_for(25, 45, 31)
     win = [(g.X, host[0], 1), (g.W1, host[1], 10), (g.W2, host[2], 2), (g.W3, host[3], 1)]
     got = [(d[:, :, :s * 25, s * 31:s * 45].clone(), h[:, :, :s * 25, s * 31:s * 45]) for d, h, s in win]
@@ -624,8 +625,49 @@ def test_streamed_grids_upload_order_and_waits(pinned):
     g.enqueue_rows(H)
     g.wait_for(H, W)
     torch.cuda.synchronize()
-    for d, h, _ in win:
-        assert torch.equal(d.cpu(), h)
+    for d, h, sc in win:
+        dc = d.cpu()
+        # left of the leading block only the rows the next tile row reads (>= keep_from) were uploaded
+        assert torch.equal(dc[:, :, sc * 10:], h[:, :, sc * 10:]) and torch.equal(dc[..., sc * xa0:], h[..., sc * xa0:])
+        if xa0 > 0:
+            assert bool((dc[:, :, :sc * 10, :sc * xa0] == -1.0).all())
+    # a run ending in the middle of its last tile row: blocks wholly right of x_last are not uploaded
+    g2 = tiler.StreamedGrids(*host)
+    g2.X.fill_(-1.0)
+    g2.enqueue_rows(H, x_last=20)
+    g2.wait_for(H, 20)
+    torch.cuda.synchronize()
+    xr = max(e[2] for e in g2._events)
+    assert 20 <= xr < W and torch.equal(g2.X.cpu()[..., :xr], host[0][..., :xr]) and bool((g2.X.cpu()[..., xr:] == -1.0).all())
+
+
+@pytest.mark.parametrize("world", [3, 5])
+def test_multi_rank_streaming_partitions_the_dem(world, monkeypatch):
+    """The per-rank streamed path (HostBand of the rank's rows in, HostDEM out, first / last tile rows of a run cut in
+    the middle) run rank by rank in ONE process into the same host DEM: the union of what the ranks write equals the
+    single-rank product bit for bit, NaN frame included (what an N-GPU torchrun job produces, without N GPUs)."""
+    from deepbedmap_b200 import predict_continent, tiler
+    m, _ = make_generator(1, "fp32")
+    final, ary, pad = (120, 160), (40, 40), (3, 3)
+    H, W = 32, 42
+    rng = np.random.RandomState(13)
+    X = rng.rand(1, 1, H, W).astype(np.float32)
+    W1 = (rng.rand(1, 1, 10 * H, 10 * W) - 0.3).astype(np.float32)
+    W2 = (rng.rand(1, 2, 2 * H, 2 * W) - 0.3).astype(np.float32)
+    W3 = (rng.rand(1, 1, H, W) - 0.3).astype(np.float32)
+    kw = dict(final_shape=final, ary_shape=ary, stride=ary, xtrapad=pad, batch_tiles=2)
+    want = predict_continent(m, X, W1, W2, W3, **kw)
+    dem = tiler.HostDEM(final)
+    dem.tensor.fill_(7.0)
+    plan = tiler.tile_plan(final, ary, ary, pad)
+    for rank in range(world):
+        monkeypatch.setattr(tiler, "_dist", lambda rank=rank: (None, rank, world))
+        r0, r1 = tiler.rank_row_band(plan, rank, world)
+        band = tiler.HostBand(*[torch.from_numpy(np.ascontiguousarray(a[:, :, s * r0:s * r1])).pin_memory()
+                                for a, s in ((X, 1), (W1, 10), (W2, 2), (W3, 1))], row0=r0, full_rows=H)
+        predict_continent(m, band, out=dem, **kw)
+    monkeypatch.undo()
+    assert np.array_equal(dem.array, want, equal_nan=True)
 
 
 def test_int16_dem_matches_numpy_astype():
