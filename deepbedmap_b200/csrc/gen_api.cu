@@ -314,8 +314,8 @@ extern "C" int dbm_gen_create(int num_residual_blocks, float residual_scaling, i
   DBM_REQUIRE(out != nullptr, "gen_create: null output");
   DBM_REQUIRE(num_residual_blocks >= 1 && 2 + 15 * num_residual_blocks <= 512, "gen_create: %d residual blocks",
               num_residual_blocks);
-  DBM_REQUIRE(inter_channels == 32, "gen_create: the model-level tensor-core path implements inter_channels == 32 "
-                                    "(the reference's value, srgan_train.py:283-284); got %d", inter_channels);
+  DBM_REQUIRE(inter_channels == 32 || inter_channels == 64, "gen_create: inter_channels must be 32 or 64 (the "
+              "reference's search space, srgan_train.py:283-284); got %d", inter_channels);
   dbm_gen* h = new dbm_gen();
   Gen* g = &h->g;
   g->nb = num_residual_blocks; g->beta = residual_scaling; g->inter = inter_channels;

@@ -848,8 +848,7 @@ class GeneratorModel(_Link):
     def _c_forward_applies(self):
         return (self.c_model_api and self.persistent_trunk and self.paired_trunk and self.paired_convs == (1, 3)
                 and not self.per_layer_ck16
-                and self.stem_w1_tensor_core and not self.fuse_out_projection and self.inter_channels == 32
-                and self.out_channels == 1)
+                and self.stem_w1_tensor_core and not self.fuse_out_projection and self.out_channels == 1)
 
     def _forward_c_api(self, x, w1, w2, w3):
         """GeneratorModel.forward through dbm_gen_forward: this class only owns the flat parameter buffer (bound into

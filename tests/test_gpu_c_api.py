@@ -69,3 +69,22 @@ def test_c_api_follows_weight_updates():
     assert not torch.equal(y0, y1)
     m.c_model_api = False
     assert torch.equal(m.forward(*ins).array, y1)
+
+
+def test_c_model_api_wide_dense_blocks_equal_python_composition():
+    """inter_channels = 64 (srgan_train.py:283-284) through dbm_gen_forward (the handle builds the unpaired pass table
+    and the 320-channel dense-block workspace) against the same kernels composed by the Python class, bit for bit, and
+    against the oracle."""
+    from deepbedmap_b200 import GeneratorModel
+    nb = 2
+    params = O.init_generator_params(nb, seed=0, bias_std=0.1, scale=0.5, inter_channels=64)
+    m = GeneratorModel(num_residual_blocks=nb, precision="bf16", inter_channels=64)
+    for k, v in params.items():
+        m.set_param(k, v)
+    ins = O.synthetic_inputs(2, 37, 44)
+    assert m._c_forward_applies()
+    y = m.forward(*ins).numpy()
+    m.c_model_api = False
+    assert np.array_equal(m.forward(*ins).numpy(), y)
+    ref = O.generator_forward_numpy(params, *ins, num_residual_blocks=nb)
+    assert rel_l2(y, ref) < 2e-2
