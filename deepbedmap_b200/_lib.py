@@ -96,6 +96,7 @@ SIGNATURES = {
     "dbm_gen_set_param": [_P, ctypes.c_char_p, _P, _I, ctypes.POINTER(_I)],
     "dbm_gen_bind_params": [_P, _P],
     "dbm_gen_mark_updated": [_P],
+    "dbm_gen_set_precision": [_P, _I],
     "dbm_gen_workspace_bytes": [_P, _I, _I, _I],
     "dbm_gen_forward": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, ctypes.c_size_t, _P],
 }

@@ -861,6 +861,7 @@ class GeneratorModel(_Link):
             ops.call("dbm_gen_create", self.num_residual_blocks, float(self.residual_scaling), self.inter_channels,
                      ctypes.byref(hnd))
             ops.call("dbm_gen_bind_params", hnd, self.flat.data_ptr())
+            ops.call("dbm_gen_set_precision", hnd, 1 if self.precision == "bf16x3" else 0)
             self._cgen, self._cgen_version = (hnd, self.residual_scaling), -1
         hnd = self._cgen[0]
         if self._cgen_version != self.version:
@@ -964,6 +965,9 @@ class GeneratorModel(_Link):
         chunk, fp32 accumulation and residual stream) -> deformable layers in fp32."""
         n, _, h, w = x.shape
         H, W = h - 2, w - 2
+        if self.c_model_api and self.out_channels == 1:
+            # the same sequence composed in C++ (csrc/gen_api.cu, dbm_gen_set_precision(gen, 1)): bit-identical
+            return self._forward_c_api(x, w1, w2, w3)
         pk = self._pack(self.PACK_SPLIT)
         ws = self._split_workspace(n, H, W, pk)
         st = ops.stream()

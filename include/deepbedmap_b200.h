@@ -355,7 +355,8 @@ int dbm_gather_rows_f32(const float* src, long src_rows, const long* index_dev, 
  * the pass table of the persistent trunk kernel -- the only device memory this library ever allocates. Activations
  * live in the caller's `workspace` (device, 1024-byte aligned, dbm_gen_workspace_bytes(n, h, w) bytes); everything is
  * enqueued on `stream`. Arithmetic: the tensor-core inference path (bf16 operands, fp32 accumulation, fp32 residual
- * stream; conv_on_W1 as a split-bf16 GEMM), inter_channels == 32 and out_channels == 1 as in the reference.
+ * stream; conv_on_W1 as a split-bf16 GEMM) or, after dbm_gen_set_precision(gen, 1), the split-bf16 path;
+ * inter_channels 32 or 64, out_channels == 1 as in the reference.
  *   x (n,1,h,w), w1 (n,1,10h,10w), w2 (n,2,2h,2w), w3 (n,1,h,w) fp32 NCHW device -> y_out (n,1,4(h-2),4(w-2)).
  * A handle is bound to the device current at creation and is not thread-safe (one host thread per GPU, as the
  * reference's one process per GPU, srgan_train.py:58-61). The first forward on a new (workspace, shape) uploads the
@@ -369,6 +370,10 @@ int dbm_gen_array_info(const dbm_gen* gen, int index, const char** key, int* ndi
 int dbm_gen_set_param(dbm_gen* gen, const char* key, const float* host_values, int ndim, const int* dims);
 int dbm_gen_bind_params(dbm_gen* gen, float* device_flat);
 int dbm_gen_mark_updated(dbm_gen* gen);                     /* after writing into a bound parameter buffer */
+/* precision of dbm_gen_forward: 0 = bf16 tensor-core path (default), 1 = "bf16x3" -- split-bf16 trunk and upsample convs
+ * on the tensor cores (dbm_trunk_umma_split), input block and deformable layers on the fp32 kernels: fp32-grade results
+ * (the reference computes in fp32). Changes dbm_gen_workspace_bytes; call before sizing the workspace. */
+int dbm_gen_set_precision(dbm_gen* gen, int precision);
 size_t dbm_gen_workspace_bytes(const dbm_gen* gen, int n, int h, int w);
 int dbm_gen_forward(dbm_gen* gen, const float* x, const float* w1, const float* w2, const float* w3, int n, int h,
                     int w, float* y_out, void* workspace, size_t workspace_bytes, cudaStream_t stream);

@@ -1,6 +1,7 @@
 // C-only host of the generator (no Python, no model.py): creates a dbm_gen handle, loads every parameter array through
 // dbm_gen_set_param by its Chainer .npz key, runs dbm_gen_forward and writes the prediction.
 //   usage: gen_forward_main <num_residual_blocks> <residual_scaling> <n> <h> <w> <params.bin> <inputs.bin> <out.bin>
+//          [precision: 0 = bf16 (default), 1 = bf16x3]
 //   params.bin : the arrays of dbm_gen_array_info, in its order, float32, concatenated
 //   inputs.bin : x (n,1,h,w) | w1 (n,1,10h,10w) | w2 (n,2,2h,2w) | w3 (n,1,h,w), float32
 //   out.bin    : y (n,1,4(h-2),4(w-2)) float32
@@ -35,12 +36,14 @@ static std::vector<float> read_all(const char* path) {
 }
 
 int main(int argc, char** argv) {
-  if (argc != 9) { fprintf(stderr, "usage: see the header of this file\n"); return 2; }
+  if (argc != 9 && argc != 10) { fprintf(stderr, "usage: see the header of this file\n"); return 2; }
+  const int precision = argc == 10 ? atoi(argv[9]) : 0;   // 0 = bf16, 1 = bf16x3 (dbm_gen_set_precision)
   const int nb = atoi(argv[1]);
   const float beta = (float)atof(argv[2]);
   const int n = atoi(argv[3]), h = atoi(argv[4]), w = atoi(argv[5]);
   dbm_gen* gen = nullptr;
   CHECK(dbm_gen_create(nb, beta, 32, &gen));
+  CHECK(dbm_gen_set_precision(gen, precision));
   std::vector<float> params = read_all(argv[6]);
   if ((long)params.size() != dbm_gen_count_params(gen)) {
     fprintf(stderr, "params.bin holds %zu floats, the model has %ld\n", params.size(), dbm_gen_count_params(gen));

@@ -88,3 +88,34 @@ def test_c_model_api_wide_dense_blocks_equal_python_composition():
     assert np.array_equal(m.forward(*ins).numpy(), y)
     ref = O.generator_forward_numpy(params, *ins, num_residual_blocks=nb)
     assert rel_l2(y, ref) < 2e-2
+
+
+def test_c_host_runs_the_split_bf16_forward(tmp_path):
+    """dbm_gen_set_precision(gen, 1): the split-bf16 path (fp32 stem, split trunk + upsample convs, fp32 deformable
+    layers) composed in C++: fp32-grade against the fp64 oracle from a C-only host, and bit-identical to the Python
+    class, whether it drives the handle or composes the per-op entry points itself."""
+    nb, n, h, w = 2, 2, 21, 38
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "gen_forward_main")
+    lib_dir = os.path.join(ROOT, "deepbedmap_b200")
+    subprocess.run([nvcc, "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "c_api", "gen_forward_main.cu"), "-L", lib_dir, "-ldeepbedmap_b200",
+                    "-Xlinker", "-rpath", "-Xlinker", lib_dir], check=True)
+    params = O.init_generator_params(nb, seed=0, bias_std=0.1, scale=0.7)
+    ins = O.synthetic_inputs(n, h, w)
+    np.concatenate([v.reshape(-1) for v in params.values()]).astype(np.float32).tofile(tmp_path / "params.bin")
+    np.concatenate([a.reshape(-1) for a in ins]).astype(np.float32).tofile(tmp_path / "inputs.bin")
+    out = subprocess.run([exe, str(nb), "0.1", str(n), str(h), str(w), str(tmp_path / "params.bin"),
+                          str(tmp_path / "inputs.bin"), str(tmp_path / "out.bin"), "1"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    y = np.fromfile(tmp_path / "out.bin", np.float32).reshape(n, 1, 4 * (h - 2), 4 * (w - 2))
+    ref = O.generator_forward_numpy(params, *ins, num_residual_blocks=nb)
+    print(f"C host, bf16x3: rel_l2 vs fp64 oracle {rel_l2(y, ref):.2e}")
+    assert rel_l2(y, ref) < 5e-5
+    from deepbedmap_b200 import GeneratorModel
+    m = GeneratorModel(num_residual_blocks=nb, precision="bf16x3")
+    for k, v in params.items():
+        m.set_param(k, v)
+    assert np.array_equal(m.forward(*ins).numpy(), y)           # through the handle
+    m.c_model_api = False
+    assert np.array_equal(m.forward(*ins).numpy(), y)           # composed from per-op calls in model.py
