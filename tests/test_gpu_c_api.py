@@ -53,11 +53,13 @@ def test_c_host_runs_the_generator_forward(tmp_path, nb, n, h, w):
     assert np.array_equal(composed, y)
 
 
-def test_c_api_follows_weight_updates():
-    """The handle views the class's flat parameter buffer: a set_param / optimizer update must reach the packed operands."""
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_c_api_follows_weight_updates(precision):
+    """The handle views the class's flat parameter buffer: a set_param / optimizer update must reach the packed operands
+    (bf16 and split-bf16 images alike)."""
     from deepbedmap_b200 import GeneratorModel
     params = O.init_generator_params(1, seed=0, bias_std=0.1, scale=0.7)
-    m = GeneratorModel(num_residual_blocks=1, precision="bf16")
+    m = GeneratorModel(num_residual_blocks=1, precision=precision)
     for k, v in params.items():
         m.set_param(k, v)
     m.local_trunk = False
