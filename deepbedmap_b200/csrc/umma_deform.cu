@@ -17,12 +17,20 @@ namespace dbm {
 // cycles, ncu r1g) : thread = (pixel, tap slot), all 64 channels of one tap per thread.
 constexpr int kDTileW = 32, kDTileH = 8;
 constexpr int kDPix = kDTileW * kDTileH;   // 256
-constexpr int kDStages = 3;                // stage s holds taps s, s+3, s+6 (filled by tap-slot s)
+constexpr int kDSlots = 3;                 // tap-slot s gathers taps s, s+3, s+6 of every item ...
+constexpr int kDBuf = 1;                   // ... into kDBuf stages of its own, in turn
+constexpr int kDStages = kDBuf * kDSlots;
+constexpr int kDWRing = 3;                 // the 576x64 filter is not resident: its nine 8 KB tap slices stream through a
+                                           // three-slot ring, two taps ahead of the MMAs. The 49 KB this frees go to the
+                                           // L1 cache the bilinear gathers live on (the shared-memory carve-out drops from
+                                           // 172 KB to 123 KB)
 constexpr int kDGatherThreads = 3 * kDPix; // 768
 constexpr int kDThreads = kDGatherThreads + 128 + 32;  // + 4 epilogue warps + MMA warp
 constexpr int kDABytes = kDPix * 64 * 2;               // one tap: 2 M-tiles x 128 px x 64 ch bf16
 constexpr int kDBBytes = 9 * 64 * 64 * 2;
-constexpr int kDSmem = kDBBytes + kDStages * kDABytes + 256 + 9 * 64 * 4 + 1024;
+constexpr int kDWTapBytes = kDBBytes / 9;              // 8192
+constexpr int kDSmem = kDWRing * kDWTapBytes + kDStages * kDABytes + 256 + 9 * 64 * 4 + 1024;
+static_assert(kDSmem <= 227 * 1024, "deform_umma_kernel: shared memory");
 
 struct DeformParams {
   int N, H, W;
@@ -121,16 +129,17 @@ template <bool PROJ>   // PROJ: also compute the following single-output layer's
 __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* smB = smem;
-  uint8_t* smA = smem + kDBBytes;
-  uint64_t* bars = (uint64_t*)(smem + kDBBytes + kDStages * kDABytes);
+  uint8_t* smB = smem;                    // [kDWRing][8 KB] filter tap ring
+  uint8_t* smA = smem + kDWRing * kDWTapBytes;
+  uint64_t* bars = (uint64_t*)(smA + kDStages * kDABytes);
   uint64_t* full = bars;                  // gather -> MMA   (one arrive per gather warp)
   uint64_t* empty = bars + kDStages;      // MMA -> gather   (tcgen05.commit)
   uint64_t* tfull = bars + 2 * kDStages;  // MMA -> epilogue
   uint64_t* tempty = bars + 2 * kDStages + 2;
-  uint64_t* wbar = bars + 2 * kDStages + 4;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kDStages + 5);
-  float* sproj = (float*)(smem + kDBBytes + kDStages * kDABytes + 256);   // [9][64] projection filter, tap-major
+  uint64_t* wfull = bars + 2 * kDStages + 4;             // [kDWRing] filter tap landed
+  uint64_t* wempty = wfull + kDWRing;                    // [kDWRing] the MMAs that read the slot have completed
+  uint32_t* tmem_slot = (uint32_t*)(wempty + kDWRing);
+  float* sproj = (float*)((uint8_t*)bars + 256);         // [9][64] projection filter, tap-major
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kMmaWarp = kDGatherThreads / 32;
@@ -144,7 +153,10 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
       mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], 4);
     }
-    mbar_init(wbar, 1);
+    for (int r = 0; r < kDWRing; ++r) {
+      mbar_init(&wfull[r], 1);
+      mbar_init(&wempty[r], 1);
+    }
     fence_mbar_init();
   }
   if (PROJ)
@@ -164,8 +176,9 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
     const int t = threadIdx.x;
     const int pix = t & (kDPix - 1), slot = t >> 8;
     uint32_t fills = 0;
-    // element (pixel m of M-tile j, slab q) of the stage lives at ((j * 8 + q) * 128 + m) * 16 bytes
-    uint8_t* a = smA + slot * kDABytes + (pix >> 7) * (kDABytes / 2) + (pix & 127) * 16;
+    // element (pixel m of M-tile j, slab q) of the stage lives at ((j * 8 + q) * 128 + m) * 16 bytes; the slot's fill f
+    // goes to stage kDBuf * slot + f % kDBuf
+    uint8_t* a0 = smA + (kDBuf * slot) * kDABytes + (pix >> 7) * (kDABytes / 2) + (pix & 127) * 16;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int n = item / items_per_img;
       const int r = item - n * items_per_img;
@@ -191,7 +204,9 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
 #pragma unroll
       for (int k = 0; k < 3; ++k, ++fills) {
         const int tap = slot + 3 * k;
-        mbar_wait(&empty[slot], (fills & 1) ^ 1);
+        const int st = kDBuf * slot + (int)(fills % kDBuf);
+        uint8_t* a = a0 + (fills % kDBuf) * kDABytes;
+        mbar_wait(&empty[st], ((fills / kDBuf) & 1) ^ 1);
         if (valid) {
           const TapPos tp = tap_pos(odx[k], ody[k], x, y, tap, p.H, p.W);
 #pragma unroll
@@ -212,24 +227,31 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full[slot]);
+        if (lane == 0) mbar_arrive(&full[st]);
       }
     }
   } else if (warp == kMmaWarp) {
     // ======================= MMA issuer (converged warp, one elected lane issues) =======================
-    if (elect_one_sync()) {
-      mbar_arrive_expect_tx(wbar, kDBBytes);
-      for (int c = 0; c < 9; ++c)
-        bulk_load(smB + c * (kDBBytes / 9), reinterpret_cast<const uint8_t*>(p.wpacked) + c * (kDBBytes / 9),
-                  kDBBytes / 9, wbar);
-    }
-    __syncwarp();
-    mbar_wait(wbar, 0);
     constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
     constexpr uint32_t a_hi = desc_hi(128u), b_hi = desc_hi(128u);
-    const uint32_t smA_u = smem_u32(smA);
-    const uint32_t b_lo = desc_lo(smem_u32(smB), 1024u);
-    uint32_t phbits = 0;  // bit s = parity the MMA warp waits for on full[s]
+    const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked);
+    const int my_items = p.num_items > (int)blockIdx.x ? (p.num_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const long total_taps = 9L * my_items;
+    // Filter tap g (counted over all of this CTA's items) sits in ring slot g % 3 and is requested two taps ahead:
+    // tap g + 2 goes into the slot tap g - 1 was read from, once the MMAs of tap g - 1 have completed (wempty).
+    auto load_tap = [&](long gg) {   // elected lane only
+      const int r = (int)(gg % kDWRing);
+      mbar_arrive_expect_tx(&wfull[r], kDWTapBytes);
+      bulk_load(smB + r * kDWTapBytes, wsrc + (size_t)(gg % 9) * kDWTapBytes, kDWTapBytes, &wfull[r]);
+    };
+    if (elect_one_sync()) {
+      if (total_taps > 0) load_tap(0);
+      if (total_taps > 1) load_tap(1);
+    }
+    __syncwarp();
+    uint32_t fcount[kDSlots] = {0, 0, 0};   // stages consumed per tap slot
+    long g = 0;
     int it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -237,12 +259,16 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)(buf * 128);
 #pragma unroll 1
-      for (int tap = 0; tap < 9; ++tap) {
-        const int s = tap % 3;
-        mbar_wait(&full[s], (phbits >> s) & 1u);
+      for (int tap = 0; tap < 9; ++tap, ++g) {
+        const int slot = tap % 3;
+        const uint32_t f = fcount[slot]++;
+        const int st = kDBuf * slot + (int)(f % kDBuf);
+        const int r = (int)(g % kDWRing);
+        mbar_wait(&full[st], (f / kDBuf) & 1u);
+        mbar_wait(&wfull[r], (uint32_t)((g / kDWRing) & 1));
         tc_fence_after();
-        const uint32_t a_lo = desc_lo(smA_u + s * kDABytes, 2048u);
-        const uint32_t bt_lo = b_lo + (uint32_t)(tap * 8 * 8 * 8);  // tap stride = 8 slabs x 8 groups x 128 B
+        const uint32_t a_lo = desc_lo(smA_u + st * kDABytes, 2048u);
+        const uint32_t bt_lo = desc_lo(smB_u + r * kDWTapBytes, 1024u);
         if (elect_one_sync()) {
           const uint32_t acc0 = tap != 0 ? 1u : 0u;
           // M-tile 0 (item rows 0-3), then M-tile 1 (rows 4-7, 16 KB further = 1024 x 16 B): 4 K-steps of 16 channels
@@ -254,11 +280,17 @@ __global__ void __launch_bounds__(kDThreads, 1) deform_umma_kernel(const DeformP
           umma_bf16_off<1280u, 128u>(d + 64, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
           umma_bf16_off<1536u, 256u>(d + 64, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
           umma_bf16_off<1792u, 384u>(d + 64, a_lo, a_hi, bt_lo, b_hi, idesc, 1u);
-          umma_commit(&empty[s]);
+          umma_commit(&empty[st]);
+          umma_commit(&wempty[r]);
           if (tap == 8) umma_commit(&tfull[buf]);
         }
         __syncwarp();
-        phbits ^= 1u << s;
+        if (g + 2 < total_taps) {
+          // slot of tap g + 2 = slot of tap g - 1 (its (g - 1) / 3-th use): wait for those MMAs, then refill
+          if (g >= 1) mbar_wait(&wempty[(g + 2) % kDWRing], (uint32_t)(((g - 1) / kDWRing) & 1));
+          if (elect_one_sync()) load_tap(g + 2);
+          __syncwarp();
+        }
       }
     }
   } else {
