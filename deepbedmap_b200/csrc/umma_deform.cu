@@ -80,15 +80,24 @@ __device__ __forceinline__ TapPos tap_pos(float dx, float dy, int x, int y, int 
   return t;
 }
 
-__device__ __forceinline__ void fma8(float (&acc)[8], const uint4& v, float w) {
-  acc[0] = fmaf(w, __uint_as_float(v.x << 16), acc[0]);
-  acc[1] = fmaf(w, __uint_as_float(v.x & 0xffff0000u), acc[1]);
-  acc[2] = fmaf(w, __uint_as_float(v.y << 16), acc[2]);
-  acc[3] = fmaf(w, __uint_as_float(v.y & 0xffff0000u), acc[3]);
-  acc[4] = fmaf(w, __uint_as_float(v.z << 16), acc[4]);
-  acc[5] = fmaf(w, __uint_as_float(v.z & 0xffff0000u), acc[5]);
-  acc[6] = fmaf(w, __uint_as_float(v.w << 16), acc[6]);
-  acc[7] = fmaf(w, __uint_as_float(v.w & 0xffff0000u), acc[7]);
+// acc[0..7] += w * (the eight bf16 channels of v), as four packed fp32 FMAs (FFMA2: two IEEE fma per instruction --
+// the same bits as eight scalar FFMAs, half the issue slots of the kernel's busiest loop)
+__device__ __forceinline__ unsigned long long pack_f32x2(uint32_t lo, uint32_t hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void fma8(unsigned long long (&acc)[4], const uint4& v, float w) {
+  const unsigned long long w2 = pack_f32x2(__float_as_uint(w), __float_as_uint(w));
+  acc[0] = ffma2(pack_f32x2(v.x << 16, v.x & 0xffff0000u), w2, acc[0]);
+  acc[1] = ffma2(pack_f32x2(v.y << 16, v.y & 0xffff0000u), w2, acc[1]);
+  acc[2] = ffma2(pack_f32x2(v.z << 16, v.z & 0xffff0000u), w2, acc[2]);
+  acc[3] = ffma2(pack_f32x2(v.w << 16, v.w & 0xffff0000u), w2, acc[3]);
 }
 
 struct Corners {
@@ -103,13 +112,17 @@ __device__ __forceinline__ Corners load_corners(const __nv_bfloat16* __restrict_
   c.c11 = __ldg(p + t.o11);
   return c;
 }
-__device__ __forceinline__ void blend8(const Corners& c, const TapPos& t, float (&acc)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+__device__ __forceinline__ void blend8(const Corners& c, const TapPos& t, float (&out)[8]) {
+  unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
   fma8(acc, c.c00, t.w00);
   fma8(acc, c.c01, t.w01);
   fma8(acc, c.c10, t.w10);
   fma8(acc, c.c11, t.w11);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    out[2 * i] = __uint_as_float((uint32_t)(acc[i] & 0xffffffffull));
+    out[2 * i + 1] = __uint_as_float((uint32_t)(acc[i] >> 32));
+  }
 }
 
 __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
